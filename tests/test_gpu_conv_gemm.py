@@ -1,0 +1,201 @@
+"""GPU parity tests of the tcgen05 implicit-GEMM kernel (through the C ABI) against a plain torch fp32
+reference of the same op (F.conv2d / matmul with TF32 disabled) on identical 16-bit-rounded inputs.
+
+Tolerance: the kernel accumulates in fp32 and rounds ONCE to the 16-bit output type, so
+|err| <= 2^-10 * |y| (fp16) or 2^-7 * |y| (bf16) plus fp32 summation-order noise.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(0)
+
+
+def _tol(dtype):
+    return 2.0 ** -9 if dtype == torch.float16 else 2.0 ** -6
+
+
+def _nhwc(x):  # NCHW fp32 -> NHWC
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def _check(got, ref, dtype, what=""):
+    got = got.float()
+    err = (got - ref).abs()
+    bound = _tol(dtype) * ref.abs() + _tol(dtype) * ref.abs().mean() + 1e-4
+    bad = (err > bound).sum().item()
+    assert bad == 0, f"{what}: {bad}/{err.numel()} mismatches, max err {err.max().item():.4g}, ref absmax {ref.abs().max().item():.4g}"
+
+
+def _run_conv(B, H, W, cins, Cout, ks, dtype, *, bias=False, relu1=False, affine=False, residual=False, relu2=False,
+              shuffle=False, dilation=1, bn=None, box=None):
+    from vsdeoldify_b200 import ops
+    _setup()
+    dev = "cuda"
+    Cin = sum(cins)
+    xs = [torch.randn(B, c, H, W, device=dev) for c in cins]
+    w = torch.randn(Cout, Cin, ks, ks, device=dev) / (Cin * ks * ks) ** 0.5
+    xs16 = [x.to(dtype) for x in xs]
+    w16 = w.to(dtype)
+    xcat = torch.cat([x.float() for x in xs16], 1)
+    ref = F.conv2d(xcat, w16.float(), padding=dilation * (ks - 1) // 2, dilation=dilation)
+    bvec = torch.randn(Cout, device=dev) if bias else None
+    svec = (torch.rand(Cout, device=dev) + 0.5) if affine else None
+    tvec = torch.randn(Cout, device=dev) if affine else None
+    if bias:
+        ref = ref + bvec[None, :, None, None]
+    if relu1:
+        ref = ref.relu()
+    if affine:
+        ref = ref * svec[None, :, None, None] + tvec[None, :, None, None]
+    res16 = None
+    if residual:
+        res = torch.randn(B, Cout, H, W, device=dev)
+        res16 = res.to(dtype)
+        ref = ref + res16.float()
+    if relu2:
+        ref = ref.relu()
+    if shuffle:
+        ref = F.pixel_shuffle(ref, 2)
+
+    # device-side operands
+    srcs = []
+    for x16, c in zip(xs16, cins):
+        cp = ops.pad_to(c, 8)
+        t = torch.zeros(B, H, W, cp, device=dev, dtype=dtype)
+        t[..., :c] = _nhwc(x16)
+        srcs.append(t)
+    wp, meta = ops.pack_conv_weight(w16.float().cpu(), cins, dtype=dtype, shuffle=shuffle)
+    wp = wp.to(dev)
+    n_total = meta["rows"]
+    pc = lambda v, fill: None if v is None else ops.pack_cols(v, n_total, fill, meta if shuffle else None).to(dev)
+    if shuffle:
+        cg = Cout // 4
+        out = torch.full((B, 2 * H, 2 * W, ops.pad_to(cg, 8)), float("nan"), device=dev, dtype=dtype)
+    else:
+        out = torch.full((B, H, W, ops.pad_to(Cout, 8)), float("nan"), device=dev, dtype=dtype)
+    rs = None
+    if residual:
+        rs = torch.zeros(B, H, W, ops.pad_to(Cout, 8), device=dev, dtype=dtype)
+        rs[..., :Cout] = _nhwc(res16)
+    op = ops.make_conv(srcs[0], wp, out, ops.taps_for(ks, dilation), src1=srcs[1] if len(srcs) > 1 else None,
+                       w_c1_off=meta["c1_off"], n_total=n_total, bn=bn, box=box,
+                       bias=pc(bvec, 0.0), scale=pc(svec, 1.0), shift=pc(tvec, 0.0),
+                       relu1=relu1, relu2=relu2, residual=rs, shuffle=shuffle, group_n=meta.get("group_n", 0))
+    op.launch()
+    torch.cuda.synchronize()
+    cvalid = Cout // 4 if shuffle else Cout
+    got = out[..., :cvalid].permute(0, 3, 1, 2)
+    _check(got, ref, dtype, f"conv {cins}->{Cout} k{ks} {H}x{W}x{B}")
+    pad = out[..., cvalid:]
+    if pad.numel():
+        assert torch.isfinite(pad.float()).all() and (pad == 0).all(), "pad channels must be written as zeros"
+
+
+def test_conv1x1_minimal():
+    _run_conv(1, 8, 16, [64], 64, 1, torch.float16)
+
+
+def test_conv1x1_k256():
+    _run_conv(2, 16, 16, [256], 128, 1, torch.float16)
+
+
+def test_conv3x3_basic():
+    _run_conv(2, 16, 16, [64], 64, 3, torch.float16)
+
+
+def test_conv3x3_bias_relu_bf16():
+    _run_conv(2, 24, 24, [128], 128, 3, torch.bfloat16, bias=True, relu1=True)
+
+
+def test_conv3x3_two_sources_affine():
+    _run_conv(2, 24, 24, [96, 40], 64, 3, torch.float16, relu1=True, affine=True)
+
+
+def test_conv3x3_residual_relu():
+    _run_conv(2, 16, 16, [64], 256, 3, torch.float16, bias=True, residual=True, relu2=True)
+
+
+def test_conv3x3_cout259_bn272():
+    _run_conv(1, 32, 32, [256, 3], 259, 3, torch.float16, bias=True, relu1=True)
+
+
+def test_conv1x1_shuffle():
+    _run_conv(2, 12, 12, [128], 256, 1, torch.float16, bias=True, relu1=True, shuffle=True)
+
+
+def test_conv1x1_shuffle_odd_group():
+    _run_conv(1, 16, 16, [64], 4 * 75, 1, torch.float16, bias=True, relu1=True, shuffle=True)
+
+
+def test_conv3x3_small_spatial_batch_box():
+    _run_conv(8, 12, 12, [128], 512, 3, torch.float16, relu1=True, affine=True)
+
+
+def test_conv3x3_dilated():
+    _run_conv(1, 32, 32, [64], 64, 3, torch.float16, dilation=2)
+
+
+def test_conv3x3_many_tiles_persistent():
+    # 4*96*96/128 = 288 m-tiles x 2 n-tiles > 148 SMs: exercises the persistent loop, both
+    # accumulator stages and the smem ring wrap-around.
+    _run_conv(4, 96, 96, [256], 512, 3, torch.float16, relu1=True, affine=True)
+
+
+def test_conv_stride2_phase_split():
+    from vsdeoldify_b200 import ops
+    _setup()
+    dev, dtype = "cuda", torch.float16
+    B, H, W, Cin, Cout = 2, 32, 32, 64, 128
+    x = torch.randn(B, Cin, H, W, device=dev).to(dtype)
+    w = (torch.randn(Cout, Cin, 3, 3, device=dev) / (Cin * 9) ** 0.5).to(dtype)
+    ref = F.conv2d(x.float(), w.float(), stride=2, padding=1)
+    xn = _nhwc(x)  # [B,H,W,C]
+    ph = torch.stack([xn[:, a::2, b::2] for a in range(2) for b in range(2)], 0).contiguous()  # [4,B,H/2,W/2,C]
+    wp, meta = ops.pack_conv_weight(w.float().cpu(), dtype=dtype)
+    out = torch.zeros(B, H // 2, W // 2, Cout, device=dev, dtype=dtype)
+    op = ops.make_conv(ph, wp.to(dev), out, ops.taps_stride2(3), n_total=meta["rows"])
+    op.launch()
+    torch.cuda.synchronize()
+    _check(out.permute(0, 3, 1, 2), ref, dtype, "stride-2 conv")
+
+
+def test_batched_gemm_fp32_out():
+    """S[b, j, i] = sum_c g[b, j, c] f[b, i, c]  (the attention logits: both operands per-image)."""
+    from vsdeoldify_b200 import ops
+    _setup()
+    dev, dtype = "cuda", torch.float16
+    B, N, d = 3, 320, 64
+    g = torch.randn(B, N, d, device=dev).to(dtype)
+    f = torch.randn(B, N, d, device=dev).to(dtype)
+    ref = torch.einsum("bjc,bic->bji", g.float(), f.float())
+    out = torch.zeros(B, 1, N, N, device=dev, dtype=torch.float32)
+    op = ops.make_conv(g.view(B, 1, N, d), f.view(B, N, 1, d), out, [(0, 0, 0, 0)], n_total=N, b_batched=True,
+                       out_space=(B, 1, N))
+    op.launch()
+    torch.cuda.synchronize()
+    err = (out.view(B, N, N) - ref).abs().max().item()
+    assert err < 1e-3, err
+
+
+def test_gemm_shared_a_batched_b():
+    """Ht[b, c, i] = sum_k Wv[c, k] x[b, i, k]  (value projection written channel-major)."""
+    from vsdeoldify_b200 import ops
+    _setup()
+    dev, dtype = "cuda", torch.float16
+    B, N, Cc = 2, 192, 128
+    wv = (torch.randn(Cc, Cc, device=dev) / Cc ** 0.5).to(dtype)
+    x = torch.randn(B, N, Cc, device=dev).to(dtype)
+    ref = torch.einsum("ck,bik->bci", wv.float(), x.float())
+    out = torch.zeros(B, 1, Cc, N, device=dev, dtype=dtype)
+    op = ops.make_conv(wv.view(1, 1, Cc, Cc), x.view(B, N, 1, Cc), out, [(0, 0, 0, 0)], n_total=N,
+                       a_batched=False, b_batched=True, out_space=(B, 1, Cc))
+    op.launch()
+    torch.cuda.synchronize()
+    _check(out.view(B, Cc, N), ref, dtype, "shared-A batched-B gemm")

@@ -1,0 +1,75 @@
+// Shared host/device helpers for libhavc_b200 (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+#include "../../include/havc_b200.h"
+
+namespace havc {
+
+void set_error(const char *fmt, ...);
+extern std::atomic<long long> g_launches;
+
+#define HAVC_CHECK_ARG(cond, ...)                                                                  \
+    do {                                                                                           \
+        if (!(cond)) {                                                                             \
+            havc::set_error(__VA_ARGS__);                                                          \
+            return HAVC_ERR_ARG;                                                                   \
+        }                                                                                          \
+    } while (0)
+
+#define HAVC_CHECK_CUDA(expr)                                                                      \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            havc::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,      \
+                            __LINE__);                                                             \
+            return HAVC_ERR_CUDA;                                                                  \
+        }                                                                                          \
+    } while (0)
+
+// Called after every kernel launch: counts it and surfaces launch-configuration errors.
+#define HAVC_LAUNCHED()                                                                            \
+    do {                                                                                           \
+        havc::g_launches.fetch_add(1, std::memory_order_relaxed);                                  \
+        HAVC_CHECK_CUDA(cudaGetLastError());                                                       \
+    } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+int num_sms();
+
+// ---- device-side numeric helpers -------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t pack2(float a, float b, int dtype) {
+    if (dtype == HAVC_F16) {
+        __half2 h = __floats2half2_rn(a, b);
+        return *reinterpret_cast<uint32_t *>(&h);
+    } else {
+        __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        return *reinterpret_cast<uint32_t *>(&h);
+    }
+}
+__device__ __forceinline__ float2 unpack2(uint32_t v, int dtype) {
+    if (dtype == HAVC_F16) {
+        return __half22float2(*reinterpret_cast<__half2 *>(&v));
+    } else {
+        return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162 *>(&v));
+    }
+}
+__device__ __forceinline__ float load16(const void *p, int64_t idx, int dtype) {
+    if (dtype == HAVC_F16) return __half2float(reinterpret_cast<const __half *>(p)[idx]);
+    return __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(p)[idx]);
+}
+__device__ __forceinline__ void store16(void *p, int64_t idx, float v, int dtype) {
+    if (dtype == HAVC_F16)
+        reinterpret_cast<__half *>(p)[idx] = __float2half_rn(v);
+    else
+        reinterpret_cast<__nv_bfloat16 *>(p)[idx] = __float2bfloat16_rn(v);
+}
+#endif
+
+}  // namespace havc

@@ -1,0 +1,587 @@
+// conv_gemm.cu — the implicit-GEMM convolution / batched GEMM kernel of libhavc_b200 (sm_100a).
+//
+// One persistent, warp-specialised kernel covers every dense contraction on the HAVC hot path
+// (reference: torch Conv2d/Conv1d/bmm calls in vsdeoldify/deoldify/unet.py:24-285,
+// vsdeoldify/fastai/layers.py:81-96, torchvision resnet via fastai/vision/learner.py:54-63,
+// vsdeoldify/colorization/colorizers/{eccv16,siggraph17}.py):
+//
+//   * activations are NHWC 16-bit; a 128-pixel M tile is a (box_w x box_h x box_b) spatial box that
+//     TMA (cp.async.bulk.tensor.5d) fetches once per filter tap and 64-channel K chunk, shifted by the
+//     tap offset — out-of-image taps are zero-filled by the TMA unit, so padding costs nothing and no
+//     im2col buffer exists;
+//   * the K loop can walk two source tensors (torch.cat is never materialised);
+//   * weights [Cout][tap][Cin] arrive through a second tensor map; both operands land in shared memory
+//     in the 128-byte-swizzled K-major layout tcgen05.mma consumes directly;
+//   * one elected thread issues tcgen05.mma (M=128, N<=256, K=16, kind::f16, fp32 accumulate) into a
+//     double-buffered TMEM accumulator; tcgen05.commit releases smem stages / publishes accumulators;
+//   * four epilogue warps drain TMEM with tcgen05.ld and apply, in fp32,
+//         +bias -> ReLU -> *scale+shift (eval BatchNorm) -> +residual -> ReLU
+//     then store fp16/bf16/fp32, optionally in PixelShuffle(2) order or to a strided sub-pixel phase.
+//
+// Warp roles (256 threads, 1 CTA/SM): warp0 = TMA producer, warp1 = MMA issuer, warp2 = TMEM
+// allocator, warps4-7 = epilogue (TMEM lane quarter = warp % 4).
+#include "common.cuh"
+
+namespace havc {
+
+static constexpr int kTileM = 128;
+static constexpr int kChunkK = 64;  // 64 x 16-bit = 128 B = one swizzle row
+static constexpr int kABytes = kTileM * kChunkK * 2;
+static constexpr int kMaxStages = 8;
+static constexpr int kThreads = 256;
+static constexpr uint32_t kTmemCols = 512;
+
+struct ConvParams {
+    int out_B, out_H, out_W;
+    int bw, bh, bb;
+    int tiles_w, tiles_h, tiles_b, tiles_n, total_tiles;
+    int BN, n_wloads, w_box_rows;
+    int n_taps;
+    int8_t dh[HAVC_MAX_TAPS], dw[HAVC_MAX_TAPS], tp[HAVC_MAX_TAPS], twi[HAVC_MAX_TAPS];
+    int chunks0, chunks1, w_c1_off;
+    int a_batched, b_batched;
+    int acc_stages, acc_stride;
+    int num_stages;
+    uint32_t stage_bytes;
+    int n_part0, n_part1;
+    uint32_t idesc0, idesc1;
+    int N_total;
+    const float *bias, *scale, *shift;
+    int relu1, relu2;
+    const void *residual;
+    long long rsw, rsh, rsb;
+    void *out;
+    int out_dtype;
+    long long osw, osh, osb;
+    int up, oy, ox, shuffle, group_n, c_store;
+    int dtype;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must trap (launch failure) instead of hanging the GPU box.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (!mbar_try_wait(bar, parity)) {
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 4000000000ull) {  // 4 s
+            printf("havc conv_gemm: mbarrier timeout (block %d thread %d bar %u parity %u)\n",
+                   blockIdx.x, threadIdx.x, bar, parity);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0,
+                                            int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        :
+        : "r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0,
+                                            int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        :
+        : "r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *tm) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16/fp16 operands, fp32 accumulate, single-CTA group.
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                         uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :
+        : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+          "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte-swizzled shared-memory matrix descriptor (8-row groups 1024 B apart).
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+    const uint32_t lo = ((smem_addr >> 4) & 0x3FFFu) | (1u << 16);            // LBO = 1 (unused)
+    const uint32_t hi = (1024u >> 4) | (1u << 14) /* version 1 */ | (2u << 29) /* SWIZZLE_128B */;
+    return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The kernel
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                 const __grid_constant__ CUtensorMap tmW, const __grid_constant__ ConvParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + p.num_stages * p.stage_bytes;
+    // barrier layout: full[kMaxStages], empty[kMaxStages], tmem_full[2], tmem_empty[2], tmem_ptr
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 2 + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 4);
+    volatile uint32_t *tmem_slot_ptr =
+        reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA0);
+        tma_prefetch_desc(&tmA1);
+        tma_prefetch_desc(&tmW);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.num_stages; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(tfull_bar(s), 1);
+            mbar_init(tempty_bar(s), 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                     "r"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    const int ksteps_per_tap = p.chunks0 + p.chunks1;
+    const int ksteps = p.n_taps * ksteps_per_tap;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                int t = tile;
+                const int nt = t % p.tiles_n; t /= p.tiles_n;
+                const int wt = t % p.tiles_w; t /= p.tiles_w;
+                const int ht = t % p.tiles_h; t /= p.tiles_h;
+                const int bt = t;
+                const int n0 = nt * p.BN;
+                const int w0 = wt * p.bw, h0 = ht * p.bh, b0 = bt * p.bb;
+                for (int tap = 0; tap < p.n_taps; ++tap) {
+                    const int cw = w0 + p.dw[tap], ch = h0 + p.dh[tap], cp = p.tp[tap], wi = p.twi[tap];
+                    for (int kc = 0; kc < ksteps_per_tap; ++kc) {
+                        mbar_wait(empty_bar(stage), phase ^ 1u);
+                        const uint32_t sa = smem_base + stage * p.stage_bytes;
+                        const uint32_t sb = sa + kABytes;
+                        mbar_arrive_expect_tx(full_bar(stage), p.stage_bytes);
+                        int wc;
+                        if (kc < p.chunks0) {
+                            tma_load_5d(sa, &tmA0, full_bar(stage), kc * kChunkK, cw, ch,
+                                        p.a_batched ? b0 : 0, cp);
+                            wc = kc * kChunkK;
+                        } else {
+                            tma_load_5d(sa, &tmA1, full_bar(stage), (kc - p.chunks0) * kChunkK, cw, ch,
+                                        p.a_batched ? b0 : 0, cp);
+                            wc = p.w_c1_off + (kc - p.chunks0) * kChunkK;
+                        }
+                        for (int l = 0; l < p.n_wloads; ++l)
+                            tma_load_4d(sb + l * p.w_box_rows * 128, &tmW, full_bar(stage), wc, wi,
+                                        n0 + l * p.w_box_rows, p.b_batched ? b0 : 0);
+                        if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int as = 0;
+            uint32_t aphase = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                mbar_wait(tempty_bar(as), aphase ^ 1u);
+                tc_fence_after();
+                const uint32_t acc = tmem_base + as * p.acc_stride;
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * p.stage_bytes;
+                    const uint32_t sb = sa + kABytes;
+                    const uint64_t da = make_sw128_desc(sa);
+                    const uint64_t db0 = make_sw128_desc(sb);
+#pragma unroll
+                    for (int k = 0; k < kChunkK / 16; ++k) {
+                        const uint32_t accum = (ks > 0 || k > 0) ? 1u : 0u;
+                        umma_f16(acc, da + 2u * k, db0 + 2u * k, p.idesc0, accum);
+                        if (p.n_part1 > 0) {
+                            const uint64_t db1 = make_sw128_desc(sb + p.n_part0 * 128);
+                            umma_f16(acc + p.n_part0, da + 2u * k, db1 + 2u * k, p.idesc1, accum);
+                        }
+                    }
+                    umma_commit(empty_bar(stage));  // frees this smem stage when the MMAs retire
+                    if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit(tfull_bar(as));  // accumulator complete -> epilogue
+                if (++as == p.acc_stages) { as = 0; aphase ^= 1u; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const int rw = r % p.bw;
+        const int rh = (r / p.bw) % p.bh;
+        const int rb = r / (p.bw * p.bh);
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            int t = tile;
+            const int nt = t % p.tiles_n; t /= p.tiles_n;
+            const int wt = t % p.tiles_w; t /= p.tiles_w;
+            const int ht = t % p.tiles_h; t /= p.tiles_h;
+            const int bt = t;
+            const int n0 = nt * p.BN;
+            const int ow = wt * p.bw + rw, oh = ht * p.bh + rh, ob = bt * p.bb + rb;
+            const bool valid = (ow < p.out_W) && (oh < p.out_H) && (ob < p.out_B);
+            const uint8_t *res_row = nullptr;
+            if (p.residual != nullptr)
+                res_row = reinterpret_cast<const uint8_t *>(p.residual) +
+                          2ll * (ob * p.rsb + oh * p.rsh + ow * p.rsw);
+
+            mbar_wait(tfull_bar(as), aphase);
+            tc_fence_after();
+            const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * p.acc_stride;
+            for (int c0 = 0; c0 < p.BN; c0 += 16) {
+                uint32_t v[16];
+                __syncwarp();
+                tmem_ld16(tbase + c0, v);
+                tmem_ld_wait();
+                const int n = n0 + c0;
+                if (n >= p.N_total || !valid) continue;
+                float y[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) y[j] = __uint_as_float(v[j]);
+                if (p.bias != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) y[j] += __ldg(p.bias + n + j);
+                }
+                if (p.relu1) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) y[j] = fmaxf(y[j], 0.f);
+                }
+                if (p.scale != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        y[j] = fmaf(y[j], __ldg(p.scale + n + j), __ldg(p.shift + n + j));
+                }
+                // destination channel / pixel
+                int chan = n, py = oh * p.up + p.oy, px = ow * p.up + p.ox;
+                if (p.shuffle) {
+                    const int g = n / p.group_n;
+                    chan = n - g * p.group_n;
+                    py = oh * 2 + (g >> 1);
+                    px = ow * 2 + (g & 1);
+                }
+                if (chan >= p.c_store) continue;
+                const bool hi_ok = (chan + 8) < p.c_store;  // second 8-channel group in range
+                if (res_row != nullptr) {
+                    const uint4 r0 = __ldg(reinterpret_cast<const uint4 *>(res_row + 2 * n));
+                    const uint32_t rr0[4] = {r0.x, r0.y, r0.z, r0.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 f = unpack2(rr0[j], p.dtype);
+                        y[2 * j] += f.x;
+                        y[2 * j + 1] += f.y;
+                    }
+                    if (hi_ok) {
+                        const uint4 r1 = __ldg(reinterpret_cast<const uint4 *>(res_row + 2 * n + 16));
+                        const uint32_t rr1[4] = {r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float2 f = unpack2(rr1[j], p.dtype);
+                            y[8 + 2 * j] += f.x;
+                            y[8 + 2 * j + 1] += f.y;
+                        }
+                    }
+                }
+                if (p.relu2) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) y[j] = fmaxf(y[j], 0.f);
+                }
+                const long long opix = ob * p.osb + py * p.osh + px * p.osw + chan;
+                if (p.out_dtype == HAVC_F32) {
+                    float4 *dst = reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out) + opix);
+                    dst[0] = make_float4(y[0], y[1], y[2], y[3]);
+                    dst[1] = make_float4(y[4], y[5], y[6], y[7]);
+                    if (hi_ok) {
+                        dst[2] = make_float4(y[8], y[9], y[10], y[11]);
+                        dst[3] = make_float4(y[12], y[13], y[14], y[15]);
+                    }
+                } else {
+                    uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<uint16_t *>(p.out) + opix);
+                    const int od = p.out_dtype;
+                    dst[0] = make_uint4(pack2(y[0], y[1], od), pack2(y[2], y[3], od),
+                                        pack2(y[4], y[5], od), pack2(y[6], y[7], od));
+                    if (hi_ok)
+                        dst[1] = make_uint4(pack2(y[8], y[9], od), pack2(y[10], y[11], od),
+                                            pack2(y[12], y[13], od), pack2(y[14], y[15], od));
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(tempty_bar(as));
+            if (++as == p.acc_stages) { as = 0; aphase ^= 1u; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                     "r"(kTmemCols)
+                     : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host side: tensor maps + launch
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void *sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || sym == nullptr) return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(sym);
+    return fn;
+}
+
+static int encode_map(CUtensorMap *tm, int dtype, int rank, const void *ptr, const uint64_t *dims,
+                      const uint64_t *strides_elems, const uint32_t *box) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled driver entry point unavailable");
+        return HAVC_ERR_NO_DEVICE;
+    }
+    cuuint64_t gdim[5], gstr[4];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bx[i] = box[i];
+        es[i] = 1;
+        if (i > 0) gstr[i - 1] = strides_elems[i] * 2ull;
+    }
+    CUresult r = fn(tm, dtype == HAVC_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                    rank, const_cast<void *>(ptr), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu %llu %llu %llu %llu)",
+                  (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+                  (unsigned long long)dims[2], (unsigned long long)(rank > 3 ? dims[3] : 0),
+                  (unsigned long long)(rank > 4 ? dims[4] : 0));
+        return HAVC_ERR_CUDA;
+    }
+    return HAVC_OK;
+}
+
+static int encode_act(CUtensorMap *tm, const havc_act_view &a, int dtype, int bw, int bh, int bb) {
+    const int P = a.P > 0 ? a.P : 1;
+    uint64_t dims[5] = {(uint64_t)a.C, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.B, (uint64_t)P};
+    // size-1 dimensions still need a legal (non-zero, 16 B multiple) stride
+    uint64_t sw = a.stride_w, sh = a.stride_h, sb = a.stride_b, sp = a.stride_p;
+    if (sh == 0) sh = sw * a.W;
+    if (sb == 0) sb = sh * a.H;
+    if (sp == 0) sp = sb * a.B;
+    uint64_t strides[5] = {1, sw, sh, sb, sp};
+    uint32_t box[5] = {(uint32_t)kChunkK, (uint32_t)bw, (uint32_t)bh, (uint32_t)bb, 1u};
+    return encode_map(tm, dtype, 5, a.ptr, dims, strides, box);
+}
+
+static bool act_ok(const havc_act_view &a) {
+    return a.ptr != nullptr && a.C > 0 && a.C % 8 == 0 && a.W > 0 && a.H > 0 && a.B > 0 &&
+           a.stride_w % 8 == 0 && a.stride_h % 8 == 0 && a.stride_b % 8 == 0 && a.stride_p % 8 == 0 &&
+           (reinterpret_cast<uintptr_t>(a.ptr) & 15) == 0;
+}
+
+}  // namespace havc
+
+using namespace havc;
+
+extern "C" int havc_conv_gemm(const havc_conv_desc *d, void *stream) {
+    HAVC_CHECK_ARG(d != nullptr, "havc_conv_gemm: null descriptor");
+    HAVC_CHECK_ARG(d->dtype == HAVC_F16 || d->dtype == HAVC_BF16, "havc_conv_gemm: dtype must be f16/bf16");
+    HAVC_CHECK_ARG(act_ok(d->src0), "havc_conv_gemm: src0 view invalid (C/strides must be multiples of 8, ptr 16 B aligned)");
+    const bool two = d->src1.ptr != nullptr;
+    if (two) HAVC_CHECK_ARG(act_ok(d->src1), "havc_conv_gemm: src1 view invalid");
+    HAVC_CHECK_ARG(d->box_w > 0 && d->box_h > 0 && d->box_b > 0 && d->box_w * d->box_h * d->box_b == kTileM &&
+                       d->box_w <= 256 && d->box_h <= 256 && d->box_b <= 256,
+                   "havc_conv_gemm: box %dx%dx%d must multiply to 128", d->box_w, d->box_h, d->box_b);
+    HAVC_CHECK_ARG(d->BN >= 16 && d->BN % 16 == 0 && d->BN <= 272, "havc_conv_gemm: BN=%d unsupported", d->BN);
+    HAVC_CHECK_ARG(d->N_total > 0 && d->N_total % 16 == 0, "havc_conv_gemm: N_total=%d must be a multiple of 16", d->N_total);
+    HAVC_CHECK_ARG(d->n_taps >= 1 && d->n_taps <= HAVC_MAX_TAPS, "havc_conv_gemm: n_taps=%d", d->n_taps);
+    HAVC_CHECK_ARG(d->weight != nullptr && d->w_cin % 8 == 0 && d->w_rows > 0 && d->w_taps > 0 && d->w_batches > 0 &&
+                       (reinterpret_cast<uintptr_t>(d->weight) & 15) == 0,
+                   "havc_conv_gemm: weight tensor invalid");
+    HAVC_CHECK_ARG(d->out != nullptr && d->c_store > 0 && d->c_store % 8 == 0, "havc_conv_gemm: out/c_store invalid");
+    HAVC_CHECK_ARG(d->out_dtype == HAVC_F16 || d->out_dtype == HAVC_BF16 || d->out_dtype == HAVC_F32, "havc_conv_gemm: out_dtype");
+    HAVC_CHECK_ARG(d->out_stride_w % 8 == 0 && d->out_stride_h % 8 == 0 && d->out_stride_b % 8 == 0 &&
+                       (reinterpret_cast<uintptr_t>(d->out) & 15) == 0,
+                   "havc_conv_gemm: output strides must be multiples of 8 elements");
+    HAVC_CHECK_ARG(d->up >= 1, "havc_conv_gemm: up must be >= 1");
+    if (d->shuffle) HAVC_CHECK_ARG(d->group_n > 0 && d->group_n % 16 == 0 && d->N_total == 4 * d->group_n,
+                                   "havc_conv_gemm: shuffle needs N_total == 4*group_n, group_n %% 16 == 0");
+    if (d->residual) HAVC_CHECK_ARG(d->res_stride_w % 8 == 0 && d->res_stride_h % 8 == 0 && d->res_stride_b % 8 == 0 &&
+                                        (reinterpret_cast<uintptr_t>(d->residual) & 15) == 0 && !d->shuffle,
+                                    "havc_conv_gemm: residual strides invalid");
+    HAVC_CHECK_ARG((d->scale == nullptr) == (d->shift == nullptr), "havc_conv_gemm: scale and shift go together");
+
+    ConvParams p;
+    memset(&p, 0, sizeof(p));
+    p.out_B = d->out_B; p.out_H = d->out_H; p.out_W = d->out_W;
+    p.bw = d->box_w; p.bh = d->box_h; p.bb = d->box_b;
+    p.tiles_w = ceil_div(d->out_W, d->box_w);
+    p.tiles_h = ceil_div(d->out_H, d->box_h);
+    p.tiles_b = ceil_div(d->out_B, d->box_b);
+    p.BN = d->BN;
+    p.tiles_n = ceil_div(d->N_total, d->BN);
+    p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_b * p.tiles_n;
+    p.N_total = d->N_total;
+    p.n_wloads = d->BN > 256 ? 2 : 1;
+    p.w_box_rows = d->BN / p.n_wloads;
+    HAVC_CHECK_ARG(p.w_box_rows % 8 == 0, "havc_conv_gemm: weight box rows %d not a multiple of 8", p.w_box_rows);
+    p.n_taps = d->n_taps;
+    for (int i = 0; i < d->n_taps; ++i) {
+        p.dh[i] = d->tap_dh[i]; p.dw[i] = d->tap_dw[i]; p.tp[i] = d->tap_p[i]; p.twi[i] = d->tap_wi[i];
+        HAVC_CHECK_ARG(d->tap_wi[i] >= 0 && d->tap_wi[i] < d->w_taps, "havc_conv_gemm: tap_wi out of range");
+    }
+    p.chunks0 = ceil_div(d->src0.C, kChunkK);
+    p.chunks1 = two ? ceil_div(d->src1.C, kChunkK) : 0;
+    p.w_c1_off = d->w_c1_off;
+    p.a_batched = d->a_batched; p.b_batched = d->b_batched;
+    p.acc_stages = (2 * d->BN <= (int)kTmemCols) ? 2 : 1;
+    p.acc_stride = d->BN;
+    p.stage_bytes = kABytes + d->BN * 128;
+    int stages = (227 * 1024 - 1024 - 256) / (int)p.stage_bytes;
+    if (stages > kMaxStages) stages = kMaxStages;
+    HAVC_CHECK_ARG(stages >= 2, "havc_conv_gemm: tile too large for shared memory");
+    p.num_stages = stages;
+    p.n_part0 = d->BN > 256 ? 256 : d->BN;
+    p.n_part1 = d->BN - p.n_part0;
+    const uint32_t fmt = d->dtype == HAVC_F16 ? 0u : 1u;
+    auto idesc = [&](int n) -> uint32_t {
+        return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    };
+    p.idesc0 = idesc(p.n_part0);
+    p.idesc1 = p.n_part1 > 0 ? idesc(p.n_part1) : 0u;
+    p.bias = d->bias; p.scale = d->scale; p.shift = d->shift;
+    p.relu1 = d->relu1; p.relu2 = d->relu2;
+    p.residual = d->residual; p.rsw = d->res_stride_w; p.rsh = d->res_stride_h; p.rsb = d->res_stride_b;
+    p.out = d->out; p.out_dtype = d->out_dtype;
+    p.osw = d->out_stride_w; p.osh = d->out_stride_h; p.osb = d->out_stride_b;
+    p.up = d->up; p.oy = d->oy; p.ox = d->ox; p.shuffle = d->shuffle; p.group_n = d->group_n > 0 ? d->group_n : 16;
+    p.c_store = d->c_store; p.dtype = d->dtype;
+
+    CUtensorMap tmA0, tmA1, tmW;
+    int rc = encode_act(&tmA0, d->src0, d->dtype, d->box_w, d->box_h, d->a_batched ? d->box_b : 1);
+    if (rc) return rc;
+    if (!d->a_batched) HAVC_CHECK_ARG(d->box_b == 1, "havc_conv_gemm: a_batched=0 needs box_b=1");
+    if (two) {
+        rc = encode_act(&tmA1, d->src1, d->dtype, d->box_w, d->box_h, d->a_batched ? d->box_b : 1);
+        if (rc) return rc;
+    } else {
+        tmA1 = tmA0;
+    }
+    {
+        uint64_t dims[4] = {(uint64_t)d->w_cin, (uint64_t)d->w_taps, (uint64_t)d->w_rows, (uint64_t)d->w_batches};
+        uint64_t strides[4] = {1, (uint64_t)d->w_cin, (uint64_t)d->w_cin * d->w_taps,
+                               (uint64_t)d->w_cin * d->w_taps * d->w_rows};
+        uint32_t box[4] = {(uint32_t)kChunkK, 1u, (uint32_t)p.w_box_rows, 1u};
+        rc = encode_map(&tmW, d->dtype, 4, d->weight, dims, strides, box);
+        if (rc) return rc;
+    }
+    if (d->b_batched) HAVC_CHECK_ARG(d->box_b == 1, "havc_conv_gemm: b_batched=1 needs box_b=1");
+
+    const size_t smem = (size_t)p.num_stages * p.stage_bytes + 1024 + 256;
+    static bool attr_set = false;
+    if (!attr_set) {
+        HAVC_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+    conv_gemm_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA0, tmA1, tmW, p);
+    HAVC_LAUNCHED();
+    return HAVC_OK;
+}

@@ -1,0 +1,229 @@
+"""Host-side launch helpers over the C ABI: build `havc_conv_desc` records from torch tensor handles.
+
+torch is used here only for device memory (tensor handles) and dtype bookkeeping; all arithmetic is
+done by libhavc_b200.so.  Layout conventions:
+
+  * activations: NHWC `[B, H, W, C]` (or phase-split `[P, B, H, W, C]`), C and strides multiples of 8;
+  * packed conv weights: `[rows, taps, cin]` with `rows` = GEMM N (padded to 16), `cin` = concatenated
+    K sources each padded to 8; pad rows / channels are zero.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import HAVC_BF16, HAVC_F16, HAVC_F32, ActView, ConvDesc
+
+
+def pad_to(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+def havc_dtype(t: torch.dtype) -> int:
+    if t == torch.float16:
+        return HAVC_F16
+    if t == torch.bfloat16:
+        return HAVC_BF16
+    if t == torch.float32:
+        return HAVC_F32
+    raise ValueError(f"unsupported dtype {t}")
+
+
+def act_view(t: torch.Tensor) -> ActView:
+    """View of an NHWC tensor [B,H,W,C] or [P,B,H,W,C] whose last dim is contiguous."""
+    assert t.stride(-1) == 1, "channel dim must be contiguous"
+    v = ActView()
+    v.ptr = t.data_ptr()
+    if t.dim() == 5:
+        P, B, H, W, Cc = t.shape
+        sp, sb, sh, sw, _ = t.stride()
+    else:
+        assert t.dim() == 4
+        B, H, W, Cc = t.shape
+        sb, sh, sw, _ = t.stride()
+        P, sp = 1, 0
+    v.C, v.W, v.H, v.B, v.P = Cc, W, H, B, P
+    v.stride_w, v.stride_h, v.stride_b, v.stride_p = sw, sh, sb, sp
+    return v
+
+
+def choose_box(W: int, H: int, B: int) -> Tuple[int, int, int]:
+    """Pick the (box_w, box_h, box_b) with product 128 that wastes the fewest padded pixels."""
+    best = None
+    for lw in range(8):
+        for lh in range(8 - lw):
+            bw, bh = 1 << lw, 1 << lh
+            bb = 128 // (bw * bh)
+            tiles = -(-W // bw) * -(-H // bh) * -(-B // bb)
+            key = (tiles, bb, -bw)  # fewest tiles, then least batch folding, then widest rows
+            if best is None or key < best[0]:
+                best = (key, (bw, bh, bb))
+    return best[1]
+
+
+def taps_for(ks: int, dilation: int = 1) -> List[Tuple[int, int, int, int]]:
+    """(dh, dw, phase, weight_tap_index) for a stride-1 'same' convolution."""
+    r = (ks - 1) // 2
+    return [((i - r) * dilation, (j - r) * dilation, 0, i * ks + j) for i in range(ks) for j in range(ks)]
+
+
+def taps_stride2(ks: int) -> List[Tuple[int, int, int, int]]:
+    """Taps of a stride-2 'same' (pad=(ks-1)//2) conv over a phase-split input [4,B,H/2,W/2,C].
+
+    Input pixel (2i+kh-r, 2j+kw-r) lives in phase ((kh-r)&1, (kw-r)&1) at offset floor((kh-r)/2)."""
+    r = (ks - 1) // 2
+    out = []
+    for i in range(ks):
+        for j in range(ks):
+            a, b = i - r, j - r
+            out.append((a >> 1, b >> 1, (a & 1) * 2 + (b & 1), i * ks + j))
+    return out
+
+
+def pack_conv_weight(w: torch.Tensor, cin_splits: Optional[Sequence[int]] = None, dtype=torch.float16,
+                     shuffle: bool = False, row_pad: int = 16) -> Tuple[torch.Tensor, dict]:
+    """[Cout, Cin, kh, kw] (or [Cout, Cin]) fp32 -> packed [rows, taps, cin_storage] 16-bit (CPU tensor).
+
+    cin_splits: channel counts of the K sources (torch.cat order); each is padded to 8.
+    shuffle: reorder rows for the PixelShuffle(2) store: row g*group_n + c <- out channel c*4 + g."""
+    if w.dim() == 2:
+        w = w[:, :, None, None]
+    if w.dim() == 3:  # conv1d, kernel size 1
+        w = w[:, :, :, None]
+    Cout, Cin, kh, kw = w.shape
+    cin_splits = list(cin_splits) if cin_splits else [Cin]
+    assert sum(cin_splits) == Cin
+    parts, off, c1_off = [], 0, 0
+    for i, c in enumerate(cin_splits):
+        blk = w[:, off:off + c]
+        cp = pad_to(c, 8)
+        if cp != c:
+            blk = torch.cat([blk, blk.new_zeros(Cout, cp - c, kh, kw)], 1)
+        parts.append(blk)
+        off += c
+        if i == 0:
+            c1_off = cp
+    wcat = torch.cat(parts, 1)  # [Cout, cin_storage, kh, kw]
+    cin_storage = wcat.shape[1]
+    wk = wcat.permute(0, 2, 3, 1).reshape(Cout, kh * kw, cin_storage)
+    meta = {"c1_off": c1_off, "taps": kh * kw, "cin": cin_storage, "cout": Cout}
+    if shuffle:
+        assert Cout % 4 == 0
+        cg = Cout // 4
+        gn = pad_to(cg, row_pad)
+        rows = wk.new_zeros(4 * gn, kh * kw, cin_storage)
+        for g in range(4):
+            rows[g * gn:g * gn + cg] = wk[g::4]
+        meta.update(group_n=gn, cg=cg, rows=4 * gn)
+        wk = rows
+    else:
+        rp = pad_to(Cout, row_pad)
+        if rp != Cout:
+            wk = torch.cat([wk, wk.new_zeros(rp - Cout, kh * kw, cin_storage)], 0)
+        meta.update(rows=rp)
+    return wk.to(dtype).contiguous(), meta
+
+
+def pack_cols(v: Optional[torch.Tensor], n_alloc: int, fill: float, shuffle_meta: Optional[dict] = None) -> Optional[torch.Tensor]:
+    """Per-output-channel fp32 vector -> per-GEMM-column vector of length n_alloc (row order of the packed weight)."""
+    if v is None:
+        return None
+    v = v.detach().float().cpu()
+    out = torch.full((n_alloc,), fill, dtype=torch.float32)
+    if shuffle_meta and "group_n" in shuffle_meta:
+        gn, cg = shuffle_meta["group_n"], shuffle_meta["cg"]
+        for g in range(4):
+            out[g * gn:g * gn + cg] = v[g::4]
+    else:
+        out[:v.numel()] = v
+    return out
+
+
+def choose_bn(n_total: int, m_tiles: int, sms: int = 148) -> int:
+    """N tile: as wide as possible (fewest A re-reads) while still giving every SM a tile."""
+    if n_total <= 256 or n_total == 272:
+        return n_total
+    for bn in (256, 128, 64):
+        if n_total % bn == 0 and m_tiles * (n_total // bn) >= sms:
+            return bn
+    for bn in (64, 128, 256):  # cannot fill the machine anyway: maximise parallelism
+        if n_total % bn == 0:
+            return bn
+    return 128
+
+
+@dataclass
+class ConvOp:
+    """A fully specified havc_conv_gemm launch (descriptor + the tensors it points at)."""
+    desc: ConvDesc
+    keep: list = field(default_factory=list)
+    flops: float = 0.0   # algorithmic (unpadded) FLOPs, filled by the planner
+    name: str = ""
+
+    def launch(self, stream: Optional[int] = None):
+        rc = _lib.lib().havc_conv_gemm(C.byref(self.desc), C.c_void_p(stream or 0))
+        _lib.check(rc, f"havc_conv_gemm[{self.name}]")
+
+
+def make_conv(src0: torch.Tensor, weight: torch.Tensor, out: torch.Tensor, taps, *, src1: Optional[torch.Tensor] = None,
+              w_c1_off: int = 0, n_total: Optional[int] = None, bn: Optional[int] = None,
+              bias=None, scale=None, shift=None, relu1=False, relu2=False, residual=None,
+              out_space: Optional[Tuple[int, int, int]] = None, box=None, a_batched=True, b_batched=False,
+              up=1, oy=0, ox=0, shuffle=False, group_n=0, c_store: Optional[int] = None,
+              out_view: Optional[ActView] = None, name: str = "") -> ConvOp:
+    """src0/src1: NHWC (or [P,B,H,W,C]) 16-bit device tensors; weight: packed [rows,taps,cin] or
+    [batches,rows,taps,cin]; out: NHWC tensor written at pixel (h*up+oy, w*up+ox)."""
+    d = ConvDesc()
+    d.dtype = havc_dtype(src0.dtype)
+    d.src0 = act_view(src0)
+    if src1 is not None:
+        d.src1 = act_view(src1)
+    if weight.dim() == 3:
+        wb, (rows, wt, cin) = 1, weight.shape
+    else:
+        wb, rows, wt, cin = weight.shape
+    assert weight.is_contiguous()
+    d.weight = weight.data_ptr()
+    d.w_rows, d.w_taps, d.w_cin, d.w_batches = rows, wt, cin, wb
+    d.w_c1_off = w_c1_off
+    d.n_taps = len(taps)
+    for i, (dh, dw, p, wi) in enumerate(taps):
+        d.tap_dh[i], d.tap_dw[i], d.tap_p[i], d.tap_wi[i] = dh, dw, p, wi
+    if out_space is None:
+        B, H, W = src0.shape[-4], src0.shape[-3], src0.shape[-2]
+    else:
+        B, H, W = out_space
+    d.out_B, d.out_H, d.out_W = B, H, W
+    if box is None:
+        box = choose_box(W, H, B if (a_batched and not b_batched) else 1)
+        if not a_batched or b_batched:
+            box = choose_box(W, H, 1)
+    d.box_w, d.box_h, d.box_b = box
+    d.a_batched, d.b_batched = int(a_batched), int(b_batched)
+    d.N_total = n_total if n_total is not None else rows
+    m_tiles = -(-W // box[0]) * -(-H // box[1]) * -(-B // box[2])
+    d.BN = bn if bn is not None else choose_bn(d.N_total, m_tiles)
+    n_alloc = -(-d.N_total // d.BN) * d.BN
+    keep = [src0, src1, weight, out, residual]
+    for nm, v in (("bias", bias), ("scale", scale), ("shift", shift)):
+        if v is not None:
+            assert v.dtype == torch.float32 and v.is_cuda and v.numel() >= d.N_total, nm
+            setattr(d, nm, v.data_ptr())
+            keep.append(v)
+    d.relu1, d.relu2 = int(relu1), int(relu2)
+    if residual is not None:
+        assert residual.dtype == src0.dtype and residual.dim() == 4
+        d.residual = residual.data_ptr()
+        d.res_stride_b, d.res_stride_h, d.res_stride_w = residual.stride()[:3]
+    d.out = out.data_ptr()
+    d.out_dtype = havc_dtype(out.dtype)
+    assert out.dim() == 4 and out.stride(-1) == 1
+    d.out_stride_b, d.out_stride_h, d.out_stride_w = out.stride()[:3]
+    d.up, d.oy, d.ox = up, oy, ox
+    d.shuffle, d.group_n = int(shuffle), group_n
+    d.c_store = c_store if c_store is not None else out.shape[-1]
+    return ConvOp(d, keep, name=name)
