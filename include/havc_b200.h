@@ -87,6 +87,53 @@ void havc_launch_count_reset(void);
 
 int havc_conv_gemm(const havc_conv_desc *d, void *stream);
 
+/* ---- memory-bound network ops (NHWC 16-bit, C multiple of 8) -------------------------------- */
+
+/* im2col for tiny-Cin convolutions: out[b,oy,ox,(kh*ks+kw)*cin+c] = in[b,oy*stride-pad+kh,ox*stride-pad+kw,c],
+ * zero outside the image, K zero-padded to Kp.  Feeds havc_conv_gemm for the ResNet 7x7/s2 stem
+ * (torchvision conv1 behind vsdeoldify/fastai/vision/learner.py:54-63) and Zhang's model1.0
+ * (vsdeoldify/colorization/colorizers/eccv16.py:16, siggraph17.py:20).  in: [B,H,W,Cs], out: [B,OH,OW,Kp]. */
+int havc_im2col_small(const void *in, void *out, int B, int H, int W, int Cs, int cin, int ks, int stride,
+                      int pad, int Kp, int dtype, void *stream);
+/* nn.MaxPool2d(3, 2, 1) of the torchvision resnet stem. */
+int havc_maxpool3x3s2(const void *in, void *out, int B, int H, int W, int C, int dtype, void *stream);
+/* out[p=a*2+b][n][i][j][:] = in[n][2i+a][2j+b][:] — the input layout of a stride-2 havc_conv_gemm. */
+int havc_phase_split(const void *in, void *out, int B, int H, int W, int C, int n_phases, void *stream);
+/* y = x*scale[c]+shift[c] (+ReLU): eval BatchNorm on U-Net skips / encoder output
+ * (vsdeoldify/deoldify/unet.py:203, :244).  Pixel strides (elements) let it read/write a channel slice of a
+ * wider NHWC buffer, which is how torch.cat partners are written in place (MergeLayer, fastai/layers.py:149-152). */
+int havc_affine_act(const void *in, void *out, long long n_pixels, int C, int in_pix_stride, int out_pix_stride,
+                    const float *scale, const float *shift, int relu, int dtype, void *stream);
+/* ReplicationPad2d((1,0,1,0)) + AvgPool2d(2,1) of (Custom)PixelShuffle_ICNR
+ * (vsdeoldify/deoldify/unet.py:47-52, vsdeoldify/fastai/layers.py:214-220). */
+int havc_blur2x2(const void *in, void *out, int B, int H, int W, int C, int out_pix_stride, int dtype, void *stream);
+/* Row soft-max of fp32 attention logits -> 16-bit probabilities (F.softmax(.., dim=1) of
+ * vsdeoldify/fastai/layers.py:94, stored transposed so the reduction runs along contiguous rows). */
+int havc_softmax_rows(const float *in, void *out, long long rows, int cols, int out_dtype, void *stream);
+
+/* ---- frame pre / post pixel passes (planar u8 RGB frames [B][3][H][W]) ----------------------- */
+
+/* Table-driven separable resampling, horizontal pass: out[row][o] = sum_t weights[o][t]*in[row][start[o]+t].
+ * With Spline64 tables this is zimg's resize.Spline64 of vsdeoldify/__init__.py:2504 and :3547. */
+int havc_resample_h(const uint8_t *in, float *out, long long rows, int Win, int Wout, const int *start,
+                    const float *weights, int taps, void *stream);
+/* Vertical pass of the squeeze to S x S, fused with ColorizerFilter._transform (Pillow 'L' luma,
+ * vsdeoldify/deoldify/filters.py:92-93) and ImageNet normalisation (filters.py:50-53).
+ * in: float [B][3][Hin][S]; rgb_small: u8 [B][3][S][S]; x: 16-bit NHWC [B][S][S][8]. */
+int havc_pre_vertical(const float *in, uint8_t *rgb_small, void *x, int B, int Hin, int S, const int *start,
+                      const float *weights, int taps, int dtype, void *stream);
+/* Network head: 1x1 conv 259->3 + SigmoidRange(-3,3) (unet.py:276-281), de-normalise, clamp, *255, truncate
+ * to u8 (filters.py:64-67), and — if transplant — ColorizerFilter._post_process (filters.py:100-110) at S x S
+ * against rgb_small.  res: [B,S,S,Cs] 16-bit; w11: fp32 [3][Cs]; colored: u8 [B][3][S][S];
+ * net_out (optional): fp32 [B][3][S][S] network output for parity tests. */
+int havc_head(const void *res, int Cs, const float *w11, const float *b11, const uint8_t *rgb_small,
+              uint8_t *colored, float *net_out, int B, int S, int dtype, int transplant, void *stream);
+/* Vertical pass of the resize back to W x H fused with vs_recover_clip_luma / chroma_post_process
+ * (vsdeoldify/vsslib/vsfilters.py:863-899, imfilters.py:312-321): keep the luma of `orig`, the chroma of the
+ * upscaled colour image (OpenCV Q14 8-bit YUV).  in: float [B][3][S][W]; orig/out: u8 [B][3][H][W]. */
+int havc_post_vertical(const float *in, const uint8_t *orig, uint8_t *out, int B, int S, int H, int W,
+                       const int *start, const float *weights, int taps, int transplant, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

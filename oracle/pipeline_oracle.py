@@ -1,0 +1,43 @@
+"""TEST INFRASTRUCTURE (parity oracle) — CPU restatement of the whole per-frame DeOldify path.
+
+  havc_colorizer_frame: HAVC_colorizer(method=0) on one RGB24 frame (vsdeoldify/__init__.py:2290-2523):
+      Spline64 squeeze -> ModelImageRender/ColorizerFilter.filter (deoldify/filters.py:81-110) ->
+      _clip_chroma_resize (vsdeoldify/__init__.py:3545-3554).
+  colorizer_filter: MasterFilter([ColorizerFilter]).filter on a PIL-sized image (cfg1 path, Pillow BILINEAR).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import pixel_oracle as px
+from . import unet_oracle
+
+
+def model_process_square(sd, rgb_sq: np.ndarray) -> np.ndarray:
+    """BaseFilter._model_process (filters.py:48-68) on an already square S x S uint8 RGB image -> uint8 RGB."""
+    L = px.pil_luma(rgb_sq)
+    x = torch.from_numpy(px.normalize_gray(L))[None]
+    y = unet_oracle.unet_forward(sd, x)[0].numpy()
+    return px.denorm_quantize(y)
+
+
+def net_output_square(sd, rgb_sq: np.ndarray) -> np.ndarray:
+    L = px.pil_luma(rgb_sq)
+    x = torch.from_numpy(px.normalize_gray(L))[None]
+    return unet_oracle.unet_forward(sd, x)[0].numpy()
+
+
+def havc_colorizer_frame(sd, frame: np.ndarray, render_factor: int = 24, kernel: str = "spline64",
+                         return_stages: bool = False):
+    """frame: uint8 [H,W,3].  Returns uint8 [H,W,3] (and the intermediate stages on request)."""
+    H, W = frame.shape[:2]
+    S = min(render_factor * 16, W)
+    small = px.resize_plane_u8(frame, S, S, kernel)                   # clip.resize.Spline64(S, S)
+    model_img = model_process_square(sd, small)                       # _scale_to_square is the identity here
+    colored = px.chroma_post_process(model_img, small)                # _post_process at S x S
+    up = px.resize_plane_u8(colored, W, H, kernel)                    # clip_lowres.resize.Spline64(W, H)
+    out = px.chroma_post_process(up, frame)                           # vs_recover_clip_luma
+    if return_stages:
+        return out, dict(small=small, model_img=model_img, colored=colored, up=up)
+    return out

@@ -65,6 +65,21 @@ _SIGNATURES = {
     "havc_launch_count": (C.c_int64, []),
     "havc_launch_count_reset": (None, []),
     "havc_conv_gemm": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
+    "havc_im2col_small": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 10 + [C.c_void_p]),
+    "havc_maxpool3x3s2": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]),
+    "havc_phase_split": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]),
+    "havc_affine_act": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                  C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "havc_blur2x2": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p]),
+    "havc_softmax_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
+    "havc_resample_h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                  C.c_int, C.c_void_p]),
+    "havc_pre_vertical": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                    C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "havc_head": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                            C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "havc_post_vertical": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
 }
 
 _lib = None

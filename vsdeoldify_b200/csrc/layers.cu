@@ -1,0 +1,271 @@
+// layers.cu — the memory-bound network ops around the tcgen05 GEMM: small-Cin im2col (ResNet stem,
+// Zhang first conv), max-pool, stride-2 phase split, eval-BatchNorm(+ReLU), the PixelShuffle_ICNR blur,
+// the attention row soft-max.  All NHWC 16-bit, 8 channels (16 B) per thread access, grid-stride loops.
+#include "common.cuh"
+
+namespace havc {
+
+static inline int grid_for(long long n_threads, int block) {
+    long long g = (n_threads + block - 1) / block;
+    long long cap = (long long)num_sms() * 16;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+// ---------------------------------------------------------------------------------------------
+// im2col for convolutions with a tiny channel count (7x7 s2 stem on the 3-channel normalised image,
+// torchvision resnet conv1 via vsdeoldify/fastai/vision/learner.py:54-63; Zhang model1.0 on the
+// 1-channel L image, colorizers/eccv16.py:16).  out[b,oy,ox, (kh*ks+kw)*cin + c] = in[b, oy*s-pad+kh,
+// ox*s-pad+kw, c] (zero outside), K padded with zeros to Kp.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void im2col_small_kernel(const T *__restrict__ in, T *__restrict__ out, int B, int H, int W, int Cs,
+                                    int cin, int ks, int stride, int pad, int OH, int OW, int Kp) {
+    const long long total = (long long)B * OH * OW * (Kp / 8);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int kg = (int)(i % (Kp / 8));
+        long long pix = i / (Kp / 8);
+        const int ox = (int)(pix % OW);
+        const int oy = (int)((pix / OW) % OH);
+        const int b = (int)(pix / ((long long)OW * OH));
+        T vals[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = kg * 8 + j;
+            T v = T(0.f);
+            if (k < ks * ks * cin) {
+                const int c = k % cin, tap = k / cin;
+                const int iy = oy * stride - pad + tap / ks, ix = ox * stride - pad + tap % ks;
+                if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = in[(((long long)b * H + iy) * W + ix) * Cs + c];
+            }
+            vals[j] = v;
+        }
+        *reinterpret_cast<uint4 *>(out + pix * Kp + kg * 8) = *reinterpret_cast<uint4 *>(vals);
+    }
+}
+
+// 3x3 stride-2 pad-1 max-pool (torchvision resnet maxpool).
+template <typename T2>
+__global__ void maxpool_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, int B, int H, int W, int C8,
+                               int OH, int OW) {
+    const long long total = (long long)B * OH * OW * C8;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int cg = (int)(i % C8);
+        long long pix = i / C8;
+        const int ox = (int)(pix % OW);
+        const int oy = (int)((pix / OW) % OH);
+        const int b = (int)(pix / ((long long)OW * OH));
+        T2 m[4];
+        bool first = true;
+        for (int dy = -1; dy <= 1; ++dy) {
+            const int iy = oy * 2 + dy;
+            if (iy < 0 || iy >= H) continue;
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int ix = ox * 2 + dx;
+                if (ix < 0 || ix >= W) continue;
+                uint4 v = __ldg(in + (((long long)b * H + iy) * W + ix) * C8 + cg);
+                const T2 *pv = reinterpret_cast<const T2 *>(&v);
+                if (first) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) m[j] = pv[j];
+                    first = false;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) m[j] = __hmax2(m[j], pv[j]);
+                }
+            }
+        }
+        out[i] = *reinterpret_cast<uint4 *>(m);
+    }
+}
+
+// Phase split for stride-2 convolutions: out[p=(a*2+b)][n][i][j][c] = in[n][2i+a][2j+b][c] (zero past the edge).
+__global__ void phase_split_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, int B, int H, int W,
+                                   int C8, int OH, int OW, int P) {
+    const long long total = (long long)P * B * OH * OW * C8;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int cg = (int)(i % C8);
+        long long r = i / C8;
+        const int ox = (int)(r % OW); r /= OW;
+        const int oy = (int)(r % OH); r /= OH;
+        const int b = (int)(r % B);
+        const int p = (int)(r / B);
+        const int iy = oy * 2 + (p >> 1), ix = ox * 2 + (p & 1);
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (iy < H && ix < W) v = __ldg(in + (((long long)b * H + iy) * W + ix) * C8 + cg);
+        out[i] = v;
+    }
+}
+
+// y = x*scale[c] + shift[c], optional ReLU (eval BatchNorm on skips / encoder output:
+// unet.py:203 `self.bn(s)`, unet.py:244 layers[1..2]).
+__global__ void affine_act_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, long long n_pix, int C8,
+                                  int in_stride8, int out_stride8, const float *__restrict__ scale,
+                                  const float *__restrict__ shift, int relu, int dtype) {
+    const long long total = n_pix * C8;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int cg = (int)(i % C8);
+        const long long pix = i / C8;
+        uint4 v = __ldg(in + pix * in_stride8 + cg);
+        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float2 f = unpack2(w[j], dtype);
+            const int c = cg * 8 + 2 * j;
+            f.x = fmaf(f.x, __ldg(scale + c), __ldg(shift + c));
+            f.y = fmaf(f.y, __ldg(scale + c + 1), __ldg(shift + c + 1));
+            if (relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); }
+            w[j] = pack2(f.x, f.y, dtype);
+        }
+        out[pix * out_stride8 + cg] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+// ReplicationPad2d((1,0,1,0)) + AvgPool2d(2, stride=1): out[y][x] = mean(in[y-1..y][x-1..x]) with the
+// index clamped at 0 (CustomPixelShuffle_ICNR, unet.py:47-52; PixelShuffle_ICNR, fastai/layers.py:214-220).
+__global__ void blur2x2_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, int B, int H, int W, int C8,
+                               int out_stride8, int dtype) {
+    const long long total = (long long)B * H * W * C8;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int cg = (int)(i % C8);
+        long long pix = i / C8;
+        const int x = (int)(pix % W);
+        const int y = (int)((pix / W) % H);
+        const int b = (int)(pix / ((long long)W * H));
+        const int y0 = y > 0 ? y - 1 : 0, x0 = x > 0 ? x - 1 : 0;
+        const uint4 *base = in + (long long)b * H * W * C8 + cg;
+        const uint4 v00 = __ldg(base + ((long long)y0 * W + x0) * C8);
+        const uint4 v01 = __ldg(base + ((long long)y0 * W + x) * C8);
+        const uint4 v10 = __ldg(base + ((long long)y * W + x0) * C8);
+        const uint4 v11 = __ldg(base + ((long long)y * W + x) * C8);
+        const uint32_t a[4] = {v00.x, v00.y, v00.z, v00.w}, bq[4] = {v01.x, v01.y, v01.z, v01.w};
+        const uint32_t c[4] = {v10.x, v10.y, v10.z, v10.w}, d[4] = {v11.x, v11.y, v11.z, v11.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 fa = unpack2(a[j], dtype), fb = unpack2(bq[j], dtype), fc = unpack2(c[j], dtype),
+                         fd = unpack2(d[j], dtype);
+            o[j] = pack2(((fa.x + fb.x) + (fc.x + fd.x)) * 0.25f, ((fa.y + fb.y) + (fc.y + fd.y)) * 0.25f, dtype);
+        }
+        out[pix * out_stride8 + cg] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// Row soft-max of the attention logits: P[j, :] = softmax_i S[j, i] (SelfAttention, fastai/layers.py:94:
+// softmax over dim=1 of beta[b,i,j] == over the contiguous row of the transposed logits we store).
+// One warp per row; the row lives in registers across the three passes when cols <= 32*kMaxPerLane.
+__global__ void softmax_rows_kernel(const float *__restrict__ in, void *__restrict__ out, long long rows, int cols,
+                                    int out_dtype) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long row = warp0; row < rows; row += nwarps) {
+        const float *r = in + row * cols;
+        float m = -INFINITY;
+        for (int c = lane * 4; c < cols; c += 128) {
+            const float4 v = *reinterpret_cast<const float4 *>(r + c);
+            m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        float s = 0.f;
+        for (int c = lane * 4; c < cols; c += 128) {
+            const float4 v = *reinterpret_cast<const float4 *>(r + c);
+            s += __expf(v.x - m) + __expf(v.y - m) + __expf(v.z - m) + __expf(v.w - m);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float inv = 1.f / s;
+        for (int c = lane * 4; c < cols; c += 128) {
+            const float4 v = *reinterpret_cast<const float4 *>(r + c);
+            const float e0 = __expf(v.x - m) * inv, e1 = __expf(v.y - m) * inv, e2 = __expf(v.z - m) * inv,
+                        e3 = __expf(v.w - m) * inv;
+            uint2 pk = make_uint2(pack2(e0, e1, out_dtype), pack2(e2, e3, out_dtype));
+            *reinterpret_cast<uint2 *>(reinterpret_cast<uint16_t *>(out) + row * cols + c) = pk;
+        }
+    }
+}
+
+}  // namespace havc
+
+using namespace havc;
+
+static bool dt16(int d) { return d == HAVC_F16 || d == HAVC_BF16; }
+
+extern "C" int havc_im2col_small(const void *in, void *out, int B, int H, int W, int Cs, int cin, int ks, int stride,
+                                 int pad, int Kp, int dtype, void *stream) {
+    HAVC_CHECK_ARG(in && out && dt16(dtype) && Kp % 8 == 0 && Kp >= ks * ks * cin && cin <= Cs,
+                   "havc_im2col_small: bad arguments");
+    const int OH = (H + 2 * pad - ks) / stride + 1, OW = (W + 2 * pad - ks) / stride + 1;
+    const long long n = (long long)B * OH * OW * (Kp / 8);
+    if (dtype == HAVC_F16)
+        im2col_small_kernel<__half><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
+            (const __half *)in, (__half *)out, B, H, W, Cs, cin, ks, stride, pad, OH, OW, Kp);
+    else
+        im2col_small_kernel<__nv_bfloat16><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
+            (const __nv_bfloat16 *)in, (__nv_bfloat16 *)out, B, H, W, Cs, cin, ks, stride, pad, OH, OW, Kp);
+    HAVC_LAUNCHED();
+    return HAVC_OK;
+}
+
+extern "C" int havc_maxpool3x3s2(const void *in, void *out, int B, int H, int W, int C, int dtype, void *stream) {
+    HAVC_CHECK_ARG(in && out && dt16(dtype) && C % 8 == 0, "havc_maxpool3x3s2: bad arguments");
+    const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
+    const long long n = (long long)B * OH * OW * (C / 8);
+    if (dtype == HAVC_F16)
+        maxpool_kernel<__half2><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const uint4 *)in, (uint4 *)out, B, H,
+                                                                                    W, C / 8, OH, OW);
+    else
+        maxpool_kernel<__nv_bfloat162><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
+            (const uint4 *)in, (uint4 *)out, B, H, W, C / 8, OH, OW);
+    HAVC_LAUNCHED();
+    return HAVC_OK;
+}
+
+extern "C" int havc_phase_split(const void *in, void *out, int B, int H, int W, int C, int n_phases, void *stream) {
+    HAVC_CHECK_ARG(in && out && C % 8 == 0 && (n_phases == 1 || n_phases == 4), "havc_phase_split: bad arguments");
+    const int OH = (H + 1) / 2, OW = (W + 1) / 2;
+    const long long n = (long long)n_phases * B * OH * OW * (C / 8);
+    phase_split_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const uint4 *)in, (uint4 *)out, B, H, W,
+                                                                          C / 8, OH, OW, n_phases);
+    HAVC_LAUNCHED();
+    return HAVC_OK;
+}
+
+extern "C" int havc_affine_act(const void *in, void *out, long long n_pixels, int C, int in_pix_stride,
+                               int out_pix_stride, const float *scale, const float *shift, int relu, int dtype,
+                               void *stream) {
+    HAVC_CHECK_ARG(in && out && scale && shift && dt16(dtype) && C % 8 == 0 && in_pix_stride % 8 == 0 &&
+                       out_pix_stride % 8 == 0 && in_pix_stride >= C && out_pix_stride >= C,
+                   "havc_affine_act: bad arguments");
+    const long long n = n_pixels * (C / 8);
+    affine_act_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const uint4 *)in, (uint4 *)out, n_pixels, C / 8, in_pix_stride / 8, out_pix_stride / 8, scale, shift, relu, dtype);
+    HAVC_LAUNCHED();
+    return HAVC_OK;
+}
+
+extern "C" int havc_blur2x2(const void *in, void *out, int B, int H, int W, int C, int out_pix_stride, int dtype,
+                            void *stream) {
+    HAVC_CHECK_ARG(in && out && in != out && dt16(dtype) && C % 8 == 0 && out_pix_stride % 8 == 0 && out_pix_stride >= C,
+                   "havc_blur2x2: bad arguments");
+    const long long n = (long long)B * H * W * (C / 8);
+    blur2x2_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const uint4 *)in, (uint4 *)out, B, H, W, C / 8,
+                                                                      out_pix_stride / 8, dtype);
+    HAVC_LAUNCHED();
+    return HAVC_OK;
+}
+
+extern "C" int havc_softmax_rows(const float *in, void *out, long long rows, int cols, int out_dtype, void *stream) {
+    HAVC_CHECK_ARG(in && out && dt16(out_dtype) && cols % 4 == 0, "havc_softmax_rows: cols must be a multiple of 4");
+    const long long nthreads = rows * 32;
+    softmax_rows_kernel<<<grid_for(nthreads, 256), 256, 0, (cudaStream_t)stream>>>(in, out, rows, cols, out_dtype);
+    HAVC_LAUNCHED();
+    return HAVC_OK;
+}

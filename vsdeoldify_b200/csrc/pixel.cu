@@ -1,0 +1,234 @@
+// pixel.cu — frame pre/post pixel passes (HBM-bound, one thread per output element, coalesced rows).
+//
+// Pre  (reference: HAVC_colorizer Spline64 squeeze vsdeoldify/__init__.py:2504; ColorizerFilter._transform
+//       filters.py:92-93; normalize filters.py:50-53 + fastai/vision/data.py:56-79):
+//       planar RGB u8 W x H --separable resample--> RGB u8 S x S --L--> (L/255 - mean)/std  NHWC 16-bit.
+// Head (unet.py:276-281 final 1x1 conv + SigmoidRange; denorm/clamp/*255/trunc filters.py:64-67 +
+//       fastai/basic_train.py:358-362 + vision/data.py:300; _post_process filters.py:100-110 at S x S).
+// Post (_clip_chroma_resize vsdeoldify/__init__.py:3545-3554: Spline64 back to W x H, then
+//       chroma_post_process imfilters.py:312-321 with the original frame).
+//
+// Resampling is table driven: for output index o, out[o] = sum_t w[o][t] * in[start[o] + t]; the host
+// builds the tables (Spline64 / Spline36 / Pillow triangle), so every resampler shares these kernels.
+#include "common.cuh"
+
+namespace havc {
+
+static inline int grid1d(long long n, int block) {
+    long long g = (n + block - 1) / block;
+    long long cap = (long long)num_sms() * 32;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+__device__ __forceinline__ int sat8(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
+
+// OpenCV 8-bit COLOR_RGB2YUV / COLOR_YUV2RGB, Q14 fixed point (pinned against
+// cv2 4.13 by tests/test_pixel_oracle.py).
+__device__ __forceinline__ void rgb2yuv(int r, int g, int b, int &y, int &u, int &v) {
+    y = (4899 * r + 9617 * g + 1868 * b + 8192) >> 14;
+    u = sat8(((b - y) * 8061 + (128 << 14) + 8192) >> 14);
+    v = sat8(((r - y) * 14369 + (128 << 14) + 8192) >> 14);
+}
+__device__ __forceinline__ void yuv2rgb(int y, int u, int v, int &r, int &g, int &b) {
+    r = sat8(y + (((v - 128) * 18678 + 8192) >> 14));
+    g = sat8(y + (((u - 128) * -6472 + (v - 128) * -9519 + 8192) >> 14));
+    b = sat8(y + (((u - 128) * 33292 + 8192) >> 14));
+}
+// Keep the luma of `o` and the chroma of `c` (ColorizerFilter._post_process, filters.py:100-110).
+__device__ __forceinline__ void luma_transplant(int orr, int og, int ob, int cr, int cg, int cb, int &r, int &g,
+                                                int &b) {
+    int y, u, v, y2, u2, v2;
+    rgb2yuv(orr, og, ob, y, u, v);
+    rgb2yuv(cr, cg, cb, y2, u2, v2);
+    yuv2rgb(y, u2, v2, r, g, b);
+}
+
+// Horizontal pass: u8 rows -> float rows.
+__global__ void resample_h_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, long long rows, int Win,
+                                  int Wout, const int *__restrict__ start, const float *__restrict__ wts, int T) {
+    const long long total = rows * Wout;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int ox = (int)(i % Wout);
+        const long long row = i / Wout;
+        const uint8_t *src = in + row * Win + __ldg(start + ox);
+        const float *w = wts + (long long)ox * T;
+        float acc = 0.f;
+        for (int t = 0; t < T; ++t) acc = fmaf(__ldg(w + t), (float)src[t], acc);
+        out[i] = acc;
+    }
+}
+
+__device__ __forceinline__ int round_u8(float v) { return sat8(__float2int_rn(v)); }
+
+// Vertical pass of the pre-resize fused with gray conversion + ImageNet normalisation.
+// in: float [B][3][Hin][S]; out: rgb_small u8 [B][3][S][S]; x: 16-bit [B][S][S][8] (channels 3..7 = 0).
+__global__ void pre_vertical_kernel(const float *__restrict__ in, uint8_t *__restrict__ rgb_small, void *__restrict__ x,
+                                    int B, int Hin, int S, const int *__restrict__ start,
+                                    const float *__restrict__ wts, int T, int dtype) {
+    const long long total = (long long)B * S * S;
+    const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int ox = (int)(i % S);
+        const int oy = (int)((i / S) % S);
+        const int b = (int)(i / ((long long)S * S));
+        const int s0 = __ldg(start + oy);
+        const float *w = wts + (long long)oy * T;
+        int q[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float *src = in + (((long long)b * 3 + c) * Hin + s0) * S + ox;
+            float acc = 0.f;
+            for (int t = 0; t < T; ++t) acc = fmaf(__ldg(w + t), __ldg(src + (long long)t * S), acc);
+            q[c] = round_u8(acc);
+            rgb_small[(((long long)b * 3 + c) * S + oy) * S + ox] = (uint8_t)q[c];
+        }
+        // Pillow convert('L'): (19595 R + 38470 G + 7471 B + 0x8000) >> 16, replicated to 3 channels
+        const int L = (19595 * q[0] + 38470 * q[1] + 7471 * q[2] + 0x8000) >> 16;
+        const float lf = __fdiv_rn((float)L, 255.f);
+        float n[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) n[c] = __fdiv_rn(__fsub_rn(lf, mean[c]), stdv[c]);
+        uint4 pk = make_uint4(pack2(n[0], n[1], dtype), pack2(n[2], 0.f, dtype), 0u, 0u);
+        *reinterpret_cast<uint4 *>(reinterpret_cast<uint16_t *>(x) + i * 8) = pk;
+    }
+}
+
+// Output head: one warp per pixel.  logits = W11 . res + b; y = sigmoid*6-3; rgb = trunc(clamp(y*std+mean)*255);
+// then the S x S luma transplant against the resized source.  Optionally dumps the fp32 net output.
+__global__ void head_kernel(const void *__restrict__ res, int Cs, const float *__restrict__ w11 /*[3][Cs]*/,
+                            const float *__restrict__ b11, const uint8_t *__restrict__ rgb_small,
+                            uint8_t *__restrict__ colored, float *__restrict__ net_out, int B, int S, int dtype,
+                            int transplant) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long total = (long long)B * S * S;
+    const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+    for (long long pix = warp0; pix < total; pix += nwarps) {
+        const uint4 *row = reinterpret_cast<const uint4 *>(reinterpret_cast<const uint16_t *>(res) + pix * Cs);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        for (int g = lane; g < Cs / 8; g += 32) {
+            const uint4 v = __ldg(row + g);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = unpack2(w[j], dtype);
+                const int c = g * 8 + 2 * j;
+                a0 = fmaf(f.x, __ldg(w11 + c), a0);          a0 = fmaf(f.y, __ldg(w11 + c + 1), a0);
+                a1 = fmaf(f.x, __ldg(w11 + Cs + c), a1);     a1 = fmaf(f.y, __ldg(w11 + Cs + c + 1), a1);
+                a2 = fmaf(f.x, __ldg(w11 + 2 * Cs + c), a2); a2 = fmaf(f.y, __ldg(w11 + 2 * Cs + c + 1), a2);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+            a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+            a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+        }
+        if (lane == 0) {
+            const int ox = (int)(pix % S);
+            const int oy = (int)((pix / S) % S);
+            const int b = (int)(pix / ((long long)S * S));
+            const float lg[3] = {a0 + __ldg(b11), a1 + __ldg(b11 + 1), a2 + __ldg(b11 + 2)};
+            int q[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float sg = 1.f / (1.f + expf(-lg[c]));
+                const float y = __fadd_rn(__fmul_rn(sg, 6.f), -3.f);                 // SigmoidRange(-3,3)
+                if (net_out) net_out[(((long long)b * 3 + c) * S + oy) * S + ox] = y;
+                float d = __fadd_rn(__fmul_rn(y, stdv[c]), mean[c]);                 // denorm
+                d = fminf(fmaxf(d, 0.f), 1.f);                                       // reconstruct: clamp(0,1)
+                q[c] = (int)__fmul_rn(d, 255.f);                                     // astype(uint8): truncation
+            }
+            int r = q[0], g = q[1], bl = q[2];
+            if (transplant) {
+                const long long o = ((long long)b * 3 * S + oy) * S + ox;
+                luma_transplant(rgb_small[o], rgb_small[o + (long long)S * S], rgb_small[o + 2ll * S * S], q[0], q[1],
+                                q[2], r, g, bl);
+            }
+            const long long o = ((long long)b * 3 * S + oy) * S + ox;
+            colored[o] = (uint8_t)r;
+            colored[o + (long long)S * S] = (uint8_t)g;
+            colored[o + 2ll * S * S] = (uint8_t)bl;
+        }
+    }
+}
+
+// Vertical pass of the post-resize fused with the full-resolution luma transplant.
+// in: float [B][3][S][W]; orig/out: u8 [B][3][H][W].
+__global__ void post_vertical_kernel(const float *__restrict__ in, const uint8_t *__restrict__ orig,
+                                     uint8_t *__restrict__ out, int B, int S, int H, int W,
+                                     const int *__restrict__ start, const float *__restrict__ wts, int T,
+                                     int transplant) {
+    const long long total = (long long)B * H * W;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int ox = (int)(i % W);
+        const int oy = (int)((i / W) % H);
+        const int b = (int)(i / ((long long)W * H));
+        const int s0 = __ldg(start + oy);
+        const float *w = wts + (long long)oy * T;
+        int q[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float *src = in + (((long long)b * 3 + c) * S + s0) * W + ox;
+            float acc = 0.f;
+            for (int t = 0; t < T; ++t) acc = fmaf(__ldg(w + t), __ldg(src + (long long)t * W), acc);
+            q[c] = round_u8(acc);
+        }
+        const long long o = ((long long)b * 3 * H + oy) * W + ox;
+        const long long ps = (long long)H * W;
+        int r = q[0], g = q[1], bl = q[2];
+        if (transplant) luma_transplant(orig[o], orig[o + ps], orig[o + 2 * ps], q[0], q[1], q[2], r, g, bl);
+        out[o] = (uint8_t)r;
+        out[o + ps] = (uint8_t)g;
+        out[o + 2 * ps] = (uint8_t)bl;
+    }
+}
+
+}  // namespace havc
+
+using namespace havc;
+
+extern "C" int havc_resample_h(const uint8_t *in, float *out, long long rows, int Win, int Wout, const int *start,
+                               const float *weights, int taps, void *stream) {
+    HAVC_CHECK_ARG(in && out && start && weights && taps > 0, "havc_resample_h: bad arguments");
+    resample_h_kernel<<<grid1d(rows * Wout, 256), 256, 0, (cudaStream_t)stream>>>(in, out, rows, Win, Wout, start,
+                                                                               weights, taps);
+    HAVC_LAUNCHED();
+    return HAVC_OK;
+}
+
+extern "C" int havc_pre_vertical(const float *in, uint8_t *rgb_small, void *x, int B, int Hin, int S, const int *start,
+                                 const float *weights, int taps, int dtype, void *stream) {
+    HAVC_CHECK_ARG(in && rgb_small && x && start && weights && taps > 0 && (dtype == HAVC_F16 || dtype == HAVC_BF16),
+                   "havc_pre_vertical: bad arguments");
+    pre_vertical_kernel<<<grid1d((long long)B * S * S, 256), 256, 0, (cudaStream_t)stream>>>(
+        in, rgb_small, x, B, Hin, S, start, weights, taps, dtype);
+    HAVC_LAUNCHED();
+    return HAVC_OK;
+}
+
+extern "C" int havc_head(const void *res, int Cs, const float *w11, const float *b11, const uint8_t *rgb_small,
+                         uint8_t *colored, float *net_out, int B, int S, int dtype, int transplant, void *stream) {
+    HAVC_CHECK_ARG(res && w11 && b11 && colored && Cs % 8 == 0 && (!transplant || rgb_small) &&
+                       (dtype == HAVC_F16 || dtype == HAVC_BF16),
+                   "havc_head: bad arguments");
+    head_kernel<<<grid1d((long long)B * S * S * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+        res, Cs, w11, b11, rgb_small, colored, net_out, B, S, dtype, transplant);
+    HAVC_LAUNCHED();
+    return HAVC_OK;
+}
+
+extern "C" int havc_post_vertical(const float *in, const uint8_t *orig, uint8_t *out, int B, int S, int H, int W,
+                                  const int *start, const float *weights, int taps, int transplant, void *stream) {
+    HAVC_CHECK_ARG(in && out && start && weights && taps > 0 && (!transplant || orig), "havc_post_vertical: bad arguments");
+    post_vertical_kernel<<<grid1d((long long)B * H * W, 256), 256, 0, (cudaStream_t)stream>>>(
+        in, orig, out, B, S, H, W, start, weights, taps, transplant);
+    HAVC_LAUNCHED();
+    return HAVC_OK;
+}

@@ -1,0 +1,162 @@
+"""Per-GPU frame engine: planar RGB24 frames in (host) -> colourised planar RGB24 frames out (host).
+
+Implements the device side of HAVC_colorizer(method=0) (vsdeoldify/__init__.py:2290-2523):
+  Spline64 squeeze to S x S -> DeOldify generator -> S x S luma transplant -> Spline64 back to W x H ->
+  full-resolution luma transplant,
+as one CUDA graph of libhavc_b200 launches per batch of B frames, fed through pinned double buffers on
+separate copy streams.  torch supplies device/pinned memory, streams and graph capture only.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib, ops, resample
+from .unet import UnetProgram
+
+
+class _Tables:
+    def __init__(self, src: int, dst: int, kernel: str, dev):
+        start, w = resample.build_tables(src, dst, kernel)
+        self.taps = int(w.shape[1])
+        self.start = torch.from_numpy(start).to(dev)
+        self.w = torch.from_numpy(w).contiguous().to(dev)
+
+
+class DeoldifyEngine:
+    """One DeOldify generator at render size S = render_factor*16 on frames of width x height, batch B.
+
+    Second generator + 50/50 blend ('stable'/'artistic', visualize.py:118-137) is layered on top by
+    `vsdeoldify_b200.vsmodels`; this class is the single-network path (model 'video')."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], width: int, height: int, render_factor: int = 24, batch: int = 8,
+                 dtype: torch.dtype = torch.float16, device: str = "cuda:0", resize_kernel: str = "spline64",
+                 use_graph: bool = True, keep_taps: bool = False, debug_net_out: bool = False):
+        self.lib = _lib.lib()
+        self.dev = torch.device(device)
+        torch.cuda.set_device(self.dev)
+        self.W, self.H, self.B = width, height, batch
+        self.S = min(render_factor * 16, width)          # frame_size, vsdeoldify/__init__.py:2502
+        S, B, W, H = self.S, batch, width, height
+        self.dtype, self.hd = dtype, ops.havc_dtype(dtype)
+        self.prog = UnetProgram(sd, B, S, dtype, device=self.dev, keep_taps=keep_taps)
+        self.t_down_h = _Tables(W, S, resize_kernel, self.dev)
+        self.t_down_v = _Tables(H, S, resize_kernel, self.dev)
+        self.t_up_h = _Tables(S, W, resize_kernel, self.dev)
+        self.t_up_v = _Tables(S, H, resize_kernel, self.dev)
+        u8 = dict(dtype=torch.uint8, device=self.dev)
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        self.n_slots = 2
+        self.d_in = [torch.empty(B, 3, H, W, **u8) for _ in range(self.n_slots)]
+        self.d_out = [torch.empty(B, 3, H, W, **u8) for _ in range(self.n_slots)]
+        self.h_in = [torch.empty(B, 3, H, W, dtype=torch.uint8).pin_memory() for _ in range(self.n_slots)]
+        self.h_out = [torch.empty(B, 3, H, W, dtype=torch.uint8).pin_memory() for _ in range(self.n_slots)]
+        self.tmp_down = torch.empty(B, 3, H, S, **f32)
+        self.rgb_small = torch.empty(B, 3, S, S, **u8)
+        self.colored = torch.empty(B, 3, S, S, **u8)
+        self.tmp_up = torch.empty(B, 3, S, W, **f32)
+        self.net_out = torch.empty(B, 3, S, S, **f32) if debug_net_out else None
+        self.compute = torch.cuda.Stream(device=self.dev)
+        self.copy_in = torch.cuda.Stream(device=self.dev)
+        self.copy_out = torch.cuda.Stream(device=self.dev)
+        self.graphs: List[Optional[torch.cuda.CUDAGraph]] = [None] * self.n_slots
+        self.use_graph = use_graph
+        self.launches_per_batch = 0
+        self._warm()
+
+    # ---- launch list ------------------------------------------------------------------------------
+    def _launch(self, slot: int, stream: int):
+        lib, B, S, W, H = self.lib, self.B, self.S, self.W, self.H
+        chk = _lib.check
+        td, tv, uh, uv = self.t_down_h, self.t_down_v, self.t_up_h, self.t_up_v
+        chk(lib.havc_resample_h(self.d_in[slot].data_ptr(), self.tmp_down.data_ptr(), B * 3 * H, W, S,
+                                td.start.data_ptr(), td.w.data_ptr(), td.taps, stream), "pre.h")
+        chk(lib.havc_pre_vertical(self.tmp_down.data_ptr(), self.rgb_small.data_ptr(), self.prog.x.data_ptr(), B, H, S,
+                                  tv.start.data_ptr(), tv.w.data_ptr(), tv.taps, self.hd, stream), "pre.v")
+        self.prog.run(stream)
+        chk(lib.havc_head(self.prog.res.data_ptr(), self.prog.n_res_channels, self.prog.w11.data_ptr(),
+                          self.prog.b11.data_ptr(), self.rgb_small.data_ptr(), self.colored.data_ptr(),
+                          self.net_out.data_ptr() if self.net_out is not None else None, B, S, self.hd, 1, stream),
+            "head")
+        chk(lib.havc_resample_h(self.colored.data_ptr(), self.tmp_up.data_ptr(), B * 3 * S, S, W,
+                                uh.start.data_ptr(), uh.w.data_ptr(), uh.taps, stream), "post.h")
+        chk(lib.havc_post_vertical(self.tmp_up.data_ptr(), self.d_in[slot].data_ptr(), self.d_out[slot].data_ptr(), B, S,
+                                   H, W, uv.start.data_ptr(), uv.w.data_ptr(), uv.taps, 1, stream), "post.v")
+
+    def _warm(self):
+        with torch.cuda.stream(self.compute):
+            for s in range(self.n_slots):
+                self.d_in[s].zero_()
+            n0 = self.lib.havc_launch_count()
+            self._launch(0, self.compute.cuda_stream)
+            self.launches_per_batch = int(self.lib.havc_launch_count() - n0)
+        self.compute.synchronize()
+        if self.use_graph:
+            for s in range(self.n_slots):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=self.compute):
+                    self._launch(s, torch.cuda.current_stream().cuda_stream)
+                self.graphs[s] = g
+            self.compute.synchronize()
+
+    def run_slot(self, slot: int):
+        """Enqueue the device work for the frames resident in d_in[slot] on the compute stream."""
+        with torch.cuda.stream(self.compute):
+            if self.use_graph:
+                self.graphs[slot].replay()
+            else:
+                self._launch(slot, self.compute.cuda_stream)
+
+    # ---- synchronous convenience API (tests) ---------------------------------------------------------
+    def colorize_batch(self, frames: np.ndarray) -> np.ndarray:
+        """frames: uint8 [n<=B, 3, H, W] planar RGB (host).  Returns uint8 [n, 3, H, W]."""
+        n = frames.shape[0]
+        assert n <= self.B and frames.shape[1:] == (3, self.H, self.W) and frames.dtype == np.uint8
+        self.h_in[0][:n].copy_(torch.from_numpy(np.ascontiguousarray(frames)))
+        with torch.cuda.stream(self.compute):
+            self.d_in[0].copy_(self.h_in[0], non_blocking=True)
+        self.run_slot(0)
+        with torch.cuda.stream(self.compute):
+            self.h_out[0].copy_(self.d_out[0], non_blocking=True)
+        self.compute.synchronize()
+        return self.h_out[0][:n].numpy().copy()
+
+    # ---- pipelined API (bench e2e / clip rendering) ----------------------------------------------------
+    def colorize_stream(self, batches, on_result):
+        """batches: iterable of uint8 [B,3,H,W] host arrays (a full batch each); on_result(i, out) is called
+        in order with a view of the pinned output buffer (valid until the next-but-one call).
+        H2D of batch i+1 and D2H of batch i-1 overlap the compute of batch i."""
+        ev_in = [torch.cuda.Event() for _ in range(self.n_slots)]
+        ev_done = [torch.cuda.Event() for _ in range(self.n_slots)]
+        ev_out = [torch.cuda.Event() for _ in range(self.n_slots)]
+        ev_free = [None] * self.n_slots
+        pending = []
+        i = -1
+        for i, fr in enumerate(batches):
+            s = i % self.n_slots
+            if len(pending) >= self.n_slots:           # slot about to be reused: deliver its previous result
+                j, sj = pending.pop(0)
+                ev_out[sj].synchronize()
+                on_result(j, self.h_out[sj].numpy())
+            self.h_in[s].copy_(torch.from_numpy(fr) if isinstance(fr, np.ndarray) else fr)
+            with torch.cuda.stream(self.copy_in):
+                if ev_free[s] is not None:
+                    self.copy_in.wait_event(ev_free[s])   # previous compute on this slot has consumed d_in
+                self.d_in[s].copy_(self.h_in[s], non_blocking=True)
+                ev_in[s].record(self.copy_in)
+            self.compute.wait_event(ev_in[s])
+            self.compute.wait_event(ev_out[s]) if i >= self.n_slots else None
+            self.run_slot(s)
+            ev_done[s].record(self.compute)
+            ev_free[s] = ev_done[s]
+            with torch.cuda.stream(self.copy_out):
+                self.copy_out.wait_event(ev_done[s])
+                self.h_out[s].copy_(self.d_out[s], non_blocking=True)
+                ev_out[s].record(self.copy_out)
+            pending.append((i, s))
+        for j, sj in pending:
+            ev_out[sj].synchronize()
+            on_result(j, self.h_out[sj].numpy())
+        return i + 1

@@ -144,16 +144,18 @@ def pack_cols(v: Optional[torch.Tensor], n_alloc: int, fill: float, shuffle_meta
 
 
 def choose_bn(n_total: int, m_tiles: int, sms: int = 148) -> int:
-    """N tile: as wide as possible (fewest A re-reads) while still giving every SM a tile."""
+    """N tile (UMMA N: multiple of 16, <= 256; 272 = 256+16 for the 259-channel tail): the widest divisor
+    of n_total (fewest re-reads of the activation tile) that still gives every SM a tile."""
     if n_total <= 256 or n_total == 272:
         return n_total
-    for bn in (256, 128, 64):
-        if n_total % bn == 0 and m_tiles * (n_total // bn) >= sms:
+    cands = [bn for bn in range(256, 15, -16) if n_total % bn == 0]
+    if not cands:
+        return 128
+    for bn in cands:
+        if m_tiles * (n_total // bn) >= sms:
             return bn
-    for bn in (64, 128, 256):  # cannot fill the machine anyway: maximise parallelism
-        if n_total % bn == 0:
-            return bn
-    return 128
+    small = [bn for bn in cands if bn >= 64]   # cannot fill the machine anyway: maximise parallelism
+    return (small or cands)[-1]
 
 
 @dataclass
@@ -211,7 +213,7 @@ def make_conv(src0: torch.Tensor, weight: torch.Tensor, out: torch.Tensor, taps,
     keep = [src0, src1, weight, out, residual]
     for nm, v in (("bias", bias), ("scale", scale), ("shift", shift)):
         if v is not None:
-            assert v.dtype == torch.float32 and v.is_cuda and v.numel() >= d.N_total, nm
+            assert v.dtype == torch.float32 and v.numel() >= d.N_total, nm
             setattr(d, nm, v.data_ptr())
             keep.append(v)
     d.relu1, d.relu2 = int(relu1), int(relu2)

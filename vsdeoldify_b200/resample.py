@@ -1,0 +1,87 @@
+"""Host-side resampling tables for the table-driven GPU resize kernels (havc_resample_h & co).
+
+zimg (VapourSynth `resize.Spline64/Spline36`, used by HAVC_colorizer at vsdeoldify/__init__.py:2504 and
+:3547 and by vsresize.py) is not available in this environment, so the filter bank follows the published
+zimg / Avisynth definitions: separable, half-pixel centres, support widened by the
+shrink ratio, per-output normalised weights, taps that fall outside the image mirrored back in.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Tuple
+
+import numpy as np
+
+
+def spline64(x: float) -> float:
+    x = abs(x)
+    if x < 1.0:
+        return ((49.0 / 41.0 * x - 6387.0 / 2911.0) * x - 3.0 / 2911.0) * x + 1.0
+    if x < 2.0:
+        t = x - 1.0
+        return ((-24.0 / 41.0 * t + 4032.0 / 2911.0) * t - 2328.0 / 2911.0) * t
+    if x < 3.0:
+        t = x - 2.0
+        return ((6.0 / 41.0 * t - 1008.0 / 2911.0) * t + 582.0 / 2911.0) * t
+    if x < 4.0:
+        t = x - 3.0
+        return ((-1.0 / 41.0 * t + 168.0 / 2911.0) * t - 97.0 / 2911.0) * t
+    return 0.0
+
+
+def spline36(x: float) -> float:
+    x = abs(x)
+    if x < 1.0:
+        return ((13.0 / 11.0 * x - 453.0 / 209.0) * x - 3.0 / 209.0) * x + 1.0
+    if x < 2.0:
+        t = x - 1.0
+        return ((-6.0 / 11.0 * t + 270.0 / 209.0) * t - 156.0 / 209.0) * t
+    if x < 3.0:
+        t = x - 2.0
+        return ((1.0 / 11.0 * t - 45.0 / 209.0) * t + 26.0 / 209.0) * t
+    return 0.0
+
+
+KERNELS = {"spline64": (spline64, 4), "spline36": (spline36, 3)}
+
+
+def filter_matrix(src: int, dst: int, kernel: str = "spline64") -> np.ndarray:
+    """Dense [dst, src] float64 resampling matrix (zimg compute_filter semantics)."""
+    f, support = KERNELS[kernel]
+    scale = dst / src
+    step = min(scale, 1.0)
+    fsupport = support / step
+    fsize = max(int(math.ceil(fsupport)) * 2, 1)
+    m = np.zeros((dst, src), dtype=np.float64)
+    for i in range(dst):
+        pos = (i + 0.5) / scale
+        begin = math.floor(pos - fsize / 2.0 + 0.5) + 0.5
+        ws = [f((begin + j - pos) * step) for j in range(fsize)]
+        total = sum(ws)
+        for j in range(fsize):
+            xpos = begin + j
+            if xpos < 0.0:
+                real = -xpos
+            elif xpos >= src:
+                real = 2.0 * src - xpos
+            else:
+                real = xpos
+            idx = min(max(int(math.floor(real)), 0), src - 1)
+            m[i, idx] += ws[j] / total
+    return m
+
+
+def build_tables(src: int, dst: int, kernel: str = "spline64") -> Tuple[np.ndarray, np.ndarray]:
+    """(start int32 [dst], weights float32 [dst, T]) with out[o] = sum_t weights[o,t] * in[start[o]+t]."""
+    m = filter_matrix(src, dst, kernel)
+    nz = m != 0.0
+    first = np.where(nz.any(1), nz.argmax(1), 0)
+    last = np.where(nz.any(1), src - 1 - nz[:, ::-1].argmax(1), 0)
+    T = int((last - first).max()) + 1
+    start = np.minimum(first, src - T).astype(np.int32)
+    start = np.maximum(start, 0)
+    w = np.zeros((dst, T), dtype=np.float32)
+    for o in range(dst):
+        seg = m[o, start[o]:start[o] + T]
+        w[o, :len(seg)] = seg
+    return start, w

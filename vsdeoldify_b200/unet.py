@@ -1,0 +1,414 @@
+"""DeOldify DynamicUnet (wide / deep) as a program of libhavc_b200 launches.
+
+Host side of the network: reads a state-dict in the reference's schema (Learner.load,
+vsdeoldify/fastai/basic_train.py:264-286), folds the re-parametrisations and the eval BatchNorms
+(SURVEY.md Appendix C), packs 16-bit K-major weights, allocates the NHWC activation buffers for a fixed
+(batch, S) and emits the ordered launch list.  The list is replayed through a CUDA graph by
+`vsdeoldify_b200.engine`.  No arithmetic on activations happens in Python/torch.
+
+Graph (reference: DynamicUnetWide unet.py:208-285, DynamicUnetDeep unet.py:94-166):
+  x -> im2col+GEMM stem(+BN+ReLU) -> maxpool -> resnet blocks (BN folded, ReLU/residual in epilogues)
+    -> BN+ReLU -> middle_conv x2 (ReLU->BN epilogue)
+    -> 4 x [shuf 1x1 GEMM (BN folded, ReLU, PixelShuffle store) -> blur ; BN+ReLU(skip) ; 3x3 GEMM over two
+            K sources (no concat) (ReLU->BN epilogue) ; (+ self-attention as 4 GEMMs + row soft-max)]
+    -> shuf 1x1 (+bias, ReLU, PixelShuffle store) -> blur into the 'cat' buffer next to x
+    -> res_block: 2 x 3x3 GEMM (+bias, ReLU; second adds the cat buffer) -> head kernel.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib, ops
+from .ops import pad_to
+
+SD = Dict[str, torch.Tensor]
+BN_EPS = 1e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# folding (load time, fp32/fp64 on the CPU)
+# ------------------------------------------------------------------------------------------------
+def bn_affine(sd: SD, p: str) -> Tuple[torch.Tensor, torch.Tensor]:
+    """eval BatchNorm as y = x*scale + shift."""
+    scale = sd[p + ".weight"].double() / torch.sqrt(sd[p + ".running_var"].double() + BN_EPS)
+    shift = sd[p + ".bias"].double() - sd[p + ".running_mean"].double() * scale
+    return scale.float(), shift.float()
+
+
+def folded_weight(sd: SD, p: str) -> torch.Tensor:
+    """Effective conv weight in eval mode: spectral norm (W/sigma, sigma=u^T W v, with the legacy
+    'no weight_v' case solved like torch's load hook is NOT needed for >=1.0 checkpoints), weight norm
+    (g*v/||v||) or plain."""
+    if p + ".weight_orig" in sd:
+        w = sd[p + ".weight_orig"].double()
+        u = sd[p + ".weight_u"].double()
+        if p + ".weight_v" in sd:
+            v = sd[p + ".weight_v"].double()
+        else:  # spectral-norm state-dict version < 1: derive v from u (one half power-iteration step)
+            v = torch.nn.functional.normalize(torch.mv(w.flatten(1).t(), u), dim=0)
+        sigma = torch.dot(u, torch.mv(w.flatten(1), v))
+        return (w / sigma).float()
+    if p + ".weight_g" in sd:
+        v, g = sd[p + ".weight_v"].double(), sd[p + ".weight_g"].double()
+        n = v.flatten(1).norm(dim=1).view(-1, *[1] * (v.dim() - 1))
+        return (v * (g / n)).float()
+    return sd[p + ".weight"].float()
+
+
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class Op:
+    name: str
+    fn: Callable[[int], None]
+    flops: float = 0.0       # algorithmic FLOPs (2*MAC, unpadded)
+    bytes: float = 0.0       # algorithmic HBM bytes for memory-bound ops
+    kind: str = "aux"
+
+
+class UnetProgram:
+    """Compiled launch list for one (state-dict, batch, S, dtype)."""
+
+    def __init__(self, sd: SD, batch: int, size: int, dtype: torch.dtype = torch.float16, device="cuda",
+                 keep_taps: bool = False):
+        if size % 32 != 0:
+            raise ValueError(f"render size {size} must be a multiple of 32 (even render_factor); the nearest-"
+                             "neighbour up-path resize of unet.py:201-203 is not implemented")
+        self.sd, self.B, self.S, self.dtype, self.dev = sd, batch, size, dtype, torch.device(device)
+        self.hd = ops.havc_dtype(dtype)
+        self.lib = _lib.lib()
+        self.ops: List[Op] = []
+        self.keep: list = []
+        self.taps: Dict[str, torch.Tensor] = {}
+        self.keep_taps = keep_taps
+        self.bottleneck = "layers.0.4.0.conv3.weight" in sd
+        self._build()
+
+    # ---- buffers / params ---------------------------------------------------------------------
+    def buf(self, *shape, dtype=None, zero=False) -> torch.Tensor:
+        t = (torch.zeros if zero else torch.empty)(*shape, dtype=dtype or self.dtype, device=self.dev)
+        self.keep.append(t)
+        return t
+
+    def dev_f32(self, v: torch.Tensor) -> torch.Tensor:
+        t = v.detach().float().contiguous().to(self.dev)
+        self.keep.append(t)
+        return t
+
+    def tap(self, name, t):
+        if self.keep_taps:
+            self.taps[name] = t
+        return t
+
+    # ---- op emitters --------------------------------------------------------------------------
+    def conv(self, name: str, src0, w: torch.Tensor, *, ks=1, src1=None, cin_splits=None, stride=1, bias=None,
+             relu1=False, scale=None, shift=None, residual=None, relu2=False, shuffle=False, out=None,
+             out_c: Optional[int] = None) -> torch.Tensor:
+        """w: folded fp32 [Cout, Cin, ks, ks].  Returns the NHWC output tensor."""
+        Cout, Cin = w.shape[0], w.shape[1]
+        wp, meta = ops.pack_conv_weight(w, cin_splits, dtype=self.dtype, shuffle=shuffle)
+        wp = wp.to(self.dev)
+        self.keep.append(wp)
+        n_total = meta["rows"]
+        pc = lambda v, fill: None if v is None else self.dev_f32(ops.pack_cols(v, n_total, fill, meta if shuffle else None))
+        if stride == 1:
+            B, H, W = src0.shape[0], src0.shape[1], src0.shape[2]
+            taps = ops.taps_for(ks)
+        else:  # src0 is phase-split [P,B,H/2,W/2,C]
+            B, H, W = src0.shape[1], src0.shape[2], src0.shape[3]
+            taps = ops.taps_stride2(ks) if ks > 1 else [(0, 0, 0, 0)]
+        if out is None:
+            if shuffle:
+                out = self.buf(B, 2 * H, 2 * W, pad_to(meta["cg"], 8))
+            else:
+                out = self.buf(B, H, W, pad_to(out_c or Cout, 8))
+        op = ops.make_conv(src0, wp, out, taps, src1=src1, w_c1_off=meta["c1_off"], n_total=n_total,
+                           bias=pc(bias, 0.0), scale=pc(scale, 1.0), shift=pc(shift, 0.0), relu1=relu1, relu2=relu2,
+                           residual=residual, out_space=(B, H, W), shuffle=shuffle, group_n=meta.get("group_n", 0),
+                           name=name)
+        flops = 2.0 * B * H * W * Cout * Cin * ks * ks
+        self.ops.append(Op(name, op.launch, flops=flops, kind="gemm"))
+        self.keep.append(op)
+        return out
+
+    def aux(self, name, fn, nbytes=0.0):
+        self.ops.append(Op(name, fn, bytes=nbytes))
+
+    def affine(self, name, src, scale, shift, relu, out=None, out_c_off=0, c=None):
+        B, H, W, Cs = src.shape
+        c = c or Cs
+        if out is None:
+            out = self.buf(B, H, W, Cs)
+        sc = self.dev_f32(torch.cat([scale, scale.new_ones(pad_to(c, 8) - scale.numel())]))
+        sh = self.dev_f32(torch.cat([shift, shift.new_zeros(pad_to(c, 8) - shift.numel())]))
+        in_ptr, out_ptr = src.data_ptr(), out.data_ptr() + 2 * out_c_off
+        n_pix, cc, istr, ostr, hd, lib = B * H * W, pad_to(c, 8), src.stride(2), out.stride(2), self.hd, self.lib
+
+        def fn(stream):
+            _lib.check(lib.havc_affine_act(in_ptr, out_ptr, n_pix, cc, istr, ostr, sc.data_ptr(), sh.data_ptr(),
+                                           int(relu), hd, stream), name)
+        self.aux(name, fn, nbytes=4.0 * n_pix * cc)
+        return out
+
+    def blur(self, name, src, out=None):
+        B, H, W, Cs = src.shape
+        if out is None:
+            out = self.buf(B, H, W, Cs)
+        ip, op_, ostr, hd, lib = src.data_ptr(), out.data_ptr(), out.stride(2), self.hd, self.lib
+
+        def fn(stream):
+            _lib.check(lib.havc_blur2x2(ip, op_, B, H, W, Cs, ostr, hd, stream), name)
+        self.aux(name, fn, nbytes=4.0 * B * H * W * Cs)
+        return out
+
+    def phase_split(self, name, src, n_phases):
+        B, H, W, Cs = src.shape
+        out = self.buf(n_phases, B, (H + 1) // 2, (W + 1) // 2, Cs)
+        ip, op_, lib = src.data_ptr(), out.data_ptr(), self.lib
+
+        def fn(stream):
+            _lib.check(lib.havc_phase_split(ip, op_, B, H, W, Cs, n_phases, stream), name)
+        self.aux(name, fn, nbytes=2.0 * B * H * W * Cs * (1 + n_phases / 4))
+        return out
+
+    # ---- network ------------------------------------------------------------------------------
+    def _build(self):
+        sd, B, S, lib, hd = self.sd, self.B, self.S, self.lib, self.hd
+        # network input: normalised image, NHWC [B,S,S,8] (3 real channels), written by the pre kernel
+        self.x = self.buf(B, S, S, 8, zero=True)
+
+        # ---- encoder stem: 7x7/s2 conv as im2col + GEMM, BN folded, ReLU --------------------------
+        w = sd["layers.0.0.weight"].float()
+        sc, sh = bn_affine(sd, "layers.0.1")
+        wf = (w * sc.view(-1, 1, 1, 1)).permute(0, 2, 3, 1).reshape(64, 147)     # K order (kh, kw, c)
+        Kp = pad_to(147, 8)
+        wf = torch.cat([wf, wf.new_zeros(64, Kp - 147)], 1).view(64, Kp, 1, 1)
+        H2 = S // 2
+        col = self.buf(B, H2, H2, Kp)
+        xp, cp = self.x.data_ptr(), col.data_ptr()
+
+        def im2col(stream):
+            _lib.check(lib.havc_im2col_small(xp, cp, B, S, S, 8, 3, 7, 2, 3, Kp, hd, stream), "stem.im2col")
+        self.aux("stem.im2col", im2col, nbytes=2.0 * B * H2 * H2 * Kp)
+        stem = self.conv("stem.conv", col, wf, bias=sh, relu1=True)
+        self.ops[-1].flops = 2.0 * B * H2 * H2 * 64 * 147
+        self.tap("enc.stem", stem)
+        H4 = S // 4
+        pool = self.buf(B, H4, H4, 64)
+        sp, pp = stem.data_ptr(), pool.data_ptr()
+
+        def maxpool(stream):
+            _lib.check(lib.havc_maxpool3x3s2(sp, pp, B, H2, H2, 64, hd, stream), "stem.maxpool")
+        self.aux("stem.maxpool", maxpool, nbytes=2.0 * B * (H2 * H2 + H4 * H4) * 64)
+
+        # ---- resnet layers --------------------------------------------------------------------------
+        y = pool
+        skips = []
+        for li in (4, 5, 6, 7):
+            bi = 0
+            while f"layers.0.{li}.{bi}.conv1.weight" in sd:
+                stride = 2 if (bi == 0 and li > 4) else 1
+                y = (self._bottleneck if self.bottleneck else self._basic)(y, f"layers.0.{li}.{bi}", stride)
+                bi += 1
+            self.tap(f"enc.layer{li - 3}", y)
+            skips.append(y)
+        skips = [skips[2], skips[1], skips[0], stem]
+
+        # ---- layers[1..2] BN + ReLU; layers[3] middle_conv ----------------------------------------
+        sc, sh = bn_affine(sd, "layers.1")
+        y = self.affine("enc.bn_relu", y, sc, sh, True)
+        self.tap("enc.out", y)
+        for j in (0, 1):
+            sc, sh = bn_affine(sd, f"layers.3.{j}.2")
+            y = self.conv(f"middle.{j}", y, folded_weight(sd, f"layers.3.{j}.0"), ks=3, relu1=True, scale=sc, shift=sh)
+        self.tap("middle", y)
+
+        # ---- U-Net blocks ---------------------------------------------------------------------------
+        for i, s in enumerate(skips):
+            y = self._unet_block(y, s, f"layers.{4 + i}")
+            self.tap(f"block{i}", y)
+
+        # ---- layers[8] PixelShuffle_ICNR -> cat buffer [u | x] ---------------------------------------
+        w8 = folded_weight(sd, "layers.8.conv.0")
+        t8 = self.conv("shuf8.conv", y, w8, bias=sd["layers.8.conv.0.bias"].float(), relu1=True, shuffle=True)
+        cu = w8.shape[0] // 4
+        assert cu % 8 == 0 or True
+        cu8 = pad_to(cu, 8)
+        ncat = cu + 3
+        cat = self.buf(B, S, S, pad_to(cu8 + 8, 8), zero=True)
+        # the cat buffer stores u at [0,cu8) and x at [cu8, cu8+8); weights are packed with matching splits
+        self.blur("shuf8.blur", t8, out=cat)
+        ones, zeros = torch.ones(8), torch.zeros(8)
+        self.affine("cat.x", self.x, ones, zeros, False, out=cat, out_c_off=cu8, c=8)
+        self.tap("cat", cat)
+        self.cat_splits = [cu, 3] if cu8 != cu else None
+        # res_block (fastai/layers.py:154-161): two conv+bias+ReLU, then + input
+        ccat = cat.shape[-1]
+        w0 = self._pad_cin_to_cat(folded_weight(sd, "layers.10.layers.0.0"), cu, cu8, ccat)
+        w1 = self._pad_cin_to_cat(folded_weight(sd, "layers.10.layers.1.0"), cu, cu8, ccat)
+        # output channels of both convs must line up with the cat buffer's channel positions
+        w0 = self._pad_cout_to_cat(w0, cu, cu8, ccat)
+        w1 = self._pad_cout_to_cat(w1, cu, cu8, ccat)
+        b0 = self._pad_vec_to_cat(sd["layers.10.layers.0.0.bias"].float(), cu, cu8, ccat)
+        b1 = self._pad_vec_to_cat(sd["layers.10.layers.1.0.bias"].float(), cu, cu8, ccat)
+        r1 = self.conv("res.conv0", cat, w0, ks=3, bias=b0, relu1=True)
+        self.ops[-1].flops = 2.0 * B * S * S * ncat * ncat * 9
+        r2 = self.conv("res.conv1", r1, w1, ks=3, bias=b1, relu1=True, residual=cat)
+        self.ops[-1].flops = 2.0 * B * S * S * ncat * ncat * 9
+        self.tap("res", r2)
+        self.res = r2
+        # head weights (layers.11 1x1 conv + bias), laid out on the cat channel positions
+        w11 = folded_weight(sd, "layers.11.0").view(3, ncat)
+        w11p = torch.zeros(3, ccat)
+        w11p[:, :cu] = w11[:, :cu]
+        w11p[:, cu8:cu8 + 3] = w11[:, cu:]
+        self.w11 = self.dev_f32(w11p)
+        self.b11 = self.dev_f32(sd["layers.11.0.bias"].float())
+        self.head_flops = 2.0 * B * S * S * ncat * 3
+        self.n_res_channels = ccat
+
+    @staticmethod
+    def _pad_cin_to_cat(w, cu, cu8, ccat):
+        """[Cout, cu+3, k, k] -> [Cout, ccat, k, k] with the 3 image channels moved to position cu8."""
+        out = w.new_zeros(w.shape[0], ccat, w.shape[2], w.shape[3])
+        out[:, :cu] = w[:, :cu]
+        out[:, cu8:cu8 + 3] = w[:, cu:]
+        return out
+
+    @staticmethod
+    def _pad_cout_to_cat(w, cu, cu8, ccat):
+        out = w.new_zeros(ccat, *w.shape[1:])
+        out[:cu] = w[:cu]
+        out[cu8:cu8 + 3] = w[cu:]
+        return out
+
+    @staticmethod
+    def _pad_vec_to_cat(v, cu, cu8, ccat):
+        out = v.new_zeros(ccat)
+        out[:cu] = v[:cu]
+        out[cu8:cu8 + 3] = v[cu:]
+        return out
+
+    def _fold_bn(self, p_conv, p_bn):
+        w = self.sd[p_conv + ".weight"].float()
+        sc, sh = bn_affine(self.sd, p_bn)
+        return w * sc.view(-1, 1, 1, 1), sh
+
+    def _bottleneck(self, x, p, stride):
+        """torchvision Bottleneck, v1.5 (stride on conv2); BN folded into each conv."""
+        w1, b1 = self._fold_bn(p + ".conv1", p + ".bn1")
+        w2, b2 = self._fold_bn(p + ".conv2", p + ".bn2")
+        w3, b3 = self._fold_bn(p + ".conv3", p + ".bn3")
+        c1 = self.conv(p + ".conv1", x, w1, bias=b1, relu1=True)
+        if stride == 2:
+            ph = self.phase_split(p + ".split", c1, 4)
+            c2 = self.conv(p + ".conv2", ph, w2, ks=3, stride=2, bias=b2, relu1=True)
+        else:
+            c2 = self.conv(p + ".conv2", c1, w2, ks=3, bias=b2, relu1=True)
+        idt = x
+        if p + ".downsample.0.weight" in self.sd:
+            wd, bd = self._fold_bn(p + ".downsample.0", p + ".downsample.1")
+            if stride == 2:
+                xs = self.phase_split(p + ".ds_split", x, 1)
+                idt = self.conv(p + ".downsample", xs, wd, stride=2, bias=bd)
+            else:
+                idt = self.conv(p + ".downsample", x, wd, bias=bd)
+        return self.conv(p + ".conv3", c2, w3, bias=b3, residual=idt, relu2=True)
+
+    def _basic(self, x, p, stride):
+        w1, b1 = self._fold_bn(p + ".conv1", p + ".bn1")
+        w2, b2 = self._fold_bn(p + ".conv2", p + ".bn2")
+        idt = x
+        if stride == 2:
+            ph = self.phase_split(p + ".split", x, 4)
+            c1 = self.conv(p + ".conv1", ph, w1, ks=3, stride=2, bias=b1, relu1=True)
+            if p + ".downsample.0.weight" in self.sd:
+                wd, bd = self._fold_bn(p + ".downsample.0", p + ".downsample.1")
+                idt = self.conv(p + ".downsample", ph[0:1], wd, stride=2, bias=bd)
+        else:
+            c1 = self.conv(p + ".conv1", x, w1, ks=3, bias=b1, relu1=True)
+            if p + ".downsample.0.weight" in self.sd:
+                wd, bd = self._fold_bn(p + ".downsample.0", p + ".downsample.1")
+                idt = self.conv(p + ".downsample", x, wd, bias=bd)
+        return self.conv(p + ".conv2", c1, w2, ks=3, bias=b2, residual=idt, relu2=True)
+
+    def _unet_block(self, up_in, skip, p):
+        """UnetBlockWide / UnetBlockDeep (unet.py:170-205 / 55-91)."""
+        sd = self.sd
+        # shuf: conv1x1 (no bias) -> BN -> ReLU -> PixelShuffle -> blur; BN folds into the conv (exact: 1x1, no pad)
+        ws = folded_weight(sd, p + ".shuf.conv.0")
+        sc, sh = bn_affine(sd, p + ".shuf.conv.1")
+        t = self.conv(p + ".shuf.conv", up_in, ws * sc.view(-1, 1, 1, 1), bias=sh, relu1=True, shuffle=True)
+        u = self.blur(p + ".shuf.blur", t)
+        if u.shape[1:3] != skip.shape[1:3]:
+            raise ValueError("up-path / skip size mismatch (odd render_factor) is not supported")
+        sc, sh = bn_affine(sd, p + ".bn")
+        sb = self.affine(p + ".skip_bn_relu", skip, sc, sh, True)
+        cu = ws.shape[0] // 4
+        cs = sc.numel()
+        convs = ["conv"] if p + ".conv.0.weight_orig" in sd else ["conv1", "conv2"]
+        y = None
+        for k, cv in enumerate(convs):
+            w = folded_weight(sd, f"{p}.{cv}.0")
+            bsc, bsh = bn_affine(sd, f"{p}.{cv}.2")
+            if k == 0:
+                y = self.conv(f"{p}.{cv}", u, w, ks=3, src1=sb, cin_splits=[cu, cs], relu1=True, scale=bsc, shift=bsh)
+            else:
+                y = self.conv(f"{p}.{cv}", y, w, ks=3, relu1=True, scale=bsc, shift=bsh)
+            if f"{p}.{cv}.3.gamma" in sd:
+                y = self._attention(y, f"{p}.{cv}.3")
+        return y
+
+    def _attention(self, x, p):
+        """SelfAttention (fastai/layers.py:81-96) as GEMMs + a row soft-max; N x N logits in fp32."""
+        sd, B = self.sd, self.B
+        _, H, W, Cc = x.shape
+        N = H * W
+        wq, wk, wv = (folded_weight(sd, f"{p}.{n}") for n in ("query", "key", "value"))
+        d = wq.shape[0]
+        gamma = float(sd[p + ".gamma"].flatten()[0])
+        xt = x.view(B, 1, N, Cc)
+        q = self.conv(p + ".query", xt, wq)          # f  [B,1,N,d]
+        k = self.conv(p + ".key", xt, wk)            # g  [B,1,N,d]
+        dp = q.shape[-1]
+        # Ht[b, c, i] = sum_k Wv[c,k] x[b,i,k]  (A = Wv shared, B = tokens per image)
+        wv16 = self.buf(1, 1, Cc, Cc)
+        wv16.copy_(wv.view(1, 1, Cc, Cc).to(self.dtype))
+        Ht = self.buf(B, 1, Cc, N)
+        op = ops.make_conv(wv16, x.view(B, N, 1, Cc), Ht, [(0, 0, 0, 0)], n_total=pad_to(N, 16), a_batched=False,
+                           b_batched=True, out_space=(B, 1, Cc), c_store=N, name=p + ".value_t")
+        self.ops.append(Op(p + ".value_t", op.launch, flops=2.0 * B * N * Cc * Cc, kind="gemm"))
+        self.keep.append(op)
+        # S[b, j, i] = sum_c g[b,j,c] f[b,i,c]
+        Sx = self.buf(B, 1, N, N, dtype=torch.float32)
+        op = ops.make_conv(k, q.view(B, N, 1, dp), Sx, [(0, 0, 0, 0)], n_total=pad_to(N, 16), b_batched=True,
+                           out_space=(B, 1, N), c_store=N, name=p + ".logits")
+        self.ops.append(Op(p + ".logits", op.launch, flops=2.0 * B * N * N * d, kind="gemm"))
+        self.keep.append(op)
+        P = self.buf(B, 1, N, N)
+        sp, pp, hd, lib = Sx.data_ptr(), P.data_ptr(), self.hd, self.lib
+
+        def softmax(stream):
+            _lib.check(lib.havc_softmax_rows(sp, pp, B * N, N, hd, stream), p + ".softmax")
+        self.aux(p + ".softmax", softmax, nbytes=6.0 * B * N * N)
+        # out[b, j, c] = x[b,j,c] + gamma * sum_i P[b,j,i] Ht[b,c,i]
+        out = self.buf(B, H, W, Cc)
+        gs = self.dev_f32(torch.full((pad_to(Cc, 16),), gamma))
+        gz = self.dev_f32(torch.zeros(pad_to(Cc, 16)))
+        op = ops.make_conv(P, Ht.view(B, Cc, 1, N), out.view(B, 1, N, Cc), [(0, 0, 0, 0)], n_total=pad_to(Cc, 16),
+                           b_batched=True, out_space=(B, 1, N), scale=gs, shift=gz, residual=xt, name=p + ".pv")
+        self.ops.append(Op(p + ".pv", op.launch, flops=2.0 * B * N * N * Cc, kind="gemm"))
+        self.keep.append(op)
+        return out
+
+    # ---- execution ----------------------------------------------------------------------------
+    def run(self, stream: int = 0):
+        for op in self.ops:
+            op.fn(stream)
+
+    @property
+    def flops(self) -> float:
+        return sum(o.flops for o in self.ops) + self.head_flops
