@@ -133,3 +133,98 @@ def resize_plane_u8(img: np.ndarray, out_w: int, out_h: int, kernel: str = "spli
         t = np.einsum("hwc,ow->hoc", x, mh)
         o = np.einsum("ph,hoc->poc", mv, t)
     return np.clip(np.rint(o), 0, 255).astype(np.uint8)
+
+
+# ---- Pillow Image.resize (ImagingResample: separable, 8-bit fixed-point coefficients, u8 intermediate) ------
+# Used by BaseFilter._scale_to_square / _unsquare with BILINEAR (deoldify/filters.py:37-41,70-73) and by
+# colorizers/util.py:21-22 with BICUBIC.  Restated from Pillow's libImaging/Resample.c; pinned bit-exact
+# against the installed Pillow by tests/test_pixel_oracle.py.
+_PRECISION_BITS = 32 - 8 - 2
+
+
+def _bilinear_filter(x):
+    x = abs(x)
+    return 1.0 - x if x < 1.0 else 0.0
+
+
+def _bicubic_filter(x, a=-0.5):
+    x = abs(x)
+    if x < 1.0:
+        return ((a + 2.0) * x - (a + 3.0)) * x * x + 1
+    if x < 2.0:
+        return (((x - 5) * x + 8) * x - 4) * a
+    return 0.0
+
+
+_PIL_FILTERS = {"bilinear": (_bilinear_filter, 1.0), "bicubic": (_bicubic_filter, 2.0)}
+
+
+def pil_coeffs(in_size: int, out_size: int, filt: str = "bilinear"):
+    """(bounds [out,2] = (xmin, count), integer coefficients [out, ksize]) as Pillow's precompute_coeffs +
+    normalize_coeffs_8bpc build them (float64 weights, normalised, then rounded to 22-bit fixed point)."""
+    f, support0 = _PIL_FILTERS[filt]
+    scale = in_size / out_size
+    filterscale = max(scale, 1.0)
+    support = support0 * filterscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    bounds = np.zeros((out_size, 2), dtype=np.int64)
+    kk = np.zeros((out_size, ksize), dtype=np.int64)
+    ss = 1.0 / filterscale
+    for xx in range(out_size):
+        center = (xx + 0.5) * scale
+        xmin = int(center - support + 0.5)
+        if xmin < 0:
+            xmin = 0
+        xmax = int(center + support + 0.5)
+        if xmax > in_size:
+            xmax = in_size
+        xmax -= xmin
+        w = np.array([f((x + xmin - center + 0.5) * ss) for x in range(xmax)], dtype=np.float64)
+        ww = w.sum()
+        if ww != 0.0:
+            w = w / ww
+        for x in range(xmax):
+            v = w[x] * (1 << _PRECISION_BITS)
+            kk[xx, x] = int(v - 0.5) if v < 0 else int(v + 0.5)
+        bounds[xx] = (xmin, xmax)
+    return bounds, kk
+
+
+def _pil_pass(img: np.ndarray, out_size: int, axis: int, filt: str) -> np.ndarray:
+    """One separable pass along `axis` (0 = vertical, 1 = horizontal) on uint8 [H,W,C]."""
+    in_size = img.shape[axis]
+    bounds, kk = pil_coeffs(in_size, out_size, filt)
+    src = np.moveaxis(img.astype(np.int64), axis, 0)           # [in, ...]
+    out = np.empty((out_size,) + src.shape[1:], dtype=np.uint8)
+    for xx in range(out_size):
+        xmin, cnt = bounds[xx]
+        acc = np.tensordot(kk[xx, :cnt], src[xmin:xmin + cnt], axes=(0, 0)) + (1 << (_PRECISION_BITS - 1))
+        out[xx] = np.clip(acc >> _PRECISION_BITS, 0, 255)
+    return np.moveaxis(out, 0, axis)
+
+
+def pil_resize(img: np.ndarray, out_w: int, out_h: int, filt: str = "bilinear") -> np.ndarray:
+    """uint8 [H,W,C] -> uint8 [out_h,out_w,C]; horizontal pass first, then vertical, each only if the size
+    changes (Pillow skips identity passes), with a uint8 intermediate image."""
+    h, w = img.shape[:2]
+    x = img
+    if out_w != w:
+        x = _pil_pass(x, out_w, 1, filt)
+    if out_h != h:
+        x = _pil_pass(x, out_h, 0, filt)
+    return x
+
+
+def pil_blend(a: np.ndarray, b: np.ndarray, alpha: float) -> np.ndarray:
+    """PIL.Image.blend(a, b, alpha) (ModelImageRender, deoldify/visualize.py:129,135; image_weighted_merge,
+    vsslib/imfilters.py:113-124): a + alpha*(b-a) in float32; inside [0,1] the result is truncated, outside it is
+    clipped to [0,255] first."""
+    if alpha == 0.0:
+        return a.copy()
+    if alpha == 1.0:
+        return b.copy()
+    af, bf = a.astype(np.float32), b.astype(np.float32)
+    t = af + np.float32(alpha) * (bf - af)
+    if 0.0 <= alpha <= 1.0:
+        return t.astype(np.uint8)
+    return np.clip(t, 0, 255).astype(np.uint8)
