@@ -41,3 +41,25 @@ def havc_colorizer_frame(sd, frame: np.ndarray, render_factor: int = 24, kernel:
     if return_stages:
         return out, dict(small=small, model_img=model_img, colored=colored, up=up)
     return out
+
+
+def colorizer_filter(sd, img: np.ndarray, render_factor: int) -> np.ndarray:
+    """MasterFilter([ColorizerFilter]).filter(img, img, rf) (deoldify/filters.py:81-124) on a uint8 [H,W,3] image:
+    Pillow-BILINEAR squeeze to S x S, network, Pillow-BILINEAR back, luma transplant.  This is the path
+    ModelImageRender.get_transformed_image takes when it is handed a non-square image (BASELINE cfg1)."""
+    H, W = img.shape[:2]
+    S = render_factor * 16
+    sq = px.pil_resize(img, S, S, "bilinear")                          # _scale_to_square
+    model_img = model_process_square(sd, sq)                           # _transform + _model_process
+    raw = px.pil_resize(model_img, W, H, "bilinear")                   # _unsquare
+    return px.chroma_post_process(raw, img)                            # _post_process
+
+
+def model_image_render(sd_video, sd_other, img: np.ndarray, render_factor: int, video_weight: float = 0.5) -> np.ndarray:
+    """ModelImageRender.get_transformed_image (deoldify/visualize.py:118-137): the video net always runs;
+    'stable'/'artistic' blend a second net: Image.blend(img_other, img_video, video_weight)."""
+    v = colorizer_filter(sd_video, img, render_factor)
+    if sd_other is None:
+        return v
+    o = colorizer_filter(sd_other, img, render_factor)
+    return px.pil_blend(o, v, video_weight)

@@ -14,12 +14,12 @@
 //     in the 128-byte-swizzled K-major layout tcgen05.mma consumes directly;
 //   * one elected thread issues tcgen05.mma (M=128, N<=256, K=16, kind::f16, fp32 accumulate) into a
 //     double-buffered TMEM accumulator; tcgen05.commit releases smem stages / publishes accumulators;
-//   * four epilogue warps drain TMEM with tcgen05.ld and apply, in fp32,
+//   * eight epilogue warps drain TMEM with software-pipelined tcgen05.ld and apply, in fp32,
 //         +bias -> ReLU -> *scale+shift (eval BatchNorm) -> +residual -> ReLU
 //     then store fp16/bf16/fp32, optionally in PixelShuffle(2) order or to a strided sub-pixel phase.
 //
-// Warp roles (256 threads, 1 CTA/SM): warp0 = TMA producer, warp1 = MMA issuer, warp2 = TMEM
-// allocator, warps4-7 = epilogue (TMEM lane quarter = warp % 4).
+// Warp roles (384 threads, 1 CTA/SM): warp0 = TMA producer, warp1 = MMA issuer, warp2 = TMEM
+// allocator, warps4-11 = epilogue (TMEM lane quarter = warp % 4; two warps per quarter split the columns).
 #include "common.cuh"
 
 namespace havc {
@@ -28,7 +28,8 @@ static constexpr int kTileM = 128;
 static constexpr int kChunkK = 64;  // 64 x 16-bit = 128 B = one swizzle row
 static constexpr int kABytes = kTileM * kChunkK * 2;
 static constexpr int kMaxStages = 8;
-static constexpr int kThreads = 256;
+static constexpr int kThreads = 384;   // 4 control warps + 8 epilogue warps
+static constexpr int kMaxBN = 288;      // parameter staging rows (BN <= 272)
 static constexpr uint32_t kTmemCols = 512;
 
 struct ConvParams {
@@ -157,6 +158,27 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+// 32 accumulator columns (or the last 16 of a tile whose width is 16 mod 32)
+__device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t (&v)[32], int cols_left) {
+    if (cols_left >= 32) {
+        tmem_ld32(taddr, v);
+    } else {
+        uint32_t(&lo)[16] = *reinterpret_cast<uint32_t(*)[16]>(&v[0]);
+        tmem_ld16(taddr, lo);
+    }
+}
 __device__ __forceinline__ void tmem_ld_wait() {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -201,7 +223,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(tfull_bar(s), 1);
-            mbar_init(tempty_bar(s), 128);
+            mbar_init(tempty_bar(s), 256);
         }
         fence_barrier_init();
     }
@@ -292,14 +314,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             }
         }
     } else if (warp >= 4) {
-        // ===================== epilogue =====================
+        // ===================== epilogue (8 warps) =====================
+        // warp w owns TMEM lanes 32*(w%4)..+31 (hardware rule); the two warps that share a lane quarter
+        // split the accumulator columns in interleaved 32-column chunks.
         const int q = warp & 3;
+        const int half = (warp - 4) >> 2;
+        const int etid = threadIdx.x - 128;              // 0..255
         const int r = q * 32 + lane;
         const int rw = r % p.bw;
         const int rh = (r / p.bw) % p.bh;
         const int rb = r / (p.bw * p.bh);
+        float *sparams = reinterpret_cast<float *>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));
         int as = 0;
         uint32_t aphase = 0;
+        int pbuf = 0;
+        const int nchunks = (p.BN + 31) >> 5;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             int t = tile;
             const int nt = t % p.tiles_n; t /= p.tiles_n;
@@ -309,89 +338,117 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             const int n0 = nt * p.BN;
             const int ow = wt * p.bw + rw, oh = ht * p.bh + rh, ob = bt * p.bb + rb;
             const bool valid = (ow < p.out_W) && (oh < p.out_H) && (ob < p.out_B);
+
+            // stage this tile's per-column parameters in shared memory (double-buffered by tile parity)
+            float *sb = sparams + pbuf * (3 * kMaxBN);
+            for (int i = etid; i < p.BN; i += 256) {
+                const int n = n0 + i;
+                const bool in = n < p.N_total;
+                sb[i] = (in && p.bias) ? __ldg(p.bias + n) : 0.f;
+                sb[kMaxBN + i] = (in && p.scale) ? __ldg(p.scale + n) : 1.f;
+                sb[2 * kMaxBN + i] = (in && p.shift) ? __ldg(p.shift + n) : 0.f;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            pbuf ^= 1;
+
             const uint8_t *res_row = nullptr;
-            if (p.residual != nullptr)
-                res_row = reinterpret_cast<const uint8_t *>(p.residual) +
-                          2ll * (ob * p.rsb + oh * p.rsh + ow * p.rsw);
+            if (p.residual != nullptr && valid)
+                res_row = reinterpret_cast<const uint8_t *>(p.residual) + 2ll * (ob * p.rsb + oh * p.rsh + ow * p.rsw);
 
             mbar_wait(tfull_bar(as), aphase);
             tc_fence_after();
             const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * p.acc_stride;
-            for (int c0 = 0; c0 < p.BN; c0 += 16) {
-                uint32_t v[16];
-                __syncwarp();
-                tmem_ld16(tbase + c0, v);
-                tmem_ld_wait();
+
+            uint32_t va[32], vb[32];
+            // One chunk: wait for its TMEM load, kick off the load of the chunk after next into `vn`,
+            // then run the fp32 epilogue on `vc` and store.
+            auto process = [&](int ci, uint32_t(&vc)[32], uint32_t(&vn)[32]) {
+                const int c0 = ci * 32;
+                uint4 rres[4];
                 const int n = n0 + c0;
-                if (n >= p.N_total || !valid) continue;
-                float y[16];
+                const bool do_res = res_row != nullptr && n < p.N_total;
+                if (do_res) {  // residual prefetch: global loads overlap the TMEM load latency
 #pragma unroll
-                for (int j = 0; j < 16; ++j) y[j] = __uint_as_float(v[j]);
-                if (p.bias != nullptr) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) y[j] += __ldg(p.bias + n + j);
-                }
-                if (p.relu1) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) y[j] = fmaxf(y[j], 0.f);
-                }
-                if (p.scale != nullptr) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        y[j] = fmaf(y[j], __ldg(p.scale + n + j), __ldg(p.shift + n + j));
-                }
-                // destination channel / pixel
-                int chan = n, py = oh * p.up + p.oy, px = ow * p.up + p.ox;
-                if (p.shuffle) {
-                    const int g = n / p.group_n;
-                    chan = n - g * p.group_n;
-                    py = oh * 2 + (g >> 1);
-                    px = ow * 2 + (g & 1);
-                }
-                if (chan >= p.c_store) continue;
-                const bool hi_ok = (chan + 8) < p.c_store;  // second 8-channel group in range
-                if (res_row != nullptr) {
-                    const uint4 r0 = __ldg(reinterpret_cast<const uint4 *>(res_row + 2 * n));
-                    const uint32_t rr0[4] = {r0.x, r0.y, r0.z, r0.w};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float2 f = unpack2(rr0[j], p.dtype);
-                        y[2 * j] += f.x;
-                        y[2 * j + 1] += f.y;
+                    for (int g = 0; g < 4; ++g) {
+                        rres[g] = make_uint4(0, 0, 0, 0);
+                        if (n + 8 * g < p.c_store && c0 + 8 * g < p.BN)
+                            rres[g] = __ldg(reinterpret_cast<const uint4 *>(res_row + 2 * (n + 8 * g)));
                     }
-                    if (hi_ok) {
-                        const uint4 r1 = __ldg(reinterpret_cast<const uint4 *>(res_row + 2 * n + 16));
-                        const uint32_t rr1[4] = {r1.x, r1.y, r1.z, r1.w};
+                }
+                tmem_ld_wait();
+                const int nxt = ci + 2;
+                if (nxt < nchunks) {
+                    __syncwarp();
+                    tmem_ld_chunk(tbase + nxt * 32, vn, p.BN - nxt * 32);
+                }
+                if (!valid) return;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float2 f = unpack2(rr1[j], p.dtype);
-                            y[8 + 2 * j] += f.x;
-                            y[8 + 2 * j + 1] += f.y;
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int cc = c0 + 16 * hh;       // column within the tile
+                    const int nn = n0 + cc;            // GEMM column
+                    if (cc >= p.BN || nn >= p.N_total) continue;
+                    float y[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) y[j] = __uint_as_float(vc[16 * hh + j]) + sb[cc + j];
+                    if (p.relu1) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) y[j] = fmaxf(y[j], 0.f);
+                    }
+                    if (p.scale != nullptr) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) y[j] = fmaf(y[j], sb[kMaxBN + cc + j], sb[2 * kMaxBN + cc + j]);
+                    }
+                    int chan = nn, py = oh * p.up + p.oy, px = ow * p.up + p.ox;
+                    if (p.shuffle) {
+                        const int g = nn / p.group_n;
+                        chan = nn - g * p.group_n;
+                        py = oh * 2 + (g >> 1);
+                        px = ow * 2 + (g & 1);
+                    }
+                    if (chan >= p.c_store) continue;
+                    const bool hi_ok = (chan + 8) < p.c_store;
+                    if (do_res) {
+                        const uint32_t rr[8] = {rres[2 * hh].x, rres[2 * hh].y, rres[2 * hh].z, rres[2 * hh].w,
+                                                rres[2 * hh + 1].x, rres[2 * hh + 1].y, rres[2 * hh + 1].z,
+                                                rres[2 * hh + 1].w};
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float2 f = unpack2(rr[j], p.dtype);
+                            y[2 * j] += f.x;
+                            y[2 * j + 1] += f.y;
                         }
                     }
-                }
-                if (p.relu2) {
+                    if (p.relu2) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) y[j] = fmaxf(y[j], 0.f);
-                }
-                const long long opix = ob * p.osb + py * p.osh + px * p.osw + chan;
-                if (p.out_dtype == HAVC_F32) {
-                    float4 *dst = reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out) + opix);
-                    dst[0] = make_float4(y[0], y[1], y[2], y[3]);
-                    dst[1] = make_float4(y[4], y[5], y[6], y[7]);
-                    if (hi_ok) {
-                        dst[2] = make_float4(y[8], y[9], y[10], y[11]);
-                        dst[3] = make_float4(y[12], y[13], y[14], y[15]);
+                        for (int j = 0; j < 16; ++j) y[j] = fmaxf(y[j], 0.f);
                     }
-                } else {
-                    uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<uint16_t *>(p.out) + opix);
-                    const int od = p.out_dtype;
-                    dst[0] = make_uint4(pack2(y[0], y[1], od), pack2(y[2], y[3], od),
-                                        pack2(y[4], y[5], od), pack2(y[6], y[7], od));
-                    if (hi_ok)
-                        dst[1] = make_uint4(pack2(y[8], y[9], od), pack2(y[10], y[11], od),
-                                            pack2(y[12], y[13], od), pack2(y[14], y[15], od));
+                    const long long opix = ob * p.osb + py * p.osh + px * p.osw + chan;
+                    if (p.out_dtype == HAVC_F32) {
+                        float4 *dst = reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out) + opix);
+                        dst[0] = make_float4(y[0], y[1], y[2], y[3]);
+                        dst[1] = make_float4(y[4], y[5], y[6], y[7]);
+                        if (hi_ok) {
+                            dst[2] = make_float4(y[8], y[9], y[10], y[11]);
+                            dst[3] = make_float4(y[12], y[13], y[14], y[15]);
+                        }
+                    } else {
+                        uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<uint16_t *>(p.out) + opix);
+                        const int od = p.out_dtype;
+                        dst[0] = make_uint4(pack2(y[0], y[1], od), pack2(y[2], y[3], od), pack2(y[4], y[5], od),
+                                            pack2(y[6], y[7], od));
+                        if (hi_ok)
+                            dst[1] = make_uint4(pack2(y[8], y[9], od), pack2(y[10], y[11], od),
+                                                pack2(y[12], y[13], od), pack2(y[14], y[15], od));
+                    }
                 }
+            };
+            if (half < nchunks) {
+                __syncwarp();
+                tmem_ld_chunk(tbase + half * 32, va, p.BN - half * 32);
+            }
+            for (int ci = half; ci < nchunks; ci += 4) {
+                process(ci, va, vb);
+                if (ci + 2 < nchunks) process(ci + 2, vb, va);
             }
             tc_fence_before();
             mbar_arrive(tempty_bar(as));
@@ -534,7 +591,7 @@ extern "C" int havc_conv_gemm(const havc_conv_desc *d, void *stream) {
     p.acc_stages = (2 * d->BN <= (int)kTmemCols) ? 2 : 1;
     p.acc_stride = d->BN;
     p.stage_bytes = kABytes + d->BN * 128;
-    int stages = (227 * 1024 - 1024 - 256) / (int)p.stage_bytes;
+    int stages = (227 * 1024 - 1024 - 256 - 2 * 3 * kMaxBN * (int)sizeof(float)) / (int)p.stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     HAVC_CHECK_ARG(stages >= 2, "havc_conv_gemm: tile too large for shared memory");
     p.num_stages = stages;
@@ -574,7 +631,7 @@ extern "C" int havc_conv_gemm(const havc_conv_desc *d, void *stream) {
     }
     if (d->b_batched) HAVC_CHECK_ARG(d->box_b == 1, "havc_conv_gemm: b_batched=1 needs box_b=1");
 
-    const size_t smem = (size_t)p.num_stages * p.stage_bytes + 1024 + 256;
+    const size_t smem = (size_t)p.num_stages * p.stage_bytes + 1024 + 256 + 2 * 3 * kMaxBN * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
         HAVC_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
