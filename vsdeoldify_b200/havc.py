@@ -1,0 +1,231 @@
+"""The reference-facing plugin surface: HAVC_main / HAVC_colorizer / HAVC_deoldify / HAVC_ddeoldify.
+
+Same names, argument order, defaults and error behaviour as the reference for the per-frame colorization
+path (vsdeoldify/__init__.py:101-109 HAVC_main, :2290-2523 HAVC_colorizer, :3612-3628 HAVC_ddeoldify); clips in,
+clips out, frame properties passed through bit-exactly (every output frame is `f.copy()` of the input frame with
+its planes overwritten, like vsslib/vsutils.py:92-95), scene-change gating as vsslib/vsmodels.py:221-224.
+
+What differs is underneath: frames are not colourised one by one in a `std.ModifyFrame` callback that calls
+torch; the returned clip pulls B consecutive source frames at a time and hands them to the per-GPU
+`DeoldifyEngine` (one CUDA graph of libhavc_b200 kernels per batch).  Out-of-order frame requests are served
+from a small batch cache, so any access pattern yields the same frames.
+
+Not built (raise `vs.Error` instead of silently doing something else): DDColor (external `vsddcolor`, method 1 /
+ddcolor models 0-1), the exemplar models, scene detection itself (`sc_threshold`/`sc_min_freq` > 0 require
+the `_SceneChangePrev` props to be present on the input clip already), CPU mode (device_index=99).
+"""
+from __future__ import annotations
+
+import math
+import os
+import threading
+from collections import OrderedDict
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import vs_shim
+from .constants import (DEF_ALM_p, DEF_ARTISTIC_WEIGHT, DEF_CMC_p, DEF_CRT_p, DEF_LMM_p, DEF_STABLE_WEIGHT, DEF_THT_BLACK,
+                        DEF_THT_WHITE, DEF_TWEAK_p)
+
+vs = vs_shim.get_vs()
+
+package_dir = os.path.dirname(os.path.realpath(__file__))
+model_dir = os.path.join(package_dir, "models")
+
+_WEIGHT_FILES = {0: "ColorizeVideo_gen", 1: "ColorizeStable_gen", 2: "ColorizeArtistic_gen"}
+_REGISTERED: Dict[str, Dict[str, torch.Tensor]] = {}
+_BATCH = int(os.environ.get("HAVC_B200_BATCH", "8"))
+_DTYPE = {"fp16": torch.float16, "bf16": torch.bfloat16}[os.environ.get("HAVC_B200_DTYPE", "fp16")]
+
+
+def HAVC_LogMessage(level: int, *args):
+    """vsslib/vsutils.py:42-47: level EXCEPTION raises vs.Error, anything else goes to the VapourSynth log."""
+    text = " ".join(map(str, args))
+    if level == "EXCEPTION":
+        raise vs.Error(text)
+    vs.core.log_message(int(level), text)
+
+
+def _raise(text: str):
+    raise vs.Error(text)
+
+
+def register_state_dict(weights_name: str, sd: Dict[str, torch.Tensor]):
+    """Provide weights in memory (tests / synthetic weights) instead of `<models>/<weights_name>.pth`."""
+    _REGISTERED[weights_name] = sd
+
+
+def load_state_dict(weights_name: str, models_dir: str = model_dir) -> Dict[str, torch.Tensor]:
+    """Learner.load semantics (vsdeoldify/fastai/basic_train.py:264-286): `<dir>/<name>.pth`, either
+    {'model': sd, 'opt': ...} or a bare state-dict."""
+    if weights_name in _REGISTERED:
+        return _REGISTERED[weights_name]
+    path = os.path.join(models_dir, weights_name + ".pth")
+    if not os.path.exists(path) or os.path.getsize(path) == 0:
+        _raise("HAVC_colorizer: model files have not been downloaded.")      # vsdeoldify/__init__.py:2477
+    state = torch.load(path, map_location="cpu", weights_only=True)
+    return state["model"] if isinstance(state, dict) and "model" in state else state
+
+
+class _ColorizedClip:
+    """frame_fn of the output clip: batches source frames through the engine, caches results by frame number."""
+
+    def __init__(self, clip, engines, video_weight: float, scenechange: bool, batch: int):
+        self.clip, self.engines, self.video_weight = clip, engines, video_weight
+        self.scenechange, self.B = scenechange, batch
+        self.cache: "OrderedDict[int, object]" = OrderedDict()
+        self.lock = threading.Lock()
+
+    def _planes(self, f) -> np.ndarray:
+        return np.stack([np.asarray(f[p]) for p in range(3)])
+
+    def __call__(self, n: int):
+        with self.lock:
+            if n in self.cache:
+                return self.cache[n]
+            n1 = min(n + self.B, self.clip.num_frames)
+            srcs = [self.clip.get_frame(i) for i in range(n, n1)]
+            batch = np.stack([self._planes(f) for f in srcs])
+            skip = None
+            if self.scenechange:    # vsslib/vsmodels.py:221-224: only scene-change frames are colourised
+                skip = np.array([not (i == 0 or f.props.get("_SceneChangePrev", 0) == 1) for i, f in zip(range(n, n1), srcs)])
+            out = self.engines[0].colorize_batch(batch, skip=skip)
+            if len(self.engines) > 1:   # 'stable'/'artistic': Image.blend(other, video, video_weight), visualize.py:129,135
+                other = self.engines[1].colorize_batch(batch, skip=skip)
+                out = _pil_blend(other, out, self.video_weight)
+            for i, f in zip(range(n, n1), srcs):
+                g = f.copy()                              # all props of the source frame survive (vsutils.py:92-95)
+                for p in range(3):
+                    np.copyto(np.asarray(g[p]), out[i - n, p])
+                self.cache[i] = g
+            while len(self.cache) > 4 * self.B:
+                self.cache.popitem(last=False)
+            return self.cache[n]
+
+
+def _pil_blend(a: np.ndarray, b: np.ndarray, alpha: float) -> np.ndarray:
+    """PIL.Image.blend(a, b, alpha): trunc(a + alpha*(b - a)) in float32."""
+    if alpha == 0.0:
+        return a
+    if alpha == 1.0:
+        return b
+    af = a.astype(np.float32)
+    return (af + np.float32(alpha) * (b.astype(np.float32) - af)).astype(np.uint8)
+
+
+def HAVC_colorizer(
+        clip, method: int = 2, mweight: float = 0.4, deoldify_p: Sequence = (0, 24, 1.0, 0.0),
+        ddcolor_p: Sequence = (1, 24, 1.0, 0.0, True), ddtweak: Sequence[bool] = (False, False, False),
+        ddtweak_p: Sequence = (DEF_TWEAK_p, "300:360|0.8,0.1"),
+        cmc_p: Sequence = DEF_CMC_p, lmm_p: Sequence = DEF_LMM_p, alm_p: Sequence = DEF_ALM_p,
+        crt_p: Sequence = DEF_CRT_p, cmb_sw: bool = False, sc_threshold: float = 0.0, sc_tht_offset: int = 1,
+        sc_min_freq: int = 0, sc_tht_ssim: float = 0.0, sc_normalize: bool = False, sc_min_int: int = 1,
+        sc_tht_white: float = DEF_THT_WHITE, sc_tht_black: float = DEF_THT_BLACK, device_index: int = 0,
+        torch_dir: str = model_dir, debug_level: int = 0):
+    """Drop-in for vsdeoldify.HAVC_colorizer (vsdeoldify/__init__.py:2290-2523) on the DeOldify path."""
+    if device_index == 99:
+        _raise("HAVC_colorizer: CPU mode (device_index=99) is not available in the B200 build (no CPU fallback)")
+    if not torch.cuda.is_available():
+        _raise("HAVC_colorizer: CUDA is not available")                                   # :2441
+    if clip.format.id != vs.RGB24.id if hasattr(vs.RGB24, "id") else clip.format.id != vs.RGB24:
+        _raise("HAVC_colorizer: only RGB24 input is handled by the B200 build (convert_format_RGB24 is a 'next' row)")
+    if sc_threshold < 0:
+        _raise("HAVC_colorizer: sc_threshold must be >= 0")                              # :2447
+    if sc_min_freq < 0:
+        _raise("HAVC_colorizer: sc_min_freq must be >= 0")                               # :2450
+    merge_weight = 0.0 if method == 0 else (1.0 if method == 1 else mweight)              # :2452-2462
+    if merge_weight == 0.0:
+        method = 0
+    elif merge_weight == 1.0:
+        method = 1
+    deoldify_model, deoldify_rf, deoldify_sat, deoldify_hue = deoldify_p[:4]
+    ddcolor_model, ddcolor_rf = ddcolor_p[0], ddcolor_p[1]
+    if device_index > 7:
+        _raise("HAVC_colorizer: wrong device_index, choices are: GPU0...GPU7, CPU=99")    # :2480
+    if ddcolor_rf != 0 and ddcolor_rf not in range(10, 65):
+        _raise("HAVC_colorizer: ddcolor render_factor must be between: 10-64")            # :2483
+    if method != 0:
+        _raise("HAVC_colorizer: only method=0 (DeOldify) is built so far; the Zhang/DDColor side and the vsslib merges "
+               "are the next rows of the hot-path table")
+    if deoldify_sat != 1.0 or deoldify_hue != 0.0:
+        _raise("HAVC_colorizer: vs_tweak (sat/hue != identity) is not built yet")
+    if ddcolor_rf == 0:
+        ddcolor_rf = min(max(math.trunc(0.4 * clip.width / 16), 16), 32)                  # :2492
+    scenechange = not (sc_threshold == 0 and sc_min_freq == 0)                            # :2494
+    # frame_size: HAVC_colorizer:2502 uses max(ddcolor_rf, deoldify_rf) even when method == 0
+    frame_size = min(max(ddcolor_rf, deoldify_rf) * 16, clip.width)
+    from .engine import DeoldifyEngine
+    dev = f"cuda:{device_index}"
+    names = [_WEIGHT_FILES[0]] + ([_WEIGHT_FILES[deoldify_model]] if deoldify_model in (1, 2) else [])
+    engines = [DeoldifyEngine(load_state_dict(nm, torch_dir or model_dir), clip.width, clip.height, render_factor=deoldify_rf,
+                              frame_size=frame_size, batch=_BATCH, dtype=_DTYPE, device=dev) for nm in names]
+    weight = {1: DEF_STABLE_WEIGHT, 2: DEF_ARTISTIC_WEIGHT}.get(deoldify_model, 0.0)
+    fn = _ColorizedClip(clip, engines, weight, scenechange, _BATCH)
+    return vs_shim.VideoNode(clip.num_frames, clip.width, clip.height, clip.format, fn, clip.fps_num, clip.fps_den) \
+        if vs is vs_shim else _wrap_real_vs(clip, fn)
+
+
+def _wrap_real_vs(clip, fn):
+    """Real VapourSynth: serve frames through std.ModifyFrame; the selector ignores `f` and returns our frame."""
+    return clip.std.ModifyFrame(clips=[clip], selector=lambda n, f: fn(n))
+
+
+def HAVC_deoldify(clip, model: int = 0, render_factor: int = 24, sat: float = 1.0, hue: float = 0.0, **kw):
+    """DeOldify only: HAVC_colorizer(method=0) (vsdeoldify/__init__.py:2452-2462).  The name is in the north star;
+    the reference tree has no function of this name."""
+    return HAVC_colorizer(clip, method=0, deoldify_p=[model, render_factor, sat, hue], **kw)
+
+
+def HAVC_ddeoldify(
+        clip, method: int = 2, mweight: float = 0.4, deoldify_p: Sequence = (0, 24, 1.0, 0.0),
+        ddcolor_p: Sequence = (1, 24, 1.0, 0.0, True), ddtweak: bool = False,
+        ddtweak_p: Sequence = (DEF_TWEAK_p, "300:360|0.8,0.1"),
+        cmc_tresh: float = 0.2, lmm_p: Sequence = (0.2, 0.8, 1.0), alm_p: Sequence = (0.8, 1.0, 0.15), cmb_sw: bool = False,
+        sc_threshold: float = 0.0, sc_tht_offset: int = 1, sc_min_freq: int = 0, sc_tht_ssim: float = 0.0,
+        sc_normalize: bool = False, sc_min_int: int = 1, sc_tht_white: float = DEF_THT_WHITE,
+        sc_tht_black: float = DEF_THT_BLACK, device_index: int = 0, torch_dir: str = model_dir, sc_debug: bool = False):
+    """Deprecated positional alias, same mapping as vsdeoldify/__init__.py:3612-3628."""
+    vs.core.log_message(vs.MESSAGE_TYPE_WARNING,
+                        "Warning: HAVC_ddeoldify is deprecated and may be removed in the future, please use 'HAVC_colorizer' instead.")
+    debug_level = 2 if sc_debug else 0
+    return HAVC_colorizer(clip, method, mweight, deoldify_p, ddcolor_p, [ddtweak, False, False], ddtweak_p, [cmc_tresh], lmm_p,
+                          alm_p, DEF_CRT_p, cmb_sw, sc_threshold, sc_tht_offset, sc_min_freq, sc_tht_ssim, sc_normalize,
+                          sc_min_int, sc_tht_white, sc_tht_black, device_index, torch_dir, debug_level)
+
+
+# ---- HAVC_main: preset tables of vsdeoldify/havc_utils.py:335-443 (image-model branch only) -------------------------
+_PRESETS = ['placebo', 'veryslow', 'slower', 'slow', 'medium', 'fast', 'faster', 'veryfast']
+_PRESET_RF = [32, 32, 32, 28, 24, 22, 20, 16]
+_DEOLDIFY_MODELS = ["video", "stable", "artistic"]
+
+
+def _get_render_factor(Preset: str) -> int:
+    try:
+        return _PRESET_RF[_PRESETS.index(Preset.lower())]
+    except ValueError:
+        _raise("HAVC_main: Preset choice is invalid for '" + str(Preset) + "'")
+
+
+def HAVC_main(clip, Preset: str = 'Medium', FrameInterp: int = 0, ColorModel: str = 'Video+Artistic', CombMethod: str = 'Simple',
+              VideoTune: str = 'Stable', ColorFix: str = 'Magenta/Violet', ColorTune: str = 'Light', ColorMap: str = 'None',
+              ColorTemp: str = 'None', BlackWhiteTune: str = 'None', BlackWhiteMode: int = 0, BlackWhiteBlend: bool = True,
+              EnableDeepEx: bool = False, enable_fp16: bool = True, debug_level: int = 0, device_index: int = 0, **kw):
+    """Drop-in for vsdeoldify.HAVC_main (vsdeoldify/__init__.py:101-330) restricted to the per-frame DeOldify
+    branch: ColorModel 'DeOldify(Video|Stable|Artistic)', every post filter at its 'None' setting."""
+    rf = _get_render_factor(Preset)
+    cm = ColorModel.lower()
+    if EnableDeepEx or FrameInterp != 0:
+        _raise("HAVC_main: exemplar-based models are sequential and out of scope of the B200 build")
+    if "deoldify" not in cm or "+" in cm:
+        _raise("HAVC_main: ColorModel '" + ColorModel + "' needs the DDColor/Zhang side, which is not built yet; "
+               "use 'DeOldify(Video)', 'DeOldify(Stable)' or 'DeOldify(Artistic)'")
+    name = cm.replace("deoldify", "").replace("(", "").replace(")", "")
+    if name not in _DEOLDIFY_MODELS:
+        _raise("HAVC_main: ColorModel choice is invalid for '" + ColorModel + "'")
+    for label, v in (("ColorMap", ColorMap), ("ColorTemp", ColorTemp), ("BlackWhiteTune", BlackWhiteTune)):
+        if str(v).lower() != "none":
+            _raise(f"HAVC_main: {label} post filters are not built yet (HAVC_stabilizer is row N1 of the scope table)")
+    return HAVC_colorizer(clip, method=0, deoldify_p=[_DEOLDIFY_MODELS.index(name), rf, 1.0, 0.0],
+                          ddcolor_p=[1, rf, 1.0, 0.0, enable_fp16], device_index=device_index, debug_level=debug_level)
