@@ -109,7 +109,8 @@ int havc_affine_act(const void *in, void *out, long long n_pixels, int C, int in
 int havc_blur2x2(const void *in, void *out, int B, int H, int W, int C, int out_pix_stride, int dtype, void *stream);
 /* Row soft-max of fp32 attention logits -> 16-bit probabilities (F.softmax(.., dim=1) of
  * vsdeoldify/fastai/layers.py:94, stored transposed so the reduction runs along contiguous rows). */
-int havc_softmax_rows(const float *in, void *out, long long rows, int cols, int out_dtype, void *stream);
+int havc_softmax_rows(const float *in, void *out, long long rows, int cols, int in_stride, int out_stride,
+                      int out_dtype, void *stream);
 
 /* ---- frame pre / post pixel passes (planar u8 RGB frames [B][3][H][W]) ----------------------- */
 
@@ -125,9 +126,11 @@ int havc_pre_vertical(const float *in, uint8_t *rgb_small, void *x, int B, int H
 /* Network head: 1x1 conv 259->3 + SigmoidRange(-3,3) (unet.py:276-281), de-normalise, clamp, *255, truncate
  * to u8 (filters.py:64-67), and — if transplant — ColorizerFilter._post_process (filters.py:100-110) at S x S
  * against rgb_small.  res: [B,S,S,Cs] 16-bit; w11: fp32 [3][Cs]; colored: u8 [B][3][S][S];
- * net_out (optional): fp32 [B][3][S][S] network output for parity tests. */
+ * net_out (optional): fp32 [B][3][S][S] network output for parity tests; skip (optional): u8 [B], 1 = the
+ * scene-change gate of vsslib/vsmodels.py:221-224 returned this frame uncoloured (colored := rgb_small). */
 int havc_head(const void *res, int Cs, const float *w11, const float *b11, const uint8_t *rgb_small,
-              uint8_t *colored, float *net_out, int B, int S, int dtype, int transplant, void *stream);
+              uint8_t *colored, float *net_out, const uint8_t *skip, int B, int S, int dtype, int transplant,
+              void *stream);
 /* Vertical pass of the resize back to W x H fused with vs_recover_clip_luma / chroma_post_process
  * (vsdeoldify/vsslib/vsfilters.py:863-899, imfilters.py:312-321): keep the luma of `orig`, the chroma of the
  * upscaled colour image (OpenCV Q14 8-bit YUV).  in: float [B][3][S][W]; orig/out: u8 [B][3][H][W]. */

@@ -1,0 +1,178 @@
+"""CPU tests of the host-side logic: weight packing / tap tables / concat layout (checked by emulating the
+implicit GEMM in plain torch and comparing with F.conv2d), tile/box heuristics, resampling tables, BN folding,
+frame partitioning (incl. a world_size-2 gloo run)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def emulate_conv(srcs, wp, taps, c1_off, out_hw, phase_split=False):
+    """Reference semantics of havc_conv_gemm's mainloop in torch: srcs NHWC (or [P,B,H,W,C]) fp32, wp [rows,taps,cin]."""
+    rows = wp.shape[0]
+    B = srcs[0].shape[-4]
+    H, W = out_hw
+    acc = torch.zeros(B, H, W, rows)
+    for (dh, dw, p, wi) in taps:
+        off = 0
+        for si, s in enumerate(srcs):
+            x = s[p] if s.dim() == 5 else s
+            C = x.shape[-1]
+            xp = F.pad(x, (0, 0, 8, 8, 8, 8))                                   # zero fill outside the image (TMA OOB)
+            win = xp[:, 8 + dh:8 + dh + H, 8 + dw:8 + dw + W, :]
+            wsl = wp[:, wi, off:off + C] if si == 0 else wp[:, wi, c1_off:c1_off + C]
+            acc += torch.einsum("bhwc,nc->bhwn", win, wsl)
+            off += C
+    return acc
+
+
+@pytest.mark.parametrize("cins,ks,dil", [([64], 3, 1), ([96, 40], 3, 1), ([24], 1, 1), ([16], 3, 2), ([300, 3], 3, 1)])
+def test_pack_and_taps_stride1(cins, ks, dil):
+    from vsdeoldify_b200 import ops
+    torch.manual_seed(0)
+    B, H, W, Cout = 2, 9, 11, 20
+    xs = [torch.randn(B, c, H, W) for c in cins]
+    w = torch.randn(Cout, sum(cins), ks, ks)
+    ref = F.conv2d(torch.cat(xs, 1), w, padding=dil * (ks - 1) // 2, dilation=dil)
+    wp, meta = ops.pack_conv_weight(w, cins, dtype=torch.float32)
+    srcs = []
+    for x, c in zip(xs, cins):
+        t = torch.zeros(B, H, W, ops.pad_to(c, 8))
+        t[..., :c] = x.permute(0, 2, 3, 1)
+        srcs.append(t)
+    got = emulate_conv(srcs, wp, ops.taps_for(ks, dil), meta["c1_off"], (H, W))
+    assert torch.allclose(got[..., :Cout].permute(0, 3, 1, 2), ref, atol=1e-4)
+    assert (got[..., Cout:] == 0).all()
+
+
+@pytest.mark.parametrize("ks", [1, 3])
+def test_taps_stride2_phase_split(ks):
+    from vsdeoldify_b200 import ops
+    torch.manual_seed(1)
+    B, H, W, Cin, Cout = 2, 12, 10, 16, 8
+    x = torch.randn(B, Cin, H, W)
+    w = torch.randn(Cout, Cin, ks, ks)
+    ref = F.conv2d(x, w, stride=2, padding=(ks - 1) // 2)
+    xn = x.permute(0, 2, 3, 1)
+    ph = torch.stack([xn[:, a::2, b::2] for a in range(2) for b in range(2)], 0)
+    wp, meta = ops.pack_conv_weight(w, dtype=torch.float32)
+    taps = ops.taps_stride2(ks) if ks > 1 else [(0, 0, 0, 0)]
+    got = emulate_conv([ph], wp, taps, 0, (H // 2, W // 2))
+    assert torch.allclose(got[..., :Cout].permute(0, 3, 1, 2), ref, atol=1e-4)
+
+
+def test_shuffle_row_order_matches_pixel_shuffle():
+    from vsdeoldify_b200 import ops
+    torch.manual_seed(2)
+    B, H, W, Cin, Cout = 1, 4, 5, 8, 4 * 6
+    x = torch.randn(B, Cin, H, W)
+    w = torch.randn(Cout, Cin, 1, 1)
+    ref = F.pixel_shuffle(F.conv2d(x, w), 2)                         # [B, 6, 2H, 2W]
+    wp, meta = ops.pack_conv_weight(w, dtype=torch.float32, shuffle=True)
+    acc = emulate_conv([x.permute(0, 2, 3, 1).contiguous()], wp, [(0, 0, 0, 0)], 0, (H, W))
+    gn, cg = meta["group_n"], meta["cg"]
+    out = torch.zeros(B, 2 * H, 2 * W, cg)
+    for g in range(4):                                               # the kernel's store rule
+        out[:, (g >> 1)::2, (g & 1)::2, :] = acc[..., g * gn:g * gn + cg]
+    assert torch.allclose(out.permute(0, 3, 1, 2), ref, atol=1e-5)
+    v = torch.arange(Cout, dtype=torch.float32)
+    pv = ops.pack_cols(v, meta["rows"], -1.0, meta)
+    assert pv[0] == 0 and pv[1] == 4 and pv[gn] == 1                  # row g*gn + c <- channel c*4 + g
+
+
+def test_choose_box_and_bn():
+    from vsdeoldify_b200 import ops
+    for (W, H, B) in [(384, 384, 8), (12, 12, 8), (24, 24, 8), (15, 15, 4), (2, 2, 2), (48, 48, 1)]:
+        bw, bh, bb = ops.choose_box(W, H, B)
+        assert bw * bh * bb == 128
+        tiles = -(-W // bw) * -(-H // bh) * -(-B // bb)
+        assert tiles * 128 >= W * H * B
+    assert ops.choose_box(12, 12, 8) == (4, 4, 8)                     # 3x3 boxes of 4x4 over 8 images: no waste
+    assert ops.choose_bn(272, 9216) == 272 and ops.choose_bn(256, 10) == 256
+    assert ops.choose_bn(4096, 9) in (64, 128, 256) and 4096 % ops.choose_bn(4096, 9) == 0
+    assert ops.choose_bn(320, 9216) == 160                            # artistic res_block: 2 x 160, not 5 x 64
+
+
+def test_resample_tables_match_oracle_matrix():
+    from oracle import pixel_oracle as px
+    from vsdeoldify_b200 import resample
+    for src, dst in [(1920, 384), (384, 1920), (1080, 384), (384, 1080), (64, 64), (100, 37)]:
+        start, w = resample.build_tables(src, dst)
+        dense = np.zeros((dst, src))
+        for o in range(dst):
+            for t in range(w.shape[1]):
+                if start[o] + t < src:
+                    dense[o, start[o] + t] += w[o, t]
+        assert np.abs(dense - px.resize_matrix(src, dst)).max() < 1e-6
+        assert (start >= 0).all() and (start + w.shape[1] <= src + w.shape[1]).all()
+
+
+def test_bn_and_spectral_fold_match_torch():
+    from oracle import synth_weights, unet_oracle
+    from vsdeoldify_b200 import unet
+    sd = synth_weights.make_unet_state_dict("deep", 7, calibrate=False)
+    for p in ("layers.3.0.0", "layers.8.conv.0", "layers.10.layers.0.0", "layers.0.0"):
+        assert torch.allclose(unet.folded_weight(sd, p), unet_oracle.conv_weight(sd, p), rtol=1e-5, atol=1e-7)
+    sd["layers.1.running_mean"] = torch.randn(512)
+    sd["layers.1.running_var"] = torch.rand(512) + 0.1
+    x = torch.randn(2, 512, 3, 3)
+    sc, sh = unet.bn_affine(sd, "layers.1")
+    ref = F.batch_norm(x, sd["layers.1.running_mean"], sd["layers.1.running_var"], sd["layers.1.weight"], sd["layers.1.bias"],
+                       False, 0.0, 1e-5)
+    assert torch.allclose(x * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1), ref, atol=1e-5)
+
+
+def test_block_partition_properties():
+    from vsdeoldify_b200 import partition
+    for n in (0, 1, 7, 2000, 2001):
+        for world in (1, 2, 3, 4, 8):
+            seen = []
+            for r in range(world):
+                s, e = partition.block_range(n, r, world)
+                assert 0 <= s <= e <= n
+                seen += list(range(s, e))
+                for f in range(s, e):
+                    assert partition.owner_of(f, n, world) == r
+            assert seen == list(range(n))                             # disjoint, complete, in order
+    assert list(partition.batches(3, 20, 8)) == [(3, 11), (11, 19), (19, 20)]
+
+
+def _gloo_worker(rank, world, port, n_frames, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from vsdeoldify_b200 import partition
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    s, e = partition.block_range(n_frames, rank, world)
+    mine = torch.arange(s, e, dtype=torch.int64) * 10 + 1             # stand-in for "rendered frame n"
+    sizes = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([e - s]))
+    bufs = [torch.zeros(int(z), dtype=torch.int64) for z in sizes]
+    dist.all_gather(bufs, mine) if len(set(int(z) for z in sizes)) == 1 else [dist.broadcast(bufs[r], r) if r != rank else dist.broadcast(mine, r) for r in range(world)]
+    if len(set(int(z) for z in sizes)) != 1:
+        bufs[rank] = mine
+    if rank == 0:
+        q.put(torch.cat(bufs).tolist())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_partition_gloo():
+    """world_size 2 over gloo: each rank renders its block; concatenation in rank order is frame order."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    n_frames, world, port = 11, 2, 29000 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, world, port, n_frames, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got == [n * 10 + 1 for n in range(n_frames)]

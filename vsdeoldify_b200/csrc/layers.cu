@@ -161,12 +161,12 @@ __global__ void blur2x2_kernel(const uint4 *__restrict__ in, uint4 *__restrict__
 // softmax over dim=1 of beta[b,i,j] == over the contiguous row of the transposed logits we store).
 // One warp per row; the row lives in registers across the three passes when cols <= 32*kMaxPerLane.
 __global__ void softmax_rows_kernel(const float *__restrict__ in, void *__restrict__ out, long long rows, int cols,
-                                    int out_dtype) {
+                                    int in_stride, int out_stride, int out_dtype) {
     const int lane = threadIdx.x & 31;
     const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     for (long long row = warp0; row < rows; row += nwarps) {
-        const float *r = in + row * cols;
+        const float *r = in + row * in_stride;
         float m = -INFINITY;
         for (int c = lane * 4; c < cols; c += 128) {
             const float4 v = *reinterpret_cast<const float4 *>(r + c);
@@ -187,7 +187,7 @@ __global__ void softmax_rows_kernel(const float *__restrict__ in, void *__restri
             const float e0 = __expf(v.x - m) * inv, e1 = __expf(v.y - m) * inv, e2 = __expf(v.z - m) * inv,
                         e3 = __expf(v.w - m) * inv;
             uint2 pk = make_uint2(pack2(e0, e1, out_dtype), pack2(e2, e3, out_dtype));
-            *reinterpret_cast<uint2 *>(reinterpret_cast<uint16_t *>(out) + row * cols + c) = pk;
+            *reinterpret_cast<uint2 *>(reinterpret_cast<uint16_t *>(out) + row * out_stride + c) = pk;
         }
     }
 }
@@ -262,10 +262,14 @@ extern "C" int havc_blur2x2(const void *in, void *out, int B, int H, int W, int 
     return HAVC_OK;
 }
 
-extern "C" int havc_softmax_rows(const float *in, void *out, long long rows, int cols, int out_dtype, void *stream) {
-    HAVC_CHECK_ARG(in && out && dt16(out_dtype) && cols % 4 == 0, "havc_softmax_rows: cols must be a multiple of 4");
+extern "C" int havc_softmax_rows(const float *in, void *out, long long rows, int cols, int in_stride, int out_stride,
+                                 int out_dtype, void *stream) {
+    HAVC_CHECK_ARG(in && out && dt16(out_dtype) && cols % 4 == 0 && in_stride % 4 == 0 && out_stride % 4 == 0 &&
+                       in_stride >= cols && out_stride >= cols,
+                   "havc_softmax_rows: cols and strides must be multiples of 4");
     const long long nthreads = rows * 32;
-    softmax_rows_kernel<<<grid_for(nthreads, 256), 256, 0, (cudaStream_t)stream>>>(in, out, rows, cols, out_dtype);
+    softmax_rows_kernel<<<grid_for(nthreads, 256), 256, 0, (cudaStream_t)stream>>>(in, out, rows, cols, in_stride,
+                                                                                  out_stride, out_dtype);
     HAVC_LAUNCHED();
     return HAVC_OK;
 }

@@ -101,8 +101,8 @@ __global__ void pre_vertical_kernel(const float *__restrict__ in, uint8_t *__res
 // then the S x S luma transplant against the resized source.  Optionally dumps the fp32 net output.
 __global__ void head_kernel(const void *__restrict__ res, int Cs, const float *__restrict__ w11 /*[3][Cs]*/,
                             const float *__restrict__ b11, const uint8_t *__restrict__ rgb_small,
-                            uint8_t *__restrict__ colored, float *__restrict__ net_out, int B, int S, int dtype,
-                            int transplant) {
+                            uint8_t *__restrict__ colored, float *__restrict__ net_out,
+                            const uint8_t *__restrict__ skip, int B, int S, int dtype, int transplant) {
     const int lane = threadIdx.x & 31;
     const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -145,12 +145,13 @@ __global__ void head_kernel(const void *__restrict__ res, int Cs, const float *_
                 q[c] = (int)__fmul_rn(d, 255.f);                                     // astype(uint8): truncation
             }
             int r = q[0], g = q[1], bl = q[2];
-            if (transplant) {
-                const long long o = ((long long)b * 3 * S + oy) * S + ox;
+            const long long o = ((long long)b * 3 * S + oy) * S + ox;
+            if (skip != nullptr && skip[b]) {   // scene-change gate: the selector returned the frame unchanged
+                r = rgb_small[o]; g = rgb_small[o + (long long)S * S]; bl = rgb_small[o + 2ll * S * S];
+            } else if (transplant) {
                 luma_transplant(rgb_small[o], rgb_small[o + (long long)S * S], rgb_small[o + 2ll * S * S], q[0], q[1],
                                 q[2], r, g, bl);
             }
-            const long long o = ((long long)b * 3 * S + oy) * S + ox;
             colored[o] = (uint8_t)r;
             colored[o + (long long)S * S] = (uint8_t)g;
             colored[o + 2ll * S * S] = (uint8_t)bl;
@@ -214,12 +215,13 @@ extern "C" int havc_pre_vertical(const float *in, uint8_t *rgb_small, void *x, i
 }
 
 extern "C" int havc_head(const void *res, int Cs, const float *w11, const float *b11, const uint8_t *rgb_small,
-                         uint8_t *colored, float *net_out, int B, int S, int dtype, int transplant, void *stream) {
-    HAVC_CHECK_ARG(res && w11 && b11 && colored && Cs % 8 == 0 && (!transplant || rgb_small) &&
+                         uint8_t *colored, float *net_out, const uint8_t *skip, int B, int S, int dtype, int transplant,
+                         void *stream) {
+    HAVC_CHECK_ARG(res && w11 && b11 && colored && Cs % 8 == 0 && ((!transplant && !skip) || rgb_small) &&
                        (dtype == HAVC_F16 || dtype == HAVC_BF16),
                    "havc_head: bad arguments");
     head_kernel<<<grid1d((long long)B * S * S * 32, 256), 256, 0, (cudaStream_t)stream>>>(
-        res, Cs, w11, b11, rgb_small, colored, net_out, B, S, dtype, transplant);
+        res, Cs, w11, b11, rgb_small, colored, net_out, skip, B, S, dtype, transplant);
     HAVC_LAUNCHED();
     return HAVC_OK;
 }

@@ -33,12 +33,17 @@ class DeoldifyEngine:
 
     def __init__(self, sd: Dict[str, torch.Tensor], width: int, height: int, render_factor: int = 24, batch: int = 8,
                  dtype: torch.dtype = torch.float16, device: str = "cuda:0", resize_kernel: str = "spline64",
-                 use_graph: bool = True, keep_taps: bool = False, debug_net_out: bool = False):
+                 use_graph: bool = True, keep_taps: bool = False, debug_net_out: bool = False,
+                 frame_size: Optional[int] = None):
         self.lib = _lib.lib()
         self.dev = torch.device(device)
         torch.cuda.set_device(self.dev)
         self.W, self.H, self.B = width, height, batch
-        self.S = min(render_factor * 16, width)          # frame_size, vsdeoldify/__init__.py:2502
+        # frame_size, vsdeoldify/__init__.py:2502; when it exceeds render_factor*16 (a bigger ddcolor_rf) the
+        # reference squeezes twice (Spline64 then Pillow BILINEAR inside the filter) - not built, so reject it
+        self.S = min(render_factor * 16, width) if frame_size is None else frame_size
+        if self.S != min(render_factor * 16, width):
+            raise ValueError("frame_size != render_factor*16 (ddcolor_rf > deoldify_rf) is not supported yet")
         S, B, W, H = self.S, batch, width, height
         self.dtype, self.hd = dtype, ops.havc_dtype(dtype)
         self.prog = UnetProgram(sd, B, S, dtype, device=self.dev, keep_taps=keep_taps)
@@ -58,6 +63,8 @@ class DeoldifyEngine:
         self.colored = torch.empty(B, 3, S, S, **u8)
         self.tmp_up = torch.empty(B, 3, S, W, **f32)
         self.net_out = torch.empty(B, 3, S, S, **f32) if debug_net_out else None
+        self.skip = torch.zeros(B, **u8)                  # per-frame scene-change gate (1 = leave uncoloured)
+        self.h_skip = torch.zeros(B, dtype=torch.uint8).pin_memory()
         self.compute = torch.cuda.Stream(device=self.dev)
         self.copy_in = torch.cuda.Stream(device=self.dev)
         self.copy_out = torch.cuda.Stream(device=self.dev)
@@ -78,7 +85,8 @@ class DeoldifyEngine:
         self.prog.run(stream)
         chk(lib.havc_head(self.prog.res.data_ptr(), self.prog.n_res_channels, self.prog.w11.data_ptr(),
                           self.prog.b11.data_ptr(), self.rgb_small.data_ptr(), self.colored.data_ptr(),
-                          self.net_out.data_ptr() if self.net_out is not None else None, B, S, self.hd, 1, stream),
+                          self.net_out.data_ptr() if self.net_out is not None else None, self.skip.data_ptr(), B, S,
+                          self.hd, 1, stream),
             "head")
         chk(lib.havc_resample_h(self.colored.data_ptr(), self.tmp_up.data_ptr(), B * 3 * S, S, W,
                                 uh.start.data_ptr(), uh.w.data_ptr(), uh.taps, stream), "post.h")
@@ -110,12 +118,19 @@ class DeoldifyEngine:
                 self._launch(slot, self.compute.cuda_stream)
 
     # ---- synchronous convenience API (tests) ---------------------------------------------------------
-    def colorize_batch(self, frames: np.ndarray) -> np.ndarray:
-        """frames: uint8 [n<=B, 3, H, W] planar RGB (host).  Returns uint8 [n, 3, H, W]."""
+    def colorize_batch(self, frames: np.ndarray, skip: Optional[np.ndarray] = None) -> np.ndarray:
+        """frames: uint8 [n<=B, 3, H, W] planar RGB (host).  Returns uint8 [n, 3, H, W].
+        skip[i] = True leaves frame i uncoloured (scene-change gating, vsslib/vsmodels.py:221-224): it still goes
+        through the squeeze / un-squeeze / luma transplant exactly like a frame the reference's selector returned
+        unchanged."""
         n = frames.shape[0]
         assert n <= self.B and frames.shape[1:] == (3, self.H, self.W) and frames.dtype == np.uint8
         self.h_in[0][:n].copy_(torch.from_numpy(np.ascontiguousarray(frames)))
+        self.h_skip.zero_()
+        if skip is not None:
+            self.h_skip[:n].copy_(torch.from_numpy(np.asarray(skip, dtype=np.uint8)))
         with torch.cuda.stream(self.compute):
+            self.skip.copy_(self.h_skip, non_blocking=True)
             self.d_in[0].copy_(self.h_in[0], non_blocking=True)
         self.run_slot(0)
         with torch.cuda.stream(self.compute):

@@ -84,11 +84,20 @@ def taps_stride2(ks: int) -> List[Tuple[int, int, int, int]]:
     return out
 
 
+def chan_storage(c: int) -> int:
+    """Channel storage width of an activation tensor: multiples of 64 above 64 channels (a TMA box whose
+    64-channel extent is partly outside the tensor is served ~3x slower than an in-bounds one - measured),
+    multiples of 8 (16 B) below.  Pad channels are zero and never written."""
+    return pad_to(c, 64) if c > 64 else pad_to(c, 8)
+
+
 def pack_conv_weight(w: torch.Tensor, cin_splits: Optional[Sequence[int]] = None, dtype=torch.float16,
-                     shuffle: bool = False, row_pad: int = 16) -> Tuple[torch.Tensor, dict]:
+                     shuffle: bool = False, row_pad: int = 16,
+                     cin_storage: Optional[Sequence[int]] = None) -> Tuple[torch.Tensor, dict]:
     """[Cout, Cin, kh, kw] (or [Cout, Cin]) fp32 -> packed [rows, taps, cin_storage] 16-bit (CPU tensor).
 
-    cin_splits: channel counts of the K sources (torch.cat order); each is padded to 8.
+    cin_splits: channel counts of the K sources (torch.cat order); each is zero-padded to its storage width
+    (cin_storage, default: next multiple of 8).
     shuffle: reorder rows for the PixelShuffle(2) store: row g*group_n + c <- out channel c*4 + g."""
     if w.dim() == 2:
         w = w[:, :, None, None]
@@ -97,10 +106,12 @@ def pack_conv_weight(w: torch.Tensor, cin_splits: Optional[Sequence[int]] = None
     Cout, Cin, kh, kw = w.shape
     cin_splits = list(cin_splits) if cin_splits else [Cin]
     assert sum(cin_splits) == Cin
+    cin_storage = list(cin_storage) if cin_storage else [pad_to(c, 8) for c in cin_splits]
     parts, off, c1_off = [], 0, 0
     for i, c in enumerate(cin_splits):
         blk = w[:, off:off + c]
-        cp = pad_to(c, 8)
+        cp = cin_storage[i]
+        assert cp >= c and cp % 8 == 0
         if cp != c:
             blk = torch.cat([blk, blk.new_zeros(Cout, cp - c, kh, kw)], 1)
         parts.append(blk)
@@ -145,17 +156,17 @@ def pack_cols(v: Optional[torch.Tensor], n_alloc: int, fill: float, shuffle_meta
 
 def choose_bn(n_total: int, m_tiles: int, sms: int = 148) -> int:
     """N tile (UMMA N: multiple of 16, <= 256; 272 = 256+16 for the 259-channel tail): the widest divisor
-    of n_total (fewest re-reads of the activation tile) that still gives every SM a tile."""
+    of n_total (fewest re-reads of the activation tile) that still gives every SM a tile, never below 64
+    (narrow tiles re-read the activations and idle the tensor pipe)."""
     if n_total <= 256 or n_total == 272:
         return n_total
-    cands = [bn for bn in range(256, 15, -16) if n_total % bn == 0]
+    cands = [bn for bn in range(256, 63, -16) if n_total % bn == 0]
     if not cands:
         return 128
     for bn in cands:
         if m_tiles * (n_total // bn) >= sms:
             return bn
-    small = [bn for bn in cands if bn >= 64]   # cannot fill the machine anyway: maximise parallelism
-    return (small or cands)[-1]
+    return cands[-1]
 
 
 @dataclass

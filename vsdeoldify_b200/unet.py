@@ -23,7 +23,7 @@ from typing import Callable, Dict, List, Optional, Tuple
 import torch
 
 from . import _lib, ops
-from .ops import pad_to
+from .ops import chan_storage, pad_to
 
 SD = Dict[str, torch.Tensor]
 BN_EPS = 1e-5
@@ -109,7 +109,8 @@ class UnetProgram:
              out_c: Optional[int] = None) -> torch.Tensor:
         """w: folded fp32 [Cout, Cin, ks, ks].  Returns the NHWC output tensor."""
         Cout, Cin = w.shape[0], w.shape[1]
-        wp, meta = ops.pack_conv_weight(w, cin_splits, dtype=self.dtype, shuffle=shuffle)
+        storage = [src0.shape[-1]] + ([src1.shape[-1]] if src1 is not None else [])
+        wp, meta = ops.pack_conv_weight(w, cin_splits, dtype=self.dtype, shuffle=shuffle, cin_storage=storage)
         wp = wp.to(self.dev)
         self.keep.append(wp)
         n_total = meta["rows"]
@@ -120,15 +121,14 @@ class UnetProgram:
         else:  # src0 is phase-split [P,B,H/2,W/2,C]
             B, H, W = src0.shape[1], src0.shape[2], src0.shape[3]
             taps = ops.taps_stride2(ks) if ks > 1 else [(0, 0, 0, 0)]
-        if out is None:
-            if shuffle:
-                out = self.buf(B, 2 * H, 2 * W, pad_to(meta["cg"], 8))
-            else:
-                out = self.buf(B, H, W, pad_to(out_c or Cout, 8))
+        c_real = meta["cg"] if shuffle else (out_c or Cout)
+        if out is None:     # zero-initialised: the pad channels beyond c_store are never written and stay zero
+            out = self.buf(B, 2 * H, 2 * W, chan_storage(c_real), zero=True) if shuffle else \
+                self.buf(B, H, W, chan_storage(c_real), zero=True)
         op = ops.make_conv(src0, wp, out, taps, src1=src1, w_c1_off=meta["c1_off"], n_total=n_total,
                            bias=pc(bias, 0.0), scale=pc(scale, 1.0), shift=pc(shift, 0.0), relu1=relu1, relu2=relu2,
                            residual=residual, out_space=(B, H, W), shuffle=shuffle, group_n=meta.get("group_n", 0),
-                           name=name)
+                           c_store=pad_to(c_real, 8), name=name)
         flops = 2.0 * B * H * W * Cout * Cin * ks * ks
         self.ops.append(Op(name, op.launch, flops=flops, kind="gemm"))
         self.keep.append(op)
@@ -141,7 +141,7 @@ class UnetProgram:
         B, H, W, Cs = src.shape
         c = c or Cs
         if out is None:
-            out = self.buf(B, H, W, Cs)
+            out = self.buf(B, H, W, Cs, zero=True)
         sc = self.dev_f32(torch.cat([scale, scale.new_ones(pad_to(c, 8) - scale.numel())]))
         sh = self.dev_f32(torch.cat([shift, shift.new_zeros(pad_to(c, 8) - shift.numel())]))
         in_ptr, out_ptr = src.data_ptr(), out.data_ptr() + 2 * out_c_off
@@ -156,7 +156,7 @@ class UnetProgram:
     def blur(self, name, src, out=None):
         B, H, W, Cs = src.shape
         if out is None:
-            out = self.buf(B, H, W, Cs)
+            out = self.buf(B, H, W, Cs, zero=True)
         ip, op_, ostr, hd, lib = src.data_ptr(), out.data_ptr(), out.stride(2), self.hd, self.lib
 
         def fn(stream):
@@ -166,7 +166,7 @@ class UnetProgram:
 
     def phase_split(self, name, src, n_phases):
         B, H, W, Cs = src.shape
-        out = self.buf(n_phases, B, (H + 1) // 2, (W + 1) // 2, Cs)
+        out = self.buf(n_phases, B, (H + 1) // 2, (W + 1) // 2, Cs, zero=True)
         ip, op_, lib = src.data_ptr(), out.data_ptr(), self.lib
 
         def fn(stream):
@@ -184,10 +184,10 @@ class UnetProgram:
         w = sd["layers.0.0.weight"].float()
         sc, sh = bn_affine(sd, "layers.0.1")
         wf = (w * sc.view(-1, 1, 1, 1)).permute(0, 2, 3, 1).reshape(64, 147)     # K order (kh, kw, c)
-        Kp = pad_to(147, 8)
+        Kp = chan_storage(147)
         wf = torch.cat([wf, wf.new_zeros(64, Kp - 147)], 1).view(64, Kp, 1, 1)
         H2 = S // 2
-        col = self.buf(B, H2, H2, Kp)
+        col = self.buf(B, H2, H2, Kp, zero=True)
         xp, cp = self.x.data_ptr(), col.data_ptr()
 
         def im2col(stream):
@@ -238,7 +238,7 @@ class UnetProgram:
         assert cu % 8 == 0 or True
         cu8 = pad_to(cu, 8)
         ncat = cu + 3
-        cat = self.buf(B, S, S, pad_to(cu8 + 8, 8), zero=True)
+        cat = self.buf(B, S, S, chan_storage(cu8 + 8), zero=True)
         # the cat buffer stores u at [0,cu8) and x at [cu8, cu8+8); weights are packed with matching splits
         self.blur("shuf8.blur", t8, out=cat)
         ones, zeros = torch.ones(8), torch.zeros(8)
@@ -246,7 +246,7 @@ class UnetProgram:
         self.tap("cat", cat)
         self.cat_splits = [cu, 3] if cu8 != cu else None
         # res_block (fastai/layers.py:154-161): two conv+bias+ReLU, then + input
-        ccat = cat.shape[-1]
+        ccat = cu8 + 8                      # logical channel count of the cat layout [u | pad | x | pad]
         w0 = self._pad_cin_to_cat(folded_weight(sd, "layers.10.layers.0.0"), cu, cu8, ccat)
         w1 = self._pad_cin_to_cat(folded_weight(sd, "layers.10.layers.1.0"), cu, cu8, ccat)
         # output channels of both convs must line up with the cat buffer's channel positions
@@ -254,21 +254,21 @@ class UnetProgram:
         w1 = self._pad_cout_to_cat(w1, cu, cu8, ccat)
         b0 = self._pad_vec_to_cat(sd["layers.10.layers.0.0.bias"].float(), cu, cu8, ccat)
         b1 = self._pad_vec_to_cat(sd["layers.10.layers.1.0.bias"].float(), cu, cu8, ccat)
-        r1 = self.conv("res.conv0", cat, w0, ks=3, bias=b0, relu1=True)
+        r1 = self.conv("res.conv0", cat, w0, ks=3, bias=b0, relu1=True, out_c=cu8 + 8)
         self.ops[-1].flops = 2.0 * B * S * S * ncat * ncat * 9
-        r2 = self.conv("res.conv1", r1, w1, ks=3, bias=b1, relu1=True, residual=cat)
+        r2 = self.conv("res.conv1", r1, w1, ks=3, bias=b1, relu1=True, residual=cat, out_c=cu8 + 8)
         self.ops[-1].flops = 2.0 * B * S * S * ncat * ncat * 9
         self.tap("res", r2)
         self.res = r2
         # head weights (layers.11 1x1 conv + bias), laid out on the cat channel positions
         w11 = folded_weight(sd, "layers.11.0").view(3, ncat)
-        w11p = torch.zeros(3, ccat)
+        w11p = torch.zeros(3, cat.shape[-1])
         w11p[:, :cu] = w11[:, :cu]
         w11p[:, cu8:cu8 + 3] = w11[:, cu:]
         self.w11 = self.dev_f32(w11p)
         self.b11 = self.dev_f32(sd["layers.11.0.bias"].float())
         self.head_flops = 2.0 * B * S * S * ncat * 3
-        self.n_res_channels = ccat
+        self.n_res_channels = cat.shape[-1]
 
     @staticmethod
     def _pad_cin_to_cat(w, cu, cu8, ccat):
@@ -375,31 +375,34 @@ class UnetProgram:
         k = self.conv(p + ".key", xt, wk)            # g  [B,1,N,d]
         dp = q.shape[-1]
         # Ht[b, c, i] = sum_k Wv[c,k] x[b,i,k]  (A = Wv shared, B = tokens per image)
-        wv16 = self.buf(1, 1, Cc, Cc)
-        wv16.copy_(wv.view(1, 1, Cc, Cc).to(self.dtype))
-        Ht = self.buf(B, 1, Cc, N)
+        wv16 = self.buf(1, 1, Cc, Cc, zero=True)              # [rows = out channel (padded), K = in channel (padded)]
+        wv16[0, 0, :wv.shape[0], :wv.shape[1]].copy_(wv.view(wv.shape[0], wv.shape[1]).to(self.dtype))
+        Ns = chan_storage(N)                                   # K storage of the P.V GEMM
+        Cr = wv.shape[0]
+        Ht = self.buf(B, 1, Cc, Ns, zero=True)
         op = ops.make_conv(wv16, x.view(B, N, 1, Cc), Ht, [(0, 0, 0, 0)], n_total=pad_to(N, 16), a_batched=False,
-                           b_batched=True, out_space=(B, 1, Cc), c_store=N, name=p + ".value_t")
+                           b_batched=True, out_space=(B, 1, Cc), c_store=pad_to(N, 8), name=p + ".value_t")
         self.ops.append(Op(p + ".value_t", op.launch, flops=2.0 * B * N * Cc * Cc, kind="gemm"))
         self.keep.append(op)
         # S[b, j, i] = sum_c g[b,j,c] f[b,i,c]
         Sx = self.buf(B, 1, N, N, dtype=torch.float32)
         op = ops.make_conv(k, q.view(B, N, 1, dp), Sx, [(0, 0, 0, 0)], n_total=pad_to(N, 16), b_batched=True,
-                           out_space=(B, 1, N), c_store=N, name=p + ".logits")
+                           out_space=(B, 1, N), c_store=pad_to(N, 8), name=p + ".logits")
         self.ops.append(Op(p + ".logits", op.launch, flops=2.0 * B * N * N * d, kind="gemm"))
         self.keep.append(op)
-        P = self.buf(B, 1, N, N)
+        P = self.buf(B, 1, N, Ns, zero=True)
         sp, pp, hd, lib = Sx.data_ptr(), P.data_ptr(), self.hd, self.lib
 
         def softmax(stream):
-            _lib.check(lib.havc_softmax_rows(sp, pp, B * N, N, hd, stream), p + ".softmax")
+            _lib.check(lib.havc_softmax_rows(sp, pp, B * N, N, N, Ns, hd, stream), p + ".softmax")
         self.aux(p + ".softmax", softmax, nbytes=6.0 * B * N * N)
         # out[b, j, c] = x[b,j,c] + gamma * sum_i P[b,j,i] Ht[b,c,i]
-        out = self.buf(B, H, W, Cc)
+        out = self.buf(B, H, W, Cc, zero=True)
         gs = self.dev_f32(torch.full((pad_to(Cc, 16),), gamma))
         gz = self.dev_f32(torch.zeros(pad_to(Cc, 16)))
-        op = ops.make_conv(P, Ht.view(B, Cc, 1, N), out.view(B, 1, N, Cc), [(0, 0, 0, 0)], n_total=pad_to(Cc, 16),
-                           b_batched=True, out_space=(B, 1, N), scale=gs, shift=gz, residual=xt, name=p + ".pv")
+        op = ops.make_conv(P, Ht.view(B, Cc, 1, Ns), out.view(B, 1, N, Cc), [(0, 0, 0, 0)], n_total=pad_to(Cc, 16),
+                           b_batched=True, out_space=(B, 1, N), scale=gs, shift=gz, residual=xt,
+                           c_store=pad_to(Cr, 8), name=p + ".pv")
         self.ops.append(Op(p + ".pv", op.launch, flops=2.0 * B * N * N * Cc, kind="gemm"))
         self.keep.append(op)
         return out
