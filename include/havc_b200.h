@@ -131,11 +131,15 @@ int havc_pre_vertical(const float *in, uint8_t *rgb_small, void *x, int B, int H
 int havc_head(const void *res, int Cs, const float *w11, const float *b11, const uint8_t *rgb_small,
               uint8_t *colored, float *net_out, const uint8_t *skip, int B, int S, int dtype, int transplant,
               void *stream);
-/* Vertical pass of the resize back to W x H fused with vs_recover_clip_luma / chroma_post_process
+/* Vertical pass on u8 planes (first pass of the resize back to W x H, run on the S-wide image):
+ * out[plane][oy][x] = sum_t weights[oy][t] * in[plane][start[oy]+t][x].  in: u8 [planes][Hin][W]; out: float. */
+int havc_resample_v(const uint8_t *in, float *out, long long planes, int Hin, int Hout, int W, const int *start,
+                    const float *weights, int taps, void *stream);
+/* Final horizontal pass of the resize back to W x H fused with vs_recover_clip_luma / chroma_post_process
  * (vsdeoldify/vsslib/vsfilters.py:863-899, imfilters.py:312-321): keep the luma of `orig`, the chroma of the
- * upscaled colour image (OpenCV Q14 8-bit YUV).  in: float [B][3][S][W]; orig/out: u8 [B][3][H][W]. */
-int havc_post_vertical(const float *in, const uint8_t *orig, uint8_t *out, int B, int S, int H, int W,
-                       const int *start, const float *weights, int taps, int transplant, void *stream);
+ * upscaled colour image (OpenCV Q14 8-bit YUV).  in: float [B][3][H][S]; orig/out: u8 [B][3][H][W]. */
+int havc_post_horizontal(const float *in, const uint8_t *orig, uint8_t *out, int B, int S, int H, int W,
+                         const int *start, const float *weights, int taps, int transplant, void *stream);
 
 #ifdef __cplusplus
 }

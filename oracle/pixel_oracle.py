@@ -120,19 +120,24 @@ def resize_matrix(src: int, dst: int, kernel: str = "spline64") -> np.ndarray:
 
 
 def resize_plane_u8(img: np.ndarray, out_w: int, out_h: int, kernel: str = "spline64") -> np.ndarray:
-    """uint8 [H,W] (or [H,W,C]) -> uint8 resized; horizontal pass then vertical pass in float32,
-    round-half-even and clamp at the end (no dithering)."""
+    """uint8 [H,W] (or [H,W,C]) -> uint8 resized; two separable float32 passes with a float intermediate, the
+    cheaper pass first (horizontal-then-vertical when the width shrinks more work away, vertical-then-horizontal
+    otherwise - zimg orders its passes by cost too), round-half-even and clamp at the end (no dithering)."""
     h, w = img.shape[:2]
     mh = resize_matrix(w, out_w, kernel).astype(np.float32)
     mv = resize_matrix(h, out_h, kernel).astype(np.float32)
     x = img.astype(np.float32)
     if x.ndim == 2:
-        t = x @ mh.T
-        o = mv @ t
-    else:
+        x = x[..., None]
+    h_first = out_w * h <= out_h * w          # size of the intermediate image = cost of the second pass
+    if h_first:
         t = np.einsum("hwc,ow->hoc", x, mh)
         o = np.einsum("ph,hoc->poc", mv, t)
-    return np.clip(np.rint(o), 0, 255).astype(np.uint8)
+    else:
+        t = np.einsum("ph,hwc->pwc", mv, x)
+        o = np.einsum("pwc,ow->poc", t, mh)
+    o = np.clip(np.rint(o), 0, 255).astype(np.uint8)
+    return o[..., 0] if img.ndim == 2 else o
 
 
 # ---- Pillow Image.resize (ImagingResample: separable, 8-bit fixed-point coefficients, u8 intermediate) ------

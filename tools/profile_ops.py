@@ -37,3 +37,37 @@ print(f"total serialised ms/batch {tot:.3f}  ({a.batch} frames)  gemm {sum(r['ms
 for r in rows_sorted[:45]:
     print(f"{r['name']:34s} {r['ms']:8.4f} ms  {r['tflops']:7.1f} TF  {r['gbs']:7.0f} GB/s  BN={r['bn']} N={r['n']} K={r['k']} taps={r['taps']} box={r['box']}")
 json.dump(rows, open(a.out, "w"))
+# whole-batch graph time and the share outside the network launch list (pre/post/head pixel passes)
+eng2 = eng
+import time
+g_times = []
+with torch.cuda.stream(eng.compute):
+    for i in range(3):
+        eng._launch(0, eng.compute.cuda_stream)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(eng.compute)
+    for i in range(5):
+        eng._launch(0, eng.compute.cuda_stream)
+    e1.record(eng.compute)
+eng.compute.synchronize()
+full = e0.elapsed_time(e1) / 5
+print(f"full batch (pre + net + head + post), back-to-back launches: {full:.3f} ms -> {a.batch / full * 1000:.1f} frames/s; outside net list: {full - tot:.3f} ms")
+lib = eng.lib
+import ctypes
+def timed(label, fn):
+    with torch.cuda.stream(eng.compute):
+        fn(); fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(eng.compute)
+        for _ in range(5): fn()
+        e1.record(eng.compute)
+    eng.compute.synchronize()
+    print(f"  {label:10s} {e0.elapsed_time(e1) / 5:8.4f} ms")
+st = eng.compute.cuda_stream
+B, S, W, H = eng.B, eng.S, eng.W, eng.H
+td, tv, uh, uv = eng.t_down_h, eng.t_down_v, eng.t_up_h, eng.t_up_v
+timed("pre.h", lambda: lib.havc_resample_h(eng.d_in[0].data_ptr(), eng.tmp_down.data_ptr(), B * 3 * H, W, S, td.start.data_ptr(), td.w.data_ptr(), td.taps, st))
+timed("pre.v", lambda: lib.havc_pre_vertical(eng.tmp_down.data_ptr(), eng.rgb_small.data_ptr(), eng.prog.x.data_ptr(), B, H, S, tv.start.data_ptr(), tv.w.data_ptr(), tv.taps, eng.hd, st))
+timed("head", lambda: lib.havc_head(eng.prog.res.data_ptr(), eng.prog.n_res_channels, eng.prog.w11.data_ptr(), eng.prog.b11.data_ptr(), eng.rgb_small.data_ptr(), eng.colored.data_ptr(), None, eng.skip.data_ptr(), B, S, eng.hd, 1, st))
+timed("post.v", lambda: lib.havc_resample_v(eng.colored.data_ptr(), eng.tmp_up.data_ptr(), B * 3, S, H, S, uv.start.data_ptr(), uv.w.data_ptr(), uv.taps, st))
+timed("post.h", lambda: lib.havc_post_horizontal(eng.tmp_up.data_ptr(), eng.d_in[0].data_ptr(), eng.d_out[0].data_ptr(), B, S, H, W, uh.start.data_ptr(), uh.w.data_ptr(), uh.taps, 1, st))

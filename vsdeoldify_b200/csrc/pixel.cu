@@ -45,18 +45,53 @@ __device__ __forceinline__ void luma_transplant(int orr, int og, int ob, int cr,
     yuv2rgb(y, u2, v2, r, g, b);
 }
 
-// Horizontal pass: u8 rows -> float rows.
+// Horizontal pass: u8 rows -> float rows.  One block per input row: the row is staged in shared memory as
+// floats (coalesced 16-byte loads), every thread then produces outputs ox = tid, tid+blockDim, ...
 __global__ void resample_h_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, long long rows, int Win,
                                   int Wout, const int *__restrict__ start, const float *__restrict__ wts, int T) {
-    const long long total = rows * Wout;
+    extern __shared__ float srow[];
+    for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+        const uint8_t *src = in + row * Win;
+        if ((Win & 15) == 0 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+            for (int i = threadIdx.x; i < Win / 16; i += blockDim.x) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src) + i);
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    srow[i * 16 + 4 * j + 0] = (float)(w[j] & 0xff);
+                    srow[i * 16 + 4 * j + 1] = (float)((w[j] >> 8) & 0xff);
+                    srow[i * 16 + 4 * j + 2] = (float)((w[j] >> 16) & 0xff);
+                    srow[i * 16 + 4 * j + 3] = (float)(w[j] >> 24);
+                }
+            }
+        } else {
+            for (int i = threadIdx.x; i < Win; i += blockDim.x) srow[i] = (float)src[i];
+        }
+        __syncthreads();
+        for (int ox = threadIdx.x; ox < Wout; ox += blockDim.x) {
+            const float *sp = srow + __ldg(start + ox);
+            const float *w = wts + (long long)ox * T;
+            float acc = 0.f;
+            for (int t = 0; t < T; ++t) acc = fmaf(__ldg(w + t), sp[t], acc);
+            out[row * Wout + ox] = acc;
+        }
+        __syncthreads();
+    }
+}
+
+// Vertical pass on u8 planes: out[plane][oy][x] = sum_t w[oy][t] * in[plane][start[oy]+t][x]  (float out).
+__global__ void resample_v_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, long long planes, int Hin,
+                                  int Hout, int W, const int *__restrict__ start, const float *__restrict__ wts, int T) {
+    const long long total = planes * Hout * W;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
-        const int ox = (int)(i % Wout);
-        const long long row = i / Wout;
-        const uint8_t *src = in + row * Win + __ldg(start + ox);
-        const float *w = wts + (long long)ox * T;
+        const int x = (int)(i % W);
+        const int oy = (int)((i / W) % Hout);
+        const long long pl = i / ((long long)W * Hout);
+        const uint8_t *src = in + (pl * Hin + __ldg(start + oy)) * W + x;
+        const float *w = wts + (long long)oy * T;
         float acc = 0.f;
-        for (int t = 0; t < T; ++t) acc = fmaf(__ldg(w + t), (float)src[t], acc);
+        for (int t = 0; t < T; ++t) acc = fmaf(__ldg(w + t), (float)__ldg(src + (long long)t * W), acc);
         out[i] = acc;
     }
 }
@@ -108,19 +143,32 @@ __global__ void head_kernel(const void *__restrict__ res, int Cs, const float *_
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const long long total = (long long)B * S * S;
     const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+    // each lane owns channel groups g = lane, lane+32 (Cs <= 512): its slice of the 1x1 weights stays in registers
+    constexpr int kG = 2;
+    float wr[kG][3][8];
+#pragma unroll
+    for (int k = 0; k < kG; ++k) {
+        const int g = lane + 32 * k;
+#pragma unroll
+        for (int o = 0; o < 3; ++o)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) wr[k][o][j] = (g < Cs / 8) ? __ldg(w11 + o * Cs + g * 8 + j) : 0.f;
+    }
     for (long long pix = warp0; pix < total; pix += nwarps) {
         const uint4 *row = reinterpret_cast<const uint4 *>(reinterpret_cast<const uint16_t *>(res) + pix * Cs);
         float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-        for (int g = lane; g < Cs / 8; g += 32) {
+#pragma unroll
+        for (int k = 0; k < kG; ++k) {
+            const int g = lane + 32 * k;
+            if (g >= Cs / 8) break;
             const uint4 v = __ldg(row + g);
             const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float2 f = unpack2(w[j], dtype);
-                const int c = g * 8 + 2 * j;
-                a0 = fmaf(f.x, __ldg(w11 + c), a0);          a0 = fmaf(f.y, __ldg(w11 + c + 1), a0);
-                a1 = fmaf(f.x, __ldg(w11 + Cs + c), a1);     a1 = fmaf(f.y, __ldg(w11 + Cs + c + 1), a1);
-                a2 = fmaf(f.x, __ldg(w11 + 2 * Cs + c), a2); a2 = fmaf(f.y, __ldg(w11 + 2 * Cs + c + 1), a2);
+                a0 = fmaf(f.x, wr[k][0][2 * j], a0); a0 = fmaf(f.y, wr[k][0][2 * j + 1], a0);
+                a1 = fmaf(f.x, wr[k][1][2 * j], a1); a1 = fmaf(f.y, wr[k][1][2 * j + 1], a1);
+                a2 = fmaf(f.x, wr[k][2][2 * j], a2); a2 = fmaf(f.y, wr[k][2][2 * j + 1], a2);
             }
         }
 #pragma unroll
@@ -159,35 +207,67 @@ __global__ void head_kernel(const void *__restrict__ res, int Cs, const float *_
     }
 }
 
-// Vertical pass of the post-resize fused with the full-resolution luma transplant.
-// in: float [B][3][S][W]; orig/out: u8 [B][3][H][W].
-__global__ void post_vertical_kernel(const float *__restrict__ in, const uint8_t *__restrict__ orig,
-                                     uint8_t *__restrict__ out, int B, int S, int H, int W,
-                                     const int *__restrict__ start, const float *__restrict__ wts, int T,
-                                     int transplant) {
-    const long long total = (long long)B * H * W;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const int ox = (int)(i % W);
-        const int oy = (int)((i / W) % H);
-        const int b = (int)(i / ((long long)W * H));
-        const int s0 = __ldg(start + oy);
-        const float *w = wts + (long long)oy * T;
-        int q[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float *src = in + (((long long)b * 3 + c) * S + s0) * W + ox;
-            float acc = 0.f;
-            for (int t = 0; t < T; ++t) acc = fmaf(__ldg(w + t), __ldg(src + (long long)t * W), acc);
-            q[c] = round_u8(acc);
+// Final (horizontal) pass of the resize back to W x H fused with the full-resolution luma transplant.
+// in: float [B][3][H][S] (already resampled vertically); orig/out: u8 [B][3][H][W].  One block per output row:
+// the three S-wide source rows sit in shared memory, each thread produces 4 consecutive pixels (uchar4 I/O).
+__global__ void post_horizontal_kernel(const float *__restrict__ in, const uint8_t *__restrict__ orig,
+                                       uint8_t *__restrict__ out, int B, int S, int H, int W,
+                                       const int *__restrict__ start, const float *__restrict__ wts, int T,
+                                       int transplant) {
+    extern __shared__ float srows[];   // [3][S]
+    const long long ps = (long long)H * W;
+    for (long long r = blockIdx.x; r < (long long)B * H; r += gridDim.x) {
+        const int oy = (int)(r % H);
+        const int b = (int)(r / H);
+        for (int i = threadIdx.x; i < 3 * S; i += blockDim.x) {
+            const int c = i / S, x = i - c * S;
+            srows[i] = __ldg(in + (((long long)b * 3 + c) * H + oy) * S + x);
         }
-        const long long o = ((long long)b * 3 * H + oy) * W + ox;
-        const long long ps = (long long)H * W;
-        int r = q[0], g = q[1], bl = q[2];
-        if (transplant) luma_transplant(orig[o], orig[o + ps], orig[o + 2 * ps], q[0], q[1], q[2], r, g, bl);
-        out[o] = (uint8_t)r;
-        out[o + ps] = (uint8_t)g;
-        out[o + 2 * ps] = (uint8_t)bl;
+        __syncthreads();
+        const long long base = ((long long)b * 3 * H + oy) * W;
+        for (int x4 = threadIdx.x * 4; x4 < W; x4 += blockDim.x * 4) {
+            const bool vec = (x4 + 3 < W) && ((W & 3) == 0);
+            uint32_t o4[3] = {0, 0, 0};
+            uint32_t ov[3] = {0, 0, 0};
+            if (transplant && vec) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) o4[c] = __ldg(reinterpret_cast<const uint32_t *>(orig + base + c * ps + x4));
+            }
+            const int npx = vec ? 4 : min(4, W - x4);
+            for (int k = 0; k < npx; ++k) {
+                const int ox = x4 + k;
+                const int s0 = __ldg(start + ox);
+                const float *w = wts + (long long)ox * T;
+                float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+                for (int t = 0; t < T; ++t) {
+                    const float wt = __ldg(w + t);
+                    acc0 = fmaf(wt, srows[s0 + t], acc0);
+                    acc1 = fmaf(wt, srows[S + s0 + t], acc1);
+                    acc2 = fmaf(wt, srows[2 * S + s0 + t], acc2);
+                }
+                int q0 = round_u8(acc0), q1 = round_u8(acc1), q2 = round_u8(acc2);
+                int rr = q0, gg = q1, bb = q2;
+                if (transplant) {
+                    int o0, o1, o2;
+                    if (vec) {
+                        o0 = (o4[0] >> (8 * k)) & 0xff; o1 = (o4[1] >> (8 * k)) & 0xff; o2 = (o4[2] >> (8 * k)) & 0xff;
+                    } else {
+                        o0 = orig[base + ox]; o1 = orig[base + ps + ox]; o2 = orig[base + 2 * ps + ox];
+                    }
+                    luma_transplant(o0, o1, o2, q0, q1, q2, rr, gg, bb);
+                }
+                if (vec) {
+                    ov[0] |= (uint32_t)rr << (8 * k); ov[1] |= (uint32_t)gg << (8 * k); ov[2] |= (uint32_t)bb << (8 * k);
+                } else {
+                    out[base + ox] = (uint8_t)rr; out[base + ps + ox] = (uint8_t)gg; out[base + 2 * ps + ox] = (uint8_t)bb;
+                }
+            }
+            if (vec) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) *reinterpret_cast<uint32_t *>(out + base + c * ps + x4) = ov[c];
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -198,8 +278,15 @@ using namespace havc;
 extern "C" int havc_resample_h(const uint8_t *in, float *out, long long rows, int Win, int Wout, const int *start,
                                const float *weights, int taps, void *stream) {
     HAVC_CHECK_ARG(in && out && start && weights && taps > 0, "havc_resample_h: bad arguments");
-    resample_h_kernel<<<grid1d(rows * Wout, 256), 256, 0, (cudaStream_t)stream>>>(in, out, rows, Win, Wout, start,
-                                                                               weights, taps);
+    HAVC_CHECK_ARG(Win * sizeof(float) <= 96 * 1024, "havc_resample_h: row too wide for shared memory");
+    static bool attr = false;
+    if (!attr) {
+        HAVC_CHECK_CUDA(cudaFuncSetAttribute(resample_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        attr = true;
+    }
+    long long g = rows < (long long)num_sms() * 16 ? rows : (long long)num_sms() * 16;
+    resample_h_kernel<<<(int)g, 128, Win * sizeof(float), (cudaStream_t)stream>>>(in, out, rows, Win, Wout, start, weights,
+                                                                               taps);
     HAVC_LAUNCHED();
     return HAVC_OK;
 }
@@ -226,11 +313,23 @@ extern "C" int havc_head(const void *res, int Cs, const float *w11, const float 
     return HAVC_OK;
 }
 
-extern "C" int havc_post_vertical(const float *in, const uint8_t *orig, uint8_t *out, int B, int S, int H, int W,
-                                  const int *start, const float *weights, int taps, int transplant, void *stream) {
-    HAVC_CHECK_ARG(in && out && start && weights && taps > 0 && (!transplant || orig), "havc_post_vertical: bad arguments");
-    post_vertical_kernel<<<grid1d((long long)B * H * W, 256), 256, 0, (cudaStream_t)stream>>>(
-        in, orig, out, B, S, H, W, start, weights, taps, transplant);
+extern "C" int havc_resample_v(const uint8_t *in, float *out, long long planes, int Hin, int Hout, int W,
+                               const int *start, const float *weights, int taps, void *stream) {
+    HAVC_CHECK_ARG(in && out && start && weights && taps > 0, "havc_resample_v: bad arguments");
+    resample_v_kernel<<<grid1d(planes * Hout * W, 256), 256, 0, (cudaStream_t)stream>>>(in, out, planes, Hin, Hout, W,
+                                                                                     start, weights, taps);
+    HAVC_LAUNCHED();
+    return HAVC_OK;
+}
+
+extern "C" int havc_post_horizontal(const float *in, const uint8_t *orig, uint8_t *out, int B, int S, int H, int W,
+                                    const int *start, const float *weights, int taps, int transplant, void *stream) {
+    HAVC_CHECK_ARG(in && out && start && weights && taps > 0 && (!transplant || orig) && 3 * S * sizeof(float) <= 48 * 1024,
+                   "havc_post_horizontal: bad arguments");
+    long long rows = (long long)B * H;
+    long long g = rows < (long long)num_sms() * 16 ? rows : (long long)num_sms() * 16;
+    post_horizontal_kernel<<<(int)g, 256, 3 * S * sizeof(float), (cudaStream_t)stream>>>(in, orig, out, B, S, H, W, start,
+                                                                                     weights, taps, transplant);
     HAVC_LAUNCHED();
     return HAVC_OK;
 }

@@ -61,7 +61,7 @@ class DeoldifyEngine:
         self.tmp_down = torch.empty(B, 3, H, S, **f32)
         self.rgb_small = torch.empty(B, 3, S, S, **u8)
         self.colored = torch.empty(B, 3, S, S, **u8)
-        self.tmp_up = torch.empty(B, 3, S, W, **f32)
+        self.tmp_up = torch.empty(B, 3, H, S, **f32)
         self.net_out = torch.empty(B, 3, S, S, **f32) if debug_net_out else None
         self.skip = torch.zeros(B, **u8)                  # per-frame scene-change gate (1 = leave uncoloured)
         self.h_skip = torch.zeros(B, dtype=torch.uint8).pin_memory()
@@ -88,10 +88,11 @@ class DeoldifyEngine:
                           self.net_out.data_ptr() if self.net_out is not None else None, self.skip.data_ptr(), B, S,
                           self.hd, 1, stream),
             "head")
-        chk(lib.havc_resample_h(self.colored.data_ptr(), self.tmp_up.data_ptr(), B * 3 * S, S, W,
-                                uh.start.data_ptr(), uh.w.data_ptr(), uh.taps, stream), "post.h")
-        chk(lib.havc_post_vertical(self.tmp_up.data_ptr(), self.d_in[slot].data_ptr(), self.d_out[slot].data_ptr(), B, S,
-                                   H, W, uv.start.data_ptr(), uv.w.data_ptr(), uv.taps, 1, stream), "post.v")
+        # back to W x H: vertical pass on the S-wide image first, then the wide horizontal pass from shared memory
+        chk(lib.havc_resample_v(self.colored.data_ptr(), self.tmp_up.data_ptr(), B * 3, S, H, S,
+                                uv.start.data_ptr(), uv.w.data_ptr(), uv.taps, stream), "post.v")
+        chk(lib.havc_post_horizontal(self.tmp_up.data_ptr(), self.d_in[slot].data_ptr(), self.d_out[slot].data_ptr(), B, S,
+                                     H, W, uh.start.data_ptr(), uh.w.data_ptr(), uh.taps, 1, stream), "post.h")
 
     def _warm(self):
         with torch.cuda.stream(self.compute):
