@@ -63,7 +63,7 @@ typedef struct {
     int32_t out_B, out_H, out_W;/* iteration space of the GEMM M dimension (output pixels)      */
     int32_t box_w, box_h, box_b;/* M tile = box_w*box_h*box_b = 128 output pixels               */
     int32_t a_batched, b_batched;
-    int32_t BN;                 /* N tile (multiple of 16, <= 272)                              */
+    int32_t BN;                 /* N tile (multiple of 16, <= 320; > 256 is issued as 256 + rest) */
     int32_t N_total;            /* GEMM N including padding (multiple of 16)                    */
     const float *bias, *scale, *shift; /* per GEMM column, >= ceil(N_total/BN)*BN entries; NULL = skip */
     int32_t relu1, relu2;
@@ -77,6 +77,24 @@ typedef struct {
     int32_t group_n;            /* padded columns per shuffle group (multiple of 16)            */
     int32_t c_store;            /* channels written per pixel (multiple of 8)                   */
     int32_t dtype;              /* HAVC_F16 or HAVC_BF16 operands                               */
+    /* K-loop variant: src1 is an im2col'd side tensor that contributes ONE tap (offset 0) after all taps of src0;
+     * its weights live at weight tap index src1_wi, channels [w_c1_off, ...).  Used for the 3 image channels of
+     * MergeLayer(dense=True) (unet.py:273): 9 taps x 3 channels become one 64-wide K chunk instead of nine.   */
+    int32_t src1_single_tap, src1_wi;
+    /* Column split: GEMM columns n >= split_n (multiple of 16; 0 = off) are stored to out2 at channel n - split_n
+     * and take their residual from residual2.                                                                  */
+    int32_t split_n;
+    void *out2;
+    int64_t out2_stride_w, out2_stride_h, out2_stride_b;
+    int32_t c_store2;
+    const void *residual2;
+    int64_t res2_stride_w, res2_stride_h, res2_stride_b;
+    /* Fused 1x1 head (unet.py:276-278 `custom_conv_layer(ni, 3, ks=1)`): instead of storing the tile, write
+     * head_out[pixel][o] = sum_n y[n] * head_w[o][n] (o < 3; fp32, 4 floats per pixel; head_w is [3][N_total]).
+     * Requires a single N tile (BN == N_total).                                                                */
+    const float *head_w;
+    float *head_out;
+    int64_t head_stride_w, head_stride_h, head_stride_b;
 } havc_conv_desc;
 
 const char *havc_last_error(void);
@@ -89,10 +107,13 @@ int havc_conv_gemm(const havc_conv_desc *d, void *stream);
 
 /* ---- memory-bound network ops (NHWC 16-bit, C multiple of 8) -------------------------------- */
 
-/* im2col for tiny-Cin convolutions: out[b,oy,ox,(kh*ks+kw)*cin+c] = in[b,oy*stride-pad+kh,ox*stride-pad+kw,c],
- * zero outside the image, K zero-padded to Kp.  Feeds havc_conv_gemm for the ResNet 7x7/s2 stem
- * (torchvision conv1 behind vsdeoldify/fastai/vision/learner.py:54-63) and Zhang's model1.0
- * (vsdeoldify/colorization/colorizers/eccv16.py:16, siggraph17.py:20).  in: [B,H,W,Cs], out: [B,OH,OW,Kp]. */
+/* im2col for tiny-Cin convolutions over 8-channel-wide input pixels.  K layout: filter row kh occupies
+ * [kh*RW, kh*RW + ks*cin) with RW = round_up(ks*cin, 8): out[b,oy,ox, kh*RW + kw*cin + c] =
+ * in[b, oy*stride-pad+kh, ox*stride-pad+kw, c], zero outside the image; other K positions are never written
+ * (zero-initialise the buffer once).  Feeds havc_conv_gemm for the ResNet 7x7/s2 stem (torchvision conv1 behind
+ * vsdeoldify/fastai/vision/learner.py:54-63), for the 3 image channels of MergeLayer(dense=True)
+ * (vsdeoldify/deoldify/unet.py:273) and for Zhang's model1.0 (colorizers/eccv16.py:16, siggraph17.py:20).
+ * in: [B,H,W,8], out: [B,OH,OW,Kp]. */
 int havc_im2col_small(const void *in, void *out, int B, int H, int W, int Cs, int cin, int ks, int stride,
                       int pad, int Kp, int dtype, void *stream);
 /* nn.MaxPool2d(3, 2, 1) of the torchvision resnet stem. */
@@ -126,6 +147,8 @@ int havc_pre_vertical(const float *in, uint8_t *rgb_small, void *x, int B, int H
 /* Network head: 1x1 conv 259->3 + SigmoidRange(-3,3) (unet.py:276-281), de-normalise, clamp, *255, truncate
  * to u8 (filters.py:64-67), and — if transplant — ColorizerFilter._post_process (filters.py:100-110) at S x S
  * against rgb_small.  res: [B,S,S,Cs] 16-bit; w11: fp32 [3][Cs]; colored: u8 [B][3][S][S];
+ * With Cs == 0, `res` is instead fp32 logits [B][S][S][4] already produced by havc_conv_gemm's fused head
+ * (bias b11 not yet added) and w11 is ignored.
  * net_out (optional): fp32 [B][3][S][S] network output for parity tests; skip (optional): u8 [B], 1 = the
  * scene-change gate of vsslib/vsmodels.py:221-224 returned this frame uncoloured (colored := rgb_small). */
 int havc_head(const void *res, int Cs, const float *w11, const float *b11, const uint8_t *rgb_small,

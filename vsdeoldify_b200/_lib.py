@@ -55,6 +55,15 @@ class ConvDesc(C.Structure):
         ("up", C.c_int32), ("oy", C.c_int32), ("ox", C.c_int32),
         ("shuffle", C.c_int32), ("group_n", C.c_int32), ("c_store", C.c_int32),
         ("dtype", C.c_int32),
+        ("src1_single_tap", C.c_int32), ("src1_wi", C.c_int32),
+        ("split_n", C.c_int32),
+        ("out2", C.c_void_p),
+        ("out2_stride_w", C.c_int64), ("out2_stride_h", C.c_int64), ("out2_stride_b", C.c_int64),
+        ("c_store2", C.c_int32),
+        ("residual2", C.c_void_p),
+        ("res2_stride_w", C.c_int64), ("res2_stride_h", C.c_int64), ("res2_stride_b", C.c_int64),
+        ("head_w", C.c_void_p), ("head_out", C.c_void_p),
+        ("head_stride_w", C.c_int64), ("head_stride_h", C.c_int64), ("head_stride_b", C.c_int64),
     ]
 
 

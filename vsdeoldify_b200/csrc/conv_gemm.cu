@@ -29,7 +29,9 @@ static constexpr int kChunkK = 64;  // 64 x 16-bit = 128 B = one swizzle row
 static constexpr int kABytes = kTileM * kChunkK * 2;
 static constexpr int kMaxStages = 8;
 static constexpr int kThreads = 384;   // 4 control warps + 8 epilogue warps
-static constexpr int kMaxBN = 288;      // parameter staging rows (BN <= 272)
+static constexpr int kMaxBN = 320;      // parameter staging rows (BN <= 320)
+// epilogue shared memory: 2 x {bias,scale,shift}[kMaxBN] + head weights [3][kMaxBN] + head exchange [128][4]
+static constexpr int kEpiSmemFloats = 2 * 3 * kMaxBN + 3 * kMaxBN + 128 * 4;
 static constexpr uint32_t kTmemCols = 512;
 
 struct ConvParams {
@@ -56,6 +58,19 @@ struct ConvParams {
     long long osw, osh, osb;
     int up, oy, ox, shuffle, group_n, c_store;
     int dtype;
+    // K loop variant: src1 contributes once (tap offset 0) after all taps of src0 (an im2col'd side tensor)
+    int src1_single_tap, src1_wi;
+    // column split: GEMM columns >= split_n are stored to out2 / take their residual from residual2
+    int split_n;
+    void *out2;
+    long long o2sw, o2sh, o2sb;
+    int c_store2;
+    const void *residual2;
+    long long r2sw, r2sh, r2sb;
+    // fused 1x1 head: logits[pix][o] = sum_n y[n] * head_w[o][n]  (o < 3), written as fp32 [pix][4]; no tile store
+    const float *head_w;
+    float *head_out;
+    long long hsw, hsh, hsb;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -238,8 +253,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    const int ksteps_per_tap = p.chunks0 + p.chunks1;
-    const int ksteps = p.n_taps * ksteps_per_tap;
+    const int ksteps_per_tap = p.src1_single_tap ? p.chunks0 : (p.chunks0 + p.chunks1);
+    const int ksteps_main = p.n_taps * ksteps_per_tap;
+    const int ksteps = ksteps_main + (p.src1_single_tap ? p.chunks1 : 0);
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -254,28 +270,29 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 const int bt = t;
                 const int n0 = nt * p.BN;
                 const int w0 = wt * p.bw, h0 = ht * p.bh, b0 = bt * p.bb;
-                for (int tap = 0; tap < p.n_taps; ++tap) {
-                    const int cw = w0 + p.dw[tap], ch = h0 + p.dh[tap], cp = p.tp[tap], wi = p.twi[tap];
-                    for (int kc = 0; kc < ksteps_per_tap; ++kc) {
-                        mbar_wait(empty_bar(stage), phase ^ 1u);
-                        const uint32_t sa = smem_base + stage * p.stage_bytes;
-                        const uint32_t sb = sa + kABytes;
-                        mbar_arrive_expect_tx(full_bar(stage), p.stage_bytes);
-                        int wc;
-                        if (kc < p.chunks0) {
-                            tma_load_5d(sa, &tmA0, full_bar(stage), kc * kChunkK, cw, ch,
-                                        p.a_batched ? b0 : 0, cp);
-                            wc = kc * kChunkK;
-                        } else {
-                            tma_load_5d(sa, &tmA1, full_bar(stage), (kc - p.chunks0) * kChunkK, cw, ch,
-                                        p.a_batched ? b0 : 0, cp);
-                            wc = p.w_c1_off + (kc - p.chunks0) * kChunkK;
-                        }
-                        for (int l = 0; l < p.n_wloads; ++l)
-                            tma_load_4d(sb + l * p.w_box_rows * 128, &tmW, full_bar(stage), wc, wi,
-                                        n0 + l * p.w_box_rows, p.b_batched ? b0 : 0);
-                        if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    int cw = w0, ch = h0, cp = 0, wi = p.src1_wi, kc;
+                    bool from1;
+                    if (ks < ksteps_main) {
+                        const int tap = ks / ksteps_per_tap;
+                        kc = ks - tap * ksteps_per_tap;
+                        cw += p.dw[tap]; ch += p.dh[tap]; cp = p.tp[tap]; wi = p.twi[tap];
+                        from1 = kc >= p.chunks0;
+                        if (from1) kc -= p.chunks0;
+                    } else {   // single-tap side source
+                        kc = ks - ksteps_main;
+                        from1 = true;
                     }
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t sa = smem_base + stage * p.stage_bytes;
+                    const uint32_t sb = sa + kABytes;
+                    mbar_arrive_expect_tx(full_bar(stage), p.stage_bytes);
+                    tma_load_5d(sa, from1 ? &tmA1 : &tmA0, full_bar(stage), kc * kChunkK, cw, ch, p.a_batched ? b0 : 0, cp);
+                    const int wc = (from1 ? p.w_c1_off : 0) + kc * kChunkK;
+                    for (int l = 0; l < p.n_wloads; ++l)
+                        tma_load_4d(sb + l * p.w_box_rows * 128, &tmW, full_bar(stage), wc, wi, n0 + l * p.w_box_rows,
+                                    p.b_batched ? b0 : 0);
+                    if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
                 }
             }
         }
@@ -329,6 +346,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         uint32_t aphase = 0;
         int pbuf = 0;
         const int nchunks = (p.BN + 31) >> 5;
+        if (p.head_w != nullptr) {   // 1x1 head weights [3][BN] -> shared memory, once per CTA
+            float *hw = sparams + 2 * 3 * kMaxBN;
+            for (int i = etid; i < 3 * kMaxBN; i += 256) {
+                const int o = i / kMaxBN, c = i - o * kMaxBN;
+                hw[i] = (c < p.N_total) ? __ldg(p.head_w + o * p.N_total + c) : 0.f;
+            }
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+        }
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             int t = tile;
             const int nt = t % p.tiles_n; t /= p.tiles_n;
@@ -351,9 +376,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             asm volatile("bar.sync 1, 256;" ::: "memory");
             pbuf ^= 1;
 
-            const uint8_t *res_row = nullptr;
+            const uint8_t *res_row = nullptr, *res_row2 = nullptr;
             if (p.residual != nullptr && valid)
                 res_row = reinterpret_cast<const uint8_t *>(p.residual) + 2ll * (ob * p.rsb + oh * p.rsh + ow * p.rsw);
+            if (p.residual2 != nullptr && valid)
+                res_row2 = reinterpret_cast<const uint8_t *>(p.residual2) + 2ll * (ob * p.r2sb + oh * p.r2sh + ow * p.r2sw);
+            float hacc0 = 0.f, hacc1 = 0.f, hacc2 = 0.f;
 
             mbar_wait(tfull_bar(as), aphase);
             tc_fence_after();
@@ -371,8 +399,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         rres[g] = make_uint4(0, 0, 0, 0);
-                        if (n + 8 * g < p.c_store && c0 + 8 * g < p.BN)
-                            rres[g] = __ldg(reinterpret_cast<const uint4 *>(res_row + 2 * (n + 8 * g)));
+                        const int ng = n + 8 * g;
+                        if (c0 + 8 * g >= p.BN) continue;
+                        if (ng < p.split_n) {
+                            if (ng < p.c_store) rres[g] = __ldg(reinterpret_cast<const uint4 *>(res_row + 2 * ng));
+                        } else if (res_row2 != nullptr && ng - p.split_n < p.c_store2) {
+                            rres[g] = __ldg(reinterpret_cast<const uint4 *>(res_row2 + 2 * (ng - p.split_n)));
+                        }
                     }
                 }
                 tmem_ld_wait();
@@ -405,8 +438,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         py = oh * 2 + (g >> 1);
                         px = ow * 2 + (g & 1);
                     }
-                    if (chan >= p.c_store) continue;
-                    const bool hi_ok = (chan + 8) < p.c_store;
+                    const bool second = nn >= p.split_n;          // column split (out2 / residual2)
+                    if (second) chan = nn - p.split_n;
+                    const int cstore = second ? p.c_store2 : p.c_store;
+                    if (p.head_w == nullptr && chan >= cstore) continue;
+                    const bool hi_ok = (chan + 8) < cstore;
                     if (do_res) {
                         const uint32_t rr[8] = {rres[2 * hh].x, rres[2 * hh].y, rres[2 * hh].z, rres[2 * hh].w,
                                                 rres[2 * hh + 1].x, rres[2 * hh + 1].y, rres[2 * hh + 1].z,
@@ -422,9 +458,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
                         for (int j = 0; j < 16; ++j) y[j] = fmaxf(y[j], 0.f);
                     }
-                    const long long opix = ob * p.osb + py * p.osh + px * p.osw + chan;
+                    if (p.head_w != nullptr) {   // fused 1x1 head: three dot products over this thread's columns
+                        const float *hw = sparams + 2 * 3 * kMaxBN;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            hacc0 = fmaf(y[j], hw[cc + j], hacc0);
+                            hacc1 = fmaf(y[j], hw[kMaxBN + cc + j], hacc1);
+                            hacc2 = fmaf(y[j], hw[2 * kMaxBN + cc + j], hacc2);
+                        }
+                        continue;
+                    }
+                    const long long opix = second ? (ob * p.o2sb + py * p.o2sh + px * p.o2sw + chan)
+                                                  : (ob * p.osb + py * p.osh + px * p.osw + chan);
+                    void *obase = second ? p.out2 : p.out;
                     if (p.out_dtype == HAVC_F32) {
-                        float4 *dst = reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out) + opix);
+                        float4 *dst = reinterpret_cast<float4 *>(reinterpret_cast<float *>(obase) + opix);
                         dst[0] = make_float4(y[0], y[1], y[2], y[3]);
                         dst[1] = make_float4(y[4], y[5], y[6], y[7]);
                         if (hi_ok) {
@@ -432,7 +480,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                             dst[3] = make_float4(y[12], y[13], y[14], y[15]);
                         }
                     } else {
-                        uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<uint16_t *>(p.out) + opix);
+                        uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<uint16_t *>(obase) + opix);
                         const int od = p.out_dtype;
                         dst[0] = make_uint4(pack2(y[0], y[1], od), pack2(y[2], y[3], od), pack2(y[4], y[5], od),
                                             pack2(y[6], y[7], od));
@@ -449,6 +497,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             for (int ci = half; ci < nchunks; ci += 4) {
                 process(ci, va, vb);
                 if (ci + 2 < nchunks) process(ci + 2, vb, va);
+            }
+            if (p.head_w != nullptr) {   // the two warps of a lane quarter each hold half of the columns
+                float *hx = sparams + (2 * 3 + 3) * kMaxBN;   // [128 rows][4]
+                if (half == 1) {
+                    hx[r * 4 + 0] = hacc0; hx[r * 4 + 1] = hacc1; hx[r * 4 + 2] = hacc2;
+                }
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                if (half == 0 && valid) {
+                    const float4 o = make_float4(hacc0 + hx[r * 4 + 0], hacc1 + hx[r * 4 + 1], hacc2 + hx[r * 4 + 2], 0.f);
+                    *reinterpret_cast<float4 *>(p.head_out + ob * p.hsb + oh * p.hsh + ow * p.hsw) = o;
+                }
+                asm volatile("bar.sync 2, 256;" ::: "memory");
             }
             tc_fence_before();
             mbar_arrive(tempty_bar(as));
@@ -546,13 +606,13 @@ extern "C" int havc_conv_gemm(const havc_conv_desc *d, void *stream) {
     HAVC_CHECK_ARG(d->box_w > 0 && d->box_h > 0 && d->box_b > 0 && d->box_w * d->box_h * d->box_b == kTileM &&
                        d->box_w <= 256 && d->box_h <= 256 && d->box_b <= 256,
                    "havc_conv_gemm: box %dx%dx%d must multiply to 128", d->box_w, d->box_h, d->box_b);
-    HAVC_CHECK_ARG(d->BN >= 16 && d->BN % 16 == 0 && d->BN <= 272, "havc_conv_gemm: BN=%d unsupported", d->BN);
+    HAVC_CHECK_ARG(d->BN >= 16 && d->BN % 16 == 0 && d->BN <= kMaxBN, "havc_conv_gemm: BN=%d unsupported", d->BN);
     HAVC_CHECK_ARG(d->N_total > 0 && d->N_total % 16 == 0, "havc_conv_gemm: N_total=%d must be a multiple of 16", d->N_total);
     HAVC_CHECK_ARG(d->n_taps >= 1 && d->n_taps <= HAVC_MAX_TAPS, "havc_conv_gemm: n_taps=%d", d->n_taps);
     HAVC_CHECK_ARG(d->weight != nullptr && d->w_cin % 8 == 0 && d->w_rows > 0 && d->w_taps > 0 && d->w_batches > 0 &&
                        (reinterpret_cast<uintptr_t>(d->weight) & 15) == 0,
                    "havc_conv_gemm: weight tensor invalid");
-    HAVC_CHECK_ARG(d->out != nullptr && d->c_store > 0 && d->c_store % 8 == 0, "havc_conv_gemm: out/c_store invalid");
+    HAVC_CHECK_ARG((d->out != nullptr || d->head_w != nullptr) && d->c_store > 0 && d->c_store % 8 == 0, "havc_conv_gemm: out/c_store invalid");
     HAVC_CHECK_ARG(d->out_dtype == HAVC_F16 || d->out_dtype == HAVC_BF16 || d->out_dtype == HAVC_F32, "havc_conv_gemm: out_dtype");
     HAVC_CHECK_ARG(d->out_stride_w % 8 == 0 && d->out_stride_h % 8 == 0 && d->out_stride_b % 8 == 0 &&
                        (reinterpret_cast<uintptr_t>(d->out) & 15) == 0,
@@ -591,7 +651,7 @@ extern "C" int havc_conv_gemm(const havc_conv_desc *d, void *stream) {
     p.acc_stages = (2 * d->BN <= (int)kTmemCols) ? 2 : 1;
     p.acc_stride = d->BN;
     p.stage_bytes = kABytes + d->BN * 128;
-    int stages = (227 * 1024 - 1024 - 256 - 2 * 3 * kMaxBN * (int)sizeof(float)) / (int)p.stage_bytes;
+    int stages = (227 * 1024 - 1024 - 256 - kEpiSmemFloats * (int)sizeof(float)) / (int)p.stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     HAVC_CHECK_ARG(stages >= 2, "havc_conv_gemm: tile too large for shared memory");
     p.num_stages = stages;
@@ -610,6 +670,18 @@ extern "C" int havc_conv_gemm(const havc_conv_desc *d, void *stream) {
     p.osw = d->out_stride_w; p.osh = d->out_stride_h; p.osb = d->out_stride_b;
     p.up = d->up; p.oy = d->oy; p.ox = d->ox; p.shuffle = d->shuffle; p.group_n = d->group_n > 0 ? d->group_n : 16;
     p.c_store = d->c_store; p.dtype = d->dtype;
+    p.src1_single_tap = d->src1_single_tap; p.src1_wi = d->src1_wi;
+    p.split_n = d->split_n > 0 ? d->split_n : 0x7fffffff;
+    p.out2 = d->out2; p.o2sw = d->out2_stride_w; p.o2sh = d->out2_stride_h; p.o2sb = d->out2_stride_b;
+    p.c_store2 = d->c_store2;
+    p.residual2 = d->residual2; p.r2sw = d->res2_stride_w; p.r2sh = d->res2_stride_h; p.r2sb = d->res2_stride_b;
+    p.head_w = d->head_w; p.head_out = d->head_out;
+    p.hsw = d->head_stride_w; p.hsh = d->head_stride_h; p.hsb = d->head_stride_b;
+    if (d->src1_single_tap) HAVC_CHECK_ARG(two && d->src1_wi >= 0 && d->src1_wi < d->w_taps, "havc_conv_gemm: src1_single_tap needs src1 and a valid src1_wi");
+    if (d->split_n > 0) HAVC_CHECK_ARG(d->split_n % 16 == 0 && !d->shuffle && (d->out2 != nullptr || d->head_w != nullptr || d->residual2 != nullptr) &&
+                                           d->c_store2 % 8 == 0, "havc_conv_gemm: split_n must be a multiple of 16 with out2/residual2");
+    if (d->head_w) HAVC_CHECK_ARG(d->head_out != nullptr && d->BN == d->N_total && !d->shuffle && d->head_stride_w % 4 == 0,
+                                  "havc_conv_gemm: the fused head needs a single N tile (BN == N_total) and head_out");
 
     CUtensorMap tmA0, tmA1, tmW;
     int rc = encode_act(&tmA0, d->src0, d->dtype, d->box_w, d->box_h, d->a_batched ? d->box_b : 1);
@@ -631,7 +703,7 @@ extern "C" int havc_conv_gemm(const havc_conv_desc *d, void *stream) {
     }
     if (d->b_batched) HAVC_CHECK_ARG(d->box_b == 1, "havc_conv_gemm: b_batched=1 needs box_b=1");
 
-    const size_t smem = (size_t)p.num_stages * p.stage_bytes + 1024 + 256 + 2 * 3 * kMaxBN * sizeof(float);
+    const size_t smem = (size_t)p.num_stages * p.stage_bytes + 1024 + 256 + kEpiSmemFloats * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
         HAVC_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

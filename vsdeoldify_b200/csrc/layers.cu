@@ -15,34 +15,54 @@ static inline int grid_for(long long n_threads, int block) {
 
 // ---------------------------------------------------------------------------------------------
 // im2col for convolutions with a tiny channel count (7x7 s2 stem on the 3-channel normalised image,
-// torchvision resnet conv1 via vsdeoldify/fastai/vision/learner.py:54-63; Zhang model1.0 on the
-// 1-channel L image, colorizers/eccv16.py:16).  out[b,oy,ox, (kh*ks+kw)*cin + c] = in[b, oy*s-pad+kh,
-// ox*s-pad+kw, c] (zero outside), K padded with zeros to Kp.
+// torchvision resnet conv1 via vsdeoldify/fastai/vision/learner.py:54-63; the 3 image channels of
+// MergeLayer(dense=True) in the res_block; Zhang model1.0 on the 1-channel L image).
+// Input pixels are 8 channels (16 B) wide.  K layout of the output: filter row kh occupies
+// [kh*RW, kh*RW + ks*cin) with RW = round_up(ks*cin, 8), i.e. k = kh*RW + kw*cin + c; everything else is zero and
+// is never written (the buffer is zero-initialised once).  One thread = one (output pixel, filter row):
+// ks 16-byte loads, RW/8 16-byte stores.
 // ---------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void im2col_small_kernel(const T *__restrict__ in, T *__restrict__ out, int B, int H, int W, int Cs,
-                                    int cin, int ks, int stride, int pad, int OH, int OW, int Kp) {
-    const long long total = (long long)B * OH * OW * (Kp / 8);
+template <int KS>
+__global__ void im2col_rows_kernel(const uint4 *__restrict__ in, uint16_t *__restrict__ out, int B, int H, int W,
+                                   int cin, int stride, int pad, int OH, int OW, int Kp) {
+    constexpr int kMaxRW = ((KS * 8 + 7) / 8) * 8;
+    const int RW = ((KS * cin + 7) / 8) * 8;
+    const long long total = (long long)B * OH * OW * KS;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
-        const int kg = (int)(i % (Kp / 8));
-        long long pix = i / (Kp / 8);
+        const int kh = (int)(i % KS);
+        long long pix = i / KS;
         const int ox = (int)(pix % OW);
         const int oy = (int)((pix / OW) % OH);
         const int b = (int)(pix / ((long long)OW * OH));
-        T vals[8];
+        uint16_t v[kMaxRW];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int k = kg * 8 + j;
-            T v = T(0.f);
-            if (k < ks * ks * cin) {
-                const int c = k % cin, tap = k / cin;
-                const int iy = oy * stride - pad + tap / ks, ix = ox * stride - pad + tap % ks;
-                if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = in[(((long long)b * H + iy) * W + ix) * Cs + c];
+        for (int j = 0; j < kMaxRW; ++j) v[j] = 0;
+        const int iy = oy * stride - pad + kh;
+        if (iy >= 0 && iy < H) {
+#pragma unroll
+            for (int kw = 0; kw < KS; ++kw) {
+                const int ix = ox * stride - pad + kw;
+                if (ix < 0 || ix >= W) continue;
+                const uint4 q = __ldg(in + ((long long)b * H + iy) * W + ix);
+                const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    if (c < cin) v[kw * cin + c] = (uint16_t)((w[c >> 1] >> ((c & 1) * 16)) & 0xffff);
             }
-            vals[j] = v;
         }
-        *reinterpret_cast<uint4 *>(out + pix * Kp + kg * 8) = *reinterpret_cast<uint4 *>(vals);
+        uint16_t *dst = out + pix * Kp + kh * RW;
+#pragma unroll
+        for (int g = 0; g < kMaxRW / 8; ++g) {
+            if (g * 8 < RW) {
+                uint4 o;
+                o.x = v[g * 8 + 0] | ((uint32_t)v[g * 8 + 1] << 16);
+                o.y = v[g * 8 + 2] | ((uint32_t)v[g * 8 + 3] << 16);
+                o.z = v[g * 8 + 4] | ((uint32_t)v[g * 8 + 5] << 16);
+                o.w = v[g * 8 + 6] | ((uint32_t)v[g * 8 + 7] << 16);
+                *reinterpret_cast<uint4 *>(dst + g * 8) = o;
+            }
+        }
     }
 }
 
@@ -200,16 +220,20 @@ static bool dt16(int d) { return d == HAVC_F16 || d == HAVC_BF16; }
 
 extern "C" int havc_im2col_small(const void *in, void *out, int B, int H, int W, int Cs, int cin, int ks, int stride,
                                  int pad, int Kp, int dtype, void *stream) {
-    HAVC_CHECK_ARG(in && out && dt16(dtype) && Kp % 8 == 0 && Kp >= ks * ks * cin && cin <= Cs,
-                   "havc_im2col_small: bad arguments");
+    const int RW = ((ks * cin + 7) / 8) * 8;
+    HAVC_CHECK_ARG(in && out && dt16(dtype) && Kp % 8 == 0 && Kp >= ks * RW && Cs == 8 && cin >= 1 && cin <= 8 &&
+                       (ks == 1 || ks == 3 || ks == 7),
+                   "havc_im2col_small: needs 8-channel input pixels, cin <= 8, ks in {1,3,7}, Kp >= ks*round_up(ks*cin,8)");
     const int OH = (H + 2 * pad - ks) / stride + 1, OW = (W + 2 * pad - ks) / stride + 1;
-    const long long n = (long long)B * OH * OW * (Kp / 8);
-    if (dtype == HAVC_F16)
-        im2col_small_kernel<__half><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
-            (const __half *)in, (__half *)out, B, H, W, Cs, cin, ks, stride, pad, OH, OW, Kp);
+    const long long n = (long long)B * OH * OW * ks;
+    const int grid = grid_for(n, 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ks == 7)
+        im2col_rows_kernel<7><<<grid, 256, 0, st>>>((const uint4 *)in, (uint16_t *)out, B, H, W, cin, stride, pad, OH, OW, Kp);
+    else if (ks == 3)
+        im2col_rows_kernel<3><<<grid, 256, 0, st>>>((const uint4 *)in, (uint16_t *)out, B, H, W, cin, stride, pad, OH, OW, Kp);
     else
-        im2col_small_kernel<__nv_bfloat16><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
-            (const __nv_bfloat16 *)in, (__nv_bfloat16 *)out, B, H, W, Cs, cin, ks, stride, pad, OH, OW, Kp);
+        im2col_rows_kernel<1><<<grid, 256, 0, st>>>((const uint4 *)in, (uint16_t *)out, B, H, W, cin, stride, pad, OH, OW, Kp);
     HAVC_LAUNCHED();
     return HAVC_OK;
 }

@@ -132,6 +132,53 @@ __global__ void pre_vertical_kernel(const float *__restrict__ in, uint8_t *__res
     }
 }
 
+// Shared tail of the head: logits -> SigmoidRange(-3,3) -> de-normalise -> clamp -> *255 -> truncate -> (skip |
+// S x S luma transplant) -> colored u8 planes.
+__device__ __forceinline__ void head_finish_pixel(const float lg[3], long long pix, const uint8_t *__restrict__ rgb_small,
+                                                  uint8_t *__restrict__ colored, float *__restrict__ net_out,
+                                                  const uint8_t *__restrict__ skip, int S, int transplant) {
+    const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+    const int ox = (int)(pix % S);
+    const int oy = (int)((pix / S) % S);
+    const int b = (int)(pix / ((long long)S * S));
+    int q[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float sg = 1.f / (1.f + expf(-lg[c]));
+        const float y = __fadd_rn(__fmul_rn(sg, 6.f), -3.f);                 // SigmoidRange(-3,3)
+        if (net_out) net_out[(((long long)b * 3 + c) * S + oy) * S + ox] = y;
+        float d = __fadd_rn(__fmul_rn(y, stdv[c]), mean[c]);                 // denorm
+        d = fminf(fmaxf(d, 0.f), 1.f);                                       // reconstruct: clamp(0,1)
+        q[c] = (int)__fmul_rn(d, 255.f);                                     // astype(uint8): truncation
+    }
+    int r = q[0], g = q[1], bl = q[2];
+    const long long o = ((long long)b * 3 * S + oy) * S + ox;
+    if (skip != nullptr && skip[b]) {   // scene-change gate: the selector returned the frame unchanged
+        r = rgb_small[o]; g = rgb_small[o + (long long)S * S]; bl = rgb_small[o + 2ll * S * S];
+    } else if (transplant) {
+        luma_transplant(rgb_small[o], rgb_small[o + (long long)S * S], rgb_small[o + 2ll * S * S], q[0], q[1], q[2], r, g,
+                        bl);
+    }
+    colored[o] = (uint8_t)r;
+    colored[o + (long long)S * S] = (uint8_t)g;
+    colored[o + 2ll * S * S] = (uint8_t)bl;
+}
+
+// Head on pre-computed logits (the 1x1 conv ran inside the last GEMM's epilogue): fp32 [B*S*S][4], one thread/pixel.
+__global__ void head_from_logits_kernel(const float4 *__restrict__ logits, const float *__restrict__ b11,
+                                        const uint8_t *__restrict__ rgb_small, uint8_t *__restrict__ colored,
+                                        float *__restrict__ net_out, const uint8_t *__restrict__ skip, int B, int S,
+                                        int transplant) {
+    const long long total = (long long)B * S * S;
+    const float b0 = __ldg(b11), b1 = __ldg(b11 + 1), b2 = __ldg(b11 + 2);
+    for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < total;
+         pix += (long long)gridDim.x * blockDim.x) {
+        const float4 l = __ldg(logits + pix);
+        const float lg[3] = {l.x + b0, l.y + b1, l.z + b2};
+        head_finish_pixel(lg, pix, rgb_small, colored, net_out, skip, S, transplant);
+    }
+}
+
 // Output head: one warp per pixel.  logits = W11 . res + b; y = sigmoid*6-3; rgb = trunc(clamp(y*std+mean)*255);
 // then the S x S luma transplant against the resized source.  Optionally dumps the fp32 net output.
 __global__ void head_kernel(const void *__restrict__ res, int Cs, const float *__restrict__ w11 /*[3][Cs]*/,
@@ -142,7 +189,6 @@ __global__ void head_kernel(const void *__restrict__ res, int Cs, const float *_
     const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const long long total = (long long)B * S * S;
-    const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
     // each lane owns channel groups g = lane, lane+32 (Cs <= 512): its slice of the 1x1 weights stays in registers
     constexpr int kG = 2;
     float wr[kG][3][8];
@@ -178,31 +224,8 @@ __global__ void head_kernel(const void *__restrict__ res, int Cs, const float *_
             a2 += __shfl_xor_sync(0xffffffffu, a2, o);
         }
         if (lane == 0) {
-            const int ox = (int)(pix % S);
-            const int oy = (int)((pix / S) % S);
-            const int b = (int)(pix / ((long long)S * S));
             const float lg[3] = {a0 + __ldg(b11), a1 + __ldg(b11 + 1), a2 + __ldg(b11 + 2)};
-            int q[3];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float sg = 1.f / (1.f + expf(-lg[c]));
-                const float y = __fadd_rn(__fmul_rn(sg, 6.f), -3.f);                 // SigmoidRange(-3,3)
-                if (net_out) net_out[(((long long)b * 3 + c) * S + oy) * S + ox] = y;
-                float d = __fadd_rn(__fmul_rn(y, stdv[c]), mean[c]);                 // denorm
-                d = fminf(fmaxf(d, 0.f), 1.f);                                       // reconstruct: clamp(0,1)
-                q[c] = (int)__fmul_rn(d, 255.f);                                     // astype(uint8): truncation
-            }
-            int r = q[0], g = q[1], bl = q[2];
-            const long long o = ((long long)b * 3 * S + oy) * S + ox;
-            if (skip != nullptr && skip[b]) {   // scene-change gate: the selector returned the frame unchanged
-                r = rgb_small[o]; g = rgb_small[o + (long long)S * S]; bl = rgb_small[o + 2ll * S * S];
-            } else if (transplant) {
-                luma_transplant(rgb_small[o], rgb_small[o + (long long)S * S], rgb_small[o + 2ll * S * S], q[0], q[1],
-                                q[2], r, g, bl);
-            }
-            colored[o] = (uint8_t)r;
-            colored[o + (long long)S * S] = (uint8_t)g;
-            colored[o + 2ll * S * S] = (uint8_t)bl;
+            head_finish_pixel(lg, pix, rgb_small, colored, net_out, skip, S, transplant);
         }
     }
 }
@@ -304,9 +327,16 @@ extern "C" int havc_pre_vertical(const float *in, uint8_t *rgb_small, void *x, i
 extern "C" int havc_head(const void *res, int Cs, const float *w11, const float *b11, const uint8_t *rgb_small,
                          uint8_t *colored, float *net_out, const uint8_t *skip, int B, int S, int dtype, int transplant,
                          void *stream) {
-    HAVC_CHECK_ARG(res && w11 && b11 && colored && Cs % 8 == 0 && ((!transplant && !skip) || rgb_small) &&
+    HAVC_CHECK_ARG(res && b11 && colored && Cs % 8 == 0 && Cs <= 512 && ((!transplant && !skip) || rgb_small) &&
                        (dtype == HAVC_F16 || dtype == HAVC_BF16),
                    "havc_head: bad arguments");
+    if (Cs == 0) {   // `res` holds fp32 logits [B*S*S][4] produced by the fused-head GEMM epilogue
+        head_from_logits_kernel<<<grid1d((long long)B * S * S, 256), 256, 0, (cudaStream_t)stream>>>(
+            (const float4 *)res, b11, rgb_small, colored, net_out, skip, B, S, transplant);
+        HAVC_LAUNCHED();
+        return HAVC_OK;
+    }
+    HAVC_CHECK_ARG(w11 != nullptr, "havc_head: w11 missing");
     head_kernel<<<grid1d((long long)B * S * S * 32, 256), 256, 0, (cudaStream_t)stream>>>(
         res, Cs, w11, b11, rgb_small, colored, net_out, skip, B, S, dtype, transplant);
     HAVC_LAUNCHED();

@@ -83,7 +83,7 @@ class DeoldifyEngine:
         chk(lib.havc_pre_vertical(self.tmp_down.data_ptr(), self.rgb_small.data_ptr(), self.prog.x.data_ptr(), B, H, S,
                                   tv.start.data_ptr(), tv.w.data_ptr(), tv.taps, self.hd, stream), "pre.v")
         self.prog.run(stream)
-        chk(lib.havc_head(self.prog.res.data_ptr(), self.prog.n_res_channels, self.prog.w11.data_ptr(),
+        chk(lib.havc_head(self.prog.logits.data_ptr(), 0, None,
                           self.prog.b11.data_ptr(), self.rgb_small.data_ptr(), self.colored.data_ptr(),
                           self.net_out.data_ptr() if self.net_out is not None else None, self.skip.data_ptr(), B, S,
                           self.hd, 1, stream),

@@ -187,7 +187,9 @@ def make_conv(src0: torch.Tensor, weight: torch.Tensor, out: torch.Tensor, taps,
               bias=None, scale=None, shift=None, relu1=False, relu2=False, residual=None,
               out_space: Optional[Tuple[int, int, int]] = None, box=None, a_batched=True, b_batched=False,
               up=1, oy=0, ox=0, shuffle=False, group_n=0, c_store: Optional[int] = None,
-              out_view: Optional[ActView] = None, name: str = "") -> ConvOp:
+              src1_single_tap: bool = False, src1_wi: int = 0, split_n: int = 0, out2: Optional[torch.Tensor] = None,
+              c_store2: int = 0, residual2: Optional[torch.Tensor] = None, head_w: Optional[torch.Tensor] = None,
+              head_out: Optional[torch.Tensor] = None, name: str = "") -> ConvOp:
     """src0/src1: NHWC (or [P,B,H,W,C]) 16-bit device tensors; weight: packed [rows,taps,cin] or
     [batches,rows,taps,cin]; out: NHWC tensor written at pixel (h*up+oy, w*up+ox)."""
     d = ConvDesc()
@@ -232,11 +234,31 @@ def make_conv(src0: torch.Tensor, weight: torch.Tensor, out: torch.Tensor, taps,
         assert residual.dtype == src0.dtype and residual.dim() == 4
         d.residual = residual.data_ptr()
         d.res_stride_b, d.res_stride_h, d.res_stride_w = residual.stride()[:3]
-    d.out = out.data_ptr()
-    d.out_dtype = havc_dtype(out.dtype)
-    assert out.dim() == 4 and out.stride(-1) == 1
-    d.out_stride_b, d.out_stride_h, d.out_stride_w = out.stride()[:3]
+    if out is not None:
+        d.out = out.data_ptr()
+        d.out_dtype = havc_dtype(out.dtype)
+        assert out.dim() == 4 and out.stride(-1) == 1
+        d.out_stride_b, d.out_stride_h, d.out_stride_w = out.stride()[:3]
+    else:
+        assert head_w is not None, "a launch without an output tensor needs the fused head"
+        d.out_dtype = d.dtype
     d.up, d.oy, d.ox = up, oy, ox
     d.shuffle, d.group_n = int(shuffle), group_n
     d.c_store = c_store if c_store is not None else out.shape[-1]
+    d.src1_single_tap, d.src1_wi, d.split_n = int(src1_single_tap), src1_wi, split_n
+    if out2 is not None:
+        assert out2.dim() == 4 and out2.stride(-1) == 1 and out2.dtype == out.dtype
+        d.out2 = out2.data_ptr()
+        d.out2_stride_b, d.out2_stride_h, d.out2_stride_w = out2.stride()[:3]
+    d.c_store2 = c_store2
+    if residual2 is not None:
+        assert residual2.dtype == src0.dtype and residual2.dim() == 4
+        d.residual2 = residual2.data_ptr()
+        d.res2_stride_b, d.res2_stride_h, d.res2_stride_w = residual2.stride()[:3]
+    if head_w is not None:
+        assert head_w.dtype == torch.float32 and head_w.numel() == 3 * d.N_total and head_out.dtype == torch.float32
+        assert head_out.dim() == 4 and head_out.shape[-1] == 4
+        d.head_w, d.head_out = head_w.data_ptr(), head_out.data_ptr()
+        d.head_stride_b, d.head_stride_h, d.head_stride_w = head_out.stride()[:3]
+    keep += [out2, residual2, head_w, head_out]
     return ConvOp(d, keep, name=name)

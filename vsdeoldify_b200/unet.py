@@ -11,8 +11,11 @@ Graph (reference: DynamicUnetWide unet.py:208-285, DynamicUnetDeep unet.py:94-16
     -> BN+ReLU -> middle_conv x2 (ReLU->BN epilogue)
     -> 4 x [shuf 1x1 GEMM (BN folded, ReLU, PixelShuffle store) -> blur ; BN+ReLU(skip) ; 3x3 GEMM over two
             K sources (no concat) (ReLU->BN epilogue) ; (+ self-attention as 4 GEMMs + row soft-max)]
-    -> shuf 1x1 (+bias, ReLU, PixelShuffle store) -> blur into the 'cat' buffer next to x
-    -> res_block: 2 x 3x3 GEMM (+bias, ReLU; second adds the cat buffer) -> head kernel.
+    -> shuf 1x1 (+bias, ReLU, PixelShuffle store) -> blur = u
+    -> res_block on cat([u, x]): 2 x 3x3 GEMM whose K loop is 9 taps x u-channels + ONE im2col chunk holding the 3
+       image channels of all 9 taps (37 instead of 45 K steps); the first stores its 3 extra output channels to a
+       side tensor (column split), the second adds the identity from (u, x) and applies the 1x1 head in its
+       epilogue, writing only fp32 logits -> head kernel (sigmoid, de-normalise, quantise, luma transplant).
 """
 from __future__ import annotations
 
@@ -183,9 +186,11 @@ class UnetProgram:
         # ---- encoder stem: 7x7/s2 conv as im2col + GEMM, BN folded, ReLU --------------------------
         w = sd["layers.0.0.weight"].float()
         sc, sh = bn_affine(sd, "layers.0.1")
-        wf = (w * sc.view(-1, 1, 1, 1)).permute(0, 2, 3, 1).reshape(64, 147)     # K order (kh, kw, c)
-        Kp = chan_storage(147)
-        wf = torch.cat([wf, wf.new_zeros(64, Kp - 147)], 1).view(64, Kp, 1, 1)
+        # K order of havc_im2col_small: k = kh*24 + kw*3 + c  (each filter row padded from 21 to 24)
+        wf = (w * sc.view(-1, 1, 1, 1)).permute(0, 2, 3, 1).reshape(64, 7, 21)
+        Kp = chan_storage(7 * 24)
+        wf = torch.cat([wf, wf.new_zeros(64, 7, 3)], 2).reshape(64, 168)
+        wf = torch.cat([wf, wf.new_zeros(64, Kp - 168)], 1).view(64, Kp, 1, 1)
         H2 = S // 2
         col = self.buf(B, H2, H2, Kp, zero=True)
         xp, cp = self.x.data_ptr(), col.data_ptr()
@@ -231,66 +236,75 @@ class UnetProgram:
             y = self._unet_block(y, s, f"layers.{4 + i}")
             self.tap(f"block{i}", y)
 
-        # ---- layers[8] PixelShuffle_ICNR -> cat buffer [u | x] ---------------------------------------
+        # ---- layers[8] PixelShuffle_ICNR; layers[9] MergeLayer(dense); layers[10] res_block; layers[11] head -------
         w8 = folded_weight(sd, "layers.8.conv.0")
         t8 = self.conv("shuf8.conv", y, w8, bias=sd["layers.8.conv.0.bias"].float(), relu1=True, shuffle=True)
-        cu = w8.shape[0] // 4
-        assert cu % 8 == 0 or True
-        cu8 = pad_to(cu, 8)
+        u = self.blur("shuf8.blur", t8)                         # [B,S,S,cu_s]: the 'x' half of cat([x, x.orig])
+        self.tap("shuf8", u)
+        cu = w8.shape[0] // 4                                   # real channels of u (256 wide / 300 deep)
+        cu_s = u.shape[-1]                                      # storage width (multiple of 64)
+        split = pad_to(cu, 16)                                  # GEMM columns [0,split) = main, [split,split+16) = 3 image ch
+        n_tot = split + 16
         ncat = cu + 3
-        cat = self.buf(B, S, S, chan_storage(cu8 + 8), zero=True)
-        # the cat buffer stores u at [0,cu8) and x at [cu8, cu8+8); weights are packed with matching splits
-        self.blur("shuf8.blur", t8, out=cat)
-        ones, zeros = torch.ones(8), torch.zeros(8)
-        self.affine("cat.x", self.x, ones, zeros, False, out=cat, out_c_off=cu8, c=8)
-        self.tap("cat", cat)
-        self.cat_splits = [cu, 3] if cu8 != cu else None
-        # res_block (fastai/layers.py:154-161): two conv+bias+ReLU, then + input
-        ccat = cu8 + 8                      # logical channel count of the cat layout [u | pad | x | pad]
-        w0 = self._pad_cin_to_cat(folded_weight(sd, "layers.10.layers.0.0"), cu, cu8, ccat)
-        w1 = self._pad_cin_to_cat(folded_weight(sd, "layers.10.layers.1.0"), cu, cu8, ccat)
-        # output channels of both convs must line up with the cat buffer's channel positions
-        w0 = self._pad_cout_to_cat(w0, cu, cu8, ccat)
-        w1 = self._pad_cout_to_cat(w1, cu, cu8, ccat)
-        b0 = self._pad_vec_to_cat(sd["layers.10.layers.0.0.bias"].float(), cu, cu8, ccat)
-        b1 = self._pad_vec_to_cat(sd["layers.10.layers.1.0.bias"].float(), cu, cu8, ccat)
-        r1 = self.conv("res.conv0", cat, w0, ks=3, bias=b0, relu1=True, out_c=cu8 + 8)
-        self.ops[-1].flops = 2.0 * B * S * S * ncat * ncat * 9
-        r2 = self.conv("res.conv1", r1, w1, ks=3, bias=b1, relu1=True, residual=cat, out_c=cu8 + 8)
-        self.ops[-1].flops = 2.0 * B * S * S * ncat * ncat * 9
-        self.tap("res", r2)
-        self.res = r2
-        # head weights (layers.11 1x1 conv + bias), laid out on the cat channel positions
+
+        def im2col3(name, src):
+            """3x3 neighbourhood of the 3 leading channels of an 8-channel tensor -> one 64-wide K chunk."""
+            col = self.buf(B, S, S, 64, zero=True)
+            ip, op_ = src.data_ptr(), col.data_ptr()
+
+            def fn(stream):
+                _lib.check(lib.havc_im2col_small(ip, op_, B, S, S, 8, 3, 3, 1, 1, 64, hd, stream), name)
+            self.aux(name, fn, nbytes=B * S * S * (16.0 + 96.0))
+            return col
+
+        def pack_tail(wt):
+            """[ncat, ncat, 3, 3] -> [n_tot rows][9 taps][cu_s + 64]: main channels per tap, the 3 image channels of all
+            9 taps as one im2col chunk (k = kh*16 + kw*3 + c) stored at weight tap 0, channels [cu_s, cu_s+64)."""
+            wk = torch.zeros(n_tot, 9, cu_s + 64)
+            rows = torch.cat([torch.arange(cu), split + torch.arange(3)])
+            wk[rows, :, :cu] = wt[:, :cu].reshape(ncat, cu, 9).permute(0, 2, 1)
+            for kh in range(3):
+                for kw in range(3):
+                    wk[rows, 0, cu_s + kh * 16 + kw * 3: cu_s + kh * 16 + kw * 3 + 3] = wt[:, cu:, kh, kw]
+            return wk.to(self.dtype).contiguous().to(self.dev)
+
+        def cols(v, fill=0.0):
+            o = torch.full((n_tot,), fill)
+            o[:cu] = v[:cu]
+            o[split:split + 3] = v[cu:]
+            return self.dev_f32(o)
+
+        taps9 = ops.taps_for(3)
+        xcol = im2col3("cat.im2col_x", self.x)
+        w0 = pack_tail(folded_weight(sd, "layers.10.layers.0.0"))
+        w1 = pack_tail(folded_weight(sd, "layers.10.layers.1.0"))
+        self.keep += [w0, w1]
+        r1 = self.buf(B, S, S, cu_s, zero=True)
+        r1x = self.buf(B, S, S, 8, zero=True)
+        op = ops.make_conv(u, w0, r1, taps9, src1=xcol, w_c1_off=cu_s, n_total=n_tot, bn=n_tot,
+                           bias=cols(sd["layers.10.layers.0.0.bias"].float()), relu1=True, out_space=(B, S, S),
+                           c_store=pad_to(cu, 8), src1_single_tap=True, src1_wi=0, split_n=split, out2=r1x, c_store2=8,
+                           name="res.conv0")
+        self.ops.append(Op("res.conv0", op.launch, flops=2.0 * B * S * S * ncat * ncat * 9, kind="gemm"))
+        self.keep.append(op)
+        r1col = im2col3("res.im2col_r1", r1x)
+        # second conv: +bias, ReLU, + cat([u, x]) (the res_block's identity), then the fused 1x1 head -> fp32 logits
         w11 = folded_weight(sd, "layers.11.0").view(3, ncat)
-        w11p = torch.zeros(3, cat.shape[-1])
+        w11p = torch.zeros(3, n_tot)
         w11p[:, :cu] = w11[:, :cu]
-        w11p[:, cu8:cu8 + 3] = w11[:, cu:]
+        w11p[:, split:split + 3] = w11[:, cu:]
         self.w11 = self.dev_f32(w11p)
         self.b11 = self.dev_f32(sd["layers.11.0.bias"].float())
-        self.head_flops = 2.0 * B * S * S * ncat * 3
-        self.n_res_channels = cat.shape[-1]
-
-    @staticmethod
-    def _pad_cin_to_cat(w, cu, cu8, ccat):
-        """[Cout, cu+3, k, k] -> [Cout, ccat, k, k] with the 3 image channels moved to position cu8."""
-        out = w.new_zeros(w.shape[0], ccat, w.shape[2], w.shape[3])
-        out[:, :cu] = w[:, :cu]
-        out[:, cu8:cu8 + 3] = w[:, cu:]
-        return out
-
-    @staticmethod
-    def _pad_cout_to_cat(w, cu, cu8, ccat):
-        out = w.new_zeros(ccat, *w.shape[1:])
-        out[:cu] = w[:cu]
-        out[cu8:cu8 + 3] = w[cu:]
-        return out
-
-    @staticmethod
-    def _pad_vec_to_cat(v, cu, cu8, ccat):
-        out = v.new_zeros(ccat)
-        out[:cu] = v[:cu]
-        out[cu8:cu8 + 3] = v[cu:]
-        return out
+        self.logits = self.buf(B, S, S, 4, dtype=torch.float32, zero=True)
+        op = ops.make_conv(r1, w1, None, taps9, src1=r1col, w_c1_off=cu_s, n_total=n_tot, bn=n_tot,
+                           bias=cols(sd["layers.10.layers.1.0.bias"].float()), relu1=True, out_space=(B, S, S),
+                           c_store=pad_to(cu, 8), src1_single_tap=True, src1_wi=0, split_n=split, c_store2=8,
+                           residual=u, residual2=self.x, head_w=self.w11, head_out=self.logits, name="res.conv1")
+        self.ops.append(Op("res.conv1+head", op.launch, flops=2.0 * B * S * S * ncat * ncat * 9 + 2.0 * B * S * S * ncat * 3,
+                           kind="gemm"))
+        self.keep.append(op)
+        self.tap("logits", self.logits)
+        self.head_flops = 0.0
 
     def _fold_bn(self, p_conv, p_bn):
         w = self.sd[p_conv + ".weight"].float()
