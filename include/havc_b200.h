@@ -135,8 +135,10 @@ int havc_softmax_rows(const float *in, void *out, long long rows, int cols, int 
 
 /* ---- frame pre / post pixel passes (planar u8 RGB frames [B][3][H][W]) ----------------------- */
 
-/* Table-driven separable resampling, horizontal pass: out[row][o] = sum_t weights[o][t]*in[row][start[o]+t].
- * With Spline64 tables this is zimg's resize.Spline64 of vsdeoldify/__init__.py:2504 and :3547. */
+/* Table-driven separable resampling, horizontal pass: out[row][o] = sum_t weights_t[t][o]*in[row][start[o]+t]
+ * (horizontal passes take the weight table TRANSPOSED, [taps][Wout], so a warp reads it coalesced; vertical
+ * passes take it as [Hout][taps]).  With Spline64 tables this is zimg's resize.Spline64 of
+ * vsdeoldify/__init__.py:2504 and :3547. */
 int havc_resample_h(const uint8_t *in, float *out, long long rows, int Win, int Wout, const int *start,
                     const float *weights, int taps, void *stream);
 /* Vertical pass of the squeeze to S x S, fused with ColorizerFilter._transform (Pillow 'L' luma,
@@ -154,13 +156,18 @@ int havc_pre_vertical(const float *in, uint8_t *rgb_small, void *x, int B, int H
 int havc_head(const void *res, int Cs, const float *w11, const float *b11, const uint8_t *rgb_small,
               uint8_t *colored, float *net_out, const uint8_t *skip, int B, int S, int dtype, int transplant,
               void *stream);
+/* PIL.Image.blend(a, b, alpha) = trunc(a + alpha*(b-a)) on n u8 values (n % 16 == 0): the 50/50 mix of the
+ * 'stable'/'artistic' generator with the 'video' one (vsdeoldify/deoldify/visualize.py:129,135) and
+ * image_weighted_merge (vsdeoldify/vsslib/imfilters.py:113-124). */
+int havc_blend_u8(const uint8_t *a, const uint8_t *b, uint8_t *out, long long n, float alpha, void *stream);
 /* Vertical pass on u8 planes (first pass of the resize back to W x H, run on the S-wide image):
  * out[plane][oy][x] = sum_t weights[oy][t] * in[plane][start[oy]+t][x].  in: u8 [planes][Hin][W]; out: float. */
 int havc_resample_v(const uint8_t *in, float *out, long long planes, int Hin, int Hout, int W, const int *start,
                     const float *weights, int taps, void *stream);
 /* Final horizontal pass of the resize back to W x H fused with vs_recover_clip_luma / chroma_post_process
  * (vsdeoldify/vsslib/vsfilters.py:863-899, imfilters.py:312-321): keep the luma of `orig`, the chroma of the
- * upscaled colour image (OpenCV Q14 8-bit YUV).  in: float [B][3][H][S]; orig/out: u8 [B][3][H][W]. */
+ * upscaled colour image (OpenCV Q14 8-bit YUV).  in: float [B][3][H][S]; orig/out: u8 [B][3][H][W];
+ * weights transposed [taps][W]. */
 int havc_post_horizontal(const float *in, const uint8_t *orig, uint8_t *out, int B, int S, int H, int W,
                          const int *start, const float *weights, int taps, int transplant, void *stream);
 

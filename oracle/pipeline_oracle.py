@@ -29,13 +29,21 @@ def net_output_square(sd, rgb_sq: np.ndarray) -> np.ndarray:
 
 
 def havc_colorizer_frame(sd, frame: np.ndarray, render_factor: int = 24, kernel: str = "spline64",
-                         return_stages: bool = False):
-    """frame: uint8 [H,W,3].  Returns uint8 [H,W,3] (and the intermediate stages on request)."""
+                         return_stages: bool = False, skip: bool = False, sd_other=None, video_weight: float = 0.5):
+    """frame: uint8 [H,W,3].  Returns uint8 [H,W,3] (and the intermediate stages on request).
+    skip: the scene-change gate returned the squeezed frame unchanged (vsslib/vsmodels.py:221-224).
+    sd_other: 'stable'/'artistic' generator blended with the video one at S x S (visualize.py:118-137)."""
     H, W = frame.shape[:2]
     S = min(render_factor * 16, W)
     small = px.resize_plane_u8(frame, S, S, kernel)                   # clip.resize.Spline64(S, S)
-    model_img = model_process_square(sd, small)                       # _scale_to_square is the identity here
-    colored = px.chroma_post_process(model_img, small)                # _post_process at S x S
+    if skip:
+        model_img = colored = small
+    else:
+        model_img = model_process_square(sd, small)                   # _scale_to_square is the identity here
+        colored = px.chroma_post_process(model_img, small)            # _post_process at S x S
+        if sd_other is not None:
+            other = px.chroma_post_process(model_process_square(sd_other, small), small)
+            colored = px.pil_blend(other, colored, video_weight)
     up = px.resize_plane_u8(colored, W, H, kernel)                    # clip_lowres.resize.Spline64(W, H)
     out = px.chroma_post_process(up, frame)                           # vs_recover_clip_luma
     if return_stages:

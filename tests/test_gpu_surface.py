@@ -1,0 +1,97 @@
+"""GPU tests through the plugin surface (HAVC_colorizer / HAVC_main on clips): frame order under out-of-order
+requests, bit-exact property pass-through, scene-change gating, and the stable/artistic S x S blend against the
+CPU oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _register():
+    from oracle import synth_weights
+    from vsdeoldify_b200 import havc
+    if "ColorizeVideo_gen" not in havc._REGISTERED:
+        havc.register_state_dict("ColorizeVideo_gen", synth_weights.make_unet_state_dict("wide", 1234))
+        havc.register_state_dict("ColorizeStable_gen", synth_weights.make_unet_state_dict("wide", 4321))
+        havc.register_state_dict("ColorizeArtistic_gen", synth_weights.make_unet_state_dict("deep", 1234))
+    return havc
+
+
+def _clip(n, h, w, seed=50):
+    from oracle import synth_weights
+    from vsdeoldify_b200 import vs_shim
+    fr = np.stack([np.stack([synth_weights.make_test_frame(seed + 3 * i + c, h, w).numpy() for c in range(3)]) for i in range(n)])
+    props = [{"_SceneChangePrev": int(i in (0, 4)), "_SceneChangeNext": int(i == 3), "sc_threshold": 0.1, "sc_frequency": 0,
+              "sc_luma": 0.5, "sc_ratio": 1.0, "_Matrix": 1, "idx": i} for i in range(n)]
+    return vs_shim.array_clip(fr, props=props), fr, props
+
+
+def test_colorizer_clip_order_props_and_parity():
+    from oracle import metrics, pipeline_oracle
+    havc = _register()
+    H, W, rf, n = 90, 160, 4, 7
+    clip, fr, props = _clip(n, H, W)
+    out = havc.HAVC_colorizer(clip, method=0, deoldify_p=[0, rf, 1.0, 0.0], ddcolor_p=[1, rf, 1.0, 0.0, True])
+    assert (out.num_frames, out.width, out.height) == (n, W, H)
+    order = [5, 0, 6, 2, 2, 1, 4, 3]                                        # out-of-order and repeated requests
+    got = {i: out.get_frame(i) for i in order}
+    sd = havc._REGISTERED["ColorizeVideo_gen"]
+    for i in range(n):
+        f = got[i]
+        assert f.props == props[i], "frame properties must pass through bit-exactly"
+        ref = pipeline_oracle.havc_colorizer_frame(sd, np.transpose(fr[i], (1, 2, 0)), rf)
+        img = np.stack([np.asarray(f[p]) for p in range(3)], -1)
+        m = metrics.frame_parity(img, ref)
+        assert m["mean_de00"] <= 0.5, (i, m)                                 # also proves frame i is frame i
+    # the source clip is untouched
+    assert np.array_equal(np.asarray(clip.get_frame(3)[1]), fr[3, 1])
+
+
+def test_scenechange_gating():
+    """sc_min_freq > 0 -> scenechange=True: only n == 0 or _SceneChangePrev == 1 frames are colourised
+    (vsslib/vsmodels.py:221-224); the others take the uncoloured squeeze/un-squeeze path."""
+    from oracle import metrics, pipeline_oracle
+    havc = _register()
+    H, W, rf, n = 90, 160, 4, 6
+    clip, fr, props = _clip(n, H, W, seed=90)
+    out = havc.HAVC_colorizer(clip, method=0, deoldify_p=[0, rf, 1.0, 0.0], ddcolor_p=[1, rf, 1.0, 0.0, True], sc_min_freq=1)
+    sd = havc._REGISTERED["ColorizeVideo_gen"]
+    for i in range(n):
+        colourised = i in (0, 4)
+        ref = pipeline_oracle.havc_colorizer_frame(sd, np.transpose(fr[i], (1, 2, 0)), rf, skip=not colourised)
+        f = out.get_frame(i)
+        img = np.stack([np.asarray(f[p]) for p in range(3)], -1)
+        d = np.abs(img.astype(int) - ref.astype(int))
+        if colourised:
+            assert metrics.frame_parity(img, ref)["mean_de00"] <= 0.5
+        else:   # no network involved: integer pixel math + float resampling only
+            assert d.max() <= 1 and (d > 0).mean() < 0.01, (i, int(d.max()), float((d > 0).mean()))
+        assert f.props == props[i]
+
+
+def test_havc_main_preset_path():
+    """HAVC_main(Preset='VeryFast', ColorModel='DeOldify(Video)') == HAVC_colorizer(method=0, rf=16)."""
+    havc = _register()
+    clip, fr, props = _clip(2, 144, 256, seed=170)
+    a = havc.HAVC_main(clip, Preset="VeryFast", ColorModel="DeOldify(Video)")
+    b = havc.HAVC_deoldify(clip, model=0, render_factor=16, ddcolor_p=[1, 16, 1.0, 0.0, True])
+    for i in range(2):
+        fa, fb = a.get_frame(i), b.get_frame(i)
+        assert all(np.array_equal(np.asarray(fa[p]), np.asarray(fb[p])) for p in range(3))
+        assert fa.props == props[i]
+
+
+@pytest.mark.parametrize("model,name", [(1, "ColorizeStable_gen"), (2, "ColorizeArtistic_gen")])
+def test_stable_and_artistic_blend(model, name):
+    from oracle import metrics, pipeline_oracle
+    havc = _register()
+    H, W, rf, n = 96, 128, 4, 2
+    clip, fr, props = _clip(n, H, W, seed=130)
+    out = havc.HAVC_colorizer(clip, method=0, deoldify_p=[model, rf, 1.0, 0.0], ddcolor_p=[1, rf, 1.0, 0.0, True])
+    for i in range(n):
+        ref = pipeline_oracle.havc_colorizer_frame(havc._REGISTERED["ColorizeVideo_gen"], np.transpose(fr[i], (1, 2, 0)), rf,
+                                                   sd_other=havc._REGISTERED[name], video_weight=0.5)
+        f = out.get_frame(i)
+        img = np.stack([np.asarray(f[p]) for p in range(3)], -1)
+        m = metrics.frame_parity(img, ref)
+        assert m["mean_de00"] <= 0.5, (model, i, m)

@@ -93,9 +93,12 @@ def test_choose_box_and_bn():
         tiles = -(-W // bw) * -(-H // bh) * -(-B // bb)
         assert tiles * 128 >= W * H * B
     assert ops.choose_box(12, 12, 8) == (4, 4, 8)                     # 3x3 boxes of 4x4 over 8 images: no waste
-    assert ops.choose_bn(272, 9216) == 272 and ops.choose_bn(256, 10) == 256
-    assert ops.choose_bn(4096, 9) in (64, 128, 256) and 4096 % ops.choose_bn(4096, 9) == 0
-    assert ops.choose_bn(320, 9216) == 160                            # artistic res_block: 2 x 160, not 5 x 64
+    assert ops.choose_bn(272, 9216) == 272 and ops.choose_bn(320, 9216) == 320   # res_block tails: one 256+rest tile
+    assert ops.choose_bn(256, 2000) == 256                            # plenty of pixels: widest tile
+    assert ops.choose_bn(256, 72) == 128                              # 72 pixel tiles on 148 SMs: split N to fill them
+    for n, m in [(4096, 9), (512, 18), (1024, 4608), (2304, 18)]:
+        bn = ops.choose_bn(n, m)
+        assert 64 <= bn <= 256 and bn % 16 == 0 and n % bn == 0
 
 
 def test_resample_tables_match_oracle_matrix():

@@ -1,0 +1,78 @@
+"""CPU tests of the plugin surface: names/signatures mirror the reference, graph-build errors are vs.Error, the
+VapourSynth stand-in honours the selector protocol (props survive f.copy())."""
+import inspect
+
+import numpy as np
+import pytest
+
+
+def test_public_names_and_signatures():
+    import vsdeoldify_b200 as pkg
+    from vsdeoldify_b200 import havc
+    for name in ("HAVC_main", "HAVC_colorizer", "HAVC_deoldify", "HAVC_ddeoldify"):
+        assert callable(getattr(pkg, name))
+    # positional order of the reference (vsdeoldify/__init__.py:2290-2298)
+    params = list(inspect.signature(havc.HAVC_colorizer).parameters)
+    assert params == ["clip", "method", "mweight", "deoldify_p", "ddcolor_p", "ddtweak", "ddtweak_p", "cmc_p", "lmm_p",
+                      "alm_p", "crt_p", "cmb_sw", "sc_threshold", "sc_tht_offset", "sc_min_freq", "sc_tht_ssim",
+                      "sc_normalize", "sc_min_int", "sc_tht_white", "sc_tht_black", "device_index", "torch_dir",
+                      "debug_level"]
+    sig = inspect.signature(havc.HAVC_colorizer)
+    assert sig.parameters["method"].default == 2 and sig.parameters["mweight"].default == 0.4
+    assert tuple(sig.parameters["deoldify_p"].default) == (0, 24, 1.0, 0.0)
+    assert tuple(sig.parameters["ddcolor_p"].default) == (1, 24, 1.0, 0.0, True)
+    # vsdeoldify/__init__.py:3612-3628
+    dd = list(inspect.signature(havc.HAVC_ddeoldify).parameters)
+    assert dd[:8] == ["clip", "method", "mweight", "deoldify_p", "ddcolor_p", "ddtweak", "ddtweak_p", "cmc_tresh"] and dd[-1] == "sc_debug"
+    mp = inspect.signature(havc.HAVC_main).parameters
+    assert mp["Preset"].default == "Medium" and mp["ColorModel"].default == "Video+Artistic"
+
+
+def _clip(n=3, h=32, w=48):
+    from vsdeoldify_b200 import vs_shim
+    fr = np.random.default_rng(0).integers(0, 256, (n, 3, h, w), dtype=np.uint8)
+    return vs_shim.array_clip(fr, props=[{"_SceneChangePrev": int(i == 0), "sc_threshold": 0.1, "x": i} for i in range(n)])
+
+
+def test_graph_build_errors_are_vs_error():
+    import torch
+    from vsdeoldify_b200 import havc, vs_shim
+    clip = _clip()
+    with pytest.raises(vs_shim.Error, match="CPU mode"):
+        havc.HAVC_colorizer(clip, method=0, device_index=99)
+    if not torch.cuda.is_available():
+        with pytest.raises(vs_shim.Error, match="CUDA is not available"):        # vsdeoldify/__init__.py:2441
+            havc.HAVC_colorizer(clip, method=0)
+    with pytest.raises(vs_shim.Error, match="Preset choice is invalid"):           # havc_utils.py:347
+        havc.HAVC_main(clip, Preset="warp9", ColorModel="DeOldify(Video)")
+    with pytest.raises(vs_shim.Error):
+        havc.HAVC_main(clip, ColorModel="Video+Artistic")                          # DDColor side: not built
+    with pytest.raises(vs_shim.Error):
+        havc.HAVC_main(clip, ColorModel="DeOldify(Video)", EnableDeepEx=True)
+
+
+def test_preset_table_matches_reference():
+    from vsdeoldify_b200 import havc
+    # havc_utils.py:338-340
+    assert [havc._get_render_factor(p) for p in ("Placebo", "VerySlow", "Slower", "Slow", "Medium", "Fast", "Faster", "VeryFast")] \
+        == [32, 32, 32, 28, 24, 22, 20, 16]
+
+
+def test_shim_selector_protocol_keeps_props():
+    from vsdeoldify_b200 import vs_shim
+    clip = _clip()
+
+    def sel(n, f):
+        g = f.copy()
+        np.copyto(np.asarray(g[0]), 255 - np.asarray(f[0]))
+        return g
+    out = clip.std.ModifyFrame(clips=[clip], selector=sel)
+    assert out.num_frames == clip.num_frames and (out.width, out.height) == (48, 32)
+    f2 = out.get_frame(2)
+    assert f2.props == {"_SceneChangePrev": 0, "sc_threshold": 0.1, "x": 2}
+    assert np.array_equal(np.asarray(f2[0]), 255 - np.asarray(clip.get_frame(2)[0]))
+    assert np.array_equal(np.asarray(f2[1]), np.asarray(clip.get_frame(2)[1]))
+    with pytest.raises(vs_shim.Error):
+        out.get_frame(3)
+    tagged = out.std.SetFrameProp(prop="sc_frequency", intval=1).std.CopyFrameProps(prop_src=clip, props=["x"])
+    assert tagged.get_frame(1).props["sc_frequency"] == 1 and tagged.get_frame(1).props["x"] == 1

@@ -70,9 +70,9 @@ __global__ void resample_h_kernel(const uint8_t *__restrict__ in, float *__restr
         __syncthreads();
         for (int ox = threadIdx.x; ox < Wout; ox += blockDim.x) {
             const float *sp = srow + __ldg(start + ox);
-            const float *w = wts + (long long)ox * T;
+            const float *w = wts + ox;                       // transposed table [T][Wout]: coalesced across the warp
             float acc = 0.f;
-            for (int t = 0; t < T; ++t) acc = fmaf(__ldg(w + t), sp[t], acc);
+            for (int t = 0; t < T; ++t) acc = fmaf(__ldg(w + (long long)t * Wout), sp[t], acc);
             out[row * Wout + ox] = acc;
         }
         __syncthreads();
@@ -232,7 +232,8 @@ __global__ void head_kernel(const void *__restrict__ res, int Cs, const float *_
 
 // Final (horizontal) pass of the resize back to W x H fused with the full-resolution luma transplant.
 // in: float [B][3][H][S] (already resampled vertically); orig/out: u8 [B][3][H][W].  One block per output row:
-// the three S-wide source rows sit in shared memory, each thread produces 4 consecutive pixels (uchar4 I/O).
+// the three S-wide source rows sit in shared memory; consecutive threads produce consecutive pixels, so the
+// transposed weight table, the start table and the u8 planes are all read/written coalesced.
 __global__ void post_horizontal_kernel(const float *__restrict__ in, const uint8_t *__restrict__ orig,
                                        uint8_t *__restrict__ out, int B, int S, int H, int W,
                                        const int *__restrict__ start, const float *__restrict__ wts, int T,
@@ -248,55 +249,62 @@ __global__ void post_horizontal_kernel(const float *__restrict__ in, const uint8
         }
         __syncthreads();
         const long long base = ((long long)b * 3 * H + oy) * W;
-        for (int x4 = threadIdx.x * 4; x4 < W; x4 += blockDim.x * 4) {
-            const bool vec = (x4 + 3 < W) && ((W & 3) == 0);
-            uint32_t o4[3] = {0, 0, 0};
-            uint32_t ov[3] = {0, 0, 0};
-            if (transplant && vec) {
-#pragma unroll
-                for (int c = 0; c < 3; ++c) o4[c] = __ldg(reinterpret_cast<const uint32_t *>(orig + base + c * ps + x4));
+        for (int ox = threadIdx.x; ox < W; ox += blockDim.x) {
+            const int s0 = __ldg(start + ox);
+            const float *w = wts + ox;                       // transposed table [T][W]
+            float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+            for (int t = 0; t < T; ++t) {
+                const float wt = __ldg(w + (long long)t * W);
+                acc0 = fmaf(wt, srows[s0 + t], acc0);
+                acc1 = fmaf(wt, srows[S + s0 + t], acc1);
+                acc2 = fmaf(wt, srows[2 * S + s0 + t], acc2);
             }
-            const int npx = vec ? 4 : min(4, W - x4);
-            for (int k = 0; k < npx; ++k) {
-                const int ox = x4 + k;
-                const int s0 = __ldg(start + ox);
-                const float *w = wts + (long long)ox * T;
-                float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
-                for (int t = 0; t < T; ++t) {
-                    const float wt = __ldg(w + t);
-                    acc0 = fmaf(wt, srows[s0 + t], acc0);
-                    acc1 = fmaf(wt, srows[S + s0 + t], acc1);
-                    acc2 = fmaf(wt, srows[2 * S + s0 + t], acc2);
-                }
-                int q0 = round_u8(acc0), q1 = round_u8(acc1), q2 = round_u8(acc2);
-                int rr = q0, gg = q1, bb = q2;
-                if (transplant) {
-                    int o0, o1, o2;
-                    if (vec) {
-                        o0 = (o4[0] >> (8 * k)) & 0xff; o1 = (o4[1] >> (8 * k)) & 0xff; o2 = (o4[2] >> (8 * k)) & 0xff;
-                    } else {
-                        o0 = orig[base + ox]; o1 = orig[base + ps + ox]; o2 = orig[base + 2 * ps + ox];
-                    }
-                    luma_transplant(o0, o1, o2, q0, q1, q2, rr, gg, bb);
-                }
-                if (vec) {
-                    ov[0] |= (uint32_t)rr << (8 * k); ov[1] |= (uint32_t)gg << (8 * k); ov[2] |= (uint32_t)bb << (8 * k);
-                } else {
-                    out[base + ox] = (uint8_t)rr; out[base + ps + ox] = (uint8_t)gg; out[base + 2 * ps + ox] = (uint8_t)bb;
-                }
-            }
-            if (vec) {
-#pragma unroll
-                for (int c = 0; c < 3; ++c) *reinterpret_cast<uint32_t *>(out + base + c * ps + x4) = ov[c];
-            }
+            const int q0 = round_u8(acc0), q1 = round_u8(acc1), q2 = round_u8(acc2);
+            int rr = q0, gg = q1, bb = q2;
+            if (transplant)
+                luma_transplant(__ldg(orig + base + ox), __ldg(orig + base + ps + ox), __ldg(orig + base + 2 * ps + ox), q0, q1,
+                                q2, rr, gg, bb);
+            out[base + ox] = (uint8_t)rr;
+            out[base + ps + ox] = (uint8_t)gg;
+            out[base + 2 * ps + ox] = (uint8_t)bb;
         }
         __syncthreads();
+    }
+}
+
+// PIL.Image.blend(a, b, alpha) on u8 data: trunc(a + alpha*(b - a)) in float32 (Pillow's Blend.c), 16 bytes/thread.
+__global__ void blend_u8_kernel(const uint4 *__restrict__ a, const uint4 *__restrict__ b, uint4 *__restrict__ out,
+                                long long n16, float alpha) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x) {
+        const uint4 va = __ldg(a + i), vb = __ldg(b + i);
+        const uint32_t wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
+        uint32_t wo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t o = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float fa = (float)((wa[j] >> (8 * k)) & 0xff), fb = (float)((wb[j] >> (8 * k)) & 0xff);
+                const float t = __fadd_rn(fa, __fmul_rn(alpha, __fsub_rn(fb, fa)));
+                o |= (uint32_t)sat8((int)t) << (8 * k);
+            }
+            wo[j] = o;
+        }
+        out[i] = make_uint4(wo[0], wo[1], wo[2], wo[3]);
     }
 }
 
 }  // namespace havc
 
 using namespace havc;
+
+extern "C" int havc_blend_u8(const uint8_t *a, const uint8_t *b, uint8_t *out, long long n, float alpha, void *stream) {
+    HAVC_CHECK_ARG(a && b && out && n % 16 == 0 && alpha >= 0.f && alpha <= 1.f, "havc_blend_u8: n must be a multiple of 16, alpha in [0,1]");
+    blend_u8_kernel<<<grid1d(n / 16, 256), 256, 0, (cudaStream_t)stream>>>((const uint4 *)a, (const uint4 *)b, (uint4 *)out,
+                                                                        n / 16, alpha);
+    HAVC_LAUNCHED();
+    return HAVC_OK;
+}
 
 extern "C" int havc_resample_h(const uint8_t *in, float *out, long long rows, int Win, int Wout, const int *start,
                                const float *weights, int taps, void *stream) {

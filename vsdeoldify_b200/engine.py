@@ -22,19 +22,22 @@ class _Tables:
         start, w = resample.build_tables(src, dst, kernel)
         self.taps = int(w.shape[1])
         self.start = torch.from_numpy(start).to(dev)
-        self.w = torch.from_numpy(w).contiguous().to(dev)
+        self.w = torch.from_numpy(w).contiguous().to(dev)                       # [out][taps]  (vertical passes)
+        self.wt = torch.from_numpy(np.ascontiguousarray(w.T)).to(dev)           # [taps][out]  (horizontal passes)
 
 
 class DeoldifyEngine:
-    """One DeOldify generator at render size S = render_factor*16 on frames of width x height, batch B.
+    """DeOldify at render size S = render_factor*16 on frames of width x height, batch B.
 
-    Second generator + 50/50 blend ('stable'/'artistic', visualize.py:118-137) is layered on top by
-    `vsdeoldify_b200.vsmodels`; this class is the single-network path (model 'video')."""
+    `sd` is the 'video' generator, which always runs (visualize.py:120).  With `sd_other` (the 'stable' or
+    'artistic' generator) both run on the same input and their S x S results are mixed with
+    Image.blend(other, video, video_weight) before the resize back (visualize.py:118-137)."""
 
     def __init__(self, sd: Dict[str, torch.Tensor], width: int, height: int, render_factor: int = 24, batch: int = 8,
                  dtype: torch.dtype = torch.float16, device: str = "cuda:0", resize_kernel: str = "spline64",
                  use_graph: bool = True, keep_taps: bool = False, debug_net_out: bool = False,
-                 frame_size: Optional[int] = None):
+                 frame_size: Optional[int] = None, sd_other: Optional[Dict[str, torch.Tensor]] = None,
+                 video_weight: float = 0.5):
         self.lib = _lib.lib()
         self.dev = torch.device(device)
         torch.cuda.set_device(self.dev)
@@ -47,6 +50,8 @@ class DeoldifyEngine:
         S, B, W, H = self.S, batch, width, height
         self.dtype, self.hd = dtype, ops.havc_dtype(dtype)
         self.prog = UnetProgram(sd, B, S, dtype, device=self.dev, keep_taps=keep_taps)
+        self.prog2 = UnetProgram(sd_other, B, S, dtype, device=self.dev, x=self.prog.x) if sd_other is not None else None
+        self.video_weight = float(video_weight)
         self.t_down_h = _Tables(W, S, resize_kernel, self.dev)
         self.t_down_v = _Tables(H, S, resize_kernel, self.dev)
         self.t_up_h = _Tables(S, W, resize_kernel, self.dev)
@@ -61,6 +66,7 @@ class DeoldifyEngine:
         self.tmp_down = torch.empty(B, 3, H, S, **f32)
         self.rgb_small = torch.empty(B, 3, S, S, **u8)
         self.colored = torch.empty(B, 3, S, S, **u8)
+        self.colored2 = torch.empty(B, 3, S, S, **u8) if sd_other is not None else None
         self.tmp_up = torch.empty(B, 3, H, S, **f32)
         self.net_out = torch.empty(B, 3, S, S, **f32) if debug_net_out else None
         self.skip = torch.zeros(B, **u8)                  # per-frame scene-change gate (1 = leave uncoloured)
@@ -79,7 +85,7 @@ class DeoldifyEngine:
         chk = _lib.check
         td, tv, uh, uv = self.t_down_h, self.t_down_v, self.t_up_h, self.t_up_v
         chk(lib.havc_resample_h(self.d_in[slot].data_ptr(), self.tmp_down.data_ptr(), B * 3 * H, W, S,
-                                td.start.data_ptr(), td.w.data_ptr(), td.taps, stream), "pre.h")
+                                td.start.data_ptr(), td.wt.data_ptr(), td.taps, stream), "pre.h")
         chk(lib.havc_pre_vertical(self.tmp_down.data_ptr(), self.rgb_small.data_ptr(), self.prog.x.data_ptr(), B, H, S,
                                   tv.start.data_ptr(), tv.w.data_ptr(), tv.taps, self.hd, stream), "pre.v")
         self.prog.run(stream)
@@ -88,11 +94,17 @@ class DeoldifyEngine:
                           self.net_out.data_ptr() if self.net_out is not None else None, self.skip.data_ptr(), B, S,
                           self.hd, 1, stream),
             "head")
+        if self.prog2 is not None:
+            self.prog2.run(stream)
+            chk(lib.havc_head(self.prog2.logits.data_ptr(), 0, None, self.prog2.b11.data_ptr(), self.rgb_small.data_ptr(),
+                              self.colored2.data_ptr(), None, self.skip.data_ptr(), B, S, self.hd, 1, stream), "head2")
+            chk(lib.havc_blend_u8(self.colored2.data_ptr(), self.colored.data_ptr(), self.colored.data_ptr(),
+                                  B * 3 * S * S, self.video_weight, stream), "blend")
         # back to W x H: vertical pass on the S-wide image first, then the wide horizontal pass from shared memory
         chk(lib.havc_resample_v(self.colored.data_ptr(), self.tmp_up.data_ptr(), B * 3, S, H, S,
                                 uv.start.data_ptr(), uv.w.data_ptr(), uv.taps, stream), "post.v")
         chk(lib.havc_post_horizontal(self.tmp_up.data_ptr(), self.d_in[slot].data_ptr(), self.d_out[slot].data_ptr(), B, S,
-                                     H, W, uh.start.data_ptr(), uh.w.data_ptr(), uh.taps, 1, stream), "post.h")
+                                     H, W, uh.start.data_ptr(), uh.wt.data_ptr(), uh.taps, 1, stream), "post.h")
 
     def _warm(self):
         with torch.cuda.stream(self.compute):

@@ -72,8 +72,8 @@ def load_state_dict(weights_name: str, models_dir: str = model_dir) -> Dict[str,
 class _ColorizedClip:
     """frame_fn of the output clip: batches source frames through the engine, caches results by frame number."""
 
-    def __init__(self, clip, engines, video_weight: float, scenechange: bool, batch: int):
-        self.clip, self.engines, self.video_weight = clip, engines, video_weight
+    def __init__(self, clip, engine, scenechange: bool, batch: int):
+        self.clip, self.engine = clip, engine
         self.scenechange, self.B = scenechange, batch
         self.cache: "OrderedDict[int, object]" = OrderedDict()
         self.lock = threading.Lock()
@@ -91,10 +91,7 @@ class _ColorizedClip:
             skip = None
             if self.scenechange:    # vsslib/vsmodels.py:221-224: only scene-change frames are colourised
                 skip = np.array([not (i == 0 or f.props.get("_SceneChangePrev", 0) == 1) for i, f in zip(range(n, n1), srcs)])
-            out = self.engines[0].colorize_batch(batch, skip=skip)
-            if len(self.engines) > 1:   # 'stable'/'artistic': Image.blend(other, video, video_weight), visualize.py:129,135
-                other = self.engines[1].colorize_batch(batch, skip=skip)
-                out = _pil_blend(other, out, self.video_weight)
+            out = self.engine.colorize_batch(batch, skip=skip)
             for i, f in zip(range(n, n1), srcs):
                 g = f.copy()                              # all props of the source frame survive (vsutils.py:92-95)
                 for p in range(3):
@@ -103,16 +100,6 @@ class _ColorizedClip:
             while len(self.cache) > 4 * self.B:
                 self.cache.popitem(last=False)
             return self.cache[n]
-
-
-def _pil_blend(a: np.ndarray, b: np.ndarray, alpha: float) -> np.ndarray:
-    """PIL.Image.blend(a, b, alpha): trunc(a + alpha*(b - a)) in float32."""
-    if alpha == 0.0:
-        return a
-    if alpha == 1.0:
-        return b
-    af = a.astype(np.float32)
-    return (af + np.float32(alpha) * (b.astype(np.float32) - af)).astype(np.uint8)
 
 
 def HAVC_colorizer(
@@ -129,7 +116,7 @@ def HAVC_colorizer(
         _raise("HAVC_colorizer: CPU mode (device_index=99) is not available in the B200 build (no CPU fallback)")
     if not torch.cuda.is_available():
         _raise("HAVC_colorizer: CUDA is not available")                                   # :2441
-    if clip.format.id != vs.RGB24.id if hasattr(vs.RGB24, "id") else clip.format.id != vs.RGB24:
+    if getattr(clip.format, "id", clip.format) != getattr(vs.RGB24, "id", vs.RGB24):
         _raise("HAVC_colorizer: only RGB24 input is handled by the B200 build (convert_format_RGB24 is a 'next' row)")
     if sc_threshold < 0:
         _raise("HAVC_colorizer: sc_threshold must be >= 0")                              # :2447
@@ -158,11 +145,16 @@ def HAVC_colorizer(
     frame_size = min(max(ddcolor_rf, deoldify_rf) * 16, clip.width)
     from .engine import DeoldifyEngine
     dev = f"cuda:{device_index}"
-    names = [_WEIGHT_FILES[0]] + ([_WEIGHT_FILES[deoldify_model]] if deoldify_model in (1, 2) else [])
-    engines = [DeoldifyEngine(load_state_dict(nm, torch_dir or model_dir), clip.width, clip.height, render_factor=deoldify_rf,
-                              frame_size=frame_size, batch=_BATCH, dtype=_DTYPE, device=dev) for nm in names]
+    mdir = torch_dir or model_dir
+    sd_video = load_state_dict(_WEIGHT_FILES[0], mdir)                   # the video generator always runs (visualize.py:120)
+    sd_other = load_state_dict(_WEIGHT_FILES[deoldify_model], mdir) if deoldify_model in (1, 2) else None
     weight = {1: DEF_STABLE_WEIGHT, 2: DEF_ARTISTIC_WEIGHT}.get(deoldify_model, 0.0)
-    fn = _ColorizedClip(clip, engines, weight, scenechange, _BATCH)
+    try:
+        engine = DeoldifyEngine(sd_video, clip.width, clip.height, render_factor=deoldify_rf, frame_size=frame_size,
+                                batch=_BATCH, dtype=_DTYPE, device=dev, sd_other=sd_other, video_weight=weight)
+    except ValueError as e:
+        _raise("HAVC_colorizer: " + str(e))
+    fn = _ColorizedClip(clip, engine, scenechange, _BATCH)
     return vs_shim.VideoNode(clip.num_frames, clip.width, clip.height, clip.format, fn, clip.fps_num, clip.fps_den) \
         if vs is vs_shim else _wrap_real_vs(clip, fn)
 

@@ -154,19 +154,25 @@ def pack_cols(v: Optional[torch.Tensor], n_alloc: int, fill: float, shuffle_meta
     return out
 
 
-def choose_bn(n_total: int, m_tiles: int, sms: int = 148) -> int:
-    """N tile (UMMA N: multiple of 16, <= 256; 272 = 256+16 for the 259-channel tail): the widest divisor
-    of n_total (fewest re-reads of the activation tile) that still gives every SM a tile, never below 64
-    (narrow tiles re-read the activations and idle the tensor pipe)."""
-    if n_total <= 256 or n_total == 272:
+def choose_bn(n_total: int, m_tiles: int, sms: int = 148, ksteps: int = 36) -> int:
+    """N tile (UMMA N: multiple of 16, <= 256; 272..320 = 256 + rest for the res_block tail) from a small cost
+    model fitted to measurements on B200: a tile costs ksteps * t_k(BN) + a fixed prologue/epilogue share, the
+    launch costs ceil(tiles / SMs) waves of that.  Wide tiles re-read the activations least; narrow tiles fill the
+    machine when the layer has few pixels."""
+    if 256 < n_total <= 320:
         return n_total
-    cands = [bn for bn in range(256, 63, -16) if n_total % bn == 0]
-    if not cands:
-        return 128
+    cands = [bn for bn in range(256, 63, -16) if n_total % bn == 0] or [min(n_total, 256)]
+    if n_total <= 256 and n_total not in cands:
+        cands = [n_total] + cands
+    best, best_cost = cands[0], None
     for bn in cands:
-        if m_tiles * (n_total // bn) >= sms:
-            return bn
-    return cands[-1]
+        tiles = m_tiles * -(-n_total // bn)
+        waves = -(-tiles // sms)
+        t_k = max(0.22, 0.5 * bn / 256.0)                 # us per 64-deep K step (smem/L2 floor below BN~112)
+        cost = waves * (ksteps * t_k + 2.0 + 3.0 * bn / 256.0)
+        if best_cost is None or cost < best_cost * 0.98:  # prefer the wider tile on (near) ties
+            best, best_cost = bn, cost
+    return best
 
 
 @dataclass
@@ -221,7 +227,8 @@ def make_conv(src0: torch.Tensor, weight: torch.Tensor, out: torch.Tensor, taps,
     d.a_batched, d.b_batched = int(a_batched), int(b_batched)
     d.N_total = n_total if n_total is not None else rows
     m_tiles = -(-W // box[0]) * -(-H // box[1]) * -(-B // box[2])
-    d.BN = bn if bn is not None else choose_bn(d.N_total, m_tiles)
+    ksteps = len(taps) * (-(-d.src0.C // 64) + (-(-d.src1.C // 64) if src1 is not None and not src1_single_tap else 0))
+    d.BN = bn if bn is not None else choose_bn(d.N_total, m_tiles, ksteps=ksteps)
     n_alloc = -(-d.N_total // d.BN) * d.BN
     keep = [src0, src1, weight, out, residual]
     for nm, v in (("bias", bias), ("scale", scale), ("shift", shift)):

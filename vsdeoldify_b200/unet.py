@@ -76,7 +76,7 @@ class UnetProgram:
     """Compiled launch list for one (state-dict, batch, S, dtype)."""
 
     def __init__(self, sd: SD, batch: int, size: int, dtype: torch.dtype = torch.float16, device="cuda",
-                 keep_taps: bool = False):
+                 keep_taps: bool = False, x: Optional[torch.Tensor] = None):
         if size % 32 != 0:
             raise ValueError(f"render size {size} must be a multiple of 32 (even render_factor); the nearest-"
                              "neighbour up-path resize of unet.py:201-203 is not implemented")
@@ -88,6 +88,7 @@ class UnetProgram:
         self.taps: Dict[str, torch.Tensor] = {}
         self.keep_taps = keep_taps
         self.bottleneck = "layers.0.4.0.conv3.weight" in sd
+        self._x_shared = x
         self._build()
 
     # ---- buffers / params ---------------------------------------------------------------------
@@ -181,7 +182,7 @@ class UnetProgram:
     def _build(self):
         sd, B, S, lib, hd = self.sd, self.B, self.S, self.lib, self.hd
         # network input: normalised image, NHWC [B,S,S,8] (3 real channels), written by the pre kernel
-        self.x = self.buf(B, S, S, 8, zero=True)
+        self.x = self._x_shared if self._x_shared is not None else self.buf(B, S, S, 8, zero=True)
 
         # ---- encoder stem: 7x7/s2 conv as im2col + GEMM, BN folded, ReLU --------------------------
         w = sd["layers.0.0.weight"].float()
