@@ -43,7 +43,8 @@ struct ConvParams {
     int8_t dh[HAVC_MAX_TAPS], dw[HAVC_MAX_TAPS], tp[HAVC_MAX_TAPS], twi[HAVC_MAX_TAPS];
     int chunks0, chunks1, w_c1_off;
     int a_batched, b_batched;
-    int acc_stages, acc_stride;
+    int acc_stages, acc_stride;   // acc_stride = TMEM column offset of accumulator stage 1
+    int staggered;                // BN > 256: the two accumulators overlap in columns [acc_stride, BN) (see MMA issuer)
     int num_stages;
     uint32_t stage_bytes;
     int n_part0, n_part1;
@@ -220,6 +221,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + s); };
     auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 2 + s); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 4);
+    auto tearly_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 5 + s); };
     volatile uint32_t *tmem_slot_ptr =
         reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -239,6 +241,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         for (int s = 0; s < 2; ++s) {
             mbar_init(tfull_bar(s), 1);
             mbar_init(tempty_bar(s), 256);
+            mbar_init(tearly_bar(s), 256);
         }
         fence_barrier_init();
     }
@@ -303,8 +306,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             uint32_t phase = 0;
             int as = 0;
             uint32_t aphase = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            int seq = 0;   // index of this tile in the CTA's own sequence
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++seq) {
+                // Accumulator hand-over.  Normal double buffering: wait until the epilogue has fully drained this
+                // stage (its tile before last).  Staggered (BN > 256, 2*BN > 512 TMEM columns): stage 1 starts at
+                // column 512-BN, so the stages share columns [512-BN, BN); the epilogue drains that shared range
+                // of the PREVIOUS tile first and signals `tearly`, after which this tile may start while the rest of
+                // the previous tile is still being drained.
                 mbar_wait(tempty_bar(as), aphase ^ 1u);
+                if (p.staggered && seq > 0) mbar_wait(tearly_bar(as ^ 1), ((uint32_t)(seq - 1) >> 1) & 1u);
                 tc_fence_after();
                 const uint32_t acc = tmem_base + as * p.acc_stride;
                 for (int ks = 0; ks < ksteps; ++ks) {
@@ -390,7 +400,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             uint32_t va[32], vb[32];
             // One chunk: wait for its TMEM load, kick off the load of the chunk after next into `vn`,
             // then run the fp32 epilogue on `vc` and store.
-            auto process = [&](int ci, uint32_t(&vc)[32], uint32_t(&vn)[32]) {
+            auto process = [&](int ci, int nxt, uint32_t(&vc)[32], uint32_t(&vn)[32]) {
                 const int c0 = ci * 32;
                 uint4 rres[4];
                 const int n = n0 + c0;
@@ -409,8 +419,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                     }
                 }
                 tmem_ld_wait();
-                const int nxt = ci + 2;
-                if (nxt < nchunks) {
+                if (nxt >= 0) {
                     __syncwarp();
                     tmem_ld_chunk(tbase + nxt * 32, vn, p.BN - nxt * 32);
                 }
@@ -490,13 +499,40 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                     }
                 }
             };
-            if (half < nchunks) {
+            // This warp's chunks are ci = half, half+2, ...; in staggered mode the columns shared with the other
+            // accumulator stage are drained first (stage 0: the highest chunks, stage 1: the lowest) and `tearly`
+            // is signalled as soon as they are out of TMEM.
+            const int n_my = (nchunks - half + 1) >> 1;
+            const bool desc = p.staggered && as == 0;
+            auto chunk_at = [&](int k) { return desc ? (half + 2 * (n_my - 1 - k)) : (half + 2 * k); };
+            auto shared_cols = [&](int ci) {   // does local chunk ci touch columns [acc_stride, BN) of the other stage?
+                if (!p.staggered) return false;
+                return as == 0 ? (ci * 32 + 32 > p.acc_stride) : (ci * 32 < p.BN - p.acc_stride);
+            };
+            bool early_done = !p.staggered;
+            if (n_my > 0) {
                 __syncwarp();
-                tmem_ld_chunk(tbase + half * 32, va, p.BN - half * 32);
+                tmem_ld_chunk(tbase + chunk_at(0) * 32, va, p.BN - chunk_at(0) * 32);
             }
-            for (int ci = half; ci < nchunks; ci += 4) {
-                process(ci, va, vb);
-                if (ci + 2 < nchunks) process(ci + 2, vb, va);
+            for (int k = 0; k < n_my; k += 2) {
+                if (!early_done && !shared_cols(chunk_at(k))) {
+                    tc_fence_before();
+                    mbar_arrive(tearly_bar(as));
+                    early_done = true;
+                }
+                process(chunk_at(k), k + 1 < n_my ? chunk_at(k + 1) : -1, va, vb);
+                if (k + 1 < n_my) {
+                    if (!early_done && !shared_cols(chunk_at(k + 1))) {
+                        tc_fence_before();
+                        mbar_arrive(tearly_bar(as));
+                        early_done = true;
+                    }
+                    process(chunk_at(k + 1), k + 2 < n_my ? chunk_at(k + 2) : -1, vb, va);
+                }
+            }
+            if (!early_done) {
+                tc_fence_before();
+                mbar_arrive(tearly_bar(as));
             }
             if (p.head_w != nullptr) {   // the two warps of a lane quarter each hold half of the columns
                 float *hx = sparams + (2 * 3 + 3) * kMaxBN;   // [128 rows][4]
@@ -648,8 +684,9 @@ extern "C" int havc_conv_gemm(const havc_conv_desc *d, void *stream) {
     p.chunks1 = two ? ceil_div(d->src1.C, kChunkK) : 0;
     p.w_c1_off = d->w_c1_off;
     p.a_batched = d->a_batched; p.b_batched = d->b_batched;
-    p.acc_stages = (2 * d->BN <= (int)kTmemCols) ? 2 : 1;
-    p.acc_stride = d->BN;
+    p.acc_stages = 2;
+    p.staggered = (2 * d->BN > (int)kTmemCols) ? 1 : 0;
+    p.acc_stride = p.staggered ? (int)kTmemCols - d->BN : d->BN;
     p.stage_bytes = kABytes + d->BN * 128;
     int stages = (227 * 1024 - 1024 - 256 - kEpiSmemFloats * (int)sizeof(float)) / (int)p.stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
