@@ -398,90 +398,119 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * p.acc_stride;
 
             uint32_t va[32], vb[32];
-            // One chunk: wait for its TMEM load, kick off the load of the chunk after next into `vn`,
+            // ---- per-tile invariants of this thread (hoisted out of the chunk loop) ----
+            const int BN = p.BN, N_total = p.N_total, split_n = p.split_n, c_store = p.c_store, c_store2 = p.c_store2;
+            const int dt = p.dtype, od = p.out_dtype, gn = p.group_n;
+            const bool shuffle = p.shuffle != 0, has_scale = p.scale != nullptr, head = p.head_w != nullptr;
+            const float lo1 = p.relu1 ? 0.f : -INFINITY, lo2 = p.relu2 ? 0.f : -INFINITY;
+            const long long pix_main = ob * p.osb + (long long)(oh * p.up + p.oy) * p.osh + (long long)(ow * p.up + p.ox) * p.osw;
+            const long long pix_shuf = ob * p.osb + (long long)(oh * 2) * p.osh + (long long)(ow * 2) * p.osw;
+            const long long pix_out2 = ob * p.o2sb + (long long)(oh * p.up + p.oy) * p.o2sh + (long long)(ow * p.up + p.ox) * p.o2sw;
+            const float *hw = sparams + 2 * 3 * kMaxBN;
+            // One chunk: wait for its TMEM load, kick off the load of the next chunk of this warp into `vn`,
             // then run the fp32 epilogue on `vc` and store.
             auto process = [&](int ci, int nxt, uint32_t(&vc)[32], uint32_t(&vn)[32]) {
                 const int c0 = ci * 32;
                 uint4 rres[4];
                 const int n = n0 + c0;
-                const bool do_res = res_row != nullptr && n < p.N_total;
+                const bool do_res = res_row != nullptr && n < N_total;
                 if (do_res) {  // residual prefetch: global loads overlap the TMEM load latency
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         rres[g] = make_uint4(0, 0, 0, 0);
                         const int ng = n + 8 * g;
-                        if (c0 + 8 * g >= p.BN) continue;
-                        if (ng < p.split_n) {
-                            if (ng < p.c_store) rres[g] = __ldg(reinterpret_cast<const uint4 *>(res_row + 2 * ng));
-                        } else if (res_row2 != nullptr && ng - p.split_n < p.c_store2) {
-                            rres[g] = __ldg(reinterpret_cast<const uint4 *>(res_row2 + 2 * (ng - p.split_n)));
+                        if (c0 + 8 * g >= BN) continue;
+                        if (ng < split_n) {
+                            if (ng < c_store) rres[g] = __ldg(reinterpret_cast<const uint4 *>(res_row + 2 * ng));
+                        } else if (res_row2 != nullptr && ng - split_n < c_store2) {
+                            rres[g] = __ldg(reinterpret_cast<const uint4 *>(res_row2 + 2 * (ng - split_n)));
                         }
                     }
                 }
                 tmem_ld_wait();
                 if (nxt >= 0) {
                     __syncwarp();
-                    tmem_ld_chunk(tbase + nxt * 32, vn, p.BN - nxt * 32);
+                    tmem_ld_chunk(tbase + nxt * 32, vn, BN - nxt * 32);
                 }
                 if (!valid) return;
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
                     const int cc = c0 + 16 * hh;       // column within the tile
                     const int nn = n0 + cc;            // GEMM column
-                    if (cc >= p.BN || nn >= p.N_total) continue;
+                    if (cc >= BN || nn >= N_total) continue;
                     float y[16];
+                    {   // +bias, ReLU  (parameters are read as 4 x LDS.128 broadcasts)
+                        const float4 *b4 = reinterpret_cast<const float4 *>(sb + cc);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) y[j] = __uint_as_float(vc[16 * hh + j]) + sb[cc + j];
-                    if (p.relu1) {
+                        for (int g = 0; g < 4; ++g) {
+                            const float4 bv = b4[g];
+                            y[4 * g + 0] = fmaxf(__uint_as_float(vc[16 * hh + 4 * g + 0]) + bv.x, lo1);
+                            y[4 * g + 1] = fmaxf(__uint_as_float(vc[16 * hh + 4 * g + 1]) + bv.y, lo1);
+                            y[4 * g + 2] = fmaxf(__uint_as_float(vc[16 * hh + 4 * g + 2]) + bv.z, lo1);
+                            y[4 * g + 3] = fmaxf(__uint_as_float(vc[16 * hh + 4 * g + 3]) + bv.w, lo1);
+                        }
+                    }
+                    if (has_scale) {
+                        const float4 *s4 = reinterpret_cast<const float4 *>(sb + kMaxBN + cc);
+                        const float4 *t4 = reinterpret_cast<const float4 *>(sb + 2 * kMaxBN + cc);
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) y[j] = fmaxf(y[j], 0.f);
+                        for (int g = 0; g < 4; ++g) {
+                            const float4 sv = s4[g], tv = t4[g];
+                            y[4 * g + 0] = fmaf(y[4 * g + 0], sv.x, tv.x);
+                            y[4 * g + 1] = fmaf(y[4 * g + 1], sv.y, tv.y);
+                            y[4 * g + 2] = fmaf(y[4 * g + 2], sv.z, tv.z);
+                            y[4 * g + 3] = fmaf(y[4 * g + 3], sv.w, tv.w);
+                        }
                     }
-                    if (p.scale != nullptr) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) y[j] = fmaf(y[j], sb[kMaxBN + cc + j], sb[2 * kMaxBN + cc + j]);
-                    }
-                    int chan = nn, py = oh * p.up + p.oy, px = ow * p.up + p.ox;
-                    if (p.shuffle) {
-                        const int g = nn / p.group_n;
-                        chan = nn - g * p.group_n;
-                        py = oh * 2 + (g >> 1);
-                        px = ow * 2 + (g & 1);
-                    }
-                    const bool second = nn >= p.split_n;          // column split (out2 / residual2)
-                    if (second) chan = nn - p.split_n;
-                    const int cstore = second ? p.c_store2 : p.c_store;
-                    if (p.head_w == nullptr && chan >= cstore) continue;
-                    const bool hi_ok = (chan + 8) < cstore;
                     if (do_res) {
                         const uint32_t rr[8] = {rres[2 * hh].x, rres[2 * hh].y, rres[2 * hh].z, rres[2 * hh].w,
                                                 rres[2 * hh + 1].x, rres[2 * hh + 1].y, rres[2 * hh + 1].z,
                                                 rres[2 * hh + 1].w};
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const float2 f = unpack2(rr[j], p.dtype);
+                            const float2 f = unpack2(rr[j], dt);
                             y[2 * j] += f.x;
                             y[2 * j + 1] += f.y;
                         }
                     }
-                    if (p.relu2) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) y[j] = fmaxf(y[j], 0.f);
-                    }
-                    if (p.head_w != nullptr) {   // fused 1x1 head: three dot products over this thread's columns
-                        const float *hw = sparams + 2 * 3 * kMaxBN;
+                    for (int j = 0; j < 16; ++j) y[j] = fmaxf(y[j], lo2);
+                    if (head) {   // fused 1x1 head: three dot products over this thread's columns
+                        const float4 *h0 = reinterpret_cast<const float4 *>(hw + cc);
+                        const float4 *h1 = reinterpret_cast<const float4 *>(hw + kMaxBN + cc);
+                        const float4 *h2 = reinterpret_cast<const float4 *>(hw + 2 * kMaxBN + cc);
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            hacc0 = fmaf(y[j], hw[cc + j], hacc0);
-                            hacc1 = fmaf(y[j], hw[kMaxBN + cc + j], hacc1);
-                            hacc2 = fmaf(y[j], hw[2 * kMaxBN + cc + j], hacc2);
+                        for (int g = 0; g < 4; ++g) {
+                            const float4 a = h0[g], b = h1[g], c = h2[g];
+                            hacc0 = fmaf(y[4 * g + 3], a.w, fmaf(y[4 * g + 2], a.z, fmaf(y[4 * g + 1], a.y, fmaf(y[4 * g], a.x, hacc0))));
+                            hacc1 = fmaf(y[4 * g + 3], b.w, fmaf(y[4 * g + 2], b.z, fmaf(y[4 * g + 1], b.y, fmaf(y[4 * g], b.x, hacc1))));
+                            hacc2 = fmaf(y[4 * g + 3], c.w, fmaf(y[4 * g + 2], c.z, fmaf(y[4 * g + 1], c.y, fmaf(y[4 * g], c.x, hacc2))));
                         }
                         continue;
                     }
-                    const long long opix = second ? (ob * p.o2sb + py * p.o2sh + px * p.o2sw + chan)
-                                                  : (ob * p.osb + py * p.osh + px * p.osw + chan);
-                    void *obase = second ? p.out2 : p.out;
-                    if (p.out_dtype == HAVC_F32) {
-                        float4 *dst = reinterpret_cast<float4 *>(reinterpret_cast<float *>(obase) + opix);
+                    // destination
+                    long long off;
+                    int chan, cs;
+                    void *obase = p.out;
+                    if (shuffle) {   // column group g -> sub-pixel (g>>1, g&1); no division: groups are >= 16 wide
+                        const int g = (nn >= gn) + (nn >= 2 * gn) + (nn >= 3 * gn);
+                        chan = nn - g * gn;
+                        cs = c_store;
+                        off = pix_shuf + (g >> 1) * p.osh + (g & 1) * p.osw + chan;
+                    } else if (nn >= split_n) {
+                        chan = nn - split_n;
+                        cs = c_store2;
+                        off = pix_out2 + chan;
+                        obase = p.out2;
+                    } else {
+                        chan = nn;
+                        cs = c_store;
+                        off = pix_main + chan;
+                    }
+                    if (chan >= cs) continue;
+                    const bool hi_ok = (chan + 8) < cs;
+                    if (od == HAVC_F32) {
+                        float4 *dst = reinterpret_cast<float4 *>(reinterpret_cast<float *>(obase) + off);
                         dst[0] = make_float4(y[0], y[1], y[2], y[3]);
                         dst[1] = make_float4(y[4], y[5], y[6], y[7]);
                         if (hi_ok) {
@@ -489,8 +518,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                             dst[3] = make_float4(y[12], y[13], y[14], y[15]);
                         }
                     } else {
-                        uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<uint16_t *>(obase) + opix);
-                        const int od = p.out_dtype;
+                        uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<uint16_t *>(obase) + off);
                         dst[0] = make_uint4(pack2(y[0], y[1], od), pack2(y[2], y[3], od), pack2(y[4], y[5], od),
                                             pack2(y[6], y[7], od));
                         if (hi_ok)
