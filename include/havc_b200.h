@@ -95,6 +95,10 @@ typedef struct {
     const float *head_w;
     float *head_out;
     int64_t head_stride_w, head_stride_h, head_stride_b;
+    /* 1: stage the output tile in shared memory and write it with TMA bulk tensor stores (coalesced, clipped at the
+     * tensor bounds).  Honoured for 16-bit NHWC / PixelShuffle outputs with BN % 64 == 0; otherwise the epilogue falls
+     * back to per-thread vector stores.                                                                           */
+    int32_t tma_store;
 } havc_conv_desc;
 
 const char *havc_last_error(void);

@@ -64,6 +64,7 @@ class ConvDesc(C.Structure):
         ("res2_stride_w", C.c_int64), ("res2_stride_h", C.c_int64), ("res2_stride_b", C.c_int64),
         ("head_w", C.c_void_p), ("head_out", C.c_void_p),
         ("head_stride_w", C.c_int64), ("head_stride_h", C.c_int64), ("head_stride_b", C.c_int64),
+        ("tma_store", C.c_int32),
     ]
 
 

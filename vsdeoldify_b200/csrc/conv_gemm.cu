@@ -68,6 +68,10 @@ struct ConvParams {
     int c_store2;
     const void *residual2;
     long long r2sw, r2sh, r2sb;
+    // TMA-store epilogue: the tile is staged in shared memory (128B-swizzled 64-channel sub-tiles) and written with
+    // cp.async.bulk.tensor stores (coalesced, clipped at the tensor bounds); stage_out_bytes = 128*BN*2
+    int tma_store;
+    uint32_t stage_out_bytes;
     // fused 1x1 head: logits[pix][o] = sum_n y[n] * head_w[o][n]  (o < 3), written as fp32 [pix][4]; no tile store
     const float *head_w;
     float *head_out;
@@ -209,12 +213,25 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 // ---------------------------------------------------------------------------------------------
 // The kernel
 // ---------------------------------------------------------------------------------------------
+struct StoreMaps {
+    CUtensorMap m[4];   // [0] plain NHWC output; [0..3] the four PixelShuffle sub-pixel views
+};
+
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap *tm, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                 :
+                 : "l"(tm), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+                 : "memory");
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                 const __grid_constant__ CUtensorMap tmW, const __grid_constant__ ConvParams p) {
+                 const __grid_constant__ CUtensorMap tmW, const __grid_constant__ StoreMaps tmO,
+                 const __grid_constant__ ConvParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bar_base = smem_base + p.num_stages * p.stage_bytes;
+    const uint32_t stage_out = smem_base + p.num_stages * p.stage_bytes;        // 1024-aligned output staging
+    const uint32_t bar_base = stage_out + p.stage_out_bytes;
     // barrier layout: full[kMaxStages], empty[kMaxStages], tmem_full[2], tmem_empty[2], tmem_ptr
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
@@ -374,6 +391,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             const int ow = wt * p.bw + rw, oh = ht * p.bh + rh, ob = bt * p.bb + rb;
             const bool valid = (ow < p.out_W) && (oh < p.out_H) && (ob < p.out_B);
 
+            if (p.tma_store && etid == 0)   // previous tile's bulk stores must have finished reading the staging buffer
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             // stage this tile's per-column parameters in shared memory (double-buffered by tile parity)
             float *sb = sparams + pbuf * (3 * kMaxBN);
             for (int i = etid; i < p.BN; i += 256) {
@@ -402,6 +421,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             const int BN = p.BN, N_total = p.N_total, split_n = p.split_n, c_store = p.c_store, c_store2 = p.c_store2;
             const int dt = p.dtype, od = p.out_dtype, gn = p.group_n;
             const bool shuffle = p.shuffle != 0, has_scale = p.scale != nullptr, head = p.head_w != nullptr;
+            const bool tma_store = p.tma_store != 0;
             const float lo1 = p.relu1 ? 0.f : -INFINITY, lo2 = p.relu2 ? 0.f : -INFINITY;
             const long long pix_main = ob * p.osb + (long long)(oh * p.up + p.oy) * p.osh + (long long)(ow * p.up + p.ox) * p.osw;
             const long long pix_shuf = ob * p.osb + (long long)(oh * 2) * p.osh + (long long)(ow * 2) * p.osw;
@@ -488,6 +508,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         }
                         continue;
                     }
+                    if (tma_store) {   // stage into the swizzled 64-channel sub-tile; garbage rows/columns are clipped by TMA
+                        const uint32_t sub = stage_out + (uint32_t)(cc >> 6) * (kTileM * 128u) + (uint32_t)r * 128u;
+                        const uint32_t k16 = (uint32_t)(cc & 63) >> 3;
+                        const uint4 v0 = make_uint4(pack2(y[0], y[1], od), pack2(y[2], y[3], od), pack2(y[4], y[5], od),
+                                                    pack2(y[6], y[7], od));
+                        const uint4 v1 = make_uint4(pack2(y[8], y[9], od), pack2(y[10], y[11], od), pack2(y[12], y[13], od),
+                                                    pack2(y[14], y[15], od));
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sub + ((k16 ^ (r & 7u)) << 4)), "r"(v0.x),
+                                     "r"(v0.y), "r"(v0.z), "r"(v0.w) : "memory");
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sub + (((k16 + 1u) ^ (r & 7u)) << 4)),
+                                     "r"(v1.x), "r"(v1.y), "r"(v1.z), "r"(v1.w) : "memory");
+                        continue;
+                    }
                     // destination
                     long long off;
                     int chan, cs;
@@ -562,6 +595,24 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 tc_fence_before();
                 mbar_arrive(tearly_bar(as));
             }
+            if (tma_store) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> async proxy
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                if (etid == 0) {
+                    const int w0 = wt * p.bw, h0 = ht * p.bh, b0 = bt * p.bb;
+                    for (int sub = 0; sub < (BN >> 6); ++sub) {
+                        const int nn = n0 + sub * 64;
+                        if (nn >= N_total) break;
+                        if (shuffle) {
+                            const int g = (nn >= gn) + (nn >= 2 * gn) + (nn >= 3 * gn);
+                            tma_store_5d(&tmO.m[g], stage_out + sub * (kTileM * 128u), nn - g * gn, w0, h0, b0, 0);
+                        } else {
+                            tma_store_5d(&tmO.m[0], stage_out + sub * (kTileM * 128u), nn, w0, h0, b0, 0);
+                        }
+                    }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            }
             if (p.head_w != nullptr) {   // the two warps of a lane quarter each hold half of the columns
                 float *hx = sparams + (2 * 3 + 3) * kMaxBN;   // [128 rows][4]
                 if (half == 1) {
@@ -580,6 +631,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         }
     }
 
+    if (p.tma_store && threadIdx.x == 128) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     tc_fence_before();
     __syncthreads();
     if (warp == 2) {
@@ -716,7 +768,12 @@ extern "C" int havc_conv_gemm(const havc_conv_desc *d, void *stream) {
     p.staggered = (2 * d->BN > (int)kTmemCols) ? 1 : 0;
     p.acc_stride = p.staggered ? (int)kTmemCols - d->BN : d->BN;
     p.stage_bytes = kABytes + d->BN * 128;
-    int stages = (227 * 1024 - 1024 - 256 - kEpiSmemFloats * (int)sizeof(float)) / (int)p.stage_bytes;
+    const bool out16 = d->out_dtype == HAVC_F16 || d->out_dtype == HAVC_BF16;
+    p.tma_store = (d->tma_store && out16 && d->out != nullptr && d->BN % 64 == 0 && d->N_total % 64 == 0 && d->split_n == 0 &&
+                   d->head_w == nullptr && d->up == 1 && d->oy == 0 && d->ox == 0 && (!d->shuffle || d->group_n % 64 == 0))
+                      ? 1 : 0;
+    p.stage_out_bytes = p.tma_store ? (uint32_t)(kTileM * d->BN * 2) : 0u;
+    int stages = (227 * 1024 - 1024 - 256 - kEpiSmemFloats * (int)sizeof(float) - (int)p.stage_out_bytes) / (int)p.stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     HAVC_CHECK_ARG(stages >= 2, "havc_conv_gemm: tile too large for shared memory");
     p.num_stages = stages;
@@ -768,14 +825,31 @@ extern "C" int havc_conv_gemm(const havc_conv_desc *d, void *stream) {
     }
     if (d->b_batched) HAVC_CHECK_ARG(d->box_b == 1, "havc_conv_gemm: b_batched=1 needs box_b=1");
 
-    const size_t smem = (size_t)p.num_stages * p.stage_bytes + 1024 + 256 + kEpiSmemFloats * sizeof(float);
+    const size_t smem = (size_t)p.num_stages * p.stage_bytes + p.stage_out_bytes + 1024 + 256 + kEpiSmemFloats * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
         HAVC_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
+    StoreMaps tmO;
+    memset(&tmO, 0, sizeof(tmO));
+    if (p.tma_store) {
+        const int nmaps = d->shuffle ? 4 : 1;
+        for (int g = 0; g < nmaps; ++g) {
+            havc_act_view v;
+            memset(&v, 0, sizeof(v));
+            const long long off = d->shuffle ? ((g >> 1) * d->out_stride_h + (g & 1) * d->out_stride_w) : 0;
+            v.ptr = reinterpret_cast<const uint16_t *>(d->out) + off;
+            v.C = d->c_store; v.W = d->out_W; v.H = d->out_H; v.B = d->out_B; v.P = 1;
+            const int m = d->shuffle ? 2 : 1;
+            v.stride_w = m * d->out_stride_w; v.stride_h = m * d->out_stride_h; v.stride_b = d->out_stride_b;
+            v.stride_p = d->out_stride_b * d->out_B;
+            rc = encode_act(&tmO.m[g], v, d->out_dtype, d->box_w, d->box_h, d->box_b);
+            if (rc) return rc;
+        }
+    }
     int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-    conv_gemm_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA0, tmA1, tmW, p);
+    conv_gemm_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA0, tmA1, tmW, tmO, p);
     HAVC_LAUNCHED();
     return HAVC_OK;
 }

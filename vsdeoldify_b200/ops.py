@@ -10,6 +10,7 @@ done by libhavc_b200.so.  Layout conventions:
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence, Tuple
 
@@ -17,6 +18,9 @@ import torch
 
 from . import _lib
 from ._lib import HAVC_BF16, HAVC_F16, HAVC_F32, ActView, ConvDesc
+
+
+TMA_STORE_DEFAULT = os.environ.get("HAVC_B200_TMA_STORE", "1") != "0"
 
 
 def pad_to(x: int, m: int) -> int:
@@ -195,7 +199,7 @@ def make_conv(src0: torch.Tensor, weight: torch.Tensor, out: torch.Tensor, taps,
               up=1, oy=0, ox=0, shuffle=False, group_n=0, c_store: Optional[int] = None,
               src1_single_tap: bool = False, src1_wi: int = 0, split_n: int = 0, out2: Optional[torch.Tensor] = None,
               c_store2: int = 0, residual2: Optional[torch.Tensor] = None, head_w: Optional[torch.Tensor] = None,
-              head_out: Optional[torch.Tensor] = None, name: str = "") -> ConvOp:
+              head_out: Optional[torch.Tensor] = None, tma_store: Optional[bool] = None, name: str = "") -> ConvOp:
     """src0/src1: NHWC (or [P,B,H,W,C]) 16-bit device tensors; weight: packed [rows,taps,cin] or
     [batches,rows,taps,cin]; out: NHWC tensor written at pixel (h*up+oy, w*up+ox)."""
     d = ConvDesc()
@@ -267,5 +271,6 @@ def make_conv(src0: torch.Tensor, weight: torch.Tensor, out: torch.Tensor, taps,
         assert head_out.dim() == 4 and head_out.shape[-1] == 4
         d.head_w, d.head_out = head_w.data_ptr(), head_out.data_ptr()
         d.head_stride_b, d.head_stride_h, d.head_stride_w = head_out.stride()[:3]
+    d.tma_store = int(TMA_STORE_DEFAULT if tma_store is None else tma_store)
     keep += [out2, residual2, head_w, head_out]
     return ConvOp(d, keep, name=name)
