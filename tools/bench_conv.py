@@ -20,6 +20,9 @@ CASES = {
     "enc_l3_c2_b32": (32, 24, 24, [256], 256, 3, None, dict(bias=True, relu1=True)),
     "enc_l3_c1_b32": (32, 24, 24, [1024], 256, 1, None, dict(bias=True, relu1=True)),
     "enc_l3_c3_b32": (32, 24, 24, [256], 1024, 1, None, dict(bias=True, residual=True, relu2=True)),
+    "enc_l1_c3_b16": (16, 96, 96, [64], 256, 1, None, dict(bias=True, residual=True, relu2=True)),
+    "enc_l1_c1_b16": (16, 96, 96, [256], 64, 1, None, dict(bias=True, relu1=True)),
+    "enc_l2_c3_b16": (16, 48, 48, [128], 512, 1, None, dict(bias=True, residual=True, relu2=True)),
     "middle0_b8": (8, 12, 12, [2048], 4096, 3, None, dict(relu1=True, affine=True)),
     "middle0_b32": (32, 12, 12, [2048], 4096, 3, None, dict(relu1=True, affine=True)),
 }

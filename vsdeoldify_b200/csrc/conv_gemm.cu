@@ -21,6 +21,7 @@
 // Warp roles (384 threads, 1 CTA/SM): warp0 = TMA producer, warp1 = MMA issuer, warp2 = TMEM
 // allocator, warps4-11 = epilogue (TMEM lane quarter = warp % 4; two warps per quarter split the columns).
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace havc {
 
@@ -371,7 +372,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         float *sparams = reinterpret_cast<float *>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));
         int as = 0;
         uint32_t aphase = 0;
-        int pbuf = 0;
+        int pbuf = 0, last_nt = -1;
         const int nchunks = (p.BN + 31) >> 5;
         if (p.head_w != nullptr) {   // 1x1 head weights [3][BN] -> shared memory, once per CTA
             float *hw = sparams + 2 * 3 * kMaxBN;
@@ -393,17 +394,22 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
             if (p.tma_store && etid == 0)   // previous tile's bulk stores must have finished reading the staging buffer
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            // stage this tile's per-column parameters in shared memory (double-buffered by tile parity)
-            float *sb = sparams + pbuf * (3 * kMaxBN);
-            for (int i = etid; i < p.BN; i += 256) {
-                const int n = n0 + i;
-                const bool in = n < p.N_total;
-                sb[i] = (in && p.bias) ? __ldg(p.bias + n) : 0.f;
-                sb[kMaxBN + i] = (in && p.scale) ? __ldg(p.scale + n) : 1.f;
-                sb[2 * kMaxBN + i] = (in && p.shift) ? __ldg(p.shift + n) : 0.f;
+            // stage this tile's per-column parameters in shared memory (double-buffered; reloaded only when the N tile
+            // changes, i.e. never after the first tile of a launch with a single N tile)
+            if (nt != last_nt) {
+                pbuf ^= 1;
+                float *sbw = sparams + pbuf * (3 * kMaxBN);
+                for (int i = etid; i < p.BN; i += 256) {
+                    const int n = n0 + i;
+                    const bool in = n < p.N_total;
+                    sbw[i] = (in && p.bias) ? __ldg(p.bias + n) : 0.f;
+                    sbw[kMaxBN + i] = (in && p.scale) ? __ldg(p.scale + n) : 1.f;
+                    sbw[2 * kMaxBN + i] = (in && p.shift) ? __ldg(p.shift + n) : 0.f;
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                last_nt = nt;
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            pbuf ^= 1;
+            const float *sb = sparams + pbuf * (3 * kMaxBN);
 
             const uint8_t *res_row = nullptr, *res_row2 = nullptr;
             if (p.residual != nullptr && valid)
@@ -777,7 +783,10 @@ extern "C" int havc_conv_gemm(const havc_conv_desc *d, void *stream) {
     if (stages > kMaxStages) stages = kMaxStages;
     HAVC_CHECK_ARG(stages >= 2, "havc_conv_gemm: tile too large for shared memory");
     p.num_stages = stages;
-    p.n_part0 = d->BN > 256 ? 256 : d->BN;
+    // BN > 256 is issued as two MMAs per K step.  Balanced halves (272 = 144 + 128) keep both compute-bound; a 256 + 16
+    // split makes the narrow one shared-memory-bound (it re-reads the whole 128 x 16 A slice for 16 columns).
+    static const bool legacy_split = getenv("HAVC_B200_SPLIT256") != nullptr;   // A/B switch for profiling
+    p.n_part0 = d->BN > 256 ? (legacy_split ? 256 : ((d->BN / 2 + 15) / 16) * 16) : d->BN;
     p.n_part1 = d->BN - p.n_part0;
     const uint32_t fmt = d->dtype == HAVC_F16 ? 0u : 1u;
     auto idesc = [&](int n) -> uint32_t {
