@@ -94,8 +94,80 @@ def golden_pixels():
     np.savez_compressed(os.path.join(HERE, "vsslib_pixels.npz"), **out)
 
 
+def filter_test_pair(seed, h, w, luma):
+    """Two colourful uint8 RGB images with frame-mean luma near `luma` (0..1): `a` plays the DeOldify result,
+    `b` the second model; saturated patches of every hue, gray areas and hard edges included."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for k in range(2):
+        base = color_test_image(seed * 10 + k * 3, h, w).astype(np.float32) / 255
+        hue_patch = rng.uniform(0, 1, (h // 8 + 1, w // 8 + 1, 3)).astype(np.float32)
+        hue_patch = np.kron(hue_patch, np.ones((8, 8, 1), np.float32))[:h, :w]
+        img = 0.6 * base + 0.4 * hue_patch
+        img[: h // 6] = img[: h // 6].mean(-1, keepdims=True)            # a gray band (low saturation)
+        img = img * (luma / max(img.mean(), 1e-3))
+        out.append((np.clip(img, 0, 1) * 255).astype(np.uint8))
+    return out
+
+
+def golden_filters():
+    """vsslib merges and chroma-adjust filters, run through the REAL reference code: mcomb.vs_sc_combine_models on
+    clips of the in-repo VapourSynth stand-in (the reference's selectors, frame_to_image / image_to_frame and
+    imfilters / restcolor / nputils execute unmodified), plus the image-level helpers called directly."""
+    refshim.install()
+    from vsdeoldify_b200 import vs_shim
+    sys.modules["vapoursynth"] = vs_shim
+    from PIL import Image
+    from vsdeoldify.vsslib import imfilters, mcomb, restcolor, vsfilters
+    out = {}
+    H, W = 64, 80
+    lumas = (0.05, 0.15, 0.25, 0.5, 0.85)
+    for li, luma in enumerate(lumas):
+        a, b = filter_test_pair(50 + li, H, W, luma)
+        out[f"a_{li}"], out[f"b_{li}"] = a, b
+        clip_a = vs_shim.array_clip(np.ascontiguousarray(np.transpose(a, (2, 0, 1)))[None])
+        clip_b = vs_shim.array_clip(np.ascontiguousarray(np.transpose(b, (2, 0, 1)))[None])
+        for method in (2, 3, 4, 5, 7):
+            for wi, w in enumerate((0.4, 0.7)):
+                c = mcomb.vs_sc_combine_models(clip_a, clip_b, method=method, clipb_weight=w, scenechange=False)
+                f = c.get_frame(0)
+                out[f"combine_m{method}_w{wi}_{li}"] = np.dstack([np.asarray(f[p]) for p in range(3)])
+        # non-default parameters: hard luma mask (limit == white), no red fix, adaptive alpha 2
+        c = mcomb.vs_sc_combine_models(clip_a, clip_b, method=4, clipb_weight=0.6, LMM_p=[0.3, 0.3, 1.0], scenechange=False)
+        out[f"combine_m4_hard_{li}"] = np.dstack([np.asarray(c.get_frame(0)[p]) for p in range(3)])
+        c = mcomb.vs_sc_combine_models(clip_a, clip_b, method=3, clipb_weight=0.5, CMC_p=[0.3, False, 20, 24], scenechange=False)
+        out[f"combine_m3_noredfix_{li}"] = np.dstack([np.asarray(c.get_frame(0)[p]) for p in range(3)])
+        c = mcomb.vs_sc_combine_models(clip_a, clip_b, method=5, clipb_weight=0.5, ALM_p=[0.6, 2.0, 0.1], scenechange=False)
+        out[f"combine_m5_alpha2_{li}"] = np.dstack([np.asarray(c.get_frame(0)[p]) for p in range(3)])
+        # method 6 up to (not including) std.Merge: vs_sc_recover_gradient_color on the clips
+        for algo in (0, 1, 2):
+            c = vsfilters.vs_sc_recover_gradient_color(clip=clip_a, clip_color=clip_b, sat=0.8, tht=30, weight=0, alpha=2.0,
+                                                       scenechange=False, algo=algo)
+            out[f"recover_gradient_algo{algo}_{li}"] = np.dstack([np.asarray(c.get_frame(0)[p]) for p in range(3)])
+        out[f"luma_{li}"] = np.float64(imfilters.get_image_luma(Image.fromarray(a), 255))
+        ia = Image.fromarray(b)
+        out[f"hue_adjust_default_{li}"] = np.asarray(restcolor.adjust_hue_range(ia, hue_adjust="300:360|0.8,0.1"))
+        out[f"hue_adjust_shift_{li}"] = np.asarray(restcolor.adjust_hue_range(ia, hue_adjust="blue,cyan|+40,0.3"))
+        out[f"hue_adjust_neg_{li}"] = np.asarray(restcolor.adjust_hue_range(ia, hue_adjust="0:60,200:260|0.5,-0.4"))
+        out[f"tweak_bcg_{li}"] = np.asarray(imfilters.image_tweak(ia, bright=12, cont=1.1))
+        out[f"tweak_sat_range_{li}"] = np.asarray(imfilters.image_tweak(ia, sat=0.6, hue_range="280:360,0:30"))
+        out[f"tweak_sat_up_{li}"] = np.asarray(imfilters.image_tweak(ia, sat=1.4, bright=-20))
+        out[f"levels_{li}"] = np.asarray(imfilters.luma_adjusted_levels(ia, luma_min=0.3, gamma=1.3, gamma_luma_min=0.4,
+                                                                         gamma_alpha=0.5, gamma_min=0.5))
+        out[f"levels_plain_{li}"] = np.asarray(imfilters.luma_adjusted_levels(ia, luma_min=0.2, gamma=0.8, gamma_luma_min=0.6))
+        out[f"stab_adaptive_{li}"] = np.asarray(imfilters.chroma_stabilizer_adaptive(Image.fromarray(a), ia, 14, 18, 1.0))
+        out[f"stab_{li}"] = np.asarray(imfilters.chroma_stabilizer(Image.fromarray(a), ia, 0.1, 1.0))
+        out[f"restore_w_{li}"] = np.asarray(restcolor.restore_color_gradient(ia, Image.fromarray(a), sat=0.7, tht=40, weight=0.3,
+                                                                             alpha=3.0, algo=0))
+        out[f"restore_wneg_{li}"] = np.asarray(restcolor.restore_color_gradient(ia, Image.fromarray(a), sat=1.0, tht=20, weight=-0.5,
+                                                                                alpha=4.0, algo=1))
+    np.savez_compressed(os.path.join(HERE, "vsslib_filters.npz"), **out)
+    print("filters golden:", len(out), "arrays")
+
+
 if __name__ == "__main__":
     golden_unets()
     golden_pixels()
+    golden_filters()
     golden_render()
     print("golden fixtures written to", HERE)

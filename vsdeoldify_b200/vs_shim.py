@@ -25,7 +25,7 @@ class Error(Exception):
     pass
 
 
-@dataclass(frozen=True)
+@dataclass(frozen=True, eq=False)
 class VideoFormat:
     id: int
     name: str
@@ -34,6 +34,20 @@ class VideoFormat:
     num_planes: int
     subsampling_w: int = 0
     subsampling_h: int = 0
+
+    # real VapourSynth: `clip.format.id == vs.RGB24` holds (the preset constant is an int enum); keep that true here
+    def __eq__(self, other):
+        if isinstance(other, VideoFormat):
+            return self.id == other.id
+        if isinstance(other, int):
+            return self.id == other
+        return NotImplemented
+
+    def __hash__(self):
+        return hash(self.id)
+
+    def __int__(self):
+        return self.id
 
 
 RGB24 = VideoFormat(1, "RGB24", RGB, 8, 3)
