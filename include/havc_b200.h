@@ -175,6 +175,56 @@ int havc_resample_v(const uint8_t *in, float *out, long long planes, int Hin, in
 int havc_post_horizontal(const float *in, const uint8_t *orig, uint8_t *out, int B, int S, int H, int W,
                          const int *start, const float *weights, int taps, int transplant, void *stream);
 
+/* ---- vsslib model merges and chroma-adjust filters (planar u8 RGB frames [B][3][H][W]) ---------------------
+ * Per-frame statistics live on the device as exact integer sums: stats[2*b] = sum of OpenCV 8-bit Y,
+ * stats[2*b+1] = sum of Pillow 'L' of frame b; the kernels derive get_image_luma() = round(mean(Y)/255, 6)
+ * (vsdeoldify/vsslib/imfilters.py:597-601) and ImageStat means from them, so no host round trip is needed.
+ * `simd_width` is the per-row vector block of the host OpenCV build whose 8-bit HSV->RGB the reference calls
+ * (its SIMD body truncates x*255, the scalar row tail rounds; 32 for an AVX2 build, 0 = round everywhere). */
+#define HAVC_MAX_HUE_RANGES 8
+typedef struct {
+    int32_t n;                                   /* number of (min, max) hue ranges in DEGREES (0..360), strict bounds */
+    double lo_deg[HAVC_MAX_HUE_RANGES], hi_deg[HAVC_MAX_HUE_RANGES];
+} havc_hue_ranges;
+
+/* Frame sums of `img` (or of ImageEnhance.Brightness(img).enhance(bright) when bright != 1). */
+int havc_frame_stats(const uint8_t *img, int B, int H, int W, float bright, unsigned long long *stats, void *stream);
+/* chroma_stabilizer (imfilters.py:160-200; adaptive=0) / chroma_stabilizer_adaptive (imfilters.py:202-269; adaptive=1):
+ * U,V of b clamped around those of a, Y of a, Image.blend(a, result, weight) when weight < 1.  stats_out (optional)
+ * receives the Y sums of the result for the red fix. */
+int havc_chroma_stabilizer(const uint8_t *a, const uint8_t *b, uint8_t *out, int B, int H, int W, int adaptive, double alpha,
+                           int base_tol, int max_extra, float weight, unsigned long long *stats_out, void *stream);
+/* Dark-frame red-shift adjustment of ConstrainedChromaMerge / ChromaBoundAdaptiveMerge (mcomb.py:351-362, :405-416):
+ * image_tweak(sat, hue_range="280:360,0:30") + w_image_luma_merge chosen by the frame luma in `stats`. */
+int havc_red_fix(const uint8_t *stab, uint8_t *out, int B, int H, int W, const unsigned long long *stats, void *stream);
+/* LumaMaskedMerge.merge_frame (mcomb.py:238-271): image_luma_merge / w_image_luma_merge of (c, b), then
+ * image_weighted_merge(a, masked, weight). */
+int havc_luma_masked_merge(const uint8_t *a, const uint8_t *b, const uint8_t *c, uint8_t *out, int B, int H, int W,
+                           double luma_limit, double white_limit, float weight, void *stream);
+/* AdaptiveLumaMerge.merge_frame (mcomb.py:289-314): Image.blend(a, b, w') with w' from the frame luma of b. */
+int havc_adaptive_luma_merge(const uint8_t *a, const uint8_t *b, uint8_t *out, int B, int H, int W,
+                             const unsigned long long *stats_b, double luma_threshold, double alpha, double weight,
+                             double min_weight, void *stream);
+/* restore_color_gradient (restcolor.py:98-134) with the luma gating of vs_sc_recover_gradient_color
+ * (vsfilters.py:403-409; stats_gray != NULL) and the final std.Merge(gray, restored, merge_weight) of
+ * ChromaRetentionMerge (mcomb.py:511, vsfilters.py:730-739; merge_weight < 0 = none).  lut / lut_gated: device
+ * tables [256] of w_np_gradient_mask(S) for the normal and the gated alpha (built by the host). */
+int havc_restore_color_gradient(const uint8_t *color, const uint8_t *gray, uint8_t *out, int B, int H, int W, double sat,
+                                const uint8_t *lut, const uint8_t *lut_gated, double weight, double weight_gated,
+                                const unsigned long long *stats_gray, double merge_weight, int simd_width, void *stream);
+/* adjust_chroma (restcolor.py:239-286) behind adjust_hue_range / vs_sc_adjust_clip_hue (vsfilters.py:435-455). */
+int havc_adjust_chroma(const uint8_t *img, uint8_t *out, int B, int H, int W, const havc_hue_ranges *ranges, double sat, int hue,
+                       double weight, int simd_width, void *stream);
+/* image_tweak (imfilters.py:463-504) without gamma / hue (gamma raises in the reference, see oracle/filters_oracle.py):
+ * ImageEnhance Brightness -> Contrast -> Color, optionally restricted to hue ranges of the input.  stats_scratch
+ * (2*B u64) is needed when cont != 1. */
+int havc_image_tweak(const uint8_t *img, uint8_t *out, int B, int H, int W, double sat, double cont, double bright,
+                     const havc_hue_ranges *ranges, unsigned long long *stats_scratch, void *stream);
+/* luma_adjusted_levels (imfilters.py:335-372) behind sc_constrained_tweak (vsfilters.py:656-675). */
+int havc_luma_adjusted_levels(const uint8_t *img, uint8_t *out, int B, int H, int W, const unsigned long long *stats,
+                              double luma_min, double gamma, double gamma_luma_min, double gamma_alpha, double gamma_min,
+                              void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -68,6 +68,10 @@ class ConvDesc(C.Structure):
     ]
 
 
+class HueRanges(C.Structure):
+    _fields_ = [("n", C.c_int32), ("lo_deg", C.c_double * 8), ("hi_deg", C.c_double * 8)]
+
+
 # every symbol include/havc_b200.h declares: name -> (restype, argtypes)
 _SIGNATURES = {
     "havc_last_error": (C.c_char_p, []),
@@ -94,6 +98,23 @@ _SIGNATURES = {
                                   C.c_int, C.c_void_p]),
     "havc_post_horizontal": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                        C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "havc_frame_stats": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
+    "havc_chroma_stabilizer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
+                                         C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
+    "havc_red_fix": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "havc_luma_masked_merge": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double,
+                                         C.c_double, C.c_float, C.c_void_p]),
+    "havc_adaptive_luma_merge": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_double,
+                                           C.c_double, C.c_double, C.c_double, C.c_void_p]),
+    "havc_restore_color_gradient": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double,
+                                              C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_double, C.c_int,
+                                              C.c_void_p]),
+    "havc_adjust_chroma": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(HueRanges), C.c_double, C.c_int,
+                                     C.c_double, C.c_int, C.c_void_p]),
+    "havc_image_tweak": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
+                                   C.POINTER(HueRanges), C.c_void_p, C.c_void_p]),
+    "havc_luma_adjusted_levels": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_double, C.c_double,
+                                            C.c_double, C.c_double, C.c_double, C.c_void_p]),
 }
 
 _lib = None

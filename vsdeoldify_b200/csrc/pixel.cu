@@ -11,39 +11,9 @@
 // Resampling is table driven: for output index o, out[o] = sum_t w[o][t] * in[start[o] + t]; the host
 // builds the tables (Spline64 / Spline36 / Pillow triangle), so every resampler shares these kernels.
 #include "common.cuh"
+#include "pixel_math.cuh"
 
 namespace havc {
-
-static inline int grid1d(long long n, int block) {
-    long long g = (n + block - 1) / block;
-    long long cap = (long long)num_sms() * 32;
-    if (g > cap) g = cap;
-    if (g < 1) g = 1;
-    return (int)g;
-}
-
-__device__ __forceinline__ int sat8(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
-
-// OpenCV 8-bit COLOR_RGB2YUV / COLOR_YUV2RGB, Q14 fixed point (pinned against
-// cv2 4.13 by tests/test_pixel_oracle.py).
-__device__ __forceinline__ void rgb2yuv(int r, int g, int b, int &y, int &u, int &v) {
-    y = (4899 * r + 9617 * g + 1868 * b + 8192) >> 14;
-    u = sat8(((b - y) * 8061 + (128 << 14) + 8192) >> 14);
-    v = sat8(((r - y) * 14369 + (128 << 14) + 8192) >> 14);
-}
-__device__ __forceinline__ void yuv2rgb(int y, int u, int v, int &r, int &g, int &b) {
-    r = sat8(y + (((v - 128) * 18678 + 8192) >> 14));
-    g = sat8(y + (((u - 128) * -6472 + (v - 128) * -9519 + 8192) >> 14));
-    b = sat8(y + (((u - 128) * 33292 + 8192) >> 14));
-}
-// Keep the luma of `o` and the chroma of `c` (ColorizerFilter._post_process, filters.py:100-110).
-__device__ __forceinline__ void luma_transplant(int orr, int og, int ob, int cr, int cg, int cb, int &r, int &g,
-                                                int &b) {
-    int y, u, v, y2, u2, v2;
-    rgb2yuv(orr, og, ob, y, u, v);
-    rgb2yuv(cr, cg, cb, y2, u2, v2);
-    yuv2rgb(y, u2, v2, r, g, b);
-}
 
 // Horizontal pass: u8 rows -> float rows.  One block per input row: the row is staged in shared memory as
 // floats (coalesced 16-byte loads), every thread then produces outputs ox = tid, tid+blockDim, ...
@@ -298,11 +268,26 @@ __global__ void blend_u8_kernel(const uint4 *__restrict__ a, const uint4 *__rest
 
 using namespace havc;
 
+__global__ void blend_u8_tail_kernel(const uint8_t *__restrict__ a, const uint8_t *__restrict__ b, uint8_t *__restrict__ out,
+                                     long long n, float alpha) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint8_t)pil_blend(a[i], b[i], alpha);
+}
+
 extern "C" int havc_blend_u8(const uint8_t *a, const uint8_t *b, uint8_t *out, long long n, float alpha, void *stream) {
-    HAVC_CHECK_ARG(a && b && out && n % 16 == 0 && alpha >= 0.f && alpha <= 1.f, "havc_blend_u8: n must be a multiple of 16, alpha in [0,1]");
-    blend_u8_kernel<<<grid1d(n / 16, 256), 256, 0, (cudaStream_t)stream>>>((const uint4 *)a, (const uint4 *)b, (uint4 *)out,
-                                                                        n / 16, alpha);
-    HAVC_LAUNCHED();
+    HAVC_CHECK_ARG(a && b && out && n > 0 && alpha >= 0.f && alpha <= 1.f, "havc_blend_u8: alpha must be in [0,1]");
+    const bool aligned = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    const long long n16 = aligned ? n / 16 : 0;
+    if (n16 > 0) {
+        blend_u8_kernel<<<grid1d(n16, 256), 256, 0, (cudaStream_t)stream>>>((const uint4 *)a, (const uint4 *)b, (uint4 *)out, n16, alpha);
+        HAVC_LAUNCHED();
+    }
+    const long long rest = n - 16 * n16;
+    if (rest > 0) {   // unaligned buffers or the last n % 16 values
+        blend_u8_tail_kernel<<<(unsigned)((rest + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a + 16 * n16, b + 16 * n16, out + 16 * n16,
+                                                                                                rest, alpha);
+        HAVC_LAUNCHED();
+    }
     return HAVC_OK;
 }
 

@@ -1,0 +1,240 @@
+"""Host side of the vsslib model merges and chroma-adjust filters.
+
+Mirrors the reference's dispatcher `vs_sc_combine_models` (vsdeoldify/vsslib/mcomb.py:125-192) and the helpers
+around it: it parses the parameter lists and the hue-range mini language (restcolor.py:378-470), prepares the few
+host-side tables (gradient masks, restcolor.py:137-202) and sequences libhavc_b200 launches on planar RGB24 device
+batches `[B, 3, H, W]`.  Every frame-global quantity (mean luma) stays on the device, so a merge is graph-capturable.
+No pixel arithmetic happens here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .constants import DEF_ALM_p, DEF_CMC_p, DEF_CRT_p, DEF_LMM_p
+
+# per-row vector block of OpenCV's 8-bit HSV->RGB on the AVX2 build the reference was pinned against (its SIMD
+# body truncates, the row tail rounds — see include/havc_b200.h)
+CV_SIMD_WIDTH = 32
+DEF_MAX_COLOR_ALPHA, DEF_MIN_COLOR_ALPHA = 10.0, 1.0          # vsslib/constants.py
+
+_HUE_NAMES = {"red": (0, 30), "orange": (30, 60), "yellow": (60, 90), "yellow-green": (90, 120), "green": (120, 150),
+              "blue-green": (150, 180), "cyan": (180, 210), "blue": (210, 240), "blue-violet": (240, 270),
+              "violet": (270, 300), "red-violet": (300, 330), "rose": (330, 360)}
+
+
+class FilterError(ValueError):
+    """Raised for parameter combinations the reference rejects (or that are not built); havc.py turns it into vs.Error."""
+
+
+def parse_hue_range(hue_range: str) -> List[Tuple[float, float]]:
+    """_parse_hue_range per comma-separated item (restcolor.py:430-470): a colour name or 'min:max' in degrees."""
+    out = []
+    for part in hue_range.split(","):
+        if part in _HUE_NAMES:
+            lo, hi = _HUE_NAMES[part]
+        else:
+            p = part.split(":")
+            if len(p) == 2 and p[0].isnumeric() and p[1].isnumeric():
+                lo, hi = float(p[0]), float(p[1])
+            else:
+                raise FilterError("HybridAVC: unknown hue name: " + part)
+        out.append((float(lo), float(hi)))
+    return out
+
+
+def parse_hue_adjust(hue_adjust: str):
+    """_parse_hue_adjust (restcolor.py:378-410): 'ranges|sat_or_+-hue,weight' -> (ranges, sat, hue, weight) or None."""
+    p = hue_adjust.split("|")
+    sat, hue, weight = 1.0, 0, 0.0
+    if len(p) < 1 or len(p) > 2:
+        return None
+    if len(p) == 1:
+        return p[0], sat, hue, weight
+
+    def isfloat(x):
+        try:
+            float(x)
+            return True
+        except ValueError:
+            return False
+    sw = p[1].split(",")
+    if len(sw) != 2 or not isfloat(sw[0]) or not isfloat(sw[1]):
+        return None
+    if sw[0][0] in ("-", "+"):
+        hue = int(sw[0])
+    else:
+        sat = float(sw[0])
+    if sat > 10:
+        hue, sat = int(sat), 1.0
+    return p[0], sat, hue, float(sw[1])
+
+
+def hue_ranges_struct(hue_range: Optional[str]) -> Optional[_lib.HueRanges]:
+    if hue_range in (None, "", "none"):
+        return None
+    rs = parse_hue_range(hue_range)
+    if len(rs) > 8:
+        raise FilterError("at most 8 hue ranges are supported")
+    h = _lib.HueRanges()
+    h.n = len(rs)
+    for i, (lo, hi) in enumerate(rs):
+        h.lo_deg[i], h.hi_deg[i] = lo, hi
+    return h
+
+
+def gradient_mask_lut(tht: int, alpha: float, algo: int) -> np.ndarray:
+    """w_np_gradient_mask (restcolor.py:137-202) tabulated over the 256 possible saturation values; the table is what
+    the reference stores into its uint8 mask image."""
+    s = np.arange(256, dtype=np.uint8)
+    if algo == 0:
+        lum = s.clip(0, 255)
+        steep = 2.0
+        grad = np.where(lum < tht, steep * lum / alpha - tht, steep * (lum - tht) * alpha)
+        return (255.0 - tht - grad).clip(0, 255).astype(int).astype(np.uint8)
+    sf = s.astype(np.float32)
+    tht = int(np.clip(tht, 0, 255))
+    if tht == 0:
+        return np.zeros(256, np.uint8)
+    if algo == 1:
+        max_s = min(2 * tht, 200)
+        norm = (1.0 - (np.clip(sf, 0, max_s) / max_s)) ** alpha
+    else:
+        rel = np.clip(sf / tht, 0, 2)
+        norm = np.exp(-alpha * rel * np.log(2))
+        norm = np.where(sf >= 2 * tht, 0.0, norm)
+    return np.clip(norm * 255, 0, 255).astype(np.uint8)
+
+
+class FilterBank:
+    """Scratch buffers + launch sequencing for one (B, H, W) on one device."""
+
+    def __init__(self, B: int, H: int, W: int, device, simd_width: int = CV_SIMD_WIDTH):
+        self.B, self.H, self.W, self.dev = B, H, W, torch.device(device)
+        self.simd = simd_width
+        self.lib = _lib.lib()
+        u8 = dict(dtype=torch.uint8, device=self.dev)
+        self.tmp = [torch.empty(B, 3, H, W, **u8) for _ in range(3)]
+        self.stats = [torch.zeros(B, 2, dtype=torch.int64, device=self.dev) for _ in range(2)]
+        self._luts = {}
+        self.keep = []
+
+    # ---- helpers ---------------------------------------------------------------------------------------
+    def _chk(self, t: torch.Tensor):
+        assert t.dtype == torch.uint8 and t.is_contiguous() and tuple(t.shape) == (self.B, 3, self.H, self.W) and t.device == self.dev
+
+    def _lut(self, tht, alpha, algo) -> torch.Tensor:
+        key = (int(tht), float(alpha), int(algo))
+        if key not in self._luts:
+            self._luts[key] = torch.from_numpy(gradient_mask_lut(*key)).to(self.dev)
+        return self._luts[key]
+
+    def _dims(self):
+        return self.B, self.H, self.W
+
+    def frame_stats(self, img, stats, stream=0, bright: float = 1.0):
+        _lib.check(self.lib.havc_frame_stats(img.data_ptr(), *self._dims(), bright, stats.data_ptr(), stream), "frame_stats")
+
+    def blend(self, a, b, out, w: float, stream=0):
+        """image_weighted_merge (imfilters.py:113-124): Image.blend with the 0 / 1 shortcuts."""
+        if w == 0.0 or w == 1.0:
+            src = a if w == 0.0 else b
+            if out.data_ptr() != src.data_ptr():
+                _lib.check(self.lib.havc_blend_u8(src.data_ptr(), src.data_ptr(), out.data_ptr(), out.numel(), 0.0, stream), "copy")
+            return
+        _lib.check(self.lib.havc_blend_u8(a.data_ptr(), b.data_ptr(), out.data_ptr(), out.numel(), w, stream), "blend")
+
+    # ---- merges (mcomb.py) -------------------------------------------------------------------------------
+    def combine(self, a, b, out, method: int, weight: float, cmc_p: Sequence = DEF_CMC_p, lmm_p: Sequence = DEF_LMM_p,
+                alm_p: Sequence = DEF_ALM_p, crt_p: Sequence = DEF_CRT_p, stream: int = 0):
+        """vs_sc_combine_models (mcomb.py:125-192) for two S x S batches (sat / hue tweaks are the caller's)."""
+        for t in (a, b, out):
+            self._chk(t)
+        lib, (B, H, W) = self.lib, self._dims()
+        chroma_threshold = cmc_p[0]
+        red_fix, base_tol, max_extra = (cmc_p[1], cmc_p[2], cmc_p[3]) if len(cmc_p) > 1 else (True, 20, 24)
+        t0, t1, t2 = self.tmp
+        if method == 2:                                            # SimpleMerge
+            return self.blend(a, b, out, weight, stream)
+        if method in (3, 7):                                       # ConstrainedChromaMerge / ChromaBoundAdaptiveMerge
+            stab = t0 if (red_fix or method == 3) else out
+            _lib.check(lib.havc_chroma_stabilizer(a.data_ptr(), b.data_ptr(), stab.data_ptr(), B, H, W, int(method == 7),
+                                                  float(chroma_threshold), int(base_tol), int(max_extra), float(weight),
+                                                  self.stats[0].data_ptr() if red_fix else None, stream), "chroma_stabilizer")
+            res = stab
+            if red_fix:
+                res = t1 if method == 3 else out
+                _lib.check(lib.havc_red_fix(stab.data_ptr(), res.data_ptr(), B, H, W, self.stats[0].data_ptr(), stream), "red_fix")
+            if method == 3:                                        # mcomb.py:173-177
+                self.blend(a, b, t2, min(weight, 0.6), stream)
+                self.blend(res, t2, out, 0.3, stream)
+            return
+        if method == 4:                                            # LumaMaskedMerge
+            if lmm_p[2] < 1:
+                raise FilterError("LumaMaskedMerge with luma_mask_sat < 1 needs vs_tweak (zimg YUV420 round trip), not built")
+            _lib.check(lib.havc_luma_masked_merge(a.data_ptr(), b.data_ptr(), a.data_ptr(), out.data_ptr(), B, H, W, float(lmm_p[0]),
+                                                  float(lmm_p[1]), float(weight), stream), "luma_masked_merge")
+            return
+        if method == 5:                                            # AdaptiveLumaMerge
+            self.frame_stats(b, self.stats[0], stream)
+            _lib.check(lib.havc_adaptive_luma_merge(a.data_ptr(), b.data_ptr(), out.data_ptr(), B, H, W, self.stats[0].data_ptr(),
+                                                    float(alm_p[0]), float(alm_p[1]), float(weight), float(alm_p[2]), stream),
+                       "adaptive_luma_merge")
+            return
+        if method == 6:                                            # ChromaRetentionMerge
+            sat, tht, alpha, resize, mask_weight, algo = crt_p[0], crt_p[1], crt_p[2], crt_p[3], crt_p[4], crt_p[5]
+            if resize:
+                raise FilterError("ChromaRetentionMerge with chroma_resize=True (Spline64 down/up) is not built")
+            alpha = max(min(alpha, DEF_MAX_COLOR_ALPHA), DEF_MIN_COLOR_ALPHA)
+            self.frame_stats(a, self.stats[0], stream)
+            lut, lut_g = self._lut(tht, alpha, algo), self._lut(tht, max(alpha, 4.0), algo)
+            if weight == 0:                                        # vs_simple_merge (vsfilters.py:730-739) returns clipa
+                return self.blend(a, a, out, 0.0, stream)
+            mw = -1.0 if weight == 1 else float(weight)            # weight 1: the restored clip itself, no std.Merge
+            _lib.check(lib.havc_restore_color_gradient(b.data_ptr(), a.data_ptr(), out.data_ptr(), B, H, W, float(sat), lut.data_ptr(),
+                                                       lut_g.data_ptr(), float(mask_weight), float(min(mask_weight, -0.5)),
+                                                       self.stats[0].data_ptr(), float(mw), self.simd, stream),
+                       "restore_color_gradient")
+            return
+        raise FilterError("HAVC: only dd_method in (0,6) is supported")          # mcomb.py:192
+
+    # ---- chroma-adjust filters ------------------------------------------------------------------------------
+    def adjust_hue_range(self, img, out, hue_adjust: str, stream: int = 0) -> bool:
+        """adjust_hue_range (restcolor.py:221-237).  Returns False when the filter is the identity."""
+        if hue_adjust in ("none", ""):
+            return False
+        p = parse_hue_adjust(hue_adjust)
+        if p is None:
+            return False
+        rng = hue_ranges_struct(p[0])
+        if rng is None:
+            return False
+        _lib.check(self.lib.havc_adjust_chroma(img.data_ptr(), out.data_ptr(), *self._dims(), C.byref(rng), float(p[1]), int(p[2]),
+                                               float(p[3]), self.simd, stream), "adjust_chroma")
+        return True
+
+    def image_tweak(self, img, out, sat=1.0, cont=1.0, bright=0.0, hue=0.0, gamma=1.0, hue_range="none", stream: int = 0) -> bool:
+        """image_tweak (imfilters.py:463-504).  gamma != 1 raises like the reference does (its LUT has the wrong size);
+        hue != 0 (Pillow HSV round trip) is not built."""
+        if gamma != 1.0:
+            raise FilterError("wrong number of lut entries")
+        if hue != 0.0:
+            raise FilterError("image_tweak: hue shift (Pillow HSV) is not built")
+        rng = hue_ranges_struct(hue_range)
+        if sat == 1.0 and cont == 1.0 and bright == 0.0:
+            return False
+        _lib.check(self.lib.havc_image_tweak(img.data_ptr(), out.data_ptr(), *self._dims(), float(sat), float(cont), float(bright),
+                                             C.byref(rng) if rng is not None else None, self.stats[1].data_ptr(), stream), "image_tweak")
+        return True
+
+    def luma_adjusted_levels(self, img, out, luma_min=0.0, gamma=1.0, gamma_luma_min=0.0, gamma_alpha=0.0, gamma_min=0.2,
+                             stream: int = 0):
+        """luma_adjusted_levels (imfilters.py:335-372)."""
+        self.frame_stats(img, self.stats[1], stream)
+        _lib.check(self.lib.havc_luma_adjusted_levels(img.data_ptr(), out.data_ptr(), *self._dims(), self.stats[1].data_ptr(),
+                                                      float(luma_min), float(gamma), float(gamma_luma_min), float(gamma_alpha),
+                                                      float(gamma_min), stream), "luma_adjusted_levels")
