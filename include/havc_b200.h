@@ -224,6 +224,10 @@ int havc_image_tweak(const uint8_t *img, uint8_t *out, int B, int H, int W, doub
 int havc_luma_adjusted_levels(const uint8_t *img, uint8_t *out, int B, int H, int W, const unsigned long long *stats,
                               double luma_min, double gamma, double gamma_luma_min, double gamma_alpha, double gamma_min,
                               void *stream);
+/* VapourSynth std.Merge(clipa, clipb, weight) on 8-bit samples (vs_simple_merge, vsfilters.py:730-739; HAVC_merge
+ * method 2, vsdeoldify/__init__.py:2648): 15-bit fixed-point weight, out = a + (((b - a)*w15 + 2^14) >> 15).
+ * Restated from the VapourSynth sources; the library is absent here, so this edge is parity-unpinned. */
+int havc_vs_merge_u8(const uint8_t *a, const uint8_t *b, uint8_t *out, long long n, double weight, void *stream);
 
 #ifdef __cplusplus
 }

@@ -165,9 +165,29 @@ def golden_filters():
     print("filters golden:", len(out), "arrays")
 
 
+def golden_zhang():
+    """ECCVGenerator / SIGGRAPHGenerator (colorization/colorizers/*.py), the real modules with synthetic weights
+    loaded strict=True, on a seeded L input."""
+    from oracle import zhang_oracle
+    for name in ("eccv16", "siggraph17"):
+        sd = zhang_oracle.make_zhang_state_dict(name, 1234)
+        m = refshim.build_zhang(name)
+        ref_sd = m.state_dict()
+        assert set(ref_sd.keys()) == set(sd.keys()), (set(ref_sd) ^ set(sd))
+        m.load_state_dict(sd, strict=True)
+        g = torch.Generator().manual_seed(99)
+        low = torch.rand(1, 1, 12, 12, generator=g)
+        l = torch.nn.functional.interpolate(low, size=(96, 96), mode="bicubic", align_corners=False).clamp(0, 1) * 100.0
+        with torch.no_grad():
+            y = m(l)
+        np.savez_compressed(os.path.join(HERE, f"zhang_{name}_96.npz"), l=l.numpy(), ab=y.numpy(), weight_seed=1234)
+        print(name, "golden: ab mean/std/min/max", float(y.mean()), float(y.std()), float(y.min()), float(y.max()))
+
+
 if __name__ == "__main__":
     golden_unets()
     golden_pixels()
     golden_filters()
+    golden_zhang()
     golden_render()
     print("golden fixtures written to", HERE)

@@ -130,3 +130,29 @@ def test_random_frames_odd_size_vs_oracle():
     torch.cuda.synchronize()
     for i, r in enumerate(hwc(out)):
         same(r, fo.adjust_hue_range(b[i], "300:360|0.8,0.1"), f"hue adjust frame {i}")
+
+
+def test_havc_merge_surface():
+    """HAVC_merge on clips (vsdeoldify/__init__.py:2536-2675): frame order, props of clipa pass through, method 2 is
+    std.Merge (restated), methods 3-7 are the vsslib merges; 0 / 1 shortcuts return the input clips themselves."""
+    from vsdeoldify_b200 import havc, vs_shim
+    rng = np.random.default_rng(11)
+    n, H, W = 5, 40, 56
+    fa = rng.integers(0, 256, (n, 3, H, W), dtype=np.uint8)
+    fb = rng.integers(0, 256, (n, 3, H, W), dtype=np.uint8)
+    fa[2] //= 5
+    props = [{"_SceneChangePrev": int(i == 0), "idx": i, "sc_luma": 0.25 * i} for i in range(n)]
+    ca, cb = vs_shim.array_clip(fa, props=props), vs_shim.array_clip(fb)
+    assert havc.HAVC_merge(ca, cb, method=0) is ca and havc.HAVC_merge(ca, cb, weight=0) is ca
+    assert havc.HAVC_merge(ca, cb, method=1) is cb and havc.HAVC_merge(ca, cb, weight=1) is cb
+    to_hwc = lambda f: np.stack([np.asarray(f[p]) for p in range(3)], -1)
+    for method in (2, 3, 5, 7):
+        out = havc.HAVC_merge(ca, cb, weight=0.6, method=method)
+        for i in (3, 0, 4, 1, 2):
+            f = out.get_frame(i)
+            assert f.props == props[i]
+            a, b = np.transpose(fa[i], (1, 2, 0)), np.transpose(fb[i], (1, 2, 0))
+            want = fo.vs_merge(a, b, 0.6) if method == 2 else fo.combine_models(a, b, method, 0.6)
+            same(to_hwc(f), want, f"HAVC_merge method {method} frame {i}")
+    with pytest.raises(vs_shim.Error):
+        havc.HAVC_merge(ca, cb, method=9).get_frame(0) if False else havc.HAVC_merge(ca, cb, method=9)

@@ -113,6 +113,7 @@ _SIGNATURES = {
                                      C.c_double, C.c_int, C.c_void_p]),
     "havc_image_tweak": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
                                    C.POINTER(HueRanges), C.c_void_p, C.c_void_p]),
+    "havc_vs_merge_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_double, C.c_void_p]),
     "havc_luma_adjusted_levels": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_double, C.c_double,
                                             C.c_double, C.c_double, C.c_double, C.c_void_p]),
 }

@@ -363,6 +363,15 @@ __global__ void luma_adjusted_levels_kernel(Img img, uint8_t *out, LevelsParams 
     }
 }
 
+// ---- VapourSynth std.Merge on 8-bit planes (vs_simple_merge, vsfilters.py:730-739): restated, parity unpinned ------
+__global__ void vs_merge_u8_kernel(const uint8_t *__restrict__ a, const uint8_t *__restrict__ b, uint8_t *__restrict__ out, long long n,
+                                   int w15) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int va = a[i], vb = b[i];
+        out[i] = (uint8_t)(va + (((vb - va) * w15 + (1 << 14)) >> 15));
+    }
+}
+
 static dim3 frame_grid(long long plane, int B, int block = 256) {
     long long g = (plane + block - 1) / block;
     const long long cap = (long long)num_sms() * 8;
@@ -538,6 +547,18 @@ extern "C" int havc_luma_adjusted_levels(const uint8_t *img, uint8_t *out, int B
     LevelsParams p{luma_min, gamma, gamma_luma_min, gamma_alpha, gamma_min};
     Img im{img, (long long)H * W};
     luma_adjusted_levels_kernel<<<frame_grid(im.plane, B), 256, 0, (cudaStream_t)stream>>>(im, out, p, stats);
+    HAVC_LAUNCHED();
+    return HAVC_OK;
+}
+
+extern "C" int havc_vs_merge_u8(const uint8_t *a, const uint8_t *b, uint8_t *out, long long n, double weight, void *stream) {
+    HAVC_CHECK_ARG(a && b && out && n > 0 && weight >= 0.0 && weight <= 1.0, "havc_vs_merge_u8: bad arguments");
+    int w15 = (int)(weight * 32768.0 + 0.5);
+    w15 = w15 < 0 ? 0 : (w15 > 32768 ? 32768 : w15);
+    long long g = (n + 255) / 256;
+    const long long cap = (long long)num_sms() * 32;
+    if (g > cap) g = cap;
+    vs_merge_u8_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(a, b, out, n, w15);
     HAVC_LAUNCHED();
     return HAVC_OK;
 }

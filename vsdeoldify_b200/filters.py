@@ -238,3 +238,38 @@ class FilterBank:
         _lib.check(self.lib.havc_luma_adjusted_levels(img.data_ptr(), out.data_ptr(), *self._dims(), self.stats[1].data_ptr(),
                                                       float(luma_min), float(gamma), float(gamma_luma_min), float(gamma_alpha),
                                                       float(gamma_min), stream), "luma_adjusted_levels")
+
+
+class MergeEngine:
+    """HAVC_merge on batches of planar RGB24 host frames: H2D -> FilterBank.combine / std.Merge -> D2H."""
+
+    def __init__(self, width: int, height: int, batch: int = 8, device: str = "cuda:0"):
+        self.dev = torch.device(device)
+        torch.cuda.set_device(self.dev)
+        self.B, self.H, self.W = batch, height, width
+        self.bank = FilterBank(batch, height, width, self.dev)
+        u8 = dict(dtype=torch.uint8, device=self.dev)
+        self.d_a, self.d_b, self.d_out = (torch.empty(batch, 3, height, width, **u8) for _ in range(3))
+        self.h_a, self.h_b, self.h_out = (torch.empty(batch, 3, height, width, dtype=torch.uint8).pin_memory() for _ in range(3))
+        self.stream = torch.cuda.Stream(device=self.dev)
+
+    def merge_batch(self, a: np.ndarray, b: np.ndarray, method: int, weight: float, cmc_p=DEF_CMC_p, lmm_p=DEF_LMM_p,
+                    alm_p=DEF_ALM_p, crt_p=DEF_CRT_p) -> np.ndarray:
+        """a, b: uint8 [n<=B, 3, H, W].  method 2 = std.Merge (HAVC_merge, vsdeoldify/__init__.py:2648), 3..7 =
+        vs_combine_models (mcomb.py:125-192)."""
+        n = a.shape[0]
+        assert a.shape == b.shape and n <= self.B and a.shape[1:] == (3, self.H, self.W)
+        self.h_a[:n].copy_(torch.from_numpy(np.ascontiguousarray(a)))
+        self.h_b[:n].copy_(torch.from_numpy(np.ascontiguousarray(b)))
+        with torch.cuda.stream(self.stream):
+            st = self.stream.cuda_stream
+            self.d_a.copy_(self.h_a, non_blocking=True)
+            self.d_b.copy_(self.h_b, non_blocking=True)
+            if method == 2:
+                _lib.check(self.bank.lib.havc_vs_merge_u8(self.d_a.data_ptr(), self.d_b.data_ptr(), self.d_out.data_ptr(),
+                                                          self.d_out.numel(), float(weight), st), "vs_merge")
+            else:
+                self.bank.combine(self.d_a, self.d_b, self.d_out, method, weight, cmc_p, lmm_p, alm_p, crt_p, stream=st)
+            self.h_out.copy_(self.d_out, non_blocking=True)
+        self.stream.synchronize()
+        return self.h_out[:n].numpy().copy()

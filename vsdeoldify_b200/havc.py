@@ -159,6 +159,71 @@ def HAVC_colorizer(
         if vs is vs_shim else _wrap_real_vs(clip, fn)
 
 
+class _MergedClip:
+    """frame_fn of HAVC_merge's output clip: pulls B consecutive frames of both clips, merges them on the GPU."""
+
+    def __init__(self, clipa, clipb, engine, batch, method, weight, cmc_p, lmm_p, alm_p, crt_p):
+        self.clipa, self.clipb, self.engine, self.B = clipa, clipb, engine, batch
+        self.args = (method, weight, cmc_p, lmm_p, alm_p, crt_p)
+        self.cache: "OrderedDict[int, object]" = OrderedDict()
+        self.lock = threading.Lock()
+
+    def __call__(self, n: int):
+        with self.lock:
+            if n in self.cache:
+                return self.cache[n]
+            n1 = min(n + self.B, self.clipa.num_frames)
+            fa = [self.clipa.get_frame(i) for i in range(n, n1)]
+            fb = [self.clipb.get_frame(i) for i in range(n, n1)]
+            stack = lambda fs: np.stack([np.stack([np.asarray(f[p]) for p in range(3)]) for f in fs])
+            out = self.engine.merge_batch(stack(fa), stack(fb), *self.args)
+            for i, f in zip(range(n, n1), fa):
+                g = f.copy()                              # props of clipa's frame survive (mcomb.py selectors return f[0].copy())
+                for p in range(3):
+                    np.copyto(np.asarray(g[p]), out[i - n, p])
+                self.cache[i] = g
+            while len(self.cache) > 4 * self.B:
+                self.cache.popitem(last=False)
+            return self.cache[n]
+
+
+def HAVC_merge(clipa=None, clipb=None, clip_luma=None, weight: float = 0.5, method: int = 2, cmc_p: Sequence = DEF_CMC_p,
+               lmm_p: Sequence = DEF_LMM_p, alm_p: Sequence = DEF_ALM_p, crt_p: Sequence = DEF_CRT_p, device_index: int = 0):
+    """Drop-in for vsdeoldify.HAVC_merge (vsdeoldify/__init__.py:2536-2675) on RGB24 clips: method 2 = std.Merge,
+    methods 3-7 = the vsslib merges of vs_combine_models.  `clip_luma` (the Spline64 squeeze + chroma-resize detour of
+    :2653-2673) and non-RGB24 formats (convert_format_RGB24 / restore_format) are not built and raise."""
+    for name, c in (("clipa", clipa), ("clipb", clipb), ("clip_luma", clip_luma)):
+        if c is not None and not hasattr(c, "get_frame"):
+            _raise("HAVC_merge: this is not a clip: " + name)                            # :2624-2631
+    if clip_luma is not None:
+        _raise("HAVC_merge: clip_luma is not handled by the B200 build yet")
+    if method == 0 or weight == 0:                                                        # :2633-2638
+        return clipa
+    if method == 1 or weight == 1:                                                        # :2640-2645
+        return clipb
+    rgb24 = getattr(vs.RGB24, "id", vs.RGB24)
+    for c in (clipa, clipb):
+        if getattr(c.format, "id", c.format) != rgb24:
+            _raise("HAVC_merge: only RGB24 clips are handled by the B200 build (convert_format_RGB24 is a 'next' row)")
+    if (clipa.width, clipa.height) != (clipb.width, clipb.height):
+        _raise("HAVC_merge: clipa and clipb must have the same size")
+    if not torch.cuda.is_available():
+        _raise("HAVC_merge: CUDA is not available")
+    if method not in (2, 3, 4, 5, 6, 7):
+        _raise("HAVC: only dd_method in (0,6) is supported")                              # mcomb.py:192
+    from .filters import FilterError, MergeEngine
+    engine = MergeEngine(clipa.width, clipa.height, batch=_BATCH, device=f"cuda:{device_index}")
+    fn = _MergedClip(clipa, clipb, engine, _BATCH, method, weight, list(cmc_p), list(lmm_p), list(alm_p), list(crt_p))
+
+    def guarded(n):
+        try:
+            return fn(n)
+        except FilterError as e:
+            _raise("HAVC_merge: " + str(e))
+    return vs_shim.VideoNode(clipa.num_frames, clipa.width, clipa.height, clipa.format, guarded, clipa.fps_num, clipa.fps_den) \
+        if vs is vs_shim else _wrap_real_vs(clipa, guarded)
+
+
 def _wrap_real_vs(clip, fn):
     """Real VapourSynth: serve frames through std.ModifyFrame; the selector ignores `f` and returns our frame."""
     return clip.std.ModifyFrame(clips=[clip], selector=lambda n, f: fn(n))
