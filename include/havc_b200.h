@@ -99,6 +99,8 @@ typedef struct {
      * tensor bounds).  Honoured for 16-bit NHWC / PixelShuffle outputs with BN % 64 == 0; otherwise the epilogue falls
      * back to per-thread vector stores.                                                                           */
     int32_t tma_store;
+    /* relu1 becomes LeakyReLU(leaky1) when leaky1 > 0 (siggraph17.py:98 `nn.LeakyReLU(negative_slope=.2)`); 0 = ReLU. */
+    float leaky1;
 } havc_conv_desc;
 
 const char *havc_last_error(void);
@@ -224,6 +226,37 @@ int havc_image_tweak(const uint8_t *img, uint8_t *out, int B, int H, int W, doub
 int havc_luma_adjusted_levels(const uint8_t *img, uint8_t *out, int B, int H, int W, const unsigned long long *stats,
                               double luma_min, double gamma, double gamma_luma_min, double gamma_alpha, double gamma_min,
                               void *stream);
+
+/* ---- Zhang et al. colorizers: pre/post passes (vsdeoldify/colorization/__init__.py:76-95, colorizers/util.py:21-55) ---- */
+
+/* One separable pass of Pillow's Image.resize on 8-bit planes (ImagingResample, libImaging/Resample.c): 22-bit
+ * fixed-point coefficients, (sum + 2^21) >> 22, clip.  horizontal=1: in [planes][Hin][Win] -> out [planes][Hin][out_size];
+ * horizontal=0: -> out [planes][out_size][Win].  bounds: int [out_size][2] = (first tap, count); coeffs: int [out_size][ksize].
+ * Pillow runs the horizontal pass first and stores a uint8 intermediate; BICUBIC feeds preprocess_img (util.py:21-30),
+ * BILINEAR is BaseFilter._scale_to_square / _unsquare (vsdeoldify/deoldify/filters.py:37-41,70-73). */
+int havc_pil_resample_u8(const uint8_t *in, uint8_t *out, long long planes, int Hin, int Win, int out_size, int horizontal,
+                         const int *bounds, const int *coeffs, int ksize, void *stream);
+/* skimage.color.rgb2lab L channel (float64, stored float32 like torch.Tensor(img_l), util.py:29-36) of planar u8 RGB
+ * [B][3][n]; L_out: float [B][n] (optional); x: 16-bit NHWC [B][n][8] whose channel 0 receives (L-50)/100
+ * (BaseColor.normalize_l, base_color.py:13-14) (optional). */
+int havc_zhang_pre(const uint8_t *rgb, int B, long long n_pixels, float *L_out, void *x, int dtype, void *stream);
+/* eccv16 tail (eccv16.py:94): softmax over n_classes logits (fp32, row stride ld) and the bias-free 1x1 conv
+ * n_classes -> 2 (w_out: float [2][n_classes]); out: float [pixels][2]. */
+int havc_eccv_head(const float *logits, int ld, int n_classes, const float *w_out, float *out, long long pixels, void *stream);
+/* siggraph17 tail (siggraph17.py:101-102,159-161): out[p] = tanh(head[p][0..1] + bias) * mul on the fused-head output
+ * ([pixels][4] fp32) of the last havc_conv_gemm. */
+int havc_zhang_tanh(const float *head, const float *bias, float *out, long long pixels, float mul, void *stream);
+/* torch bilinear resize, align_corners=False, of 2-channel interleaved float maps [B][h][w][2] -> [B][H][W][2], times mul
+ * (nn.Upsample(scale_factor=4) + unnormalize_ab, eccv16.py:84,96). */
+int havc_bilinear_ab(const float *in, float *out, int B, int h, int w, int H, int W, float mul, void *stream);
+/* postprocess_tens + uint8 conversion (util.py:38-55, colorization/__init__.py:93-95): ab [B][h][w][2] resized
+ * bilinearly to H x W, concatenated with L [B][H][W], skimage lab2rgb in float64, uint8(clip(x*255, 0, 255)) ->
+ * planar u8 RGB [B][3][H][W]. */
+int havc_zhang_post(const float *ab, int h, int w, const float *L, uint8_t *out, int B, int H, int W, void *stream);
+
+/* Scene-change gate of the per-frame selectors (vsslib/vsmodels.py:221-224, mcomb.py:210-213: `return f[0].copy()`):
+ * frames b with skip[b] != 0 are overwritten by the same frame of `src`. */
+int havc_select_frames(uint8_t *dst, const uint8_t *src, const uint8_t *skip, int B, long long frame_bytes, void *stream);
 /* VapourSynth std.Merge(clipa, clipb, weight) on 8-bit samples (vs_simple_merge, vsfilters.py:730-739; HAVC_merge
  * method 2, vsdeoldify/__init__.py:2648): 15-bit fixed-point weight, out = a + (((b - a)*w15 + 2^14) >> 15).
  * Restated from the VapourSynth sources; the library is absent here, so this edge is parity-unpinned. */

@@ -29,21 +29,39 @@ def net_output_square(sd, rgb_sq: np.ndarray) -> np.ndarray:
 
 
 def havc_colorizer_frame(sd, frame: np.ndarray, render_factor: int = 24, kernel: str = "spline64",
-                         return_stages: bool = False, skip: bool = False, sd_other=None, video_weight: float = 0.5):
+                         return_stages: bool = False, skip: bool = False, sd_other=None, video_weight: float = 0.5,
+                         zhang=None, method: int = 0, merge_weight: float = 0.4, hue_adjust: str = "none", cmc_p=None,
+                         lmm_p=None, alm_p=None, crt_p=None, invert: bool = False):
     """frame: uint8 [H,W,3].  Returns uint8 [H,W,3] (and the intermediate stages on request).
     skip: the scene-change gate returned the squeezed frame unchanged (vsslib/vsmodels.py:221-224).
-    sd_other: 'stable'/'artistic' generator blended with the video one at S x S (visualize.py:118-137)."""
+    sd_other: 'stable'/'artistic' generator blended with the video one at S x S (visualize.py:118-137).
+    zhang = (name, state_dict): second colour model (vs_sc_ddcolor models 2/3, vsmodels.py:339-344) with its hue
+    adjustment (vsmodels.py:361-362), merged by vs_sc_combine_models(method, merge_weight, ...) (mcomb.py:125-192);
+    method 1 = second model only."""
+    from . import filters_oracle as fo
+    from . import zhang_oracle
     H, W = frame.shape[:2]
     S = min(render_factor * 16, W)
     small = px.resize_plane_u8(frame, S, S, kernel)                   # clip.resize.Spline64(S, S)
     if skip:
         model_img = colored = small
     else:
-        model_img = model_process_square(sd, small)                   # _scale_to_square is the identity here
-        colored = px.chroma_post_process(model_img, small)            # _post_process at S x S
-        if sd_other is not None:
-            other = px.chroma_post_process(model_process_square(sd_other, small), small)
-            colored = px.pil_blend(other, colored, video_weight)
+        model_img = colored = None
+        if method != 1:
+            model_img = model_process_square(sd, small)               # _scale_to_square is the identity here
+            colored = px.chroma_post_process(model_img, small)        # _post_process at S x S
+            if sd_other is not None:
+                other = px.chroma_post_process(model_process_square(sd_other, small), small)
+                colored = px.pil_blend(other, colored, video_weight)
+        if zhang is not None and method != 0:
+            clipb = zhang_oracle.colorize_frame(zhang[1], zhang[0], small)
+            clipb = fo.adjust_hue_range(clipb, hue_adjust)
+            if method == 1:
+                colored = clipb
+            else:
+                a, b = (clipb, colored) if invert else (colored, clipb)
+                kw = {k: v for k, v in dict(cmc_p=cmc_p, lmm_p=lmm_p, alm_p=alm_p, crt_p=crt_p).items() if v is not None}
+                colored = fo.combine_models(a, b, method, merge_weight, **kw)
     up = px.resize_plane_u8(colored, W, H, kernel)                    # clip_lowres.resize.Spline64(W, H)
     out = px.chroma_post_process(up, frame)                           # vs_recover_clip_luma
     if return_stages:

@@ -186,7 +186,7 @@ def make_zhang_state_dict(name: str, seed: int = 1234, calibrate: bool = True) -
         else:
             siggraph17_forward(sd, l, calibrate=True, taps=taps)
             pre = F.conv2d(taps["model10"], sd["model_out.0.weight"], sd["model_out.0.bias"])
-            k = 0.2 / float(pre.std().clamp_min(1e-6))
+            k = 0.12 / float(pre.std().clamp_min(1e-6))
             sd["model_out.0.weight"] = sd["model_out.0.weight"] * k
             sd["model_out.0.bias"] = (sd["model_out.0.bias"] - pre.mean(dim=(0, 2, 3))) * k
     return sd

@@ -199,3 +199,16 @@ def test_gemm_shared_a_batched_b():
     op.launch()
     torch.cuda.synchronize()
     _check(out.view(B, Cc, N), ref, dtype, "shared-A batched-B gemm")
+
+
+def test_conv_k24_single_kstep_many_tiles():
+    """Zhang model1.0 shape: K = 24 (one partial 64-chunk), BN = 64, ~7 tiles per CTA."""
+    _run_conv(2, 256, 256, [24], 64, 1, torch.float16, bias=True, relu1=True)
+
+
+def test_conv3x3_c64_large_map():
+    _run_conv(2, 256, 256, [64], 64, 3, torch.float16, bias=True, relu1=True, affine=True)
+
+
+def test_conv3x3_c64_medium_map():
+    _run_conv(2, 128, 128, [64], 64, 3, torch.float16, bias=True, relu1=True, affine=True)

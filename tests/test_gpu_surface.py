@@ -95,3 +95,43 @@ def test_stable_and_artistic_blend(model, name):
         img = np.stack([np.asarray(f[p]) for p in range(3)], -1)
         m = metrics.frame_parity(img, ref)
         assert m["mean_de00"] <= 0.5, (model, i, m)
+
+
+def _register_zhang(havc):
+    from oracle import zhang_oracle
+    for name, file in havc._ZHANG_FILES.items():
+        if file not in havc._REGISTERED:
+            havc.register_state_dict(file, zhang_oracle.make_zhang_state_dict(name, 1234))
+
+
+@pytest.mark.parametrize("method", [1, 2, 3, 4, 5, 6, 7])
+def test_colorizer_two_models_merge_methods(method):
+    """HAVC_colorizer with the Zhang siggraph17 model as second colour model (ddcolor_p model 2) and every merge
+    method of vs_sc_combine_models, default ddtweak_p hue adjustment included, against the CPU oracle of the whole
+    path (DeOldify + Zhang + hue adjust + merge + Spline64 back + luma transplant)."""
+    from oracle import metrics, pipeline_oracle, zhang_oracle
+    havc = _register()
+    _register_zhang(havc)
+    H, W, rf, n = 96, 176, 10, 2
+    clip, fr, props = _clip(n, H, W, seed=130)
+    out = havc.HAVC_colorizer(clip, method=method, mweight=0.45, deoldify_p=[0, rf, 1.0, 0.0], ddcolor_p=[2, rf, 1.0, 0.0, True])
+    sd = havc._REGISTERED["ColorizeVideo_gen"]
+    sdz = havc._REGISTERED[havc._ZHANG_FILES["siggraph17"]]
+    for i in (1, 0):
+        f = out.get_frame(i)
+        assert f.props == props[i]
+        ref = pipeline_oracle.havc_colorizer_frame(sd, np.transpose(fr[i], (1, 2, 0)), rf, zhang=("siggraph17", sdz), method=method,
+                                                   merge_weight=0.45, hue_adjust="300:360|0.8,0.1")
+        img = np.stack([np.asarray(f[p]) for p in range(3)], -1)
+        m = metrics.frame_parity(img, ref)
+        assert m["mean_de00"] <= 0.5, (method, i, m)
+
+
+def test_colorizer_second_model_errors():
+    from vsdeoldify_b200 import vs_shim
+    havc = _register()
+    clip, _, _ = _clip(2, 64, 96)
+    with pytest.raises(vs_shim.Error):       # DDColor itself is out of scope
+        havc.HAVC_colorizer(clip, method=2, deoldify_p=[0, 4, 1.0, 0.0], ddcolor_p=[1, 10, 1.0, 0.0, True])
+    with pytest.raises(vs_shim.Error):
+        havc.HAVC_colorizer(clip, method=9, deoldify_p=[0, 4, 1.0, 0.0], ddcolor_p=[2, 10, 1.0, 0.0, True])

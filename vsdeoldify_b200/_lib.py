@@ -65,6 +65,7 @@ class ConvDesc(C.Structure):
         ("head_w", C.c_void_p), ("head_out", C.c_void_p),
         ("head_stride_w", C.c_int64), ("head_stride_h", C.c_int64), ("head_stride_b", C.c_int64),
         ("tma_store", C.c_int32),
+        ("leaky1", C.c_float),
     ]
 
 
@@ -113,6 +114,14 @@ _SIGNATURES = {
                                      C.c_double, C.c_int, C.c_void_p]),
     "havc_image_tweak": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
                                    C.POINTER(HueRanges), C.c_void_p, C.c_void_p]),
+    "havc_pil_resample_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                       C.c_void_p, C.c_int, C.c_void_p]),
+    "havc_zhang_pre": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "havc_eccv_head": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
+    "havc_zhang_tanh": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_float, C.c_void_p]),
+    "havc_bilinear_ab": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
+    "havc_zhang_post": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "havc_select_frames": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p]),
     "havc_vs_merge_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_double, C.c_void_p]),
     "havc_luma_adjusted_levels": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_double, C.c_double,
                                             C.c_double, C.c_double, C.c_double, C.c_void_p]),

@@ -53,6 +53,7 @@ struct ConvParams {
     int N_total;
     const float *bias, *scale, *shift;
     int relu1, relu2;
+    float slope1;                 // first activation as max(t, t*slope1): 0 = ReLU, 1 = none, 0.2 = LeakyReLU(0.2)
     const void *residual;
     long long rsw, rsh, rsb;
     void *out;
@@ -406,8 +407,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                     sbw[kMaxBN + i] = (in && p.scale) ? __ldg(p.scale + n) : 1.f;
                     sbw[2 * kMaxBN + i] = (in && p.shift) ? __ldg(p.shift + n) : 0.f;
                 }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
                 last_nt = nt;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            } else if (p.tma_store) {
+                // no parameter reload: the barrier is still what orders thread 0's wait on the previous tile's bulk
+                // store (above) before any warp overwrites the staging buffer
+                asm volatile("bar.sync 1, 256;" ::: "memory");
             }
             const float *sb = sparams + pbuf * (3 * kMaxBN);
 
@@ -428,7 +433,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             const int dt = p.dtype, od = p.out_dtype, gn = p.group_n;
             const bool shuffle = p.shuffle != 0, has_scale = p.scale != nullptr, head = p.head_w != nullptr;
             const bool tma_store = p.tma_store != 0;
-            const float lo1 = p.relu1 ? 0.f : -INFINITY, lo2 = p.relu2 ? 0.f : -INFINITY;
+            const float slope1 = p.slope1, lo2 = p.relu2 ? 0.f : -INFINITY;
             const long long pix_main = ob * p.osb + (long long)(oh * p.up + p.oy) * p.osh + (long long)(ow * p.up + p.ox) * p.osw;
             const long long pix_shuf = ob * p.osb + (long long)(oh * 2) * p.osh + (long long)(ow * 2) * p.osw;
             const long long pix_out2 = ob * p.o2sb + (long long)(oh * p.up + p.oy) * p.o2sh + (long long)(ow * p.up + p.ox) * p.o2sw;
@@ -470,10 +475,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
                             const float4 bv = b4[g];
-                            y[4 * g + 0] = fmaxf(__uint_as_float(vc[16 * hh + 4 * g + 0]) + bv.x, lo1);
-                            y[4 * g + 1] = fmaxf(__uint_as_float(vc[16 * hh + 4 * g + 1]) + bv.y, lo1);
-                            y[4 * g + 2] = fmaxf(__uint_as_float(vc[16 * hh + 4 * g + 2]) + bv.z, lo1);
-                            y[4 * g + 3] = fmaxf(__uint_as_float(vc[16 * hh + 4 * g + 3]) + bv.w, lo1);
+                            const float t0 = __uint_as_float(vc[16 * hh + 4 * g + 0]) + bv.x, t1 = __uint_as_float(vc[16 * hh + 4 * g + 1]) + bv.y;
+                            const float t2 = __uint_as_float(vc[16 * hh + 4 * g + 2]) + bv.z, t3 = __uint_as_float(vc[16 * hh + 4 * g + 3]) + bv.w;
+                            y[4 * g + 0] = fmaxf(t0, t0 * slope1);
+                            y[4 * g + 1] = fmaxf(t1, t1 * slope1);
+                            y[4 * g + 2] = fmaxf(t2, t2 * slope1);
+                            y[4 * g + 3] = fmaxf(t3, t3 * slope1);
                         }
                     }
                     if (has_scale) {
@@ -796,6 +803,8 @@ extern "C" int havc_conv_gemm(const havc_conv_desc *d, void *stream) {
     p.idesc1 = p.n_part1 > 0 ? idesc(p.n_part1) : 0u;
     p.bias = d->bias; p.scale = d->scale; p.shift = d->shift;
     p.relu1 = d->relu1; p.relu2 = d->relu2;
+    p.slope1 = d->relu1 ? d->leaky1 : 1.0f;
+    HAVC_CHECK_ARG(d->leaky1 >= 0.f && d->leaky1 < 1.f, "havc_conv_gemm: leaky1 must be in [0,1)");
     p.residual = d->residual; p.rsw = d->res_stride_w; p.rsh = d->res_stride_h; p.rsb = d->res_stride_b;
     p.out = d->out; p.out_dtype = d->out_dtype;
     p.osw = d->out_stride_w; p.osh = d->out_stride_h; p.osb = d->out_stride_b;

@@ -372,6 +372,16 @@ __global__ void vs_merge_u8_kernel(const uint8_t *__restrict__ a, const uint8_t 
     }
 }
 
+// ---- scene-change gate (vsslib/vsmodels.py:221-224, mcomb.py:210-213): frames with skip[b] != 0 take `src` unchanged ------
+__global__ void select_frames_kernel(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, const uint8_t *__restrict__ skip,
+                                     long long frame_bytes) {
+    const int b = blockIdx.y;
+    if (!skip[b]) return;
+    uint8_t *d = dst + (long long)b * frame_bytes;
+    const uint8_t *s = src + (long long)b * frame_bytes;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < frame_bytes; i += (long long)gridDim.x * blockDim.x) d[i] = s[i];
+}
+
 static dim3 frame_grid(long long plane, int B, int block = 256) {
     long long g = (plane + block - 1) / block;
     const long long cap = (long long)num_sms() * 8;
@@ -559,6 +569,13 @@ extern "C" int havc_vs_merge_u8(const uint8_t *a, const uint8_t *b, uint8_t *out
     const long long cap = (long long)num_sms() * 32;
     if (g > cap) g = cap;
     vs_merge_u8_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(a, b, out, n, w15);
+    HAVC_LAUNCHED();
+    return HAVC_OK;
+}
+
+extern "C" int havc_select_frames(uint8_t *dst, const uint8_t *src, const uint8_t *skip, int B, long long frame_bytes, void *stream) {
+    HAVC_CHECK_ARG(dst && src && skip && B > 0 && frame_bytes > 0, "havc_select_frames: bad arguments");
+    select_frames_kernel<<<frame_grid(frame_bytes, B), 256, 0, (cudaStream_t)stream>>>(dst, src, skip, frame_bytes);
     HAVC_LAUNCHED();
     return HAVC_OK;
 }

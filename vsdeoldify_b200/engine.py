@@ -37,7 +37,12 @@ class DeoldifyEngine:
                  dtype: torch.dtype = torch.float16, device: str = "cuda:0", resize_kernel: str = "spline64",
                  use_graph: bool = True, keep_taps: bool = False, debug_net_out: bool = False,
                  frame_size: Optional[int] = None, sd_other: Optional[Dict[str, torch.Tensor]] = None,
-                 video_weight: float = 0.5):
+                 video_weight: float = 0.5, zhang: Optional[tuple] = None, merge: Optional[dict] = None,
+                 hue_adjust: str = "none", run_deoldify: bool = True):
+        """zhang = (name, state_dict): the second colour model of HAVC_colorizer (vs_sc_ddcolor models 2 / 3,
+        vsslib/vsmodels.py:339-344), colourising the same S x S frame; hue_adjust: its vs_sc_adjust_clip_hue string
+        (vsmodels.py:361-362); merge = dict(method, weight, cmc_p, lmm_p, alm_p, crt_p, invert) for
+        vs_sc_combine_models (mcomb.py:125-192).  run_deoldify=False is method 1 (second model only)."""
         self.lib = _lib.lib()
         self.dev = torch.device(device)
         torch.cuda.set_device(self.dev)
@@ -49,8 +54,22 @@ class DeoldifyEngine:
             raise ValueError("frame_size != render_factor*16 (ddcolor_rf > deoldify_rf) is not supported yet")
         S, B, W, H = self.S, batch, width, height
         self.dtype, self.hd = dtype, ops.havc_dtype(dtype)
-        self.prog = UnetProgram(sd, B, S, dtype, device=self.dev, keep_taps=keep_taps)
-        self.prog2 = UnetProgram(sd_other, B, S, dtype, device=self.dev, x=self.prog.x) if sd_other is not None else None
+        self.run_deoldify = run_deoldify
+        self.prog = UnetProgram(sd, B, S, dtype, device=self.dev, keep_taps=keep_taps) if run_deoldify else None
+        self.prog2 = UnetProgram(sd_other, B, S, dtype, device=self.dev, x=self.prog.x) \
+            if (sd_other is not None and run_deoldify) else None
+        self.zhang = None
+        self.merge, self.hue_adjust = merge, hue_adjust
+        if zhang is not None:
+            from .filters import FilterBank
+            from .zhang import ZhangColorizer
+            self.zhang = ZhangColorizer(zhang[1], zhang[0], B, S, dtype, device=self.dev)
+            self.bank = FilterBank(B, S, S, self.dev)
+            self.colored_b = torch.empty(B, 3, S, S, dtype=torch.uint8, device=self.dev)
+            self.colored_b2 = torch.empty(B, 3, S, S, dtype=torch.uint8, device=self.dev)
+            self.merged = torch.empty(B, 3, S, S, dtype=torch.uint8, device=self.dev)
+        if not run_deoldify and zhang is None:
+            raise ValueError("nothing to run: method 1 needs the second colour model")
         self.video_weight = float(video_weight)
         self.t_down_h = _Tables(W, S, resize_kernel, self.dev)
         self.t_down_v = _Tables(H, S, resize_kernel, self.dev)
@@ -69,6 +88,7 @@ class DeoldifyEngine:
         self.colored2 = torch.empty(B, 3, S, S, **u8) if sd_other is not None else None
         self.tmp_up = torch.empty(B, 3, H, S, **f32)
         self.net_out = torch.empty(B, 3, S, S, **f32) if debug_net_out else None
+        self.x_in = self.prog.x if self.prog is not None else torch.zeros(B, S, S, 8, dtype=dtype, device=self.dev)
         self.skip = torch.zeros(B, **u8)                  # per-frame scene-change gate (1 = leave uncoloured)
         self.h_skip = torch.zeros(B, dtype=torch.uint8).pin_memory()
         self.compute = torch.cuda.Stream(device=self.dev)
@@ -86,22 +106,40 @@ class DeoldifyEngine:
         td, tv, uh, uv = self.t_down_h, self.t_down_v, self.t_up_h, self.t_up_v
         chk(lib.havc_resample_h(self.d_in[slot].data_ptr(), self.tmp_down.data_ptr(), B * 3 * H, W, S,
                                 td.start.data_ptr(), td.wt.data_ptr(), td.taps, stream), "pre.h")
-        chk(lib.havc_pre_vertical(self.tmp_down.data_ptr(), self.rgb_small.data_ptr(), self.prog.x.data_ptr(), B, H, S,
+        chk(lib.havc_pre_vertical(self.tmp_down.data_ptr(), self.rgb_small.data_ptr(), self.x_in.data_ptr(), B, H, S,
                                   tv.start.data_ptr(), tv.w.data_ptr(), tv.taps, self.hd, stream), "pre.v")
-        self.prog.run(stream)
-        chk(lib.havc_head(self.prog.logits.data_ptr(), 0, None,
-                          self.prog.b11.data_ptr(), self.rgb_small.data_ptr(), self.colored.data_ptr(),
-                          self.net_out.data_ptr() if self.net_out is not None else None, self.skip.data_ptr(), B, S,
-                          self.hd, 1, stream),
-            "head")
+        result = self.colored
+        if self.run_deoldify:
+            self.prog.run(stream)
+            chk(lib.havc_head(self.prog.logits.data_ptr(), 0, None,
+                              self.prog.b11.data_ptr(), self.rgb_small.data_ptr(), self.colored.data_ptr(),
+                              self.net_out.data_ptr() if self.net_out is not None else None, self.skip.data_ptr(), B, S,
+                              self.hd, 1, stream),
+                "head")
         if self.prog2 is not None:
             self.prog2.run(stream)
             chk(lib.havc_head(self.prog2.logits.data_ptr(), 0, None, self.prog2.b11.data_ptr(), self.rgb_small.data_ptr(),
                               self.colored2.data_ptr(), None, self.skip.data_ptr(), B, S, self.hd, 1, stream), "head2")
             chk(lib.havc_blend_u8(self.colored2.data_ptr(), self.colored.data_ptr(), self.colored.data_ptr(),
                                   B * 3 * S * S, self.video_weight, stream), "blend")
+        if self.zhang is not None:
+            # second colour model on the same S x S frame, its hue adjustment, then the model merge
+            self.zhang.run(self.rgb_small, self.colored_b, stream)
+            clipb = self.colored_b
+            if self.bank.adjust_hue_range(clipb, self.colored_b2, self.hue_adjust, stream):
+                clipb = self.colored_b2
+            self.bank.select_frames(clipb, self.rgb_small, self.skip, stream)        # scene-change gate of the 2nd model
+            if not self.run_deoldify:
+                result = clipb
+            else:
+                m = self.merge
+                a, b = (clipb, self.colored) if m.get("invert") else (self.colored, clipb)
+                self.bank.combine(a, b, self.merged, m["method"], m["weight"], m["cmc_p"], m["lmm_p"], m["alm_p"], m["crt_p"],
+                                  stream=stream)
+                self.bank.select_frames(self.merged, a, self.skip, stream)           # merge selectors return f[0].copy()
+                result = self.merged
         # back to W x H: vertical pass on the S-wide image first, then the wide horizontal pass from shared memory
-        chk(lib.havc_resample_v(self.colored.data_ptr(), self.tmp_up.data_ptr(), B * 3, S, H, S,
+        chk(lib.havc_resample_v(result.data_ptr(), self.tmp_up.data_ptr(), B * 3, S, H, S,
                                 uv.start.data_ptr(), uv.w.data_ptr(), uv.taps, stream), "post.v")
         chk(lib.havc_post_horizontal(self.tmp_up.data_ptr(), self.d_in[slot].data_ptr(), self.d_out[slot].data_ptr(), B, S,
                                      H, W, uh.start.data_ptr(), uh.wt.data_ptr(), uh.taps, 1, stream), "post.h")

@@ -139,6 +139,11 @@ class FilterBank:
     def frame_stats(self, img, stats, stream=0, bright: float = 1.0):
         _lib.check(self.lib.havc_frame_stats(img.data_ptr(), *self._dims(), bright, stats.data_ptr(), stream), "frame_stats")
 
+    def select_frames(self, dst, src, skip, stream=0):
+        """Scene-change gate: frames with skip[b] != 0 become the corresponding frame of `src`."""
+        _lib.check(self.lib.havc_select_frames(dst.data_ptr(), src.data_ptr(), skip.data_ptr(), self.B, 3 * self.H * self.W, stream),
+                   "select_frames")
+
     def blend(self, a, b, out, w: float, stream=0):
         """image_weighted_merge (imfilters.py:113-124): Image.blend with the 0 / 1 shortcuts."""
         if w == 0.0 or w == 1.0:

@@ -35,6 +35,9 @@ package_dir = os.path.dirname(os.path.realpath(__file__))
 model_dir = os.path.join(package_dir, "models")
 
 _WEIGHT_FILES = {0: "ColorizeVideo_gen", 1: "ColorizeStable_gen", 2: "ColorizeArtistic_gen"}
+# torch.hub file names of the Zhang checkpoints (eccv16.py:105-107, siggraph17.py:168-170), looked up under
+# <torch_dir>/checkpoints like model_zoo.load_url does after torch.hub.set_dir(torch_dir) (vsdeoldify/__init__.py:2489-2490)
+_ZHANG_FILES = {"siggraph17": "siggraph17-df00044c", "eccv16": "colorization_release_v2-9b330a0b"}
 _REGISTERED: Dict[str, Dict[str, torch.Tensor]] = {}
 _BATCH = int(os.environ.get("HAVC_B200_BATCH", "8"))
 _DTYPE = {"fp16": torch.float16, "bf16": torch.bfloat16}[os.environ.get("HAVC_B200_DTYPE", "fp16")]
@@ -133,11 +136,21 @@ def HAVC_colorizer(
         _raise("HAVC_colorizer: wrong device_index, choices are: GPU0...GPU7, CPU=99")    # :2480
     if ddcolor_rf != 0 and ddcolor_rf not in range(10, 65):
         _raise("HAVC_colorizer: ddcolor render_factor must be between: 10-64")            # :2483
-    if method != 0:
-        _raise("HAVC_colorizer: only method=0 (DeOldify) is built so far; the Zhang/DDColor side and the vsslib merges "
-               "are the next rows of the hot-path table")
-    if deoldify_sat != 1.0 or deoldify_hue != 0.0:
-        _raise("HAVC_colorizer: vs_tweak (sat/hue != identity) is not built yet")
+    ddcolor_sat = ddcolor_p[2] if len(ddcolor_p) > 2 else 1.0
+    ddcolor_hue = ddcolor_p[3] if len(ddcolor_p) > 3 else 0.0
+    if method not in (0, 1, 2, 3, 4, 5, 6, 7):
+        _raise("HAVC: only dd_method in (0,6) is supported")                              # mcomb.py:192
+    if method != 0 and ddcolor_model not in (2, 3):
+        _raise("HAVC_colorizer: DDColor (ddcolor_p model 0/1, the external vsddcolor package) is out of scope of the B200 "
+               "build; use model 2 (Zhang siggraph17) or 3 (Zhang eccv16) as the second colour model")
+    if deoldify_sat != 1.0 or deoldify_hue != 0.0 or (method != 0 and (ddcolor_sat != 1.0 or ddcolor_hue != 0.0)):
+        _raise("HAVC_colorizer: vs_tweak (sat/hue != identity; a zimg YUV420 round trip) is not built yet")
+    ddtweak = list(ddtweak) if isinstance(ddtweak, (list, tuple)) else [bool(ddtweak), False, False]
+    if method != 0 and any(ddtweak[:3]):
+        _raise("HAVC_colorizer: ddtweak (pre-tweak / denoise / retinex of the second model's input) is not built yet")
+    hue_adjust = "none"
+    if method != 0:                                                                       # vsmodels.py:312-336
+        hue_adjust = (ddtweak_p[1] if len(ddtweak_p) == 2 else (ddtweak_p[8] if len(ddtweak_p) > 8 else "none")).lower()
     if ddcolor_rf == 0:
         ddcolor_rf = min(max(math.trunc(0.4 * clip.width / 16), 16), 32)                  # :2492
     scenechange = not (sc_threshold == 0 and sc_min_freq == 0)                            # :2494
@@ -146,13 +159,22 @@ def HAVC_colorizer(
     from .engine import DeoldifyEngine
     dev = f"cuda:{device_index}"
     mdir = torch_dir or model_dir
-    sd_video = load_state_dict(_WEIGHT_FILES[0], mdir)                   # the video generator always runs (visualize.py:120)
-    sd_other = load_state_dict(_WEIGHT_FILES[deoldify_model], mdir) if deoldify_model in (1, 2) else None
+    run_deoldify = method != 1                                            # vs_sc_deoldify returns None for method 1 (vsmodels.py:198)
+    sd_video = load_state_dict(_WEIGHT_FILES[0], mdir) if run_deoldify else None   # the video generator always runs (visualize.py:120)
+    sd_other = load_state_dict(_WEIGHT_FILES[deoldify_model], mdir) if (run_deoldify and deoldify_model in (1, 2)) else None
     weight = {1: DEF_STABLE_WEIGHT, 2: DEF_ARTISTIC_WEIGHT}.get(deoldify_model, 0.0)
+    zhang = merge = None
+    if method != 0:
+        zname = "siggraph17" if ddcolor_model == 2 else "eccv16"                           # vsmodels.py:339-344
+        zhang = (zname, load_state_dict(_ZHANG_FILES[zname], os.path.join(mdir, "checkpoints")))
+        merge = dict(method=method, weight=merge_weight, cmc_p=list(cmc_p), lmm_p=list(lmm_p), alm_p=list(alm_p),
+                     crt_p=list(crt_p), invert=bool(cmb_sw))
+    from .filters import FilterError
     try:
         engine = DeoldifyEngine(sd_video, clip.width, clip.height, render_factor=deoldify_rf, frame_size=frame_size,
-                                batch=_BATCH, dtype=_DTYPE, device=dev, sd_other=sd_other, video_weight=weight)
-    except ValueError as e:
+                                batch=_BATCH, dtype=_DTYPE, device=dev, sd_other=sd_other, video_weight=weight, zhang=zhang,
+                                merge=merge, hue_adjust=hue_adjust, run_deoldify=run_deoldify)
+    except (ValueError, FilterError) as e:
         _raise("HAVC_colorizer: " + str(e))
     fn = _ColorizedClip(clip, engine, scenechange, _BATCH)
     return vs_shim.VideoNode(clip.num_frames, clip.width, clip.height, clip.format, fn, clip.fps_num, clip.fps_den) \

@@ -199,7 +199,8 @@ def make_conv(src0: torch.Tensor, weight: torch.Tensor, out: torch.Tensor, taps,
               up=1, oy=0, ox=0, shuffle=False, group_n=0, c_store: Optional[int] = None,
               src1_single_tap: bool = False, src1_wi: int = 0, split_n: int = 0, out2: Optional[torch.Tensor] = None,
               c_store2: int = 0, residual2: Optional[torch.Tensor] = None, head_w: Optional[torch.Tensor] = None,
-              head_out: Optional[torch.Tensor] = None, tma_store: Optional[bool] = None, name: str = "") -> ConvOp:
+              head_out: Optional[torch.Tensor] = None, tma_store: Optional[bool] = None, leaky1: float = 0.0,
+              name: str = "") -> ConvOp:
     """src0/src1: NHWC (or [P,B,H,W,C]) 16-bit device tensors; weight: packed [rows,taps,cin] or
     [batches,rows,taps,cin]; out: NHWC tensor written at pixel (h*up+oy, w*up+ox)."""
     d = ConvDesc()
@@ -241,6 +242,7 @@ def make_conv(src0: torch.Tensor, weight: torch.Tensor, out: torch.Tensor, taps,
             setattr(d, nm, v.data_ptr())
             keep.append(v)
     d.relu1, d.relu2 = int(relu1), int(relu2)
+    d.leaky1 = float(leaky1)
     if residual is not None:
         assert residual.dtype == src0.dtype and residual.dim() == 4
         d.residual = residual.data_ptr()

@@ -85,3 +85,52 @@ def build_tables(src: int, dst: int, kernel: str = "spline64") -> Tuple[np.ndarr
         seg = m[o, start[o]:start[o] + T]
         w[o, :len(seg)] = seg
     return start, w
+
+
+# ---- Pillow Image.resize tables (ImagingResample, libImaging/Resample.c: precompute_coeffs + normalize_coeffs_8bpc) ----
+# BILINEAR: BaseFilter._scale_to_square / _unsquare (vsdeoldify/deoldify/filters.py:37-41,70-73); BICUBIC (a = -0.5):
+# colorizers/util.py:21-22.  The support is widened by the shrink ratio, weights are normalised in float64 and then
+# rounded to 22-bit fixed point; the GPU pass (havc_pil_resample_u8) accumulates them in integers like Pillow does.
+PIL_PRECISION_BITS = 32 - 8 - 2
+
+
+def _pil_bilinear(x: float) -> float:
+    x = abs(x)
+    return 1.0 - x if x < 1.0 else 0.0
+
+
+def _pil_bicubic(x: float, a: float = -0.5) -> float:
+    x = abs(x)
+    if x < 1.0:
+        return ((a + 2.0) * x - (a + 3.0)) * x * x + 1
+    if x < 2.0:
+        return (((x - 5) * x + 8) * x - 4) * a
+    return 0.0
+
+
+PIL_FILTERS = {"bilinear": (_pil_bilinear, 1.0), "bicubic": (_pil_bicubic, 2.0)}
+
+
+def pil_tables(in_size: int, out_size: int, filt: str = "bilinear") -> Tuple[np.ndarray, np.ndarray]:
+    """(bounds int32 [out, 2] = (first tap, tap count), coeffs int32 [out, ksize]) for one axis."""
+    f, support = PIL_FILTERS[filt]
+    scale = in_size / out_size
+    filterscale = max(scale, 1.0)
+    support = support * filterscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    inv = 1.0 / filterscale
+    bounds = np.zeros((out_size, 2), np.int32)
+    coeffs = np.zeros((out_size, ksize), np.int32)
+    for o in range(out_size):
+        center = (o + 0.5) * scale
+        lo = max(int(center - support + 0.5), 0)
+        hi = min(int(center + support + 0.5), in_size)
+        n = hi - lo
+        w = np.array([f((j + lo - center + 0.5) * inv) for j in range(n)], np.float64)
+        tot = w.sum()
+        if tot != 0.0:
+            w = w / tot
+        fixed = w * (1 << PIL_PRECISION_BITS)
+        coeffs[o, :n] = np.where(fixed < 0, np.trunc(fixed - 0.5), np.trunc(fixed + 0.5)).astype(np.int32)
+        bounds[o] = (lo, n)
+    return bounds, coeffs

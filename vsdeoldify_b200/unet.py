@@ -72,14 +72,12 @@ class Op:
     kind: str = "aux"
 
 
-class UnetProgram:
-    """Compiled launch list for one (state-dict, batch, S, dtype)."""
+class LaunchProgram:
+    """Ordered launch list over libhavc_b200 for one (state-dict, batch, size, dtype): buffers, folded parameters and
+    the op emitters shared by the DeOldify U-Nets (below) and the Zhang colorizers (zhang.py)."""
 
     def __init__(self, sd: SD, batch: int, size: int, dtype: torch.dtype = torch.float16, device="cuda",
-                 keep_taps: bool = False, x: Optional[torch.Tensor] = None):
-        if size % 32 != 0:
-            raise ValueError(f"render size {size} must be a multiple of 32 (even render_factor); the nearest-"
-                             "neighbour up-path resize of unet.py:201-203 is not implemented")
+                 keep_taps: bool = False):
         self.sd, self.B, self.S, self.dtype, self.dev = sd, batch, size, dtype, torch.device(device)
         self.hd = ops.havc_dtype(dtype)
         self.lib = _lib.lib()
@@ -87,9 +85,7 @@ class UnetProgram:
         self.keep: list = []
         self.taps: Dict[str, torch.Tensor] = {}
         self.keep_taps = keep_taps
-        self.bottleneck = "layers.0.4.0.conv3.weight" in sd
-        self._x_shared = x
-        self._build()
+        self.head_flops = 0.0
 
     # ---- buffers / params ---------------------------------------------------------------------
     def buf(self, *shape, dtype=None, zero=False) -> torch.Tensor:
@@ -110,8 +106,11 @@ class UnetProgram:
     # ---- op emitters --------------------------------------------------------------------------
     def conv(self, name: str, src0, w: torch.Tensor, *, ks=1, src1=None, cin_splits=None, stride=1, bias=None,
              relu1=False, scale=None, shift=None, residual=None, relu2=False, shuffle=False, out=None,
-             out_c: Optional[int] = None) -> torch.Tensor:
-        """w: folded fp32 [Cout, Cin, ks, ks].  Returns the NHWC output tensor."""
+             out_c: Optional[int] = None, dilation: int = 1, leaky1: float = 0.0, out_dtype=None, taps=None,
+             phase=None, flops: Optional[float] = None, head_w=None, head_out=None) -> torch.Tensor:
+        """w: folded fp32 [Cout, Cin, ks, ks].  Returns the NHWC output tensor.
+        taps: explicit (dh, dw, phase, weight tap) list (transposed convolutions); phase = (up, oy, ox): the output
+        pixel of (h, w) is (h*up+oy, w*up+ox) of `out`."""
         Cout, Cin = w.shape[0], w.shape[1]
         storage = [src0.shape[-1]] + ([src1.shape[-1]] if src1 is not None else [])
         wp, meta = ops.pack_conv_weight(w, cin_splits, dtype=self.dtype, shuffle=shuffle, cin_storage=storage)
@@ -121,19 +120,23 @@ class UnetProgram:
         pc = lambda v, fill: None if v is None else self.dev_f32(ops.pack_cols(v, n_total, fill, meta if shuffle else None))
         if stride == 1:
             B, H, W = src0.shape[0], src0.shape[1], src0.shape[2]
-            taps = ops.taps_for(ks)
+            if taps is None:
+                taps = ops.taps_for(ks, dilation)
         else:  # src0 is phase-split [P,B,H/2,W/2,C]
             B, H, W = src0.shape[1], src0.shape[2], src0.shape[3]
             taps = ops.taps_stride2(ks) if ks > 1 else [(0, 0, 0, 0)]
         c_real = meta["cg"] if shuffle else (out_c or Cout)
-        if out is None:     # zero-initialised: the pad channels beyond c_store are never written and stay zero
+        up, oy, ox = phase if phase is not None else (1, 0, 0)
+        if out is None and head_w is None:     # zero-initialised: the pad channels beyond c_store are never written and stay zero
             out = self.buf(B, 2 * H, 2 * W, chan_storage(c_real), zero=True) if shuffle else \
-                self.buf(B, H, W, chan_storage(c_real), zero=True)
+                self.buf(B, up * H, up * W, chan_storage(c_real), zero=True, dtype=out_dtype)
         op = ops.make_conv(src0, wp, out, taps, src1=src1, w_c1_off=meta["c1_off"], n_total=n_total,
                            bias=pc(bias, 0.0), scale=pc(scale, 1.0), shift=pc(shift, 0.0), relu1=relu1, relu2=relu2,
                            residual=residual, out_space=(B, H, W), shuffle=shuffle, group_n=meta.get("group_n", 0),
-                           c_store=pad_to(c_real, 8), name=name)
-        flops = 2.0 * B * H * W * Cout * Cin * ks * ks
+                           c_store=pad_to(c_real, 8), up=up, oy=oy, ox=ox, leaky1=leaky1, head_w=head_w, head_out=head_out,
+                           bn=n_total if head_w is not None else None, name=name)
+        if flops is None:
+            flops = 2.0 * B * H * W * Cout * Cin * len(taps)
         self.ops.append(Op(name, op.launch, flops=flops, kind="gemm"))
         self.keep.append(op)
         return out
@@ -177,6 +180,29 @@ class UnetProgram:
             _lib.check(lib.havc_phase_split(ip, op_, B, H, W, Cs, n_phases, stream), name)
         self.aux(name, fn, nbytes=2.0 * B * H * W * Cs * (1 + n_phases / 4))
         return out
+
+    # ---- execution ----------------------------------------------------------------------------
+    def run(self, stream: int = 0):
+        for op in self.ops:
+            op.fn(stream)
+
+    @property
+    def flops(self) -> float:
+        return sum(o.flops for o in self.ops) + self.head_flops
+
+
+class UnetProgram(LaunchProgram):
+    """Compiled launch list of a DeOldify generator for one (state-dict, batch, S, dtype)."""
+
+    def __init__(self, sd: SD, batch: int, size: int, dtype: torch.dtype = torch.float16, device="cuda",
+                 keep_taps: bool = False, x: Optional[torch.Tensor] = None):
+        if size % 32 != 0:
+            raise ValueError(f"render size {size} must be a multiple of 32 (even render_factor); the nearest-"
+                             "neighbour up-path resize of unet.py:201-203 is not implemented")
+        super().__init__(sd, batch, size, dtype, device, keep_taps)
+        self.bottleneck = "layers.0.4.0.conv3.weight" in sd
+        self._x_shared = x
+        self._build()
 
     # ---- network ------------------------------------------------------------------------------
     def _build(self):
@@ -422,11 +448,3 @@ class UnetProgram:
         self.keep.append(op)
         return out
 
-    # ---- execution ----------------------------------------------------------------------------
-    def run(self, stream: int = 0):
-        for op in self.ops:
-            op.fn(stream)
-
-    @property
-    def flops(self) -> float:
-        return sum(o.flops for o in self.ops) + self.head_flops
