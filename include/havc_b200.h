@@ -152,6 +152,10 @@ int havc_resample_h(const uint8_t *in, float *out, long long rows, int Win, int 
  * in: float [B][3][Hin][S]; rgb_small: u8 [B][3][S][S]; x: 16-bit NHWC [B][S][S][8]. */
 int havc_pre_vertical(const float *in, uint8_t *rgb_small, void *x, int B, int Hin, int S, const int *start,
                       const float *weights, int taps, int dtype, void *stream);
+/* ColorizerFilter._transform (Pillow 'L' gray, filters.py:92-93) + ImageNet normalisation (filters.py:50-53) of an
+ * already S x S image (the direct ModelImageRender path, where Pillow did the squeeze): rgb u8 [B][3][n] -> x 16-bit
+ * NHWC [B][n][8]. */
+int havc_gray_normalize(const uint8_t *rgb, void *x, int B, long long n_pixels, int dtype, void *stream);
 /* Network head: 1x1 conv 259->3 + SigmoidRange(-3,3) (unet.py:276-281), de-normalise, clamp, *255, truncate
  * to u8 (filters.py:64-67), and — if transplant — ColorizerFilter._post_process (filters.py:100-110) at S x S
  * against rgb_small.  res: [B,S,S,Cs] 16-bit; w11: fp32 [3][Cs]; colored: u8 [B][3][S][S];
@@ -254,6 +258,9 @@ int havc_bilinear_ab(const float *in, float *out, int B, int h, int w, int H, in
  * planar u8 RGB [B][3][H][W]. */
 int havc_zhang_post(const float *ab, int h, int w, const float *L, uint8_t *out, int B, int H, int W, void *stream);
 
+/* chroma_post_process (vsslib/imfilters.py:312-321) == ColorizerFilter._post_process (deoldify/filters.py:100-110) ==
+ * vs_recover_clip_luma (vsfilters.py:863-899): luma of `orig`, chroma of `color` through OpenCV's 8-bit Q14 YUV. */
+int havc_chroma_post_process(const uint8_t *color, const uint8_t *orig, uint8_t *out, int B, int H, int W, void *stream);
 /* Scene-change gate of the per-frame selectors (vsslib/vsmodels.py:221-224, mcomb.py:210-213: `return f[0].copy()`):
  * frames b with skip[b] != 0 are overwritten by the same frame of `src`. */
 int havc_select_frames(uint8_t *dst, const uint8_t *src, const uint8_t *skip, int B, long long frame_bytes, void *stream);

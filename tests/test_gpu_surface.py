@@ -135,3 +135,25 @@ def test_colorizer_second_model_errors():
         havc.HAVC_colorizer(clip, method=2, deoldify_p=[0, 4, 1.0, 0.0], ddcolor_p=[1, 10, 1.0, 0.0, True])
     with pytest.raises(vs_shim.Error):
         havc.HAVC_colorizer(clip, method=9, deoldify_p=[0, 4, 1.0, 0.0], ddcolor_p=[2, 10, 1.0, 0.0, True])
+
+
+@pytest.mark.parametrize("model,rf", [("video", 4), ("stable", 4), ("artistic", 6)])
+def test_model_image_render_vs_reference_golden(model, rf):
+    """ModelImageRender.get_transformed_image (the reference's per-image entry point, BASELINE cfg1) against outputs of
+    the REAL reference (tests/golden/model_image_render.npz): Pillow BILINEAR squeeze / un-squeeze on non-square
+    images, identity on square ones, the 50/50 blend of the second generator."""
+    import os
+    from PIL import Image
+    from oracle import metrics, synth_weights
+    havc = _register()
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "model_image_render.npz"))
+    color = lambda seed, h, w: np.stack([synth_weights.make_test_frame(seed + c, h, w).numpy() for c in range(3)], -1)
+    S = rf * 16
+    inputs = {"color": color(7, 120, 160), "gray": np.repeat(synth_weights.make_test_frame(9, 90, 144).numpy()[..., None], 3, -1),
+              "square": color(21, S, S)}
+    r = havc.ModelImageRender(package_dir=None, modelname=model, render_factor=rf, video_weight=0.5)
+    for name, img in inputs.items():
+        got = np.asarray(r.get_transformed_image(Image.fromarray(img)))
+        m = metrics.frame_parity(got, g[f"{model}_rf{rf}_{name}"])
+        assert m["mean_de00"] <= 0.5, (model, name, m)
+        assert m["n_err_gt2"] <= 0.02 * m["n_values"], (model, name, m)

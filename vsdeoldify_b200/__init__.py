@@ -7,7 +7,7 @@ __version__ = "0.1.0"
 
 
 def __getattr__(name):   # lazy: importing the package must not import torch / load the CUDA library
-    if name in ("HAVC_main", "HAVC_colorizer", "HAVC_deoldify", "HAVC_ddeoldify", "HAVC_merge", "register_state_dict"):
+    if name in ("HAVC_main", "HAVC_colorizer", "HAVC_deoldify", "HAVC_ddeoldify", "HAVC_merge", "ModelImageRender", "register_state_dict"):
         from . import havc
         return getattr(havc, name)
     raise AttributeError(name)

@@ -372,6 +372,18 @@ __global__ void vs_merge_u8_kernel(const uint8_t *__restrict__ a, const uint8_t 
     }
 }
 
+// ---- chroma_post_process (imfilters.py:312-321; ColorizerFilter._post_process filters.py:100-110) --------------------------
+__global__ void chroma_post_process_kernel(Img color, Img orig, uint8_t *out) {
+    const int fb = blockIdx.y;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < orig.plane; i += (long long)gridDim.x * blockDim.x) {
+        int rc, gc, bc, ro, go, bo, r, g, b;
+        color.load(fb, i, rc, gc, bc);
+        orig.load(fb, i, ro, go, bo);
+        luma_transplant(ro, go, bo, rc, gc, bc, r, g, b);
+        store_px(out, orig.plane, fb, i, r, g, b);
+    }
+}
+
 // ---- scene-change gate (vsslib/vsmodels.py:221-224, mcomb.py:210-213): frames with skip[b] != 0 take `src` unchanged ------
 __global__ void select_frames_kernel(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, const uint8_t *__restrict__ skip,
                                      long long frame_bytes) {
@@ -576,6 +588,14 @@ extern "C" int havc_vs_merge_u8(const uint8_t *a, const uint8_t *b, uint8_t *out
 extern "C" int havc_select_frames(uint8_t *dst, const uint8_t *src, const uint8_t *skip, int B, long long frame_bytes, void *stream) {
     HAVC_CHECK_ARG(dst && src && skip && B > 0 && frame_bytes > 0, "havc_select_frames: bad arguments");
     select_frames_kernel<<<frame_grid(frame_bytes, B), 256, 0, (cudaStream_t)stream>>>(dst, src, skip, frame_bytes);
+    HAVC_LAUNCHED();
+    return HAVC_OK;
+}
+
+extern "C" int havc_chroma_post_process(const uint8_t *color, const uint8_t *orig, uint8_t *out, int B, int H, int W, void *stream) {
+    HAVC_CHECK_ARG(color && orig && out && HAVC_IMG_ARGS_OK(B, H, W), "havc_chroma_post_process: bad arguments");
+    Img ic{color, (long long)H * W}, io{orig, (long long)H * W};
+    chroma_post_process_kernel<<<frame_grid(io.plane, B), 256, 0, (cudaStream_t)stream>>>(ic, io, out);
     HAVC_LAUNCHED();
     return HAVC_OK;
 }

@@ -102,6 +102,23 @@ __global__ void pre_vertical_kernel(const float *__restrict__ in, uint8_t *__res
     }
 }
 
+// ColorizerFilter._transform (convert('LA').convert('RGB'), filters.py:92-93) + ImageNet normalisation (filters.py:50-53)
+// of an already square u8 image: rgb u8 [B][3][n] -> x 16-bit [B][n][8].
+__global__ void gray_normalize_kernel(const uint8_t *__restrict__ rgb, void *__restrict__ x, int B, long long n, int dtype) {
+    const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+    const long long total = (long long)B * n;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / n, px = i - b * n;
+        const uint8_t *q = rgb + b * 3 * n + px;
+        const int L = pil_luma(__ldg(q), __ldg(q + n), __ldg(q + 2 * n));
+        const float lf = __fdiv_rn((float)L, 255.f);
+        float v[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[c] = __fdiv_rn(__fsub_rn(lf, mean[c]), stdv[c]);
+        *reinterpret_cast<uint4 *>(reinterpret_cast<uint16_t *>(x) + i * 8) = make_uint4(pack2(v[0], v[1], dtype), pack2(v[2], 0.f, dtype), 0u, 0u);
+    }
+}
+
 // Shared tail of the head: logits -> SigmoidRange(-3,3) -> de-normalise -> clamp -> *255 -> truncate -> (skip |
 // S x S luma transplant) -> colored u8 planes.
 __device__ __forceinline__ void head_finish_pixel(const float lg[3], long long pix, const uint8_t *__restrict__ rgb_small,
@@ -313,6 +330,13 @@ extern "C" int havc_pre_vertical(const float *in, uint8_t *rgb_small, void *x, i
                    "havc_pre_vertical: bad arguments");
     pre_vertical_kernel<<<grid1d((long long)B * S * S, 256), 256, 0, (cudaStream_t)stream>>>(
         in, rgb_small, x, B, Hin, S, start, weights, taps, dtype);
+    HAVC_LAUNCHED();
+    return HAVC_OK;
+}
+
+extern "C" int havc_gray_normalize(const uint8_t *rgb, void *x, int B, long long n_pixels, int dtype, void *stream) {
+    HAVC_CHECK_ARG(rgb && x && B > 0 && n_pixels > 0 && (dtype == HAVC_F16 || dtype == HAVC_BF16), "havc_gray_normalize: bad arguments");
+    gray_normalize_kernel<<<grid1d((long long)B * n_pixels, 256), 256, 0, (cudaStream_t)stream>>>(rgb, x, B, n_pixels, dtype);
     HAVC_LAUNCHED();
     return HAVC_OK;
 }

@@ -226,3 +226,80 @@ class DeoldifyEngine:
             ev_out[sj].synchronize()
             on_result(j, self.h_out[sj].numpy())
         return i + 1
+
+
+class ImageRenderEngine:
+    """vsdeoldify.deoldify.visualize.ModelImageRender on the GPU (deoldify/visualize.py:41-137): the direct, per-image
+    path (BASELINE cfg1) in which the FILTER squeezes the W x H image to S x S with Pillow BILINEAR
+    (BaseFilter._scale_to_square, filters.py:37-41), runs the generator, resizes the result back with Pillow BILINEAR
+    (_unsquare, filters.py:70-73) and only then transplants the original luma at full resolution
+    (ColorizerFilter._post_process, filters.py:100-110).  The video generator always runs; 'stable' / 'artistic' run a
+    second generator through the same steps and mix the two full-size results with Image.blend (visualize.py:118-137).
+    Both resizes are the bit-exact integer Pillow passes (havc_pil_resample_u8)."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], width: int, height: int, render_factor: int = 24, batch: int = 1,
+                 dtype: torch.dtype = torch.float16, device: str = "cuda:0", sd_other: Optional[Dict[str, torch.Tensor]] = None,
+                 video_weight: float = 0.5):
+        self.lib = _lib.lib()
+        self.dev = torch.device(device)
+        torch.cuda.set_device(self.dev)
+        self.W, self.H, self.B, self.S = width, height, batch, render_factor * 16
+        S, B, W, H = self.S, batch, width, height
+        self.hd = ops.havc_dtype(dtype)
+        self.prog = UnetProgram(sd, B, S, dtype, device=self.dev)
+        self.prog2 = UnetProgram(sd_other, B, S, dtype, device=self.dev, x=self.prog.x) if sd_other is not None else None
+        self.video_weight = float(video_weight)
+        mk = lambda a, b: tuple(torch.from_numpy(t).to(self.dev) for t in resample.pil_tables(a, b, "bilinear"))
+        self.t_dw, self.t_dh = (mk(W, S) if W != S else None), (mk(H, S) if H != S else None)      # squeeze
+        self.t_uw, self.t_uh = (mk(S, W) if W != S else None), (mk(S, H) if H != S else None)      # back
+        u8 = dict(dtype=torch.uint8, device=self.dev)
+        self.d_in = torch.empty(B, 3, H, W, **u8)
+        self.d_out = torch.empty(B, 3, H, W, **u8)
+        self.d_out2 = torch.empty(B, 3, H, W, **u8) if sd_other is not None else None
+        self.sq_h = torch.empty(B, 3, H, S, **u8)          # after the horizontal squeeze pass
+        self.sq = torch.empty(B, 3, S, S, **u8)
+        self.model_img = torch.empty(B, 3, S, S, **u8)
+        self.up_h = torch.empty(B, 3, S, W, **u8)          # after the horizontal pass back
+        self.raw = torch.empty(B, 3, H, W, **u8)
+        self.stream = torch.cuda.Stream(device=self.dev)
+
+    def _pil_resize(self, src, tmp, dst, Hin, Win, Hout, Wout, tw, th, st):
+        lib, B, chk = self.lib, self.B, _lib.check
+        cur, h, w = src, Hin, Win
+        if tw is not None:                                 # Pillow: horizontal pass first, each pass only if the size changes
+            target = tmp if th is not None else dst
+            chk(lib.havc_pil_resample_u8(cur.data_ptr(), target.data_ptr(), B * 3, h, w, Wout, 1, tw[0].data_ptr(), tw[1].data_ptr(),
+                                         tw[1].shape[1], st), "pil.h")
+            cur, w = target, Wout
+        if th is not None:
+            chk(lib.havc_pil_resample_u8(cur.data_ptr(), dst.data_ptr(), B * 3, h, w, Hout, 0, th[0].data_ptr(), th[1].data_ptr(),
+                                         th[1].shape[1], st), "pil.v")
+            cur = dst
+        return cur
+
+    def _filter(self, prog, out, st):
+        lib, B, S, W, H, chk = self.lib, self.B, self.S, self.W, self.H, _lib.check
+        prog.run(st)
+        chk(lib.havc_head(prog.logits.data_ptr(), 0, None, prog.b11.data_ptr(), None, self.model_img.data_ptr(), None, None, B, S,
+                          self.hd, 0, st), "head")
+        raw = self._pil_resize(self.model_img, self.up_h, self.raw, S, S, H, W, self.t_uw, self.t_uh, st)
+        chk(lib.havc_chroma_post_process(raw.data_ptr(), self.d_in.data_ptr(), out.data_ptr(), B, H, W, st), "post_process")
+
+    def render_batch(self, frames: np.ndarray) -> np.ndarray:
+        """frames: uint8 [n<=B, 3, H, W] planar RGB -> uint8 [n, 3, H, W] (get_transformed_image per image)."""
+        n = frames.shape[0]
+        assert n <= self.B and frames.shape[1:] == (3, self.H, self.W) and frames.dtype == np.uint8
+        lib, B, S, W, H, chk = self.lib, self.B, self.S, self.W, self.H, _lib.check
+        with torch.cuda.stream(self.stream):
+            st = self.stream.cuda_stream
+            self.d_in[:n].copy_(torch.from_numpy(np.ascontiguousarray(frames)), non_blocking=False)
+            sq = self._pil_resize(self.d_in, self.sq_h, self.sq, H, W, S, S, self.t_dw, self.t_dh, st)
+            chk(lib.havc_gray_normalize(sq.data_ptr(), self.prog.x.data_ptr(), B, S * S, self.hd, st), "gray_normalize")
+            self._filter(self.prog, self.d_out, st)
+            if self.prog2 is not None:
+                self._filter(self.prog2, self.d_out2, st)
+                chk(lib.havc_blend_u8(self.d_out2.data_ptr(), self.d_out.data_ptr(), self.d_out.data_ptr(), self.d_out.numel(),
+                                      self.video_weight, st), "blend")
+            out = self.d_out.cpu()
+        self.stream.synchronize()
+        return out[:n].numpy().copy()

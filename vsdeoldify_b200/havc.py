@@ -246,6 +246,39 @@ def HAVC_merge(clipa=None, clipb=None, clip_luma=None, weight: float = 0.5, meth
         if vs is vs_shim else _wrap_real_vs(clipa, guarded)
 
 
+class ModelImageRender:
+    """Drop-in for vsdeoldify.deoldify.visualize.ModelImageRender (deoldify/visualize.py:41-137): the reference's own
+    per-image entry point (`get_transformed_image(PIL image) -> PIL image`; BASELINE cfg1 runs it on still images).
+    The filter-level Pillow BILINEAR squeeze / un-squeeze and the full-resolution luma transplant run on the GPU
+    (engine.ImageRenderEngine); one engine per image size is kept."""
+
+    def __init__(self, package_dir: Optional[str] = None, modelname: str = 'video', render_factor: int = 24,
+                 video_weight: float = 0, device_index: int = 0):
+        self.package_dir = package_dir
+        self._modelname, self._video_weight, self._render_factor = modelname, video_weight, render_factor
+        mdir = os.path.join(package_dir, "models") if package_dir else model_dir             # generators.py:18-19
+        self._sd_video = load_state_dict(_WEIGHT_FILES[0], mdir)
+        other = {"stable": 1, "artistic": 2}.get(modelname)
+        self._sd_other = load_state_dict(_WEIGHT_FILES[other], mdir) if other is not None else None
+        self._device = f"cuda:{device_index}"
+        self._engines: Dict[tuple, object] = {}
+
+    def get_transformed_image(self, img_orig, post_process: bool = True):
+        from PIL import Image
+        from .engine import ImageRenderEngine
+        if not post_process:
+            _raise("ModelImageRender: post_process=False is not built")
+        arr = np.asarray(img_orig.convert("RGB") if img_orig.mode != "RGB" else img_orig)
+        H, W = arr.shape[:2]
+        eng = self._engines.get((W, H))
+        if eng is None:
+            eng = self._engines[(W, H)] = ImageRenderEngine(self._sd_video, W, H, self._render_factor, batch=1, dtype=_DTYPE,
+                                                            device=self._device, sd_other=self._sd_other,
+                                                            video_weight=self._video_weight)
+        out = eng.render_batch(np.ascontiguousarray(np.transpose(arr, (2, 0, 1)))[None])
+        return Image.fromarray(np.ascontiguousarray(np.transpose(out[0], (1, 2, 0))), "RGB")
+
+
 def _wrap_real_vs(clip, fn):
     """Real VapourSynth: serve frames through std.ModifyFrame; the selector ignores `f` and returns our frame."""
     return clip.std.ModifyFrame(clips=[clip], selector=lambda n, f: fn(n))
