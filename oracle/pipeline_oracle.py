@@ -31,7 +31,7 @@ def net_output_square(sd, rgb_sq: np.ndarray) -> np.ndarray:
 def havc_colorizer_frame(sd, frame: np.ndarray, render_factor: int = 24, kernel: str = "spline64",
                          return_stages: bool = False, skip: bool = False, sd_other=None, video_weight: float = 0.5,
                          zhang=None, method: int = 0, merge_weight: float = 0.4, hue_adjust: str = "none", cmc_p=None,
-                         lmm_p=None, alm_p=None, crt_p=None, invert: bool = False):
+                         lmm_p=None, alm_p=None, crt_p=None, invert: bool = False, ddtweak=None):
     """frame: uint8 [H,W,3].  Returns uint8 [H,W,3] (and the intermediate stages on request).
     skip: the scene-change gate returned the squeezed frame unchanged (vsslib/vsmodels.py:221-224).
     sd_other: 'stable'/'artistic' generator blended with the video one at S x S (visualize.py:118-137).
@@ -54,8 +54,16 @@ def havc_colorizer_frame(sd, frame: np.ndarray, render_factor: int = 24, kernel:
                 other = px.chroma_post_process(model_process_square(sd_other, small), small)
                 colored = px.pil_blend(other, colored, video_weight)
         if zhang is not None and method != 0:
-            clipb = zhang_oracle.colorize_frame(zhang[1], zhang[0], small)
+            src_b = small
+            if ddtweak is not None:            # vs_sc_tweak(bright, cont) + sc_constrained_tweak (vsmodels.py:326-332)
+                if ddtweak.get("bright", 0) != 0 or ddtweak.get("cont", 1) != 1:
+                    src_b = fo.image_tweak(src_b, cont=ddtweak["cont"], bright=ddtweak["bright"])
+                src_b = fo.luma_adjusted_levels(src_b, ddtweak["luma_min"], ddtweak["gamma"], ddtweak["gamma_luma_min"],
+                                                ddtweak["gamma_alpha"], ddtweak["gamma_min"])
+            clipb = zhang_oracle.colorize_frame(zhang[1], zhang[0], src_b)
             clipb = fo.adjust_hue_range(clipb, hue_adjust)
+            if ddtweak is not None:            # vs_recover_clip_luma(clip, clipb_rgb) (vsmodels.py:367-368)
+                clipb = px.chroma_post_process(clipb, small)
             if method == 1:
                 colored = clipb
             else:

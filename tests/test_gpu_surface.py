@@ -157,3 +157,31 @@ def test_model_image_render_vs_reference_golden(model, rf):
         m = metrics.frame_parity(got, g[f"{model}_rf{rf}_{name}"])
         assert m["mean_de00"] <= 0.5, (model, name, m)
         assert m["n_err_gt2"] <= 0.02 * m["n_values"], (model, name, m)
+
+
+@pytest.mark.parametrize("zmodel,zname,gate", [(2, "siggraph17", 0.5), (3, "eccv16", 1.4)])
+def test_colorizer_ddtweak_inverted_merge(zmodel, zname, gate):
+    """cfg4-style call: ddtweak=[True, False, False] with the default luma-constrained tweak (luma_adjusted_levels on the
+    second model's input, vs_recover_clip_luma on its output), clips swapped (cmb_sw).  The eccv16 gate is wider: its
+    random-weight stack amplifies storage rounding (see tests/test_gpu_zhang.py)."""
+    from oracle import metrics, pipeline_oracle
+    from vsdeoldify_b200.constants import DEF_TWEAK_p
+    havc = _register()
+    _register_zhang(havc)
+    H, W, rf, n = 96, 176, 10, 2
+    clip, fr, props = _clip(n, H, W, seed=170)
+    fr[1] //= 3                                                     # a dark frame: the luma floor / gamma branch is taken
+    out = havc.HAVC_colorizer(clip, method=5, mweight=0.5, deoldify_p=[0, rf, 1.0, 0.0], ddcolor_p=[zmodel, rf, 1.0, 0.0, True],
+                              ddtweak=[True, False, False], cmb_sw=True)
+    sd = havc._REGISTERED["ColorizeVideo_gen"]
+    sdz = havc._REGISTERED[havc._ZHANG_FILES[zname]]
+    t = DEF_TWEAK_p
+    tw = dict(bright=t[0], cont=t[1], gamma=t[2], luma_min=t[4], gamma_luma_min=t[5], gamma_alpha=t[6], gamma_min=t[7])
+    for i in range(n):
+        f = out.get_frame(i)
+        assert f.props == props[i]
+        ref = pipeline_oracle.havc_colorizer_frame(sd, np.transpose(fr[i], (1, 2, 0)), rf, zhang=(zname, sdz), method=5,
+                                                   merge_weight=0.5, hue_adjust="300:360|0.8,0.1", invert=True, ddtweak=tw)
+        img = np.stack([np.asarray(f[p]) for p in range(3)], -1)
+        m = metrics.frame_parity(img, ref)
+        assert m["mean_de00"] <= gate, (zname, i, m)

@@ -76,3 +76,38 @@ def test_shim_selector_protocol_keeps_props():
         out.get_frame(3)
     tagged = out.std.SetFrameProp(prop="sc_frequency", intval=1).std.CopyFrameProps(prop_src=clip, props=["x"])
     assert tagged.get_frame(1).props["sc_frequency"] == 1 and tagged.get_frame(1).props["x"] == 1
+
+
+def test_havc_main_preset_tables_match_reference():
+    """The string -> number tables behind HAVC_main (havc_utils.py:335-517), compared with the REAL reference functions when
+    the reference tree is present (skipped on the GPU box, where it is not)."""
+    import sys
+    from oracle import refshim
+    if not refshim.available():
+        pytest.skip("reference tree not present")
+    refshim.install()
+    from vsdeoldify_b200 import havc, vs_shim
+    saved = sys.modules.get("vapoursynth")
+    sys.modules["vapoursynth"] = vs_shim
+    try:
+        from vsdeoldify import havc_utils as ref
+    finally:
+        if saved is None:
+            sys.modules.pop("vapoursynth", None)
+        else:
+            sys.modules["vapoursynth"] = saved
+    for preset in ['Placebo', 'VerySlow', 'Slower', 'Slow', 'Medium', 'Fast', 'Faster', 'VeryFast']:
+        assert havc._get_render_factor(preset) == ref._get_render_factors(preset)[1]
+    for vt in ['VeryStable', 'MoreStable', 'Stable', 'Balanced', 'Vivid', 'MoreVivid', 'VeryVivid']:
+        assert havc._VIDEO_TUNE[vt.lower()] == ref._get_mweight(vt)
+    for cm in ['Simple', 'Constrained-Chroma', 'Luma-Masked', 'Adaptive-Luma', 'Chroma-Retention', 'ChromaBound Adaptive']:
+        assert havc._COMB_METHOD[cm.lower()] == ref._get_comb_method(cm)
+    for model in ['Video+Siggraph17', 'Stable+ECCV16', 'Artistic+Artistic', 'Video+ModelScope', 'DeOldify(Video)', 'DeOldify(Stable)',
+                  'DeOldify(Artistic)', 'Zhang(Siggraph17)', 'Zhang(ECCV16)', 'DDColor(Artistic)']:
+        assert havc._get_color_model(model) == ref._get_color_model(model), model
+    for tune in ['None', 'Light', 'Medium', 'Strong']:
+        for fix in ['None', 'Magenta', 'Magenta/Violet', 'Violet', 'Violet/Red', 'Blue/Magenta', 'Yellow', 'Yellow/Orange',
+                    'Yellow/Green', 'Retinex/Red']:
+            for dd in (0, 1, 2, 3):
+                want = ref._get_color_tune(tune, fix, 'None', dd)
+                assert havc._get_color_tune(tune, fix, dd) == (want[0], want[1]), (tune, fix, dd)

@@ -226,6 +226,10 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap *tm, uint32_t src
                  : "memory");
 }
 
+// kDT: operand / 16-bit output type (HAVC_F16 or HAVC_BF16), fixed at compile time so the pack / unpack helpers fold.
+// kFast: the streamlined epilogue for the common case (16-bit output through the TMA-store staging buffer, whole N tiles,
+// no head / column split / staggered accumulators); the generic epilogue covers everything else.
+template <int kDT, bool kFast>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmW, const __grid_constant__ StoreMaps tmO,
@@ -422,6 +426,24 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             if (p.residual2 != nullptr && valid)
                 res_row2 = reinterpret_cast<const uint8_t *>(p.residual2) + 2ll * (ob * p.r2sb + oh * p.r2sh + ow * p.r2sw);
             float hacc0 = 0.f, hacc1 = 0.f, hacc2 = 0.f;
+            if (p.residual != nullptr) {
+                // pull the NEXT tile's residual rows towards L2 while this tile is processed: each thread covers the
+                // 128-byte lines of its own row that its warp half will read
+                const int tn = tile + gridDim.x;
+                if (tn < p.total_tiles) {
+                    int t2 = tn;
+                    const int nt2 = t2 % p.tiles_n; t2 /= p.tiles_n;
+                    const int wt2 = t2 % p.tiles_w; t2 /= p.tiles_w;
+                    const int ht2 = t2 % p.tiles_h; t2 /= p.tiles_h;
+                    const int ow2 = wt2 * p.bw + rw, oh2 = ht2 * p.bh + rh, ob2 = t2 * p.bb + rb;
+                    if (ow2 < p.out_W && oh2 < p.out_H && ob2 < p.out_B) {
+                        const uint8_t *row = reinterpret_cast<const uint8_t *>(p.residual) + 2ll * (ob2 * p.rsb + oh2 * p.rsh + ow2 * p.rsw);
+                        const int cbeg = nt2 * p.BN, cend = min(cbeg + p.BN, p.c_store);
+                        for (int c = cbeg + half * 64; c < cend; c += 128)
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 2 * c));
+                    }
+                }
+            }
 
             mbar_wait(tfull_bar(as), aphase);
             tc_fence_after();
@@ -430,7 +452,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             uint32_t va[32], vb[32];
             // ---- per-tile invariants of this thread (hoisted out of the chunk loop) ----
             const int BN = p.BN, N_total = p.N_total, split_n = p.split_n, c_store = p.c_store, c_store2 = p.c_store2;
-            const int dt = p.dtype, od = p.out_dtype, gn = p.group_n;
+            constexpr int dt = kDT;
+            const int od = p.out_dtype == HAVC_F32 ? HAVC_F32 : kDT, gn = p.group_n;
             const bool shuffle = p.shuffle != 0, has_scale = p.scale != nullptr, head = p.head_w != nullptr;
             const bool tma_store = p.tma_store != 0;
             const float slope1 = p.slope1, lo2 = p.relu2 ? 0.f : -INFINITY;
@@ -573,6 +596,71 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                     }
                 }
             };
+            // Streamlined variant (kFast): every chunk is a full 32 columns of a whole N tile, the result goes to the
+            // swizzled staging buffer (TMA clips rows / channels outside the tensor), residual rows are read only for
+            // pixels inside the image.
+            auto process_fast = [&](int ci, int nxt, uint32_t(&vc)[32], uint32_t(&vn)[32]) {
+                const int c0 = ci * 32;
+                const int n = n0 + c0;
+                uint4 rres[4];
+                const bool do_res = res_row != nullptr;
+                if (do_res) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g)
+                        rres[g] = (n + 8 * g < c_store) ? __ldg(reinterpret_cast<const uint4 *>(res_row + 2 * (n + 8 * g))) : make_uint4(0, 0, 0, 0);
+                }
+                tmem_ld_wait();
+                if (nxt >= 0) {
+                    __syncwarp();
+                    tmem_ld32(tbase + nxt * 32, vn);
+                }
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int cc = c0 + 16 * hh;
+                    float y[16];
+                    const float4 *b4 = reinterpret_cast<const float4 *>(sb + cc);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const float4 bv = b4[g];
+                        const float t0 = __uint_as_float(vc[16 * hh + 4 * g + 0]) + bv.x, t1 = __uint_as_float(vc[16 * hh + 4 * g + 1]) + bv.y;
+                        const float t2 = __uint_as_float(vc[16 * hh + 4 * g + 2]) + bv.z, t3 = __uint_as_float(vc[16 * hh + 4 * g + 3]) + bv.w;
+                        y[4 * g + 0] = fmaxf(t0, t0 * slope1);
+                        y[4 * g + 1] = fmaxf(t1, t1 * slope1);
+                        y[4 * g + 2] = fmaxf(t2, t2 * slope1);
+                        y[4 * g + 3] = fmaxf(t3, t3 * slope1);
+                    }
+                    if (has_scale) {
+                        const float4 *s4 = reinterpret_cast<const float4 *>(sb + kMaxBN + cc);
+                        const float4 *t4 = reinterpret_cast<const float4 *>(sb + 2 * kMaxBN + cc);
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const float4 sv = s4[g], tv = t4[g];
+                            y[4 * g + 0] = fmaf(y[4 * g + 0], sv.x, tv.x);
+                            y[4 * g + 1] = fmaf(y[4 * g + 1], sv.y, tv.y);
+                            y[4 * g + 2] = fmaf(y[4 * g + 2], sv.z, tv.z);
+                            y[4 * g + 3] = fmaf(y[4 * g + 3], sv.w, tv.w);
+                        }
+                    }
+                    if (do_res) {
+                        const uint32_t rr[8] = {rres[2 * hh].x, rres[2 * hh].y, rres[2 * hh].z, rres[2 * hh].w,
+                                                rres[2 * hh + 1].x, rres[2 * hh + 1].y, rres[2 * hh + 1].z, rres[2 * hh + 1].w};
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float2 f = unpack2(rr[j], kDT);
+                            y[2 * j] += f.x;
+                            y[2 * j + 1] += f.y;
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) y[j] = fmaxf(y[j], lo2);
+                    const uint32_t sub = stage_out + (uint32_t)(cc >> 6) * (kTileM * 128u) + (uint32_t)r * 128u;
+                    const uint32_t k16 = (uint32_t)(cc & 63) >> 3;
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sub + ((k16 ^ (r & 7u)) << 4)), "r"(pack2(y[0], y[1], kDT)),
+                                 "r"(pack2(y[2], y[3], kDT)), "r"(pack2(y[4], y[5], kDT)), "r"(pack2(y[6], y[7], kDT)) : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sub + (((k16 + 1u) ^ (r & 7u)) << 4)), "r"(pack2(y[8], y[9], kDT)),
+                                 "r"(pack2(y[10], y[11], kDT)), "r"(pack2(y[12], y[13], kDT)), "r"(pack2(y[14], y[15], kDT)) : "memory");
+                }
+            };
             // This warp's chunks are ci = half, half+2, ...; in staggered mode the columns shared with the other
             // accumulator stage are drained first (stage 0: the highest chunks, stage 1: the lowest) and `tearly`
             // is signalled as soon as they are out of TMEM.
@@ -584,6 +672,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 return as == 0 ? (ci * 32 + 32 > p.acc_stride) : (ci * 32 < p.BN - p.acc_stride);
             };
             bool early_done = !p.staggered;
+            if constexpr (kFast) {
+                __syncwarp();
+                tmem_ld32(tbase + half * 32, va);
+                for (int k = 0; k < n_my; k += 2) {
+                    process_fast(half + 2 * k, k + 1 < n_my ? half + 2 * (k + 1) : -1, va, vb);
+                    if (k + 1 < n_my) process_fast(half + 2 * (k + 1), k + 2 < n_my ? half + 2 * (k + 2) : -1, vb, va);
+                }
+            } else {
             if (n_my > 0) {
                 __syncwarp();
                 tmem_ld_chunk(tbase + chunk_at(0) * 32, va, p.BN - chunk_at(0) * 32);
@@ -608,6 +704,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 tc_fence_before();
                 mbar_arrive(tearly_bar(as));
             }
+            }   // generic path
             if (tma_store) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> async proxy
                 asm volatile("bar.sync 2, 256;" ::: "memory");
@@ -844,9 +941,18 @@ extern "C" int havc_conv_gemm(const havc_conv_desc *d, void *stream) {
     if (d->b_batched) HAVC_CHECK_ARG(d->box_b == 1, "havc_conv_gemm: b_batched=1 needs box_b=1");
 
     const size_t smem = (size_t)p.num_stages * p.stage_bytes + p.stage_out_bytes + 1024 + 256 + kEpiSmemFloats * sizeof(float);
+    static const bool no_fast = getenv("HAVC_B200_NO_FAST_EPILOGUE") != nullptr;   // A/B switch for profiling
+    const bool fast = !no_fast && p.tma_store && !p.staggered && d->head_w == nullptr && d->split_n == 0 && d->residual2 == nullptr &&
+                      d->out_dtype == d->dtype && d->BN % 32 == 0 && d->N_total % d->BN == 0;
+    typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const StoreMaps, const ConvParams);
+    KernelFn kern = d->dtype == HAVC_F16 ? (fast ? conv_gemm_kernel<HAVC_F16, true> : conv_gemm_kernel<HAVC_F16, false>)
+                                         : (fast ? conv_gemm_kernel<HAVC_BF16, true> : conv_gemm_kernel<HAVC_BF16, false>);
     static bool attr_set = false;
     if (!attr_set) {
-        HAVC_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        HAVC_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<HAVC_F16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        HAVC_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<HAVC_F16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        HAVC_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<HAVC_BF16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        HAVC_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<HAVC_BF16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
     StoreMaps tmO;
@@ -867,7 +973,7 @@ extern "C" int havc_conv_gemm(const havc_conv_desc *d, void *stream) {
         }
     }
     int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-    conv_gemm_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA0, tmA1, tmW, tmO, p);
+    kern<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA0, tmA1, tmW, tmO, p);
     HAVC_LAUNCHED();
     return HAVC_OK;
 }

@@ -22,17 +22,12 @@ __global__ void resample_h_kernel(const uint8_t *__restrict__ in, float *__restr
     extern __shared__ float srow[];
     for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
         const uint8_t *src = in + row * Win;
-        if ((Win & 15) == 0 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
-            for (int i = threadIdx.x; i < Win / 16; i += blockDim.x) {
-                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src) + i);
-                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    srow[i * 16 + 4 * j + 0] = (float)(w[j] & 0xff);
-                    srow[i * 16 + 4 * j + 1] = (float)((w[j] >> 8) & 0xff);
-                    srow[i * 16 + 4 * j + 2] = (float)((w[j] >> 16) & 0xff);
-                    srow[i * 16 + 4 * j + 3] = (float)(w[j] >> 24);
-                }
+        if ((Win & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) & 3) == 0)) {
+            // 4 pixels per thread: coalesced 4-byte loads, one conflict-free 16-byte shared store (lane i -> bytes 16 i)
+            for (int i = threadIdx.x; i < Win / 4; i += blockDim.x) {
+                const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(src) + i);
+                reinterpret_cast<float4 *>(srow)[i] = make_float4((float)(w & 0xff), (float)((w >> 8) & 0xff), (float)((w >> 16) & 0xff),
+                                                                  (float)(w >> 24));
             }
         } else {
             for (int i = threadIdx.x; i < Win; i += blockDim.x) srow[i] = (float)src[i];
@@ -236,7 +231,7 @@ __global__ void post_horizontal_kernel(const float *__restrict__ in, const uint8
         }
         __syncthreads();
         const long long base = ((long long)b * 3 * H + oy) * W;
-        for (int ox = threadIdx.x; ox < W; ox += blockDim.x) {
+        auto pixel = [&](int ox, int o_r, int o_g, int o_b, int &rr, int &gg, int &bb) {
             const int s0 = __ldg(start + ox);
             const float *w = wts + ox;                       // transposed table [T][W]
             float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
@@ -247,13 +242,36 @@ __global__ void post_horizontal_kernel(const float *__restrict__ in, const uint8
                 acc2 = fmaf(wt, srows[2 * S + s0 + t], acc2);
             }
             const int q0 = round_u8(acc0), q1 = round_u8(acc1), q2 = round_u8(acc2);
-            int rr = q0, gg = q1, bb = q2;
-            if (transplant)
-                luma_transplant(__ldg(orig + base + ox), __ldg(orig + base + ps + ox), __ldg(orig + base + 2 * ps + ox), q0, q1,
-                                q2, rr, gg, bb);
-            out[base + ox] = (uint8_t)rr;
-            out[base + ps + ox] = (uint8_t)gg;
-            out[base + 2 * ps + ox] = (uint8_t)bb;
+            rr = q0; gg = q1; bb = q2;
+            if (transplant) luma_transplant(o_r, o_g, o_b, q0, q1, q2, rr, gg, bb);
+        };
+        if ((W & 3) == 0 && transplant && ((reinterpret_cast<uintptr_t>(orig) | reinterpret_cast<uintptr_t>(out)) & 3) == 0) {
+            // 4 pixels per thread: 4-byte loads of the original planes and 4-byte stores (128 B per warp and plane)
+            for (int x4 = threadIdx.x; x4 < W / 4; x4 += blockDim.x) {
+                const int ox = 4 * x4;
+                const uint32_t o0 = __ldg(reinterpret_cast<const uint32_t *>(orig + base + ox));
+                const uint32_t o1 = __ldg(reinterpret_cast<const uint32_t *>(orig + base + ps + ox));
+                const uint32_t o2 = __ldg(reinterpret_cast<const uint32_t *>(orig + base + 2 * ps + ox));
+                uint32_t p0 = 0, p1 = 0, p2 = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    int rr, gg, bb;
+                    pixel(ox + k, (o0 >> (8 * k)) & 0xff, (o1 >> (8 * k)) & 0xff, (o2 >> (8 * k)) & 0xff, rr, gg, bb);
+                    p0 |= (uint32_t)rr << (8 * k); p1 |= (uint32_t)gg << (8 * k); p2 |= (uint32_t)bb << (8 * k);
+                }
+                *reinterpret_cast<uint32_t *>(out + base + ox) = p0;
+                *reinterpret_cast<uint32_t *>(out + base + ps + ox) = p1;
+                *reinterpret_cast<uint32_t *>(out + base + 2 * ps + ox) = p2;
+            }
+        } else {
+            for (int ox = threadIdx.x; ox < W; ox += blockDim.x) {
+                int rr, gg, bb, o_r = 0, o_g = 0, o_b = 0;
+                if (transplant) { o_r = __ldg(orig + base + ox); o_g = __ldg(orig + base + ps + ox); o_b = __ldg(orig + base + 2 * ps + ox); }
+                pixel(ox, o_r, o_g, o_b, rr, gg, bb);
+                out[base + ox] = (uint8_t)rr;
+                out[base + ps + ox] = (uint8_t)gg;
+                out[base + 2 * ps + ox] = (uint8_t)bb;
+            }
         }
         __syncthreads();
     }

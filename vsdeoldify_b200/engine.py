@@ -38,11 +38,14 @@ class DeoldifyEngine:
                  use_graph: bool = True, keep_taps: bool = False, debug_net_out: bool = False,
                  frame_size: Optional[int] = None, sd_other: Optional[Dict[str, torch.Tensor]] = None,
                  video_weight: float = 0.5, zhang: Optional[tuple] = None, merge: Optional[dict] = None,
-                 hue_adjust: str = "none", run_deoldify: bool = True):
+                 hue_adjust: str = "none", run_deoldify: bool = True, ddtweak: Optional[dict] = None):
         """zhang = (name, state_dict): the second colour model of HAVC_colorizer (vs_sc_ddcolor models 2 / 3,
         vsslib/vsmodels.py:339-344), colourising the same S x S frame; hue_adjust: its vs_sc_adjust_clip_hue string
         (vsmodels.py:361-362); merge = dict(method, weight, cmc_p, lmm_p, alm_p, crt_p, invert) for
-        vs_sc_combine_models (mcomb.py:125-192).  run_deoldify=False is method 1 (second model only)."""
+        vs_sc_combine_models (mcomb.py:125-192).  run_deoldify=False is method 1 (second model only).  ddtweak =
+        dict(bright, cont, luma_min, gamma, gamma_luma_min, gamma_alpha, gamma_min): the luma-constrained pre-tweak of the
+        second model's input (vs_sc_tweak + sc_constrained_tweak, vsmodels.py:326-332) followed by vs_recover_clip_luma
+        on its output (vsmodels.py:367-368)."""
         self.lib = _lib.lib()
         self.dev = torch.device(device)
         torch.cuda.set_device(self.dev)
@@ -59,7 +62,7 @@ class DeoldifyEngine:
         self.prog2 = UnetProgram(sd_other, B, S, dtype, device=self.dev, x=self.prog.x) \
             if (sd_other is not None and run_deoldify) else None
         self.zhang = None
-        self.merge, self.hue_adjust = merge, hue_adjust
+        self.merge, self.hue_adjust, self.ddtweak = merge, hue_adjust, ddtweak
         if zhang is not None:
             from .filters import FilterBank
             from .zhang import ZhangColorizer
@@ -124,10 +127,25 @@ class DeoldifyEngine:
                                   B * 3 * S * S, self.video_weight, stream), "blend")
         if self.zhang is not None:
             # second colour model on the same S x S frame, its hue adjustment, then the model merge
-            self.zhang.run(self.rgb_small, self.colored_b, stream)
+            src_b = self.rgb_small
+            if self.ddtweak is not None:                       # pre-tweak of the second model's input
+                t, tmp = self.ddtweak, self.bank.tmp
+                if self.bank.image_tweak(src_b, tmp[0], cont=t["cont"], bright=t["bright"], stream=stream):
+                    self.bank.select_frames(tmp[0], src_b, self.skip, stream)
+                    src_b = tmp[0]
+                self.bank.luma_adjusted_levels(src_b, tmp[1], t["luma_min"], t["gamma"], t["gamma_luma_min"], t["gamma_alpha"],
+                                               t["gamma_min"], stream=stream)
+                self.bank.select_frames(tmp[1], src_b, self.skip, stream)
+                src_b = tmp[1]
+            self.zhang.run(src_b, self.colored_b, stream)
             clipb = self.colored_b
             if self.bank.adjust_hue_range(clipb, self.colored_b2, self.hue_adjust, stream):
                 clipb = self.colored_b2
+            if self.ddtweak is not None:                       # vs_recover_clip_luma(clip, clipb_rgb)
+                other = self.colored_b if clipb is self.colored_b2 else self.colored_b2
+                chk(lib.havc_chroma_post_process(clipb.data_ptr(), self.rgb_small.data_ptr(), other.data_ptr(), B, S, S, stream),
+                    "recover_luma")
+                clipb = other
             self.bank.select_frames(clipb, self.rgb_small, self.skip, stream)        # scene-change gate of the 2nd model
             if not self.run_deoldify:
                 result = clipb

@@ -146,11 +146,24 @@ def HAVC_colorizer(
     if deoldify_sat != 1.0 or deoldify_hue != 0.0 or (method != 0 and (ddcolor_sat != 1.0 or ddcolor_hue != 0.0)):
         _raise("HAVC_colorizer: vs_tweak (sat/hue != identity; a zimg YUV420 round trip) is not built yet")
     ddtweak = list(ddtweak) if isinstance(ddtweak, (list, tuple)) else [bool(ddtweak), False, False]
-    if method != 0 and any(ddtweak[:3]):
-        _raise("HAVC_colorizer: ddtweak (pre-tweak / denoise / retinex of the second model's input) is not built yet")
-    hue_adjust = "none"
-    if method != 0:                                                                       # vsmodels.py:312-336
+    ddtweak = (ddtweak + [False, False, False])[:3]
+    scenechange = not (sc_threshold == 0 and sc_min_freq == 0)                            # :2494
+    hue_adjust, tweak = "none", None
+    if method != 0:                                                                       # vsmodels.py:296-336
+        if ddtweak[1] or ddtweak[2]:
+            _raise("HAVC_colorizer: the denoise / retinex pre-filters of the second model are not built")
+        tw = list(ddtweak_p[0]) if len(ddtweak_p) == 2 else list(ddtweak_p[:8])
         hue_adjust = (ddtweak_p[1] if len(ddtweak_p) == 2 else (ddtweak_p[8] if len(ddtweak_p) > 8 else "none")).lower()
+        if ddtweak[0]:
+            bright, cont, gamma, constrained, luma_min, gamma_luma_min, gamma_alpha, gamma_min = tw[:8]
+            if not constrained:
+                _raise("HAVC_colorizer: ddtweak without luma_constrained_tweak applies gamma through vs_tweak / image_tweak "
+                       "(std.Levels; the reference's image_tweak gamma LUT raises) - not built")
+            if (bright != 0 or cont != 1) and not scenechange:
+                _raise("HAVC_colorizer: ddtweak bright/cont without scene-change detection goes through vs_tweak (zimg YUV420 "
+                       "round trip) - not built")
+            tweak = dict(bright=bright, cont=cont, luma_min=luma_min, gamma=gamma, gamma_luma_min=gamma_luma_min,
+                         gamma_alpha=gamma_alpha, gamma_min=gamma_min)
     if ddcolor_rf == 0:
         ddcolor_rf = min(max(math.trunc(0.4 * clip.width / 16), 16), 32)                  # :2492
     scenechange = not (sc_threshold == 0 and sc_min_freq == 0)                            # :2494
@@ -173,7 +186,7 @@ def HAVC_colorizer(
     try:
         engine = DeoldifyEngine(sd_video, clip.width, clip.height, render_factor=deoldify_rf, frame_size=frame_size,
                                 batch=_BATCH, dtype=_DTYPE, device=dev, sd_other=sd_other, video_weight=weight, zhang=zhang,
-                                merge=merge, hue_adjust=hue_adjust, run_deoldify=run_deoldify)
+                                merge=merge, hue_adjust=hue_adjust, run_deoldify=run_deoldify, ddtweak=tweak)
     except (ValueError, FilterError) as e:
         _raise("HAVC_colorizer: " + str(e))
     fn = _ColorizedClip(clip, engine, scenechange, _BATCH)
@@ -307,10 +320,18 @@ def HAVC_ddeoldify(
                           sc_min_int, sc_tht_white, sc_tht_black, device_index, torch_dir, debug_level)
 
 
-# ---- HAVC_main: preset tables of vsdeoldify/havc_utils.py:335-443 (image-model branch only) -------------------------
+# ---- HAVC_main: preset tables of vsdeoldify/havc_utils.py:335-581 (values, not code) -----------------------------------
 _PRESETS = ['placebo', 'veryslow', 'slower', 'slow', 'medium', 'fast', 'faster', 'veryfast']
 _PRESET_RF = [32, 32, 32, 28, 24, 22, 20, 16]
 _DEOLDIFY_MODELS = ["video", "stable", "artistic"]
+_DDCOLOR_MODELS = ["modelscope", "artistic", "siggraph17", "eccv16"]
+_VIDEO_TUNE = {'verystable': 0.2, 'morestable': 0.3, 'stable': 0.4, 'balanced': 0.5, 'vivid': 0.6, 'morevivid': 0.7, 'veryvivid': 0.8}
+_COMB_METHOD = {'simple': 2, 'constrained-chroma': 3, 'luma-masked': 4, 'adaptive-luma': 5, 'chroma-retention': 6,
+                'chromabound adaptive': 7}
+_COLOR_TUNE = ['none', 'light', 'medium', 'strong']
+_COLOR_FIX = ['none', 'magenta', 'magenta/violet', 'violet', 'violet/red', 'blue/magenta', 'yellow', 'yellow/orange', 'yellow/green',
+              'retinex/red']
+_HUE_FIX = ["none", "270:300", "250:360", "300:330", "300:360", "220:280", "60:90", "30:90", "60:120", "none"]
 
 
 def _get_render_factor(Preset: str) -> int:
@@ -320,24 +341,77 @@ def _get_render_factor(Preset: str) -> int:
         _raise("HAVC_main: Preset choice is invalid for '" + str(Preset) + "'")
 
 
+def _get_color_model(ColorModel: str):
+    """havc_utils._get_color_model (havc_utils.py:402-441) -> (deoldify model, second model, method)."""
+    cm = ColorModel.lower()
+    try:
+        if '+' in cm:
+            a, b = cm.split("+")
+            return _DEOLDIFY_MODELS.index(a), _DDCOLOR_MODELS.index(b), 2
+        if "deoldify" in cm:
+            return _DEOLDIFY_MODELS.index(cm.replace("deoldify", "").replace("(", "").replace(")", "")), 0, 0
+        if "ddcolor" in cm or "zhang" in cm:
+            name = cm.replace("ddcolor", "").replace("zhang", "").replace("(", "").replace(")", "")
+            return 0, _DDCOLOR_MODELS.index(name), 1
+    except ValueError:
+        pass
+    _raise("HAVC_main: ColorModel choice is invalid for '" + ColorModel + "'")
+
+
+def _get_color_tune(ColorTune: str, ColorFix: str, dd_model: int):
+    """The ddtweak / hue-range part of havc_utils._get_color_tune (havc_utils.py:451-517)."""
+    tune = (ColorTune or "none").lower()
+    fix = (ColorFix or "none").lower()
+    if tune not in _COLOR_TUNE:
+        _raise("HAVC_main: ColorTune choice is invalid for '" + tune + "'")
+    if fix not in _COLOR_FIX:
+        _raise("HAVC_main: ColorFix choice is invalid for '" + fix + "'")
+    tn, co = _COLOR_TUNE.index(tune), _COLOR_FIX.index(fix)
+    hue_tune = {0: ["1.0,0.0", "0.7,0.1", "0.5,0.1", "0.2,0.1"], 2: ["1.0,0.0", "0.6,0.1", "0.4,0.2", "0.2,0.1"],
+                3: ["1.0,0.0", "0.7,0.1", "0.6,0.1", "0.3,0.1"]}.get(dd_model, ["1.0,0.0", "0.8,0.1", "0.5,0.1", "0.2,0.1"])
+    dd_tweak = [False, False, False]
+    if tn == 0:
+        return dd_tweak, "none"
+    if co == 0:
+        return [True, True, False], "none"
+    if co == 9:
+        return [True, False, True], _HUE_FIX[4] + "|" + hue_tune[2]
+    return [True, False, False], _HUE_FIX[co] + "|" + hue_tune[tn]
+
+
 def HAVC_main(clip, Preset: str = 'Medium', FrameInterp: int = 0, ColorModel: str = 'Video+Artistic', CombMethod: str = 'Simple',
               VideoTune: str = 'Stable', ColorFix: str = 'Magenta/Violet', ColorTune: str = 'Light', ColorMap: str = 'None',
               ColorTemp: str = 'None', BlackWhiteTune: str = 'None', BlackWhiteMode: int = 0, BlackWhiteBlend: bool = True,
               EnableDeepEx: bool = False, enable_fp16: bool = True, debug_level: int = 0, device_index: int = 0, **kw):
-    """Drop-in for vsdeoldify.HAVC_main (vsdeoldify/__init__.py:101-330) restricted to the per-frame DeOldify
-    branch: ColorModel 'DeOldify(Video|Stable|Artistic)', every post filter at its 'None' setting."""
+    """Drop-in for vsdeoldify.HAVC_main (vsdeoldify/__init__.py:101-330 -> HAVC_main_presets :469-912) restricted to the
+    per-frame image-model branch: the string presets are turned into HAVC_colorizer's numeric arguments exactly as the
+    reference does (colour-model split, CombMethod, VideoTune weight, ColorTune / ColorFix -> ddtweak + hue range).
+    The HAVC_stabilizer step the reference appends (dark / smooth / colormap post filters and their extra chroma-resize
+    round trip; row N1 of the scope table) is NOT applied: a warning is logged.  Exemplar models, DDColor, tiling
+    presets (placebo / veryslow), ColorMap / ColorTemp / BlackWhiteTune raise."""
     rf = _get_render_factor(Preset)
-    cm = ColorModel.lower()
+    speed_id = _PRESETS.index(Preset.lower())
     if EnableDeepEx or FrameInterp != 0:
         _raise("HAVC_main: exemplar-based models are sequential and out of scope of the B200 build")
-    if "deoldify" not in cm or "+" in cm:
-        _raise("HAVC_main: ColorModel '" + ColorModel + "' needs the DDColor/Zhang side, which is not built yet; "
-               "use 'DeOldify(Video)', 'DeOldify(Stable)' or 'DeOldify(Artistic)'")
-    name = cm.replace("deoldify", "").replace("(", "").replace(")", "")
-    if name not in _DEOLDIFY_MODELS:
-        _raise("HAVC_main: ColorModel choice is invalid for '" + ColorModel + "'")
+    if speed_id in (0, 1):
+        _raise("HAVC_main: the tiled 'placebo' / 'veryslow' presets (HAVC_clip_slice) are not built")
+    do_model, dd_model, dd_method = _get_color_model(ColorModel)
+    if dd_method != 0 and dd_model in (0, 1):
+        _raise("HAVC_main: ColorModel '" + ColorModel + "' needs DDColor (external vsddcolor package), which is out of scope of the "
+               "B200 build; use 'DeOldify(...)', '<Video|Stable|Artistic>+Siggraph17', '...+ECCV16' or 'Zhang(...)'")
+    if VideoTune.lower() not in _VIDEO_TUNE:
+        _raise("HAVC_main: VideoTune choice is invalid for '" + VideoTune.lower() + "'")
+    weight = _VIDEO_TUNE[VideoTune.lower()]
+    if dd_method == 2:
+        if CombMethod.lower() not in _COMB_METHOD:
+            _raise("HAVC_main: CombMethod choice is invalid for '" + CombMethod + "'")
+        dd_method = _COMB_METHOD[CombMethod.lower()]
+    dd_tweak, hue_range = _get_color_tune(ColorTune, ColorFix, dd_model)
     for label, v in (("ColorMap", ColorMap), ("ColorTemp", ColorTemp), ("BlackWhiteTune", BlackWhiteTune)):
         if str(v).lower() != "none":
             _raise(f"HAVC_main: {label} post filters are not built yet (HAVC_stabilizer is row N1 of the scope table)")
-    return HAVC_colorizer(clip, method=0, deoldify_p=[_DEOLDIFY_MODELS.index(name), rf, 1.0, 0.0],
-                          ddcolor_p=[1, rf, 1.0, 0.0, enable_fp16], device_index=device_index, debug_level=debug_level)
+    vs.core.log_message(vs.MESSAGE_TYPE_WARNING,
+                        "HAVC_main (B200 build): the HAVC_stabilizer post step of the reference presets is not applied")
+    return HAVC_colorizer(clip, method=dd_method, mweight=weight, deoldify_p=[do_model, rf, 1.0, 0.0],
+                          ddcolor_p=[dd_model, rf, 1.0, 0.0, enable_fp16], ddtweak=dd_tweak, ddtweak_p=[DEF_TWEAK_p, hue_range],
+                          device_index=device_index, debug_level=debug_level)
