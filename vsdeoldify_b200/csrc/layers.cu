@@ -148,32 +148,41 @@ __global__ void affine_act_kernel(const uint4 *__restrict__ in, uint4 *__restric
 
 // ReplicationPad2d((1,0,1,0)) + AvgPool2d(2, stride=1): out[y][x] = mean(in[y-1..y][x-1..x]) with the
 // index clamped at 0 (CustomPixelShuffle_ICNR, unet.py:47-52; PixelShuffle_ICNR, fastai/layers.py:214-220).
+// One thread walks a strip of kBlurRows output rows for a fixed (x, 8-channel group) and keeps the previous input row's two
+// taps in registers, so every output costs two 16-byte loads instead of four.
+static constexpr int kBlurRows = 8;
 __global__ void blur2x2_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, int B, int H, int W, int C8,
                                int out_stride8, int dtype) {
-    const long long total = (long long)B * H * W * C8;
+    const int strips = (H + kBlurRows - 1) / kBlurRows;
+    const long long total = (long long)B * strips * W * C8;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         const int cg = (int)(i % C8);
-        long long pix = i / C8;
-        const int x = (int)(pix % W);
-        const int y = (int)((pix / W) % H);
-        const int b = (int)(pix / ((long long)W * H));
-        const int y0 = y > 0 ? y - 1 : 0, x0 = x > 0 ? x - 1 : 0;
+        long long t = i / C8;
+        const int x = (int)(t % W);
+        t /= W;
+        const int ys = (int)(t % strips) * kBlurRows;
+        const int b = (int)(t / strips);
+        const int x0 = x > 0 ? x - 1 : 0;
         const uint4 *base = in + (long long)b * H * W * C8 + cg;
-        const uint4 v00 = __ldg(base + ((long long)y0 * W + x0) * C8);
-        const uint4 v01 = __ldg(base + ((long long)y0 * W + x) * C8);
-        const uint4 v10 = __ldg(base + ((long long)y * W + x0) * C8);
-        const uint4 v11 = __ldg(base + ((long long)y * W + x) * C8);
-        const uint32_t a[4] = {v00.x, v00.y, v00.z, v00.w}, bq[4] = {v01.x, v01.y, v01.z, v01.w};
-        const uint32_t c[4] = {v10.x, v10.y, v10.z, v10.w}, d[4] = {v11.x, v11.y, v11.z, v11.w};
-        uint32_t o[4];
+        const int yp = ys > 0 ? ys - 1 : 0;
+        uint4 p0 = __ldg(base + ((long long)yp * W + x0) * C8), p1 = __ldg(base + ((long long)yp * W + x) * C8);
+        const int yend = min(ys + kBlurRows, H);
+        for (int y = ys; y < yend; ++y) {
+            const uint4 c0 = __ldg(base + ((long long)y * W + x0) * C8), c1 = __ldg(base + ((long long)y * W + x) * C8);
+            const uint32_t a[4] = {p0.x, p0.y, p0.z, p0.w}, bq[4] = {p1.x, p1.y, p1.z, p1.w};
+            const uint32_t c[4] = {c0.x, c0.y, c0.z, c0.w}, d[4] = {c1.x, c1.y, c1.z, c1.w};
+            uint32_t o[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float2 fa = unpack2(a[j], dtype), fb = unpack2(bq[j], dtype), fc = unpack2(c[j], dtype),
-                         fd = unpack2(d[j], dtype);
-            o[j] = pack2(((fa.x + fb.x) + (fc.x + fd.x)) * 0.25f, ((fa.y + fb.y) + (fc.y + fd.y)) * 0.25f, dtype);
+            for (int j = 0; j < 4; ++j) {
+                const float2 fa = unpack2(a[j], dtype), fb = unpack2(bq[j], dtype), fc = unpack2(c[j], dtype),
+                             fd = unpack2(d[j], dtype);
+                o[j] = pack2(((fa.x + fb.x) + (fc.x + fd.x)) * 0.25f, ((fa.y + fb.y) + (fc.y + fd.y)) * 0.25f, dtype);
+            }
+            out[(((long long)b * H + y) * W + x) * out_stride8 + cg] = make_uint4(o[0], o[1], o[2], o[3]);
+            p0 = c0;
+            p1 = c1;
         }
-        out[pix * out_stride8 + cg] = make_uint4(o[0], o[1], o[2], o[3]);
     }
 }
 
@@ -279,7 +288,7 @@ extern "C" int havc_blur2x2(const void *in, void *out, int B, int H, int W, int 
                             void *stream) {
     HAVC_CHECK_ARG(in && out && in != out && dt16(dtype) && C % 8 == 0 && out_pix_stride % 8 == 0 && out_pix_stride >= C,
                    "havc_blur2x2: bad arguments");
-    const long long n = (long long)B * H * W * (C / 8);
+    const long long n = (long long)B * ((H + kBlurRows - 1) / kBlurRows) * W * (C / 8);
     blur2x2_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const uint4 *)in, (uint4 *)out, B, H, W, C / 8,
                                                                       out_pix_stride / 8, dtype);
     HAVC_LAUNCHED();
