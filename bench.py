@@ -34,6 +34,7 @@ sys.path.insert(0, ROOT)
 
 W1080, H1080, RF = 1920, 1080, 24
 GFLOP_PER_FRAME_SURVEY = 639.0
+WORKLOAD = "DeOldify video rf=24 (ResNet-101 DynamicUnetWide @384x384), HAVC_colorizer(method=0), synthetic 1080p grayscale clip"
 
 
 def synth_clip(n: int, h: int, w: int, seed: int = 0) -> np.ndarray:
@@ -99,6 +100,16 @@ def load_peaks():
     return dict(tf_sustained=1400.0, tf_burst=1590.0, hbm=6650.0, src="fallback")
 
 
+def load_traffic(batch: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant conv_gemm launch (res.conv0) from the
+    committed `ncu --set full` capture (profiles/r01_roofline_traffic.json), scaled linearly to this batch."""
+    p = os.path.join(ROOT, "profiles", "r01_roofline_traffic.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    return d["dram_bytes_per_launch"] * batch / d["batch"]
+
+
 def cpu_reference_fps(n_frames: int, threads: int, h: int = H1080, w: int = W1080, rf: int = RF, seed: int = 1234):
     """The CPU restatement of the reference path (oracle/pipeline_oracle.py), end to end per frame."""
     from oracle import pipeline_oracle, synth_weights
@@ -135,8 +146,8 @@ def run_reference(args):
         "impl": "reference", "metric": "1080p colorized frames/s", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "DeOldify video rf=24, HAVC_colorizer(method=0), synthetic 1080p grayscale clip",
-                   "frames_per_step": 1, "weights": "synthetic seed 1234"},
+        "config": {"workload": WORKLOAD, "frames_per_step": 1, "weights": "synthetic seed 1234 (reference state-dict schema)",
+                   "sample": "each step = 1 frame of the clip on the host cores (bounded sample of the same workload)"},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
                          "sample": f"{args.steps} frames of the 1080p clip, 1 frame per step, torch CPU fp32 oracle port of the reference path"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -148,10 +159,11 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=12)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("HAVC_BENCH_BATCH", "8")))
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("HAVC_BENCH_BATCH", "32")),
+                    help="frames per step and per CUDA-graph launch (32 frames = 16 GB of activations of the 180 GB)")
     ap.add_argument("--dtype", default=os.environ.get("HAVC_BENCH_DTYPE", "fp16"), choices=["fp16", "bf16"])
     ap.add_argument("--cpu-frames", type=int, default=4, help="frames of the bounded CPU-baseline sample (0 = skip)")
     ap.add_argument("--no-graph", action="store_true")
@@ -263,7 +275,7 @@ def main():
         peaks = load_peaks()
         ach = gemm_flops / (gemm_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM)", "achieved": ach,
-                "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sustained"], "traffic": None,
+                "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sustained"], "traffic": load_traffic(B),
                 "peak_source": f"{peaks['src']} sustained bf16 (kernel timed inside a long step)",
                 "launches_per_step": n_gemm, "avg_launch_ms": gemm_ms / max(n_gemm, 1),
                 "algorithmic_gflop_per_frame": gemm_flops / B / 1e9}
@@ -288,7 +300,7 @@ def main():
             "metric": "1080p colorized frames/s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16" if dtype == torch.float16 else "bf16", "data": "synthetic",
-            "config": {"workload": "DeOldify video rf=24 (ResNet-101 DynamicUnetWide @384x384), HAVC_colorizer(method=0), synthetic 1080p grayscale clip",
+            "config": {"workload": WORKLOAD,
                        "frames_per_step": B, "weights": "synthetic seed 1234 (reference state-dict schema)",
                        "cache": "inputs+activations per step (>1 GB) exceed the 126 MB L2; 4 distinct input batches rotated",
                        "partition": "contiguous frame blocks per rank, no collective"},

@@ -44,6 +44,50 @@ __global__ void resample_h_kernel(const uint8_t *__restrict__ in, float *__restr
     }
 }
 
+// Horizontal pass, register-resident weights: one thread per OUTPUT COLUMN keeps its kMaxT weights in registers and walks
+// the rows of its block, so the inner loop is one shared-memory load + one FMA per tap (the table is read once per block
+// instead of once per row).  Rows are double-buffered in shared memory: row r+1 is staged while row r is computed.
+template <int kMaxT>
+__global__ void resample_h_regw_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, long long rows, int Win,
+                                       int Wout, const int *__restrict__ start, const float *__restrict__ wts, int T) {
+    extern __shared__ float srow[];          // [2][Win + kMaxT]; the kMaxT floats behind each row stay zero
+    const int rowlen = Win + kMaxT;
+    for (int i = threadIdx.x; i < 2 * kMaxT; i += blockDim.x) srow[(i / kMaxT) * rowlen + Win + (i % kMaxT)] = 0.f;
+    const int ox = threadIdx.x;
+    const bool active = ox < Wout;
+    float w[kMaxT];
+    int s0 = 0;
+    if (active) s0 = __ldg(start + ox);
+#pragma unroll
+    for (int t = 0; t < kMaxT; ++t) w[t] = (active && t < T) ? __ldg(wts + (long long)t * Wout + ox) : 0.f;
+    // taps t >= T carry zero weights and read either real pixels or the zero pad behind the row
+    auto stage = [&](long long row, float *dst) {
+        const uint8_t *src = in + row * Win;
+        for (int i = threadIdx.x; i < Win / 4; i += blockDim.x) {
+            const uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(src) + i);
+            reinterpret_cast<float4 *>(dst)[i] = make_float4((float)(v & 0xff), (float)((v >> 8) & 0xff), (float)((v >> 16) & 0xff),
+                                                             (float)(v >> 24));
+        }
+    };
+    const long long r0 = blockIdx.x;
+    if (r0 < rows) stage(r0, srow);
+    __syncthreads();
+    int buf = 0;
+    for (long long row = r0; row < rows; row += gridDim.x) {
+        const long long nxt = row + gridDim.x;
+        if (nxt < rows) stage(nxt, srow + (buf ^ 1) * rowlen);
+        if (active) {
+            const float *sp = srow + buf * rowlen + s0;
+            float acc = 0.f;
+#pragma unroll
+            for (int t = 0; t < kMaxT; ++t) acc = fmaf(w[t], sp[t], acc);
+            out[row * Wout + ox] = acc;
+        }
+        __syncthreads();
+        buf ^= 1;
+    }
+}
+
 // Vertical pass on u8 planes: out[plane][oy][x] = sum_t w[oy][t] * in[plane][start[oy]+t][x]  (float out).
 __global__ void resample_v_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, long long planes, int Hin,
                                   int Hout, int W, const int *__restrict__ start, const float *__restrict__ wts, int T) {
@@ -330,6 +374,27 @@ extern "C" int havc_resample_h(const uint8_t *in, float *out, long long rows, in
                                const float *weights, int taps, void *stream) {
     HAVC_CHECK_ARG(in && out && start && weights && taps > 0, "havc_resample_h: bad arguments");
     HAVC_CHECK_ARG(Win * sizeof(float) <= 96 * 1024, "havc_resample_h: row too wide for shared memory");
+    if (Wout <= 512 && taps <= 48 && (Win & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 3) == 0 && 2 * (Win + 48) * sizeof(float) <= 96 * 1024) {
+        static bool attr2 = false;
+        if (!attr2) {
+            HAVC_CHECK_CUDA(cudaFuncSetAttribute(resample_h_regw_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            HAVC_CHECK_CUDA(cudaFuncSetAttribute(resample_h_regw_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            HAVC_CHECK_CUDA(cudaFuncSetAttribute(resample_h_regw_kernel<40>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            HAVC_CHECK_CUDA(cudaFuncSetAttribute(resample_h_regw_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            attr2 = true;
+        }
+        const int block = ((Wout + 31) / 32) * 32;
+        long long g2 = rows < (long long)num_sms() * 4 ? rows : (long long)num_sms() * 4;
+        const int kt = taps <= 8 ? 8 : (taps <= 24 ? 24 : (taps <= 40 ? 40 : 48));
+        const size_t sm = 2 * (size_t)(Win + kt) * sizeof(float);
+        cudaStream_t st = (cudaStream_t)stream;
+        if (kt == 8) resample_h_regw_kernel<8><<<(int)g2, block, sm, st>>>(in, out, rows, Win, Wout, start, weights, taps);
+        else if (kt == 24) resample_h_regw_kernel<24><<<(int)g2, block, sm, st>>>(in, out, rows, Win, Wout, start, weights, taps);
+        else if (kt == 40) resample_h_regw_kernel<40><<<(int)g2, block, sm, st>>>(in, out, rows, Win, Wout, start, weights, taps);
+        else resample_h_regw_kernel<48><<<(int)g2, block, sm, st>>>(in, out, rows, Win, Wout, start, weights, taps);
+        HAVC_LAUNCHED();
+        return HAVC_OK;
+    }
     static bool attr = false;
     if (!attr) {
         HAVC_CHECK_CUDA(cudaFuncSetAttribute(resample_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
