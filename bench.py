@@ -7,8 +7,9 @@ reference state-dict schema).  A "step" = one batch of B frames through
    Spline64 squeeze -> network -> S x S luma transplant -> Spline64 back -> full-res luma transplant.
 
   value   : frames/s with the input batches already resident in HBM (CUDA-graph replays, CUDA events)
-  e2e     : frames/s through the engine's public host API (pinned H2D of every input frame and D2H of every
-            output frame inside the timed region, copies overlapped with compute on separate streams)
+  e2e     : frames/s through the engine's public host API: inputs in pinned HOST memory, H2D of every input frame and D2H
+            of every output frame into pinned host memory inside the timed region (copies overlap compute on separate
+            streams), the host touches every result batch
   roofline: the tcgen05 implicit-GEMM kernel (the dominant kernel): algorithmic conv/attention FLOPs of its
             launches / the summed CUDA-event durations of those launches, vs the measured sustained bf16 peak
   cpu_baseline / --impl reference: the CPU restatement of the reference path (oracle/, torch fp32 on all host
@@ -202,6 +203,7 @@ def main():
     clip = synth_clip(n_host_batches * B, H1080, W1080, seed=100 + rank)
     host_batches = [np.ascontiguousarray(clip[i * B:(i + 1) * B]) for i in range(n_host_batches)]
     dev_batches = [torch.from_numpy(b).to(dev) for b in host_batches]
+    pinned_batches = [torch.from_numpy(b).pin_memory() for b in host_batches]   # e2e inputs live in pinned host memory
 
     def barrier():
         torch.cuda.synchronize()
@@ -240,10 +242,10 @@ def main():
         sink["n"] += out.shape[0]
         sink["sum"] += int(out[0, 0, 0, 0])     # touch the result on the host
 
-    eng.colorize_stream((host_batches[i % n_host_batches] for i in range(Wm)), on_result)
+    eng.colorize_stream((pinned_batches[i % n_host_batches] for i in range(Wm)), on_result)
     barrier()
     t0 = time.perf_counter()
-    eng.colorize_stream((host_batches[i % n_host_batches] for i in range(K)), on_result)
+    eng.colorize_stream((pinned_batches[i % n_host_batches] for i in range(K)), on_result)
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
     te = torch.tensor([t_e2e], device=dev)

@@ -521,3 +521,81 @@ def luma_adjusted_levels(img: np.ndarray, luma_min: float = 0, gamma: float = 1.
     out = yuv.copy().clip(i_min, i_max)
     out[..., 0] = y_new
     return cv_yuv2rgb(out)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# HAVC_stabilizer per-frame stages: vs_dark_tweak, vs_chroma_bright_tweak, vs_colormap
+# ---------------------------------------------------------------------------------------------------------
+def np_image_chroma_tweak(img: np.ndarray, sat: float = 1, bright: float = 0, hue: int = 0, hue_adjust: str = "none") -> np.ndarray:
+    """restcolor.py:288-342: cv HSV hue add / S scale / V scale, then (optionally) the "chroma adjustment" stage whose
+    mask is taken from the hue AFTER the first stage and whose unmasked pixels come from the ORIGINAL image."""
+    hsv = cv_rgb2hsv(img)
+    hsv[..., 0] = np_hue_add(hsv[..., 0], hue)
+    hsv[..., 1] = _scale_u8(hsv[..., 1], min(max(sat, 0), 10))
+    hsv[..., 2] = _scale_u8(hsv[..., 2], min(max(1 + bright, 0), 10))
+    color = cv_hsv2rgb(hsv)
+    if hue_adjust in ("none", ""):
+        return color
+    p = parse_hue_adjust(hue_adjust)
+    if p is None:
+        return color
+    hue_range, sat2, hue2, weight = p
+    g = cv_rgb2hsv(color)
+    if hue2 != 0:
+        g[..., 0] = np_hue_add(g[..., 0], hue2)
+    if sat2 != 1:
+        g[..., 1] = _scale_u8(g[..., 1], min(max(sat2, 0), 10))
+    gray_rgb = cv_hsv2rgb(g)
+    out = mask_select(img, gray_rgb, hue_mask(hsv[..., 0], hue_range))
+    if weight > 0:
+        out = np_weighted_merge(out, gray_rgb if hue2 == 0 else img, weight)
+    if weight < 0:
+        out = np_weighted_merge(out, img, -weight)
+    return out
+
+
+def image_chroma_tweak(img, sat=1, bright=0, hue=0, hue_adjust="none"):
+    """imfilters.py:540-550."""
+    if sat == 1 and bright == 0 and hue == 0 and hue_adjust == "none":
+        return img
+    return np_image_chroma_tweak(img, sat, bright, hue, hue_adjust)
+
+
+def _luma_merge(img_dark, img_white, lo, hi):
+    return image_luma_merge(img_dark, img_white, lo) if lo == hi else w_image_luma_merge(img_dark, img_white, lo, hi)
+
+
+def dark_tweak(img: np.ndarray, dark_threshold: float = 0.3, dark_amount: float = 0.8, dark_hue_adjust: str = "none") -> np.ndarray:
+    """vs_sc_dark_tweak.merge_frame (vsfilters.py:604-636)."""
+    d_threshold = 0.1
+    d_white = min(max(dark_threshold, d_threshold), 0.50)
+    d_sat = min(max(1.1 - dark_amount, 0.10), 0.80)
+    d_bright = -min(max(dark_amount, 0.20), 0.90)
+    img2 = image_tweak(img, bright=d_bright, sat=d_sat, hue_range=dark_hue_adjust)
+    return _luma_merge(img2, img, d_threshold, d_white)
+
+
+def chroma_bright_tweak(img: np.ndarray, black_threshold=0.3, white_threshold=0.6, dark_sat=0.8, dark_bright=-0.10,
+                        chroma_adjust: str = "none") -> np.ndarray:
+    """vs_sc_chroma_bright_tweak.merge_frame (vsfilters.py:525-552)."""
+    img2 = image_chroma_tweak(img, bright=dark_bright, sat=dark_sat, hue_adjust=chroma_adjust)
+    return _luma_merge(img2, img, black_threshold, white_threshold)
+
+
+def colormap(img: np.ndarray, colormap_adjust: str) -> np.ndarray:
+    """_vs_sc_colormap.merge_frame (vsfilters.py:577-590)."""
+    return image_chroma_tweak(img, hue_adjust=colormap_adjust)
+
+
+def stabilizer_stages(img: np.ndarray, dark=False, dark_p=(0.2, 0.8), smooth=False, smooth_p=(0.3, 0.7, 0.9, 0.0, "none"),
+                      colormap_adjust: str = "none") -> np.ndarray:
+    """The per-frame stages of HAVC_stabilizer on the squeezed frame (vsdeoldify/__init__.py:2823-2861), stab=False."""
+    out = img
+    if dark:
+        out = dark_tweak(out, dark_p[0], dark_p[1], (dark_p[2] if len(dark_p) > 2 else "none").lower())
+    if smooth:
+        out = chroma_bright_tweak(out, smooth_p[0], smooth_p[1], smooth_p[2], -smooth_p[3],
+                                  (smooth_p[4] if len(smooth_p) > 4 else "none").lower())
+    if colormap_adjust not in ("none", ""):
+        out = colormap(out, colormap_adjust)
+    return out

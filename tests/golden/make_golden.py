@@ -184,10 +184,38 @@ def golden_zhang():
         print(name, "golden: ab mean/std/min/max", float(y.mean()), float(y.std()), float(y.min()), float(y.max()))
 
 
+def golden_stabilizer():
+    """Per-frame stages of HAVC_stabilizer (vs_dark_tweak, vs_chroma_bright_tweak, vs_colormap) run through the REAL
+    reference selectors on clips of the VapourSynth stand-in."""
+    refshim.install()
+    from vsdeoldify_b200 import vs_shim
+    sys.modules["vapoursynth"] = vs_shim
+    from vsdeoldify.vsslib import vsfilters
+    from vsdeoldify import havc_utils
+    out = {}
+    H, W = 48, 72
+    for li, luma in enumerate((0.08, 0.3, 0.6)):
+        a, _ = filter_test_pair(80 + li, H, W, luma)
+        out[f"img_{li}"] = a
+        clip = vs_shim.array_clip(np.ascontiguousarray(np.transpose(a, (2, 0, 1)))[None])
+        get = lambda c: np.dstack([np.asarray(c.get_frame(0)[p]) for p in range(3)])
+        out[f"dark_{li}"] = get(vsfilters.vs_dark_tweak(clip, dark_threshold=0.2, dark_amount=0.8))
+        out[f"dark_hue_{li}"] = get(vsfilters.vs_dark_tweak(clip, dark_threshold=0.35, dark_amount=0.5, dark_hue_adjust="0:60,300:360"))
+        out[f"smooth_{li}"] = get(vsfilters.vs_chroma_bright_tweak(clip, black_threshold=0.3, white_threshold=0.7, dark_sat=0.9, dark_bright=-0.0))
+        out[f"smooth_adj_{li}"] = get(vsfilters.vs_chroma_bright_tweak(clip, black_threshold=0.25, white_threshold=0.25, dark_sat=0.7,
+                                                                       dark_bright=-0.15, chroma_adjust="180:280|0.5,0.2"))
+        for name in ("blue->brown", "red->blue", "yellow->rose"):
+            adj = havc_utils._get_colormap(name)
+            out[f"colormap_{name}_{li}"] = get(vsfilters.vs_colormap(clip, colormap=adj))
+    np.savez_compressed(os.path.join(HERE, "vsslib_stabilizer.npz"), **out)
+    print("stabilizer golden:", len(out), "arrays")
+
+
 if __name__ == "__main__":
     golden_unets()
     golden_pixels()
     golden_filters()
     golden_zhang()
+    golden_stabilizer()
     golden_render()
     print("golden fixtures written to", HERE)

@@ -209,7 +209,8 @@ class DeoldifyEngine:
 
     # ---- pipelined API (bench e2e / clip rendering) ----------------------------------------------------
     def colorize_stream(self, batches, on_result):
-        """batches: iterable of uint8 [B,3,H,W] host arrays (a full batch each); on_result(i, out) is called
+        """batches: iterable of uint8 [B,3,H,W] host arrays or (pinned) torch tensors (a full batch each); pinned tensors
+        are copied to the device directly and must stay untouched until their result is delivered; on_result(i, out) is called
         in order with a view of the pinned output buffer (valid until the next-but-one call).
         H2D of batch i+1 and D2H of batch i-1 overlap the compute of batch i."""
         ev_in = [torch.cuda.Event() for _ in range(self.n_slots)]
@@ -224,11 +225,15 @@ class DeoldifyEngine:
                 j, sj = pending.pop(0)
                 ev_out[sj].synchronize()
                 on_result(j, self.h_out[sj].numpy())
-            self.h_in[s].copy_(torch.from_numpy(fr) if isinstance(fr, np.ndarray) else fr)
+            if isinstance(fr, torch.Tensor) and fr.is_pinned():
+                src = fr                                   # caller-owned pinned memory: DMA straight from it
+            else:                                          # pageable input: stage through our pinned buffer
+                self.h_in[s].copy_(torch.from_numpy(fr) if isinstance(fr, np.ndarray) else fr)
+                src = self.h_in[s]
             with torch.cuda.stream(self.copy_in):
                 if ev_free[s] is not None:
                     self.copy_in.wait_event(ev_free[s])   # previous compute on this slot has consumed d_in
-                self.d_in[s].copy_(self.h_in[s], non_blocking=True)
+                self.d_in[s].copy_(src, non_blocking=True)
                 ev_in[s].record(self.copy_in)
             self.compute.wait_event(ev_in[s])
             self.compute.wait_event(ev_out[s]) if i >= self.n_slots else None

@@ -109,7 +109,7 @@ class _Std:
 
     def ModifyFrame(self, clip=None, clips=None, selector=None):
         base = self._c(clip)
-        srcs = list(clips) if clips is not None else [base]
+        srcs = ([clips] if isinstance(clips, VideoNode) else list(clips)) if clips is not None else [base]
 
         def fn(n):
             fs = [c.get_frame(n) for c in srcs]
