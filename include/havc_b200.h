@@ -101,6 +101,9 @@ typedef struct {
     int32_t tma_store;
     /* relu1 becomes LeakyReLU(leaky1) when leaky1 > 0 (siggraph17.py:98 `nn.LeakyReLU(negative_slope=.2)`); 0 = ReLU. */
     float leaky1;
+    /* CTA pairs: two SMs of a cluster share one 256-pixel M tile pair through tcgen05.mma.cta_group::2, each loading half of
+     * the weight rows (halves the dominant L2 -> SM operand traffic).  0 = library default (on), 1 = force, -1 = off.   */
+    int32_t pair;
 } havc_conv_desc;
 
 const char *havc_last_error(void);
@@ -221,6 +224,15 @@ int havc_restore_color_gradient(const uint8_t *color, const uint8_t *gray, uint8
 /* adjust_chroma (restcolor.py:239-286) behind adjust_hue_range / vs_sc_adjust_clip_hue (vsfilters.py:435-455). */
 int havc_adjust_chroma(const uint8_t *img, uint8_t *out, int B, int H, int W, const havc_hue_ranges *ranges, double sat, int hue,
                        double weight, int simd_width, void *stream);
+/* np_image_chroma_tweak (restcolor.py:288-342): cv2 HSV hue add / S scale / V scale and, when `ranges` != NULL, the
+ * "chroma adjustment" stage (mask from the tweaked hue, unmasked pixels from the original image, weight blend), optionally
+ * fused with the luma merge that follows it in vs_sc_chroma_bright_tweak (vsfilters.py:525-552): luma_merge != 0 ->
+ * out = image_luma_merge / w_image_luma_merge(img_dark = tweaked, img_white = img, luma_limit, white_limit)
+ * (imfilters.py:66-100).  luma_merge == 0 with ranges is _vs_sc_colormap (vsfilters.py:577-590).  These are the `smooth` and
+ * `colormap` stages of HAVC_stabilizer (vsdeoldify/__init__.py:2852-2858). */
+int havc_chroma_tweak(const uint8_t *img, uint8_t *out, int B, int H, int W, double sat, double bright, int hue,
+                      const havc_hue_ranges *ranges, double sat2, int hue2, double weight, int luma_merge, double luma_limit,
+                      double white_limit, int simd_width, void *stream);
 /* image_tweak (imfilters.py:463-504) without gamma / hue (gamma raises in the reference, see oracle/filters_oracle.py):
  * ImageEnhance Brightness -> Contrast -> Color, optionally restricted to hue ranges of the input.  stats_scratch
  * (2*B u64) is needed when cont != 1. */

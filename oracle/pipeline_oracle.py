@@ -77,6 +77,19 @@ def havc_colorizer_frame(sd, frame: np.ndarray, render_factor: int = 24, kernel:
     return out
 
 
+def havc_stabilizer_frame(frame: np.ndarray, dark=False, dark_p=(0.2, 0.8), smooth=False, smooth_p=(0.3, 0.7, 0.9, 0.0, "none"),
+                          colormap_adjust: str = "none", render_factor: int = 24, kernel: str = "spline64") -> np.ndarray:
+    """HAVC_stabilizer with stab=False on one frame (vsdeoldify/__init__.py:2792-2871): Spline64 squeeze to
+    min(render_factor*16, W) squared, vs_dark_tweak / vs_chroma_bright_tweak / vs_colormap, _clip_chroma_resize."""
+    from . import filters_oracle as fo
+    H, W = frame.shape[:2]
+    S = min(render_factor * 16, W)
+    small = px.resize_plane_u8(frame, S, S, kernel)
+    colored = fo.stabilizer_stages(small, dark, dark_p, smooth, smooth_p, colormap_adjust)
+    up = px.resize_plane_u8(colored, W, H, kernel)
+    return px.chroma_post_process(up, frame)
+
+
 def colorizer_filter(sd, img: np.ndarray, render_factor: int) -> np.ndarray:
     """MasterFilter([ColorizerFilter]).filter(img, img, rf) (deoldify/filters.py:81-124) on a uint8 [H,W,3] image:
     Pillow-BILINEAR squeeze to S x S, network, Pillow-BILINEAR back, luma transplant.  This is the path

@@ -34,7 +34,7 @@ def _check(got, ref, dtype, what=""):
 
 
 def _run_conv(B, H, W, cins, Cout, ks, dtype, *, bias=False, relu1=False, affine=False, residual=False, relu2=False,
-              shuffle=False, dilation=1, bn=None, box=None):
+              shuffle=False, dilation=1, bn=None, box=None, pair=0):
     from vsdeoldify_b200 import ops
     _setup()
     dev = "cuda"
@@ -87,7 +87,7 @@ def _run_conv(B, H, W, cins, Cout, ks, dtype, *, bias=False, relu1=False, affine
     op = ops.make_conv(srcs[0], wp, out, ops.taps_for(ks, dilation), src1=srcs[1] if len(srcs) > 1 else None,
                        w_c1_off=meta["c1_off"], n_total=n_total, bn=bn, box=box,
                        bias=pc(bvec, 0.0), scale=pc(svec, 1.0), shift=pc(tvec, 0.0),
-                       relu1=relu1, relu2=relu2, residual=rs, shuffle=shuffle, group_n=meta.get("group_n", 0))
+                       relu1=relu1, relu2=relu2, residual=rs, shuffle=shuffle, group_n=meta.get("group_n", 0), pair=pair)
     op.launch()
     torch.cuda.synchronize()
     cvalid = Cout // 4 if shuffle else Cout
@@ -212,3 +212,47 @@ def test_conv3x3_c64_large_map():
 
 def test_conv3x3_c64_medium_map():
     _run_conv(2, 128, 128, [64], 64, 3, torch.float16, bias=True, relu1=True, affine=True)
+
+
+# ---- CTA pairs (tcgen05.mma.cta_group::2): forced on (the library's own policy only pairs long launches) ------------------
+@pytest.mark.parametrize("pair", [1, -1])
+def test_pair_conv3x3_many_tiles(pair):
+    _run_conv(4, 96, 96, [256], 512, 3, torch.float16, relu1=True, affine=True, pair=pair)
+
+
+def test_pair_cout259_bn272_staggered_two_part_mma():
+    # BN = 272 = 144 + 128: two cta_group::2 MMAs per K step, 72 + 64 weight rows per CTA, staggered accumulators
+    _run_conv(2, 32, 32, [256, 3], 259, 3, torch.float16, bias=True, relu1=True, pair=1)
+    _run_conv(3, 40, 24, [256, 3], 259, 3, torch.bfloat16, bias=True, relu1=True, residual=True, pair=1)
+
+
+def test_pair_odd_tile_count_and_ragged_edges():
+    # 3*20*20 = 1200 pixels -> 10 M tiles of a 20x... box grid with clipped edges; odd counts leave the peer CTA an empty tile
+    _run_conv(3, 20, 20, [64], 64, 3, torch.float16, bias=True, relu1=True, pair=1)
+    _run_conv(1, 24, 40, [128], 128, 3, torch.float16, residual=True, relu2=True, pair=1)
+    _run_conv(5, 12, 12, [128], 512, 3, torch.float16, relu1=True, affine=True, pair=1)
+
+
+def test_pair_shuffle_and_residual_fast_epilogue():
+    _run_conv(2, 24, 24, [128], 256, 1, torch.float16, bias=True, relu1=True, shuffle=True, pair=1)
+    _run_conv(2, 48, 48, [64], 256, 1, torch.float16, bias=True, residual=True, relu2=True, pair=1)
+    _run_conv(2, 64, 64, [64], 64, 3, torch.float16, bias=True, relu1=True, affine=True, pair=1)
+
+
+def test_pair_batched_gemm_same_batch_only():
+    """b_batched GEMMs pair only when both M tiles of a pair lie in the same batch (2 tiles per batch here)."""
+    from vsdeoldify_b200 import ops
+    _setup()
+    dev = "cuda"
+    B, N, d = 3, 256, 64
+    f = torch.randn(B, N, d, device=dev).half()
+    g = torch.randn(B, N, d, device=dev).half()
+    ref = torch.bmm(g.float(), f.float().transpose(1, 2))
+    for pair in (1, -1):
+        out = torch.zeros(B, 1, N, N, device=dev, dtype=torch.float32)
+        op = ops.make_conv(g.view(B, 1, N, d), f.view(B, N, 1, d), out, [(0, 0, 0, 0)], n_total=N, b_batched=True,
+                           out_space=(B, 1, N), pair=pair)
+        op.launch()
+        torch.cuda.synchronize()
+        err = (out.view(B, N, N) - ref).abs().max().item()
+        assert err < 1e-3, (pair, err)

@@ -156,3 +156,51 @@ def test_havc_merge_surface():
             same(to_hwc(f), want, f"HAVC_merge method {method} frame {i}")
     with pytest.raises(vs_shim.Error):
         havc.HAVC_merge(ca, cb, method=9).get_frame(0) if False else havc.HAVC_merge(ca, cb, method=9)
+
+
+# ---- HAVC_stabilizer per-frame stages (vs_dark_tweak, vs_chroma_bright_tweak, vs_colormap) ---------------------------------
+GS = np.load(os.path.join(os.path.dirname(__file__), "golden", "vsslib_stabilizer.npz"))
+
+
+@pytest.fixture(scope="module")
+def sbank():
+    from vsdeoldify_b200.filters import FilterBank
+    H, W = GS["img_0"].shape[:2]
+    return FilterBank(3, H, W, "cuda:0")
+
+
+def test_stabilizer_stages_vs_reference_golden(sbank):
+    imgs = [GS[f"img_{i}"] for i in range(3)]
+    t = planar(imgs)
+    out = torch.empty_like(t)
+
+    def run(key, **kw):
+        assert sbank.stabilizer_stages(t, out, **kw)
+        torch.cuda.synchronize()
+        for li, r in enumerate(hwc(out)):
+            same(r, GS[f"{key}_{li}"], f"{key} frame {li}")
+    run("dark", dark=True, dark_p=[0.2, 0.8])
+    run("dark_hue", dark=True, dark_p=[0.35, 0.5, "0:60,300:360"])
+    run("smooth", smooth=True, smooth_p=[0.3, 0.7, 0.9, 0.0, "none"])
+    run("smooth_adj", smooth=True, smooth_p=[0.25, 0.25, 0.7, 0.15, "180:280|0.5,0.2"])
+    for name, adj in (("blue->brown", "180:280|+140,0.90"), ("red->blue", "300:360|+260,0.90"), ("yellow->rose", "30:90|+300,0.90")):
+        run("colormap_" + name, colormap_adjust=adj)
+
+
+def test_stabilizer_chain_vs_oracle(sbank):
+    """All three stages chained in the reference's order, incl. identity tweaks that still run the float luma merge."""
+    imgs = [GS[f"img_{i}"] for i in range(3)]
+    t = planar(imgs)
+    out = torch.empty_like(t)
+    cases = [dict(dark=True, dark_p=(0.2, 0.8), smooth=True, smooth_p=(0.3, 0.7, 0.9, 0.0, "none"), colormap_adjust="320:360|+50,0.80"),
+             dict(dark=True, dark_p=(0.45, 0.3, "yellow,red"), smooth=True, smooth_p=(0.2, 0.6, 0.6, 0.2, "30:90|+300,0.5")),
+             dict(smooth=True, smooth_p=(0.3, 0.7, 1.0, 0.0, "none")),                   # identity tweak, luma merge only
+             dict(smooth=True, smooth_p=(0.0, 0.0, 0.5, 0.1, "none")),                   # threshold 0: mask = luma
+             dict(smooth=True, smooth_p=(0.6, 0.3, 0.5, 0.1, "300:360,0:20|0.4,-0.3")),  # dark > white: img_dark everywhere
+             dict(colormap_adjust="80:180|1.6,0.25")]
+    for kw in cases:
+        assert sbank.stabilizer_stages(t, out, **kw)
+        torch.cuda.synchronize()
+        for li, r in enumerate(hwc(out)):
+            same(r, fo.stabilizer_stages(imgs[li], **kw), f"{kw} frame {li}")
+    assert not sbank.stabilizer_stages(t, out)            # nothing enabled: identity, `out` untouched

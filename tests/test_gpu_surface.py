@@ -70,15 +70,55 @@ def test_scenechange_gating():
 
 
 def test_havc_main_preset_path():
-    """HAVC_main(Preset='VeryFast', ColorModel='DeOldify(Video)') == HAVC_colorizer(method=0, rf=16)."""
+    """HAVC_main(Preset='VeryFast', ColorModel='DeOldify(Video)') == HAVC_colorizer(method=0, rf=16) followed by the preset's
+    HAVC_stabilizer step (fast presets: colormap only, vsdeoldify/__init__.py:896-897)."""
     havc = _register()
     clip, fr, props = _clip(2, 144, 256, seed=170)
-    a = havc.HAVC_main(clip, Preset="VeryFast", ColorModel="DeOldify(Video)")
-    b = havc.HAVC_deoldify(clip, model=0, render_factor=16, ddcolor_p=[1, 16, 1.0, 0.0, True])
+    a = havc.HAVC_main(clip, Preset="VeryFast", ColorModel="DeOldify(Video)", ColorMap="red->brown")
+    b = havc.HAVC_stabilizer(havc.HAVC_deoldify(clip, model=0, render_factor=16, ddcolor_p=[1, 16, 1.0, 0.0, True]),
+                             colormap="320:360|+50,0.90")
     for i in range(2):
         fa, fb = a.get_frame(i), b.get_frame(i)
         assert all(np.array_equal(np.asarray(fa[p]), np.asarray(fb[p])) for p in range(3))
         assert fa.props == props[i]
+
+
+def _near(img, ref, what):
+    """integer pixel math is exact; the two float resampling passes may differ in the last bit before rounding"""
+    d = np.abs(img.astype(int) - ref.astype(int))
+    assert d.max() <= 2 and (d > 0).mean() < 0.02, (what, int(d.max()), float((d > 0).mean()))
+
+
+def test_stabilizer_clip_vs_oracle():
+    """HAVC_stabilizer (per-frame stages) on a colour clip against the CPU restatement of the whole path; props pass through."""
+    from oracle import pipeline_oracle
+    from vsdeoldify_b200 import havc, vs_shim
+    H, W, n = 120, 272, 3                        # rf 16 -> 256 x 256 working size (W >= 256)
+
+    def colour_frame(seed, luma):                # smooth gradients + saturated 8x8 patches of every hue + a gray band
+        rng = np.random.default_rng(seed)
+        yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+        base = np.stack([0.5 + 0.5 * np.sin(xx / (9 + 3 * c) + yy / (17 - 2 * c) + c) for c in range(3)], -1)
+        patch = np.kron(rng.uniform(0, 1, (H // 8 + 1, W // 8 + 1, 3)).astype(np.float32), np.ones((8, 8, 1), np.float32))[:H, :W]
+        img = 0.6 * base + 0.4 * patch
+        img[: H // 6] = img[: H // 6].mean(-1, keepdims=True)
+        return (np.clip(img * (luma / img.mean()), 0, 1) * 255).astype(np.uint8)
+    fr = np.stack([np.transpose(colour_frame(300 + i, luma), (2, 0, 1)) for i, luma in enumerate((0.1, 0.35, 0.7))])
+    props = [{"_SceneChangePrev": int(i == 0), "idx": i} for i in range(n)]
+    clip = vs_shim.array_clip(np.ascontiguousarray(fr), props=props)
+    cases = [dict(dark=True, dark_p=[0.2, 0.8], smooth=True, smooth_p=[0.3, 0.7, 0.9, 0.0, "none"], colormap="red->brown"),
+             dict(colormap="blue->green"), dict(smooth=True, smooth_p=[0.25, 0.6, 0.7, 0.1, "180:280|0.5,0.2"]), dict()]
+    for kw in cases:
+        out = havc.HAVC_stabilizer(clip, render_factor=16, **kw)
+        okw = dict(kw)
+        cm = okw.pop("colormap", "none")
+        okw["colormap_adjust"] = havc._get_colormap(cm) if cm != "none" else "none"
+        for i in (2, 0, 1):
+            f = out.get_frame(i)
+            assert f.props == props[i]
+            img = np.stack([np.asarray(f[p]) for p in range(3)], -1)
+            ref = pipeline_oracle.havc_stabilizer_frame(np.transpose(fr[i], (1, 2, 0)), render_factor=16, **okw)
+            _near(img, ref, (kw, i))
 
 
 @pytest.mark.parametrize("model,name", [(1, "ColorizeStable_gen"), (2, "ColorizeArtistic_gen")])

@@ -111,3 +111,28 @@ def test_havc_main_preset_tables_match_reference():
             for dd in (0, 1, 2, 3):
                 want = ref._get_color_tune(tune, fix, 'None', dd)
                 assert havc._get_color_tune(tune, fix, dd) == (want[0], want[1]), (tune, fix, dd)
+    # ColorMap -> "chroma adjustment" (havc_utils.py:519-548 inside _get_color_tune, :552-581 _get_colormap)
+    maps = ['blue->brown', 'blue->red', 'blue->green', 'green->brown', 'green->red', 'green->blue', 'redrose->brown', 'redrose->blue',
+            'red->brown', 'red->blue', 'yellow->rose', '30:90|+300,0.5']
+    for tune in ['none', 'light', 'medium', 'strong']:
+        for cm in maps:
+            assert havc._get_colormap(cm, tune) == ref._get_color_tune(tune, 'None', cm, 0)[3], (tune, cm)
+            assert havc._get_colormap(cm, tune) == ref._get_colormap(cm, tune), (tune, cm)
+    assert havc._get_colormap("teal->pink") == ref._get_colormap("teal->pink")     # an unknown name passes through (fails later)
+    with pytest.raises(vs_shim.Error, match="ColorMap choice is invalid"):
+        havc._get_colormap("a|b|c")
+
+
+def test_stabilizer_surface_and_errors():
+    """HAVC_stabilizer mirrors vsdeoldify/__init__.py:2748-2751 (names, order, defaults) and rejects what the reference rejects."""
+    from vsdeoldify_b200 import havc, vs_shim
+    params = list(inspect.signature(havc.HAVC_stabilizer).parameters)
+    assert params[:9] == ["clip", "dark", "dark_p", "smooth", "smooth_p", "stab", "stab_p", "colormap", "render_factor"]
+    sig = inspect.signature(havc.HAVC_stabilizer).parameters
+    assert tuple(sig["dark_p"].default) == (0.2, 0.8) and tuple(sig["smooth_p"].default) == (0.3, 0.7, 0.9, 0.0, "none")
+    assert tuple(sig["stab_p"].default) == (5, 'A', 1, 15, 0.2, 0.8) and sig["render_factor"].default == 24
+    clip = _clip()
+    with pytest.raises(vs_shim.Error, match="render_factor must be between: 16-64"):       # :2796
+        havc.HAVC_stabilizer(clip, dark=True, render_factor=12)
+    with pytest.raises(vs_shim.Error, match="temporal"):
+        havc.HAVC_stabilizer(clip, stab=True)

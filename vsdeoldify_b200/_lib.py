@@ -66,6 +66,7 @@ class ConvDesc(C.Structure):
         ("head_stride_w", C.c_int64), ("head_stride_h", C.c_int64), ("head_stride_b", C.c_int64),
         ("tma_store", C.c_int32),
         ("leaky1", C.c_float),
+        ("pair", C.c_int32),
     ]
 
 
@@ -113,6 +114,9 @@ _SIGNATURES = {
                                               C.c_void_p]),
     "havc_adjust_chroma": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(HueRanges), C.c_double, C.c_int,
                                      C.c_double, C.c_int, C.c_void_p]),
+    "havc_chroma_tweak": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
+                                    C.POINTER(HueRanges), C.c_double, C.c_int, C.c_double, C.c_int, C.c_double, C.c_double, C.c_int,
+                                    C.c_void_p]),
     "havc_image_tweak": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
                                    C.POINTER(HueRanges), C.c_void_p, C.c_void_p]),
     "havc_pil_resample_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,

@@ -40,6 +40,11 @@ struct ConvParams {
     int bw, bh, bb;
     int tiles_w, tiles_h, tiles_b, tiles_n, total_tiles;
     int BN, n_wloads, w_box_rows;
+    // weight loads of one K step: load l fetches the rows [n0 + wl_row0[l] + rank*wl_rank_rows[l], ...) of the N tile through
+    // tensor map wl_map[l] (its box height) to the byte offset wl_smem[l] of the stage's B area; rank = CTA rank in a pair
+    int wl_row0[2], wl_rank_rows[2], wl_map[2];
+    uint32_t wl_smem[2];
+    uint32_t b1_smem_off;         // byte offset of the second MMA's B rows (n_part1 > 0) in the stage's B area
     int n_taps;
     int8_t dh[HAVC_MAX_TAPS], dw[HAVC_MAX_TAPS], tp[HAVC_MAX_TAPS], twi[HAVC_MAX_TAPS];
     int chunks0, chunks1, w_c1_off;
@@ -170,6 +175,65 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                  : "memory");
 }
+// ---- CTA-pair (cta_group::2) helpers ---------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA's layout) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    __syncwarp();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA loads of a CTA pair: the data lands in the executing CTA's shared memory, the transaction bytes are counted on
+// `bar`, a shared::cluster address that may belong to the peer (the leader's full barrier).
+__device__ __forceinline__ void tma_load_5d_pair(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0,
+                                                 int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        :
+        : "r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0,
+                                                 int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        :
+        : "r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+// D[tmem of both CTAs] (+)= A[256 rows: 128 per CTA] * B[N rows: N/2 per CTA]^T, issued by the leader CTA only.
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                              uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :
+        : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives on the barrier at the same shared-memory offset in BOTH CTAs of the pair when the MMAs issued so far retire
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+    asm volatile(
+        "{\n\t.reg .b16 m;\n\t"
+        "mov.b16 m, 3;\n\t"
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}"
+        ::"r"(bar)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -229,11 +293,15 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap *tm, uint32_t src
 // kDT: operand / 16-bit output type (HAVC_F16 or HAVC_BF16), fixed at compile time so the pack / unpack helpers fold.
 // kFast: the streamlined epilogue for the common case (16-bit output through the TMA-store staging buffer, whole N tiles,
 // no head / column split / staggered accumulators); the generic epilogue covers everything else.
-template <int kDT, bool kFast>
+// kPair: two CTAs of a cluster (one TPC) work on two adjacent M tiles of the same N tile with cta_group::2 MMAs
+// (M = 256): each CTA loads its own 128 pixels of A and only HALF of the weight rows, the leader's MMA reads both
+// shared memories and writes both TMEMs.  Per CTA and K step 16 KB + BN*64 B arrive from L2 instead of 16 KB + BN*128 B
+// (the 3x3 decoder convs are bound by exactly that L2 -> SM traffic).
+template <int kDT, bool kFast, bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                 const __grid_constant__ CUtensorMap tmW, const __grid_constant__ StoreMaps tmO,
-                 const __grid_constant__ ConvParams p) {
+                 const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmW1,
+                 const __grid_constant__ StoreMaps tmO, const __grid_constant__ ConvParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t stage_out = smem_base + p.num_stages * p.stage_bytes;        // 1024-aligned output staging
@@ -250,11 +318,24 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    // work distribution: a "group" is one CTA (or one CTA pair); tiles are dealt round-robin to groups
+    const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+    const int group = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int ngroups = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    auto decode_tile = [&](int tile, int &nt, int &wt, int &ht, int &bt) {
+        int t = tile;
+        nt = t % p.tiles_n; t /= p.tiles_n;
+        if (kPair) t = 2 * t + (int)rank;    // the pair's two M tiles are neighbours; an odd tail lands outside the batch
+        wt = t % p.tiles_w; t /= p.tiles_w;
+        ht = t % p.tiles_h; t /= p.tiles_h;
+        bt = t;
+    };
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA0);
         tma_prefetch_desc(&tmA1);
         tma_prefetch_desc(&tmW);
+        if (kPair) tma_prefetch_desc(&tmW1);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.num_stages; ++s) {
@@ -263,19 +344,22 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(tfull_bar(s), 1);
-            mbar_init(tempty_bar(s), 256);
-            mbar_init(tearly_bar(s), 256);
+            mbar_init(tempty_bar(s), kPair ? 512 : 256);   // pair: the leader's barrier collects both CTAs' epilogues
+            mbar_init(tearly_bar(s), kPair ? 512 : 256);
         }
         fence_barrier_init();
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
-                     "r"(kTmemCols)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (kPair) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (kPair) cluster_sync_all(); else __syncthreads();   // pair: the peer's barriers must be initialised before any remote signal
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -288,12 +372,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                int t = tile;
-                const int nt = t % p.tiles_n; t /= p.tiles_n;
-                const int wt = t % p.tiles_w; t /= p.tiles_w;
-                const int ht = t % p.tiles_h; t /= p.tiles_h;
-                const int bt = t;
+            for (int tile = group; tile < p.total_tiles; tile += ngroups) {
+                int nt, wt, ht, bt;
+                decode_tile(tile, nt, wt, ht, bt);
                 const int n0 = nt * p.BN;
                 const int w0 = wt * p.bw, h0 = ht * p.bh, b0 = bt * p.bb;
                 for (int ks = 0; ks < ksteps; ++ks) {
@@ -312,25 +393,34 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t sa = smem_base + stage * p.stage_bytes;
                     const uint32_t sb = sa + kABytes;
-                    mbar_arrive_expect_tx(full_bar(stage), p.stage_bytes);
-                    tma_load_5d(sa, from1 ? &tmA1 : &tmA0, full_bar(stage), kc * kChunkK, cw, ch, p.a_batched ? b0 : 0, cp);
                     const int wc = (from1 ? p.w_c1_off : 0) + kc * kChunkK;
-                    for (int l = 0; l < p.n_wloads; ++l)
-                        tma_load_4d(sb + l * p.w_box_rows * 128, &tmW, full_bar(stage), wc, wi, n0 + l * p.w_box_rows,
-                                    p.b_batched ? b0 : 0);
+                    if (kPair) {
+                        // both CTAs' loads complete on the LEADER's full barrier, which expects the bytes of both
+                        if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2u * p.stage_bytes);
+                        const uint32_t fb = mapa_rank(full_bar(stage), 0);
+                        tma_load_5d_pair(sa, from1 ? &tmA1 : &tmA0, fb, kc * kChunkK, cw, ch, p.a_batched ? b0 : 0, cp);
+                        for (int l = 0; l < p.n_wloads; ++l)
+                            tma_load_4d_pair(sb + p.wl_smem[l], p.wl_map[l] ? &tmW1 : &tmW, fb, wc, wi,
+                                             n0 + p.wl_row0[l] + (int)rank * p.wl_rank_rows[l], p.b_batched ? b0 : 0);
+                    } else {
+                        mbar_arrive_expect_tx(full_bar(stage), p.stage_bytes);
+                        tma_load_5d(sa, from1 ? &tmA1 : &tmA0, full_bar(stage), kc * kChunkK, cw, ch, p.a_batched ? b0 : 0, cp);
+                        for (int l = 0; l < p.n_wloads; ++l)
+                            tma_load_4d(sb + p.wl_smem[l], &tmW, full_bar(stage), wc, wi, n0 + p.wl_row0[l], p.b_batched ? b0 : 0);
+                    }
                     if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (lane == 0 && rank == 0) {   // pair: the leader issues for both CTAs
             int stage = 0;
             uint32_t phase = 0;
             int as = 0;
             uint32_t aphase = 0;
             int seq = 0;   // index of this tile in the CTA's own sequence
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++seq) {
+            for (int tile = group; tile < p.total_tiles; tile += ngroups, ++seq) {
                 // Accumulator hand-over.  Normal double buffering: wait until the epilogue has fully drained this
                 // stage (its tile before last).  Staggered (BN > 256, 2*BN > 512 TMEM columns): stage 1 starts at
                 // column 512-BN, so the stages share columns [512-BN, BN); the epilogue drains that shared range
@@ -350,16 +440,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
                     for (int k = 0; k < kChunkK / 16; ++k) {
                         const uint32_t accum = (ks > 0 || k > 0) ? 1u : 0u;
-                        umma_f16(acc, da + 2u * k, db0 + 2u * k, p.idesc0, accum);
+                        if (kPair) umma_f16_pair(acc, da + 2u * k, db0 + 2u * k, p.idesc0, accum);
+                        else umma_f16(acc, da + 2u * k, db0 + 2u * k, p.idesc0, accum);
                         if (p.n_part1 > 0) {
-                            const uint64_t db1 = make_sw128_desc(sb + p.n_part0 * 128);
-                            umma_f16(acc + p.n_part0, da + 2u * k, db1 + 2u * k, p.idesc1, accum);
+                            const uint64_t db1 = make_sw128_desc(sb + p.b1_smem_off);
+                            if (kPair) umma_f16_pair(acc + p.n_part0, da + 2u * k, db1 + 2u * k, p.idesc1, accum);
+                            else umma_f16(acc + p.n_part0, da + 2u * k, db1 + 2u * k, p.idesc1, accum);
                         }
                     }
-                    umma_commit(empty_bar(stage));  // frees this smem stage when the MMAs retire
+                    // frees this smem stage (in both CTAs of a pair) when the MMAs retire
+                    if (kPair) umma_commit_pair(empty_bar(stage)); else umma_commit(empty_bar(stage));
                     if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
                 }
-                umma_commit(tfull_bar(as));  // accumulator complete -> epilogue
+                // accumulator complete -> epilogue (of both CTAs)
+                if (kPair) umma_commit_pair(tfull_bar(as)); else umma_commit(tfull_bar(as));
                 if (++as == p.acc_stages) { as = 0; aphase ^= 1u; }
             }
         }
@@ -387,12 +481,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             }
             asm volatile("bar.sync 2, 256;" ::: "memory");
         }
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-            int t = tile;
-            const int nt = t % p.tiles_n; t /= p.tiles_n;
-            const int wt = t % p.tiles_w; t /= p.tiles_w;
-            const int ht = t % p.tiles_h; t /= p.tiles_h;
-            const int bt = t;
+        // accumulator hand-back barriers live in the leader CTA
+        const uint32_t tempty_sig[2] = {kPair ? mapa_rank(tempty_bar(0), 0) : tempty_bar(0), kPair ? mapa_rank(tempty_bar(1), 0) : tempty_bar(1)};
+        const uint32_t tearly_sig[2] = {kPair ? mapa_rank(tearly_bar(0), 0) : tearly_bar(0), kPair ? mapa_rank(tearly_bar(1), 0) : tearly_bar(1)};
+        auto acc_signal = [&](uint32_t bar) { if (kPair) mbar_arrive_cluster(bar); else mbar_arrive(bar); };
+        for (int tile = group; tile < p.total_tiles; tile += ngroups) {
+            int nt, wt, ht, bt;
+            decode_tile(tile, nt, wt, ht, bt);
             const int n0 = nt * p.BN;
             const int ow = wt * p.bw + rw, oh = ht * p.bh + rh, ob = bt * p.bb + rb;
             const bool valid = (ow < p.out_W) && (oh < p.out_H) && (ob < p.out_B);
@@ -429,13 +524,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             if (p.residual != nullptr) {
                 // pull the NEXT tile's residual rows towards L2 while this tile is processed: each thread covers the
                 // 128-byte lines of its own row that its warp half will read
-                const int tn = tile + gridDim.x;
+                const int tn = tile + ngroups;
                 if (tn < p.total_tiles) {
-                    int t2 = tn;
-                    const int nt2 = t2 % p.tiles_n; t2 /= p.tiles_n;
-                    const int wt2 = t2 % p.tiles_w; t2 /= p.tiles_w;
-                    const int ht2 = t2 % p.tiles_h; t2 /= p.tiles_h;
-                    const int ow2 = wt2 * p.bw + rw, oh2 = ht2 * p.bh + rh, ob2 = t2 * p.bb + rb;
+                    int nt2, wt2, ht2, bt2;
+                    decode_tile(tn, nt2, wt2, ht2, bt2);
+                    const int ow2 = wt2 * p.bw + rw, oh2 = ht2 * p.bh + rh, ob2 = bt2 * p.bb + rb;
                     if (ow2 < p.out_W && oh2 < p.out_H && ob2 < p.out_B) {
                         const uint8_t *row = reinterpret_cast<const uint8_t *>(p.residual) + 2ll * (ob2 * p.rsb + oh2 * p.rsh + ow2 * p.rsw);
                         const int cbeg = nt2 * p.BN, cend = min(cbeg + p.BN, p.c_store);
@@ -687,14 +780,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             for (int k = 0; k < n_my; k += 2) {
                 if (!early_done && !shared_cols(chunk_at(k))) {
                     tc_fence_before();
-                    mbar_arrive(tearly_bar(as));
+                    acc_signal(tearly_sig[as]);
                     early_done = true;
                 }
                 process(chunk_at(k), k + 1 < n_my ? chunk_at(k + 1) : -1, va, vb);
                 if (k + 1 < n_my) {
                     if (!early_done && !shared_cols(chunk_at(k + 1))) {
                         tc_fence_before();
-                        mbar_arrive(tearly_bar(as));
+                        acc_signal(tearly_sig[as]);
                         early_done = true;
                     }
                     process(chunk_at(k + 1), k + 2 < n_my ? chunk_at(k + 2) : -1, vb, va);
@@ -702,7 +795,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             }
             if (!early_done) {
                 tc_fence_before();
-                mbar_arrive(tearly_bar(as));
+                acc_signal(tearly_sig[as]);
             }
             }   // generic path
             if (tma_store) {
@@ -736,19 +829,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 asm volatile("bar.sync 2, 256;" ::: "memory");
             }
             tc_fence_before();
-            mbar_arrive(tempty_bar(as));
+            acc_signal(tempty_sig[as]);
             if (++as == p.acc_stages) { as = 0; aphase ^= 1u; }
         }
     }
 
     if (p.tma_store && threadIdx.x == 128) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     tc_fence_before();
-    __syncthreads();
+    if (kPair) cluster_sync_all(); else __syncthreads();   // pair: neither CTA may exit while the peer can still signal it
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                     "r"(kTmemCols)
-                     : "memory");
+        if (kPair)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
     }
 }
 
@@ -860,11 +954,39 @@ extern "C" int havc_conv_gemm(const havc_conv_desc *d, void *stream) {
     p.tiles_b = ceil_div(d->out_B, d->box_b);
     p.BN = d->BN;
     p.tiles_n = ceil_div(d->N_total, d->BN);
-    p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_b * p.tiles_n;
+    const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_b;
     p.N_total = d->N_total;
-    p.n_wloads = d->BN > 256 ? 2 : 1;
-    p.w_box_rows = d->BN / p.n_wloads;
-    HAVC_CHECK_ARG(p.w_box_rows % 8 == 0, "havc_conv_gemm: weight box rows %d not a multiple of 8", p.w_box_rows);
+    // BN > 256 is issued as two MMAs per K step.  Balanced halves (272 = 144 + 128) keep both compute-bound; a 256 + 16
+    // split makes the narrow one shared-memory-bound (it re-reads the whole 128 x 16 A slice for 16 columns).
+    static const bool legacy_split = getenv("HAVC_B200_SPLIT256") != nullptr;   // A/B switch for profiling
+    p.n_part0 = d->BN > 256 ? (legacy_split ? 256 : ((d->BN / 2 + 15) / 16) * 16) : d->BN;
+    p.n_part1 = d->BN - p.n_part0;
+    // CTA pairs (cta_group::2): d->pair = 1 forces, -1 forbids, 0 = library default (env HAVC_B200_PAIR=0 turns it off)
+    static const char *pair_env = getenv("HAVC_B200_PAIR");
+    const bool pair_default = !(pair_env && pair_env[0] == '0');
+    // a pair shares ONE weight tile: with per-batch weights (b_batched) both M tiles must lie in the same batch
+    // Default policy (d->pair == 0), measured per layer shape on B200 (profiles/r01_pair_vs_single.txt): pairs win 3-8 % on
+    // long launches (>= ~55 tiles per SM: the 384^2 / 192^2 decoder convs, where the halved weight traffic dominates) and lose
+    // 3-15 % on short ones (cluster launch + the cross-SM barrier round trips are not amortised).
+    const bool pair_auto = pair_default && (long long)tiles_m * p.tiles_n >= 8192;
+    const bool pair = (d->pair > 0 || (d->pair == 0 && pair_auto)) && tiles_m >= 2 && num_sms() >= 2 &&
+                      (!d->b_batched || (p.tiles_w * p.tiles_h) % 2 == 0);
+    p.total_tiles = (pair ? ceil_div(tiles_m, 2) : tiles_m) * p.tiles_n;
+    if (pair) {      // each CTA loads half of the rows of each MMA's B operand
+        p.n_wloads = p.n_part1 > 0 ? 2 : 1;
+        p.wl_row0[0] = 0;          p.wl_rank_rows[0] = p.n_part0 / 2; p.wl_map[0] = 0; p.wl_smem[0] = 0;
+        p.wl_row0[1] = p.n_part0;  p.wl_rank_rows[1] = p.n_part1 / 2; p.wl_map[1] = 1; p.wl_smem[1] = (uint32_t)(p.n_part0 / 2) * 128u;
+        p.b1_smem_off = p.wl_smem[1];
+        p.w_box_rows = p.n_part0 / 2;
+    } else {
+        p.n_wloads = d->BN > 256 ? 2 : 1;
+        p.w_box_rows = d->BN / p.n_wloads;
+        for (int l = 0; l < p.n_wloads; ++l) {
+            p.wl_row0[l] = l * p.w_box_rows; p.wl_rank_rows[l] = 0; p.wl_map[l] = 0; p.wl_smem[l] = (uint32_t)(l * p.w_box_rows) * 128u;
+        }
+        p.b1_smem_off = (uint32_t)p.n_part0 * 128u;
+    }
+    HAVC_CHECK_ARG(p.w_box_rows % 8 == 0 && (p.n_part1 / 2) % 8 == 0, "havc_conv_gemm: weight box rows %d not a multiple of 8", p.w_box_rows);
     p.n_taps = d->n_taps;
     for (int i = 0; i < d->n_taps; ++i) {
         p.dh[i] = d->tap_dh[i]; p.dw[i] = d->tap_dw[i]; p.tp[i] = d->tap_p[i]; p.twi[i] = d->tap_wi[i];
@@ -877,7 +999,7 @@ extern "C" int havc_conv_gemm(const havc_conv_desc *d, void *stream) {
     p.acc_stages = 2;
     p.staggered = (2 * d->BN > (int)kTmemCols) ? 1 : 0;
     p.acc_stride = p.staggered ? (int)kTmemCols - d->BN : d->BN;
-    p.stage_bytes = kABytes + d->BN * 128;
+    p.stage_bytes = kABytes + (pair ? d->BN / 2 : d->BN) * 128;     // per CTA
     const bool out16 = d->out_dtype == HAVC_F16 || d->out_dtype == HAVC_BF16;
     p.tma_store = (d->tma_store && out16 && d->out != nullptr && d->BN % 64 == 0 && d->N_total % 64 == 0 && d->split_n == 0 &&
                    d->head_w == nullptr && d->up == 1 && d->oy == 0 && d->ox == 0 && (!d->shuffle || d->group_n % 64 == 0))
@@ -887,14 +1009,9 @@ extern "C" int havc_conv_gemm(const havc_conv_desc *d, void *stream) {
     if (stages > kMaxStages) stages = kMaxStages;
     HAVC_CHECK_ARG(stages >= 2, "havc_conv_gemm: tile too large for shared memory");
     p.num_stages = stages;
-    // BN > 256 is issued as two MMAs per K step.  Balanced halves (272 = 144 + 128) keep both compute-bound; a 256 + 16
-    // split makes the narrow one shared-memory-bound (it re-reads the whole 128 x 16 A slice for 16 columns).
-    static const bool legacy_split = getenv("HAVC_B200_SPLIT256") != nullptr;   // A/B switch for profiling
-    p.n_part0 = d->BN > 256 ? (legacy_split ? 256 : ((d->BN / 2 + 15) / 16) * 16) : d->BN;
-    p.n_part1 = d->BN - p.n_part0;
     const uint32_t fmt = d->dtype == HAVC_F16 ? 0u : 1u;
     auto idesc = [&](int n) -> uint32_t {
-        return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+        return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)((pair ? 2 * kTileM : kTileM) >> 4) << 24);
     };
     p.idesc0 = idesc(p.n_part0);
     p.idesc1 = p.n_part1 > 0 ? idesc(p.n_part1) : 0u;
@@ -920,7 +1037,7 @@ extern "C" int havc_conv_gemm(const havc_conv_desc *d, void *stream) {
     if (d->head_w) HAVC_CHECK_ARG(d->head_out != nullptr && d->BN == d->N_total && !d->shuffle && d->head_stride_w % 4 == 0,
                                   "havc_conv_gemm: the fused head needs a single N tile (BN == N_total) and head_out");
 
-    CUtensorMap tmA0, tmA1, tmW;
+    CUtensorMap tmA0, tmA1, tmW, tmW1;
     int rc = encode_act(&tmA0, d->src0, d->dtype, d->box_w, d->box_h, d->a_batched ? d->box_b : 1);
     if (rc) return rc;
     if (!d->a_batched) HAVC_CHECK_ARG(d->box_b == 1, "havc_conv_gemm: a_batched=0 needs box_b=1");
@@ -937,6 +1054,12 @@ extern "C" int havc_conv_gemm(const havc_conv_desc *d, void *stream) {
         uint32_t box[4] = {(uint32_t)kChunkK, 1u, (uint32_t)p.w_box_rows, 1u};
         rc = encode_map(&tmW, d->dtype, 4, d->weight, dims, strides, box);
         if (rc) return rc;
+        tmW1 = tmW;
+        if (pair && p.n_part1 > 0) {
+            box[2] = (uint32_t)(p.n_part1 / 2);
+            rc = encode_map(&tmW1, d->dtype, 4, d->weight, dims, strides, box);
+            if (rc) return rc;
+        }
     }
     if (d->b_batched) HAVC_CHECK_ARG(d->box_b == 1, "havc_conv_gemm: b_batched=1 needs box_b=1");
 
@@ -944,15 +1067,18 @@ extern "C" int havc_conv_gemm(const havc_conv_desc *d, void *stream) {
     static const bool no_fast = getenv("HAVC_B200_NO_FAST_EPILOGUE") != nullptr;   // A/B switch for profiling
     const bool fast = !no_fast && p.tma_store && !p.staggered && d->head_w == nullptr && d->split_n == 0 && d->residual2 == nullptr &&
                       d->out_dtype == d->dtype && d->BN % 32 == 0 && d->N_total % d->BN == 0;
-    typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const StoreMaps, const ConvParams);
-    KernelFn kern = d->dtype == HAVC_F16 ? (fast ? conv_gemm_kernel<HAVC_F16, true> : conv_gemm_kernel<HAVC_F16, false>)
-                                         : (fast ? conv_gemm_kernel<HAVC_BF16, true> : conv_gemm_kernel<HAVC_BF16, false>);
+    typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const StoreMaps, const ConvParams);
+    static const KernelFn kernels[2][2][2] = {
+        {{conv_gemm_kernel<HAVC_F16, false, false>, conv_gemm_kernel<HAVC_F16, false, true>},
+         {conv_gemm_kernel<HAVC_F16, true, false>, conv_gemm_kernel<HAVC_F16, true, true>}},
+        {{conv_gemm_kernel<HAVC_BF16, false, false>, conv_gemm_kernel<HAVC_BF16, false, true>},
+         {conv_gemm_kernel<HAVC_BF16, true, false>, conv_gemm_kernel<HAVC_BF16, true, true>}}};
+    KernelFn kern = kernels[d->dtype == HAVC_F16 ? 0 : 1][fast ? 1 : 0][pair ? 1 : 0];
     static bool attr_set = false;
     if (!attr_set) {
-        HAVC_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<HAVC_F16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        HAVC_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<HAVC_F16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        HAVC_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<HAVC_BF16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        HAVC_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<HAVC_BF16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        for (int i = 0; i < 8; ++i)
+            HAVC_CHECK_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void *>(kernels[i >> 2][(i >> 1) & 1][i & 1]),
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
     StoreMaps tmO;
@@ -972,8 +1098,25 @@ extern "C" int havc_conv_gemm(const havc_conv_desc *d, void *stream) {
             if (rc) return rc;
         }
     }
-    int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-    kern<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA0, tmA1, tmW, tmO, p);
+    if (pair) {
+        const int max_groups = num_sms() / 2;
+        const int groups = p.total_tiles < max_groups ? p.total_tiles : max_groups;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(2 * groups);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        HAVC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA0, tmA1, tmW, tmW1, tmO, p));
+    } else {
+        int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+        kern<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA0, tmA1, tmW, tmW1, tmO, p);
+    }
     HAVC_LAUNCHED();
     return HAVC_OK;
 }

@@ -312,6 +312,69 @@ __global__ void adjust_chroma_kernel(Img img, uint8_t *out, AdjustParams p) {
     }
 }
 
+// ---- np_image_chroma_tweak (restcolor.py:288-342) fused with the luma merge of vs_sc_chroma_bright_tweak ------------
+// (vsfilters.py:525-552) / _vs_sc_colormap (vsfilters.py:577-590): HAVC_stabilizer's `smooth` and `colormap` stages.
+struct ChromaTweakParams {
+    double sat, val, hue_half; int hue_on;
+    int stage2; HueRanges rng; double sat2; int scale_sat2; double hue2_half; int hue2_on; double w, omw; int wsign;
+    int merge; LumaMaskParams lm;      // merge != 0: out = luma_merge(img_dark = tweaked, img_white = img)
+    int W, simd_width;
+};
+__device__ __forceinline__ int cv_hue_add(int h, double half) {     // np_hue_add (nputils.py:330-340) + the uint8 store
+    double x = __dadd_rn((double)h, half);
+    x = x > 180.0 ? x - 180.0 : x;
+    x = x < 0.0 ? x + 180.0 : x;
+    return (int)x & 0xff;
+}
+__global__ void chroma_tweak_kernel(Img img, uint8_t *out, ChromaTweakParams p) {
+    const int fb = blockIdx.y;
+    const int body = p.simd_width > 0 ? (p.W / p.simd_width) * p.simd_width : 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < img.plane; i += (long long)gridDim.x * blockDim.x) {
+        int r0, g0, b0;
+        img.load(fb, i, r0, g0, b0);
+        const bool simd = (int)(i % p.W) < body;
+        int h, s, v;
+        rgb2hsv(r0, g0, b0, h, s, v);
+        if (p.hue_on) h = cv_hue_add(h, p.hue_half);
+        s = (int)((long long)__dmul_rn((double)s, p.sat) & 0xff);      // float64 product stored into a uint8 plane
+        v = (int)((long long)__dmul_rn((double)v, p.val) & 0xff);
+        int r, g, b;
+        hsv2rgb(h, s, v, simd, r, g, b);
+        if (p.stage2) {           // "chroma adjustment": the mask comes from the tweaked hue, unmasked pixels from the ORIGINAL image
+            int hg, sg, vg, rg, gg, bg;
+            rgb2hsv(r, g, b, hg, sg, vg);
+            if (p.hue2_on) hg = cv_hue_add(hg, p.hue2_half);
+            if (p.scale_sat2) sg = (int)((long long)__dmul_rn((double)sg, p.sat2) & 0xff);
+            hsv2rgb(hg, sg, vg, simd, rg, gg, bg);
+            const bool in = p.rng.hit(h);
+            r = in ? rg : r0; g = in ? gg : g0; b = in ? bg : b0;
+            if (p.wsign > 0) {
+                if (!p.hue2_on) { r = np_wmerge(r, rg, p.omw, p.w); g = np_wmerge(g, gg, p.omw, p.w); b = np_wmerge(b, bg, p.omw, p.w); }
+                else { r = np_wmerge(r, r0, p.omw, p.w); g = np_wmerge(g, g0, p.omw, p.w); b = np_wmerge(b, b0, p.omw, p.w); }
+            }
+            if (p.wsign < 0) { r = np_wmerge(r, r0, p.omw, p.w); g = np_wmerge(g, g0, p.omw, p.w); b = np_wmerge(b, b0, p.omw, p.w); }
+        }
+        if (p.merge) {
+            int ro, go, bo;
+            if (p.lm.hard) {
+                if (p.lm.zero_limit) {
+                    const double mw = (double)trunc8(np_luma(r0, g0, b0)) / 255.0, mk = __dsub_rn(1.0, mw);
+                    ro = trunc8(clip255(__dadd_rn(__dmul_rn((double)r, mk), __dmul_rn((double)r0, mw))));
+                    go = trunc8(clip255(__dadd_rn(__dmul_rn((double)g, mk), __dmul_rn((double)g0, mw))));
+                    bo = trunc8(clip255(__dadd_rn(__dmul_rn((double)b, mk), __dmul_rn((double)b0, mw))));
+                } else {
+                    const bool white = np_luma(r0, g0, b0) > p.lm.hard_thr;
+                    ro = white ? r0 : r; go = white ? g0 : g; bo = white ? b0 : b;
+                }
+            } else {
+                ramp_merge(p.lm.ramp, r, g, b, r0, g0, b0, ro, go, bo);
+            }
+            r = ro; g = go; b = bo;
+        }
+        store_px(out, img.plane, fb, i, r, g, b);
+    }
+}
+
 // ---- image_tweak (imfilters.py:463-504): Brightness -> Contrast -> Color, optional hue-range restriction --------
 struct TweakParams { float bright; int use_bright; float cont; int use_cont; float sat; int use_sat; HueRanges rng; };
 __global__ void image_tweak_kernel(Img img, uint8_t *out, TweakParams p, const unsigned long long *stats) {
@@ -463,23 +526,29 @@ extern "C" int havc_red_fix(const uint8_t *stab, uint8_t *out, int B, int H, int
     return HAVC_OK;
 }
 
+// Fills the hard-mask / ramp description shared by havc_luma_masked_merge and havc_chroma_tweak; false = unsupported.
+static bool make_luma_mask(double luma_limit, double white_limit, LumaMaskParams &p) {
+    if (luma_limit == white_limit) {                    // image_luma_merge: hard mask (imfilters.py:66-78)
+        p.hard = 1;
+        p.zero_limit = !(luma_limit > 0);
+        p.hard_thr = nearbyint(luma_limit * 255.0);
+    } else if (luma_limit > white_limit) {              // w_image_luma_merge returns img_dark
+        p.hard = 1; p.zero_limit = 0; p.hard_thr = 1e30;
+    } else if (!(luma_limit > 0)) {                     // ramp with dark_luma == 0: weight = luma / 255 (nputils.py:178-183)
+        return false;
+    } else {
+        p.ramp = make_ramp(luma_limit, white_limit);
+    }
+    return true;
+}
+
 extern "C" int havc_luma_masked_merge(const uint8_t *a, const uint8_t *b, const uint8_t *c, uint8_t *out, int B, int H, int W,
                                       double luma_limit, double white_limit, float weight, void *stream) {
     HAVC_CHECK_ARG(a && b && c && out && HAVC_IMG_ARGS_OK(B, H, W), "havc_luma_masked_merge: bad arguments");
     LumaMaskParams p;
     memset(&p, 0, sizeof(p));
     p.weight = weight;
-    if (luma_limit == white_limit) {                    // image_luma_merge: hard mask (imfilters.py:66-78)
-        p.hard = 1;
-        p.zero_limit = !(luma_limit > 0);
-        p.hard_thr = nearbyint(luma_limit * 255.0);
-    } else if (luma_limit > white_limit) {              // w_image_luma_merge returns img_dark (= c)
-        p.hard = 1; p.zero_limit = 0; p.hard_thr = 1e30;
-    } else if (!(luma_limit > 0)) {                     // ramp with dark_luma == 0: weight = luma / 255 (nputils.py:178-183)
-        HAVC_CHECK_ARG(false, "havc_luma_masked_merge: luma_limit = 0 with a white limit is not supported");
-    } else {
-        p.ramp = make_ramp(luma_limit, white_limit);
-    }
+    HAVC_CHECK_ARG(make_luma_mask(luma_limit, white_limit, p), "havc_luma_masked_merge: luma_limit = 0 with a white limit is not supported");
     Img ia{a, (long long)H * W}, ib{b, (long long)H * W}, ic{c, (long long)H * W};
     luma_masked_merge_kernel<<<frame_grid(ia.plane, B), 256, 0, (cudaStream_t)stream>>>(ia, ib, ic, out, p);
     HAVC_LAUNCHED();
@@ -537,6 +606,35 @@ extern "C" int havc_adjust_chroma(const uint8_t *img, uint8_t *out, int B, int H
     p.W = W; p.simd_width = simd_width;
     Img im{img, (long long)H * W};
     adjust_chroma_kernel<<<frame_grid(im.plane, B), 256, 0, (cudaStream_t)stream>>>(im, out, p);
+    HAVC_LAUNCHED();
+    return HAVC_OK;
+}
+
+extern "C" int havc_chroma_tweak(const uint8_t *img, uint8_t *out, int B, int H, int W, double sat, double bright, int hue,
+                                 const havc_hue_ranges *ranges, double sat2, int hue2, double weight, int luma_merge,
+                                 double luma_limit, double white_limit, int simd_width, void *stream) {
+    HAVC_CHECK_ARG(img && out && HAVC_IMG_ARGS_OK(B, H, W) && (ranges == nullptr || (ranges_ok(ranges) && ranges->n > 0)),
+                   "havc_chroma_tweak: bad arguments");
+    ChromaTweakParams p;
+    memset(&p, 0, sizeof(p));
+    auto clamp10 = [](double x) { return x < 0 ? 0.0 : (x > 10 ? 10.0 : x); };
+    auto half_hue = [](int h) { return 0.5 * (h < -360 ? -360 : (h > 360 ? 360 : h)); };
+    p.sat = clamp10(sat); p.val = clamp10(1.0 + bright);
+    p.hue_on = hue != 0; p.hue_half = half_hue(hue);
+    if (ranges != nullptr) {
+        p.stage2 = 1;
+        p.rng = to_dev_ranges(ranges);
+        p.scale_sat2 = sat2 != 1.0; p.sat2 = clamp10(sat2);
+        p.hue2_on = hue2 != 0; p.hue2_half = half_hue(hue2);
+        p.w = fabs(weight); p.omw = 1.0 - p.w; p.wsign = weight > 0 ? 1 : (weight < 0 ? -1 : 0);
+    }
+    if (luma_merge) {
+        p.merge = 1;
+        HAVC_CHECK_ARG(make_luma_mask(luma_limit, white_limit, p.lm), "havc_chroma_tweak: luma_limit = 0 with a white limit is not supported");
+    }
+    p.W = W; p.simd_width = simd_width;
+    Img im{img, (long long)H * W};
+    chroma_tweak_kernel<<<frame_grid(im.plane, B), 256, 0, (cudaStream_t)stream>>>(im, out, p);
     HAVC_LAUNCHED();
     return HAVC_OK;
 }

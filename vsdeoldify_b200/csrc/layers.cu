@@ -2,6 +2,7 @@
 // Zhang first conv), max-pool, stride-2 phase split, eval-BatchNorm(+ReLU), the PixelShuffle_ICNR blur,
 // the attention row soft-max.  All NHWC 16-bit, 8 channels (16 B) per thread access, grid-stride loops.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace havc {
 
@@ -22,10 +23,13 @@ static inline int grid_for(long long n_threads, int block) {
 // is never written (the buffer is zero-initialised once).  One thread = one (output pixel, filter row):
 // ks 16-byte loads, RW/8 16-byte stores.
 // ---------------------------------------------------------------------------------------------
-template <int KS>
+// CIN > 0 fixes the channel count at compile time: the K-row scratch `v` is then indexed statically and lives in registers
+// (with a run-time cin it sits in local memory and the kernel is bound by those load/store-unit round trips).
+template <int KS, int CIN>
 __global__ void im2col_rows_kernel(const uint4 *__restrict__ in, uint16_t *__restrict__ out, int B, int H, int W,
-                                   int cin, int stride, int pad, int OH, int OW, int Kp) {
-    constexpr int kMaxRW = ((KS * 8 + 7) / 8) * 8;
+                                   int cin_rt, int stride, int pad, int OH, int OW, int Kp) {
+    constexpr int kMaxRW = ((KS * (CIN > 0 ? CIN : 8) + 7) / 8) * 8;
+    const int cin = CIN > 0 ? CIN : cin_rt;
     const int RW = ((KS * cin + 7) / 8) * 8;
     const long long total = (long long)B * OH * OW * KS;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -63,6 +67,68 @@ __global__ void im2col_rows_kernel(const uint4 *__restrict__ in, uint16_t *__res
                 *reinterpret_cast<uint4 *>(dst + g * 8) = o;
             }
         }
+    }
+}
+
+// Same im2col, tiled: a block builds the K rows of 128 consecutive output pixels in shared memory (16-byte chunks XOR-swizzled
+// so both sides are bank-conflict free) and then streams the tile out as ONE contiguous run of whole 128-byte lines, zero tail
+// included.  The per-(pixel, filter row) kernel above leaves a never-written tail in every K row and issues half-sector
+// stores; partially written lines cost a read-modify-write at the (ECC) HBM and held it to 1-1.7 TB/s.  Needs Kp % 64 == 0.
+template <int KS, int CIN>
+__global__ void im2col_tile_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, int H, int W, int cin_rt, int stride,
+                                   int pad, int OH, int OW, int Kp, long long total_pix) {
+    extern __shared__ uint4 tile[];          // [128][Kp / 8]
+    constexpr int kMaxRW = ((KS * (CIN > 0 ? CIN : 8) + 7) / 8) * 8;
+    const int cin = CIN > 0 ? CIN : cin_rt;
+    const int CH = Kp >> 3;                  // 16-byte chunks per pixel (multiple of 8)
+    const int RW = ((KS * cin + 7) / 8) * 8, RC = RW >> 3;
+    const int t = threadIdx.x;
+    for (long long p0 = blockIdx.x * 128ll; p0 < total_pix; p0 += gridDim.x * 128ll) {
+        const long long pix = p0 + t;
+        if (pix < total_pix) {
+            const int ox = (int)(pix % OW);
+            const int oy = (int)((pix / OW) % OH);
+            const long long b = pix / ((long long)OW * OH);
+            uint4 *row = tile + t * CH;
+#pragma unroll
+            for (int kh = 0; kh < KS; ++kh) {
+                uint16_t v[kMaxRW];
+#pragma unroll
+                for (int j = 0; j < kMaxRW; ++j) v[j] = 0;
+                const int iy = oy * stride - pad + kh;
+                if (iy >= 0 && iy < H) {
+#pragma unroll
+                    for (int kw = 0; kw < KS; ++kw) {
+                        const int ix = ox * stride - pad + kw;
+                        if (ix < 0 || ix >= W) continue;
+                        const uint4 q = __ldg(in + (b * H + iy) * W + ix);
+                        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                        for (int c = 0; c < 8; ++c)
+                            if (c < cin) v[kw * cin + c] = (uint16_t)((w[c >> 1] >> ((c & 1) * 16)) & 0xffff);
+                    }
+                }
+#pragma unroll
+                for (int g = 0; g < kMaxRW / 8; ++g) {
+                    if (g < RC) {
+                        const int chunk = kh * RC + g;
+                        row[(chunk & ~7) | ((chunk ^ t) & 7)] =
+                            make_uint4(v[g * 8 + 0] | ((uint32_t)v[g * 8 + 1] << 16), v[g * 8 + 2] | ((uint32_t)v[g * 8 + 3] << 16),
+                                       v[g * 8 + 4] | ((uint32_t)v[g * 8 + 5] << 16), v[g * 8 + 6] | ((uint32_t)v[g * 8 + 7] << 16));
+                    }
+                }
+            }
+            for (int chunk = KS * RC; chunk < CH; ++chunk) row[(chunk & ~7) | ((chunk ^ t) & 7)] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        __syncthreads();
+        const long long left = total_pix - p0;
+        const int n = (int)(left < 128 ? left : 128) * CH;
+        uint4 *dst = out + p0 * CH;
+        for (int f = t; f < n; f += 128) {
+            const int pl = f / CH, slot = f - pl * CH;
+            dst[pl * CH + ((slot & ~7) | ((slot ^ pl) & 7))] = tile[f];
+        }
+        __syncthreads();
     }
 }
 
@@ -237,12 +303,26 @@ extern "C" int havc_im2col_small(const void *in, void *out, int B, int H, int W,
     const long long n = (long long)B * OH * OW * ks;
     const int grid = grid_for(n, 256);
     cudaStream_t st = (cudaStream_t)stream;
-    if (ks == 7)
-        im2col_rows_kernel<7><<<grid, 256, 0, st>>>((const uint4 *)in, (uint16_t *)out, B, H, W, cin, stride, pad, OH, OW, Kp);
-    else if (ks == 3)
-        im2col_rows_kernel<3><<<grid, 256, 0, st>>>((const uint4 *)in, (uint16_t *)out, B, H, W, cin, stride, pad, OH, OW, Kp);
-    else
-        im2col_rows_kernel<1><<<grid, 256, 0, st>>>((const uint4 *)in, (uint16_t *)out, B, H, W, cin, stride, pad, OH, OW, Kp);
+    static const bool legacy = getenv("HAVC_B200_LEGACY_IM2COL") != nullptr;   // A/B switch for profiling
+    const bool tiled = !legacy && Kp % 64 == 0 && 128 * Kp * 2 <= 48 * 1024;
+    const long long pixels = (long long)B * OH * OW;
+    const long long blocks = (pixels + 127) / 128;
+    const int g2 = (int)(blocks < (long long)num_sms() * 8 ? blocks : (long long)num_sms() * 8);
+    const size_t sm = (size_t)128 * Kp * 2;
+#define HAVC_IM2COL(KS_, CIN_)                                                                                                   \
+    do {                                                                                                                         \
+        if (tiled)                                                                                                               \
+            im2col_tile_kernel<KS_, CIN_><<<g2, 128, sm, st>>>((const uint4 *)in, (uint4 *)out, H, W, cin, stride, pad, OH, OW, Kp, pixels); \
+        else                                                                                                                     \
+            im2col_rows_kernel<KS_, CIN_><<<grid, 256, 0, st>>>((const uint4 *)in, (uint16_t *)out, B, H, W, cin, stride, pad, OH, OW, Kp); \
+    } while (0)
+    if (ks == 7 && cin == 3) HAVC_IM2COL(7, 3);
+    else if (ks == 3 && cin == 3) HAVC_IM2COL(3, 3);
+    else if (ks == 3 && cin == 1) HAVC_IM2COL(3, 1);
+    else if (ks == 7) HAVC_IM2COL(7, 0);
+    else if (ks == 3) HAVC_IM2COL(3, 0);
+    else HAVC_IM2COL(1, 0);
+#undef HAVC_IM2COL
     HAVC_LAUNCHED();
     return HAVC_OK;
 }

@@ -12,6 +12,7 @@
 // builds the tables (Spline64 / Spline36 / Pillow triangle), so every resampler shares these kernels.
 #include "common.cuh"
 #include "pixel_math.cuh"
+#include <stdlib.h>
 
 namespace havc {
 
@@ -88,6 +89,76 @@ __global__ void resample_h_regw_kernel(const uint8_t *__restrict__ in, float *__
     }
 }
 
+// Horizontal pass, register-resident weights, kR rows per step: like resample_h_regw_kernel, but a block stages kR rows at a
+// time and the NEXT group's pixels are already in flight (registers) while the current group is computed, so the global-load
+// latency never sits on the critical path; each weight register feeds kR independent FMAs.  One block per SM (the two
+// kR-row buffers take most of the shared memory), bound by the one-LDS-per-FMA rate of the inner loop.
+template <int kMaxT, int kR>
+__global__ void __launch_bounds__(640, 1)
+resample_h_rows_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, long long rows, int Win, int Wout,
+                       const int *__restrict__ start, const float *__restrict__ wts, int T) {
+    extern __shared__ float srow[];          // [2][kR][Win + kMaxT]; the kMaxT floats behind each row stay zero
+    constexpr int kPre = 6;                  // uint32 (4-pixel) loads in flight per thread
+    const int rowlen = Win + kMaxT;
+    const int w4 = Win / 4;                  // 4-pixel words per row
+    const int words = kR * w4;               // per group
+    for (int i = threadIdx.x; i < 2 * kR * kMaxT; i += blockDim.x) srow[(i / kMaxT) * rowlen + Win + (i % kMaxT)] = 0.f;
+    const int ox = threadIdx.x;
+    const bool active = ox < Wout;
+    float w[kMaxT];
+    int s0 = 0;
+    if (active) s0 = __ldg(start + ox);
+#pragma unroll
+    for (int t = 0; t < kMaxT; ++t) w[t] = (active && t < T) ? __ldg(wts + (long long)t * Wout + ox) : 0.f;
+    const long long groups = (rows + kR - 1) / kR;
+    uint32_t pre[kPre];
+    auto fetch = [&](long long g) {          // rows of a group are consecutive in memory: one flat run of `words` words
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(in + g * kR * (long long)Win);
+        const long long lim = (rows - g * kR) * w4;      // words that exist (last group may be short)
+#pragma unroll
+        for (int k = 0; k < kPre; ++k) {
+            const int i = threadIdx.x + k * blockDim.x;
+            pre[k] = (i < words && i < lim) ? __ldg(src + i) : 0u;
+        }
+    };
+    auto stash = [&](float *dst) {
+#pragma unroll
+        for (int k = 0; k < kPre; ++k) {
+            const int i = threadIdx.x + k * blockDim.x;
+            if (i < words) {
+                const int r = i / w4, c = i - r * w4;
+                const uint32_t v = pre[k];
+                *reinterpret_cast<float4 *>(dst + r * rowlen + 4 * c) =
+                    make_float4((float)(v & 0xff), (float)((v >> 8) & 0xff), (float)((v >> 16) & 0xff), (float)(v >> 24));
+            }
+        }
+    };
+    long long g = blockIdx.x;
+    if (g < groups) { fetch(g); stash(srow); }
+    __syncthreads();
+    int buf = 0;
+    for (; g < groups; g += gridDim.x) {
+        const long long nxt = g + gridDim.x;
+        if (nxt < groups) fetch(nxt);
+        if (active) {
+            const float *sp = srow + buf * (kR * rowlen) + s0;
+            float acc[kR];
+#pragma unroll
+            for (int r = 0; r < kR; ++r) acc[r] = 0.f;
+#pragma unroll
+            for (int t = 0; t < kMaxT; ++t)
+#pragma unroll
+                for (int r = 0; r < kR; ++r) acc[r] = fmaf(w[t], sp[r * rowlen + t], acc[r]);
+#pragma unroll
+            for (int r = 0; r < kR; ++r)
+                if (g * kR + r < rows) out[(g * kR + r) * Wout + ox] = acc[r];
+        }
+        if (nxt < groups) stash(srow + (buf ^ 1) * (kR * rowlen));
+        __syncthreads();
+        buf ^= 1;
+    }
+}
+
 // Vertical pass on u8 planes: out[plane][oy][x] = sum_t w[oy][t] * in[plane][start[oy]+t][x]  (float out).
 __global__ void resample_v_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, long long planes, int Hin,
                                   int Hout, int W, const int *__restrict__ start, const float *__restrict__ wts, int T) {
@@ -102,6 +173,31 @@ __global__ void resample_v_kernel(const uint8_t *__restrict__ in, float *__restr
         float acc = 0.f;
         for (int t = 0; t < T; ++t) acc = fmaf(__ldg(w + t), (float)__ldg(src + (long long)t * W), acc);
         out[i] = acc;
+    }
+}
+
+// Same pass, four adjacent columns per thread (W % 4 == 0): one 4-byte load per tap instead of four 1-byte loads, a
+// warp-uniform weight load, one 16-byte store.
+__global__ void resample_v4_kernel(const uint8_t *__restrict__ in, float4 *__restrict__ out, long long planes, int Hin,
+                                   int Hout, int W, const int *__restrict__ start, const float *__restrict__ wts, int T) {
+    const int W4 = W >> 2;
+    const long long total = planes * Hout * W4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int x4 = (int)(i % W4);
+        const int oy = (int)((i / W4) % Hout);
+        const long long pl = i / ((long long)W4 * Hout);
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(in + (pl * Hin + __ldg(start + oy)) * W) + x4;
+        const float *w = wts + (long long)oy * T;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        for (int t = 0; t < T; ++t) {
+            const float wt = __ldg(w + t);
+            const uint32_t v = __ldg(src + (long long)t * W4);
+            a0 = fmaf(wt, (float)(v & 0xff), a0);
+            a1 = fmaf(wt, (float)((v >> 8) & 0xff), a1);
+            a2 = fmaf(wt, (float)((v >> 16) & 0xff), a2);
+            a3 = fmaf(wt, (float)(v >> 24), a3);
+        }
+        out[i] = make_float4(a0, a1, a2, a3);
     }
 }
 
@@ -138,6 +234,46 @@ __global__ void pre_vertical_kernel(const float *__restrict__ in, uint8_t *__res
         for (int c = 0; c < 3; ++c) n[c] = __fdiv_rn(__fsub_rn(lf, mean[c]), stdv[c]);
         uint4 pk = make_uint4(pack2(n[0], n[1], dtype), pack2(n[2], 0.f, dtype), 0u, 0u);
         *reinterpret_cast<uint4 *>(reinterpret_cast<uint16_t *>(x) + i * 8) = pk;
+    }
+}
+
+// Same pass, four adjacent output columns per thread (S % 4 == 0): 16-byte loads of the fp32 rows, warp-uniform weights.
+__global__ void pre_vertical4_kernel(const float *__restrict__ in, uint8_t *__restrict__ rgb_small, void *__restrict__ x,
+                                     int B, int Hin, int S, const int *__restrict__ start,
+                                     const float *__restrict__ wts, int T, int dtype) {
+    const int S4 = S >> 2;
+    const long long total = (long long)B * S * S4;
+    const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int x4 = (int)(i % S4);
+        const int oy = (int)((i / S4) % S);
+        const int b = (int)(i / ((long long)S4 * S));
+        const int s0 = __ldg(start + oy);
+        const float *w = wts + (long long)oy * T;
+        int q[3][4];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float4 *src = reinterpret_cast<const float4 *>(in + (((long long)b * 3 + c) * Hin + s0) * S) + x4;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            for (int t = 0; t < T; ++t) {
+                const float wt = __ldg(w + t);
+                const float4 v = __ldg(src + (long long)t * S4);
+                a0 = fmaf(wt, v.x, a0); a1 = fmaf(wt, v.y, a1); a2 = fmaf(wt, v.z, a2); a3 = fmaf(wt, v.w, a3);
+            }
+            q[c][0] = round_u8(a0); q[c][1] = round_u8(a1); q[c][2] = round_u8(a2); q[c][3] = round_u8(a3);
+            *reinterpret_cast<uint32_t *>(rgb_small + (((long long)b * 3 + c) * S + oy) * S + 4 * x4) =
+                (uint32_t)q[c][0] | ((uint32_t)q[c][1] << 8) | ((uint32_t)q[c][2] << 16) | ((uint32_t)q[c][3] << 24);
+        }
+        uint4 *xo = reinterpret_cast<uint4 *>(reinterpret_cast<uint16_t *>(x) + (((long long)b * S + oy) * S + 4 * x4) * 8);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int L = (19595 * q[0][k] + 38470 * q[1][k] + 7471 * q[2][k] + 0x8000) >> 16;   // Pillow convert('L')
+            const float lf = __fdiv_rn((float)L, 255.f);
+            float n[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) n[c] = __fdiv_rn(__fsub_rn(lf, mean[c]), stdv[c]);
+            xo[k] = make_uint4(pack2(n[0], n[1], dtype), pack2(n[2], 0.f, dtype), 0u, 0u);
+        }
     }
 }
 
@@ -374,6 +510,32 @@ extern "C" int havc_resample_h(const uint8_t *in, float *out, long long rows, in
                                const float *weights, int taps, void *stream) {
     HAVC_CHECK_ARG(in && out && start && weights && taps > 0, "havc_resample_h: bad arguments");
     HAVC_CHECK_ARG(Win * sizeof(float) <= 96 * 1024, "havc_resample_h: row too wide for shared memory");
+    static const bool legacy_h = getenv("HAVC_B200_LEGACY_PIXEL") != nullptr;   // A/B switch for profiling
+    constexpr int kR = 4;
+    if (!legacy_h && Wout <= 640 && taps <= 48 && (Win & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 3) == 0 && rows >= kR) {
+        const int kt = taps <= 8 ? 8 : (taps <= 24 ? 24 : (taps <= 40 ? 40 : 48));
+        const int block = ((Wout + 31) / 32) * 32;
+        const size_t sm = 2 * (size_t)kR * (Win + kt) * sizeof(float);
+        if (sm <= 200 * 1024 && kR * (Win / 4) <= 6 * block) {
+            static bool attr3 = false;
+            if (!attr3) {
+                HAVC_CHECK_CUDA(cudaFuncSetAttribute(resample_h_rows_kernel<8, kR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                HAVC_CHECK_CUDA(cudaFuncSetAttribute(resample_h_rows_kernel<24, kR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                HAVC_CHECK_CUDA(cudaFuncSetAttribute(resample_h_rows_kernel<40, kR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                HAVC_CHECK_CUDA(cudaFuncSetAttribute(resample_h_rows_kernel<48, kR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                attr3 = true;
+            }
+            const long long groups = (rows + kR - 1) / kR;
+            const int g3 = (int)(groups < (long long)num_sms() ? groups : (long long)num_sms());
+            cudaStream_t st = (cudaStream_t)stream;
+            if (kt == 8) resample_h_rows_kernel<8, kR><<<g3, block, sm, st>>>(in, out, rows, Win, Wout, start, weights, taps);
+            else if (kt == 24) resample_h_rows_kernel<24, kR><<<g3, block, sm, st>>>(in, out, rows, Win, Wout, start, weights, taps);
+            else if (kt == 40) resample_h_rows_kernel<40, kR><<<g3, block, sm, st>>>(in, out, rows, Win, Wout, start, weights, taps);
+            else resample_h_rows_kernel<48, kR><<<g3, block, sm, st>>>(in, out, rows, Win, Wout, start, weights, taps);
+            HAVC_LAUNCHED();
+            return HAVC_OK;
+        }
+    }
     if (Wout <= 512 && taps <= 48 && (Win & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 3) == 0 && 2 * (Win + 48) * sizeof(float) <= 96 * 1024) {
         static bool attr2 = false;
         if (!attr2) {
@@ -411,8 +573,13 @@ extern "C" int havc_pre_vertical(const float *in, uint8_t *rgb_small, void *x, i
                                  const float *weights, int taps, int dtype, void *stream) {
     HAVC_CHECK_ARG(in && rgb_small && x && start && weights && taps > 0 && (dtype == HAVC_F16 || dtype == HAVC_BF16),
                    "havc_pre_vertical: bad arguments");
-    pre_vertical_kernel<<<grid1d((long long)B * S * S, 256), 256, 0, (cudaStream_t)stream>>>(
-        in, rgb_small, x, B, Hin, S, start, weights, taps, dtype);
+    static const bool legacy_v = getenv("HAVC_B200_LEGACY_PIXEL") != nullptr;   // A/B switch for profiling
+    if (!legacy_v && (S & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(rgb_small) & 3) == 0)
+        pre_vertical4_kernel<<<grid1d((long long)B * S * (S / 4), 256), 256, 0, (cudaStream_t)stream>>>(
+            in, rgb_small, x, B, Hin, S, start, weights, taps, dtype);
+    else
+        pre_vertical_kernel<<<grid1d((long long)B * S * S, 256), 256, 0, (cudaStream_t)stream>>>(
+            in, rgb_small, x, B, Hin, S, start, weights, taps, dtype);
     HAVC_LAUNCHED();
     return HAVC_OK;
 }
@@ -446,8 +613,13 @@ extern "C" int havc_head(const void *res, int Cs, const float *w11, const float 
 extern "C" int havc_resample_v(const uint8_t *in, float *out, long long planes, int Hin, int Hout, int W,
                                const int *start, const float *weights, int taps, void *stream) {
     HAVC_CHECK_ARG(in && out && start && weights && taps > 0, "havc_resample_v: bad arguments");
-    resample_v_kernel<<<grid1d(planes * Hout * W, 256), 256, 0, (cudaStream_t)stream>>>(in, out, planes, Hin, Hout, W,
-                                                                                     start, weights, taps);
+    static const bool legacy_v = getenv("HAVC_B200_LEGACY_PIXEL") != nullptr;   // A/B switch for profiling
+    if (!legacy_v && (W & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0)
+        resample_v4_kernel<<<grid1d(planes * Hout * (W / 4), 256), 256, 0, (cudaStream_t)stream>>>(
+            in, reinterpret_cast<float4 *>(out), planes, Hin, Hout, W, start, weights, taps);
+    else
+        resample_v_kernel<<<grid1d(planes * Hout * W, 256), 256, 0, (cudaStream_t)stream>>>(in, out, planes, Hin, Hout, W,
+                                                                                         start, weights, taps);
     HAVC_LAUNCHED();
     return HAVC_OK;
 }

@@ -245,6 +245,75 @@ class FilterBank:
                                                       float(gamma_min), stream), "luma_adjusted_levels")
 
 
+    # ---- HAVC_stabilizer per-frame stages (vsdeoldify/__init__.py:2823-2861; vsfilters.py:525-641) ----------------
+    def chroma_tweak(self, img, out, sat=1.0, bright=0.0, hue=0, hue_adjust="none", luma_merge: Optional[Tuple[float, float]] = None,
+                     stream: int = 0) -> bool:
+        """image_chroma_tweak (imfilters.py:540-550 -> restcolor.np_image_chroma_tweak :288-342), optionally fused with the luma
+        merge of vs_sc_chroma_bright_tweak (img_dark = tweaked, img_white = img).  Returns False when it is the identity."""
+        if sat == 1 and bright == 0 and hue == 0 and hue_adjust == "none":
+            if luma_merge is None:
+                return False
+            # the tweak returns img itself, but the float luma merge of img with img still truncates (a*(1-m) + a*m can land
+            # just below a), so it runs
+            _lib.check(self.lib.havc_luma_masked_merge(img.data_ptr(), img.data_ptr(), img.data_ptr(), out.data_ptr(), *self._dims(),
+                                                       float(luma_merge[0]), float(luma_merge[1]), 1.0, stream), "luma_merge")
+            return True
+        rng, sat2, hue2, weight = None, 1.0, 0, 0.0
+        if hue_adjust not in ("none", ""):
+            p = parse_hue_adjust(hue_adjust)
+            if p is not None:
+                rng = hue_ranges_struct(p[0])
+                if rng is None:
+                    raise FilterError("HybridAVC: unknown hue name: " + str(p[0]))
+                sat2, hue2, weight = p[1], p[2], p[3]
+        lm = luma_merge is not None
+        _lib.check(self.lib.havc_chroma_tweak(img.data_ptr(), out.data_ptr(), *self._dims(), float(sat), float(bright), int(hue),
+                                              C.byref(rng) if rng is not None else None, float(sat2), int(hue2), float(weight),
+                                              int(lm), float(luma_merge[0]) if lm else 0.0, float(luma_merge[1]) if lm else 0.0,
+                                              self.simd, stream), "chroma_tweak")
+        return True
+
+    def dark_tweak(self, img, out, dark_threshold=0.3, dark_amount=0.8, dark_hue_adjust="none", stream: int = 0):
+        """vs_sc_dark_tweak.merge_frame (vsfilters.py:604-636): image_tweak(bright, sat, hue_range) merged back by luma."""
+        d_threshold = 0.1
+        d_white = min(max(dark_threshold, d_threshold), 0.50)
+        d_sat = min(max(1.1 - dark_amount, 0.10), 0.80)
+        d_bright = -min(max(dark_amount, 0.20), 0.90)
+        t = self.tmp[2]
+        self.image_tweak(img, t, sat=d_sat, bright=d_bright, hue_range=dark_hue_adjust, stream=stream)   # never the identity
+        _lib.check(self.lib.havc_luma_masked_merge(img.data_ptr(), img.data_ptr(), t.data_ptr(), out.data_ptr(), *self._dims(),
+                                                   float(d_threshold), float(d_white), 1.0, stream), "dark_tweak.luma_merge")
+
+    def stabilizer_stages(self, img, out, dark=False, dark_p=(0.2, 0.8), smooth=False, smooth_p=(0.3, 0.7, 0.9, 0.0, "none"),
+                          colormap_adjust: str = "none", stream: int = 0) -> bool:
+        """The per-frame stages of HAVC_stabilizer on S x S batches, in the reference's order: vs_dark_tweak,
+        vs_chroma_bright_tweak, vs_colormap.  The result is in `out`; returns False if no stage ran (out untouched)."""
+        self._chk(img), self._chk(out)
+        cur, ping = img, [out, self.tmp[0]]
+
+        def nxt():
+            return ping[0] if cur is not ping[0] else ping[1]
+        if dark:
+            dst = nxt()
+            self.dark_tweak(cur, dst, dark_p[0], dark_p[1], (dark_p[2] if len(dark_p) > 2 else "none").lower(), stream)
+            cur = dst
+        if smooth:
+            dst = nxt()
+            adj = (smooth_p[4] if len(smooth_p) > 4 else "none").lower()
+            if self.chroma_tweak(cur, dst, sat=smooth_p[2], bright=-smooth_p[3], hue_adjust=adj,
+                                 luma_merge=(smooth_p[0], smooth_p[1]), stream=stream):
+                cur = dst
+        if colormap_adjust not in ("none", ""):
+            dst = nxt()
+            if self.chroma_tweak(cur, dst, hue_adjust=colormap_adjust, stream=stream):
+                cur = dst
+        if cur is img:
+            return False
+        if cur is not out:
+            self.blend(cur, cur, out, 0.0, stream)
+        return True
+
+
 class MergeEngine:
     """HAVC_merge on batches of planar RGB24 host frames: H2D -> FilterBank.combine / std.Merge -> D2H."""
 
@@ -275,6 +344,66 @@ class MergeEngine:
                                                           self.d_out.numel(), float(weight), st), "vs_merge")
             else:
                 self.bank.combine(self.d_a, self.d_b, self.d_out, method, weight, cmc_p, lmm_p, alm_p, crt_p, stream=st)
+            self.h_out.copy_(self.d_out, non_blocking=True)
+        self.stream.synchronize()
+        return self.h_out[:n].numpy().copy()
+
+
+class StabilizerEngine:
+    """HAVC_stabilizer's per-frame path on batches of planar RGB24 host frames (vsdeoldify/__init__.py:2748-2873, stab=False):
+    Spline64 squeeze to S x S (:2804) -> vs_dark_tweak / vs_chroma_bright_tweak / vs_colormap -> _clip_chroma_resize (:3545-3554:
+    Spline64 back to W x H + full-resolution luma transplant), one CUDA graph per batch."""
+
+    def __init__(self, width: int, height: int, frame_size: int, stages: dict, batch: int = 8, device: str = "cuda:0",
+                 resize_kernel: str = "spline64"):
+        from .engine import _Tables
+        self.lib = _lib.lib()
+        self.dev = torch.device(device)
+        torch.cuda.set_device(self.dev)
+        self.B, self.H, self.W, self.S = batch, height, width, frame_size
+        B, H, W, S = batch, height, width, frame_size
+        self.stages = stages
+        self.bank = FilterBank(B, S, S, self.dev)
+        self.t_down_h, self.t_down_v = _Tables(W, S, resize_kernel, self.dev), _Tables(H, S, resize_kernel, self.dev)
+        self.t_up_h, self.t_up_v = _Tables(S, W, resize_kernel, self.dev), _Tables(S, H, resize_kernel, self.dev)
+        u8, f32 = dict(dtype=torch.uint8, device=self.dev), dict(dtype=torch.float32, device=self.dev)
+        self.d_in, self.d_out = torch.empty(B, 3, H, W, **u8), torch.empty(B, 3, H, W, **u8)
+        self.h_in = torch.empty(B, 3, H, W, dtype=torch.uint8).pin_memory()
+        self.h_out = torch.empty(B, 3, H, W, dtype=torch.uint8).pin_memory()
+        self.tmp_f = torch.empty(B, 3, H, S, **f32)
+        self.small, self.small_out = torch.empty(B, 3, S, S, **u8), torch.empty(B, 3, S, S, **u8)
+        self.x_scratch = torch.empty(B, S, S, 8, dtype=torch.float16, device=self.dev)    # pre_vertical's network-input by-product
+        self.stream = torch.cuda.Stream(device=self.dev)
+        with torch.cuda.stream(self.stream):
+            self.d_in.zero_()
+            self._launch(self.stream.cuda_stream)          # warm-up also surfaces FilterError for unsupported parameters
+        self.stream.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, stream=self.stream):
+            self._launch(torch.cuda.current_stream().cuda_stream)
+        self.stream.synchronize()
+
+    def _launch(self, st: int):
+        lib, B, S, W, H, chk = self.lib, self.B, self.S, self.W, self.H, _lib.check
+        td, tv, uh, uv = self.t_down_h, self.t_down_v, self.t_up_h, self.t_up_v
+        chk(lib.havc_resample_h(self.d_in.data_ptr(), self.tmp_f.data_ptr(), B * 3 * H, W, S, td.start.data_ptr(), td.wt.data_ptr(),
+                                td.taps, st), "squeeze.h")
+        chk(lib.havc_pre_vertical(self.tmp_f.data_ptr(), self.small.data_ptr(), self.x_scratch.data_ptr(), B, H, S, tv.start.data_ptr(),
+                                  tv.w.data_ptr(), tv.taps, 0, st), "squeeze.v")
+        res = self.small_out if self.bank.stabilizer_stages(self.small, self.small_out, stream=st, **self.stages) else self.small
+        chk(lib.havc_resample_v(res.data_ptr(), self.tmp_f.data_ptr(), B * 3, S, H, S, uv.start.data_ptr(), uv.w.data_ptr(), uv.taps, st),
+            "unsqueeze.v")
+        chk(lib.havc_post_horizontal(self.tmp_f.data_ptr(), self.d_in.data_ptr(), self.d_out.data_ptr(), B, S, H, W, uh.start.data_ptr(),
+                                     uh.wt.data_ptr(), uh.taps, 1, st), "unsqueeze.h")
+
+    def process_batch(self, frames: np.ndarray, skip=None) -> np.ndarray:
+        """frames: uint8 [n<=B, 3, H, W] -> uint8 [n, 3, H, W] (the stabilizer's selectors run with scenechange=False: no gate)."""
+        n = frames.shape[0]
+        assert n <= self.B and frames.shape[1:] == (3, self.H, self.W) and frames.dtype == np.uint8
+        self.h_in[:n].copy_(torch.from_numpy(np.ascontiguousarray(frames)))
+        with torch.cuda.stream(self.stream):
+            self.d_in.copy_(self.h_in, non_blocking=True)
+            self.graph.replay()
             self.h_out.copy_(self.d_out, non_blocking=True)
         self.stream.synchronize()
         return self.h_out[:n].numpy().copy()

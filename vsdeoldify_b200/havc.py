@@ -75,8 +75,9 @@ def load_state_dict(weights_name: str, models_dir: str = model_dir) -> Dict[str,
 class _ColorizedClip:
     """frame_fn of the output clip: batches source frames through the engine, caches results by frame number."""
 
-    def __init__(self, clip, engine, scenechange: bool, batch: int):
+    def __init__(self, clip, engine, scenechange: bool, batch: int, run=None):
         self.clip, self.engine = clip, engine
+        self.run = run if run is not None else engine.colorize_batch
         self.scenechange, self.B = scenechange, batch
         self.cache: "OrderedDict[int, object]" = OrderedDict()
         self.lock = threading.Lock()
@@ -94,7 +95,7 @@ class _ColorizedClip:
             skip = None
             if self.scenechange:    # vsslib/vsmodels.py:221-224: only scene-change frames are colourised
                 skip = np.array([not (i == 0 or f.props.get("_SceneChangePrev", 0) == 1) for i, f in zip(range(n, n1), srcs)])
-            out = self.engine.colorize_batch(batch, skip=skip)
+            out = self.run(batch, skip=skip)
             for i, f in zip(range(n, n1), srcs):
                 g = f.copy()                              # all props of the source frame survive (vsutils.py:92-95)
                 for p in range(3):
@@ -259,6 +260,59 @@ def HAVC_merge(clipa=None, clipb=None, clip_luma=None, weight: float = 0.5, meth
         if vs is vs_shim else _wrap_real_vs(clipa, guarded)
 
 
+_COLORMAP_NAMES = ['none', 'blue->brown', 'blue->red', 'blue->green', 'green->brown', 'green->red', 'green->blue', 'redrose->brown',
+                   'redrose->blue', "red->brown", 'red->blue', 'yellow->rose']
+_COLORMAP_HUE = ["none", "180:280|+140", "180:280|+100", "180:280|+220", "80:180|+260", "80:180|+220", "80:180|+140",
+                 "300:360,0:20|+40", "300:360,0:20|+260", "320:360|+50", "300:360|+260", "30:90|+300"]
+_COLORMAP_W = ["1.0", "0.90", "0.80", "0.75"]
+
+
+def _get_colormap(ColorMap: str = "red->brown", ColorTune: str = "light") -> str:
+    """havc_utils._get_colormap (havc_utils.py:552-581): a colour-map name -> its "chroma adjustment" string; anything
+    else must already be a valid chroma adjustment and is returned as is."""
+    if ColorTune not in _COLOR_TUNE:
+        _raise("HAVC_main: ColorTune choice is invalid for '" + ColorTune + "'")
+    cm = ColorMap.lower()
+    if cm in _COLORMAP_NAMES:
+        return _COLORMAP_HUE[_COLORMAP_NAMES.index(cm)] + "," + _COLORMAP_W[_COLOR_TUNE.index(ColorTune)]
+    from .filters import parse_hue_adjust
+    if parse_hue_adjust(cm) is None:
+        _raise("HAVC_main: ColorMap choice is invalid for '" + cm + "'")
+    return cm
+
+
+def HAVC_stabilizer(clip, dark: bool = False, dark_p: Sequence = (0.2, 0.8), smooth: bool = False,
+                    smooth_p: Sequence = (0.3, 0.7, 0.9, 0.0, "none"), stab: bool = False,
+                    stab_p: Sequence = (5, 'A', 1, 15, 0.2, 0.8), colormap: str = "none", render_factor: int = 24,
+                    device_index: int = 0):
+    """Drop-in for vsdeoldify.HAVC_stabilizer (vsdeoldify/__init__.py:2748-2873) for its per-frame stages: Spline64 squeeze
+    to render_factor*16, vs_dark_tweak (`dark`), vs_chroma_bright_tweak (`smooth`), vs_colormap (`colormap`), then
+    _clip_chroma_resize back to the clip's size with the original luma.  The temporal chroma stabiliser (`stab=True`:
+    vs_chroma_stabilizer_ex + vs_reduce_flicker average neighbouring frames - row N3 of the scope table) raises."""
+    if getattr(clip.format, "id", clip.format) != getattr(vs.RGB24, "id", vs.RGB24):
+        _raise("HAVC_stabilizer: only RGB24 input is handled by the B200 build (convert_format_RGB24 is a 'next' row)")
+    if render_factor != 0 and render_factor not in range(16, 65):
+        _raise("HAVC_stabilizer: render_factor must be between: 16-64")                   # :2796
+    if stab:
+        _raise("HAVC_stabilizer: the temporal chroma stabilizer (stab=True) is not built (cross-frame filter, scope row N3)")
+    if not torch.cuda.is_available():
+        _raise("HAVC_stabilizer: CUDA is not available")
+    if render_factor == 0:
+        render_factor = min(max(math.trunc(0.4 * clip.width / 16), 16), 32)               # :2799
+    frame_size = min(render_factor * 16, clip.width)                                      # :2803
+    cm = colormap.lower()
+    colormap_adjust = _get_colormap(cm) if cm not in ("none", "") else "none"             # :2827-2832
+    stages = dict(dark=bool(dark), dark_p=list(dark_p), smooth=bool(smooth), smooth_p=list(smooth_p), colormap_adjust=colormap_adjust)
+    from .filters import FilterError, StabilizerEngine
+    try:
+        engine = StabilizerEngine(clip.width, clip.height, frame_size, stages, batch=_BATCH, device=f"cuda:{device_index}")
+    except (ValueError, FilterError) as e:
+        _raise("HAVC_stabilizer: " + str(e))
+    fn = _ColorizedClip(clip, engine, False, _BATCH, run=engine.process_batch)
+    return vs_shim.VideoNode(clip.num_frames, clip.width, clip.height, clip.format, fn, clip.fps_num, clip.fps_den) \
+        if vs is vs_shim else _wrap_real_vs(clip, fn)
+
+
 class ModelImageRender:
     """Drop-in for vsdeoldify.deoldify.visualize.ModelImageRender (deoldify/visualize.py:41-137): the reference's own
     per-image entry point (`get_transformed_image(PIL image) -> PIL image`; BASELINE cfg1 runs it on still images).
@@ -385,10 +439,12 @@ def HAVC_main(clip, Preset: str = 'Medium', FrameInterp: int = 0, ColorModel: st
               EnableDeepEx: bool = False, enable_fp16: bool = True, debug_level: int = 0, device_index: int = 0, **kw):
     """Drop-in for vsdeoldify.HAVC_main (vsdeoldify/__init__.py:101-330 -> HAVC_main_presets :469-912) restricted to the
     per-frame image-model branch: the string presets are turned into HAVC_colorizer's numeric arguments exactly as the
-    reference does (colour-model split, CombMethod, VideoTune weight, ColorTune / ColorFix -> ddtweak + hue range).
-    The HAVC_stabilizer step the reference appends (dark / smooth / colormap post filters and their extra chroma-resize
-    round trip; row N1 of the scope table) is NOT applied: a warning is logged.  Exemplar models, DDColor, tiling
-    presets (placebo / veryslow), ColorMap / ColorTemp / BlackWhiteTune raise."""
+    reference does (colour-model split, CombMethod, VideoTune weight, ColorTune / ColorFix -> ddtweak + hue range, ColorMap ->
+    "chroma adjustment"), followed by the HAVC_stabilizer step the presets append (:896-910): colormap only for the fast
+    presets, dark + smooth + colormap for slower / slow / medium.  Where the reference would also switch on the TEMPORAL
+    chroma stabiliser (two-model presets with ColorTune != 'none'; scope row N3) the per-frame stages still run and a warning
+    says the temporal one is skipped.  Exemplar models, DDColor, tiling presets (placebo / veryslow), ColorTemp /
+    BlackWhiteTune raise."""
     rf = _get_render_factor(Preset)
     speed_id = _PRESETS.index(Preset.lower())
     if EnableDeepEx or FrameInterp != 0:
@@ -407,11 +463,18 @@ def HAVC_main(clip, Preset: str = 'Medium', FrameInterp: int = 0, ColorModel: st
             _raise("HAVC_main: CombMethod choice is invalid for '" + CombMethod + "'")
         dd_method = _COMB_METHOD[CombMethod.lower()]
     dd_tweak, hue_range = _get_color_tune(ColorTune, ColorFix, dd_model)
-    for label, v in (("ColorMap", ColorMap), ("ColorTemp", ColorTemp), ("BlackWhiteTune", BlackWhiteTune)):
+    for label, v in (("ColorTemp", ColorTemp), ("BlackWhiteTune", BlackWhiteTune)):
         if str(v).lower() != "none":
-            _raise(f"HAVC_main: {label} post filters are not built yet (HAVC_stabilizer is row N1 of the scope table)")
-    vs.core.log_message(vs.MESSAGE_TYPE_WARNING,
-                        "HAVC_main (B200 build): the HAVC_stabilizer post step of the reference presets is not applied")
-    return HAVC_colorizer(clip, method=dd_method, mweight=weight, deoldify_p=[do_model, rf, 1.0, 0.0],
-                          ddcolor_p=[dd_model, rf, 1.0, 0.0, enable_fp16], ddtweak=dd_tweak, ddtweak_p=[DEF_TWEAK_p, hue_range],
-                          device_index=device_index, debug_level=debug_level)
+            _raise(f"HAVC_main: {label} post filters are not built (temporal / B&W tuning filters are outside the per-frame path)")
+    tune = (ColorTune or "none").lower()
+    chroma_adjust = "none" if str(ColorMap).lower() in ("none", "") else _get_colormap(str(ColorMap), tune)   # havc_utils.py:519-548
+    clip_colored = HAVC_colorizer(clip, method=dd_method, mweight=weight, deoldify_p=[do_model, rf, 1.0, 0.0],
+                                  ddcolor_p=[dd_model, rf, 1.0, 0.0, enable_fp16], ddtweak=dd_tweak, ddtweak_p=[DEF_TWEAK_p, hue_range],
+                                  device_index=device_index, debug_level=debug_level)
+    if speed_id > 4:                     # 'fast', 'faster', 'veryfast': only the colormap (:896-897)
+        return HAVC_stabilizer(clip_colored, colormap=chroma_adjust, device_index=device_index)
+    if dd_method != 0 and tune != "none":    # :903-906 stab=stab_enabled
+        vs.core.log_message(vs.MESSAGE_TYPE_WARNING, "HAVC_main (B200 build): the temporal chroma stabilizer of this preset "
+                                                     "(HAVC_stabilizer stab=True) is not applied; its per-frame stages are")
+    return HAVC_stabilizer(clip_colored, dark=True, dark_p=[0.2, 0.8], colormap=chroma_adjust, smooth=True,
+                           smooth_p=[0.3, 0.7, 0.9, 0.0, "none"], stab=False, device_index=device_index)

@@ -200,7 +200,7 @@ def make_conv(src0: torch.Tensor, weight: torch.Tensor, out: torch.Tensor, taps,
               src1_single_tap: bool = False, src1_wi: int = 0, split_n: int = 0, out2: Optional[torch.Tensor] = None,
               c_store2: int = 0, residual2: Optional[torch.Tensor] = None, head_w: Optional[torch.Tensor] = None,
               head_out: Optional[torch.Tensor] = None, tma_store: Optional[bool] = None, leaky1: float = 0.0,
-              name: str = "") -> ConvOp:
+              pair: int = 0, name: str = "") -> ConvOp:
     """src0/src1: NHWC (or [P,B,H,W,C]) 16-bit device tensors; weight: packed [rows,taps,cin] or
     [batches,rows,taps,cin]; out: NHWC tensor written at pixel (h*up+oy, w*up+ox)."""
     d = ConvDesc()
@@ -274,5 +274,6 @@ def make_conv(src0: torch.Tensor, weight: torch.Tensor, out: torch.Tensor, taps,
         d.head_w, d.head_out = head_w.data_ptr(), head_out.data_ptr()
         d.head_stride_b, d.head_stride_h, d.head_stride_w = head_out.stride()[:3]
     d.tma_store = int(TMA_STORE_DEFAULT if tma_store is None else tma_store)
+    d.pair = int(pair)     # 0 = library default (CTA pairs on), 1 = force, -1 = single-CTA tiles
     keep += [out2, residual2, head_w, head_out]
     return ConvOp(d, keep, name=name)
