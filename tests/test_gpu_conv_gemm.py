@@ -256,3 +256,14 @@ def test_pair_batched_gemm_same_batch_only():
         torch.cuda.synchronize()
         err = (out.view(B, N, N) - ref).abs().max().item()
         assert err < 1e-3, (pair, err)
+
+
+# ---- fast epilogue with the TMA-loaded residual tile (staging buffer doubles as the residual source) ---------------------
+@pytest.mark.parametrize("pair", [-1, 1])
+def test_residual_tma_fast_epilogue_shapes(pair):
+    # ResNet bottleneck conv3 shapes: 1x1 + BN + residual + ReLU; BN tile 64 / 128 / 256, several tiles per CTA, ragged edges
+    _run_conv(2, 48, 48, [64], 256, 1, torch.float16, affine=True, residual=True, relu2=True, pair=pair)
+    _run_conv(4, 96, 96, [64], 256, 1, torch.float16, affine=True, residual=True, relu2=True, pair=pair)      # > 148 tiles
+    _run_conv(3, 20, 28, [128], 512, 1, torch.bfloat16, affine=True, residual=True, relu2=True, pair=pair)    # clipped boxes
+    _run_conv(2, 24, 24, [256], 64, 1, torch.float16, bias=True, residual=True, relu2=True, pair=pair)
+    _run_conv(2, 24, 24, [64], 128, 3, torch.float16, bias=True, residual=True, pair=pair)                      # no final ReLU

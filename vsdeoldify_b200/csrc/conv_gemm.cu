@@ -79,6 +79,9 @@ struct ConvParams {
     // cp.async.bulk.tensor stores (coalesced, clipped at the tensor bounds); stage_out_bytes = 128*BN*2
     int tma_store;
     uint32_t stage_out_bytes;
+    // fast epilogue only: the residual tile is TMA-loaded (tensor map tmO.m[1], same box and swizzle as the output) into the
+    // staging buffer ahead of the accumulator and read back from exactly the shared-memory words the result then overwrites
+    int res_tma;
     // fused 1x1 head: logits[pix][o] = sum_n y[n] * head_w[o][n]  (o < 3), written as fp32 [pix][4]; no tile store
     const float *head_w;
     float *head_out;
@@ -174,6 +177,16 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                  : "memory");
+}
+// One deterministic leader lane of the (fully active) warp.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
 }
 // ---- CTA-pair (cta_group::2) helpers ---------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -313,13 +326,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 2 + s); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 4);
     auto tearly_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 5 + s); };
+    const uint32_t res_bar = bar_base + 8u * (2 * kMaxStages + 7);
     volatile uint32_t *tmem_slot_ptr =
         reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
-    const int warp = threadIdx.x >> 5;
+    // Warp-uniform role / rank values are broadcast from lane 0 so that the compiler KNOWS they are uniform: the producer and the
+    // MMA issuer then run as convergent whole-warp code whose operands live in uniform registers, and only the TMA / MMA /
+    // commit instructions themselves are predicated on one elected lane.  (Issued from inside an `if (lane == 0)` region every
+    // tcgen05.mma cost a 20-instruction R2UR "waterfall"; ~190 instructions per K step made the issuing thread, not the
+    // tensor pipe, the limiter of the 3x3 convolutions: profiles/r01_ncu_resconv0_pair_issue_bound.txt.)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
     // work distribution: a "group" is one CTA (or one CTA pair); tiles are dealt round-robin to groups
-    const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+    const uint32_t rank = kPair ? __shfl_sync(0xffffffffu, cluster_ctarank(), 0) : 0u;
     const int group = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int ngroups = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     auto decode_tile = [&](int tile, int &nt, int &wt, int &ht, int &bt) {
@@ -347,6 +366,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             mbar_init(tempty_bar(s), kPair ? 512 : 256);   // pair: the leader's barrier collects both CTAs' epilogues
             mbar_init(tearly_bar(s), kPair ? 512 : 256);
         }
+        mbar_init(res_bar, 1);
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -361,65 +381,77 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     tc_fence_before();
     if (kPair) cluster_sync_all(); else __syncthreads();   // pair: the peer's barriers must be initialised before any remote signal
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot_ptr;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_ptr, 0);
 
     const int ksteps_per_tap = p.src1_single_tap ? p.chunks0 : (p.chunks0 + p.chunks1);
     const int ksteps_main = p.n_taps * ksteps_per_tap;
     const int ksteps = ksteps_main + (p.src1_single_tap ? p.chunks1 : 0);
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = group; tile < p.total_tiles; tile += ngroups) {
-                int nt, wt, ht, bt;
-                decode_tile(tile, nt, wt, ht, bt);
-                const int n0 = nt * p.BN;
-                const int w0 = wt * p.bw, h0 = ht * p.bh, b0 = bt * p.bb;
-                for (int ks = 0; ks < ksteps; ++ks) {
-                    int cw = w0, ch = h0, cp = 0, wi = p.src1_wi, kc;
-                    bool from1;
-                    if (ks < ksteps_main) {
-                        const int tap = ks / ksteps_per_tap;
-                        kc = ks - tap * ksteps_per_tap;
-                        cw += p.dw[tap]; ch += p.dh[tap]; cp = p.tp[tap]; wi = p.twi[tap];
-                        from1 = kc >= p.chunks0;
-                        if (from1) kc -= p.chunks0;
-                    } else {   // single-tap side source
-                        kc = ks - ksteps_main;
-                        from1 = true;
-                    }
-                    mbar_wait(empty_bar(stage), phase ^ 1u);
-                    const uint32_t sa = smem_base + stage * p.stage_bytes;
-                    const uint32_t sb = sa + kABytes;
-                    const int wc = (from1 ? p.w_c1_off : 0) + kc * kChunkK;
-                    if (kPair) {
-                        // both CTAs' loads complete on the LEADER's full barrier, which expects the bytes of both
-                        if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2u * p.stage_bytes);
-                        const uint32_t fb = mapa_rank(full_bar(stage), 0);
-                        tma_load_5d_pair(sa, from1 ? &tmA1 : &tmA0, fb, kc * kChunkK, cw, ch, p.a_batched ? b0 : 0, cp);
-                        for (int l = 0; l < p.n_wloads; ++l)
-                            tma_load_4d_pair(sb + p.wl_smem[l], p.wl_map[l] ? &tmW1 : &tmW, fb, wc, wi,
-                                             n0 + p.wl_row0[l] + (int)rank * p.wl_rank_rows[l], p.b_batched ? b0 : 0);
-                    } else {
-                        mbar_arrive_expect_tx(full_bar(stage), p.stage_bytes);
-                        tma_load_5d(sa, from1 ? &tmA1 : &tmA0, full_bar(stage), kc * kChunkK, cw, ch, p.a_batched ? b0 : 0, cp);
-                        for (int l = 0; l < p.n_wloads; ++l)
-                            tma_load_4d(sb + p.wl_smem[l], &tmW, full_bar(stage), wc, wi, n0 + p.wl_row0[l], p.b_batched ? b0 : 0);
-                    }
-                    if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+        // ===================== TMA producer (whole warp, one elected lane issues) =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = group; tile < p.total_tiles; tile += ngroups) {
+            int nt, wt, ht, bt;
+            decode_tile(tile, nt, wt, ht, bt);
+            const int n0 = nt * p.BN;
+            const int w0 = wt * p.bw, h0 = ht * p.bh, b0 = bt * p.bb;
+            const int ab = p.a_batched ? b0 : 0, wb = p.b_batched ? b0 : 0;
+            int tap = 0, kc_in_tap = 0;
+            for (int ks = 0; ks < ksteps; ++ks) {
+                int cw = w0, ch = h0, cp = 0, wi = p.src1_wi, kc;
+                bool from1;
+                if (ks < ksteps_main) {
+                    kc = kc_in_tap;
+                    cw += p.dw[tap]; ch += p.dh[tap]; cp = p.tp[tap]; wi = p.twi[tap];
+                    from1 = kc >= p.chunks0;
+                    if (from1) kc -= p.chunks0;
+                    if (++kc_in_tap == ksteps_per_tap) { kc_in_tap = 0; ++tap; }
+                } else {   // single-tap side source
+                    kc = ks - ksteps_main;
+                    from1 = true;
                 }
+                mbar_wait(empty_bar(stage), phase ^ 1u);
+                const uint32_t sa = smem_base + stage * p.stage_bytes;
+                const uint32_t sb = sa + kABytes;
+                const int wc = (from1 ? p.w_c1_off : 0) + kc * kChunkK;
+                const CUtensorMap *ta = from1 ? &tmA1 : &tmA0;
+                if (kPair) {
+                    // both CTAs' loads complete on the LEADER's full barrier, which expects the bytes of both.  Within a CTA
+                    // pair the shared::cluster address of the leader's copy of a barrier is this CTA's address with the rank
+                    // bit (bit 24) cleared
+                    const uint32_t fb = full_bar(stage) & 0xFEFFFFFFu;
+                    if (elect_one()) {
+                        if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2u * p.stage_bytes);
+                        tma_load_5d_pair(sa, ta, fb, kc * kChunkK, cw, ch, ab, cp);
+                        tma_load_4d_pair(sb + p.wl_smem[0], &tmW, fb, wc, wi, n0 + p.wl_row0[0] + (int)rank * p.wl_rank_rows[0], wb);
+                        if (p.n_wloads > 1)
+                            tma_load_4d_pair(sb + p.wl_smem[1], &tmW1, fb, wc, wi, n0 + p.wl_row0[1] + (int)rank * p.wl_rank_rows[1], wb);
+                    }
+                } else {
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(full_bar(stage), p.stage_bytes);
+                        tma_load_5d(sa, ta, full_bar(stage), kc * kChunkK, cw, ch, ab, cp);
+                        tma_load_4d(sb + p.wl_smem[0], &tmW, full_bar(stage), wc, wi, n0 + p.wl_row0[0], wb);
+                        if (p.n_wloads > 1) tma_load_4d(sb + p.wl_smem[1], &tmW, full_bar(stage), wc, wi, n0 + p.wl_row0[1], wb);
+                    }
+                }
+                __syncwarp();
+                if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0 && rank == 0) {   // pair: the leader issues for both CTAs
+        // ===================== MMA issuer (whole warp, one elected lane issues; pair: the leader CTA issues for both) ======
+        if (rank == 0) {
             int stage = 0;
             uint32_t phase = 0;
             int as = 0;
             uint32_t aphase = 0;
             int seq = 0;   // index of this tile in the CTA's own sequence
+            const uint32_t idesc0 = p.idesc0, idesc1 = p.idesc1;
+            const bool two_parts = p.n_part1 > 0;
+            constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) /* version 1 */ | (2u << 29) /* SWIZZLE_128B */;
+            auto desc = [&](uint32_t lo) { return (static_cast<uint64_t>(kDescHi) << 32) | lo; };
             for (int tile = group; tile < p.total_tiles; tile += ngroups, ++seq) {
                 // Accumulator hand-over.  Normal double buffering: wait until the epilogue has fully drained this
                 // stage (its tile before last).  Staggered (BN > 256, 2*BN > 512 TMEM columns): stage 1 starts at
@@ -429,31 +461,39 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 mbar_wait(tempty_bar(as), aphase ^ 1u);
                 if (p.staggered && seq > 0) mbar_wait(tearly_bar(as ^ 1), ((uint32_t)(seq - 1) >> 1) & 1u);
                 tc_fence_after();
-                const uint32_t acc = tmem_base + as * p.acc_stride;
+                const uint32_t acc0 = tmem_base + as * p.acc_stride;
+                const uint32_t acc1 = acc0 + p.n_part0;
                 for (int ks = 0; ks < ksteps; ++ks) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
                     const uint32_t sa = smem_base + stage * p.stage_bytes;
-                    const uint32_t sb = sa + kABytes;
-                    const uint64_t da = make_sw128_desc(sa);
-                    const uint64_t db0 = make_sw128_desc(sb);
+                    // K-major SWIZZLE_128B descriptors (make_sw128_desc): only the 14-bit address field changes per stage / k
+                    const uint32_t a_lo = ((sa >> 4) & 0x3FFFu) | (1u << 16);
+                    const uint32_t b0_lo = (((sa + kABytes) >> 4) & 0x3FFFu) | (1u << 16);
+                    const uint32_t b1_lo = (((sa + kABytes + p.b1_smem_off) >> 4) & 0x3FFFu) | (1u << 16);
+                    const uint32_t first = ks > 0 ? 1u : 0u;
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < kChunkK / 16; ++k) {
-                        const uint32_t accum = (ks > 0 || k > 0) ? 1u : 0u;
-                        if (kPair) umma_f16_pair(acc, da + 2u * k, db0 + 2u * k, p.idesc0, accum);
-                        else umma_f16(acc, da + 2u * k, db0 + 2u * k, p.idesc0, accum);
-                        if (p.n_part1 > 0) {
-                            const uint64_t db1 = make_sw128_desc(sb + p.b1_smem_off);
-                            if (kPair) umma_f16_pair(acc + p.n_part0, da + 2u * k, db1 + 2u * k, p.idesc1, accum);
-                            else umma_f16(acc + p.n_part0, da + 2u * k, db1 + 2u * k, p.idesc1, accum);
+                        for (int k = 0; k < kChunkK / 16; ++k) {
+                            const uint32_t accum = k > 0 ? 1u : first;
+                            if (kPair) umma_f16_pair(acc0, desc(a_lo + 2u * k), desc(b0_lo + 2u * k), idesc0, accum);
+                            else umma_f16(acc0, desc(a_lo + 2u * k), desc(b0_lo + 2u * k), idesc0, accum);
+                            if (two_parts) {
+                                if (kPair) umma_f16_pair(acc1, desc(a_lo + 2u * k), desc(b1_lo + 2u * k), idesc1, accum);
+                                else umma_f16(acc1, desc(a_lo + 2u * k), desc(b1_lo + 2u * k), idesc1, accum);
+                            }
                         }
+                        // frees this smem stage (in both CTAs of a pair) when the MMAs retire
+                        if (kPair) umma_commit_pair(empty_bar(stage)); else umma_commit(empty_bar(stage));
                     }
-                    // frees this smem stage (in both CTAs of a pair) when the MMAs retire
-                    if (kPair) umma_commit_pair(empty_bar(stage)); else umma_commit(empty_bar(stage));
+                    __syncwarp();
                     if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
                 }
                 // accumulator complete -> epilogue (of both CTAs)
-                if (kPair) umma_commit_pair(tfull_bar(as)); else umma_commit(tfull_bar(as));
+                if (elect_one()) {
+                    if (kPair) umma_commit_pair(tfull_bar(as)); else umma_commit(tfull_bar(as));
+                }
+                __syncwarp();
                 if (++as == p.acc_stages) { as = 0; aphase ^= 1u; }
             }
         }
@@ -472,6 +512,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         int as = 0;
         uint32_t aphase = 0;
         int pbuf = 0, last_nt = -1;
+        uint32_t rphase = 0;
         const int nchunks = (p.BN + 31) >> 5;
         if (p.head_w != nullptr) {   // 1x1 head weights [3][BN] -> shared memory, once per CTA
             float *hw = sparams + 2 * 3 * kMaxBN;
@@ -492,8 +533,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             const int ow = wt * p.bw + rw, oh = ht * p.bh + rh, ob = bt * p.bb + rb;
             const bool valid = (ow < p.out_W) && (oh < p.out_H) && (ob < p.out_B);
 
-            if (p.tma_store && etid == 0)   // previous tile's bulk stores must have finished reading the staging buffer
+            if (p.tma_store && etid == 0) {  // previous tile's bulk stores must have finished reading the staging buffer
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                if (kFast && p.res_tma) {    // residual tile -> staging buffer (rows / channels outside the tensor arrive as zeros)
+                    mbar_arrive_expect_tx(res_bar, p.stage_out_bytes);
+                    for (int sub = 0; sub < (p.BN >> 6); ++sub)
+                        tma_load_5d(stage_out + sub * (kTileM * 128u), &tmO.m[1], res_bar, n0 + sub * 64, wt * p.bw, ht * p.bh,
+                                    bt * p.bb, 0);
+                }
+            }
             // stage this tile's per-column parameters in shared memory (double-buffered; reloaded only when the N tile
             // changes, i.e. never after the first tile of a launch with a single N tile)
             if (nt != last_nt) {
@@ -549,6 +597,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             const int od = p.out_dtype == HAVC_F32 ? HAVC_F32 : kDT, gn = p.group_n;
             const bool shuffle = p.shuffle != 0, has_scale = p.scale != nullptr, head = p.head_w != nullptr;
             const bool tma_store = p.tma_store != 0;
+            const bool res_tma = kFast && p.res_tma != 0;
             const float slope1 = p.slope1, lo2 = p.relu2 ? 0.f : -INFINITY;
             const long long pix_main = ob * p.osb + (long long)(oh * p.up + p.oy) * p.osh + (long long)(ow * p.up + p.ox) * p.osw;
             const long long pix_shuf = ob * p.osb + (long long)(oh * 2) * p.osh + (long long)(ow * 2) * p.osw;
@@ -696,8 +745,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 const int c0 = ci * 32;
                 const int n = n0 + c0;
                 uint4 rres[4];
-                const bool do_res = res_row != nullptr;
-                if (do_res) {
+                const bool do_res = res_tma || res_row != nullptr;
+                if (res_tma) {      // this thread's 64 bytes of the staged residual tile (the words its result will overwrite)
+                    const uint32_t sub = stage_out + (uint32_t)(c0 >> 6) * (kTileM * 128u) + (uint32_t)r * 128u;
+                    const uint32_t k16 = (uint32_t)(c0 & 63) >> 3;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g)
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rres[g].x), "=r"(rres[g].y), "=r"(rres[g].z), "=r"(rres[g].w)
+                                     : "r"(sub + (((k16 + g) ^ (r & 7u)) << 4)) : "memory");
+                } else if (do_res) {
 #pragma unroll
                     for (int g = 0; g < 4; ++g)
                         rres[g] = (n + 8 * g < c_store) ? __ldg(reinterpret_cast<const uint4 *>(res_row + 2 * (n + 8 * g))) : make_uint4(0, 0, 0, 0);
@@ -768,6 +824,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             if constexpr (kFast) {
                 __syncwarp();
                 tmem_ld32(tbase + half * 32, va);
+                if (res_tma) { mbar_wait(res_bar, rphase); rphase ^= 1u; }
                 for (int k = 0; k < n_my; k += 2) {
                     process_fast(half + 2 * k, k + 1 < n_my ? half + 2 * (k + 1) : -1, va, vb);
                     if (k + 1 < n_my) process_fast(half + 2 * (k + 1), k + 2 < n_my ? half + 2 * (k + 2) : -1, vb, va);
@@ -961,14 +1018,15 @@ extern "C" int havc_conv_gemm(const havc_conv_desc *d, void *stream) {
     static const bool legacy_split = getenv("HAVC_B200_SPLIT256") != nullptr;   // A/B switch for profiling
     p.n_part0 = d->BN > 256 ? (legacy_split ? 256 : ((d->BN / 2 + 15) / 16) * 16) : d->BN;
     p.n_part1 = d->BN - p.n_part0;
-    // CTA pairs (cta_group::2): d->pair = 1 forces, -1 forbids, 0 = library default (env HAVC_B200_PAIR=0 turns it off)
+    // CTA pairs (cta_group::2): d->pair = 1 forces, -1 forbids, 0 = library default (env HAVC_B200_PAIR=0 turns it off, =1 pairs every launch)
     static const char *pair_env = getenv("HAVC_B200_PAIR");
     const bool pair_default = !(pair_env && pair_env[0] == '0');
     // a pair shares ONE weight tile: with per-batch weights (b_batched) both M tiles must lie in the same batch
-    // Default policy (d->pair == 0), measured per layer shape on B200 (profiles/r01_pair_vs_single.txt): pairs win 3-8 % on
-    // long launches (>= ~55 tiles per SM: the 384^2 / 192^2 decoder convs, where the halved weight traffic dominates) and lose
-    // 3-15 % on short ones (cluster launch + the cross-SM barrier round trips are not amortised).
-    const bool pair_auto = pair_default && (long long)tiles_m * p.tiles_n >= 8192;
+    // Default policy (d->pair == 0), measured per layer shape on B200 (profiles/r01_pair_vs_single.txt): with the lean issue loop
+    // pairs win 2-10 % on every 3x3 convolution (MMA-bound: the halved weight reads relieve shared memory) and on long 1x1
+    // launches; short epilogue-bound 1x1 launches lose 3-5 % to the cross-SM barrier round trips.
+    const bool pair_everywhere = pair_env && pair_env[0] == '1';      // A/B switch for profiling
+    const bool pair_auto = pair_default && (pair_everywhere || d->n_taps > 1 || (long long)tiles_m * p.tiles_n >= 4096);
     const bool pair = (d->pair > 0 || (d->pair == 0 && pair_auto)) && tiles_m >= 2 && num_sms() >= 2 &&
                       (!d->b_batched || (p.tiles_w * p.tiles_h) % 2 == 0);
     p.total_tiles = (pair ? ceil_div(tiles_m, 2) : tiles_m) * p.tiles_n;
@@ -1005,6 +1063,7 @@ extern "C" int havc_conv_gemm(const havc_conv_desc *d, void *stream) {
                    d->head_w == nullptr && d->up == 1 && d->oy == 0 && d->ox == 0 && (!d->shuffle || d->group_n % 64 == 0))
                       ? 1 : 0;
     p.stage_out_bytes = p.tma_store ? (uint32_t)(kTileM * d->BN * 2) : 0u;
+    static const bool no_res_tma = getenv("HAVC_B200_NO_RES_TMA") != nullptr;   // A/B switch for profiling
     int stages = (227 * 1024 - 1024 - 256 - kEpiSmemFloats * (int)sizeof(float) - (int)p.stage_out_bytes) / (int)p.stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     HAVC_CHECK_ARG(stages >= 2, "havc_conv_gemm: tile too large for shared memory");
@@ -1083,6 +1142,17 @@ extern "C" int havc_conv_gemm(const havc_conv_desc *d, void *stream) {
     }
     StoreMaps tmO;
     memset(&tmO, 0, sizeof(tmO));
+    p.res_tma = (fast && d->residual != nullptr && !d->shuffle && !no_res_tma) ? 1 : 0;
+    if (p.res_tma) {     // same geometry as the output map: a 64-channel x box tile of the residual tensor per load
+        havc_act_view v;
+        memset(&v, 0, sizeof(v));
+        v.ptr = d->residual;
+        v.C = d->c_store; v.W = d->out_W; v.H = d->out_H; v.B = d->out_B; v.P = 1;
+        v.stride_w = d->res_stride_w; v.stride_h = d->res_stride_h; v.stride_b = d->res_stride_b;
+        v.stride_p = d->res_stride_b * d->out_B;
+        rc = encode_act(&tmO.m[1], v, d->dtype, d->box_w, d->box_h, d->box_b);
+        if (rc) return rc;
+    }
     if (p.tma_store) {
         const int nmaps = d->shuffle ? 4 : 1;
         for (int g = 0; g < nmaps; ++g) {
