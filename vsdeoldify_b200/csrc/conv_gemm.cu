@@ -32,7 +32,11 @@ static constexpr int kMaxStages = 8;
 static constexpr int kThreads = 384;   // 4 control warps + 8 epilogue warps
 static constexpr int kMaxBN = 320;      // parameter staging rows (BN <= 320)
 // epilogue shared memory: 2 x {bias,scale,shift}[kMaxBN] + head weights [3][kMaxBN] + head exchange [128][4]
+static constexpr int kWarpCols = 128;     // fast epilogue: columns one epilogue warp owns (BN <= 256, every other 32-column chunk)
+// the generic epilogue's arrays and the fast epilogue's per-warp slices (8 x 3 x kWarpCols floats) share the same bytes
 static constexpr int kEpiSmemFloats = 2 * 3 * kMaxBN + 3 * kMaxBN + 128 * 4;
+static_assert(8 * 3 * kWarpCols <= kEpiSmemFloats, "per-warp parameter slices must fit the epilogue area");
+static constexpr int kBarBytes = 512;    // mbarrier area in front of the epilogue parameters
 static constexpr uint32_t kTmemCols = 512;
 
 struct ConvParams {
@@ -303,6 +307,19 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap *tm, uint32_t src
                  : "memory");
 }
 
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_read_n(int n) {   // n = bulk groups that may still be reading shared memory
+    switch (n) {
+        case 0: bulk_wait_read<0>(); break;
+        case 1: bulk_wait_read<1>(); break;
+        case 2: bulk_wait_read<2>(); break;
+        default: bulk_wait_read<3>(); break;
+    }
+}
+
 // kDT: operand / 16-bit output type (HAVC_F16 or HAVC_BF16), fixed at compile time so the pack / unpack helpers fold.
 // kFast: the streamlined epilogue for the common case (16-bit output through the TMA-store staging buffer, whole N tiles,
 // no head / column split / staggered accumulators); the generic epilogue covers everything else.
@@ -326,7 +343,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 2 + s); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 4);
     auto tearly_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 5 + s); };
-    const uint32_t res_bar = bar_base + 8u * (2 * kMaxStages + 7);
+    auto wres_bar = [&](int w) { return bar_base + 8u * (2 * kMaxStages + 7 + w); };   // one per epilogue warp (fast epilogue)
     volatile uint32_t *tmem_slot_ptr =
         reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -366,7 +383,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             mbar_init(tempty_bar(s), kPair ? 512 : 256);   // pair: the leader's barrier collects both CTAs' epilogues
             mbar_init(tearly_bar(s), kPair ? 512 : 256);
         }
-        mbar_init(res_bar, 1);
+        for (int w = 0; w < 8; ++w) mbar_init(wres_bar(w), 1);
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -508,7 +525,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const int rw = r % p.bw;
         const int rh = (r / p.bw) % p.bh;
         const int rb = r / (p.bw * p.bh);
-        float *sparams = reinterpret_cast<float *>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));
+        float *sparams = reinterpret_cast<float *>(smem_raw + (bar_base + kBarBytes - smem_u32(smem_raw)));
         int as = 0;
         uint32_t aphase = 0;
         int pbuf = 0, last_nt = -1;
@@ -530,18 +547,162 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             int nt, wt, ht, bt;
             decode_tile(tile, nt, wt, ht, bt);
             const int n0 = nt * p.BN;
+            if constexpr (kFast) {
+                // ---------------- warp-private fast epilogue ----------------
+                // Every warp owns the 32 rows of its TMEM lane quarter and every other 32-column chunk: its slice of the per-
+                // column parameters, its 2 KB staging blocks (64B-swizzled), its own TMA stores (one per chunk, issued as soon
+                // as the chunk is staged), its own residual loads and barrier.  No CTA-wide barrier is left in the tile loop.
+                const int n_my = (nchunks - half + 1) >> 1;                    // <= 4
+                float *wp = sparams + (warp - 4) * (3 * kWarpCols);
+                const uint32_t my_res_bar = wres_bar(warp - 4);
+                const bool res_tma = p.res_tma != 0, has_scale = p.scale != nullptr, shuffle = p.shuffle != 0;
+                const int gn = p.group_n;
+                const float slope1 = p.slope1, lo2 = p.relu2 ? 0.f : -INFINITY;
+                // origin of this warp's 32-row slab inside the (bw x bh x bb) box (all box extents are powers of two)
+                const int row0 = q * 32;
+                const int sw0 = wt * p.bw + row0 % p.bw, sh0 = ht * p.bh + (row0 / p.bw) % p.bh, sb0 = bt * p.bb + row0 / (p.bw * p.bh);
+                auto block = [&](int ci) { return stage_out + (uint32_t)(ci * 4 + q) * 2048u; };
+                // parameters of my columns: fetched now (when the N tile changed), parked in shared memory after the accumulator wait
+                float pb[4], ps[4], pt[4];
+                const bool reload = nt != last_nt;
+                if (reload) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int n = n0 + (half + 2 * k) * 32 + lane;
+                        const bool in = k < n_my;
+                        pb[k] = (in && p.bias) ? __ldg(p.bias + n) : 0.f;
+                        ps[k] = (in && p.scale) ? __ldg(p.scale + n) : 1.f;
+                        pt[k] = (in && p.shift) ? __ldg(p.shift + n) : 0.f;
+                    }
+                    last_nt = nt;
+                }
+                if (lane == 0) {
+                    bulk_wait_read<0>();       // my stores of the previous tile have finished reading my staging blocks
+                    if (res_tma) {             // residual slab -> the same blocks (rows / channels outside the tensor arrive as zeros)
+                        mbar_arrive_expect_tx(my_res_bar, (uint32_t)n_my * 2048u);
+                        for (int k = 0; k < n_my; ++k)
+                            tma_load_5d(block(half + 2 * k), &tmO.m[1], my_res_bar, n0 + (half + 2 * k) * 32, sw0, sh0, sb0, 0);
+                    }
+                }
+                __syncwarp();
+                if (p.residual != nullptr) {   // pull the NEXT tile's residual rows towards L2 while this tile is processed
+                    const int tn = tile + ngroups;
+                    if (tn < p.total_tiles) {
+                        int nt2, wt2, ht2, bt2;
+                        decode_tile(tn, nt2, wt2, ht2, bt2);
+                        const int ow2 = wt2 * p.bw + rw, oh2 = ht2 * p.bh + rh, ob2 = bt2 * p.bb + rb;
+                        if (ow2 < p.out_W && oh2 < p.out_H && ob2 < p.out_B) {
+                            const uint8_t *row = reinterpret_cast<const uint8_t *>(p.residual) + 2ll * (ob2 * p.rsb + oh2 * p.rsh + ow2 * p.rsw);
+                            const int cbeg = nt2 * p.BN, cend = min(cbeg + p.BN, p.c_store);
+                            for (int c = cbeg + half * 64; c < cend; c += 128)
+                                asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 2 * c));
+                        }
+                    }
+                }
+                mbar_wait(tfull_bar(as), aphase);
+                tc_fence_after();
+                const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * p.acc_stride;
+                uint32_t va[32], vb[32];
+                __syncwarp();
+                tmem_ld32(tbase + half * 32, va);
+                if (reload) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        wp[k * 32 + lane] = pb[k];
+                        wp[kWarpCols + k * 32 + lane] = ps[k];
+                        wp[2 * kWarpCols + k * 32 + lane] = pt[k];
+                    }
+                    __syncwarp();
+                }
+                if (res_tma) { mbar_wait(my_res_bar, rphase); rphase ^= 1u; }
+                const uint32_t swz = ((uint32_t)lane >> 1) & 3u;               // SWIZZLE_64B: 16-byte chunk index ^= address bits [7:8]
+                auto chunk = [&](int k, uint32_t(&vc)[32], uint32_t(&vn)[32]) {
+                    const int ci = half + 2 * k;
+                    const uint32_t rowaddr = block(ci) + (uint32_t)lane * 64u;
+                    uint4 rres[4];
+                    if (res_tma) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g)
+                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rres[g].x), "=r"(rres[g].y), "=r"(rres[g].z), "=r"(rres[g].w)
+                                         : "r"(rowaddr + (((uint32_t)g ^ swz) << 4)) : "memory");
+                    }
+                    tmem_ld_wait();
+                    if (k + 1 < n_my) {
+                        __syncwarp();
+                        tmem_ld32(tbase + (ci + 2) * 32, vn);
+                    }
+                    const float *sb = wp + k * 32;
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        float y[16];
+                        const float4 *b4 = reinterpret_cast<const float4 *>(sb + 16 * hh);
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const float4 bv = b4[g];
+                            const float t0 = __uint_as_float(vc[16 * hh + 4 * g + 0]) + bv.x, t1 = __uint_as_float(vc[16 * hh + 4 * g + 1]) + bv.y;
+                            const float t2 = __uint_as_float(vc[16 * hh + 4 * g + 2]) + bv.z, t3 = __uint_as_float(vc[16 * hh + 4 * g + 3]) + bv.w;
+                            y[4 * g + 0] = fmaxf(t0, t0 * slope1);
+                            y[4 * g + 1] = fmaxf(t1, t1 * slope1);
+                            y[4 * g + 2] = fmaxf(t2, t2 * slope1);
+                            y[4 * g + 3] = fmaxf(t3, t3 * slope1);
+                        }
+                        if (has_scale) {
+                            const float4 *s4 = reinterpret_cast<const float4 *>(sb + kWarpCols + 16 * hh);
+                            const float4 *t4 = reinterpret_cast<const float4 *>(sb + 2 * kWarpCols + 16 * hh);
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                const float4 sv = s4[g], tv = t4[g];
+                                y[4 * g + 0] = fmaf(y[4 * g + 0], sv.x, tv.x);
+                                y[4 * g + 1] = fmaf(y[4 * g + 1], sv.y, tv.y);
+                                y[4 * g + 2] = fmaf(y[4 * g + 2], sv.z, tv.z);
+                                y[4 * g + 3] = fmaf(y[4 * g + 3], sv.w, tv.w);
+                            }
+                        }
+                        if (res_tma) {
+                            const uint32_t rr[8] = {rres[2 * hh].x, rres[2 * hh].y, rres[2 * hh].z, rres[2 * hh].w,
+                                                    rres[2 * hh + 1].x, rres[2 * hh + 1].y, rres[2 * hh + 1].z, rres[2 * hh + 1].w};
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float2 f = unpack2(rr[j], kDT);
+                                y[2 * j] += f.x;
+                                y[2 * j + 1] += f.y;
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) y[j] = fmaxf(y[j], lo2);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowaddr + (((uint32_t)(2 * hh) ^ swz) << 4)), "r"(pack2(y[0], y[1], kDT)),
+                                     "r"(pack2(y[2], y[3], kDT)), "r"(pack2(y[4], y[5], kDT)), "r"(pack2(y[6], y[7], kDT)) : "memory");
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowaddr + (((uint32_t)(2 * hh + 1) ^ swz) << 4)), "r"(pack2(y[8], y[9], kDT)),
+                                     "r"(pack2(y[10], y[11], kDT)), "r"(pack2(y[12], y[13], kDT)), "r"(pack2(y[14], y[15], kDT)) : "memory");
+                    }
+                    // hand the staged chunk to the TMA unit: generic-proxy writes -> async proxy, then one bulk store
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        const int nn = n0 + ci * 32;
+                        if (shuffle) {
+                            const int g = (nn >= gn) + (nn >= 2 * gn) + (nn >= 3 * gn);
+                            tma_store_5d(&tmO.m[g], block(ci), nn - g * gn, sw0, sh0, sb0, 0);
+                        } else {
+                            tma_store_5d(&tmO.m[0], block(ci), nn, sw0, sh0, sb0, 0);
+                        }
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                };
+                for (int k = 0; k < n_my; k += 2) {
+                    chunk(k, va, vb);
+                    if (k + 1 < n_my) chunk(k + 1, vb, va);
+                }
+                tc_fence_before();
+                acc_signal(tempty_sig[as]);
+                if (++as == p.acc_stages) { as = 0; aphase ^= 1u; }
+                continue;
+            }
             const int ow = wt * p.bw + rw, oh = ht * p.bh + rh, ob = bt * p.bb + rb;
             const bool valid = (ow < p.out_W) && (oh < p.out_H) && (ob < p.out_B);
 
-            if (p.tma_store && etid == 0) {  // previous tile's bulk stores must have finished reading the staging buffer
+            if (p.tma_store && etid == 0)   // previous tile's bulk stores must have finished reading the staging buffer
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                if (kFast && p.res_tma) {    // residual tile -> staging buffer (rows / channels outside the tensor arrive as zeros)
-                    mbar_arrive_expect_tx(res_bar, p.stage_out_bytes);
-                    for (int sub = 0; sub < (p.BN >> 6); ++sub)
-                        tma_load_5d(stage_out + sub * (kTileM * 128u), &tmO.m[1], res_bar, n0 + sub * 64, wt * p.bw, ht * p.bh,
-                                    bt * p.bb, 0);
-                }
-            }
             // stage this tile's per-column parameters in shared memory (double-buffered; reloaded only when the N tile
             // changes, i.e. never after the first tile of a launch with a single N tile)
             if (nt != last_nt) {
@@ -597,7 +758,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             const int od = p.out_dtype == HAVC_F32 ? HAVC_F32 : kDT, gn = p.group_n;
             const bool shuffle = p.shuffle != 0, has_scale = p.scale != nullptr, head = p.head_w != nullptr;
             const bool tma_store = p.tma_store != 0;
-            const bool res_tma = kFast && p.res_tma != 0;
             const float slope1 = p.slope1, lo2 = p.relu2 ? 0.f : -INFINITY;
             const long long pix_main = ob * p.osb + (long long)(oh * p.up + p.oy) * p.osh + (long long)(ow * p.up + p.ox) * p.osw;
             const long long pix_shuf = ob * p.osb + (long long)(oh * 2) * p.osh + (long long)(ow * 2) * p.osw;
@@ -738,78 +898,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                     }
                 }
             };
-            // Streamlined variant (kFast): every chunk is a full 32 columns of a whole N tile, the result goes to the
-            // swizzled staging buffer (TMA clips rows / channels outside the tensor), residual rows are read only for
-            // pixels inside the image.
-            auto process_fast = [&](int ci, int nxt, uint32_t(&vc)[32], uint32_t(&vn)[32]) {
-                const int c0 = ci * 32;
-                const int n = n0 + c0;
-                uint4 rres[4];
-                const bool do_res = res_tma || res_row != nullptr;
-                if (res_tma) {      // this thread's 64 bytes of the staged residual tile (the words its result will overwrite)
-                    const uint32_t sub = stage_out + (uint32_t)(c0 >> 6) * (kTileM * 128u) + (uint32_t)r * 128u;
-                    const uint32_t k16 = (uint32_t)(c0 & 63) >> 3;
-#pragma unroll
-                    for (int g = 0; g < 4; ++g)
-                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rres[g].x), "=r"(rres[g].y), "=r"(rres[g].z), "=r"(rres[g].w)
-                                     : "r"(sub + (((k16 + g) ^ (r & 7u)) << 4)) : "memory");
-                } else if (do_res) {
-#pragma unroll
-                    for (int g = 0; g < 4; ++g)
-                        rres[g] = (n + 8 * g < c_store) ? __ldg(reinterpret_cast<const uint4 *>(res_row + 2 * (n + 8 * g))) : make_uint4(0, 0, 0, 0);
-                }
-                tmem_ld_wait();
-                if (nxt >= 0) {
-                    __syncwarp();
-                    tmem_ld32(tbase + nxt * 32, vn);
-                }
-#pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    const int cc = c0 + 16 * hh;
-                    float y[16];
-                    const float4 *b4 = reinterpret_cast<const float4 *>(sb + cc);
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        const float4 bv = b4[g];
-                        const float t0 = __uint_as_float(vc[16 * hh + 4 * g + 0]) + bv.x, t1 = __uint_as_float(vc[16 * hh + 4 * g + 1]) + bv.y;
-                        const float t2 = __uint_as_float(vc[16 * hh + 4 * g + 2]) + bv.z, t3 = __uint_as_float(vc[16 * hh + 4 * g + 3]) + bv.w;
-                        y[4 * g + 0] = fmaxf(t0, t0 * slope1);
-                        y[4 * g + 1] = fmaxf(t1, t1 * slope1);
-                        y[4 * g + 2] = fmaxf(t2, t2 * slope1);
-                        y[4 * g + 3] = fmaxf(t3, t3 * slope1);
-                    }
-                    if (has_scale) {
-                        const float4 *s4 = reinterpret_cast<const float4 *>(sb + kMaxBN + cc);
-                        const float4 *t4 = reinterpret_cast<const float4 *>(sb + 2 * kMaxBN + cc);
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            const float4 sv = s4[g], tv = t4[g];
-                            y[4 * g + 0] = fmaf(y[4 * g + 0], sv.x, tv.x);
-                            y[4 * g + 1] = fmaf(y[4 * g + 1], sv.y, tv.y);
-                            y[4 * g + 2] = fmaf(y[4 * g + 2], sv.z, tv.z);
-                            y[4 * g + 3] = fmaf(y[4 * g + 3], sv.w, tv.w);
-                        }
-                    }
-                    if (do_res) {
-                        const uint32_t rr[8] = {rres[2 * hh].x, rres[2 * hh].y, rres[2 * hh].z, rres[2 * hh].w,
-                                                rres[2 * hh + 1].x, rres[2 * hh + 1].y, rres[2 * hh + 1].z, rres[2 * hh + 1].w};
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float2 f = unpack2(rr[j], kDT);
-                            y[2 * j] += f.x;
-                            y[2 * j + 1] += f.y;
-                        }
-                    }
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) y[j] = fmaxf(y[j], lo2);
-                    const uint32_t sub = stage_out + (uint32_t)(cc >> 6) * (kTileM * 128u) + (uint32_t)r * 128u;
-                    const uint32_t k16 = (uint32_t)(cc & 63) >> 3;
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sub + ((k16 ^ (r & 7u)) << 4)), "r"(pack2(y[0], y[1], kDT)),
-                                 "r"(pack2(y[2], y[3], kDT)), "r"(pack2(y[4], y[5], kDT)), "r"(pack2(y[6], y[7], kDT)) : "memory");
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sub + (((k16 + 1u) ^ (r & 7u)) << 4)), "r"(pack2(y[8], y[9], kDT)),
-                                 "r"(pack2(y[10], y[11], kDT)), "r"(pack2(y[12], y[13], kDT)), "r"(pack2(y[14], y[15], kDT)) : "memory");
-                }
-            };
             // This warp's chunks are ci = half, half+2, ...; in staggered mode the columns shared with the other
             // accumulator stage are drained first (stage 0: the highest chunks, stage 1: the lowest) and `tearly`
             // is signalled as soon as they are out of TMEM.
@@ -821,15 +909,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 return as == 0 ? (ci * 32 + 32 > p.acc_stride) : (ci * 32 < p.BN - p.acc_stride);
             };
             bool early_done = !p.staggered;
-            if constexpr (kFast) {
-                __syncwarp();
-                tmem_ld32(tbase + half * 32, va);
-                if (res_tma) { mbar_wait(res_bar, rphase); rphase ^= 1u; }
-                for (int k = 0; k < n_my; k += 2) {
-                    process_fast(half + 2 * k, k + 1 < n_my ? half + 2 * (k + 1) : -1, va, vb);
-                    if (k + 1 < n_my) process_fast(half + 2 * (k + 1), k + 2 < n_my ? half + 2 * (k + 2) : -1, vb, va);
-                }
-            } else {
             if (n_my > 0) {
                 __syncwarp();
                 tmem_ld_chunk(tbase + chunk_at(0) * 32, va, p.BN - chunk_at(0) * 32);
@@ -854,7 +933,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 tc_fence_before();
                 acc_signal(tearly_sig[as]);
             }
-            }   // generic path
             if (tma_store) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> async proxy
                 asm volatile("bar.sync 2, 256;" ::: "memory");
@@ -891,7 +969,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         }
     }
 
-    if (p.tma_store && threadIdx.x == 128) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    // shared memory must outlive the bulk stores that read it: generic epilogue = one issuing thread, fast = one per epilogue warp
+    if (p.tma_store && (kFast ? (warp >= 4 && lane == 0) : (threadIdx.x == 128))) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     tc_fence_before();
     if (kPair) cluster_sync_all(); else __syncthreads();   // pair: neither CTA may exit while the peer can still signal it
     if (warp == 2) {
@@ -923,7 +1002,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 static int encode_map(CUtensorMap *tm, int dtype, int rank, const void *ptr, const uint64_t *dims,
-                      const uint64_t *strides_elems, const uint32_t *box) {
+                      const uint64_t *strides_elems, const uint32_t *box, bool swizzle64 = false) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled driver entry point unavailable");
@@ -939,7 +1018,7 @@ static int encode_map(CUtensorMap *tm, int dtype, int rank, const void *ptr, con
     }
     CUresult r = fn(tm, dtype == HAVC_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
                     rank, const_cast<void *>(ptr), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu %llu %llu %llu %llu)",
@@ -951,7 +1030,8 @@ static int encode_map(CUtensorMap *tm, int dtype, int rank, const void *ptr, con
     return HAVC_OK;
 }
 
-static int encode_act(CUtensorMap *tm, const havc_act_view &a, int dtype, int bw, int bh, int bb) {
+// chunk32: the box of the fast epilogue's per-warp stores / residual loads (32 channels x a 32-pixel slab, 64-byte swizzle)
+static int encode_act(CUtensorMap *tm, const havc_act_view &a, int dtype, int bw, int bh, int bb, bool chunk32 = false) {
     const int P = a.P > 0 ? a.P : 1;
     uint64_t dims[5] = {(uint64_t)a.C, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.B, (uint64_t)P};
     // size-1 dimensions still need a legal (non-zero, 16 B multiple) stride
@@ -960,8 +1040,8 @@ static int encode_act(CUtensorMap *tm, const havc_act_view &a, int dtype, int bw
     if (sb == 0) sb = sh * a.H;
     if (sp == 0) sp = sb * a.B;
     uint64_t strides[5] = {1, sw, sh, sb, sp};
-    uint32_t box[5] = {(uint32_t)kChunkK, (uint32_t)bw, (uint32_t)bh, (uint32_t)bb, 1u};
-    return encode_map(tm, dtype, 5, a.ptr, dims, strides, box);
+    uint32_t box[5] = {(uint32_t)(chunk32 ? 32 : kChunkK), (uint32_t)bw, (uint32_t)bh, (uint32_t)bb, 1u};
+    return encode_map(tm, dtype, 5, a.ptr, dims, strides, box, chunk32);
 }
 
 static bool act_ok(const havc_act_view &a) {
@@ -1063,8 +1143,8 @@ extern "C" int havc_conv_gemm(const havc_conv_desc *d, void *stream) {
                    d->head_w == nullptr && d->up == 1 && d->oy == 0 && d->ox == 0 && (!d->shuffle || d->group_n % 64 == 0))
                       ? 1 : 0;
     p.stage_out_bytes = p.tma_store ? (uint32_t)(kTileM * d->BN * 2) : 0u;
-    static const bool no_res_tma = getenv("HAVC_B200_NO_RES_TMA") != nullptr;   // A/B switch for profiling
-    int stages = (227 * 1024 - 1024 - 256 - kEpiSmemFloats * (int)sizeof(float) - (int)p.stage_out_bytes) / (int)p.stage_bytes;
+
+    int stages = (227 * 1024 - 1024 - kBarBytes - kEpiSmemFloats * (int)sizeof(float) - (int)p.stage_out_bytes) / (int)p.stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     HAVC_CHECK_ARG(stages >= 2, "havc_conv_gemm: tile too large for shared memory");
     p.num_stages = stages;
@@ -1122,10 +1202,14 @@ extern "C" int havc_conv_gemm(const havc_conv_desc *d, void *stream) {
     }
     if (d->b_batched) HAVC_CHECK_ARG(d->box_b == 1, "havc_conv_gemm: b_batched=1 needs box_b=1");
 
-    const size_t smem = (size_t)p.num_stages * p.stage_bytes + p.stage_out_bytes + 1024 + 256 + kEpiSmemFloats * sizeof(float);
+    const size_t smem = (size_t)p.num_stages * p.stage_bytes + p.stage_out_bytes + 1024 + kBarBytes + kEpiSmemFloats * sizeof(float);
     static const bool no_fast = getenv("HAVC_B200_NO_FAST_EPILOGUE") != nullptr;   // A/B switch for profiling
+    static const bool no_res_tma = getenv("HAVC_B200_NO_RES_TMA") != nullptr;      // A/B switch: residual convs take the generic epilogue
+    auto is_pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
     const bool fast = !no_fast && p.tma_store && !p.staggered && d->head_w == nullptr && d->split_n == 0 && d->residual2 == nullptr &&
-                      d->out_dtype == d->dtype && d->BN % 32 == 0 && d->N_total % d->BN == 0;
+                      d->out_dtype == d->dtype && d->BN % 32 == 0 && d->N_total % d->BN == 0 &&
+                      is_pow2(d->box_w) && is_pow2(d->box_h) && is_pow2(d->box_b) &&      // 32-pixel slabs must be sub-boxes
+                      (d->residual == nullptr || !no_res_tma);                            // the fast epilogue takes its residual by TMA
     typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const StoreMaps, const ConvParams);
     static const KernelFn kernels[2][2][2] = {
         {{conv_gemm_kernel<HAVC_F16, false, false>, conv_gemm_kernel<HAVC_F16, false, true>},
@@ -1142,15 +1226,20 @@ extern "C" int havc_conv_gemm(const havc_conv_desc *d, void *stream) {
     }
     StoreMaps tmO;
     memset(&tmO, 0, sizeof(tmO));
+    // fast epilogue: every warp stores / loads its own 32-pixel slab of the box, 32 channels at a time
+    const int slab_w = d->box_w < 32 ? d->box_w : 32;
+    const int slab_h = d->box_h < 32 / slab_w ? d->box_h : 32 / slab_w;
+    const int slab_b = 32 / (slab_w * slab_h);
+    const int obw = fast ? slab_w : d->box_w, obh = fast ? slab_h : d->box_h, obb = fast ? slab_b : d->box_b;
     p.res_tma = (fast && d->residual != nullptr && !d->shuffle && !no_res_tma) ? 1 : 0;
-    if (p.res_tma) {     // same geometry as the output map: a 64-channel x box tile of the residual tensor per load
+    if (p.res_tma) {     // same geometry as the output map
         havc_act_view v;
         memset(&v, 0, sizeof(v));
         v.ptr = d->residual;
         v.C = d->c_store; v.W = d->out_W; v.H = d->out_H; v.B = d->out_B; v.P = 1;
         v.stride_w = d->res_stride_w; v.stride_h = d->res_stride_h; v.stride_b = d->res_stride_b;
         v.stride_p = d->res_stride_b * d->out_B;
-        rc = encode_act(&tmO.m[1], v, d->dtype, d->box_w, d->box_h, d->box_b);
+        rc = encode_act(&tmO.m[1], v, d->dtype, obw, obh, obb, fast);
         if (rc) return rc;
     }
     if (p.tma_store) {
@@ -1164,7 +1253,7 @@ extern "C" int havc_conv_gemm(const havc_conv_desc *d, void *stream) {
             const int m = d->shuffle ? 2 : 1;
             v.stride_w = m * d->out_stride_w; v.stride_h = m * d->out_stride_h; v.stride_b = d->out_stride_b;
             v.stride_p = d->out_stride_b * d->out_B;
-            rc = encode_act(&tmO.m[g], v, d->out_dtype, d->box_w, d->box_h, d->box_b);
+            rc = encode_act(&tmO.m[g], v, d->out_dtype, obw, obh, obb, fast);
             if (rc) return rc;
         }
     }
