@@ -29,13 +29,14 @@ static constexpr int kTileM = 128;
 static constexpr int kChunkK = 64;  // 64 x 16-bit = 128 B = one swizzle row
 static constexpr int kABytes = kTileM * kChunkK * 2;
 static constexpr int kMaxStages = 8;
-static constexpr int kThreads = 384;   // 4 control warps + 8 epilogue warps
+static constexpr int kThreads = 384;       // generic epilogue: 4 control warps + 8 epilogue warps
+static constexpr int kThreadsFast = 640;   // fast epilogue: 4 control warps + 16 epilogue warps (four per TMEM lane quarter)
 static constexpr int kMaxBN = 320;      // parameter staging rows (BN <= 320)
 // epilogue shared memory: 2 x {bias,scale,shift}[kMaxBN] + head weights [3][kMaxBN] + head exchange [128][4]
-static constexpr int kWarpCols = 128;     // fast epilogue: columns one epilogue warp owns (BN <= 256, every other 32-column chunk)
+static constexpr int kWarpCols = 64;      // fast epilogue: columns one epilogue warp owns (BN <= 256, every fourth 32-column chunk)
 // the generic epilogue's arrays and the fast epilogue's per-warp slices (8 x 3 x kWarpCols floats) share the same bytes
 static constexpr int kEpiSmemFloats = 2 * 3 * kMaxBN + 3 * kMaxBN + 128 * 4;
-static_assert(8 * 3 * kWarpCols <= kEpiSmemFloats, "per-warp parameter slices must fit the epilogue area");
+static_assert(16 * 3 * kWarpCols <= kEpiSmemFloats, "per-warp parameter slices must fit the epilogue area");
 static constexpr int kBarBytes = 512;    // mbarrier area in front of the epilogue parameters
 static constexpr uint32_t kTmemCols = 512;
 
@@ -328,7 +329,7 @@ __device__ __forceinline__ void bulk_wait_read_n(int n) {   // n = bulk groups t
 // shared memories and writes both TMEMs.  Per CTA and K step 16 KB + BN*64 B arrive from L2 instead of 16 KB + BN*128 B
 // (the 3x3 decoder convs are bound by exactly that L2 -> SM traffic).
 template <int kDT, bool kFast, bool kPair>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kFast ? kThreadsFast : kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmW1,
                  const __grid_constant__ StoreMaps tmO, const __grid_constant__ ConvParams p) {
@@ -344,6 +345,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 4);
     auto tearly_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 5 + s); };
     auto wres_bar = [&](int w) { return bar_base + 8u * (2 * kMaxStages + 7 + w); };   // one per epilogue warp (fast epilogue)
+    constexpr uint32_t kEpiThreads = kFast ? (kThreadsFast - 128) : (kThreads - 128);
     volatile uint32_t *tmem_slot_ptr =
         reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -380,10 +382,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(tfull_bar(s), 1);
-            mbar_init(tempty_bar(s), kPair ? 512 : 256);   // pair: the leader's barrier collects both CTAs' epilogues
-            mbar_init(tearly_bar(s), kPair ? 512 : 256);
+            mbar_init(tempty_bar(s), kPair ? 2 * kEpiThreads : kEpiThreads);   // pair: the leader's barrier collects both CTAs' epilogues
+            mbar_init(tearly_bar(s), kPair ? 2 * kEpiThreads : kEpiThreads);
         }
-        for (int w = 0; w < 8; ++w) mbar_init(wres_bar(w), 1);
+        for (int w = 0; w < 16; ++w) mbar_init(wres_bar(w), 1);
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -515,7 +517,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             }
         }
     } else if (warp >= 4) {
-        // ===================== epilogue (8 warps) =====================
+        // ===================== epilogue (8 warps; 16 in the fast variant) =====================
         // warp w owns TMEM lanes 32*(w%4)..+31 (hardware rule); the two warps that share a lane quarter
         // split the accumulator columns in interleaved 32-column chunks.
         const int q = warp & 3;
@@ -549,10 +551,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             const int n0 = nt * p.BN;
             if constexpr (kFast) {
                 // ---------------- warp-private fast epilogue ----------------
-                // Every warp owns the 32 rows of its TMEM lane quarter and every other 32-column chunk: its slice of the per-
+                // Sixteen warps: every warp owns the 32 rows of its TMEM lane quarter and every fourth 32-column chunk (four warps per
+                // scheduler hide the TMEM-load / shared-memory latencies that two could not): its slice of the per-
                 // column parameters, its 2 KB staging blocks (64B-swizzled), its own TMA stores (one per chunk, issued as soon
                 // as the chunk is staged), its own residual loads and barrier.  No CTA-wide barrier is left in the tile loop.
-                const int n_my = (nchunks - half + 1) >> 1;                    // <= 4
+                const int part = (warp - 4) >> 2;                              // 0..3: which chunks of the lane quarter are mine
+                const int n_my = (nchunks - part + 3) >> 2;                    // <= 2 (can be 0 for narrow N tiles)
                 float *wp = sparams + (warp - 4) * (3 * kWarpCols);
                 const uint32_t my_res_bar = wres_bar(warp - 4);
                 const bool res_tma = p.res_tma != 0, has_scale = p.scale != nullptr, shuffle = p.shuffle != 0;
@@ -563,12 +567,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 const int sw0 = wt * p.bw + row0 % p.bw, sh0 = ht * p.bh + (row0 / p.bw) % p.bh, sb0 = bt * p.bb + row0 / (p.bw * p.bh);
                 auto block = [&](int ci) { return stage_out + (uint32_t)(ci * 4 + q) * 2048u; };
                 // parameters of my columns: fetched now (when the N tile changed), parked in shared memory after the accumulator wait
-                float pb[4], ps[4], pt[4];
+                float pb[2], ps[2], pt[2];
                 const bool reload = nt != last_nt;
                 if (reload) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int n = n0 + (half + 2 * k) * 32 + lane;
+                    for (int k = 0; k < 2; ++k) {
+                        const int n = n0 + (part + 4 * k) * 32 + lane;
                         const bool in = k < n_my;
                         pb[k] = (in && p.bias) ? __ldg(p.bias + n) : 0.f;
                         ps[k] = (in && p.scale) ? __ldg(p.scale + n) : 1.f;
@@ -578,10 +582,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 }
                 if (lane == 0) {
                     bulk_wait_read<0>();       // my stores of the previous tile have finished reading my staging blocks
-                    if (res_tma) {             // residual slab -> the same blocks (rows / channels outside the tensor arrive as zeros)
+                    if (res_tma && n_my > 0) { // residual slab -> the same blocks (rows / channels outside the tensor arrive as zeros)
                         mbar_arrive_expect_tx(my_res_bar, (uint32_t)n_my * 2048u);
                         for (int k = 0; k < n_my; ++k)
-                            tma_load_5d(block(half + 2 * k), &tmO.m[1], my_res_bar, n0 + (half + 2 * k) * 32, sw0, sh0, sb0, 0);
+                            tma_load_5d(block(part + 4 * k), &tmO.m[1], my_res_bar, n0 + (part + 4 * k) * 32, sw0, sh0, sb0, 0);
                     }
                 }
                 __syncwarp();
@@ -594,7 +598,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         if (ow2 < p.out_W && oh2 < p.out_H && ob2 < p.out_B) {
                             const uint8_t *row = reinterpret_cast<const uint8_t *>(p.residual) + 2ll * (ob2 * p.rsb + oh2 * p.rsh + ow2 * p.rsw);
                             const int cbeg = nt2 * p.BN, cend = min(cbeg + p.BN, p.c_store);
-                            for (int c = cbeg + half * 64; c < cend; c += 128)
+                            for (int c = cbeg + part * 64; c < cend; c += 256)
                                 asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 2 * c));
                         }
                     }
@@ -602,22 +606,22 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 mbar_wait(tfull_bar(as), aphase);
                 tc_fence_after();
                 const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * p.acc_stride;
-                uint32_t va[32], vb[32];
-                __syncwarp();
-                tmem_ld32(tbase + half * 32, va);
+                uint32_t va[32];
                 if (reload) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
+                    for (int k = 0; k < 2; ++k) {
                         wp[k * 32 + lane] = pb[k];
                         wp[kWarpCols + k * 32 + lane] = ps[k];
                         wp[2 * kWarpCols + k * 32 + lane] = pt[k];
                     }
                     __syncwarp();
                 }
-                if (res_tma) { mbar_wait(my_res_bar, rphase); rphase ^= 1u; }
+                if (res_tma && n_my > 0) { mbar_wait(my_res_bar, rphase); rphase ^= 1u; }
                 const uint32_t swz = ((uint32_t)lane >> 1) & 3u;               // SWIZZLE_64B: 16-byte chunk index ^= address bits [7:8]
-                auto chunk = [&](int k, uint32_t(&vc)[32], uint32_t(&vn)[32]) {
-                    const int ci = half + 2 * k;
+                auto chunk = [&](int k, uint32_t(&vc)[32]) {
+                    const int ci = part + 4 * k;
+                    __syncwarp();
+                    tmem_ld32(tbase + ci * 32, vc);
                     const uint32_t rowaddr = block(ci) + (uint32_t)lane * 64u;
                     uint4 rres[4];
                     if (res_tma) {
@@ -627,10 +631,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                                          : "r"(rowaddr + (((uint32_t)g ^ swz) << 4)) : "memory");
                     }
                     tmem_ld_wait();
-                    if (k + 1 < n_my) {
-                        __syncwarp();
-                        tmem_ld32(tbase + (ci + 2) * 32, vn);
-                    }
                     const float *sb = wp + k * 32;
 #pragma unroll
                     for (int hh = 0; hh < 2; ++hh) {
@@ -689,10 +689,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                 };
-                for (int k = 0; k < n_my; k += 2) {
-                    chunk(k, va, vb);
-                    if (k + 1 < n_my) chunk(k + 1, vb, va);
-                }
+                for (int k = 0; k < n_my; ++k) chunk(k, va);
                 tc_fence_before();
                 acc_signal(tempty_sig[as]);
                 if (++as == p.acc_stages) { as = 0; aphase ^= 1u; }
@@ -1263,7 +1260,7 @@ extern "C" int havc_conv_gemm(const havc_conv_desc *d, void *stream) {
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
         cfg.gridDim = dim3(2 * groups);
-        cfg.blockDim = dim3(kThreads);
+        cfg.blockDim = dim3(fast ? kThreadsFast : kThreads);
         cfg.dynamicSmemBytes = smem;
         cfg.stream = (cudaStream_t)stream;
         cudaLaunchAttribute attr;
@@ -1274,7 +1271,7 @@ extern "C" int havc_conv_gemm(const havc_conv_desc *d, void *stream) {
         HAVC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA0, tmA1, tmW, tmW1, tmO, p));
     } else {
         int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-        kern<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA0, tmA1, tmW, tmW1, tmO, p);
+        kern<<<grid, fast ? kThreadsFast : kThreads, smem, (cudaStream_t)stream>>>(tmA0, tmA1, tmW, tmW1, tmO, p);
     }
     HAVC_LAUNCHED();
     return HAVC_OK;
