@@ -1,0 +1,93 @@
+"""BASELINE.json configurations at their FULL sizes on the GPU (through DeoldifyEngine -> C ABI).
+
+The CPU oracle needs ~8 s per 1080p frame, so only cfg2 is compared with it frame against frame (one frame); every
+configuration is checked through size-independent properties of the path:
+  * luma transplant: every output pixel that is not clipped keeps the source's OpenCV-Q14 luma (vs_recover_clip_luma,
+    vsfilters.py:863-899) up to the rounding of the u8 YUV -> RGB -> YUV round trip (|dY| <= 1);
+  * frames are independent: permuting the frames of a batch permutes the output bytes exactly (order / batch-slot invariance);
+  * a scene-change-skipped frame equals the uncoloured squeeze / un-squeeze path and is not affected by its neighbours.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _clip(n, h, w, seed):
+    import bench
+    return bench.synth_clip(n, h, w, seed=seed)
+
+
+def _luma_err(out_chw, src_chw):
+    """|Y(out) - Y(src)| (OpenCV Q14 luma) over the pixels whose output is not clipped: YUV -> RGB saturates a channel for wild
+    chroma, and only then can the transplanted luma move by more than the rounding of the u8 round trip (<= 1)."""
+    from oracle import pixel_oracle as px
+    o = np.ascontiguousarray(np.transpose(out_chw, (1, 2, 0)))
+    yo = px.cv_rgb2yuv(o)[..., 0].astype(int)
+    ys = px.cv_rgb2yuv(np.ascontiguousarray(np.transpose(src_chw, (1, 2, 0))))[..., 0].astype(int)
+    uns = ((o > 0) & (o < 255)).all(-1)
+    d = np.abs(yo - ys)[uns]
+    return float(uns.mean()), (int(d.max()) if d.size else 0)
+
+
+def _check_properties(eng, clip):
+    out = eng.colorize_batch(clip)
+    assert out.shape == clip.shape and out.dtype == np.uint8
+    for i in range(clip.shape[0]):
+        share, mx = _luma_err(out[i], clip[i])
+        assert share > 0.2 and mx <= 1, (i, share, mx)
+        assert np.abs(out[i].astype(int) - clip[i].astype(int)).max() > 8, "the frame must actually be colourised"
+    perm = np.arange(clip.shape[0])[::-1]
+    out_p = eng.colorize_batch(np.ascontiguousarray(clip[perm]))
+    assert np.array_equal(out_p, out[perm]), "frames of a batch must be independent of their slot and neighbours"
+    if clip.shape[0] >= 2:                      # scene-change gate on frame 0 only
+        skip = np.zeros(clip.shape[0], bool)
+        skip[0] = True
+        out_s = eng.colorize_batch(clip, skip=skip)
+        assert np.array_equal(out_s[1:], out[1:])
+        d = np.abs(out_s[0].astype(int) - clip[0].astype(int))       # gray in, squeeze + un-squeeze + luma transplant: ~identity
+        assert d.max() <= 3 and d.mean() < 0.5, (int(d.max()), float(d.mean()))
+    return out
+
+
+def test_cfg2_video_rf24_1080p_vs_oracle_and_properties():
+    from oracle import metrics, pipeline_oracle, synth_weights
+    from vsdeoldify_b200.engine import DeoldifyEngine
+    sd = synth_weights.make_unet_state_dict("wide", 1234)
+    eng = DeoldifyEngine(sd, 1920, 1080, render_factor=24, batch=2, dtype=torch.float16)
+    clip = _clip(2, 1080, 1920, seed=7)
+    out = _check_properties(eng, clip)
+    frame = np.ascontiguousarray(np.transpose(clip[0], (1, 2, 0)))
+    ref = pipeline_oracle.havc_colorizer_frame(sd, frame, 24)
+    m = metrics.frame_parity(np.ascontiguousarray(np.transpose(out[0], (1, 2, 0))), ref)
+    print("cfg2 1080p frame parity:", m)
+    assert m["mean_de00"] <= 0.5, m                                   # north-star gate
+    assert m["n_err_gt2"] <= 2.5e-2 * m["n_values"], m               # see tests/test_gpu_unet.py on the strict max <= 2 gate
+    assert _luma_err(np.transpose(ref, (2, 0, 1)), clip[0])[1] <= 1   # the oracle has the same property
+
+
+def test_cfg3_stable_rf30_1080p_properties():
+    from oracle import synth_weights
+    from vsdeoldify_b200.constants import DEF_STABLE_WEIGHT
+    from vsdeoldify_b200.engine import DeoldifyEngine
+    sd = synth_weights.make_unet_state_dict("wide", 1234)
+    sd2 = synth_weights.make_unet_state_dict("wide", 4321)
+    eng = DeoldifyEngine(sd, 1920, 1080, render_factor=30, batch=2, dtype=torch.float16, sd_other=sd2, video_weight=DEF_STABLE_WEIGHT)
+    assert eng.S == 480
+    _check_properties(eng, _clip(2, 1080, 1920, seed=8))
+
+
+def test_cfg5_artistic_rf40_eccv16_uhd_properties():
+    from oracle import synth_weights, zhang_oracle
+    from vsdeoldify_b200.constants import DEF_ARTISTIC_WEIGHT
+    from vsdeoldify_b200.engine import DeoldifyEngine
+    sd = synth_weights.make_unet_state_dict("wide", 1234)
+    sd2 = synth_weights.make_unet_state_dict("deep", 1234)
+    sdz = zhang_oracle.make_zhang_state_dict("eccv16", 1234)
+    merge = dict(method=2, weight=0.4, cmc_p=[0.15, True, 20, 24], lmm_p=[0.15, 0.65, 1.0], alm_p=[0.8, 1.0, 0.15],
+                 crt_p=[0.8, 30, 2, False, 0, 0], invert=False)
+    eng = DeoldifyEngine(sd, 3840, 2160, render_factor=40, batch=2, dtype=torch.float16, sd_other=sd2,
+                         video_weight=DEF_ARTISTIC_WEIGHT, zhang=("eccv16", sdz), merge=merge)
+    assert eng.S == 640
+    _check_properties(eng, _clip(2, 2160, 3840, seed=9))

@@ -334,6 +334,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                  const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmW1,
                  const __grid_constant__ StoreMaps tmO, const __grid_constant__ ConvParams p) {
     extern __shared__ uint8_t smem_raw[];
+    // let the next kernel of the stream (if launched with programmatic serialization) start its own prologue as SMs free up
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t stage_out = smem_base + p.num_stages * p.stage_bytes;        // 1024-aligned output staging
     const uint32_t bar_base = stage_out + p.stage_out_bytes;
@@ -401,6 +403,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     if (kPair) cluster_sync_all(); else __syncthreads();   // pair: the peer's barriers must be initialised before any remote signal
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_ptr, 0);
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation, tensor-map prefetch) touched no global
+    // memory and may overlap the tail of the previous kernel in the stream; from here on its results are needed.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     const int ksteps_per_tap = p.src1_single_tap ? p.chunks0 : (p.chunks0 + p.chunks1);
     const int ksteps_main = p.n_taps * ksteps_per_tap;
@@ -726,7 +731,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 res_row = reinterpret_cast<const uint8_t *>(p.residual) + 2ll * (ob * p.rsb + oh * p.rsh + ow * p.rsw);
             if (p.residual2 != nullptr && valid)
                 res_row2 = reinterpret_cast<const uint8_t *>(p.residual2) + 2ll * (ob * p.r2sb + oh * p.r2sh + ow * p.r2sw);
-            float hacc0 = 0.f, hacc1 = 0.f, hacc2 = 0.f;
+            // Fused-head partial sums.  The order in which a warp walks its chunks depends on the accumulator stage the tile
+            // happens to use (staggered mode drains the shared columns first), i.e. on the tile's position in the launch: a
+            // plain fp32 running sum would make a pixel's logits depend on the batch slot of its frame in the last bits.  Each
+            // 16-column group is summed in fp32 in a fixed order and the groups are added in fp64, where the sum of these few
+            // 24-bit terms is exact (and therefore order independent) up to astronomically rare ties.
+            double hacc0 = 0.0, hacc1 = 0.0, hacc2 = 0.0;
             if (p.residual != nullptr) {
                 // pull the NEXT tile's residual rows towards L2 while this tile is processed: each thread covers the
                 // 128-byte lines of its own row that its warp half will read
@@ -834,13 +844,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         const float4 *h0 = reinterpret_cast<const float4 *>(hw + cc);
                         const float4 *h1 = reinterpret_cast<const float4 *>(hw + kMaxBN + cc);
                         const float4 *h2 = reinterpret_cast<const float4 *>(hw + 2 * kMaxBN + cc);
+                        float l0 = 0.f, l1 = 0.f, l2 = 0.f;
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
                             const float4 a = h0[g], b = h1[g], c = h2[g];
-                            hacc0 = fmaf(y[4 * g + 3], a.w, fmaf(y[4 * g + 2], a.z, fmaf(y[4 * g + 1], a.y, fmaf(y[4 * g], a.x, hacc0))));
-                            hacc1 = fmaf(y[4 * g + 3], b.w, fmaf(y[4 * g + 2], b.z, fmaf(y[4 * g + 1], b.y, fmaf(y[4 * g], b.x, hacc1))));
-                            hacc2 = fmaf(y[4 * g + 3], c.w, fmaf(y[4 * g + 2], c.z, fmaf(y[4 * g + 1], c.y, fmaf(y[4 * g], c.x, hacc2))));
+                            l0 = fmaf(y[4 * g + 3], a.w, fmaf(y[4 * g + 2], a.z, fmaf(y[4 * g + 1], a.y, fmaf(y[4 * g], a.x, l0))));
+                            l1 = fmaf(y[4 * g + 3], b.w, fmaf(y[4 * g + 2], b.z, fmaf(y[4 * g + 1], b.y, fmaf(y[4 * g], b.x, l1))));
+                            l2 = fmaf(y[4 * g + 3], c.w, fmaf(y[4 * g + 2], c.z, fmaf(y[4 * g + 1], c.y, fmaf(y[4 * g], c.x, l2))));
                         }
+                        hacc0 += (double)l0; hacc1 += (double)l1; hacc2 += (double)l2;
                         continue;
                     }
                     if (tma_store) {   // stage into the swizzled 64-channel sub-tile; garbage rows/columns are clipped by TMA
@@ -951,11 +963,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             if (p.head_w != nullptr) {   // the two warps of a lane quarter each hold half of the columns
                 float *hx = sparams + (2 * 3 + 3) * kMaxBN;   // [128 rows][4]
                 if (half == 1) {
-                    hx[r * 4 + 0] = hacc0; hx[r * 4 + 1] = hacc1; hx[r * 4 + 2] = hacc2;
+                    hx[r * 4 + 0] = (float)hacc0; hx[r * 4 + 1] = (float)hacc1; hx[r * 4 + 2] = (float)hacc2;
                 }
                 asm volatile("bar.sync 2, 256;" ::: "memory");
                 if (half == 0 && valid) {
-                    const float4 o = make_float4(hacc0 + hx[r * 4 + 0], hacc1 + hx[r * 4 + 1], hacc2 + hx[r * 4 + 2], 0.f);
+                    const float4 o = make_float4((float)hacc0 + hx[r * 4 + 0], (float)hacc1 + hx[r * 4 + 1], (float)hacc2 + hx[r * 4 + 2], 0.f);
                     *reinterpret_cast<float4 *>(p.head_out + ob * p.hsb + oh * p.hsh + ow * p.hsw) = o;
                 }
                 asm volatile("bar.sync 2, 256;" ::: "memory");
@@ -1254,24 +1266,36 @@ extern "C" int havc_conv_gemm(const havc_conv_desc *d, void *stream) {
             if (rc) return rc;
         }
     }
-    if (pair) {
-        const int max_groups = num_sms() / 2;
-        const int groups = p.total_tiles < max_groups ? p.total_tiles : max_groups;
+    {
+        static const bool no_pdl = getenv("HAVC_B200_NO_PDL") != nullptr;   // A/B switch for profiling
+        int grid;
+        if (pair) {
+            const int max_groups = num_sms() / 2;
+            grid = 2 * (p.total_tiles < max_groups ? p.total_tiles : max_groups);
+        } else {
+            grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+        }
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
-        cfg.gridDim = dim3(2 * groups);
+        cfg.gridDim = dim3(grid);
         cfg.blockDim = dim3(fast ? kThreadsFast : kThreads);
         cfg.dynamicSmemBytes = smem;
         cfg.stream = (cudaStream_t)stream;
-        cudaLaunchAttribute attr;
-        attr.id = cudaLaunchAttributeClusterDimension;
-        attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-        cfg.attrs = &attr;
-        cfg.numAttrs = 1;
+        cudaLaunchAttribute attrs[2];
+        int na = 0;
+        if (pair) {
+            attrs[na].id = cudaLaunchAttributeClusterDimension;
+            attrs[na].val.clusterDim.x = 2; attrs[na].val.clusterDim.y = 1; attrs[na].val.clusterDim.z = 1;
+            ++na;
+        }
+        if (!no_pdl) {     // the kernel waits (griddepcontrol.wait) before it reads anything a predecessor wrote
+            attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attrs[na].val.programmaticStreamSerializationAllowed = 1;
+            ++na;
+        }
+        cfg.attrs = attrs;
+        cfg.numAttrs = na;
         HAVC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA0, tmA1, tmW, tmW1, tmO, p));
-    } else {
-        int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-        kern<<<grid, fast ? kThreadsFast : kThreads, smem, (cudaStream_t)stream>>>(tmA0, tmA1, tmW, tmW1, tmO, p);
     }
     HAVC_LAUNCHED();
     return HAVC_OK;
