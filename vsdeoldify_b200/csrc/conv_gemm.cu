@@ -22,6 +22,7 @@
 // allocator, warps4-11 = epilogue (TMEM lane quarter = warp % 4; two warps per quarter split the columns).
 #include "common.cuh"
 #include <stdlib.h>
+#include <type_traits>
 
 namespace havc {
 
@@ -566,7 +567,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 const uint32_t my_res_bar = wres_bar(warp - 4);
                 const bool res_tma = p.res_tma != 0, has_scale = p.scale != nullptr, shuffle = p.shuffle != 0;
                 const int gn = p.group_n;
-                const float slope1 = p.slope1, lo2 = p.relu2 ? 0.f : -INFINITY;
+                const float slope1 = p.slope1;
                 // origin of this warp's 32-row slab inside the (bw x bh x bb) box (all box extents are powers of two)
                 const int row0 = q * 32;
                 const int sw0 = wt * p.bw + row0 % p.bw, sh0 = ht * p.bh + (row0 / p.bw) % p.bh, sb0 = bt * p.bb + row0 / (p.bw * p.bh);
@@ -623,13 +624,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 }
                 if (res_tma && n_my > 0) { mbar_wait(my_res_bar, rphase); rphase ^= 1u; }
                 const uint32_t swz = ((uint32_t)lane >> 1) & 3u;               // SWIZZLE_64B: 16-byte chunk index ^= address bits [7:8]
-                auto chunk = [&](int k, uint32_t(&vc)[32]) {
+                // kAct: 0 = none, 1 = ReLU, 2 = run-time slope (LeakyReLU); the other flags switch whole stages off at compile time
+                auto chunk = [&](int k, uint32_t(&vc)[32], auto kActT, auto kScaleT, auto kResT, auto kRelu2T) {
+                    constexpr int kAct = decltype(kActT)::value;
+                    constexpr bool kScale = decltype(kScaleT)::value, kRes = decltype(kResT)::value, kRelu2 = decltype(kRelu2T)::value;
                     const int ci = part + 4 * k;
                     __syncwarp();
                     tmem_ld32(tbase + ci * 32, vc);
                     const uint32_t rowaddr = block(ci) + (uint32_t)lane * 64u;
                     uint4 rres[4];
-                    if (res_tma) {
+                    if constexpr (kRes) {
 #pragma unroll
                         for (int g = 0; g < 4; ++g)
                             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rres[g].x), "=r"(rres[g].y), "=r"(rres[g].z), "=r"(rres[g].w)
@@ -637,6 +641,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                     }
                     tmem_ld_wait();
                     const float *sb = wp + k * 32;
+                    auto act = [&](float t) {
+                        if constexpr (kAct == 0) return t;
+                        else if constexpr (kAct == 1) return fmaxf(t, 0.f);
+                        else return fmaxf(t, t * slope1);
+                    };
 #pragma unroll
                     for (int hh = 0; hh < 2; ++hh) {
                         float y[16];
@@ -646,12 +655,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                             const float4 bv = b4[g];
                             const float t0 = __uint_as_float(vc[16 * hh + 4 * g + 0]) + bv.x, t1 = __uint_as_float(vc[16 * hh + 4 * g + 1]) + bv.y;
                             const float t2 = __uint_as_float(vc[16 * hh + 4 * g + 2]) + bv.z, t3 = __uint_as_float(vc[16 * hh + 4 * g + 3]) + bv.w;
-                            y[4 * g + 0] = fmaxf(t0, t0 * slope1);
-                            y[4 * g + 1] = fmaxf(t1, t1 * slope1);
-                            y[4 * g + 2] = fmaxf(t2, t2 * slope1);
-                            y[4 * g + 3] = fmaxf(t3, t3 * slope1);
+                            y[4 * g + 0] = act(t0);
+                            y[4 * g + 1] = act(t1);
+                            y[4 * g + 2] = act(t2);
+                            y[4 * g + 3] = act(t3);
                         }
-                        if (has_scale) {
+                        if constexpr (kScale) {
                             const float4 *s4 = reinterpret_cast<const float4 *>(sb + kWarpCols + 16 * hh);
                             const float4 *t4 = reinterpret_cast<const float4 *>(sb + 2 * kWarpCols + 16 * hh);
 #pragma unroll
@@ -663,7 +672,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                                 y[4 * g + 3] = fmaf(y[4 * g + 3], sv.w, tv.w);
                             }
                         }
-                        if (res_tma) {
+                        if constexpr (kRes) {
                             const uint32_t rr[8] = {rres[2 * hh].x, rres[2 * hh].y, rres[2 * hh].z, rres[2 * hh].w,
                                                     rres[2 * hh + 1].x, rres[2 * hh + 1].y, rres[2 * hh + 1].z, rres[2 * hh + 1].w};
 #pragma unroll
@@ -673,8 +682,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                                 y[2 * j + 1] += f.y;
                             }
                         }
+                        if constexpr (kRelu2) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) y[j] = fmaxf(y[j], lo2);
+                            for (int j = 0; j < 16; ++j) y[j] = fmaxf(y[j], 0.f);
+                        }
                         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowaddr + (((uint32_t)(2 * hh) ^ swz) << 4)), "r"(pack2(y[0], y[1], kDT)),
                                      "r"(pack2(y[2], y[3], kDT)), "r"(pack2(y[4], y[5], kDT)), "r"(pack2(y[6], y[7], kDT)) : "memory");
                         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowaddr + (((uint32_t)(2 * hh + 1) ^ swz) << 4)), "r"(pack2(y[8], y[9], kDT)),
@@ -694,7 +705,26 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                 };
-                for (int k = 0; k < n_my; ++k) chunk(k, va);
+                // the four stage combinations the networks use get their own straight-line body; anything else takes the general one
+                using T = std::true_type;
+                using F = std::false_type;
+                using A0 = std::integral_constant<int, 0>;
+                using A1 = std::integral_constant<int, 1>;
+                using A2 = std::integral_constant<int, 2>;
+                const bool relu1 = slope1 == 0.f, noact = slope1 == 1.f, relu2 = p.relu2 != 0;
+                if (relu1 && !has_scale && !res_tma && !relu2) {            // conv + folded BN + ReLU, PixelShuffle convs
+                    for (int k = 0; k < n_my; ++k) chunk(k, va, A1{}, F{}, F{}, F{});
+                } else if (relu1 && has_scale && !res_tma && !relu2) {      // custom_conv_layer: conv -> ReLU -> BN
+                    for (int k = 0; k < n_my; ++k) chunk(k, va, A1{}, T{}, F{}, F{});
+                } else if (noact && !has_scale && res_tma && relu2) {       // bottleneck conv3: + identity, ReLU
+                    for (int k = 0; k < n_my; ++k) chunk(k, va, A0{}, F{}, T{}, T{});
+                } else if (!res_tma) {
+                    if (relu2) { for (int k = 0; k < n_my; ++k) chunk(k, va, A2{}, T{}, F{}, T{}); }
+                    else { for (int k = 0; k < n_my; ++k) chunk(k, va, A2{}, T{}, F{}, F{}); }
+                } else {
+                    if (relu2) { for (int k = 0; k < n_my; ++k) chunk(k, va, A2{}, T{}, T{}, T{}); }
+                    else { for (int k = 0; k < n_my; ++k) chunk(k, va, A2{}, T{}, T{}, F{}); }
+                }
                 tc_fence_before();
                 acc_signal(tempty_sig[as]);
                 if (++as == p.acc_stages) { as = 0; aphase ^= 1u; }
