@@ -763,10 +763,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 res_row2 = reinterpret_cast<const uint8_t *>(p.residual2) + 2ll * (ob * p.r2sb + oh * p.r2sh + ow * p.r2sw);
             // Fused-head partial sums.  The order in which a warp walks its chunks depends on the accumulator stage the tile
             // happens to use (staggered mode drains the shared columns first), i.e. on the tile's position in the launch: a
-            // plain fp32 running sum would make a pixel's logits depend on the batch slot of its frame in the last bits.  Each
-            // 16-column group is summed in fp32 in a fixed order and the groups are added in fp64, where the sum of these few
-            // 24-bit terms is exact (and therefore order independent) up to astronomically rare ties.
-            double hacc0 = 0.0, hacc1 = 0.0, hacc2 = 0.0;
+            // plain fp32 running sum would make a pixel's logits depend on the batch slot of its frame in the last bits.  Every
+            // chunk therefore sums into its own register slot (chunk index -> slot through predicated static selects) and the
+            // slots are added in ascending order at the end of the tile, whatever order they were filled in.
+            float hp0[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, hp1[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, hp2[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
             if (p.residual != nullptr) {
                 // pull the NEXT tile's residual rows towards L2 while this tile is processed: each thread covers the
                 // 128-byte lines of its own row that its warp half will read
@@ -882,7 +882,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                             l1 = fmaf(y[4 * g + 3], b.w, fmaf(y[4 * g + 2], b.z, fmaf(y[4 * g + 1], b.y, fmaf(y[4 * g], b.x, l1))));
                             l2 = fmaf(y[4 * g + 3], c.w, fmaf(y[4 * g + 2], c.z, fmaf(y[4 * g + 1], c.y, fmaf(y[4 * g], c.x, l2))));
                         }
-                        hacc0 += (double)l0; hacc1 += (double)l1; hacc2 += (double)l2;
+                        const int slot = (ci - half) >> 1;      // this warp's chunks are half, half + 2, ...: at most 5 per tile
+#pragma unroll
+                        for (int j = 0; j < 5; ++j)
+                            if (j == slot) { hp0[j] += l0; hp1[j] += l1; hp2[j] += l2; }
                         continue;
                     }
                     if (tma_store) {   // stage into the swizzled 64-channel sub-tile; garbage rows/columns are clipped by TMA
@@ -992,12 +995,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             }
             if (p.head_w != nullptr) {   // the two warps of a lane quarter each hold half of the columns
                 float *hx = sparams + (2 * 3 + 3) * kMaxBN;   // [128 rows][4]
+                const float hacc0 = (((hp0[0] + hp0[1]) + hp0[2]) + hp0[3]) + hp0[4];
+                const float hacc1 = (((hp1[0] + hp1[1]) + hp1[2]) + hp1[3]) + hp1[4];
+                const float hacc2 = (((hp2[0] + hp2[1]) + hp2[2]) + hp2[3]) + hp2[4];
                 if (half == 1) {
-                    hx[r * 4 + 0] = (float)hacc0; hx[r * 4 + 1] = (float)hacc1; hx[r * 4 + 2] = (float)hacc2;
+                    hx[r * 4 + 0] = hacc0; hx[r * 4 + 1] = hacc1; hx[r * 4 + 2] = hacc2;
                 }
                 asm volatile("bar.sync 2, 256;" ::: "memory");
                 if (half == 0 && valid) {
-                    const float4 o = make_float4((float)hacc0 + hx[r * 4 + 0], (float)hacc1 + hx[r * 4 + 1], (float)hacc2 + hx[r * 4 + 2], 0.f);
+                    const float4 o = make_float4(hacc0 + hx[r * 4 + 0], hacc1 + hx[r * 4 + 1], hacc2 + hx[r * 4 + 2], 0.f);
                     *reinterpret_cast<float4 *>(p.head_out + ob * p.hsb + oh * p.hsh + ow * p.hsw) = o;
                 }
                 asm volatile("bar.sync 2, 256;" ::: "memory");
