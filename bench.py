@@ -126,6 +126,26 @@ def cpu_reference_fps(n_frames: int, threads: int, h: int = H1080, w: int = W108
     return 1.0 / float(np.median(times)), times
 
 
+def plugin_surface_fps(sd, clip: np.ndarray, n_frames: int, batch: int):
+    """frames/s of HAVC_colorizer(method=0) itself: a clip of the in-repo VapourSynth stand-in in, frames out through
+    get_frame() in order from ONE host thread (plane stacking, f.copy(), per-plane copies and the read-ahead pipeline
+    included) - what a script switching from the reference calls."""
+    from vsdeoldify_b200 import havc, vs_shim
+    havc.register_state_dict("ColorizeVideo_gen", sd)
+    havc._BATCH = batch
+    n = min(n_frames, clip.shape[0])
+    src = vs_shim.array_clip(clip[:n], props=[{"_SceneChangePrev": int(i == 0)} for i in range(n)])
+    out = havc.HAVC_colorizer(src, method=0, deoldify_p=[0, RF, 1.0, 0.0], ddcolor_p=[1, RF, 1.0, 0.0, True])
+    out.get_frame(0)                                    # first batch: engine warm, pipeline primed
+    t0 = time.perf_counter()
+    acc = 0
+    for i in range(batch, n):
+        acc += int(np.asarray(out.get_frame(i)[0])[0, 0])
+    dt = time.perf_counter() - t0
+    return {"value": (n - batch) / dt, "unit": "frames/s", "frames": n - batch,
+            "how": "HAVC_colorizer(method=0) on a VapourSynth-stand-in clip, sequential get_frame() from one host thread"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -168,6 +188,8 @@ def main():
     ap.add_argument("--dtype", default=os.environ.get("HAVC_BENCH_DTYPE", "fp16"), choices=["fp16", "bf16"])
     ap.add_argument("--cpu-frames", type=int, default=4, help="frames of the bounded CPU-baseline sample (0 = skip)")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--plugin-frames", type=int, default=128,
+                    help="frames rendered through HAVC_colorizer on a VapourSynth-stand-in clip for the plugin_surface figure (0 = skip)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -181,6 +203,8 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION / INFO) off it
+        os.environ["NCCL_DEBUG"] = os.environ.get("HAVC_NCCL_DEBUG", "WARN")
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     if not torch.cuda.is_available():
@@ -294,6 +318,14 @@ def main():
                "sample": f"{args.cpu_frames} frames of the same 1080p workload (after 1 warm-up frame), median per-frame wall clock, "
                          "torch CPU fp32 oracle port of the reference path"}
 
+    # ---------------- the same path through the plugin surface (rank 0, N = 1 only; informational) ----------------
+    plugin = None
+    if rank == 0 and world == 1 and args.plugin_frames > 0:
+        try:
+            plugin = plugin_surface_fps(sd, clip, args.plugin_frames, B)
+        except Exception as e:      # never lose the bench line over the informational figure
+            plugin = {"error": str(e)[:200]}
+
     if rank == 0:
         frames = world * B * K
         value = frames / (ms_dev * 1e-3)
@@ -309,7 +341,7 @@ def main():
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * 3 * H1080 * W1080, "d2h_bytes_per_step": B * 3 * H1080 * W1080},
             "gpu_launches": eng.launches_per_batch * K,
             "clocks": sampler.summary(),
-            "roofline": roof, "breakdown": breakdown, "cpu_baseline": cpu,
+            "roofline": roof, "breakdown": breakdown, "cpu_baseline": cpu, "plugin_surface": plugin,
             "tensor_frac_whole_step": (GFLOP_PER_FRAME_SURVEY * 1e9 * value / world) / (load_peaks()["tf_sustained"] * 1e12),
         }
         print(json.dumps(line), flush=True)

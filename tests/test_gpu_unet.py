@@ -111,3 +111,23 @@ def test_graph_replay_is_deterministic_and_ordered():
     assert n == 5 and sorted(got) == list(range(5))
     for i in range(5):
         assert np.array_equal(got[i], ref[i]), f"batch {i} differs between sync and pipelined paths"
+
+
+@pytest.mark.parametrize("H,W,rf", [(83, 150, 8), (97, 131, 6), (64, 100, 8)])
+def test_colorizer_frame_odd_sizes_scalar_pixel_kernels(H, W, rf):
+    """Frame widths that are not multiples of 4 (and a frame narrower than render_factor*16: S = W) take the scalar
+    fall-backs of the squeeze / un-squeeze kernels instead of the 4-pixel / multi-row variants: same parity bar."""
+    from oracle import metrics, pipeline_oracle
+    from vsdeoldify_b200.engine import DeoldifyEngine
+    sd = _sd("wide")
+    if min(rf * 16, W) % 32 != 0:
+        with pytest.raises(ValueError):
+            DeoldifyEngine(sd, W, H, render_factor=rf, batch=2, dtype=torch.float16)
+        return
+    eng = DeoldifyEngine(sd, W, H, render_factor=rf, batch=2, dtype=torch.float16)
+    frames = _frames(2, H, W, seed=31)
+    out = eng.colorize_batch(frames)
+    for i in range(2):
+        ref = pipeline_oracle.havc_colorizer_frame(sd, np.transpose(frames[i], (1, 2, 0)), rf)
+        m = metrics.frame_parity(np.transpose(out[i], (1, 2, 0)), ref)
+        assert m["mean_de00"] <= 0.5, (H, W, rf, i, m)

@@ -217,37 +217,45 @@ __global__ void affine_act_kernel(const uint4 *__restrict__ in, uint4 *__restric
 // One thread walks a strip of kBlurRows output rows for a fixed (x, 8-channel group) and keeps the previous input row's two
 // taps in registers, so every output costs two 16-byte loads instead of four.
 static constexpr int kBlurRows = 8;
+static constexpr int kBlurCols = 2;   // adjacent output columns per thread: kBlurCols + 1 loads per row for kBlurCols outputs
+__device__ __forceinline__ uint4 blur_avg4(const uint4 &a, const uint4 &b, const uint4 &c, const uint4 &d, int dtype) {
+    const uint32_t pa[4] = {a.x, a.y, a.z, a.w}, pb[4] = {b.x, b.y, b.z, b.w}, pc[4] = {c.x, c.y, c.z, c.w}, pd[4] = {d.x, d.y, d.z, d.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float2 fa = unpack2(pa[j], dtype), fb = unpack2(pb[j], dtype), fc = unpack2(pc[j], dtype), fd = unpack2(pd[j], dtype);
+        o[j] = pack2(((fa.x + fb.x) + (fc.x + fd.x)) * 0.25f, ((fa.y + fb.y) + (fc.y + fd.y)) * 0.25f, dtype);
+    }
+    return make_uint4(o[0], o[1], o[2], o[3]);
+}
 __global__ void blur2x2_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, int B, int H, int W, int C8,
                                int out_stride8, int dtype) {
     const int strips = (H + kBlurRows - 1) / kBlurRows;
-    const long long total = (long long)B * strips * W * C8;
+    const int xg = (W + kBlurCols - 1) / kBlurCols;
+    const long long total = (long long)B * strips * xg * C8;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         const int cg = (int)(i % C8);
         long long t = i / C8;
-        const int x = (int)(t % W);
-        t /= W;
+        const int x = (int)(t % xg) * kBlurCols;
+        t /= xg;
         const int ys = (int)(t % strips) * kBlurRows;
         const int b = (int)(t / strips);
-        const int x0 = x > 0 ? x - 1 : 0;
+        // columns x-1 (clamped), x, x+1 (clamped to W-1: only read when x+1 < W)
+        const int xl = x > 0 ? x - 1 : 0, xr = x + 1 < W ? x + 1 : W - 1;
+        const bool two = x + 1 < W;
         const uint4 *base = in + (long long)b * H * W * C8 + cg;
         const int yp = ys > 0 ? ys - 1 : 0;
-        uint4 p0 = __ldg(base + ((long long)yp * W + x0) * C8), p1 = __ldg(base + ((long long)yp * W + x) * C8);
+        uint4 p0 = __ldg(base + ((long long)yp * W + xl) * C8), p1 = __ldg(base + ((long long)yp * W + x) * C8),
+              p2 = __ldg(base + ((long long)yp * W + xr) * C8);
         const int yend = min(ys + kBlurRows, H);
         for (int y = ys; y < yend; ++y) {
-            const uint4 c0 = __ldg(base + ((long long)y * W + x0) * C8), c1 = __ldg(base + ((long long)y * W + x) * C8);
-            const uint32_t a[4] = {p0.x, p0.y, p0.z, p0.w}, bq[4] = {p1.x, p1.y, p1.z, p1.w};
-            const uint32_t c[4] = {c0.x, c0.y, c0.z, c0.w}, d[4] = {c1.x, c1.y, c1.z, c1.w};
-            uint32_t o[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float2 fa = unpack2(a[j], dtype), fb = unpack2(bq[j], dtype), fc = unpack2(c[j], dtype),
-                             fd = unpack2(d[j], dtype);
-                o[j] = pack2(((fa.x + fb.x) + (fc.x + fd.x)) * 0.25f, ((fa.y + fb.y) + (fc.y + fd.y)) * 0.25f, dtype);
-            }
-            out[(((long long)b * H + y) * W + x) * out_stride8 + cg] = make_uint4(o[0], o[1], o[2], o[3]);
-            p0 = c0;
-            p1 = c1;
+            const uint4 c0 = __ldg(base + ((long long)y * W + xl) * C8), c1 = __ldg(base + ((long long)y * W + x) * C8),
+                        c2 = __ldg(base + ((long long)y * W + xr) * C8);
+            uint4 *dst = out + (((long long)b * H + y) * W + x) * out_stride8 + cg;
+            dst[0] = blur_avg4(p0, p1, c0, c1, dtype);
+            if (two) dst[out_stride8] = blur_avg4(p1, p2, c1, c2, dtype);
+            p0 = c0; p1 = c1; p2 = c2;
         }
     }
 }
@@ -368,7 +376,7 @@ extern "C" int havc_blur2x2(const void *in, void *out, int B, int H, int W, int 
                             void *stream) {
     HAVC_CHECK_ARG(in && out && in != out && dt16(dtype) && C % 8 == 0 && out_pix_stride % 8 == 0 && out_pix_stride >= C,
                    "havc_blur2x2: bad arguments");
-    const long long n = (long long)B * ((H + kBlurRows - 1) / kBlurRows) * W * (C / 8);
+    const long long n = (long long)B * ((H + kBlurRows - 1) / kBlurRows) * ((W + kBlurCols - 1) / kBlurCols) * (C / 8);
     blur2x2_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const uint4 *)in, (uint4 *)out, B, H, W, C / 8,
                                                                       out_pix_stride / 8, dtype);
     HAVC_LAUNCHED();

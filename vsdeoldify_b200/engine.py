@@ -92,8 +92,11 @@ class DeoldifyEngine:
         self.tmp_up = torch.empty(B, 3, H, S, **f32)
         self.net_out = torch.empty(B, 3, S, S, **f32) if debug_net_out else None
         self.x_in = self.prog.x if self.prog is not None else torch.zeros(B, S, S, 8, dtype=dtype, device=self.dev)
-        self.skip = torch.zeros(B, **u8)                  # per-frame scene-change gate (1 = leave uncoloured)
-        self.h_skip = torch.zeros(B, dtype=torch.uint8).pin_memory()
+        # per-frame scene-change gate (1 = leave uncoloured): one device / pinned pair per input slot, so that two batches
+        # can be in flight (the launch list of slot s reads skip_slots[s])
+        self.skip_slots = [torch.zeros(B, **u8) for _ in range(self.n_slots)]
+        self.h_skip_slots = [torch.zeros(B, dtype=torch.uint8).pin_memory() for _ in range(self.n_slots)]
+        self.skip, self.h_skip = self.skip_slots[0], self.h_skip_slots[0]
         self.compute = torch.cuda.Stream(device=self.dev)
         self.copy_in = torch.cuda.Stream(device=self.dev)
         self.copy_out = torch.cuda.Stream(device=self.dev)
@@ -105,6 +108,7 @@ class DeoldifyEngine:
     # ---- launch list ------------------------------------------------------------------------------
     def _launch(self, slot: int, stream: int):
         lib, B, S, W, H = self.lib, self.B, self.S, self.W, self.H
+        skip = self.skip_slots[slot]
         chk = _lib.check
         td, tv, uh, uv = self.t_down_h, self.t_down_v, self.t_up_h, self.t_up_v
         chk(lib.havc_resample_h(self.d_in[slot].data_ptr(), self.tmp_down.data_ptr(), B * 3 * H, W, S,
@@ -116,13 +120,13 @@ class DeoldifyEngine:
             self.prog.run(stream)
             chk(lib.havc_head(self.prog.logits.data_ptr(), 0, None,
                               self.prog.b11.data_ptr(), self.rgb_small.data_ptr(), self.colored.data_ptr(),
-                              self.net_out.data_ptr() if self.net_out is not None else None, self.skip.data_ptr(), B, S,
+                              self.net_out.data_ptr() if self.net_out is not None else None, skip.data_ptr(), B, S,
                               self.hd, 1, stream),
                 "head")
         if self.prog2 is not None:
             self.prog2.run(stream)
             chk(lib.havc_head(self.prog2.logits.data_ptr(), 0, None, self.prog2.b11.data_ptr(), self.rgb_small.data_ptr(),
-                              self.colored2.data_ptr(), None, self.skip.data_ptr(), B, S, self.hd, 1, stream), "head2")
+                              self.colored2.data_ptr(), None, skip.data_ptr(), B, S, self.hd, 1, stream), "head2")
             chk(lib.havc_blend_u8(self.colored2.data_ptr(), self.colored.data_ptr(), self.colored.data_ptr(),
                                   B * 3 * S * S, self.video_weight, stream), "blend")
         if self.zhang is not None:
@@ -131,11 +135,11 @@ class DeoldifyEngine:
             if self.ddtweak is not None:                       # pre-tweak of the second model's input
                 t, tmp = self.ddtweak, self.bank.tmp
                 if self.bank.image_tweak(src_b, tmp[0], cont=t["cont"], bright=t["bright"], stream=stream):
-                    self.bank.select_frames(tmp[0], src_b, self.skip, stream)
+                    self.bank.select_frames(tmp[0], src_b, skip, stream)
                     src_b = tmp[0]
                 self.bank.luma_adjusted_levels(src_b, tmp[1], t["luma_min"], t["gamma"], t["gamma_luma_min"], t["gamma_alpha"],
                                                t["gamma_min"], stream=stream)
-                self.bank.select_frames(tmp[1], src_b, self.skip, stream)
+                self.bank.select_frames(tmp[1], src_b, skip, stream)
                 src_b = tmp[1]
             self.zhang.run(src_b, self.colored_b, stream)
             clipb = self.colored_b
@@ -146,7 +150,7 @@ class DeoldifyEngine:
                 chk(lib.havc_chroma_post_process(clipb.data_ptr(), self.rgb_small.data_ptr(), other.data_ptr(), B, S, S, stream),
                     "recover_luma")
                 clipb = other
-            self.bank.select_frames(clipb, self.rgb_small, self.skip, stream)        # scene-change gate of the 2nd model
+            self.bank.select_frames(clipb, self.rgb_small, skip, stream)        # scene-change gate of the 2nd model
             if not self.run_deoldify:
                 result = clipb
             else:
@@ -154,7 +158,7 @@ class DeoldifyEngine:
                 a, b = (clipb, self.colored) if m.get("invert") else (self.colored, clipb)
                 self.bank.combine(a, b, self.merged, m["method"], m["weight"], m["cmc_p"], m["lmm_p"], m["alm_p"], m["crt_p"],
                                   stream=stream)
-                self.bank.select_frames(self.merged, a, self.skip, stream)           # merge selectors return f[0].copy()
+                self.bank.select_frames(self.merged, a, skip, stream)           # merge selectors return f[0].copy()
                 result = self.merged
         # back to W x H: vertical pass on the S-wide image first, then the wide horizontal pass from shared memory
         chk(lib.havc_resample_v(result.data_ptr(), self.tmp_up.data_ptr(), B * 3, S, H, S,
@@ -206,6 +210,64 @@ class DeoldifyEngine:
             self.h_out[0].copy_(self.d_out[0], non_blocking=True)
         self.compute.synchronize()
         return self.h_out[0][:n].numpy().copy()
+
+    # ---- asynchronous batch API (clip rendering with read-ahead) ----------------------------------------
+    def _async_state(self):
+        if not hasattr(self, "_ev"):
+            self._ev = [dict(inp=torch.cuda.Event(), done=torch.cuda.Event(), out=torch.cuda.Event(), busy=False, used=False)
+                        for _ in range(self.n_slots)]
+            self._next = 0
+        return self._ev[self._next]
+
+    def next_input(self) -> np.ndarray:
+        """The pinned host buffer [B, 3, H, W] of the slot the next submit() will use: a caller that assembles its batch
+        plane by plane can write straight into it and call submit(None, n=...) - one host copy per frame instead of three."""
+        if self._async_state()["busy"]:
+            raise RuntimeError("DeoldifyEngine.next_input: every input slot is in flight; collect() a ticket first")
+        return self.h_in[self._next].numpy()
+
+    def submit(self, frames: Optional[np.ndarray], skip: Optional[np.ndarray] = None, n: Optional[int] = None):
+        """Enqueue one batch (uint8 [n<=B, 3, H, W] host frames, or None when the caller filled next_input()[:n]) on the next
+        input slot: H2D, the CUDA graph and D2H run on the copy / compute streams; returns a ticket for collect().  At most
+        n_slots batches may be outstanding."""
+        ev = self._async_state()
+        s = self._next
+        if ev["busy"]:
+            raise RuntimeError("DeoldifyEngine.submit: every input slot is in flight; collect() a ticket first")
+        self._next = (s + 1) % self.n_slots
+        if frames is not None:
+            n = frames.shape[0]
+            assert n <= self.B and frames.shape[1:] == (3, self.H, self.W) and frames.dtype == np.uint8
+            self.h_in[s][:n].copy_(torch.from_numpy(np.ascontiguousarray(frames)))
+        assert n is not None and 0 < n <= self.B
+        self.h_skip_slots[s].zero_()
+        if skip is not None:
+            self.h_skip_slots[s][:n].copy_(torch.from_numpy(np.asarray(skip, dtype=np.uint8)))
+        with torch.cuda.stream(self.copy_in):
+            if ev["used"]:
+                self.copy_in.wait_event(ev["done"])          # the previous graph on this slot has consumed d_in / skip
+            self.d_in[s].copy_(self.h_in[s], non_blocking=True)
+            self.skip_slots[s].copy_(self.h_skip_slots[s], non_blocking=True)
+            ev["inp"].record(self.copy_in)
+        self.compute.wait_event(ev["inp"])
+        if ev["used"]:
+            self.compute.wait_event(ev["out"])               # d_out of this slot has been downloaded
+        self.run_slot(s)
+        ev["done"].record(self.compute)
+        with torch.cuda.stream(self.copy_out):
+            self.copy_out.wait_event(ev["done"])
+            self.h_out[s].copy_(self.d_out[s], non_blocking=True)
+            ev["out"].record(self.copy_out)
+        ev["busy"], ev["used"] = True, True
+        return (s, n)
+
+    def collect(self, ticket) -> np.ndarray:
+        """Wait for a submitted batch and return its uint8 [n, 3, H, W] result (a copy)."""
+        s, n = ticket
+        ev = self._ev[s]
+        ev["out"].synchronize()
+        ev["busy"] = False
+        return self.h_out[s][:n].numpy().copy()
 
     # ---- pipelined API (bench e2e / clip rendering) ----------------------------------------------------
     def colorize_stream(self, batches, on_result):

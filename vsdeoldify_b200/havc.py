@@ -73,36 +73,80 @@ def load_state_dict(weights_name: str, models_dir: str = model_dir) -> Dict[str,
 
 
 class _ColorizedClip:
-    """frame_fn of the output clip: batches source frames through the engine, caches results by frame number."""
+    """frame_fn of the output clip: batches source frames through the engine, caches results by frame number.
+
+    With an engine that has submit() / collect() the clip reads ahead: while the batch that holds frame n is on the GPU the
+    source frames of the NEXT batch are already fetched, uploaded and queued, so a sequential reader (the normal VapourSynth
+    access pattern) keeps the device busy; any other access pattern still gets the same frames, batch by batch."""
 
     def __init__(self, clip, engine, scenechange: bool, batch: int, run=None):
         self.clip, self.engine = clip, engine
         self.run = run if run is not None else engine.colorize_batch
+        self.async_ok = run is None and hasattr(engine, "submit")
         self.scenechange, self.B = scenechange, batch
         self.cache: "OrderedDict[int, object]" = OrderedDict()
+        self.pending = None                               # read-ahead job: (first frame, source frames, ticket)
         self.lock = threading.Lock()
 
     def _planes(self, f) -> np.ndarray:
         return np.stack([np.asarray(f[p]) for p in range(3)])
 
+    def _fetch(self, n: int):
+        n1 = min(n + self.B, self.clip.num_frames)
+        srcs = [self.clip.get_frame(i) for i in range(n, n1)]
+        batch = np.stack([self._planes(f) for f in srcs])
+        skip = None
+        if self.scenechange:    # vsslib/vsmodels.py:221-224: only scene-change frames are colourised
+            skip = np.array([not (i == 0 or f.props.get("_SceneChangePrev", 0) == 1) for i, f in zip(range(n, n1), srcs)])
+        return srcs, batch, skip
+
+    def _store(self, n: int, srcs, out):
+        for i, f in zip(range(n, n + len(srcs)), srcs):
+            if hasattr(f, "with_planes"):             # the stand-in adopts the result planes (views of `out`, which is ours)
+                g = f.with_planes([out[i - n, p] for p in range(3)])
+            else:
+                g = f.copy()                          # all props of the source frame survive (vsutils.py:92-95)
+                for p in range(3):
+                    np.copyto(np.asarray(g[p]), out[i - n, p])
+            self.cache[i] = g
+        while len(self.cache) > 4 * self.B:
+            self.cache.popitem(last=False)
+
+    def _start(self, n: int):
+        """Fetch the source frames of the batch that starts at n straight into the engine's pinned input buffer and queue it."""
+        n1 = min(n + self.B, self.clip.num_frames)
+        srcs = [self.clip.get_frame(i) for i in range(n, n1)]
+        buf = self.engine.next_input()
+        for j, f in enumerate(srcs):
+            for p in range(3):
+                np.copyto(buf[j, p], np.asarray(f[p]))
+        skip = None
+        if self.scenechange:    # vsslib/vsmodels.py:221-224: only scene-change frames are colourised
+            skip = np.array([not (i == 0 or f.props.get("_SceneChangePrev", 0) == 1) for i, f in zip(range(n, n1), srcs)])
+        return (n, srcs, self.engine.submit(None, skip=skip, n=len(srcs)))
+
+    def _finish(self, job):
+        n, srcs, ticket = job
+        self._store(n, srcs, self.engine.collect(ticket))
+
     def __call__(self, n: int):
         with self.lock:
             if n in self.cache:
                 return self.cache[n]
-            n1 = min(n + self.B, self.clip.num_frames)
-            srcs = [self.clip.get_frame(i) for i in range(n, n1)]
-            batch = np.stack([self._planes(f) for f in srcs])
-            skip = None
-            if self.scenechange:    # vsslib/vsmodels.py:221-224: only scene-change frames are colourised
-                skip = np.array([not (i == 0 or f.props.get("_SceneChangePrev", 0) == 1) for i, f in zip(range(n, n1), srcs)])
-            out = self.run(batch, skip=skip)
-            for i, f in zip(range(n, n1), srcs):
-                g = f.copy()                              # all props of the source frame survive (vsutils.py:92-95)
-                for p in range(3):
-                    np.copyto(np.asarray(g[p]), out[i - n, p])
-                self.cache[i] = g
-            while len(self.cache) > 4 * self.B:
-                self.cache.popitem(last=False)
+            if not self.async_ok:
+                srcs, batch, skip = self._fetch(n)
+                self._store(n, srcs, self.run(batch, skip=skip))
+                return self.cache[n]
+            job, self.pending = self.pending, None
+            if job is not None and not (job[0] <= n < job[0] + len(job[1])):
+                self._finish(job)                         # a read-ahead nobody asked for yet: keep its frames, free its slot
+                job = None
+            if job is None:
+                job = self._start(n)
+            nxt = job[0] + len(job[1])
+            if nxt < self.clip.num_frames and nxt not in self.cache:
+                self.pending = self._start(nxt)           # queued behind `job`; its upload overlaps job's compute
+            self._finish(job)
             return self.cache[n]
 
 

@@ -76,6 +76,12 @@ class VideoFrame:
     def get_read_array(self, plane):
         return self._planes[plane]
 
+    def with_planes(self, planes: Sequence[np.ndarray]) -> "VideoFrame":
+        """A new frame with this frame's format and (copied) props that ADOPTS the given plane arrays instead of copying and
+        overwriting them: what `g = f.copy(); np.copyto(np.asarray(g[p]), plane)` yields, without the two plane copies.
+        (Stand-in only: real VapourSynth frames are copy-on-write and are filled through np.copyto.)"""
+        return VideoFrame(planes, self.format, dict(self.props))
+
 
 class VideoNode:
     """Lazily evaluated clip: `get_frame(n)` calls the frame function (like a VapourSynth filter node)."""
