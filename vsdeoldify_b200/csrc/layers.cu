@@ -199,12 +199,16 @@ __global__ void affine_act_kernel(const uint4 *__restrict__ in, uint4 *__restric
         const long long pix = i / C8;
         uint4 v = __ldg(in + pix * in_stride8 + cg);
         uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        // the 8 scales / shifts of this channel group as two 16-byte loads each (16 scalar loads per 16 bytes of data made
+        // the kernel load/store-unit bound for wide tensors: 1.7 TB/s at C = 256 against 4.4 TB/s at C = 64)
+        const float4 s0 = __ldg(reinterpret_cast<const float4 *>(scale) + 2 * cg), s1 = __ldg(reinterpret_cast<const float4 *>(scale) + 2 * cg + 1);
+        const float4 t0 = __ldg(reinterpret_cast<const float4 *>(shift) + 2 * cg), t1 = __ldg(reinterpret_cast<const float4 *>(shift) + 2 * cg + 1);
+        const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w}, sh[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             float2 f = unpack2(w[j], dtype);
-            const int c = cg * 8 + 2 * j;
-            f.x = fmaf(f.x, __ldg(scale + c), __ldg(shift + c));
-            f.y = fmaf(f.y, __ldg(scale + c + 1), __ldg(shift + c + 1));
+            f.x = fmaf(f.x, sc[2 * j], sh[2 * j]);
+            f.y = fmaf(f.y, sc[2 * j + 1], sh[2 * j + 1]);
             if (relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); }
             w[j] = pack2(f.x, f.y, dtype);
         }
@@ -217,7 +221,7 @@ __global__ void affine_act_kernel(const uint4 *__restrict__ in, uint4 *__restric
 // One thread walks a strip of kBlurRows output rows for a fixed (x, 8-channel group) and keeps the previous input row's two
 // taps in registers, so every output costs two 16-byte loads instead of four.
 static constexpr int kBlurRows = 8;
-static constexpr int kBlurCols = 2;   // adjacent output columns per thread: kBlurCols + 1 loads per row for kBlurCols outputs
+static constexpr int kBlurCols = 4;   // adjacent output columns per thread: kBlurCols + 1 loads per row for kBlurCols outputs
 __device__ __forceinline__ uint4 blur_avg4(const uint4 &a, const uint4 &b, const uint4 &c, const uint4 &d, int dtype) {
     const uint32_t pa[4] = {a.x, a.y, a.z, a.w}, pb[4] = {b.x, b.y, b.z, b.w}, pc[4] = {c.x, c.y, c.z, c.w}, pd[4] = {d.x, d.y, d.z, d.w};
     uint32_t o[4];
@@ -241,21 +245,26 @@ __global__ void blur2x2_kernel(const uint4 *__restrict__ in, uint4 *__restrict__
         t /= xg;
         const int ys = (int)(t % strips) * kBlurRows;
         const int b = (int)(t / strips);
-        // columns x-1 (clamped), x, x+1 (clamped to W-1: only read when x+1 < W)
-        const int xl = x > 0 ? x - 1 : 0, xr = x + 1 < W ? x + 1 : W - 1;
-        const bool two = x + 1 < W;
+        // input columns x-1 (clamped at 0), x, x+1, ... (clamped at W-1: those outputs are not stored)
+        int xc[kBlurCols + 1];
+        xc[0] = x > 0 ? x - 1 : 0;
+#pragma unroll
+        for (int k = 0; k < kBlurCols; ++k) xc[k + 1] = x + k < W ? x + k : W - 1;
         const uint4 *base = in + (long long)b * H * W * C8 + cg;
         const int yp = ys > 0 ? ys - 1 : 0;
-        uint4 p0 = __ldg(base + ((long long)yp * W + xl) * C8), p1 = __ldg(base + ((long long)yp * W + x) * C8),
-              p2 = __ldg(base + ((long long)yp * W + xr) * C8);
+        uint4 prev[kBlurCols + 1], cur[kBlurCols + 1];
+#pragma unroll
+        for (int k = 0; k <= kBlurCols; ++k) prev[k] = __ldg(base + ((long long)yp * W + xc[k]) * C8);
         const int yend = min(ys + kBlurRows, H);
         for (int y = ys; y < yend; ++y) {
-            const uint4 c0 = __ldg(base + ((long long)y * W + xl) * C8), c1 = __ldg(base + ((long long)y * W + x) * C8),
-                        c2 = __ldg(base + ((long long)y * W + xr) * C8);
+#pragma unroll
+            for (int k = 0; k <= kBlurCols; ++k) cur[k] = __ldg(base + ((long long)y * W + xc[k]) * C8);
             uint4 *dst = out + (((long long)b * H + y) * W + x) * out_stride8 + cg;
-            dst[0] = blur_avg4(p0, p1, c0, c1, dtype);
-            if (two) dst[out_stride8] = blur_avg4(p1, p2, c1, c2, dtype);
-            p0 = c0; p1 = c1; p2 = c2;
+#pragma unroll
+            for (int k = 0; k < kBlurCols; ++k)
+                if (x + k < W) dst[(long long)k * out_stride8] = blur_avg4(prev[k], prev[k + 1], cur[k], cur[k + 1], dtype);
+#pragma unroll
+            for (int k = 0; k <= kBlurCols; ++k) prev[k] = cur[k];
         }
     }
 }
@@ -363,8 +372,9 @@ extern "C" int havc_affine_act(const void *in, void *out, long long n_pixels, in
                                int out_pix_stride, const float *scale, const float *shift, int relu, int dtype,
                                void *stream) {
     HAVC_CHECK_ARG(in && out && scale && shift && dt16(dtype) && C % 8 == 0 && in_pix_stride % 8 == 0 &&
-                       out_pix_stride % 8 == 0 && in_pix_stride >= C && out_pix_stride >= C,
-                   "havc_affine_act: bad arguments");
+                       out_pix_stride % 8 == 0 && in_pix_stride >= C && out_pix_stride >= C &&
+                       ((reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(shift)) & 15) == 0,
+                   "havc_affine_act: bad arguments (scale / shift hold C floats, 16-byte aligned)");
     const long long n = n_pixels * (C / 8);
     affine_act_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
         (const uint4 *)in, (uint4 *)out, n_pixels, C / 8, in_pix_stride / 8, out_pix_stride / 8, scale, shift, relu, dtype);
