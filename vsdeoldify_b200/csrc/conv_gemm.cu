@@ -88,6 +88,7 @@ struct ConvParams {
     // fast epilogue only: the residual tile is TMA-loaded (tensor map tmO.m[1], same box and swizzle as the output) into the
     // staging buffer ahead of the accumulator and read back from exactly the shared-memory words the result then overwrites
     int res_tma;
+    uint32_t wait_hint_ns;        // suspend-time hint of the long mbarrier waits (0 = plain polling)
     // fused 1x1 head: logits[pix][o] = sum_n y[n] * head_w[o][n]  (o < 3), written as fp32 [pix][4]; no tile store
     const float *head_w;
     float *head_out;
@@ -132,6 +133,33 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (t1 - t0 > 4000000000ull) {  // 4 s
             printf("havc conv_gemm: mbarrier timeout (block %d thread %d bar %u parity %u)\n",
                    blockIdx.x, threadIdx.x, bar, parity);
+            __trap();
+        }
+    }
+}
+// Waits that are expected to be long (the epilogue waiting for an accumulator, the producer for a free stage): try_wait with a
+// suspend-time hint parks the warp in hardware instead of re-issuing the poll every ~100 cycles (hint = 0: plain polling).
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(hint_ns)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_long(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
+    if (hint_ns == 0) { mbar_wait(bar, parity); return; }
+    if (mbar_try_wait(bar, parity)) return;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (!mbar_try_wait_hint(bar, parity, hint_ns)) {
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 4000000000ull) {  // 4 s
+            printf("havc conv_gemm: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
             __trap();
         }
     }
@@ -436,7 +464,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                     kc = ks - ksteps_main;
                     from1 = true;
                 }
-                mbar_wait(empty_bar(stage), phase ^ 1u);
+                mbar_wait_long(empty_bar(stage), phase ^ 1u, p.wait_hint_ns);
                 const uint32_t sa = smem_base + stage * p.stage_bytes;
                 const uint32_t sb = sa + kABytes;
                 const int wc = (from1 ? p.w_c1_off : 0) + kc * kChunkK;
@@ -609,7 +637,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         }
                     }
                 }
-                mbar_wait(tfull_bar(as), aphase);
+                mbar_wait_long(tfull_bar(as), aphase, p.wait_hint_ns);
                 tc_fence_after();
                 const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * p.acc_stride;
                 uint32_t va[32];
@@ -784,7 +812,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 }
             }
 
-            mbar_wait(tfull_bar(as), aphase);
+            mbar_wait_long(tfull_bar(as), aphase, p.wait_hint_ns);
             tc_fence_after();
             const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * p.acc_stride;
 
@@ -1188,6 +1216,8 @@ extern "C" int havc_conv_gemm(const havc_conv_desc *d, void *stream) {
                    d->head_w == nullptr && d->up == 1 && d->oy == 0 && d->ox == 0 && (!d->shuffle || d->group_n % 64 == 0))
                       ? 1 : 0;
     p.stage_out_bytes = p.tma_store ? (uint32_t)(kTileM * d->BN * 2) : 0u;
+    static const char *hint_env = getenv("HAVC_B200_WAIT_HINT");            // ns; A/B switch for profiling
+    p.wait_hint_ns = hint_env ? (uint32_t)atoi(hint_env) : 0u;
 
     int stages = (227 * 1024 - 1024 - kBarBytes - kEpiSmemFloats * (int)sizeof(float) - (int)p.stage_out_bytes) / (int)p.stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
