@@ -12,14 +12,20 @@
 //   * the K loop can walk two source tensors (torch.cat is never materialised);
 //   * weights [Cout][tap][Cin] arrive through a second tensor map; both operands land in shared memory
 //     in the 128-byte-swizzled K-major layout tcgen05.mma consumes directly;
-//   * one elected thread issues tcgen05.mma (M=128, N<=256, K=16, kind::f16, fp32 accumulate) into a
-//     double-buffered TMEM accumulator; tcgen05.commit releases smem stages / publishes accumulators;
-//   * eight epilogue warps drain TMEM with software-pipelined tcgen05.ld and apply, in fp32,
-//         +bias -> ReLU -> *scale+shift (eval BatchNorm) -> +residual -> ReLU
+//   * tcgen05.mma (M=128, or M=256 across a CTA pair with cta_group::2; N<=256, K=16, kind::f16, fp32 accumulate) into a
+//     double-buffered TMEM accumulator; tcgen05.commit releases smem stages / publishes accumulators.  The producer and
+//     the issuer are convergent whole-warp code with warp-uniform operands; only the TMA / MMA / commit instructions are
+//     predicated on one elected lane (issued from a divergent `if (lane == 0)` region every instruction paid an R2UR
+//     waterfall and the issuing thread, not the tensor pipe, was the limiter);
+//   * the epilogue warps drain TMEM with tcgen05.ld and apply, in fp32,
+//         +bias -> (Leaky)ReLU -> *scale+shift (eval BatchNorm) -> +residual -> ReLU
 //     then store fp16/bf16/fp32, optionally in PixelShuffle(2) order or to a strided sub-pixel phase.
 //
-// Warp roles (384 threads, 1 CTA/SM): warp0 = TMA producer, warp1 = MMA issuer, warp2 = TMEM
-// allocator, warps4-11 = epilogue (TMEM lane quarter = warp % 4; two warps per quarter split the columns).
+// Warp roles (1 CTA/SM): warp0 = TMA producer, warp1 = MMA issuer, warp2 = TMEM allocator, warps 4.. = epilogue (TMEM lane
+// quarter = warp % 4).  Two epilogues: the generic one (8 warps, 384 threads: fp32 / split / strided outputs, fused head,
+// staggered accumulators) and the fast one (16 warps, 640 threads: warp-private parameter slices, 2 KB staging blocks, one
+// TMA store per 32x32 chunk, TMA-loaded residual).  Launches are programmatic-dependent (griddepcontrol) so a kernel's
+// prologue overlaps its predecessor's tail.
 #include "common.cuh"
 #include <stdlib.h>
 #include <type_traits>

@@ -399,7 +399,7 @@ __global__ void head_kernel(const void *__restrict__ res, int Cs, const float *_
 __global__ void post_horizontal_kernel(const float *__restrict__ in, const uint8_t *__restrict__ orig,
                                        uint8_t *__restrict__ out, int B, int S, int H, int W,
                                        const int *__restrict__ start, const float *__restrict__ wts, int T,
-                                       int transplant) {
+                                       int transplant, int vec_tables) {
     extern __shared__ float srows[];   // [3][S]
     const long long ps = (long long)H * W;
     for (long long r = blockIdx.x; r < (long long)B * H; r += gridDim.x) {
@@ -433,11 +433,41 @@ __global__ void post_horizontal_kernel(const float *__restrict__ in, const uint8
                 const uint32_t o1 = __ldg(reinterpret_cast<const uint32_t *>(orig + base + ps + ox));
                 const uint32_t o2 = __ldg(reinterpret_cast<const uint32_t *>(orig + base + 2 * ps + ox));
                 uint32_t p0 = 0, p1 = 0, p2 = 0;
+                if (vec_tables && T <= 8) {
+                    // the four pixels' weights arrive as ONE 16-byte load per tap and their window starts as one int4 (the
+                    // per-pixel path issues 36 scalar table loads per item and the pass is L1 / load-store bound); same FMA order
+                    const int4 s4 = __ldg(reinterpret_cast<const int4 *>(start) + x4);
+                    const int s0k[4] = {s4.x, s4.y, s4.z, s4.w};
+                    float wk[8][4];
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        const float4 w4 = t < T ? __ldg(reinterpret_cast<const float4 *>(wts + (long long)t * W) + x4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        wk[t][0] = w4.x; wk[t][1] = w4.y; wk[t][2] = w4.z; wk[t][3] = w4.w;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+                        const float *sp = srows + s0k[k];
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) {
+                            if (t < T) {
+                                acc0 = fmaf(wk[t][k], sp[t], acc0);
+                                acc1 = fmaf(wk[t][k], sp[S + t], acc1);
+                                acc2 = fmaf(wk[t][k], sp[2 * S + t], acc2);
+                            }
+                        }
+                        const int q0 = round_u8(acc0), q1 = round_u8(acc1), q2 = round_u8(acc2);
+                        int rr = q0, gg = q1, bb = q2;
+                        luma_transplant((o0 >> (8 * k)) & 0xff, (o1 >> (8 * k)) & 0xff, (o2 >> (8 * k)) & 0xff, q0, q1, q2, rr, gg, bb);
+                        p0 |= (uint32_t)rr << (8 * k); p1 |= (uint32_t)gg << (8 * k); p2 |= (uint32_t)bb << (8 * k);
+                    }
+                } else {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     int rr, gg, bb;
                     pixel(ox + k, (o0 >> (8 * k)) & 0xff, (o1 >> (8 * k)) & 0xff, (o2 >> (8 * k)) & 0xff, rr, gg, bb);
                     p0 |= (uint32_t)rr << (8 * k); p1 |= (uint32_t)gg << (8 * k); p2 |= (uint32_t)bb << (8 * k);
+                }
                 }
                 *reinterpret_cast<uint32_t *>(out + base + ox) = p0;
                 *reinterpret_cast<uint32_t *>(out + base + ps + ox) = p1;
@@ -630,8 +660,11 @@ extern "C" int havc_post_horizontal(const float *in, const uint8_t *orig, uint8_
                    "havc_post_horizontal: bad arguments");
     long long rows = (long long)B * H;
     long long g = rows < (long long)num_sms() * 16 ? rows : (long long)num_sms() * 16;
+    static const bool legacy_p = getenv("HAVC_B200_LEGACY_PIXEL") != nullptr;   // A/B switch for profiling
+    // 16-byte loads of the start / weight tables need aligned tables and rows (W % 4 == 0)
+    const bool vec = !legacy_p && (W & 3) == 0 && ((reinterpret_cast<uintptr_t>(start) | reinterpret_cast<uintptr_t>(weights)) & 15) == 0;
     post_horizontal_kernel<<<(int)g, 256, 3 * S * sizeof(float), (cudaStream_t)stream>>>(in, orig, out, B, S, H, W, start,
-                                                                                     weights, taps, transplant);
+                                                                                     weights, taps, transplant, vec ? 1 : 0);
     HAVC_LAUNCHED();
     return HAVC_OK;
 }
