@@ -174,10 +174,29 @@ def run_reference(args):
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line: everything any library prints to fd 1 while the bench runs (NCCL's version banner,
+    warnings) is sent to stderr instead, and emit() writes the line to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -203,8 +222,8 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION / INFO) off it
-        os.environ["NCCL_DEBUG"] = os.environ.get("HAVC_NCCL_DEBUG", "WARN")
+        if "HAVC_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["HAVC_NCCL_DEBUG"]
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     if not torch.cuda.is_available():
@@ -344,7 +363,7 @@ def main():
             "roofline": roof, "breakdown": breakdown, "cpu_baseline": cpu, "plugin_surface": plugin,
             "tensor_frac_whole_step": (GFLOP_PER_FRAME_SURVEY * 1e9 * value / world) / (load_peaks()["tf_sustained"] * 1e12),
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
