@@ -179,3 +179,21 @@ def test_two_rank_partition_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert got == [n * 10 + 1 for n in range(n_frames)]
+
+
+def test_clip_adapter_recycles_only_unreferenced_result_arrays():
+    """The clip adapter hands out frames whose planes are views of big result arrays; an array may be reused for a later batch
+    only when no frame (view) references it any more."""
+    from vsdeoldify_b200 import havc
+
+    class FakeClip:
+        height, width, num_frames = 4, 6, 10
+    c = havc._ColorizedClip.__new__(havc._ColorizedClip)
+    c.B, c.clip, c._bufs = 2, FakeClip(), []
+    v = c._result_buf()[0, 1]                 # a frame plane keeps the first array alive and busy
+    first = id(v.base)
+    w = c._result_buf()[:1]
+    assert id(w.base) != first and len(c._bufs) == 2
+    del v
+    assert id(c._result_buf()) == first       # free again -> recycled, no new allocation
+    assert len(c._bufs) == 2

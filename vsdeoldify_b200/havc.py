@@ -18,7 +18,9 @@ from __future__ import annotations
 
 import math
 import os
+import sys
 import threading
+from concurrent.futures import ThreadPoolExecutor
 from collections import OrderedDict
 from typing import Dict, List, Optional, Sequence
 
@@ -41,6 +43,10 @@ _ZHANG_FILES = {"siggraph17": "siggraph17-df00044c", "eccv16": "colorization_rel
 _REGISTERED: Dict[str, Dict[str, torch.Tensor]] = {}
 _BATCH = int(os.environ.get("HAVC_B200_BATCH", "8"))
 _DTYPE = {"fp16": torch.float16, "bf16": torch.bfloat16}[os.environ.get("HAVC_B200_DTYPE", "fp16")]
+
+
+# host threads for the big plane copies of the clip adapters (numpy releases the GIL while it copies)
+_COPY_POOL = ThreadPoolExecutor(max_workers=max(1, min(8, (os.cpu_count() or 2) // 2)))
 
 
 def HAVC_LogMessage(level: int, *args):
@@ -87,6 +93,7 @@ class _ColorizedClip:
         self.cache: "OrderedDict[int, object]" = OrderedDict()
         self.pending = None                               # read-ahead job: (first frame, source frames, ticket)
         self.lock = threading.Lock()
+        self._bufs: List[np.ndarray] = []                 # recycled result arrays [B, 3, H, W] (see _result_buf)
 
     def _planes(self, f) -> np.ndarray:
         return np.stack([np.asarray(f[p]) for p in range(3)])
@@ -117,17 +124,30 @@ class _ColorizedClip:
         n1 = min(n + self.B, self.clip.num_frames)
         srcs = [self.clip.get_frame(i) for i in range(n, n1)]
         buf = self.engine.next_input()
-        for j, f in enumerate(srcs):
+
+        def put(j):
             for p in range(3):
-                np.copyto(buf[j, p], np.asarray(f[p]))
+                np.copyto(buf[j, p], np.asarray(srcs[j][p]))
+        list(_COPY_POOL.map(put, range(len(srcs))))
         skip = None
         if self.scenechange:    # vsslib/vsmodels.py:221-224: only scene-change frames are colourised
             skip = np.array([not (i == 0 or f.props.get("_SceneChangePrev", 0) == 1) for i, f in zip(range(n, n1), srcs)])
         return (n, srcs, self.engine.submit(None, skip=skip, n=len(srcs)))
 
+    def _result_buf(self) -> np.ndarray:
+        """A result array nobody references any more (the frames we hand out are views of these arrays and keep them alive
+        through `.base`), else a new one: allocating 200 MB per batch costs far more in page faults than the copy."""
+        for b in self._bufs:
+            if sys.getrefcount(b) <= 3:                   # the list, the loop variable, getrefcount's argument
+                return b
+        b = np.empty((self.B, 3, self.clip.height, self.clip.width), np.uint8)
+        if len(self._bufs) < 8:
+            self._bufs.append(b)
+        return b
+
     def _finish(self, job):
         n, srcs, ticket = job
-        self._store(n, srcs, self.engine.collect(ticket))
+        self._store(n, srcs, self.engine.collect(ticket, out=self._result_buf(), pool=_COPY_POOL))
 
     def __call__(self, n: int):
         with self.lock:
