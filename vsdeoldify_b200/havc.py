@@ -46,7 +46,9 @@ _DTYPE = {"fp16": torch.float16, "bf16": torch.bfloat16}[os.environ.get("HAVC_B2
 
 
 # host threads for the big plane copies of the clip adapters (numpy releases the GIL while it copies)
-_COPY_POOL = ThreadPoolExecutor(max_workers=max(1, min(8, (os.cpu_count() or 2) // 2)))
+# (one process per GPU: share the host's cores between the local ranks)
+_LOCAL_RANKS = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")) or 1))
+_COPY_POOL = ThreadPoolExecutor(max_workers=max(1, min(8, (os.cpu_count() or 2) // (2 * _LOCAL_RANKS))))
 
 
 def HAVC_LogMessage(level: int, *args):
