@@ -136,3 +136,29 @@ def test_stabilizer_surface_and_errors():
         havc.HAVC_stabilizer(clip, dark=True, render_factor=12)
     with pytest.raises(vs_shim.Error, match="temporal"):
         havc.HAVC_stabilizer(clip, stab=True)
+
+
+def test_deprecated_aliases_forward_like_the_reference(monkeypatch):
+    """ddeoldify_main / ddeoldify / ddeoldify_stabilizer (vsdeoldify/__init__.py:3631-3664): same names, parameter order and
+    forwarding as the reference's deprecated wrappers."""
+    import vsdeoldify_b200 as pkg
+    from vsdeoldify_b200 import havc
+    from vsdeoldify_b200.constants import DEF_CRT_p
+    assert list(inspect.signature(havc.ddeoldify_main).parameters) == ["clip", "Preset", "VideoTune", "ColorFix", "ColorTune", "ColorMap",
+                                                                       "degrain_strength", "enable_fp16"]
+    assert list(inspect.signature(havc.ddeoldify).parameters)[:9] == ["clip", "method", "mweight", "deoldify_p", "ddcolor_p", "dotweak",
+                                                                      "dotweak_p", "ddtweak", "ddtweak_p"]
+    assert inspect.signature(havc.ddeoldify_main).parameters["Preset"].default == "Fast"
+    calls = {}
+    monkeypatch.setattr(havc, "HAVC_main", lambda **kw: calls.setdefault("main", kw))
+    monkeypatch.setattr(havc, "HAVC_colorizer", lambda *a, **kw: calls.setdefault("col", (a, kw)))
+    monkeypatch.setattr(havc, "HAVC_stabilizer", lambda *a: calls.setdefault("stab", a))
+    clip = _clip()
+    pkg.ddeoldify_main(clip, Preset="Slow", ColorMap="red->brown")
+    assert calls["main"]["Preset"] == "Slow" and calls["main"]["ColorMap"] == "red->brown" and calls["main"]["clip"] is clip
+    havc.ddeoldify(clip, 3, 0.5, ddtweak=True, cmc_tresh=0.3)
+    a, kw = calls["col"]
+    assert a[1:3] == (3, 0.5) and a[5] == [True, False, False] and a[7] == [0.3] and a[10] == DEF_CRT_p
+    assert kw["sc_threshold"] == 0 and kw["sc_min_freq"] == 0
+    havc.ddeoldify_stabilizer(clip, True, (0.3, 0.7), colormap="blue->brown", render_factor=20)
+    assert calls["stab"][1] is True and calls["stab"][7] == "blue->brown" and calls["stab"][8] == 20

@@ -440,6 +440,37 @@ def HAVC_ddeoldify(
                           sc_min_int, sc_tht_white, sc_tht_black, device_index, torch_dir, debug_level)
 
 
+# ---- deprecated names the reference still exports (vsdeoldify/__init__.py:3631-3664): same forwarding, same warnings ----------
+def _deprecated(old: str, new: str):
+    vs.core.log_message(vs.MESSAGE_TYPE_WARNING,
+                        f"Warning: {old} is deprecated and may be removed in the future, please use '{new}' instead.")
+
+
+def ddeoldify_main(clip, Preset: str = 'Fast', VideoTune: str = 'Stable', ColorFix: str = 'Violet/Red', ColorTune: str = 'Light',
+                   ColorMap: str = 'None', degrain_strength: int = 0, enable_fp16: bool = True):
+    _deprecated("ddeoldify_main", "HAVC_main")
+    return HAVC_main(clip=clip, Preset=Preset, VideoTune=VideoTune, ColorFix=ColorFix, ColorTune=ColorTune, ColorMap=ColorMap,
+                     enable_fp16=enable_fp16)
+
+
+def ddeoldify(clip, method: int = 2, mweight: float = 0.4, deoldify_p: Sequence = (0, 24, 1.0, 0.0),
+              ddcolor_p: Sequence = (1, 24, 1.0, 0.0, True), dotweak: bool = False,
+              dotweak_p: Sequence = (0.0, 1.0, 1.0, False, 0.2, 0.5, 1.5, 0.5), ddtweak: bool = False,
+              ddtweak_p: Sequence = (DEF_TWEAK_p, "300:360|0.8,0.1"), degrain_strength: int = 0, cmc_tresh: float = 0.2,
+              lmm_p: Sequence = (0.2, 0.8, 1.0), alm_p: Sequence = (0.8, 1.0, 0.15), cmb_sw: bool = False, device_index: int = 0,
+              torch_dir: str = model_dir):
+    _deprecated("ddeoldify", "HAVC_colorizer")
+    return HAVC_colorizer(clip, method, mweight, deoldify_p, ddcolor_p, [ddtweak, False, False], ddtweak_p, [cmc_tresh], lmm_p, alm_p,
+                          DEF_CRT_p, cmb_sw, sc_threshold=0, sc_min_freq=0, device_index=device_index, torch_dir=torch_dir)
+
+
+def ddeoldify_stabilizer(clip, dark: bool = False, dark_p: Sequence = (0.2, 0.8), smooth: bool = False,
+                         smooth_p: Sequence = (0.3, 0.7, 0.9, 0.0, "none"), stab: bool = False,
+                         stab_p: Sequence = (5, 'A', 1, 15, 0.2, 0.80), colormap: str = "none", render_factor: int = 24):
+    _deprecated("ddeoldify_stabilizer", "HAVC_stabilizer")
+    return HAVC_stabilizer(clip, dark, dark_p, smooth, smooth_p, stab, stab_p, colormap, render_factor)
+
+
 # ---- HAVC_main: preset tables of vsdeoldify/havc_utils.py:335-581 (values, not code) -----------------------------------
 _PRESETS = ['placebo', 'veryslow', 'slower', 'slow', 'medium', 'fast', 'faster', 'veryfast']
 _PRESET_RF = [32, 32, 32, 28, 24, 22, 20, 16]
