@@ -104,6 +104,14 @@ typedef struct {
     /* CTA pairs: two SMs of a cluster share one 256-pixel M tile pair through tcgen05.mma.cta_group::2, each loading half of
      * the weight rows (halves the dominant L2 -> SM operand traffic).  0 = library default (on), 1 = force, -1 = off.   */
     int32_t pair;
+    /* Split-precision operands ("x3"): a value is stored as hi + lo, two 16-bit planes of identical geometry (hi = the value
+     * rounded to 16 bit, lo = the rounded remainder), and the contraction issues hi*hi + lo*hi + hi*lo (three MMAs per K step,
+     * fp32 accumulate: ~2^-20 relative operand precision instead of 2^-11).  Any of the lo pointers may be NULL (that product
+     * is skipped).  src0_lo / src1_lo / weight_lo / residual_lo have the strides of their hi tensors; out_lo (fast TMA-store
+     * epilogue only, BN <= 128, no PixelShuffle) receives the lo plane of the result.  Used where the error budget
+     * (tools/precision_emulator.py) shows 16-bit storage dominates the logit error: the ResNet encoders.             */
+    const void *src0_lo, *src1_lo, *weight_lo, *residual_lo;
+    void *out_lo;
 } havc_conv_desc;
 
 const char *havc_last_error(void);
@@ -118,22 +126,25 @@ int havc_conv_gemm(const havc_conv_desc *d, void *stream);
 
 /* im2col for tiny-Cin convolutions over 8-channel-wide input pixels.  K layout: filter row kh occupies
  * [kh*RW, kh*RW + ks*cin) with RW = round_up(ks*cin, 8): out[b,oy,ox, kh*RW + kw*cin + c] =
- * in[b, oy*stride-pad+kh, ox*stride-pad+kw, c], zero outside the image; other K positions are never written
+ * in[b, oy*stride-pad+kh, ox*stride-pad+kw, c0 + c] (c0 = 0 or 4), zero outside the image; other K positions are never written
  * (zero-initialise the buffer once).  Feeds havc_conv_gemm for the ResNet 7x7/s2 stem (torchvision conv1 behind
  * vsdeoldify/fastai/vision/learner.py:54-63), for the 3 image channels of MergeLayer(dense=True)
  * (vsdeoldify/deoldify/unet.py:273) and for Zhang's model1.0 (colorizers/eccv16.py:16, siggraph17.py:20).
  * in: [B,H,W,8], out: [B,OH,OW,Kp]. */
-int havc_im2col_small(const void *in, void *out, int B, int H, int W, int Cs, int cin, int ks, int stride,
+int havc_im2col_small(const void *in, void *out, int B, int H, int W, int Cs, int c0, int cin, int ks, int stride,
                       int pad, int Kp, int dtype, void *stream);
-/* nn.MaxPool2d(3, 2, 1) of the torchvision resnet stem. */
-int havc_maxpool3x3s2(const void *in, void *out, int B, int H, int W, int C, int dtype, void *stream);
+/* nn.MaxPool2d(3, 2, 1) of the torchvision resnet stem.  in_lo / out_lo: optional lo planes of a split-precision tensor
+ * (value = hi + lo, see havc_conv_desc), NULL for plain 16-bit tensors. */
+int havc_maxpool3x3s2(const void *in, const void *in_lo, void *out, void *out_lo, int B, int H, int W, int C, int dtype,
+                      void *stream);
 /* out[p=a*2+b][n][i][j][:] = in[n][2i+a][2j+b][:] — the input layout of a stride-2 havc_conv_gemm. */
 int havc_phase_split(const void *in, void *out, int B, int H, int W, int C, int n_phases, void *stream);
 /* y = x*scale[c]+shift[c] (+ReLU): eval BatchNorm on U-Net skips / encoder output
  * (vsdeoldify/deoldify/unet.py:203, :244).  Pixel strides (elements) let it read/write a channel slice of a
- * wider NHWC buffer, which is how torch.cat partners are written in place (MergeLayer, fastai/layers.py:149-152). */
-int havc_affine_act(const void *in, void *out, long long n_pixels, int C, int in_pix_stride, int out_pix_stride,
-                    const float *scale, const float *shift, int relu, int dtype, void *stream);
+ * wider NHWC buffer, which is how torch.cat partners are written in place (MergeLayer, fastai/layers.py:149-152).
+ * in_lo / out_lo: optional lo planes (same strides) of split-precision tensors. */
+int havc_affine_act(const void *in, const void *in_lo, void *out, void *out_lo, long long n_pixels, int C, int in_pix_stride,
+                    int out_pix_stride, const float *scale, const float *shift, int relu, int dtype, void *stream);
 /* ReplicationPad2d((1,0,1,0)) + AvgPool2d(2,1) of (Custom)PixelShuffle_ICNR
  * (vsdeoldify/deoldify/unet.py:47-52, vsdeoldify/fastai/layers.py:214-220). */
 int havc_blur2x2(const void *in, void *out, int B, int H, int W, int C, int out_pix_stride, int dtype, void *stream);

@@ -31,7 +31,7 @@ def net_output_square(sd, rgb_sq: np.ndarray) -> np.ndarray:
 def havc_colorizer_frame(sd, frame: np.ndarray, render_factor: int = 24, kernel: str = "spline64",
                          return_stages: bool = False, skip: bool = False, sd_other=None, video_weight: float = 0.5,
                          zhang=None, method: int = 0, merge_weight: float = 0.4, hue_adjust: str = "none", cmc_p=None,
-                         lmm_p=None, alm_p=None, crt_p=None, invert: bool = False, ddtweak=None):
+                         lmm_p=None, alm_p=None, crt_p=None, invert: bool = False, ddtweak=None, frame_size=None):
     """frame: uint8 [H,W,3].  Returns uint8 [H,W,3] (and the intermediate stages on request).
     skip: the scene-change gate returned the squeezed frame unchanged (vsslib/vsmodels.py:221-224).
     sd_other: 'stable'/'artistic' generator blended with the video one at S x S (visualize.py:118-137).
@@ -41,18 +41,25 @@ def havc_colorizer_frame(sd, frame: np.ndarray, render_factor: int = 24, kernel:
     from . import filters_oracle as fo
     from . import zhang_oracle
     H, W = frame.shape[:2]
-    S = min(render_factor * 16, W)
+    # frame_size (vsdeoldify/__init__.py:2502) = min(max(ddcolor_rf, deoldify_rf)*16, W); the DeOldify filter itself renders at
+    # render_factor*16 and stretches with Pillow BILINEAR when the two differ (deoldify/filters.py:37-41,70-73,82-84)
+    S = min(render_factor * 16, W) if frame_size is None else frame_size
+    N = render_factor * 16
+
+    def deoldify(sd_):
+        if N == S:
+            return px.chroma_post_process(model_process_square(sd_, small), small)   # _scale_to_square is the identity
+        return colorizer_filter(sd_, small, render_factor)
+
     small = px.resize_plane_u8(frame, S, S, kernel)                   # clip.resize.Spline64(S, S)
     if skip:
-        model_img = colored = small
+        colored = small
     else:
-        model_img = colored = None
+        colored = None
         if method != 1:
-            model_img = model_process_square(sd, small)               # _scale_to_square is the identity here
-            colored = px.chroma_post_process(model_img, small)        # _post_process at S x S
+            colored = deoldify(sd)                                    # filter.filter(): render + _post_process at S x S
             if sd_other is not None:
-                other = px.chroma_post_process(model_process_square(sd_other, small), small)
-                colored = px.pil_blend(other, colored, video_weight)
+                colored = px.pil_blend(deoldify(sd_other), colored, video_weight)
         if zhang is not None and method != 0:
             src_b = small
             if ddtweak is not None:            # vs_sc_tweak(bright, cont) + sc_constrained_tweak (vsmodels.py:326-332)
@@ -73,7 +80,7 @@ def havc_colorizer_frame(sd, frame: np.ndarray, render_factor: int = 24, kernel:
     up = px.resize_plane_u8(colored, W, H, kernel)                    # clip_lowres.resize.Spline64(W, H)
     out = px.chroma_post_process(up, frame)                           # vs_recover_clip_luma
     if return_stages:
-        return out, dict(small=small, model_img=model_img, colored=colored, up=up)
+        return out, dict(small=small, colored=colored, up=up)
     return out
 
 

@@ -78,6 +78,35 @@ def golden_render():
     np.savez_compressed(os.path.join(HERE, "model_image_render.npz"), **out)
 
 
+def golden_render_narrow():
+    """ModelImageRender on SQUARE images whose side F differs from render_factor*16 - what vs_sc_deoldify hands it when the clip
+    is narrower than render_factor*16 or when ddcolor_rf > deoldify_rf (frame_size, vsdeoldify/__init__.py:2502): the filter
+    stretches F -> rf*16 with Pillow BILINEAR, renders, and resizes back (deoldify/filters.py:37-41,70-73)."""
+    refshim.install()
+    import vsdeoldify.deoldify.generators as gen
+    from vsdeoldify.fastai.vision.learner import create_body as _cb
+    gen.create_body = lambda arch, pretrained=True, cut=None: _cb(arch, False, cut)   # no network
+    from vsdeoldify.deoldify import device
+    from vsdeoldify.deoldify.device_id import DeviceId
+    device.set(device=DeviceId.CPU)
+    from PIL import Image
+    from vsdeoldify.deoldify.visualize import ModelImageRender
+    with tempfile.TemporaryDirectory() as tmp:
+        os.makedirs(os.path.join(tmp, "models"))
+        torch.save(synth_weights.make_unet_state_dict("wide", 1234), os.path.join(tmp, "models", "ColorizeVideo_gen.pth"))
+        cwd = os.getcwd()
+        os.chdir(tmp)
+        try:
+            out = {}
+            r = ModelImageRender(package_dir=tmp, modelname="video", render_factor=4, video_weight=0.5)
+            for F in (48, 80):
+                sq = color_test_image(23 + F, F, F)
+                out[f"video_rf4_sq{F}"] = np.asarray(r.get_transformed_image(Image.fromarray(sq)))
+        finally:
+            os.chdir(cwd)
+    np.savez_compressed(os.path.join(HERE, "model_image_render_narrow.npz"), **out)
+
+
 def golden_pixels():
     """Reference vsslib helpers that import without VapourSynth (imfilters/nputils)."""
     refshim.install()
@@ -212,6 +241,11 @@ def golden_stabilizer():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1:        # regenerate selected fixtures only: python make_golden.py golden_render_narrow ...
+        for name in sys.argv[1:]:
+            globals()[name]()
+        sys.exit(0)
+    golden_render_narrow()
     golden_unets()
     golden_pixels()
     golden_filters()

@@ -267,3 +267,116 @@ def test_residual_tma_fast_epilogue_shapes(pair):
     _run_conv(3, 20, 28, [128], 512, 1, torch.bfloat16, affine=True, residual=True, relu2=True, pair=pair)    # clipped boxes
     _run_conv(2, 24, 24, [256], 64, 1, torch.float16, bias=True, residual=True, relu2=True, pair=pair)
     _run_conv(2, 24, 24, [64], 128, 3, torch.float16, bias=True, residual=True, pair=pair)                      # no final ReLU
+
+
+# ---- split-precision ("x3") launches: value = hi + lo planes, products hi*hi + lo*hi + hi*lo -------------------------------
+def _run_conv_x3(B, H, W, cins, Cout, ks, dtype, *, bias=True, relu1=True, affine=False, residual=False, relu2=False,
+                 stride=1, pair=0, a_lo=True, w_lo=True):
+    """fp32 inputs / weights, compared with an fp64 reference: the result (hi + lo of the output Pair) must be fp32-class."""
+    from vsdeoldify_b200 import ops
+    _setup()
+    dev = "cuda"
+    Cin = sum(cins)
+    xs = [torch.randn(B, c, H, W, device=dev) for c in cins]
+    w = torch.randn(Cout, Cin, ks, ks, device=dev) / (Cin * ks * ks) ** 0.5
+    q = lambda t: t if a_lo else t.to(dtype).float()
+    qw = lambda t: t if w_lo else t.to(dtype).float()
+    xcat = torch.cat([q(x) for x in xs], 1).double()
+    ref = F.conv2d(xcat, qw(w).double(), padding=(ks - 1) // 2, stride=stride)
+    bvec = torch.randn(Cout, device=dev) if bias else None
+    svec = (torch.rand(Cout, device=dev) + 0.5) if affine else None
+    tvec = torch.randn(Cout, device=dev) if affine else None
+    if bias:
+        ref = ref + bvec.double()[None, :, None, None]
+    if relu1:
+        ref = ref.relu()
+    if affine:
+        ref = ref * svec.double()[None, :, None, None] + tvec.double()[None, :, None, None]
+    OH, OW = ref.shape[2], ref.shape[3]
+    res = None
+    if residual:
+        res = torch.randn(B, Cout, OH, OW, device=dev)
+        ref = ref + res.double()
+    if relu2:
+        ref = ref.relu()
+
+    def pair_of(x, c):          # NCHW fp32 -> Pair [2,B,H,W,cp]
+        cp = ops.pad_to(c, 8)
+        t = torch.zeros(2, x.shape[0], x.shape[2], x.shape[3], cp, device=dev, dtype=dtype)
+        hi, lo = ops.split_hi_lo(_nhwc(x), dtype)
+        t[0, ..., :c], t[1, ..., :c] = hi, lo
+        return ops.Pair(t)
+    srcs = [pair_of(x, c) for x, c in zip(xs, cins)]
+    g = 1024.0                                           # power-of-two weight pre-scale, undone by the epilogue scale
+    w32, meta = ops.pack_conv_weight((w.double() * g).cpu(), cins, dtype=None)
+    whi, wlo = ops.split_hi_lo(w32, dtype)
+    whi, wlo = whi.to(dev), wlo.to(dev)
+    n_total = meta["rows"]
+    pc = lambda v, fill: None if v is None else ops.pack_cols(v, n_total, fill).to(dev)
+    scale = (svec if affine else torch.ones(Cout, device=dev)) / g
+    shift = tvec if affine else torch.zeros(Cout, device=dev)
+    out = ops.Pair(torch.full((2, B, OH, OW, ops.pad_to(Cout, 8)), float("nan"), device=dev, dtype=dtype))
+    rs = pair_of(res, Cout) if residual else None
+    if stride == 2:
+        # phase-split inputs [P,B,H/2,W/2,C] per plane
+        def split(t):
+            P = torch.zeros(2, 4, B, (H + 1) // 2, (W + 1) // 2, t.shape[-1], device=dev, dtype=dtype)
+            for a in (0, 1):
+                for b in (0, 1):
+                    v = t.t[:, :, a::2, b::2]
+                    P[:, a * 2 + b, :, :v.shape[2], :v.shape[3]] = v
+            return ops.Pair(P)
+        srcs = [split(s) for s in srcs]
+        taps = ops.taps_stride2(ks) if ks > 1 else [(0, 0, 0, 0)]
+    else:
+        taps = ops.taps_for(ks)
+    op = ops.make_conv(srcs[0].hi, whi, out.hi, taps, src1=srcs[1].hi if len(srcs) > 1 else None, w_c1_off=meta["c1_off"],
+                       n_total=n_total, bias=pc(bvec * g if bias else None, 0.0), scale=pc(scale, 1.0), shift=pc(shift, 0.0),
+                       relu1=relu1, relu2=relu2, residual=rs.hi if rs is not None else None, out_space=(B, OH, OW), pair=pair,
+                       src0_lo=srcs[0].lo if a_lo else None, src1_lo=srcs[1].lo if (a_lo and len(srcs) > 1) else None,
+                       weight_lo=wlo if w_lo else None, out_lo=out.lo, residual_lo=rs.lo if rs is not None else None)
+    op.launch()
+    torch.cuda.synchronize()
+    got = out.float()[..., :Cout].permute(0, 3, 1, 2).double()
+    err = (got - ref).abs()
+    scale_ref = float(ref.abs().mean()) + 1e-6
+    # hi + lo of fp16 carries ~2^-21 per operand and the three-product contraction drops lo*lo (2^-22 relative per term): the
+    # error of a K-term sum grows like sqrt(K) * 2^-21 (measured 4.5e-6 of the output range at K = 1152); plain fp16 operands
+    # sit at ~5e-4, so the bound still separates the two by 30x
+    tol = 1.5e-5 if dtype == torch.float16 else 3e-4
+    assert float(err.max()) <= tol * (float(ref.abs().max()) + scale_ref), \
+        f"x3 conv {cins}->{Cout} k{ks} s{stride}: max err {float(err.max()):.3e} (ref absmax {float(ref.abs().max()):.3g})"
+    pad = out.t[..., Cout:]
+    if pad.numel():
+        assert (pad == 0).all(), "pad channels must be written as zeros"
+
+
+def test_x3_conv1x1_bias_relu():
+    _run_conv_x3(2, 16, 16, [64], 64, 1, torch.float16)
+
+
+def test_x3_conv1x1_wide_residual_relu2():
+    _run_conv_x3(2, 24, 24, [256], 1024, 1, torch.float16, relu1=False, residual=True, relu2=True)
+
+
+def test_x3_conv3x3_pair_and_single():
+    _run_conv_x3(4, 24, 24, [128], 128, 3, torch.float16, pair=1)
+    _run_conv_x3(4, 24, 24, [128], 128, 3, torch.float16, pair=-1)
+
+
+def test_x3_conv3x3_stride2():
+    _run_conv_x3(2, 32, 32, [64], 128, 3, torch.float16, stride=2)
+
+
+def test_x3_conv3x3_affine_two_sources():
+    _run_conv_x3(2, 16, 16, [64, 64], 128, 3, torch.float16, affine=True)
+
+
+def test_x3_partial_planes():
+    """Only one of the lo planes present: the launch equals the contraction of the operands it was given."""
+    _run_conv_x3(2, 16, 16, [64], 64, 3, torch.float16, a_lo=False)
+    _run_conv_x3(2, 16, 16, [64], 64, 3, torch.float16, w_lo=False)
+
+
+def test_x3_bf16():
+    _run_conv_x3(2, 16, 16, [64], 64, 3, torch.bfloat16)

@@ -32,6 +32,7 @@ def _frames(n, h, w, seed=3):
 
 
 def _nchw(t, c):
+    t = t.float() if hasattr(t, "hi") else t          # split-precision tensors (ops.Pair): hi + lo
     return t[..., :c].permute(0, 3, 1, 2).float().cpu()
 
 
@@ -120,10 +121,6 @@ def test_colorizer_frame_odd_sizes_scalar_pixel_kernels(H, W, rf):
     from oracle import metrics, pipeline_oracle
     from vsdeoldify_b200.engine import DeoldifyEngine
     sd = _sd("wide")
-    if min(rf * 16, W) % 32 != 0:
-        with pytest.raises(ValueError):
-            DeoldifyEngine(sd, W, H, render_factor=rf, batch=2, dtype=torch.float16)
-        return
     eng = DeoldifyEngine(sd, W, H, render_factor=rf, batch=2, dtype=torch.float16)
     frames = _frames(2, H, W, seed=31)
     out = eng.colorize_batch(frames)
@@ -131,3 +128,23 @@ def test_colorizer_frame_odd_sizes_scalar_pixel_kernels(H, W, rf):
         ref = pipeline_oracle.havc_colorizer_frame(sd, np.transpose(frames[i], (1, 2, 0)), rf)
         m = metrics.frame_parity(np.transpose(out[i], (1, 2, 0)), ref)
         assert m["mean_de00"] <= 0.5, (H, W, rf, i, m)
+
+
+@pytest.mark.parametrize("H,W,rf,frame_size", [(90, 80, 6, None), (96, 160, 4, 96), (120, 200, 6, 160)])
+def test_colorizer_frame_size_differs_from_render_size(H, W, rf, frame_size):
+    """frame_size != render_factor*16: a clip narrower than rf*16 (W = 80 < 96) and a second model with a bigger render factor
+    (frame_size = ddcolor_rf*16 > deoldify_rf*16).  The filter's own Pillow BILINEAR stretch to rf*16 and back
+    (deoldify/filters.py:37-41,70-73) runs around the generator; the oracle branch is pinned against the real
+    ModelImageRender by tests/test_oracle_golden.py (model_image_render_narrow.npz)."""
+    from oracle import metrics, pipeline_oracle
+    from vsdeoldify_b200.engine import DeoldifyEngine
+    sd = _sd("wide")
+    eng = DeoldifyEngine(sd, W, H, render_factor=rf, batch=2, dtype=torch.float16, frame_size=frame_size)
+    assert eng.N == rf * 16 and eng.S == (frame_size or min(rf * 16, W)) and eng.N != eng.S
+    frames = _frames(2, H, W, seed=51)
+    out = eng.colorize_batch(frames, skip=np.array([False, True]))
+    ref = pipeline_oracle.havc_colorizer_frame(sd, np.transpose(frames[0], (1, 2, 0)), rf, frame_size=frame_size)
+    m = metrics.frame_parity(np.transpose(out[0], (1, 2, 0)), ref)
+    assert m["mean_de00"] <= 0.5, m
+    ref_skip = pipeline_oracle.havc_colorizer_frame(sd, np.transpose(frames[1], (1, 2, 0)), rf, frame_size=frame_size, skip=True)
+    assert np.array_equal(np.transpose(out[1], (1, 2, 0)), ref_skip), "a scene-change-skipped frame is the uncoloured squeeze path"

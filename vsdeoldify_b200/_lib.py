@@ -67,6 +67,8 @@ class ConvDesc(C.Structure):
         ("tma_store", C.c_int32),
         ("leaky1", C.c_float),
         ("pair", C.c_int32),
+        ("src0_lo", C.c_void_p), ("src1_lo", C.c_void_p), ("weight_lo", C.c_void_p), ("residual_lo", C.c_void_p),
+        ("out_lo", C.c_void_p),
     ]
 
 
@@ -81,10 +83,10 @@ _SIGNATURES = {
     "havc_launch_count": (C.c_int64, []),
     "havc_launch_count_reset": (None, []),
     "havc_conv_gemm": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
-    "havc_im2col_small": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 10 + [C.c_void_p]),
-    "havc_maxpool3x3s2": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]),
+    "havc_im2col_small": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 11 + [C.c_void_p]),
+    "havc_maxpool3x3s2": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 5 + [C.c_void_p]),
     "havc_phase_split": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]),
-    "havc_affine_act": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p,
+    "havc_affine_act": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                   C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "havc_blur2x2": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p]),
     "havc_softmax_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int,

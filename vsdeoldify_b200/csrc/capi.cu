@@ -16,11 +16,14 @@ void set_error(const char *fmt, ...) {
 }
 
 int num_sms() {
-    static int n = 0;
+    // per device: engines for several GPUs may live in one process
+    static std::atomic<int> cache[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    int n = cache[dev & 63].load(std::memory_order_relaxed);
     if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
         if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cache[dev & 63].store(n, std::memory_order_relaxed);
     }
     return n;
 }

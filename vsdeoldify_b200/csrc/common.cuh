@@ -41,6 +41,17 @@ extern std::atomic<long long> g_launches;
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 int num_sms();
+// Per-DEVICE one-time setup (cudaFuncSetAttribute opt-ins are per device, and one process may drive several GPUs):
+// true while the calling thread's current device has not been marked in `mask`; mark it with device_done() afterwards.
+static inline bool device_pending(std::atomic<unsigned long long> &mask, unsigned long long *bit) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    *bit = 1ull << (dev & 63);
+    return (mask.load(std::memory_order_acquire) & *bit) == 0;
+}
+static inline void device_done(std::atomic<unsigned long long> &mask, unsigned long long bit) {
+    mask.fetch_or(bit, std::memory_order_release);
+}
 
 // ---- device-side numeric helpers -------------------------------------------------------------
 #ifdef __CUDACC__

@@ -99,6 +99,11 @@ struct ConvParams {
     const float *head_w;
     float *head_out;
     long long hsw, hsh, hsb;
+    // split-precision operands ("x3": value = hi + lo, both 16-bit): K sub-steps per (tap, chunk) of source 0 / 1 =
+    // 1 (hi*hi) + [A has a lo plane] (lo*hi) + [W has a lo plane] (hi*lo); x3_out: the fast epilogue stores hi and lo planes
+    int a0_lo, a1_lo, w_lo, nsub0, nsub1;
+    int x3_out, res_lo;
+    uint32_t lo_stage_off;        // byte offset of the lo plane's staging blocks inside the output staging area
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -333,7 +338,11 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 // The kernel
 // ---------------------------------------------------------------------------------------------
 struct StoreMaps {
-    CUtensorMap m[4];   // [0] plain NHWC output; [0..3] the four PixelShuffle sub-pixel views
+    CUtensorMap m[4];   // [0] plain NHWC output; [0..3] the four PixelShuffle sub-pixel views; non-shuffle: [1] residual,
+                        // [2] lo plane of the output, [3] lo plane of the residual (split-precision launches)
+};
+struct LoMaps {
+    CUtensorMap a0, a1, w, w1;   // lo planes of src0 / src1 / weight (same geometry as the hi maps)
 };
 
 __device__ __forceinline__ void tma_store_5d(const CUtensorMap *tm, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
@@ -367,6 +376,7 @@ template <int kDT, bool kFast, bool kPair>
 __global__ void __launch_bounds__(kFast ? kThreadsFast : kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmW1,
+                 const __grid_constant__ LoMaps tmL,
                  const __grid_constant__ StoreMaps tmO, const __grid_constant__ ConvParams p) {
     extern __shared__ uint8_t smem_raw[];
     // let the next kernel of the stream (if launched with programmatic serialization) start its own prologue as SMs free up
@@ -445,6 +455,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int ksteps_per_tap = p.src1_single_tap ? p.chunks0 : (p.chunks0 + p.chunks1);
     const int ksteps_main = p.n_taps * ksteps_per_tap;
     const int ksteps = ksteps_main + (p.src1_single_tap ? p.chunks1 : 0);
+    // MMA-side K steps: every (tap, chunk) of source s is issued nsub_s times (split-precision products)
+    const int ksteps_mma = p.n_taps * (p.chunks0 * p.nsub0 + (p.src1_single_tap ? 0 : p.chunks1 * p.nsub1)) +
+                           (p.src1_single_tap ? p.chunks1 * p.nsub1 : 0);
 
     if (warp == 0) {
         // ===================== TMA producer (whole warp, one elected lane issues) =====================
@@ -470,11 +483,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                     kc = ks - ksteps_main;
                     from1 = true;
                 }
+                const int nsub = from1 ? p.nsub1 : p.nsub0;
+                const bool a_has_lo = (from1 ? p.a1_lo : p.a0_lo) != 0;
+                for (int sub = 0; sub < nsub; ++sub) {
+                // sub 0: A.hi x W.hi;  then A.lo x W.hi (if the source has a lo plane);  then A.hi x W.lo (if the weight has one)
+                const bool use_a_lo = sub == 1 && a_has_lo;
+                const bool use_w_lo = sub >= 1 && !use_a_lo;
                 mbar_wait_long(empty_bar(stage), phase ^ 1u, p.wait_hint_ns);
                 const uint32_t sa = smem_base + stage * p.stage_bytes;
                 const uint32_t sb = sa + kABytes;
                 const int wc = (from1 ? p.w_c1_off : 0) + kc * kChunkK;
-                const CUtensorMap *ta = from1 ? &tmA1 : &tmA0;
+                const CUtensorMap *ta = from1 ? (use_a_lo ? &tmL.a1 : &tmA1) : (use_a_lo ? &tmL.a0 : &tmA0);
+                const CUtensorMap *tw = use_w_lo ? &tmL.w : &tmW;
+                const CUtensorMap *tw1 = use_w_lo ? &tmL.w1 : &tmW1;
                 if (kPair) {
                     // both CTAs' loads complete on the LEADER's full barrier, which expects the bytes of both.  Within a CTA
                     // pair the shared::cluster address of the leader's copy of a barrier is this CTA's address with the rank
@@ -483,20 +504,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                     if (elect_one()) {
                         if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2u * p.stage_bytes);
                         tma_load_5d_pair(sa, ta, fb, kc * kChunkK, cw, ch, ab, cp);
-                        tma_load_4d_pair(sb + p.wl_smem[0], &tmW, fb, wc, wi, n0 + p.wl_row0[0] + (int)rank * p.wl_rank_rows[0], wb);
+                        tma_load_4d_pair(sb + p.wl_smem[0], tw, fb, wc, wi, n0 + p.wl_row0[0] + (int)rank * p.wl_rank_rows[0], wb);
                         if (p.n_wloads > 1)
-                            tma_load_4d_pair(sb + p.wl_smem[1], &tmW1, fb, wc, wi, n0 + p.wl_row0[1] + (int)rank * p.wl_rank_rows[1], wb);
+                            tma_load_4d_pair(sb + p.wl_smem[1], tw1, fb, wc, wi, n0 + p.wl_row0[1] + (int)rank * p.wl_rank_rows[1], wb);
                     }
                 } else {
                     if (elect_one()) {
                         mbar_arrive_expect_tx(full_bar(stage), p.stage_bytes);
                         tma_load_5d(sa, ta, full_bar(stage), kc * kChunkK, cw, ch, ab, cp);
-                        tma_load_4d(sb + p.wl_smem[0], &tmW, full_bar(stage), wc, wi, n0 + p.wl_row0[0], wb);
-                        if (p.n_wloads > 1) tma_load_4d(sb + p.wl_smem[1], &tmW, full_bar(stage), wc, wi, n0 + p.wl_row0[1], wb);
+                        tma_load_4d(sb + p.wl_smem[0], tw, full_bar(stage), wc, wi, n0 + p.wl_row0[0], wb);
+                        if (p.n_wloads > 1) tma_load_4d(sb + p.wl_smem[1], tw, full_bar(stage), wc, wi, n0 + p.wl_row0[1], wb);
                     }
                 }
                 __syncwarp();
                 if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+                }
             }
         }
     } else if (warp == 1) {
@@ -522,7 +544,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 tc_fence_after();
                 const uint32_t acc0 = tmem_base + as * p.acc_stride;
                 const uint32_t acc1 = acc0 + p.n_part0;
-                for (int ks = 0; ks < ksteps; ++ks) {
+                for (int ks = 0; ks < ksteps_mma; ++ks) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
                     const uint32_t sa = smem_base + stage * p.stage_bytes;
@@ -600,6 +622,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 float *wp = sparams + (warp - 4) * (3 * kWarpCols);
                 const uint32_t my_res_bar = wres_bar(warp - 4);
                 const bool res_tma = p.res_tma != 0, has_scale = p.scale != nullptr, shuffle = p.shuffle != 0;
+                const bool x3_out = p.x3_out != 0, res_lo = p.res_lo != 0;      // split-precision output / residual (hi + lo planes)
+                const uint32_t lo_off = p.lo_stage_off;
                 const int gn = p.group_n;
                 const float slope1 = p.slope1;
                 // origin of this warp's 32-row slab inside the (bw x bh x bb) box (all box extents are powers of two)
@@ -623,9 +647,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 if (lane == 0) {
                     bulk_wait_read<0>();       // my stores of the previous tile have finished reading my staging blocks
                     if (res_tma && n_my > 0) { // residual slab -> the same blocks (rows / channels outside the tensor arrive as zeros)
-                        mbar_arrive_expect_tx(my_res_bar, (uint32_t)n_my * 2048u);
-                        for (int k = 0; k < n_my; ++k)
+                        mbar_arrive_expect_tx(my_res_bar, (uint32_t)n_my * (res_lo ? 4096u : 2048u));
+                        for (int k = 0; k < n_my; ++k) {
                             tma_load_5d(block(part + 4 * k), &tmO.m[1], my_res_bar, n0 + (part + 4 * k) * 32, sw0, sh0, sb0, 0);
+                            if (res_lo) tma_load_5d(block(part + 4 * k) + lo_off, &tmO.m[3], my_res_bar, n0 + (part + 4 * k) * 32, sw0, sh0, sb0, 0);
+                        }
                     }
                 }
                 __syncwarp();
@@ -659,19 +685,29 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 if (res_tma && n_my > 0) { mbar_wait(my_res_bar, rphase); rphase ^= 1u; }
                 const uint32_t swz = ((uint32_t)lane >> 1) & 3u;               // SWIZZLE_64B: 16-byte chunk index ^= address bits [7:8]
                 // kAct: 0 = none, 1 = ReLU, 2 = run-time slope (LeakyReLU); the other flags switch whole stages off at compile time
-                auto chunk = [&](int k, uint32_t(&vc)[32], auto kActT, auto kScaleT, auto kResT, auto kRelu2T) {
+                auto chunk = [&](int k, uint32_t(&vc)[32], auto kActT, auto kScaleT, auto kResT, auto kRelu2T, auto kX3T) {
                     constexpr int kAct = decltype(kActT)::value;
                     constexpr bool kScale = decltype(kScaleT)::value, kRes = decltype(kResT)::value, kRelu2 = decltype(kRelu2T)::value;
+                    constexpr bool kX3 = decltype(kX3T)::value;
                     const int ci = part + 4 * k;
                     __syncwarp();
                     tmem_ld32(tbase + ci * 32, vc);
                     const uint32_t rowaddr = block(ci) + (uint32_t)lane * 64u;
-                    uint4 rres[4];
+                    uint4 rres[4], rlo[4];
                     if constexpr (kRes) {
 #pragma unroll
                         for (int g = 0; g < 4; ++g)
                             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rres[g].x), "=r"(rres[g].y), "=r"(rres[g].z), "=r"(rres[g].w)
                                          : "r"(rowaddr + (((uint32_t)g ^ swz) << 4)) : "memory");
+                        if constexpr (kX3) {
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                rlo[g] = make_uint4(0u, 0u, 0u, 0u);
+                                if (res_lo)
+                                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rlo[g].x), "=r"(rlo[g].y), "=r"(rlo[g].z), "=r"(rlo[g].w)
+                                                 : "r"(rowaddr + lo_off + (((uint32_t)g ^ swz) << 4)) : "memory");
+                            }
+                        }
                     }
                     tmem_ld_wait();
                     const float *sb = wp + k * 32;
@@ -715,15 +751,40 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                                 y[2 * j] += f.x;
                                 y[2 * j + 1] += f.y;
                             }
+                            if constexpr (kX3) {
+                                const uint32_t rl[8] = {rlo[2 * hh].x, rlo[2 * hh].y, rlo[2 * hh].z, rlo[2 * hh].w,
+                                                        rlo[2 * hh + 1].x, rlo[2 * hh + 1].y, rlo[2 * hh + 1].z, rlo[2 * hh + 1].w};
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const float2 f = unpack2(rl[j], kDT);
+                                    y[2 * j] += f.x;
+                                    y[2 * j + 1] += f.y;
+                                }
+                            }
                         }
                         if constexpr (kRelu2) {
 #pragma unroll
                             for (int j = 0; j < 16; ++j) y[j] = fmaxf(y[j], 0.f);
                         }
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowaddr + (((uint32_t)(2 * hh) ^ swz) << 4)), "r"(pack2(y[0], y[1], kDT)),
-                                     "r"(pack2(y[2], y[3], kDT)), "r"(pack2(y[4], y[5], kDT)), "r"(pack2(y[6], y[7], kDT)) : "memory");
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowaddr + (((uint32_t)(2 * hh + 1) ^ swz) << 4)), "r"(pack2(y[8], y[9], kDT)),
-                                     "r"(pack2(y[10], y[11], kDT)), "r"(pack2(y[12], y[13], kDT)), "r"(pack2(y[14], y[15], kDT)) : "memory");
+                        uint32_t hp[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) hp[j] = pack2(y[2 * j], y[2 * j + 1], kDT);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowaddr + (((uint32_t)(2 * hh) ^ swz) << 4)), "r"(hp[0]),
+                                     "r"(hp[1]), "r"(hp[2]), "r"(hp[3]) : "memory");
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowaddr + (((uint32_t)(2 * hh + 1) ^ swz) << 4)), "r"(hp[4]),
+                                     "r"(hp[5]), "r"(hp[6]), "r"(hp[7]) : "memory");
+                        if constexpr (kX3) {     // lo plane: what the 16-bit rounding of the hi plane dropped, rounded to 16 bit itself
+                            uint32_t lp[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float2 h = unpack2(hp[j], kDT);
+                                lp[j] = pack2(y[2 * j] - h.x, y[2 * j + 1] - h.y, kDT);
+                            }
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowaddr + lo_off + (((uint32_t)(2 * hh) ^ swz) << 4)), "r"(lp[0]),
+                                         "r"(lp[1]), "r"(lp[2]), "r"(lp[3]) : "memory");
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowaddr + lo_off + (((uint32_t)(2 * hh + 1) ^ swz) << 4)), "r"(lp[4]),
+                                         "r"(lp[5]), "r"(lp[6]), "r"(lp[7]) : "memory");
+                        }
                     }
                     // hand the staged chunk to the TMA unit: generic-proxy writes -> async proxy, then one bulk store
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -735,6 +796,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                             tma_store_5d(&tmO.m[g], block(ci), nn - g * gn, sw0, sh0, sb0, 0);
                         } else {
                             tma_store_5d(&tmO.m[0], block(ci), nn, sw0, sh0, sb0, 0);
+                            if constexpr (kX3) tma_store_5d(&tmO.m[2], block(ci) + lo_off, nn, sw0, sh0, sb0, 0);
                         }
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
@@ -746,18 +808,30 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 using A1 = std::integral_constant<int, 1>;
                 using A2 = std::integral_constant<int, 2>;
                 const bool relu1 = slope1 == 0.f, noact = slope1 == 1.f, relu2 = p.relu2 != 0;
-                if (relu1 && !has_scale && !res_tma && !relu2) {            // conv + folded BN + ReLU, PixelShuffle convs
-                    for (int k = 0; k < n_my; ++k) chunk(k, va, A1{}, F{}, F{}, F{});
+                if (x3_out) {   // split-precision output (encoders): the same stage combinations, storing hi and lo planes
+                    if (relu1 && !has_scale && !res_tma && !relu2) {
+                        for (int k = 0; k < n_my; ++k) chunk(k, va, A1{}, F{}, F{}, F{}, T{});
+                    } else if (noact && !has_scale && res_tma && relu2) {
+                        for (int k = 0; k < n_my; ++k) chunk(k, va, A0{}, F{}, T{}, T{}, T{});
+                    } else if (!res_tma) {
+                        if (relu2) { for (int k = 0; k < n_my; ++k) chunk(k, va, A2{}, T{}, F{}, T{}, T{}); }
+                        else { for (int k = 0; k < n_my; ++k) chunk(k, va, A2{}, T{}, F{}, F{}, T{}); }
+                    } else {
+                        if (relu2) { for (int k = 0; k < n_my; ++k) chunk(k, va, A2{}, T{}, T{}, T{}, T{}); }
+                        else { for (int k = 0; k < n_my; ++k) chunk(k, va, A2{}, T{}, T{}, F{}, T{}); }
+                    }
+                } else if (relu1 && !has_scale && !res_tma && !relu2) {            // conv + folded BN + ReLU, PixelShuffle convs
+                    for (int k = 0; k < n_my; ++k) chunk(k, va, A1{}, F{}, F{}, F{}, F{});
                 } else if (relu1 && has_scale && !res_tma && !relu2) {      // custom_conv_layer: conv -> ReLU -> BN
-                    for (int k = 0; k < n_my; ++k) chunk(k, va, A1{}, T{}, F{}, F{});
+                    for (int k = 0; k < n_my; ++k) chunk(k, va, A1{}, T{}, F{}, F{}, F{});
                 } else if (noact && !has_scale && res_tma && relu2) {       // bottleneck conv3: + identity, ReLU
-                    for (int k = 0; k < n_my; ++k) chunk(k, va, A0{}, F{}, T{}, T{});
+                    for (int k = 0; k < n_my; ++k) chunk(k, va, A0{}, F{}, T{}, T{}, F{});
                 } else if (!res_tma) {
-                    if (relu2) { for (int k = 0; k < n_my; ++k) chunk(k, va, A2{}, T{}, F{}, T{}); }
-                    else { for (int k = 0; k < n_my; ++k) chunk(k, va, A2{}, T{}, F{}, F{}); }
+                    if (relu2) { for (int k = 0; k < n_my; ++k) chunk(k, va, A2{}, T{}, F{}, T{}, F{}); }
+                    else { for (int k = 0; k < n_my; ++k) chunk(k, va, A2{}, T{}, F{}, F{}, F{}); }
                 } else {
-                    if (relu2) { for (int k = 0; k < n_my; ++k) chunk(k, va, A2{}, T{}, T{}, T{}); }
-                    else { for (int k = 0; k < n_my; ++k) chunk(k, va, A2{}, T{}, T{}, F{}); }
+                    if (relu2) { for (int k = 0; k < n_my; ++k) chunk(k, va, A2{}, T{}, T{}, T{}, F{}); }
+                    else { for (int k = 0; k < n_my; ++k) chunk(k, va, A2{}, T{}, T{}, F{}, F{}); }
                 }
                 tc_fence_before();
                 acc_signal(tempty_sig[as]);
@@ -1221,7 +1295,16 @@ extern "C" int havc_conv_gemm(const havc_conv_desc *d, void *stream) {
     p.tma_store = (d->tma_store && out16 && d->out != nullptr && d->BN % 64 == 0 && d->N_total % 64 == 0 && d->split_n == 0 &&
                    d->head_w == nullptr && d->up == 1 && d->oy == 0 && d->ox == 0 && (!d->shuffle || d->group_n % 64 == 0))
                       ? 1 : 0;
-    p.stage_out_bytes = p.tma_store ? (uint32_t)(kTileM * d->BN * 2) : 0u;
+    // split precision (hi + lo planes)
+    p.a0_lo = d->src0_lo != nullptr; p.a1_lo = (two && d->src1_lo != nullptr); p.w_lo = d->weight_lo != nullptr;
+    p.nsub0 = 1 + p.a0_lo + p.w_lo; p.nsub1 = 1 + p.a1_lo + p.w_lo;
+    p.x3_out = d->out_lo != nullptr; p.res_lo = (d->residual != nullptr && d->residual_lo != nullptr);
+    if (p.x3_out) HAVC_CHECK_ARG(p.tma_store && !d->shuffle && d->BN <= 128 && (reinterpret_cast<uintptr_t>(d->out_lo) & 15) == 0,
+                                 "havc_conv_gemm: out_lo needs the TMA-store epilogue (16-bit NHWC output, BN %% 64 == 0, BN <= 128, no PixelShuffle)");
+    for (const void *lp : {d->src0_lo, d->src1_lo, d->weight_lo, d->residual_lo})
+        HAVC_CHECK_ARG((reinterpret_cast<uintptr_t>(lp) & 15) == 0, "havc_conv_gemm: lo planes must be 16-byte aligned");
+    p.lo_stage_off = (uint32_t)(kTileM * d->BN * 2);
+    p.stage_out_bytes = p.tma_store ? (uint32_t)(kTileM * d->BN * 2) * (p.x3_out ? 2u : 1u) : 0u;
     static const char *hint_env = getenv("HAVC_B200_WAIT_HINT");            // ns; A/B switch for profiling
     p.wait_hint_ns = hint_env ? (uint32_t)atoi(hint_env) : 0u;
 
@@ -1282,6 +1365,34 @@ extern "C" int havc_conv_gemm(const havc_conv_desc *d, void *stream) {
         }
     }
     if (d->b_batched) HAVC_CHECK_ARG(d->box_b == 1, "havc_conv_gemm: b_batched=1 needs box_b=1");
+    LoMaps tmL;
+    tmL.a0 = tmA0; tmL.a1 = tmA1; tmL.w = tmW; tmL.w1 = tmW1;
+    if (p.a0_lo) {
+        havc_act_view v = d->src0;
+        v.ptr = d->src0_lo;
+        rc = encode_act(&tmL.a0, v, d->dtype, d->box_w, d->box_h, d->a_batched ? d->box_b : 1);
+        if (rc) return rc;
+    }
+    if (p.a1_lo) {
+        havc_act_view v = d->src1;
+        v.ptr = d->src1_lo;
+        rc = encode_act(&tmL.a1, v, d->dtype, d->box_w, d->box_h, d->a_batched ? d->box_b : 1);
+        if (rc) return rc;
+    }
+    if (p.w_lo) {
+        uint64_t dims[4] = {(uint64_t)d->w_cin, (uint64_t)d->w_taps, (uint64_t)d->w_rows, (uint64_t)d->w_batches};
+        uint64_t strides[4] = {1, (uint64_t)d->w_cin, (uint64_t)d->w_cin * d->w_taps,
+                               (uint64_t)d->w_cin * d->w_taps * d->w_rows};
+        uint32_t box[4] = {(uint32_t)kChunkK, 1u, (uint32_t)p.w_box_rows, 1u};
+        rc = encode_map(&tmL.w, d->dtype, 4, d->weight_lo, dims, strides, box);
+        if (rc) return rc;
+        tmL.w1 = tmL.w;
+        if (pair && p.n_part1 > 0) {
+            box[2] = (uint32_t)(p.n_part1 / 2);
+            rc = encode_map(&tmL.w1, d->dtype, 4, d->weight_lo, dims, strides, box);
+            if (rc) return rc;
+        }
+    }
 
     const size_t smem = (size_t)p.num_stages * p.stage_bytes + p.stage_out_bytes + 1024 + kBarBytes + kEpiSmemFloats * sizeof(float);
     static const bool no_fast = getenv("HAVC_B200_NO_FAST_EPILOGUE") != nullptr;   // A/B switch for profiling
@@ -1291,19 +1402,25 @@ extern "C" int havc_conv_gemm(const havc_conv_desc *d, void *stream) {
                       d->out_dtype == d->dtype && d->BN % 32 == 0 && d->N_total % d->BN == 0 &&
                       is_pow2(d->box_w) && is_pow2(d->box_h) && is_pow2(d->box_b) &&      // 32-pixel slabs must be sub-boxes
                       (d->residual == nullptr || !no_res_tma);                            // the fast epilogue takes its residual by TMA
-    typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const StoreMaps, const ConvParams);
+    if (p.x3_out) HAVC_CHECK_ARG(fast, "havc_conv_gemm: out_lo is only implemented in the fast (TMA-store) epilogue");
+    typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const LoMaps, const StoreMaps, const ConvParams);
     static const KernelFn kernels[2][2][2] = {
         {{conv_gemm_kernel<HAVC_F16, false, false>, conv_gemm_kernel<HAVC_F16, false, true>},
          {conv_gemm_kernel<HAVC_F16, true, false>, conv_gemm_kernel<HAVC_F16, true, true>}},
         {{conv_gemm_kernel<HAVC_BF16, false, false>, conv_gemm_kernel<HAVC_BF16, false, true>},
          {conv_gemm_kernel<HAVC_BF16, true, false>, conv_gemm_kernel<HAVC_BF16, true, true>}}};
     KernelFn kern = kernels[d->dtype == HAVC_F16 ? 0 : 1][fast ? 1 : 0][pair ? 1 : 0];
-    static bool attr_set = false;
-    if (!attr_set) {
-        for (int i = 0; i < 8; ++i)
-            HAVC_CHECK_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void *>(kernels[i >> 2][(i >> 1) & 1][i & 1]),
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
+    {   // the opt-in to > 48 KB of dynamic shared memory is per device (one engine per GPU may live in this process)
+        static std::atomic<unsigned long long> attr_done{0ull};
+        int dev = 0;
+        HAVC_CHECK_CUDA(cudaGetDevice(&dev));
+        const unsigned long long bit = 1ull << (dev & 63);
+        if (!(attr_done.load(std::memory_order_acquire) & bit)) {
+            for (int i = 0; i < 8; ++i)
+                HAVC_CHECK_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void *>(kernels[i >> 2][(i >> 1) & 1][i & 1]),
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            attr_done.fetch_or(bit, std::memory_order_release);
+        }
     }
     StoreMaps tmO;
     memset(&tmO, 0, sizeof(tmO));
@@ -1321,6 +1438,28 @@ extern "C" int havc_conv_gemm(const havc_conv_desc *d, void *stream) {
         v.stride_w = d->res_stride_w; v.stride_h = d->res_stride_h; v.stride_b = d->res_stride_b;
         v.stride_p = d->res_stride_b * d->out_B;
         rc = encode_act(&tmO.m[1], v, d->dtype, obw, obh, obb, fast);
+        if (rc) return rc;
+    }
+    if (p.res_tma && p.res_lo) {
+        havc_act_view v;
+        memset(&v, 0, sizeof(v));
+        v.ptr = d->residual_lo;
+        v.C = d->c_store; v.W = d->out_W; v.H = d->out_H; v.B = d->out_B; v.P = 1;
+        v.stride_w = d->res_stride_w; v.stride_h = d->res_stride_h; v.stride_b = d->res_stride_b;
+        v.stride_p = d->res_stride_b * d->out_B;
+        rc = encode_act(&tmO.m[3], v, d->dtype, obw, obh, obb, fast);
+        if (rc) return rc;
+    } else {
+        p.res_lo = 0;
+    }
+    if (p.x3_out) {
+        havc_act_view v;
+        memset(&v, 0, sizeof(v));
+        v.ptr = d->out_lo;
+        v.C = d->c_store; v.W = d->out_W; v.H = d->out_H; v.B = d->out_B; v.P = 1;
+        v.stride_w = d->out_stride_w; v.stride_h = d->out_stride_h; v.stride_b = d->out_stride_b;
+        v.stride_p = d->out_stride_b * d->out_B;
+        rc = encode_act(&tmO.m[2], v, d->out_dtype, obw, obh, obb, fast);
         if (rc) return rc;
     }
     if (p.tma_store) {
@@ -1367,7 +1506,7 @@ extern "C" int havc_conv_gemm(const havc_conv_desc *d, void *stream) {
         }
         cfg.attrs = attrs;
         cfg.numAttrs = na;
-        HAVC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA0, tmA1, tmW, tmW1, tmO, p));
+        HAVC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA0, tmA1, tmW, tmW1, tmL, tmO, p));
     }
     HAVC_LAUNCHED();
     return HAVC_OK;

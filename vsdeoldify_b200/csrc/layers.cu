@@ -27,7 +27,7 @@ static inline int grid_for(long long n_threads, int block) {
 // (with a run-time cin it sits in local memory and the kernel is bound by those load/store-unit round trips).
 template <int KS, int CIN>
 __global__ void im2col_rows_kernel(const uint4 *__restrict__ in, uint16_t *__restrict__ out, int B, int H, int W,
-                                   int cin_rt, int stride, int pad, int OH, int OW, int Kp) {
+                                   int cin_rt, int stride, int pad, int OH, int OW, int Kp, int c0) {
     constexpr int kMaxRW = ((KS * (CIN > 0 ? CIN : 8) + 7) / 8) * 8;
     const int cin = CIN > 0 ? CIN : cin_rt;
     const int RW = ((KS * cin + 7) / 8) * 8;
@@ -49,7 +49,7 @@ __global__ void im2col_rows_kernel(const uint4 *__restrict__ in, uint16_t *__res
                 const int ix = ox * stride - pad + kw;
                 if (ix < 0 || ix >= W) continue;
                 const uint4 q = __ldg(in + ((long long)b * H + iy) * W + ix);
-                const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+                const uint32_t w[4] = {c0 ? q.z : q.x, c0 ? q.w : q.y, q.z, q.w};     // c0 = 4: channels 4.. of the pixel
 #pragma unroll
                 for (int c = 0; c < 8; ++c)
                     if (c < cin) v[kw * cin + c] = (uint16_t)((w[c >> 1] >> ((c & 1) * 16)) & 0xffff);
@@ -76,7 +76,7 @@ __global__ void im2col_rows_kernel(const uint4 *__restrict__ in, uint16_t *__res
 // stores; partially written lines cost a read-modify-write at the (ECC) HBM and held it to 1-1.7 TB/s.  Needs Kp % 64 == 0.
 template <int KS, int CIN>
 __global__ void im2col_tile_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, int H, int W, int cin_rt, int stride,
-                                   int pad, int OH, int OW, int Kp, long long total_pix) {
+                                   int pad, int OH, int OW, int Kp, long long total_pix, int c0) {
     extern __shared__ uint4 tile[];          // [128][Kp / 8]
     constexpr int kMaxRW = ((KS * (CIN > 0 ? CIN : 8) + 7) / 8) * 8;
     const int cin = CIN > 0 ? CIN : cin_rt;
@@ -102,7 +102,7 @@ __global__ void im2col_tile_kernel(const uint4 *__restrict__ in, uint4 *__restri
                         const int ix = ox * stride - pad + kw;
                         if (ix < 0 || ix >= W) continue;
                         const uint4 q = __ldg(in + (b * H + iy) * W + ix);
-                        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+                        const uint32_t w[4] = {c0 ? q.z : q.x, c0 ? q.w : q.y, q.z, q.w};
 #pragma unroll
                         for (int c = 0; c < 8; ++c)
                             if (c < cin) v[kw * cin + c] = (uint16_t)((w[c >> 1] >> ((c & 1) * 16)) & 0xffff);
@@ -132,10 +132,10 @@ __global__ void im2col_tile_kernel(const uint4 *__restrict__ in, uint4 *__restri
     }
 }
 
-// 3x3 stride-2 pad-1 max-pool (torchvision resnet maxpool).
-template <typename T2>
-__global__ void maxpool_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, int B, int H, int W, int C8,
-                               int OH, int OW) {
+// 3x3 stride-2 pad-1 max-pool (torchvision resnet maxpool).  Split-precision tensors (in_lo / out_lo != NULL) are compared as
+// hi + lo in fp32 (exact: 11 + 11 significant bits) and stored as hi / lo planes again.
+__global__ void maxpool_kernel(const uint4 *__restrict__ in, const uint4 *__restrict__ in_lo, uint4 *__restrict__ out,
+                               uint4 *__restrict__ out_lo, int B, int H, int W, int C8, int OH, int OW, int dtype) {
     const long long total = (long long)B * OH * OW * C8;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -144,27 +144,41 @@ __global__ void maxpool_kernel(const uint4 *__restrict__ in, uint4 *__restrict__
         const int ox = (int)(pix % OW);
         const int oy = (int)((pix / OW) % OH);
         const int b = (int)(pix / ((long long)OW * OH));
-        T2 m[4];
-        bool first = true;
+        float m[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
         for (int dy = -1; dy <= 1; ++dy) {
             const int iy = oy * 2 + dy;
             if (iy < 0 || iy >= H) continue;
             for (int dx = -1; dx <= 1; ++dx) {
                 const int ix = ox * 2 + dx;
                 if (ix < 0 || ix >= W) continue;
-                uint4 v = __ldg(in + (((long long)b * H + iy) * W + ix) * C8 + cg);
-                const T2 *pv = reinterpret_cast<const T2 *>(&v);
-                if (first) {
+                const long long off = (((long long)b * H + iy) * W + ix) * C8 + cg;
+                const uint4 v = __ldg(in + off);
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                float f[8];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) m[j] = pv[j];
-                    first = false;
-                } else {
+                for (int j = 0; j < 4; ++j) { const float2 t = unpack2(w[j], dtype); f[2 * j] = t.x; f[2 * j + 1] = t.y; }
+                if (in_lo != nullptr) {
+                    const uint4 l = __ldg(in_lo + off);
+                    const uint32_t wl[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) m[j] = __hmax2(m[j], pv[j]);
+                    for (int j = 0; j < 4; ++j) { const float2 t = unpack2(wl[j], dtype); f[2 * j] += t.x; f[2 * j + 1] += t.y; }
                 }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
             }
         }
-        out[i] = *reinterpret_cast<uint4 *>(m);
+        uint32_t hp[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) hp[j] = pack2(m[2 * j], m[2 * j + 1], dtype);
+        out[i] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+        if (out_lo != nullptr) {
+            uint32_t lp[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const float2 h = unpack2(hp[j], dtype); lp[j] = pack2(m[2 * j] - h.x, m[2 * j + 1] - h.y, dtype); }
+            out_lo[i] = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+        }
     }
 }
 
@@ -189,9 +203,9 @@ __global__ void phase_split_kernel(const uint4 *__restrict__ in, uint4 *__restri
 
 // y = x*scale[c] + shift[c], optional ReLU (eval BatchNorm on skips / encoder output:
 // unet.py:203 `self.bn(s)`, unet.py:244 layers[1..2]).
-__global__ void affine_act_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, long long n_pix, int C8,
-                                  int in_stride8, int out_stride8, const float *__restrict__ scale,
-                                  const float *__restrict__ shift, int relu, int dtype) {
+__global__ void affine_act_kernel(const uint4 *__restrict__ in, const uint4 *__restrict__ in_lo, uint4 *__restrict__ out,
+                                  uint4 *__restrict__ out_lo, long long n_pix, int C8, int in_stride8, int out_stride8,
+                                  const float *__restrict__ scale, const float *__restrict__ shift, int relu, int dtype) {
     const long long total = n_pix * C8;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -199,6 +213,11 @@ __global__ void affine_act_kernel(const uint4 *__restrict__ in, uint4 *__restric
         const long long pix = i / C8;
         uint4 v = __ldg(in + pix * in_stride8 + cg);
         uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t wl[4] = {0u, 0u, 0u, 0u};
+        if (in_lo != nullptr) {     // split-precision input: value = hi + lo
+            const uint4 l = __ldg(in_lo + pix * in_stride8 + cg);
+            wl[0] = l.x; wl[1] = l.y; wl[2] = l.z; wl[3] = l.w;
+        }
         // the 8 scales / shifts of this channel group as two 16-byte loads each (16 scalar loads per 16 bytes of data made
         // the kernel load/store-unit bound for wide tensors: 1.7 TB/s at C = 256 against 4.4 TB/s at C = 64)
         const float4 s0 = __ldg(reinterpret_cast<const float4 *>(scale) + 2 * cg), s1 = __ldg(reinterpret_cast<const float4 *>(scale) + 2 * cg + 1);
@@ -207,12 +226,18 @@ __global__ void affine_act_kernel(const uint4 *__restrict__ in, uint4 *__restric
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             float2 f = unpack2(w[j], dtype);
-            f.x = fmaf(f.x, sc[2 * j], sh[2 * j]);
-            f.y = fmaf(f.y, sc[2 * j + 1], sh[2 * j + 1]);
+            const float2 fl = unpack2(wl[j], dtype);
+            f.x = fmaf(f.x + fl.x, sc[2 * j], sh[2 * j]);
+            f.y = fmaf(f.y + fl.y, sc[2 * j + 1], sh[2 * j + 1]);
             if (relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); }
             w[j] = pack2(f.x, f.y, dtype);
+            if (out_lo != nullptr) {
+                const float2 h = unpack2(w[j], dtype);
+                wl[j] = pack2(f.x - h.x, f.y - h.y, dtype);
+            }
         }
         out[pix * out_stride8 + cg] = make_uint4(w[0], w[1], w[2], w[3]);
+        if (out_lo != nullptr) out_lo[pix * out_stride8 + cg] = make_uint4(wl[0], wl[1], wl[2], wl[3]);
     }
 }
 
@@ -310,12 +335,12 @@ using namespace havc;
 
 static bool dt16(int d) { return d == HAVC_F16 || d == HAVC_BF16; }
 
-extern "C" int havc_im2col_small(const void *in, void *out, int B, int H, int W, int Cs, int cin, int ks, int stride,
+extern "C" int havc_im2col_small(const void *in, void *out, int B, int H, int W, int Cs, int c0, int cin, int ks, int stride,
                                  int pad, int Kp, int dtype, void *stream) {
     const int RW = ((ks * cin + 7) / 8) * 8;
     HAVC_CHECK_ARG(in && out && dt16(dtype) && Kp % 8 == 0 && Kp >= ks * RW && Cs == 8 && cin >= 1 && cin <= 8 &&
-                       (ks == 1 || ks == 3 || ks == 7),
-                   "havc_im2col_small: needs 8-channel input pixels, cin <= 8, ks in {1,3,7}, Kp >= ks*round_up(ks*cin,8)");
+                       (c0 == 0 || (c0 == 4 && cin <= 4)) && (ks == 1 || ks == 3 || ks == 7),
+                   "havc_im2col_small: needs 8-channel input pixels, c0 in {0,4}, c0 + cin <= 8, ks in {1,3,7}, Kp >= ks*round_up(ks*cin,8)");
     const int OH = (H + 2 * pad - ks) / stride + 1, OW = (W + 2 * pad - ks) / stride + 1;
     const long long n = (long long)B * OH * OW * ks;
     const int grid = grid_for(n, 256);
@@ -329,11 +354,12 @@ extern "C" int havc_im2col_small(const void *in, void *out, int B, int H, int W,
 #define HAVC_IM2COL(KS_, CIN_)                                                                                                   \
     do {                                                                                                                         \
         if (tiled)                                                                                                               \
-            im2col_tile_kernel<KS_, CIN_><<<g2, 128, sm, st>>>((const uint4 *)in, (uint4 *)out, H, W, cin, stride, pad, OH, OW, Kp, pixels); \
+            im2col_tile_kernel<KS_, CIN_><<<g2, 128, sm, st>>>((const uint4 *)in, (uint4 *)out, H, W, cin, stride, pad, OH, OW, Kp, pixels, c0); \
         else                                                                                                                     \
-            im2col_rows_kernel<KS_, CIN_><<<grid, 256, 0, st>>>((const uint4 *)in, (uint16_t *)out, B, H, W, cin, stride, pad, OH, OW, Kp); \
+            im2col_rows_kernel<KS_, CIN_><<<grid, 256, 0, st>>>((const uint4 *)in, (uint16_t *)out, B, H, W, cin, stride, pad, OH, OW, Kp, c0); \
     } while (0)
     if (ks == 7 && cin == 3) HAVC_IM2COL(7, 3);
+    else if (ks == 7 && cin == 2) HAVC_IM2COL(7, 2);
     else if (ks == 3 && cin == 3) HAVC_IM2COL(3, 3);
     else if (ks == 3 && cin == 1) HAVC_IM2COL(3, 1);
     else if (ks == 7) HAVC_IM2COL(7, 0);
@@ -344,16 +370,13 @@ extern "C" int havc_im2col_small(const void *in, void *out, int B, int H, int W,
     return HAVC_OK;
 }
 
-extern "C" int havc_maxpool3x3s2(const void *in, void *out, int B, int H, int W, int C, int dtype, void *stream) {
+extern "C" int havc_maxpool3x3s2(const void *in, const void *in_lo, void *out, void *out_lo, int B, int H, int W, int C, int dtype,
+                                 void *stream) {
     HAVC_CHECK_ARG(in && out && dt16(dtype) && C % 8 == 0, "havc_maxpool3x3s2: bad arguments");
     const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
     const long long n = (long long)B * OH * OW * (C / 8);
-    if (dtype == HAVC_F16)
-        maxpool_kernel<__half2><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const uint4 *)in, (uint4 *)out, B, H,
-                                                                                    W, C / 8, OH, OW);
-    else
-        maxpool_kernel<__nv_bfloat162><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
-            (const uint4 *)in, (uint4 *)out, B, H, W, C / 8, OH, OW);
+    maxpool_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const uint4 *)in, (const uint4 *)in_lo, (uint4 *)out,
+                                                                      (uint4 *)out_lo, B, H, W, C / 8, OH, OW, dtype);
     HAVC_LAUNCHED();
     return HAVC_OK;
 }
@@ -368,8 +391,8 @@ extern "C" int havc_phase_split(const void *in, void *out, int B, int H, int W, 
     return HAVC_OK;
 }
 
-extern "C" int havc_affine_act(const void *in, void *out, long long n_pixels, int C, int in_pix_stride,
-                               int out_pix_stride, const float *scale, const float *shift, int relu, int dtype,
+extern "C" int havc_affine_act(const void *in, const void *in_lo, void *out, void *out_lo, long long n_pixels, int C,
+                               int in_pix_stride, int out_pix_stride, const float *scale, const float *shift, int relu, int dtype,
                                void *stream) {
     HAVC_CHECK_ARG(in && out && scale && shift && dt16(dtype) && C % 8 == 0 && in_pix_stride % 8 == 0 &&
                        out_pix_stride % 8 == 0 && in_pix_stride >= C && out_pix_stride >= C &&
@@ -377,7 +400,8 @@ extern "C" int havc_affine_act(const void *in, void *out, long long n_pixels, in
                    "havc_affine_act: bad arguments (scale / shift hold C floats, 16-byte aligned)");
     const long long n = n_pixels * (C / 8);
     affine_act_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const uint4 *)in, (uint4 *)out, n_pixels, C / 8, in_pix_stride / 8, out_pix_stride / 8, scale, shift, relu, dtype);
+        (const uint4 *)in, (const uint4 *)in_lo, (uint4 *)out, (uint4 *)out_lo, n_pixels, C / 8, in_pix_stride / 8,
+        out_pix_stride / 8, scale, shift, relu, dtype);
     HAVC_LAUNCHED();
     return HAVC_OK;
 }

@@ -232,7 +232,7 @@ __global__ void pre_vertical_kernel(const float *__restrict__ in, uint8_t *__res
         float n[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) n[c] = __fdiv_rn(__fsub_rn(lf, mean[c]), stdv[c]);
-        uint4 pk = make_uint4(pack2(n[0], n[1], dtype), pack2(n[2], 0.f, dtype), 0u, 0u);
+        uint4 pk = make_uint4(pack2(n[0], n[1], dtype), pack2(n[2], 0.f, dtype), pack2((float)L, 1.f, dtype), 0u);   // ch 4,5: (L, 1) exact
         *reinterpret_cast<uint4 *>(reinterpret_cast<uint16_t *>(x) + i * 8) = pk;
     }
 }
@@ -272,7 +272,7 @@ __global__ void pre_vertical4_kernel(const float *__restrict__ in, uint8_t *__re
             float n[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) n[c] = __fdiv_rn(__fsub_rn(lf, mean[c]), stdv[c]);
-            xo[k] = make_uint4(pack2(n[0], n[1], dtype), pack2(n[2], 0.f, dtype), 0u, 0u);
+            xo[k] = make_uint4(pack2(n[0], n[1], dtype), pack2(n[2], 0.f, dtype), pack2((float)L, 1.f, dtype), 0u);
         }
     }
 }
@@ -290,7 +290,7 @@ __global__ void gray_normalize_kernel(const uint8_t *__restrict__ rgb, void *__r
         float v[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) v[c] = __fdiv_rn(__fsub_rn(lf, mean[c]), stdv[c]);
-        *reinterpret_cast<uint4 *>(reinterpret_cast<uint16_t *>(x) + i * 8) = make_uint4(pack2(v[0], v[1], dtype), pack2(v[2], 0.f, dtype), 0u, 0u);
+        *reinterpret_cast<uint4 *>(reinterpret_cast<uint16_t *>(x) + i * 8) = make_uint4(pack2(v[0], v[1], dtype), pack2(v[2], 0.f, dtype), pack2((float)L, 1.f, dtype), 0u);
     }
 }
 
@@ -488,10 +488,11 @@ __global__ void post_horizontal_kernel(const float *__restrict__ in, const uint8
 }
 
 // PIL.Image.blend(a, b, alpha) on u8 data: trunc(a + alpha*(b - a)) in float32 (Pillow's Blend.c), 16 bytes/thread.
-__global__ void blend_u8_kernel(const uint4 *__restrict__ a, const uint4 *__restrict__ b, uint4 *__restrict__ out,
-                                long long n16, float alpha) {
+// `out` may alias `a` or `b` (the engines blend in place): no __restrict__ / non-coherent loads; element i is read before it
+// is written and no other thread touches it.
+__global__ void blend_u8_kernel(const uint4 *a, const uint4 *b, uint4 *out, long long n16, float alpha) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x) {
-        const uint4 va = __ldg(a + i), vb = __ldg(b + i);
+        const uint4 va = a[i], vb = b[i];
         const uint32_t wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
         uint32_t wo[4];
 #pragma unroll
@@ -513,8 +514,7 @@ __global__ void blend_u8_kernel(const uint4 *__restrict__ a, const uint4 *__rest
 
 using namespace havc;
 
-__global__ void blend_u8_tail_kernel(const uint8_t *__restrict__ a, const uint8_t *__restrict__ b, uint8_t *__restrict__ out,
-                                     long long n, float alpha) {
+__global__ void blend_u8_tail_kernel(const uint8_t *a, const uint8_t *b, uint8_t *out, long long n, float alpha) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i < n) out[i] = (uint8_t)pil_blend(a[i], b[i], alpha);
 }
@@ -547,13 +547,14 @@ extern "C" int havc_resample_h(const uint8_t *in, float *out, long long rows, in
         const int block = ((Wout + 31) / 32) * 32;
         const size_t sm = 2 * (size_t)kR * (Win + kt) * sizeof(float);
         if (sm <= 200 * 1024 && kR * (Win / 4) <= 6 * block) {
-            static bool attr3 = false;
-            if (!attr3) {
+            static std::atomic<unsigned long long> attr3{0ull};
+            unsigned long long attr3_bit;
+            if (device_pending(attr3, &attr3_bit)) {
                 HAVC_CHECK_CUDA(cudaFuncSetAttribute(resample_h_rows_kernel<8, kR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
                 HAVC_CHECK_CUDA(cudaFuncSetAttribute(resample_h_rows_kernel<24, kR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
                 HAVC_CHECK_CUDA(cudaFuncSetAttribute(resample_h_rows_kernel<40, kR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
                 HAVC_CHECK_CUDA(cudaFuncSetAttribute(resample_h_rows_kernel<48, kR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                attr3 = true;
+                device_done(attr3, attr3_bit);
             }
             const long long groups = (rows + kR - 1) / kR;
             const int g3 = (int)(groups < (long long)num_sms() ? groups : (long long)num_sms());
@@ -567,13 +568,14 @@ extern "C" int havc_resample_h(const uint8_t *in, float *out, long long rows, in
         }
     }
     if (Wout <= 512 && taps <= 48 && (Win & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 3) == 0 && 2 * (Win + 48) * sizeof(float) <= 96 * 1024) {
-        static bool attr2 = false;
-        if (!attr2) {
+        static std::atomic<unsigned long long> attr2{0ull};
+        unsigned long long attr2_bit;
+        if (device_pending(attr2, &attr2_bit)) {
             HAVC_CHECK_CUDA(cudaFuncSetAttribute(resample_h_regw_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
             HAVC_CHECK_CUDA(cudaFuncSetAttribute(resample_h_regw_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
             HAVC_CHECK_CUDA(cudaFuncSetAttribute(resample_h_regw_kernel<40>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
             HAVC_CHECK_CUDA(cudaFuncSetAttribute(resample_h_regw_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-            attr2 = true;
+            device_done(attr2, attr2_bit);
         }
         const int block = ((Wout + 31) / 32) * 32;
         long long g2 = rows < (long long)num_sms() * 4 ? rows : (long long)num_sms() * 4;
@@ -587,10 +589,11 @@ extern "C" int havc_resample_h(const uint8_t *in, float *out, long long rows, in
         HAVC_LAUNCHED();
         return HAVC_OK;
     }
-    static bool attr = false;
-    if (!attr) {
+    static std::atomic<unsigned long long> attr{0ull};
+    unsigned long long attr_bit;
+    if (device_pending(attr, &attr_bit)) {
         HAVC_CHECK_CUDA(cudaFuncSetAttribute(resample_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        attr = true;
+        device_done(attr, attr_bit);
     }
     long long g = rows < (long long)num_sms() * 16 ? rows : (long long)num_sms() * 16;
     resample_h_kernel<<<(int)g, 128, Win * sizeof(float), (cudaStream_t)stream>>>(in, out, rows, Win, Wout, start, weights,

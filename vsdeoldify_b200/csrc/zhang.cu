@@ -226,14 +226,15 @@ extern "C" int havc_zhang_post(const float *ab, int h, int w, const float *L, ui
     HAVC_CHECK_ARG(ab && L && out && B > 0 && h > 0 && w > 0 && H > 0 && W > 0, "havc_zhang_post: bad arguments");
     // inverse of skimage's xyz_from_rgb, computed once in double (Gauss-Jordan on the 3x3)
     static XyzToRgb M;
-    static bool have = false;
-    if (!have) {
+    static std::atomic<unsigned long long> have{0ull};
+    unsigned long long have_bit;
+    if (device_pending(have, &have_bit)) {
         const double a[9] = {0.412453, 0.357580, 0.180423, 0.212671, 0.715160, 0.072169, 0.019334, 0.119193, 0.950227};
         const double det = a[0] * (a[4] * a[8] - a[5] * a[7]) - a[1] * (a[3] * a[8] - a[5] * a[6]) + a[2] * (a[3] * a[7] - a[4] * a[6]);
         M.m[0] = (a[4] * a[8] - a[5] * a[7]) / det; M.m[1] = (a[2] * a[7] - a[1] * a[8]) / det; M.m[2] = (a[1] * a[5] - a[2] * a[4]) / det;
         M.m[3] = (a[5] * a[6] - a[3] * a[8]) / det; M.m[4] = (a[0] * a[8] - a[2] * a[6]) / det; M.m[5] = (a[2] * a[3] - a[0] * a[5]) / det;
         M.m[6] = (a[3] * a[7] - a[4] * a[6]) / det; M.m[7] = (a[1] * a[6] - a[0] * a[7]) / det; M.m[8] = (a[0] * a[4] - a[1] * a[3]) / det;
-        have = true;
+        device_done(have, have_bit);
     }
     zhang_post_kernel<<<grid_for((long long)B * H * W), 256, 0, (cudaStream_t)stream>>>((const float2 *)ab, h, w, L, out, B, H, W, M);
     HAVC_LAUNCHED();

@@ -38,7 +38,8 @@ class DeoldifyEngine:
                  use_graph: bool = True, keep_taps: bool = False, debug_net_out: bool = False,
                  frame_size: Optional[int] = None, sd_other: Optional[Dict[str, torch.Tensor]] = None,
                  video_weight: float = 0.5, zhang: Optional[tuple] = None, merge: Optional[dict] = None,
-                 hue_adjust: str = "none", run_deoldify: bool = True, ddtweak: Optional[dict] = None):
+                 hue_adjust: str = "none", run_deoldify: bool = True, ddtweak: Optional[dict] = None,
+                 precision: Optional[str] = None):
         """zhang = (name, state_dict): the second colour model of HAVC_colorizer (vs_sc_ddcolor models 2 / 3,
         vsslib/vsmodels.py:339-344), colourising the same S x S frame; hue_adjust: its vs_sc_adjust_clip_hue string
         (vsmodels.py:361-362); merge = dict(method, weight, cmc_p, lmm_p, alm_p, crt_p, invert) for
@@ -50,16 +51,20 @@ class DeoldifyEngine:
         self.dev = torch.device(device)
         torch.cuda.set_device(self.dev)
         self.W, self.H, self.B = width, height, batch
-        # frame_size, vsdeoldify/__init__.py:2502; when it exceeds render_factor*16 (a bigger ddcolor_rf) the
-        # reference squeezes twice (Spline64 then Pillow BILINEAR inside the filter) - not built, so reject it
+        # frame_size (vsdeoldify/__init__.py:2502) = min(max(ddcolor_rf, deoldify_rf)*16, width): the Spline64 squeeze size F.  The
+        # DeOldify filter itself always renders at N = render_factor*16 (BaseFilter._scale_to_square, deoldify/filters.py:37-41,82-84):
+        # when F != N it stretches the F x F frame to N x N with Pillow BILINEAR, runs the generator, resizes the result back to
+        # F x F (_unsquare, filters.py:70-73) and only then transplants the luma (filters.py:100-110).  Same passes here.
         self.S = min(render_factor * 16, width) if frame_size is None else frame_size
-        if self.S != min(render_factor * 16, width):
-            raise ValueError("frame_size != render_factor*16 (ddcolor_rf > deoldify_rf) is not supported yet")
+        self.N = render_factor * 16 if run_deoldify else self.S                # network size
+        if self.S > width or self.S < 16:
+            raise ValueError(f"frame_size {self.S} must lie in [16, clip width {width}]")
         S, B, W, H = self.S, batch, width, height
+        N = self.N
         self.dtype, self.hd = dtype, ops.havc_dtype(dtype)
         self.run_deoldify = run_deoldify
-        self.prog = UnetProgram(sd, B, S, dtype, device=self.dev, keep_taps=keep_taps) if run_deoldify else None
-        self.prog2 = UnetProgram(sd_other, B, S, dtype, device=self.dev, x=self.prog.x) \
+        self.prog = UnetProgram(sd, B, N, dtype, device=self.dev, keep_taps=keep_taps, precision=precision) if run_deoldify else None
+        self.prog2 = UnetProgram(sd_other, B, N, dtype, device=self.dev, x=self.prog.x, precision=precision) \
             if (sd_other is not None and run_deoldify) else None
         self.zhang = None
         self.merge, self.hue_adjust, self.ddtweak = merge, hue_adjust, ddtweak
@@ -90,8 +95,18 @@ class DeoldifyEngine:
         self.colored = torch.empty(B, 3, S, S, **u8)
         self.colored2 = torch.empty(B, 3, S, S, **u8) if sd_other is not None else None
         self.tmp_up = torch.empty(B, 3, H, S, **f32)
-        self.net_out = torch.empty(B, 3, S, S, **f32) if debug_net_out else None
-        self.x_in = self.prog.x if self.prog is not None else torch.zeros(B, S, S, 8, dtype=dtype, device=self.dev)
+        self.net_out = torch.empty(B, 3, N, N, **f32) if debug_net_out else None
+        self.rescale = self.prog is not None and N != S
+        if self.rescale:        # Pillow BILINEAR tables F -> N and N -> F, u8 staging images
+            mk = lambda a, b: tuple(torch.from_numpy(t).to(self.dev) for t in resample.pil_tables(a, b, "bilinear"))
+            self.t_sq, self.t_unsq = mk(S, N), mk(N, S)
+            self.sq_h = torch.empty(B, 3, S, N, **u8)        # after the horizontal pass of the stretch
+            self.sq = torch.empty(B, 3, N, N, **u8)
+            self.model_img = torch.empty(B, 3, N, N, **u8)
+            self.unsq_h = torch.empty(B, 3, N, S, **u8)      # after the horizontal pass back
+            self.raw = torch.empty(B, 3, S, S, **u8)
+        self.x_in = self.prog.x if (self.prog is not None and not self.rescale) else \
+            torch.zeros(B, S, S, 8, dtype=dtype, device=self.dev)
         # per-frame scene-change gate (1 = leave uncoloured): one device / pinned pair per input slot, so that two batches
         # can be in flight (the launch list of slot s reads skip_slots[s])
         self.skip_slots = [torch.zeros(B, **u8) for _ in range(self.n_slots)]
@@ -116,17 +131,23 @@ class DeoldifyEngine:
         chk(lib.havc_pre_vertical(self.tmp_down.data_ptr(), self.rgb_small.data_ptr(), self.x_in.data_ptr(), B, H, S,
                                   tv.start.data_ptr(), tv.w.data_ptr(), tv.taps, self.hd, stream), "pre.v")
         result = self.colored
-        if self.run_deoldify:
+        if self.run_deoldify and not self.rescale:
             self.prog.run(stream)
             chk(lib.havc_head(self.prog.logits.data_ptr(), 0, None,
                               self.prog.b11.data_ptr(), self.rgb_small.data_ptr(), self.colored.data_ptr(),
                               self.net_out.data_ptr() if self.net_out is not None else None, skip.data_ptr(), B, S,
                               self.hd, 1, stream),
                 "head")
+        elif self.run_deoldify:
+            self._stretch_in(stream)
+            self._filter_rescaled(self.prog, self.colored, self.net_out, skip, stream)
         if self.prog2 is not None:
-            self.prog2.run(stream)
-            chk(lib.havc_head(self.prog2.logits.data_ptr(), 0, None, self.prog2.b11.data_ptr(), self.rgb_small.data_ptr(),
-                              self.colored2.data_ptr(), None, skip.data_ptr(), B, S, self.hd, 1, stream), "head2")
+            if not self.rescale:
+                self.prog2.run(stream)
+                chk(lib.havc_head(self.prog2.logits.data_ptr(), 0, None, self.prog2.b11.data_ptr(), self.rgb_small.data_ptr(),
+                                  self.colored2.data_ptr(), None, skip.data_ptr(), B, S, self.hd, 1, stream), "head2")
+            else:
+                self._filter_rescaled(self.prog2, self.colored2, None, skip, stream)
             chk(lib.havc_blend_u8(self.colored2.data_ptr(), self.colored.data_ptr(), self.colored.data_ptr(),
                                   B * 3 * S * S, self.video_weight, stream), "blend")
         if self.zhang is not None:
@@ -165,6 +186,34 @@ class DeoldifyEngine:
                                 uv.start.data_ptr(), uv.w.data_ptr(), uv.taps, stream), "post.v")
         chk(lib.havc_post_horizontal(self.tmp_up.data_ptr(), self.d_in[slot].data_ptr(), self.d_out[slot].data_ptr(), B, S,
                                      H, W, uh.start.data_ptr(), uh.wt.data_ptr(), uh.taps, 1, stream), "post.h")
+
+    # ---- frame_size != render_factor*16: the filter's own Pillow BILINEAR stretch around the generator ---------------
+    def _pil(self, src, tmp, dst, Hin, Win, out_size, tabs, stream):
+        """Pillow Image.resize of square u8 planes: horizontal pass, u8 intermediate, vertical pass (ImagingResample)."""
+        lib, B, chk = self.lib, self.B, _lib.check
+        chk(lib.havc_pil_resample_u8(src.data_ptr(), tmp.data_ptr(), B * 3, Hin, Win, out_size, 1, tabs[0].data_ptr(),
+                                     tabs[1].data_ptr(), tabs[1].shape[1], stream), "pil.h")
+        chk(lib.havc_pil_resample_u8(tmp.data_ptr(), dst.data_ptr(), B * 3, Hin, out_size, out_size, 0, tabs[0].data_ptr(),
+                                     tabs[1].data_ptr(), tabs[1].shape[1], stream), "pil.v")
+
+    def _stretch_in(self, stream):
+        """_scale_to_square (filters.py:37-41) + _transform + normalise: rgb_small [F x F] -> x [N x N]."""
+        S, N = self.S, self.N
+        self._pil(self.rgb_small, self.sq_h, self.sq, S, S, N, self.t_sq, stream)
+        _lib.check(self.lib.havc_gray_normalize(self.sq.data_ptr(), self.prog.x.data_ptr(), self.B, N * N, self.hd, stream),
+                   "gray_normalize")
+
+    def _filter_rescaled(self, prog, colored, net_out, skip, stream):
+        """generator at N x N -> u8 image -> _unsquare to F x F (filters.py:70-73) -> _post_process against rgb_small
+        (filters.py:100-110); scene-change-skipped frames come back as rgb_small (vsslib/vsmodels.py:221-224)."""
+        lib, B, S, N, chk = self.lib, self.B, self.S, self.N, _lib.check
+        prog.run(stream)
+        chk(lib.havc_head(prog.logits.data_ptr(), 0, None, prog.b11.data_ptr(), None, self.model_img.data_ptr(),
+                          net_out.data_ptr() if net_out is not None else None, None, B, N, self.hd, 0, stream), "head")
+        self._pil(self.model_img, self.unsq_h, self.raw, N, N, S, self.t_unsq, stream)
+        chk(lib.havc_chroma_post_process(self.raw.data_ptr(), self.rgb_small.data_ptr(), colored.data_ptr(), B, S, S, stream),
+            "post_process")
+        chk(lib.havc_select_frames(colored.data_ptr(), self.rgb_small.data_ptr(), skip.data_ptr(), B, 3 * S * S, stream), "skip")
 
     def _warm(self):
         with torch.cuda.stream(self.compute):
@@ -283,7 +332,8 @@ class DeoldifyEngine:
     def colorize_stream(self, batches, on_result):
         """batches: iterable of uint8 [B,3,H,W] host arrays or (pinned) torch tensors (a full batch each); pinned tensors
         are copied to the device directly and must stay untouched until their result is delivered; on_result(i, out) is called
-        in order with a view of the pinned output buffer (valid until the next-but-one call).
+        in order with a view of the pinned output buffer that is valid ONLY during the callback (the download of a later batch
+        reuses the slot as soon as the callback returns: copy what you keep).
         H2D of batch i+1 and D2H of batch i-1 overlap the compute of batch i."""
         ev_in = [torch.cuda.Event() for _ in range(self.n_slots)]
         ev_done = [torch.cuda.Event() for _ in range(self.n_slots)]
@@ -334,15 +384,15 @@ class ImageRenderEngine:
 
     def __init__(self, sd: Dict[str, torch.Tensor], width: int, height: int, render_factor: int = 24, batch: int = 1,
                  dtype: torch.dtype = torch.float16, device: str = "cuda:0", sd_other: Optional[Dict[str, torch.Tensor]] = None,
-                 video_weight: float = 0.5):
+                 video_weight: float = 0.5, precision: Optional[str] = None):
         self.lib = _lib.lib()
         self.dev = torch.device(device)
         torch.cuda.set_device(self.dev)
         self.W, self.H, self.B, self.S = width, height, batch, render_factor * 16
         S, B, W, H = self.S, batch, width, height
         self.hd = ops.havc_dtype(dtype)
-        self.prog = UnetProgram(sd, B, S, dtype, device=self.dev)
-        self.prog2 = UnetProgram(sd_other, B, S, dtype, device=self.dev, x=self.prog.x) if sd_other is not None else None
+        self.prog = UnetProgram(sd, B, S, dtype, device=self.dev, precision=precision)
+        self.prog2 = UnetProgram(sd_other, B, S, dtype, device=self.dev, x=self.prog.x, precision=precision) if sd_other is not None else None
         self.video_weight = float(video_weight)
         mk = lambda a, b: tuple(torch.from_numpy(t).to(self.dev) for t in resample.pil_tables(a, b, "bilinear"))
         self.t_dw, self.t_dh = (mk(W, S) if W != S else None), (mk(H, S) if H != S else None)      # squeeze

@@ -41,7 +41,9 @@ _WEIGHT_FILES = {0: "ColorizeVideo_gen", 1: "ColorizeStable_gen", 2: "ColorizeAr
 # <torch_dir>/checkpoints like model_zoo.load_url does after torch.hub.set_dir(torch_dir) (vsdeoldify/__init__.py:2489-2490)
 _ZHANG_FILES = {"siggraph17": "siggraph17-df00044c", "eccv16": "colorization_release_v2-9b330a0b"}
 _REGISTERED: Dict[str, Dict[str, torch.Tensor]] = {}
-_BATCH = int(os.environ.get("HAVC_B200_BATCH", "8"))
+# frames per engine step (one CUDA-graph launch): the benched operating point (bench.py: B = 32 fills the 148 SMs on the 12 x 12 /
+# 24 x 24 layers; 32 frames = 16 GB of activations of the 180 GB).  HAVC_B200_BATCH overrides it.
+_BATCH = int(os.environ.get("HAVC_B200_BATCH", "32"))
 _DTYPE = {"fp16": torch.float16, "bf16": torch.bfloat16}[os.environ.get("HAVC_B200_DTYPE", "fp16")]
 
 
@@ -100,14 +102,23 @@ class _ColorizedClip:
     def _planes(self, f) -> np.ndarray:
         return np.stack([np.asarray(f[p]) for p in range(3)])
 
+    def _skip(self, n: int, srcs):
+        """vsslib/vsmodels.py:221-224: with scene-change gating only frames with _SceneChangePrev == 1 (and frame 0) are
+        colourised.  The reference runs SceneDetect itself (vsdeoldify/__init__.py:2496-2499), so the prop always exists there;
+        a frame without it is an error here (scene detection is outside this build), never a silently uncoloured frame."""
+        if not self.scenechange:
+            return None
+        from .sharded import scene_skip_flags
+        try:
+            return scene_skip_flags(n, srcs)
+        except KeyError as e:
+            _raise("HAVC_colorizer: " + str(e.args[0]))
+
     def _fetch(self, n: int):
         n1 = min(n + self.B, self.clip.num_frames)
         srcs = [self.clip.get_frame(i) for i in range(n, n1)]
         batch = np.stack([self._planes(f) for f in srcs])
-        skip = None
-        if self.scenechange:    # vsslib/vsmodels.py:221-224: only scene-change frames are colourised
-            skip = np.array([not (i == 0 or f.props.get("_SceneChangePrev", 0) == 1) for i, f in zip(range(n, n1), srcs)])
-        return srcs, batch, skip
+        return srcs, batch, self._skip(n, srcs)
 
     def _store(self, n: int, srcs, out):
         for i, f in zip(range(n, n + len(srcs)), srcs):
@@ -131,10 +142,7 @@ class _ColorizedClip:
             for p in range(3):
                 np.copyto(buf[j, p], np.asarray(srcs[j][p]))
         list(_COPY_POOL.map(put, range(len(srcs))))
-        skip = None
-        if self.scenechange:    # vsslib/vsmodels.py:221-224: only scene-change frames are colourised
-            skip = np.array([not (i == 0 or f.props.get("_SceneChangePrev", 0) == 1) for i, f in zip(range(n, n1), srcs)])
-        return (n, srcs, self.engine.submit(None, skip=skip, n=len(srcs)))
+        return (n, srcs, self.engine.submit(None, skip=self._skip(n, srcs), n=len(srcs)))
 
     def _result_buf(self) -> np.ndarray:
         """A result array nobody references any more (the frames we hand out are views of these arrays and keep them alive
@@ -182,7 +190,7 @@ def HAVC_colorizer(
         sc_tht_white: float = DEF_THT_WHITE, sc_tht_black: float = DEF_THT_BLACK, device_index: int = 0,
         torch_dir: str = model_dir, debug_level: int = 0):
     """Drop-in for vsdeoldify.HAVC_colorizer (vsdeoldify/__init__.py:2290-2523) on the DeOldify path."""
-    if device_index == 99:
+    if device_index == 99 or (isinstance(device_index, (list, tuple)) and 99 in device_index):
         _raise("HAVC_colorizer: CPU mode (device_index=99) is not available in the B200 build (no CPU fallback)")
     if not torch.cuda.is_available():
         _raise("HAVC_colorizer: CUDA is not available")                                   # :2441
@@ -199,8 +207,16 @@ def HAVC_colorizer(
         method = 1
     deoldify_model, deoldify_rf, deoldify_sat, deoldify_hue = deoldify_p[:4]
     ddcolor_model, ddcolor_rf = ddcolor_p[0], ddcolor_p[1]
-    if device_index > 7:
+    # device_index: the reference takes ONE device (GPU0...GPU7, deoldify/device_id.py:3-12).  Extension of the B200 build: a
+    # list / tuple of device indices (or HAVC_B200_DEVICES="0,1,..." with the default device_index) renders the clip on
+    # several GPUs of the box, frames partitioned over them and returned in order (vsdeoldify_b200/sharded.py).
+    devices = list(device_index) if isinstance(device_index, (list, tuple)) else [device_index]
+    if len(devices) == 1 and devices[0] == 0 and os.environ.get("HAVC_B200_DEVICES"):
+        devices = [int(t) for t in os.environ["HAVC_B200_DEVICES"].split(",") if t.strip() != ""]
+    if not devices or any((not isinstance(d, int)) or d > 7 or d < 0 for d in devices) or len(set(devices)) != len(devices):
         _raise("HAVC_colorizer: wrong device_index, choices are: GPU0...GPU7, CPU=99")    # :2480
+    if max(devices) >= torch.cuda.device_count():
+        _raise(f"HAVC_colorizer: device_index {max(devices)} but only {torch.cuda.device_count()} CUDA device(s) are visible")
     if ddcolor_rf != 0 and ddcolor_rf not in range(10, 65):
         _raise("HAVC_colorizer: ddcolor render_factor must be between: 10-64")            # :2483
     ddcolor_sat = ddcolor_p[2] if len(ddcolor_p) > 2 else 1.0
@@ -237,7 +253,6 @@ def HAVC_colorizer(
     # frame_size: HAVC_colorizer:2502 uses max(ddcolor_rf, deoldify_rf) even when method == 0
     frame_size = min(max(ddcolor_rf, deoldify_rf) * 16, clip.width)
     from .engine import DeoldifyEngine
-    dev = f"cuda:{device_index}"
     mdir = torch_dir or model_dir
     run_deoldify = method != 1                                            # vs_sc_deoldify returns None for method 1 (vsmodels.py:198)
     sd_video = load_state_dict(_WEIGHT_FILES[0], mdir) if run_deoldify else None   # the video generator always runs (visualize.py:120)
@@ -251,12 +266,24 @@ def HAVC_colorizer(
                      crt_p=list(crt_p), invert=bool(cmb_sw))
     from .filters import FilterError
     try:
-        engine = DeoldifyEngine(sd_video, clip.width, clip.height, render_factor=deoldify_rf, frame_size=frame_size,
-                                batch=_BATCH, dtype=_DTYPE, device=dev, sd_other=sd_other, video_weight=weight, zhang=zhang,
-                                merge=merge, hue_adjust=hue_adjust, run_deoldify=run_deoldify, ddtweak=tweak)
+        engines = [DeoldifyEngine(sd_video, clip.width, clip.height, render_factor=deoldify_rf, frame_size=frame_size,
+                                  batch=_BATCH, dtype=_DTYPE, device=f"cuda:{d}", sd_other=sd_other, video_weight=weight,
+                                  zhang=zhang, merge=merge, hue_adjust=hue_adjust, run_deoldify=run_deoldify, ddtweak=tweak)
+                   for d in devices]
     except (ValueError, FilterError) as e:
         _raise("HAVC_colorizer: " + str(e))
-    fn = _ColorizedClip(clip, engine, scenechange, _BATCH)
+    if len(engines) == 1:
+        fn = _ColorizedClip(clip, engines[0], scenechange, _BATCH)
+    else:
+        from .sharded import ShardedRenderer
+        renderer = ShardedRenderer(clip, engines, _BATCH, scenechange, partition=os.environ.get("HAVC_B200_PARTITION", "interleaved"),
+                                   copy_pool=_COPY_POOL)
+
+        def fn(n, renderer=renderer):
+            try:
+                return renderer(n)
+            except KeyError as e:                    # a frame without the scene-detection prop
+                _raise("HAVC_colorizer: " + str(e.args[0]))
     return vs_shim.VideoNode(clip.num_frames, clip.width, clip.height, clip.format, fn, clip.fps_num, clip.fps_den) \
         if vs is vs_shim else _wrap_real_vs(clip, fn)
 

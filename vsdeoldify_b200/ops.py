@@ -95,6 +95,51 @@ def chan_storage(c: int) -> int:
     return pad_to(c, 64) if c > 64 else pad_to(c, 8)
 
 
+class Pair:
+    """A split-precision ("x3") tensor: value = hi + lo, two 16-bit planes of one allocation `t` = [2, ...] (plane 0 = the value
+    rounded to 16 bit, plane 1 = the rounded remainder).  havc_conv_gemm multiplies such operands as hi*hi + lo*hi + hi*lo."""
+
+    def __init__(self, t: torch.Tensor):
+        assert t.shape[0] == 2
+        self.t, self.hi, self.lo = t, t[0], t[1]
+
+    @property
+    def shape(self):
+        return self.hi.shape
+
+    @property
+    def dtype(self):
+        return self.hi.dtype
+
+    def dim(self):
+        return self.hi.dim()
+
+    def float(self) -> torch.Tensor:
+        return self.hi.float() + self.lo.float()
+
+    def view(self, *shape) -> "Pair":
+        return Pair(self.t.view(2, *shape))
+
+    def sub(self, index) -> "Pair":
+        """Pair of a slice of the leading (non-plane) dimension, e.g. one phase of a phase-split tensor."""
+        return Pair(self.t[:, index])
+
+
+def hi_of(t):
+    return t.hi if isinstance(t, Pair) else t
+
+
+def lo_of(t):
+    return t.lo if isinstance(t, Pair) else None
+
+
+def split_hi_lo(w: torch.Tensor, dtype) -> Tuple[torch.Tensor, torch.Tensor]:
+    """fp32 tensor -> (hi, lo) 16-bit tensors with hi + lo ~= w to ~2^-22 relative."""
+    hi = w.to(dtype)
+    lo = (w - hi.float()).to(dtype)
+    return hi, lo
+
+
 def pack_conv_weight(w: torch.Tensor, cin_splits: Optional[Sequence[int]] = None, dtype=torch.float16,
                      shuffle: bool = False, row_pad: int = 16,
                      cin_storage: Optional[Sequence[int]] = None) -> Tuple[torch.Tensor, dict]:
@@ -140,6 +185,8 @@ def pack_conv_weight(w: torch.Tensor, cin_splits: Optional[Sequence[int]] = None
         if rp != Cout:
             wk = torch.cat([wk, wk.new_zeros(rp - Cout, kh * kw, cin_storage)], 0)
         meta.update(rows=rp)
+    if dtype is None:        # keep fp32: the caller splits it into hi / lo planes
+        return wk.float().contiguous(), meta
     return wk.to(dtype).contiguous(), meta
 
 
@@ -158,15 +205,15 @@ def pack_cols(v: Optional[torch.Tensor], n_alloc: int, fill: float, shuffle_meta
     return out
 
 
-def choose_bn(n_total: int, m_tiles: int, sms: int = 148, ksteps: int = 36) -> int:
+def choose_bn(n_total: int, m_tiles: int, sms: int = 148, ksteps: int = 36, max_bn: int = 256) -> int:
     """N tile (UMMA N: multiple of 16, <= 256; 272..320 = 256 + rest for the res_block tail) from a small cost
     model fitted to measurements on B200: a tile costs ksteps * t_k(BN) + a fixed prologue/epilogue share, the
     launch costs ceil(tiles / SMs) waves of that.  Wide tiles re-read the activations least; narrow tiles fill the
     machine when the layer has few pixels."""
-    if 256 < n_total <= 320:
+    if 256 < n_total <= 320 and max_bn >= 256:
         return n_total
-    cands = [bn for bn in range(256, 63, -16) if n_total % bn == 0] or [min(n_total, 256)]
-    if n_total <= 256 and n_total not in cands:
+    cands = [bn for bn in range(max_bn, 63, -16) if n_total % bn == 0] or [min(n_total, max_bn)]
+    if n_total <= max_bn and n_total not in cands:
         cands = [n_total] + cands
     best, best_cost = cands[0], None
     for bn in cands:
@@ -200,7 +247,9 @@ def make_conv(src0: torch.Tensor, weight: torch.Tensor, out: torch.Tensor, taps,
               src1_single_tap: bool = False, src1_wi: int = 0, split_n: int = 0, out2: Optional[torch.Tensor] = None,
               c_store2: int = 0, residual2: Optional[torch.Tensor] = None, head_w: Optional[torch.Tensor] = None,
               head_out: Optional[torch.Tensor] = None, tma_store: Optional[bool] = None, leaky1: float = 0.0,
-              pair: int = 0, name: str = "") -> ConvOp:
+              pair: int = 0, name: str = "", src0_lo: Optional[torch.Tensor] = None, src1_lo: Optional[torch.Tensor] = None,
+              weight_lo: Optional[torch.Tensor] = None, out_lo: Optional[torch.Tensor] = None,
+              residual_lo: Optional[torch.Tensor] = None) -> ConvOp:
     """src0/src1: NHWC (or [P,B,H,W,C]) 16-bit device tensors; weight: packed [rows,taps,cin] or
     [batches,rows,taps,cin]; out: NHWC tensor written at pixel (h*up+oy, w*up+ox)."""
     d = ConvDesc()
@@ -233,7 +282,7 @@ def make_conv(src0: torch.Tensor, weight: torch.Tensor, out: torch.Tensor, taps,
     d.N_total = n_total if n_total is not None else rows
     m_tiles = -(-W // box[0]) * -(-H // box[1]) * -(-B // box[2])
     ksteps = len(taps) * (-(-d.src0.C // 64) + (-(-d.src1.C // 64) if src1 is not None and not src1_single_tap else 0))
-    d.BN = bn if bn is not None else choose_bn(d.N_total, m_tiles, ksteps=ksteps)
+    d.BN = bn if bn is not None else choose_bn(d.N_total, m_tiles, ksteps=ksteps, max_bn=128 if out_lo is not None else 256)
     n_alloc = -(-d.N_total // d.BN) * d.BN
     keep = [src0, src1, weight, out, residual]
     for nm, v in (("bias", bias), ("scale", scale), ("shift", shift)):
@@ -275,5 +324,11 @@ def make_conv(src0: torch.Tensor, weight: torch.Tensor, out: torch.Tensor, taps,
         d.head_stride_b, d.head_stride_h, d.head_stride_w = head_out.stride()[:3]
     d.tma_store = int(TMA_STORE_DEFAULT if tma_store is None else tma_store)
     d.pair = int(pair)     # 0 = library default (CTA pairs on), 1 = force, -1 = single-CTA tiles
-    keep += [out2, residual2, head_w, head_out]
+    # split-precision planes: same geometry as their hi tensors
+    for nm, lo, hi in (("src0_lo", src0_lo, src0), ("src1_lo", src1_lo, src1), ("weight_lo", weight_lo, weight),
+                       ("out_lo", out_lo, out), ("residual_lo", residual_lo, residual)):
+        if lo is not None:
+            assert hi is not None and lo.shape == hi.shape and lo.stride() == hi.stride() and lo.dtype == hi.dtype, nm
+            setattr(d, nm, lo.data_ptr())
+    keep += [out2, residual2, head_w, head_out, src0_lo, src1_lo, weight_lo, out_lo, residual_lo]
     return ConvOp(d, keep, name=name)

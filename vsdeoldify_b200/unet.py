@@ -25,8 +25,17 @@ from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
 
+import math
+import os
+
 from . import _lib, ops
-from .ops import chan_storage, pad_to
+from .ops import Pair, chan_storage, hi_of, lo_of, pad_to
+
+# Operand precision policy (DESIGN.md "Precision"; tools/precision_emulator.py is the error budget it follows):
+#   fast     - every contraction takes 16-bit operands once (one MMA per K step)
+#   balanced - the ResNet encoder, where 16-bit storage injects ~95 % of the logit error for ~7 % of the FLOPs, runs
+#              split-precision (value = hi + lo; hi*hi + lo*hi + hi*lo), the decoder as in `fast`   [default]
+PRECISION = os.environ.get("HAVC_B200_PRECISION", "balanced")
 
 SD = Dict[str, torch.Tensor]
 BN_EPS = 1e-5
@@ -77,8 +86,12 @@ class LaunchProgram:
     the op emitters shared by the DeOldify U-Nets (below) and the Zhang colorizers (zhang.py)."""
 
     def __init__(self, sd: SD, batch: int, size: int, dtype: torch.dtype = torch.float16, device="cuda",
-                 keep_taps: bool = False):
+                 keep_taps: bool = False, precision: Optional[str] = None):
         self.sd, self.B, self.S, self.dtype, self.dev = sd, batch, size, dtype, torch.device(device)
+        self.precision = precision or PRECISION
+        if self.precision not in ("fast", "balanced"):
+            raise ValueError(f"unknown precision policy {self.precision!r} (fast | balanced)")
+        self.enc_x3 = self.precision != "fast"
         self.hd = ops.havc_dtype(dtype)
         self.lib = _lib.lib()
         self.ops: List[Op] = []
@@ -107,34 +120,56 @@ class LaunchProgram:
     def conv(self, name: str, src0, w: torch.Tensor, *, ks=1, src1=None, cin_splits=None, stride=1, bias=None,
              relu1=False, scale=None, shift=None, residual=None, relu2=False, shuffle=False, out=None,
              out_c: Optional[int] = None, dilation: int = 1, leaky1: float = 0.0, out_dtype=None, taps=None,
-             phase=None, flops: Optional[float] = None, head_w=None, head_out=None) -> torch.Tensor:
+             phase=None, flops: Optional[float] = None, head_w=None, head_out=None, x3: bool = False):
         """w: folded fp32 [Cout, Cin, ks, ks].  Returns the NHWC output tensor.
         taps: explicit (dh, dw, phase, weight tap) list (transposed convolutions); phase = (up, oy, ox): the output
-        pixel of (h, w) is (h*up+oy, w*up+ox) of `out`."""
+        pixel of (h, w) is (h*up+oy, w*up+ox) of `out`.
+        x3: split-precision launch - the weight is packed as hi + lo planes, sources / residual that are `Pair`s contribute
+        their lo planes, and the result is a `Pair`.  The weight is pre-scaled by a power of two (undone by the epilogue's
+        scale) so that its lo plane stays in fp16's normal range.  A launch without x3 reads only the hi plane of a Pair."""
         Cout, Cin = w.shape[0], w.shape[1]
-        storage = [src0.shape[-1]] + ([src1.shape[-1]] if src1 is not None else [])
-        wp, meta = ops.pack_conv_weight(w, cin_splits, dtype=self.dtype, shuffle=shuffle, cin_storage=storage)
+        h0, h1 = hi_of(src0), hi_of(src1) if src1 is not None else None
+        storage = [h0.shape[-1]] + ([h1.shape[-1]] if h1 is not None else [])
+        wl = None
+        if x3:
+            assert not shuffle and head_w is None and out is None
+            k = max(-8, min(14, int(math.floor(math.log2(16384.0 / max(float(w.abs().max()), 1e-30))))))
+            g = 2.0 ** k
+            w32, meta = ops.pack_conv_weight(w.double() * g, cin_splits, dtype=None, shuffle=False, cin_storage=storage)
+            wp, wl = ops.split_hi_lo(w32, self.dtype)
+            wl = wl.to(self.dev)
+            self.keep.append(wl)
+            bias = None if bias is None else bias * g                      # (acc*g + bias*g) -> act -> * (scale/g) + shift
+            scale = (torch.ones(Cout) if scale is None else scale.float().cpu()) / g
+            shift = torch.zeros(Cout) if shift is None else shift
+        else:
+            wp, meta = ops.pack_conv_weight(w, cin_splits, dtype=self.dtype, shuffle=shuffle, cin_storage=storage)
         wp = wp.to(self.dev)
         self.keep.append(wp)
         n_total = meta["rows"]
         pc = lambda v, fill: None if v is None else self.dev_f32(ops.pack_cols(v, n_total, fill, meta if shuffle else None))
         if stride == 1:
-            B, H, W = src0.shape[0], src0.shape[1], src0.shape[2]
+            B, H, W = h0.shape[0], h0.shape[1], h0.shape[2]
             if taps is None:
                 taps = ops.taps_for(ks, dilation)
         else:  # src0 is phase-split [P,B,H/2,W/2,C]
-            B, H, W = src0.shape[1], src0.shape[2], src0.shape[3]
+            B, H, W = h0.shape[1], h0.shape[2], h0.shape[3]
             taps = ops.taps_stride2(ks) if ks > 1 else [(0, 0, 0, 0)]
         c_real = meta["cg"] if shuffle else (out_c or Cout)
         up, oy, ox = phase if phase is not None else (1, 0, 0)
         if out is None and head_w is None:     # zero-initialised: the pad channels beyond c_store are never written and stay zero
-            out = self.buf(B, 2 * H, 2 * W, chan_storage(c_real), zero=True) if shuffle else \
-                self.buf(B, up * H, up * W, chan_storage(c_real), zero=True, dtype=out_dtype)
-        op = ops.make_conv(src0, wp, out, taps, src1=src1, w_c1_off=meta["c1_off"], n_total=n_total,
+            if x3:
+                out = Pair(self.buf(2, B, up * H, up * W, chan_storage(c_real), zero=True))
+            else:
+                out = self.buf(B, 2 * H, 2 * W, chan_storage(c_real), zero=True) if shuffle else \
+                    self.buf(B, up * H, up * W, chan_storage(c_real), zero=True, dtype=out_dtype)
+        lo = (lambda t: lo_of(t)) if x3 else (lambda t: None)
+        op = ops.make_conv(h0, wp, hi_of(out), taps, src1=h1, w_c1_off=meta["c1_off"], n_total=n_total,
                            bias=pc(bias, 0.0), scale=pc(scale, 1.0), shift=pc(shift, 0.0), relu1=relu1, relu2=relu2,
-                           residual=residual, out_space=(B, H, W), shuffle=shuffle, group_n=meta.get("group_n", 0),
+                           residual=hi_of(residual), out_space=(B, H, W), shuffle=shuffle, group_n=meta.get("group_n", 0),
                            c_store=pad_to(c_real, 8), up=up, oy=oy, ox=ox, leaky1=leaky1, head_w=head_w, head_out=head_out,
-                           bn=n_total if head_w is not None else None, name=name)
+                           bn=n_total if head_w is not None else None, name=name, src0_lo=lo(src0), src1_lo=lo(src1),
+                           weight_lo=wl, out_lo=lo(out), residual_lo=lo(residual))
         if flops is None:
             flops = 2.0 * B * H * W * Cout * Cin * len(taps)
         self.ops.append(Op(name, op.launch, flops=flops, kind="gemm"))
@@ -145,19 +180,22 @@ class LaunchProgram:
         self.ops.append(Op(name, fn, bytes=nbytes))
 
     def affine(self, name, src, scale, shift, relu, out=None, out_c_off=0, c=None):
-        B, H, W, Cs = src.shape
+        """src may be a Pair (read as hi + lo); the result is a plain 16-bit tensor."""
+        sh_, sl_ = hi_of(src), lo_of(src)
+        B, H, W, Cs = sh_.shape
         c = c or Cs
         if out is None:
             out = self.buf(B, H, W, Cs, zero=True)
         sc = self.dev_f32(torch.cat([scale, scale.new_ones(pad_to(c, 8) - scale.numel())]))
         sh = self.dev_f32(torch.cat([shift, shift.new_zeros(pad_to(c, 8) - shift.numel())]))
-        in_ptr, out_ptr = src.data_ptr(), out.data_ptr() + 2 * out_c_off
-        n_pix, cc, istr, ostr, hd, lib = B * H * W, pad_to(c, 8), src.stride(2), out.stride(2), self.hd, self.lib
+        in_ptr, out_ptr = sh_.data_ptr(), out.data_ptr() + 2 * out_c_off
+        lo_ptr = sl_.data_ptr() if sl_ is not None else None
+        n_pix, cc, istr, ostr, hd, lib = B * H * W, pad_to(c, 8), sh_.stride(2), out.stride(2), self.hd, self.lib
 
         def fn(stream):
-            _lib.check(lib.havc_affine_act(in_ptr, out_ptr, n_pix, cc, istr, ostr, sc.data_ptr(), sh.data_ptr(),
+            _lib.check(lib.havc_affine_act(in_ptr, lo_ptr, out_ptr, None, n_pix, cc, istr, ostr, sc.data_ptr(), sh.data_ptr(),
                                            int(relu), hd, stream), name)
-        self.aux(name, fn, nbytes=4.0 * n_pix * cc)
+        self.aux(name, fn, nbytes=(4.0 if sl_ is None else 6.0) * n_pix * cc)
         return out
 
     def blur(self, name, src, out=None):
@@ -172,13 +210,19 @@ class LaunchProgram:
         return out
 
     def phase_split(self, name, src, n_phases):
+        """src: [B,H,W,C] tensor or Pair -> [P,B,H/2,W/2,C] (Pair: both planes, one launch each)."""
         B, H, W, Cs = src.shape
-        out = self.buf(n_phases, B, (H + 1) // 2, (W + 1) // 2, Cs, zero=True)
-        ip, op_, lib = src.data_ptr(), out.data_ptr(), self.lib
+        pair = isinstance(src, Pair)
+        shape = (n_phases, B, (H + 1) // 2, (W + 1) // 2, Cs)
+        out = Pair(self.buf(2, *shape, zero=True)) if pair else self.buf(*shape, zero=True)
+        lib = self.lib
+        ptrs = [(src.hi.data_ptr(), out.hi.data_ptr()), (src.lo.data_ptr(), out.lo.data_ptr())] if pair else \
+            [(src.data_ptr(), out.data_ptr())]
 
         def fn(stream):
-            _lib.check(lib.havc_phase_split(ip, op_, B, H, W, Cs, n_phases, stream), name)
-        self.aux(name, fn, nbytes=2.0 * B * H * W * Cs * (1 + n_phases / 4))
+            for ip, op_ in ptrs:
+                _lib.check(lib.havc_phase_split(ip, op_, B, H, W, Cs, n_phases, stream), name)
+        self.aux(name, fn, nbytes=2.0 * len(ptrs) * B * H * W * Cs * (1 + n_phases / 4))
         return out
 
     # ---- execution ----------------------------------------------------------------------------
@@ -195,11 +239,11 @@ class UnetProgram(LaunchProgram):
     """Compiled launch list of a DeOldify generator for one (state-dict, batch, S, dtype)."""
 
     def __init__(self, sd: SD, batch: int, size: int, dtype: torch.dtype = torch.float16, device="cuda",
-                 keep_taps: bool = False, x: Optional[torch.Tensor] = None):
+                 keep_taps: bool = False, x: Optional[torch.Tensor] = None, precision: Optional[str] = None):
         if size % 32 != 0:
             raise ValueError(f"render size {size} must be a multiple of 32 (even render_factor); the nearest-"
                              "neighbour up-path resize of unet.py:201-203 is not implemented")
-        super().__init__(sd, batch, size, dtype, device, keep_taps)
+        super().__init__(sd, batch, size, dtype, device, keep_taps, precision)
         self.bottleneck = "layers.0.4.0.conv3.weight" in sd
         self._x_shared = x
         self._build()
@@ -211,30 +255,41 @@ class UnetProgram(LaunchProgram):
         self.x = self._x_shared if self._x_shared is not None else self.buf(B, S, S, 8, zero=True)
 
         # ---- encoder stem: 7x7/s2 conv as im2col + GEMM, BN folded, ReLU --------------------------
-        w = sd["layers.0.0.weight"].float()
+        # The three input channels are the same gray L (ColorizerFilter._transform, filters.py:92-93), normalised per channel:
+        # x_c = (L/255 - mean_c)/std_c.  The normalisation is folded into the weights and the GEMM reads the EXACT integer
+        # channels (L, 1) the pre kernel stores in x[..., 4:6] (the '1' channel carries the -mean/std term and, being zero
+        # outside the image like every im2col tap, reproduces the zero padding of the normalised image):
+        #   sum_c w_c x_c = (sum_c w_c / (255 std_c)) * L  +  (-sum_c w_c mean_c / std_c) * 1
+        x3 = self.enc_x3
+        w = sd["layers.0.0.weight"].double()
         sc, sh = bn_affine(sd, "layers.0.1")
-        # K order of havc_im2col_small: k = kh*24 + kw*3 + c  (each filter row padded from 21 to 24)
-        wf = (w * sc.view(-1, 1, 1, 1)).permute(0, 2, 3, 1).reshape(64, 7, 21)
-        Kp = chan_storage(7 * 24)
-        wf = torch.cat([wf, wf.new_zeros(64, 7, 3)], 2).reshape(64, 168)
-        wf = torch.cat([wf, wf.new_zeros(64, Kp - 168)], 1).view(64, Kp, 1, 1)
+        mean = torch.tensor([0.485, 0.456, 0.406], dtype=torch.float64).view(1, 3, 1, 1)
+        std = torch.tensor([0.229, 0.224, 0.225], dtype=torch.float64).view(1, 3, 1, 1)
+        ws = w * sc.double().view(-1, 1, 1, 1)
+        w2 = torch.stack([(ws / (255.0 * std)).sum(1), -(ws * mean / std).sum(1)], 1)          # [64, 2, 7, 7]
+        # K order of havc_im2col_small: k = kh*16 + kw*2 + c  (each filter row padded from 14 to 16)
+        Kp = chan_storage(7 * 16)
+        wf = torch.cat([w2.permute(0, 2, 3, 1).reshape(64, 7, 14), w2.new_zeros(64, 7, 2)], 2).reshape(64, 112)
+        wf = torch.cat([wf, wf.new_zeros(64, Kp - 112)], 1).view(64, Kp, 1, 1).float()
         H2 = S // 2
         col = self.buf(B, H2, H2, Kp, zero=True)
         xp, cp = self.x.data_ptr(), col.data_ptr()
 
         def im2col(stream):
-            _lib.check(lib.havc_im2col_small(xp, cp, B, S, S, 8, 3, 7, 2, 3, Kp, hd, stream), "stem.im2col")
+            _lib.check(lib.havc_im2col_small(xp, cp, B, S, S, 8, 4, 2, 7, 2, 3, Kp, hd, stream), "stem.im2col")
         self.aux("stem.im2col", im2col, nbytes=2.0 * B * H2 * H2 * Kp)
-        stem = self.conv("stem.conv", col, wf, bias=sh, relu1=True)
+        stem = self.conv("stem.conv", col, wf, bias=sh, relu1=True, x3=x3)
         self.ops[-1].flops = 2.0 * B * H2 * H2 * 64 * 147
         self.tap("enc.stem", stem)
         H4 = S // 4
-        pool = self.buf(B, H4, H4, 64)
-        sp, pp = stem.data_ptr(), pool.data_ptr()
+        pool = Pair(self.buf(2, B, H4, H4, 64)) if x3 else self.buf(B, H4, H4, 64)
+        sp, pp = hi_of(stem).data_ptr(), hi_of(pool).data_ptr()
+        spl = stem.lo.data_ptr() if x3 else None
+        ppl = pool.lo.data_ptr() if x3 else None
 
         def maxpool(stream):
-            _lib.check(lib.havc_maxpool3x3s2(sp, pp, B, H2, H2, 64, hd, stream), "stem.maxpool")
-        self.aux("stem.maxpool", maxpool, nbytes=2.0 * B * (H2 * H2 + H4 * H4) * 64)
+            _lib.check(lib.havc_maxpool3x3s2(sp, spl, pp, ppl, B, H2, H2, 64, hd, stream), "stem.maxpool")
+        self.aux("stem.maxpool", maxpool, nbytes=(4.0 if x3 else 2.0) * B * (H2 * H2 + H4 * H4) * 64)
 
         # ---- resnet layers --------------------------------------------------------------------------
         y = pool
@@ -280,7 +335,7 @@ class UnetProgram(LaunchProgram):
             ip, op_ = src.data_ptr(), col.data_ptr()
 
             def fn(stream):
-                _lib.check(lib.havc_im2col_small(ip, op_, B, S, S, 8, 3, 3, 1, 1, 64, hd, stream), name)
+                _lib.check(lib.havc_im2col_small(ip, op_, B, S, S, 8, 0, 3, 3, 1, 1, 64, hd, stream), name)
             self.aux(name, fn, nbytes=B * S * S * (16.0 + 96.0))
             return col
 
@@ -340,41 +395,44 @@ class UnetProgram(LaunchProgram):
 
     def _bottleneck(self, x, p, stride):
         """torchvision Bottleneck, v1.5 (stride on conv2); BN folded into each conv."""
+        x3 = self.enc_x3
         w1, b1 = self._fold_bn(p + ".conv1", p + ".bn1")
         w2, b2 = self._fold_bn(p + ".conv2", p + ".bn2")
         w3, b3 = self._fold_bn(p + ".conv3", p + ".bn3")
-        c1 = self.conv(p + ".conv1", x, w1, bias=b1, relu1=True)
+        c1 = self.conv(p + ".conv1", x, w1, bias=b1, relu1=True, x3=x3)
         if stride == 2:
             ph = self.phase_split(p + ".split", c1, 4)
-            c2 = self.conv(p + ".conv2", ph, w2, ks=3, stride=2, bias=b2, relu1=True)
+            c2 = self.conv(p + ".conv2", ph, w2, ks=3, stride=2, bias=b2, relu1=True, x3=x3)
         else:
-            c2 = self.conv(p + ".conv2", c1, w2, ks=3, bias=b2, relu1=True)
+            c2 = self.conv(p + ".conv2", c1, w2, ks=3, bias=b2, relu1=True, x3=x3)
         idt = x
         if p + ".downsample.0.weight" in self.sd:
             wd, bd = self._fold_bn(p + ".downsample.0", p + ".downsample.1")
             if stride == 2:
                 xs = self.phase_split(p + ".ds_split", x, 1)
-                idt = self.conv(p + ".downsample", xs, wd, stride=2, bias=bd)
+                idt = self.conv(p + ".downsample", xs, wd, stride=2, bias=bd, x3=x3)
             else:
-                idt = self.conv(p + ".downsample", x, wd, bias=bd)
-        return self.conv(p + ".conv3", c2, w3, bias=b3, residual=idt, relu2=True)
+                idt = self.conv(p + ".downsample", x, wd, bias=bd, x3=x3)
+        return self.conv(p + ".conv3", c2, w3, bias=b3, residual=idt, relu2=True, x3=x3)
 
     def _basic(self, x, p, stride):
+        x3 = self.enc_x3
         w1, b1 = self._fold_bn(p + ".conv1", p + ".bn1")
         w2, b2 = self._fold_bn(p + ".conv2", p + ".bn2")
         idt = x
         if stride == 2:
             ph = self.phase_split(p + ".split", x, 4)
-            c1 = self.conv(p + ".conv1", ph, w1, ks=3, stride=2, bias=b1, relu1=True)
+            c1 = self.conv(p + ".conv1", ph, w1, ks=3, stride=2, bias=b1, relu1=True, x3=x3)
             if p + ".downsample.0.weight" in self.sd:
                 wd, bd = self._fold_bn(p + ".downsample.0", p + ".downsample.1")
-                idt = self.conv(p + ".downsample", ph[0:1], wd, stride=2, bias=bd)
+                ph0 = ph.sub(slice(0, 1)) if isinstance(ph, Pair) else ph[0:1]
+                idt = self.conv(p + ".downsample", ph0, wd, stride=2, bias=bd, x3=x3)
         else:
-            c1 = self.conv(p + ".conv1", x, w1, ks=3, bias=b1, relu1=True)
+            c1 = self.conv(p + ".conv1", x, w1, ks=3, bias=b1, relu1=True, x3=x3)
             if p + ".downsample.0.weight" in self.sd:
                 wd, bd = self._fold_bn(p + ".downsample.0", p + ".downsample.1")
-                idt = self.conv(p + ".downsample", x, wd, bias=bd)
-        return self.conv(p + ".conv2", c1, w2, ks=3, bias=b2, residual=idt, relu2=True)
+                idt = self.conv(p + ".downsample", x, wd, bias=bd, x3=x3)
+        return self.conv(p + ".conv2", c1, w2, ks=3, bias=b2, residual=idt, relu2=True, x3=x3)
 
     def _unet_block(self, up_in, skip, p):
         """UnetBlockWide / UnetBlockDeep (unet.py:170-205 / 55-91)."""
@@ -384,7 +442,7 @@ class UnetProgram(LaunchProgram):
         sc, sh = bn_affine(sd, p + ".shuf.conv.1")
         t = self.conv(p + ".shuf.conv", up_in, ws * sc.view(-1, 1, 1, 1), bias=sh, relu1=True, shuffle=True)
         u = self.blur(p + ".shuf.blur", t)
-        if u.shape[1:3] != skip.shape[1:3]:
+        if tuple(u.shape[1:3]) != tuple(skip.shape[1:3]):
             raise ValueError("up-path / skip size mismatch (odd render_factor) is not supported")
         sc, sh = bn_affine(sd, p + ".bn")
         sb = self.affine(p + ".skip_bn_relu", skip, sc, sh, True)

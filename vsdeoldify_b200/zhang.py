@@ -59,7 +59,7 @@ class ZhangProgram(LaunchProgram):
         xp, cp = self.x.data_ptr(), col.data_ptr()
 
         def im2col(stream):
-            _lib.check(lib.havc_im2col_small(xp, cp, B, S, S, 8, 1, 3, 1, 1, Kp, hd, stream), name + ".im2col")
+            _lib.check(lib.havc_im2col_small(xp, cp, B, S, S, 8, 0, 1, 3, 1, 1, Kp, hd, stream), name + ".im2col")
         self.aux(name + ".im2col", im2col, nbytes=2.0 * B * S * S * (8 + Kp))
         cout = w.shape[0]
         wk = torch.zeros(cout, 3, 8)
