@@ -112,8 +112,9 @@ def load_traffic(batch: int):
 
 
 def cpu_reference_fps(n_frames: int, threads: int, h: int = H1080, w: int = W1080, rf: int = RF, seed: int = 1234):
-    """The CPU restatement of the reference path (oracle/pipeline_oracle.py), end to end per frame."""
-    from oracle import pipeline_oracle, synth_weights
+    """The CPU restatement of the reference path (oracle/pipeline_oracle.py): (a) end to end per frame (resize + gray + normalise
+    + forward + denorm + luma transplants), (b) the network forward alone (BASELINE.md section 4 asks for both)."""
+    from oracle import pipeline_oracle, pixel_oracle as px, synth_weights, unet_oracle
     torch.set_num_threads(threads)
     sd = synth_weights.make_unet_state_dict("wide", seed)
     clip = synth_clip(n_frames + 1, h, w, seed=0)
@@ -123,7 +124,14 @@ def cpu_reference_fps(n_frames: int, threads: int, h: int = H1080, w: int = W108
         t0 = time.perf_counter()
         pipeline_oracle.havc_colorizer_frame(sd, np.ascontiguousarray(np.transpose(clip[i], (1, 2, 0))), rf)
         times.append(time.perf_counter() - t0)
-    return 1.0 / float(np.median(times)), times
+    S = rf * 16
+    x = torch.from_numpy(px.normalize_gray(px.pil_luma(px.resize_plane_u8(np.ascontiguousarray(np.transpose(clip[0], (1, 2, 0))), S, S))))[None]
+    net = []
+    for i in range(max(2, n_frames)):
+        t0 = time.perf_counter()
+        unet_oracle.unet_forward(sd, x)
+        net.append(time.perf_counter() - t0)
+    return 1.0 / float(np.median(times)), 1.0 / float(np.median(net)), times
 
 
 def plugin_surface_fps(sd, clip: np.ndarray, n_frames: int, batch: int):
@@ -170,11 +178,87 @@ def run_reference(args):
         "config": {"workload": WORKLOAD, "frames_per_step": 1, "weights": "synthetic seed 1234 (reference state-dict schema)",
                    "sample": "each step = 1 frame of the clip on the host cores (bounded sample of the same workload)"},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
-                         "sample": f"{args.steps} frames of the 1080p clip, 1 frame per step, torch CPU fp32 oracle port of the reference path"},
+                         "sample": f"{args.steps} frames of the 1080p clip, 1 frame per step, torch CPU fp32 oracle port of the reference path "
+                                   "(banded Spline64 resize: the dense-matrix resize of round 1 inflated the CPU time ~2x)"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
+
+
+# ---- extra configurations (BASELINE.json configs[2..4]) and A/B arms: small device-resident throughput runs -----------------
+CONFIG_GFLOP = {"cfg2": 639.0, "cfg3": 2007.6, "cfg4": 789.4, "cfg5": 4405.6}      # SURVEY.md 8(d), algorithmic per frame
+DEFAULT_MERGE = dict(method=2, weight=0.4, cmc_p=[0.15, True, 20, 24], lmm_p=[0.15, 0.65, 1.0], alm_p=[0.8, 1.0, 0.15],
+                     crt_p=[0.8, 30, 2, False, 0, 0], invert=False)
+
+
+def build_config_engine(name: str, dev: str, dtype, batch: int, precision=None):
+    """(engine, width, height, description) of BASELINE.json configs[1..4] on synthetic weights."""
+    from oracle import synth_weights, zhang_oracle
+    from vsdeoldify_b200.constants import DEF_ARTISTIC_WEIGHT, DEF_STABLE_WEIGHT
+    from vsdeoldify_b200.engine import DeoldifyEngine
+    video = synth_weights.make_unet_state_dict("wide", 1234)
+    if name == "cfg2":
+        return DeoldifyEngine(video, W1080, H1080, render_factor=24, batch=batch, dtype=dtype, device=dev, precision=precision), W1080, H1080, \
+            "video rf=24, 1080p"
+    if name == "cfg3":
+        stable = synth_weights.make_unet_state_dict("wide", 4321)
+        return DeoldifyEngine(video, W1080, H1080, render_factor=30, batch=batch, dtype=dtype, device=dev, sd_other=stable,
+                              video_weight=DEF_STABLE_WEIGHT, precision=precision), W1080, H1080, "stable rf=30 (video + stable @480), 1080p"
+    if name == "cfg4":
+        sdz = zhang_oracle.make_zhang_state_dict("siggraph17", 1234)
+        return DeoldifyEngine(video, W1080, H1080, render_factor=24, batch=batch, dtype=dtype, device=dev, zhang=("siggraph17", sdz),
+                              merge=dict(DEFAULT_MERGE), hue_adjust="300:360|0.8,0.1", precision=precision), W1080, H1080, \
+            "video rf=24 + siggraph17, method 2 merge + hue adjust, 1080p"
+    if name == "cfg5":
+        deep = synth_weights.make_unet_state_dict("deep", 1234)
+        sdz = zhang_oracle.make_zhang_state_dict("eccv16", 1234)
+        return DeoldifyEngine(video, 3840, 2160, render_factor=40, batch=batch, dtype=dtype, device=dev, sd_other=deep,
+                              video_weight=DEF_ARTISTIC_WEIGHT, zhang=("eccv16", sdz), merge=dict(DEFAULT_MERGE), precision=precision), \
+            3840, 2160, "artistic rf=40 (video + artistic @640) + eccv16, method 2 merge, UHD"
+    raise ValueError(name)
+
+
+def time_engine(eng, clip_dev, steps: int, warm: int = 3, preheat_s: float = 0.0):
+    """ms per step of graph replays on device-resident input batches (CUDA events on the compute stream)."""
+    def step(i):
+        s = i % eng.n_slots
+        with torch.cuda.stream(eng.compute):
+            eng.d_in[s].copy_(clip_dev[i % len(clip_dev)], non_blocking=True)
+        eng.run_slot(s)
+    for i in range(warm):
+        step(i)
+    eng.compute.synchronize()
+    if preheat_s > 0:
+        t0 = time.perf_counter()
+        i = 0
+        while time.perf_counter() - t0 < preheat_s:
+            for _ in range(4):
+                step(i)
+                i += 1
+            eng.compute.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(eng.compute)
+    for i in range(steps):
+        step(i)
+    e1.record(eng.compute)
+    eng.compute.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def parity_check(eng, sd, frames: np.ndarray, rf: int = RF, n: int = 2) -> dict:
+    """n frames of the engine's output against the CPU oracle of the reference path (same run, same weights): the worst frame."""
+    from oracle import metrics, pipeline_oracle
+    out = eng.colorize_batch(np.ascontiguousarray(frames[:eng.B]))
+    worst = None
+    for i in range(n):
+        ref = pipeline_oracle.havc_colorizer_frame(sd, np.ascontiguousarray(np.transpose(frames[i], (1, 2, 0))), rf)
+        m = metrics.frame_parity(np.ascontiguousarray(np.transpose(out[i], (1, 2, 0))), ref)
+        if worst is None or m["mean_de00"] > worst["mean_de00"]:
+            worst = m
+    return {"mean_de00": round(worst["mean_de00"], 4), "max_err": worst["max_err"], "n_err_gt2": worst["n_err_gt2"],
+            "n_values": worst["n_values"], "frames": n, "gate": "mean dE00 <= 0.5 (north star); max_err <= 2 is violated by the "
+            "reference against itself (tests/parity_gate.py)"}
 
 
 _REAL_STDOUT = None
@@ -205,10 +289,15 @@ def main():
     ap.add_argument("--batch", type=int, default=int(os.environ.get("HAVC_BENCH_BATCH", "32")),
                     help="frames per step and per CUDA-graph launch (32 frames = 16 GB of activations of the 180 GB)")
     ap.add_argument("--dtype", default=os.environ.get("HAVC_BENCH_DTYPE", "fp16"), choices=["fp16", "bf16"])
+    ap.add_argument("--precision", default=None, choices=[None, "fast", "balanced", "auto"],
+                    help="operand precision policy of the headline arm (default: the library default, HAVC_B200_PRECISION / auto)")
     ap.add_argument("--cpu-frames", type=int, default=4, help="frames of the bounded CPU-baseline sample (0 = skip)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--plugin-frames", type=int, default=128,
                     help="frames rendered through HAVC_colorizer on a VapourSynth-stand-in clip for the plugin_surface figure (0 = skip)")
+    ap.add_argument("--preheat", type=float, default=3.0, help="seconds of untimed steps before the timed region (clocks settle)")
+    ap.add_argument("--extras", default="ab,bf16,cfg3,cfg4,cfg5,parity",
+                    help="comma list of the extra arms measured at N = 1 on rank 0 ('' = none)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -230,23 +319,34 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     dev = f"cuda:{local}"
     torch.cuda.set_device(dev)
+    extras = set(t for t in args.extras.split(",") if t) if (rank == 0 and world == 1) else set()
 
     from oracle import synth_weights   # weight generator only (test infrastructure; not on the timed path)
-    from vsdeoldify_b200 import _lib
+    from vsdeoldify_b200 import _lib, partition
     from vsdeoldify_b200.engine import DeoldifyEngine
 
     dtype = torch.float16 if args.dtype == "fp16" else torch.bfloat16
     B, K, Wm = args.batch, args.steps, args.warmup
     sd = synth_weights.make_unet_state_dict("wide", 1234)
-    eng = DeoldifyEngine(sd, W1080, H1080, render_factor=RF, batch=B, dtype=dtype, device=dev, use_graph=not args.no_graph)
+    eng = DeoldifyEngine(sd, W1080, H1080, render_factor=RF, batch=B, dtype=dtype, device=dev, use_graph=not args.no_graph,
+                         precision=args.precision)
     lib = _lib.lib()
 
-    # each rank owns a contiguous block of the clip (block partition, no collective)
-    n_host_batches = 4
-    clip = synth_clip(n_host_batches * B, H1080, W1080, seed=100 + rank)
-    host_batches = [np.ascontiguousarray(clip[i * B:(i + 1) * B]) for i in range(n_host_batches)]
-    dev_batches = [torch.from_numpy(b).to(dev) for b in host_batches]
-    pinned_batches = [torch.from_numpy(b).pin_memory() for b in host_batches]   # e2e inputs live in pinned host memory
+    # ONE clip of world * K * B frames, block-partitioned over the ranks (partition.block_range; no collective on the data path):
+    # rank r renders frames [r*K*B, (r+1)*K*B).  Frame n of the clip is base[n % len(base)] of a seeded base sequence that every
+    # rank generates identically, so what a rank renders depends only on the global frame numbers it owns.
+    n_base_batches = 4
+    base = synth_clip(n_base_batches * B, H1080, W1080, seed=100)
+    n_total = world * K * B
+    f0, f1 = partition.block_range(n_total, rank, world)
+    assert f1 - f0 == K * B
+    def host_batch(step):                      # the B frames of this rank's step `step`: global frames f0 + step*B ...
+        idx = (f0 + step * B + np.arange(B)) % base.shape[0]
+        return base[idx]
+    first_batches = [np.ascontiguousarray(host_batch(i)) for i in range(min(K, n_base_batches))]
+    dev_batches = [torch.from_numpy(b).to(dev) for b in first_batches]
+    pinned_batches = [torch.from_numpy(b).pin_memory() for b in first_batches]   # e2e inputs live in pinned host memory
+    nb = len(first_batches)
 
     def barrier():
         torch.cuda.synchronize()
@@ -258,18 +358,28 @@ def main():
     def device_step(i):
         s = i % eng.n_slots
         with torch.cuda.stream(eng.compute):
-            eng.d_in[s].copy_(dev_batches[i % n_host_batches], non_blocking=True)   # D2D: stage the next resident batch
+            eng.d_in[s].copy_(dev_batches[i % nb], non_blocking=True)   # D2D: stage the next resident batch
         eng.run_slot(s)
 
     for i in range(Wm):
         device_step(i)
+    barrier()
+    # pre-heat: the sustained tensor peak in MEASURED_PEAKS.json was taken after seconds of load (SM clock ~1.3 GHz under the
+    # power cap); a timed region that starts cold runs at a higher clock and flatters the roofline fraction
+    t_heat = time.perf_counter()
+    i = 0
+    while time.perf_counter() - t_heat < args.preheat:
+        for _ in range(4):
+            device_step(i)
+            i += 1
+        torch.cuda.synchronize()
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(eng.compute)
     for i in range(K):
-        device_step(Wm + i)
+        device_step(i)
     e1.record(eng.compute)
     barrier()
     ms = e0.elapsed_time(e1)
@@ -279,16 +389,19 @@ def main():
     ms_dev = float(tmax.item())
 
     # ---------------- end to end through the host API (e2e) ----------------
-    sink = {"n": 0, "sum": 0}
+    import zlib
+    sink = {"n": 0, "sum": 0, "crc": {}}
 
     def on_result(i, out):
         sink["n"] += out.shape[0]
         sink["sum"] += int(out[0, 0, 0, 0])     # touch the result on the host
+        if i in (0, K - 1):                      # order / bytes check material: first and last batch of this rank's block
+            sink["crc"][f0 + i * B] = [zlib.crc32(out[j].tobytes()) for j in (0, B - 1)]
 
-    eng.colorize_stream((pinned_batches[i % n_host_batches] for i in range(Wm)), on_result)
+    eng.colorize_stream((pinned_batches[i % nb] for i in range(Wm)), lambda i, o: None)
     barrier()
     t0 = time.perf_counter()
-    eng.colorize_stream((pinned_batches[i % n_host_batches] for i in range(K)), on_result)
+    eng.colorize_stream((pinned_batches[i % nb] for i in range(K)), on_result)
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
     te = torch.tensor([t_e2e], device=dev)
@@ -298,8 +411,26 @@ def main():
     sampler.stop_flag.set()
     sampler.join(timeout=3)
 
-    # ---------------- per-kernel timing of one step (roofline of the dominant kernel) ----------------
-    roof, breakdown = None, None
+    # ---------------- sharding check: every rank's block bytes == what ONE GPU renders for those frame numbers -----------
+    shard_check = None
+    if dist is not None:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, {"rank": rank, "range": [f0, f1], "crc": sink["crc"]})
+        if rank == 0:
+            ok, checked, ranges = True, 0, []
+            for g in sorted(gathered, key=lambda g: g["rank"]):
+                ranges.append(g["range"])
+                for start, crcs in g["crc"].items():
+                    idx = (int(start) + np.arange(B)) % base.shape[0]
+                    mine = eng.colorize_batch(np.ascontiguousarray(base[idx]))
+                    ok = ok and [zlib.crc32(mine[j].tobytes()) for j in (0, B - 1)] == list(crcs)
+                    checked += 2
+            in_order = all(ranges[r][1] == ranges[r + 1][0] for r in range(world - 1)) and ranges[0][0] == 0 and ranges[-1][1] == n_total
+            shard_check = {"frames_checked": checked, "bytes_equal_single_gpu": bool(ok), "blocks_contiguous_in_rank_order": bool(in_order),
+                           "clip_frames": n_total, "partition": "partition.block_range"}
+
+    # ---------------- per-kernel timing of one step (roofline of the dominant kernel + of the pixel passes) ----------------
+    roof, breakdown, roof_px = None, None, None
     if rank == 0:
         evs = []
         with torch.cuda.stream(eng.compute):
@@ -327,21 +458,70 @@ def main():
         top = sorted(((a.elapsed_time(b), op.name, op.flops) for op, a, b in evs), reverse=True)[:8]
         breakdown = {"gemm_ms_per_step": gemm_ms, "aux_ms_per_step": aux_ms,
                      "top": [{"op": n, "ms": round(t, 4), "tflops": round(f / (t * 1e-3) / 1e12, 1) if f else None} for t, n, f in top]}
+        # pixel passes: whole step (graph) minus the network launch list, measured as back-to-back launches of the same list
+        with torch.cuda.stream(eng.compute):
+            a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            for rep in range(2):
+                a.record(eng.compute)
+                eng._launch(0, eng.compute.cuda_stream)
+                b.record(eng.compute)
+                eng.prog.run(eng.compute.cuda_stream)
+                c.record(eng.compute)
+        eng.compute.synchronize()
+        px_ms = max(a.elapsed_time(b) - b.elapsed_time(c), 1e-6)
+        px_bytes = 20.6e6 * B                                  # read RGB24 once, read again + write in the post pass, + S x S
+        roof_px = {"bound": "hbm", "kernels": "resample_h_rows + pre_vertical4 + head + resample_v4 + post_horizontal",
+                   "bytes_algorithmic": px_bytes, "ms": px_ms, "achieved": px_bytes / (px_ms * 1e-3) / 1e9, "peak": peaks["hbm"],
+                   "unit": "GB/s", "frac_of_hbm": px_bytes / (px_ms * 1e-3) / 1e9 / peaks["hbm"],
+                   "how": "CUDA events: (pre + net + head + post launch list) - (net launch list), same stream, per step of B frames"}
+
+    # ---------------- extras at N = 1 (rank 0): parity in the same run, precision A/B, bf16, the other BASELINE configs ----------------
+    peaks = load_peaks()
+    parity = None
+    if "parity" in extras:
+        parity = parity_check(eng, sd, base)
+    arms = {}
+    def run_arm(label, build, gflop, frames_wh=None, steps=6, parity_of=None):
+        try:
+            e2, w_, h_, desc = build()
+            nb2 = 2
+            clip2 = base if (w_, h_) == (W1080, H1080) else synth_clip(nb2 * e2.B, h_, w_, seed=100)
+            devb = [torch.from_numpy(np.ascontiguousarray(clip2[i * e2.B:(i + 1) * e2.B])).to(dev) for i in range(nb2)]
+            ms_ = time_engine(e2, devb, steps, warm=3, preheat_s=1.0)
+            fps_ = e2.B / (ms_ * 1e-3)
+            arms[label] = {"workload": desc, "frames_per_step": e2.B, "value": fps_, "unit": "frames/s", "ms_per_step": ms_,
+                           "gflop_per_frame": gflop, "tensor_frac_whole_step": gflop * 1e9 * fps_ / (peaks["tf_sustained"] * 1e12)}
+            if parity_of is not None:
+                arms[label]["parity"] = parity_check(e2, parity_of, base)
+            del e2, devb
+        except Exception as e:                  # an extra arm never costs the bench line
+            arms[label] = {"error": str(e)[:300]}
+        torch.cuda.empty_cache()
+    if "ab" in extras:      # the explicit accuracy-vs-time trade of the operand precision policy (same workload as the headline)
+        for prec in ("fast", "balanced"):
+            run_arm(f"cfg2_{prec}", lambda prec=prec: build_config_engine("cfg2", dev, dtype, B, precision=prec), CONFIG_GFLOP["cfg2"],
+                    parity_of=sd)
+    if "bf16" in extras and dtype != torch.bfloat16:
+        run_arm("cfg2_bf16", lambda: build_config_engine("cfg2", dev, torch.bfloat16, B), CONFIG_GFLOP["cfg2"], parity_of=sd)
+    for cfg, bsz in (("cfg3", 16), ("cfg4", 16), ("cfg5", 4)):
+        if cfg in extras:
+            run_arm(cfg, lambda cfg=cfg, bsz=bsz: build_config_engine(cfg, dev, dtype, bsz), CONFIG_GFLOP[cfg])
 
     # ---------------- CPU baseline (rank 0, N = 1 only, bounded sample) ----------------
     cpu = None
     if rank == 0 and world == 1 and args.cpu_frames > 0:
         threads = os.cpu_count() or 1
-        fps_cpu, times = cpu_reference_fps(args.cpu_frames, threads)
-        cpu = {"value": fps_cpu, "unit": "frames/s", "cores": threads, "kind": "port",
+        fps_cpu, fps_net, times = cpu_reference_fps(args.cpu_frames, threads)
+        cpu = {"value": fps_cpu, "unit": "frames/s", "cores": threads, "kind": "port", "net_only": fps_net,
                "sample": f"{args.cpu_frames} frames of the same 1080p workload (after 1 warm-up frame), median per-frame wall clock, "
-                         "torch CPU fp32 oracle port of the reference path"}
+                         "torch CPU fp32 oracle port of the reference path; value = end to end per frame, net_only = the generator "
+                         "forward alone (BASELINE.md section 4)"}
 
     # ---------------- the same path through the plugin surface (rank 0, N = 1 only; informational) ----------------
     plugin = None
     if rank == 0 and world == 1 and args.plugin_frames > 0:
         try:
-            plugin = plugin_surface_fps(sd, clip, args.plugin_frames, B)
+            plugin = plugin_surface_fps(sd, base, args.plugin_frames, B)
         except Exception as e:      # never lose the bench line over the informational figure
             plugin = {"error": str(e)[:200]}
 
@@ -355,12 +535,15 @@ def main():
             "dtype": "f16" if dtype == torch.float16 else "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD,
                        "frames_per_step": B, "weights": "synthetic seed 1234 (reference state-dict schema)",
-                       "cache": "inputs+activations per step (>1 GB) exceed the 126 MB L2; 4 distinct input batches rotated",
-                       "partition": "contiguous frame blocks per rank, no collective"},
+                       "precision_policy": eng.prog.precision,
+                       "cache": "inputs+activations per step (>1 GB) exceed the 126 MB L2; distinct input batches rotated",
+                       "preheat_s": args.preheat,
+                       "partition": f"one clip of {n_total} frames, contiguous frame blocks per rank (partition.block_range), no collective"},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * 3 * H1080 * W1080, "d2h_bytes_per_step": B * 3 * H1080 * W1080},
             "gpu_launches": eng.launches_per_batch * K,
             "clocks": sampler.summary(),
-            "roofline": roof, "breakdown": breakdown, "cpu_baseline": cpu, "plugin_surface": plugin,
+            "roofline": roof, "roofline_pixel": roof_px, "breakdown": breakdown, "cpu_baseline": cpu, "plugin_surface": plugin,
+            "parity": parity, "shard_check": shard_check, "arms": arms or None,
             "tensor_frac_whole_step": (GFLOP_PER_FRAME_SURVEY * 1e9 * value / world) / (load_peaks()["tf_sustained"] * 1e12),
         }
         emit(line)

@@ -63,7 +63,7 @@ def test_cfg2_video_rf24_1080p_vs_oracle_and_properties():
     m = metrics.frame_parity(np.ascontiguousarray(np.transpose(out[0], (1, 2, 0))), ref)
     print("cfg2 1080p frame parity:", m)
     assert m["mean_de00"] <= 0.5, m                                   # north-star gate
-    assert m["n_err_gt2"] <= 2.5e-2 * m["n_values"], m               # see tests/test_gpu_unet.py on the strict max <= 2 gate
+    assert m["n_err_gt2"] <= 1.2e-2 * m["n_values"], m               # regression guard (tests/parity_gate.py), measured 6e-3
     assert _luma_err(np.transpose(ref, (2, 0, 1)), clip[0])[1] <= 1   # the oracle has the same property
 
 

@@ -220,11 +220,10 @@ def test_model_image_render_vs_reference_golden(model, rf):
         assert m["n_err_gt2"] <= 0.02 * m["n_values"], (model, name, m)
 
 
-@pytest.mark.parametrize("zmodel,zname,gate", [(2, "siggraph17", 0.65), (3, "eccv16", 1.4)])
+@pytest.mark.parametrize("zmodel,zname,gate", [(2, "siggraph17", 0.5), (3, "eccv16", 0.5)])
 def test_colorizer_ddtweak_inverted_merge(zmodel, zname, gate):
     """cfg4-style call: ddtweak=[True, False, False] with the default luma-constrained tweak (luma_adjusted_levels on the
-    second model's input, vs_recover_clip_luma on its output), clips swapped (cmb_sw).  The eccv16 gate is wider: its
-    random-weight stack amplifies storage rounding (see tests/test_gpu_zhang.py)."""
+    second model's input, vs_recover_clip_luma on its output), clips swapped (cmb_sw).  North-star mean gate for both."""
     from oracle import metrics, pipeline_oracle
     from vsdeoldify_b200.constants import DEF_TWEAK_p
     havc = _register()

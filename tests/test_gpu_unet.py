@@ -1,13 +1,15 @@
 """GPU parity of the full DeOldify generators and of the per-frame HAVC_colorizer(method=0) pipeline against
 the CPU fp32 oracle (oracle/unet_oracle.py + oracle/pipeline_oracle.py) on seeded synthetic weights.
 
-Gates (BASELINE.json north_star): mean CIEDE2000 <= 0.5 per frame; max 8-bit channel error reported with the
-count of values off by more than 2 (SURVEY.md section 7 hard part 1 explains why the strict max <= 2 cannot be
-met by any 16-bit-operand tensor-core path; the test bounds the fraction of such values instead).
+Gates (BASELINE.json north_star, tests/parity_gate.py): mean CIEDE2000 <= 0.5 per frame - asserted unmodified for every
+generator; max 8-bit channel error <= 2 - asserted unmodified in the xfail-marked *_strict_max_gate tests (the reference
+violates it against itself).
 """
 import numpy as np
 import pytest
 import torch
+
+from parity_gate import XFAIL_REASON, assert_mean_gate, assert_outlier_guard, strict_max_gate
 
 pytestmark = pytest.mark.gpu
 
@@ -75,29 +77,40 @@ def test_unet_layers_vs_oracle(arch, dtype):
     assert float((err ** 2).mean().sqrt()) < out_tol, "\n".join(report)
 
 
-@pytest.mark.parametrize("arch", ["wide", "deep"])
-def test_colorizer_frame_vs_oracle(arch):
+def _colorizer_frames_vs_oracle(arch):
     from oracle import metrics, pipeline_oracle
     from vsdeoldify_b200.engine import DeoldifyEngine
     sd = _sd(arch)
     H, W, rf, B = 180, 320, 8, 2
-    eng = DeoldifyEngine(sd, W, H, render_factor=rf, batch=B, dtype=torch.float16)
-    frames = _frames(B, H, W, seed=11)
-    out = eng.colorize_batch(frames)
-    for i in range(B):
-        ref, st = pipeline_oracle.havc_colorizer_frame(sd, np.transpose(frames[i], (1, 2, 0)), rf, return_stages=True)
-        got = np.transpose(out[i], (1, 2, 0))
-        m = metrics.frame_parity(got, ref)
+    key = ("frames", arch)
+    if key not in _CACHE:
+        eng = DeoldifyEngine(sd, W, H, render_factor=rf, batch=B, dtype=torch.float16)
+        frames = _frames(B, H, W, seed=11)
+        out = eng.colorize_batch(frames)
+        res = []
+        for i in range(B):
+            ref = pipeline_oracle.havc_colorizer_frame(sd, np.transpose(frames[i], (1, 2, 0)), rf)
+            got = np.transpose(out[i], (1, 2, 0))
+            res.append((metrics.frame_parity(got, ref), got, np.transpose(frames[i], (1, 2, 0))))
+        _CACHE[key] = res
+    return _CACHE[key]
+
+
+@pytest.mark.parametrize("arch", ["wide", "deep"])
+def test_colorizer_frame_vs_oracle(arch):
+    for i, (m, got, src) in enumerate(_colorizer_frames_vs_oracle(arch)):
         print(arch, i, m)
-        # north-star gate: mean dE00 <= 0.5 (the artistic generator alone is noisier on these synthetic weights; in
-        # the product it is always blended 50/50 with the video generator, visualize.py:135)
-        assert m["mean_de00"] <= (0.5 if arch == "wide" else 0.8), m
-        # fp16 operands carry the same 10-bit mantissa as the TF32 convolutions of the reference's own GPU path
-        # (cuDNN default): isolated +-3..7 values after the truncating quantiser and the YUV
-        # round trip are inherent to that precision class; bound their share.
-        assert m["n_err_gt2"] <= 2.5e-2 * m["n_values"], m
+        assert_mean_gate(m, (arch, i))                          # north-star gate, both generators
+        assert_outlier_guard(m, 1.0e-2, (arch, i))              # regression guard (measured: wide 3.5e-3 / deep 4.3e-3)
         # the colourised frame keeps the source luma: the path is not a pass-through
-        assert np.abs(got.astype(int) - np.transpose(frames[i], (1, 2, 0)).astype(int)).max() > 8
+        assert np.abs(got.astype(int) - src.astype(int)).max() > 8
+
+
+@pytest.mark.xfail(reason=XFAIL_REASON, strict=False)
+@pytest.mark.parametrize("arch", ["wide", "deep"])
+def test_colorizer_frame_strict_max_gate(arch):
+    for i, (m, got, src) in enumerate(_colorizer_frames_vs_oracle(arch)):
+        strict_max_gate(m, (arch, i))
 
 
 def test_graph_replay_is_deterministic_and_ordered():
@@ -127,7 +140,7 @@ def test_colorizer_frame_odd_sizes_scalar_pixel_kernels(H, W, rf):
     for i in range(2):
         ref = pipeline_oracle.havc_colorizer_frame(sd, np.transpose(frames[i], (1, 2, 0)), rf)
         m = metrics.frame_parity(np.transpose(out[i], (1, 2, 0)), ref)
-        assert m["mean_de00"] <= 0.5, (H, W, rf, i, m)
+        assert_mean_gate(m, (H, W, rf, i))
 
 
 @pytest.mark.parametrize("H,W,rf,frame_size", [(90, 80, 6, None), (96, 160, 4, 96), (120, 200, 6, 160)])
@@ -145,6 +158,6 @@ def test_colorizer_frame_size_differs_from_render_size(H, W, rf, frame_size):
     out = eng.colorize_batch(frames, skip=np.array([False, True]))
     ref = pipeline_oracle.havc_colorizer_frame(sd, np.transpose(frames[0], (1, 2, 0)), rf, frame_size=frame_size)
     m = metrics.frame_parity(np.transpose(out[0], (1, 2, 0)), ref)
-    assert m["mean_de00"] <= 0.5, m
+    assert_mean_gate(m)
     ref_skip = pipeline_oracle.havc_colorizer_frame(sd, np.transpose(frames[1], (1, 2, 0)), rf, frame_size=frame_size, skip=True)
     assert np.array_equal(np.transpose(out[1], (1, 2, 0)), ref_skip), "a scene-change-skipped frame is the uncoloured squeeze path"

@@ -30,6 +30,7 @@ def test_zhang_network_vs_oracle(name):
     xn = ((l - 50.0) / 100.0)[:, 0]
     prog.x.zero_()
     prog.x[..., 0] = xn.cuda().half()
+    prog.x[..., 4] = (xn - xn.half().float()).cuda().half()        # lo part (what havc_zhang_pre stores for the split-precision blocks)
     prog.run(0)
     torch.cuda.synchronize()
     worst = 0.0
@@ -89,10 +90,7 @@ def test_zhang_colorize_frame_vs_oracle(name, S):
         got = np.transpose(out[i].cpu().numpy(), (1, 2, 0))
         m = metrics.frame_parity(got, want)
         print(name, S, i, m)
-        # siggraph17 meets the north-star gate.  The random-init eccv16 stack amplifies the 2^-11 storage rounding of
-        # its 22 layers to a 3 % logit error (reproduced on the CPU by rounding the oracle's activations to fp16 - the
-        # same class of deviation the reference's own TF32 GPU path has against its CPU path), which the 313-way
-        # soft-max turns into ~3.5 % of the ab spread: mean dE00 ~ 1.1 at an ab std of 13.
-        gate = 0.5 if name == "siggraph17" else 1.6
-        assert m["mean_de00"] <= gate, (name, i, m)
-        assert m["n_err_gt2"] <= (0.02 if name == "siggraph17" else 0.25) * m["n_values"], (name, i, m)
+        # north-star gate for both networks.  eccv16's BatchNorm-only stack amplifies an early perturbation (nothing damps it),
+        # so its first four blocks run split-precision (zhang.ZhangProgram.X3_BLOCKS): 1.1 -> ~0.25 at an ab std of 13
+        assert m["mean_de00"] <= 0.5, (name, i, m)
+        assert m["n_err_gt2"] <= (0.02 if name == "siggraph17" else 0.05) * m["n_values"], (name, i, m)   # regression guard

@@ -58,6 +58,9 @@ __global__ void zhang_pre_kernel(const uint8_t *__restrict__ rgb, int B, long lo
         if (x) {        // BaseColor.normalize_l in float32 (base_color.py:13-14); NHWC with 8-channel storage, channel 0
             const float v = __fdiv_rn(__fsub_rn(L, 50.0f), 100.0f);
             store16(x, i * 8, v, dtype);
+            // channel 4: the remainder of the 16-bit rounding (lo plane of the split-precision first convolution)
+            const float hi = load16(x, i * 8, dtype);
+            store16(x, i * 8 + 4, v - hi, dtype);
         }
     }
 }

@@ -71,7 +71,7 @@ class DeoldifyEngine:
         if zhang is not None:
             from .filters import FilterBank
             from .zhang import ZhangColorizer
-            self.zhang = ZhangColorizer(zhang[1], zhang[0], B, S, dtype, device=self.dev)
+            self.zhang = ZhangColorizer(zhang[1], zhang[0], B, S, dtype, device=self.dev, precision=precision)
             self.bank = FilterBank(B, S, S, self.dev)
             self.colored_b = torch.empty(B, 3, S, S, dtype=torch.uint8, device=self.dev)
             self.colored_b2 = torch.empty(B, 3, S, S, dtype=torch.uint8, device=self.dev)

@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from . import _lib, ops, resample
-from .ops import chan_storage, pad_to
+from .ops import Pair, chan_storage, pad_to
 from .unet import LaunchProgram, bn_affine
 
 SD = Dict[str, torch.Tensor]
@@ -38,12 +38,17 @@ class ZhangProgram(LaunchProgram):
     """Launch list of one Zhang generator for a fixed batch: x [B,256,256,8] (channel 0 = normalised L) -> ab
     float32 [B,256,256,2] (already multiplied by ab_norm = 110)."""
 
+    # blocks that run split-precision (hi + lo operands) unless the policy is 'fast': the first four blocks inject > 90 % of the
+    # 16-bit storage error of these BatchNorm-only stacks (nothing damps an early perturbation) for < 25 % of the FLOPs
+    X3_BLOCKS = ("model1", "model2", "model3", "model4")
+
     def __init__(self, sd: SD, name: str, batch: int, dtype: torch.dtype = torch.float16, device="cuda", keep_taps: bool = False,
-                 size: int = NET_SIZE):
+                 size: int = NET_SIZE, precision: Optional[str] = None):
         assert name in ("eccv16", "siggraph17")
         if size % 8 != 0:
             raise ValueError("the Zhang networks need an input size that is a multiple of 8")
-        super().__init__(sd, batch, size, dtype, device, keep_taps)
+        super().__init__(sd, batch, size, dtype, device, keep_taps, precision)
+        self.x3_early = self.precision != "fast"
         self.name = name
         self.x = self.buf(batch, size, size, 8, zero=True)
         self.ab = self.buf(batch, size, size, 2, dtype=torch.float32)
@@ -55,24 +60,30 @@ class ZhangProgram(LaunchProgram):
         (K = 3 rows x 8) + GEMM."""
         B, S, lib, hd = self.B, self.S, self.lib, self.hd
         Kp = 24
-        col = self.buf(B, S, S, Kp, zero=True)
-        xp, cp = self.x.data_ptr(), col.data_ptr()
+        x3 = self.x3_early
+        col = Pair(self.buf(2, B, S, S, Kp, zero=True)) if x3 else self.buf(B, S, S, Kp, zero=True)
+        xp = self.x.data_ptr()
+        # split precision: channel 4 of x holds the lo part of the normalised L (havc_zhang_pre); a second im2col gathers it
+        jobs = [(0, col.hi.data_ptr()), (4, col.lo.data_ptr())] if x3 else [(0, col.data_ptr())]
 
         def im2col(stream):
-            _lib.check(lib.havc_im2col_small(xp, cp, B, S, S, 8, 0, 1, 3, 1, 1, Kp, hd, stream), name + ".im2col")
-        self.aux(name + ".im2col", im2col, nbytes=2.0 * B * S * S * (8 + Kp))
+            for c0, cp in jobs:
+                _lib.check(lib.havc_im2col_small(xp, cp, B, S, S, 8, c0, 1, 3, 1, 1, Kp, hd, stream), name + ".im2col")
+        self.aux(name + ".im2col", im2col, nbytes=2.0 * len(jobs) * B * S * S * (8 + Kp))
         cout = w.shape[0]
         wk = torch.zeros(cout, 3, 8)
         wk[:, :, :3] = w[:, 0]                                     # k = kh*8 + kw
-        y = self.conv(name, col, wk.reshape(cout, Kp, 1, 1), bias=b, relu1=relu)
+        y = self.conv(name, col, wk.reshape(cout, Kp, 1, 1), bias=b, relu1=relu, x3=x3)
         self.ops[-1].flops = 2.0 * B * S * S * cout * 9 * w.shape[1]
         return y
 
     def _block(self, name: str, spec, x, first_done=False, subsample_in=False):
         """conv -> ReLU (x n) -> BatchNorm; the BatchNorm is the scale/shift of the last conv's epilogue."""
         sd = self.sd
+        x3 = self.x3_early and name in self.X3_BLOCKS
         if subsample_in:                                           # siggraph17: conv on x[:, :, ::2, ::2]
-            x = self.phase_split(name + ".subsample", x, 1)[0]
+            ph = self.phase_split(name + ".subsample", x, 1)
+            x = ph.sub(0) if isinstance(ph, Pair) else ph[0]
         for i, (cout, stride, dil) in enumerate(spec):
             p = f"{name}.{2 * i}"
             last = i == len(spec) - 1
@@ -85,9 +96,9 @@ class ZhangProgram(LaunchProgram):
                 continue
             if stride == 2:
                 ph = self.phase_split(p + ".split", x, 4)
-                x = self.conv(p, ph, w, ks=3, stride=2, bias=b, relu1=True, scale=sc, shift=sh)
+                x = self.conv(p, ph, w, ks=3, stride=2, bias=b, relu1=True, scale=sc, shift=sh, x3=x3)
             else:
-                x = self.conv(p, x, w, ks=3, dilation=dil, bias=b, relu1=True, scale=sc, shift=sh)
+                x = self.conv(p, x, w, ks=3, dilation=dil, bias=b, relu1=True, scale=sc, shift=sh, x3=x3)
         self.tap(name, x)
         return x
 
@@ -190,9 +201,10 @@ class ZhangProgram(LaunchProgram):
 class ZhangColorizer:
     """ModelColorization.colorize_frame on a device batch: planar u8 RGB [B,3,S,S] in -> planar u8 RGB [B,3,S,S] out."""
 
-    def __init__(self, sd: SD, name: str, batch: int, size: int, dtype=torch.float16, device="cuda", keep_taps=False):
+    def __init__(self, sd: SD, name: str, batch: int, size: int, dtype=torch.float16, device="cuda", keep_taps=False,
+                 precision: Optional[str] = None):
         self.B, self.S, self.dev = batch, size, torch.device(device)
-        self.prog = ZhangProgram(sd, name, batch, dtype, device=self.dev, keep_taps=keep_taps)
+        self.prog = ZhangProgram(sd, name, batch, dtype, device=self.dev, keep_taps=keep_taps, precision=precision)
         self.lib, self.hd = self.prog.lib, self.prog.hd
         u8 = dict(dtype=torch.uint8, device=self.dev)
         self.resize = size != NET_SIZE
