@@ -434,16 +434,30 @@ def vs_merge(a: np.ndarray, b: np.ndarray, weight: float) -> np.ndarray:
     return (ai + (((bi - ai) * w15 + (1 << 14)) >> 15)).astype(np.uint8)
 
 
-def chroma_retention_merge(a, b, sat=0.8, tht=30, weight=0.9, alpha=2.0, mask_weight=0.0, algo=0):
-    """ChromaRetentionMerge with chroma_resize=False (mcomb.py:450-516) -> vs_sc_recover_gradient_color
-    (vsfilters.py:366-422) -> vs_simple_merge (vsfilters.py:730-739)."""
+def chroma_retention_merge(a, b, sat=0.8, tht=30, weight=0.9, alpha=2.0, mask_weight=0.0, algo=0, chroma_resize=False):
+    """ChromaRetentionMerge (mcomb.py:450-516) -> vs_sc_recover_gradient_color (vsfilters.py:366-422) -> vs_simple_merge
+    (vsfilters.py:730-739).  chroma_resize=True (mcomb.py:481-512): both clips are squeezed to frame_size x frame_size with
+    Spline64 first (frame_size from 0.4 * width, 16 <= rf <= 48; only if that is a downscale), the restore runs there (its
+    frame-luma gate too), the result goes back with Spline64 and takes the luma of clip_a (vs_sc_recover_clip_luma)."""
+    import math
+    from . import pixel_oracle as px
     alpha = max(min(alpha, 10.0), 1.0)                      # DEF_MAX/MIN_COLOR_ALPHA (constants.py)
+    H, W = a.shape[:2]
+    ca, cb = a, b
+    if chroma_resize:
+        fs = min(min(max(math.trunc(0.4 * W / 16), 16), 48) * 16, W)
+        if fs < W:
+            ca, cb = px.resize_plane_u8(a, fs, fs, "spline64"), px.resize_plane_u8(b, fs, fs, "spline64")
+        else:
+            chroma_resize = False
     w = mask_weight
-    luma = get_image_luma(a, 255)
+    luma = get_image_luma(ca, 255)
     if not (DEF_STANDARD_DARK <= luma <= DEF_STANDARD_BRIGHT):
         w = min(w, -0.5)
         alpha = max(alpha, 4.0)
-    restored = restore_color_gradient(b, a, sat, tht, w, alpha, algo)
+    restored = restore_color_gradient(cb, ca, sat, tht, w, alpha, algo)
+    if chroma_resize:
+        restored = px.chroma_post_process(px.resize_plane_u8(restored, W, H, "spline64"), a)
     return vs_merge(a, restored, weight)
 
 
@@ -463,9 +477,7 @@ def combine_models(a, b, method: int, weight: float, cmc_p=(0.15, True, 20, 24),
     if method == 5:
         return adaptive_luma_merge(a, b, alm_p[0], alm_p[1], weight, alm_p[2])
     if method == 6:
-        if crt_p[3]:
-            raise NotImplementedError("chroma_resize=True needs the Spline64 resize pair")
-        return chroma_retention_merge(a, b, crt_p[0], crt_p[1], weight, crt_p[2], crt_p[4], crt_p[5])
+        return chroma_retention_merge(a, b, crt_p[0], crt_p[1], weight, crt_p[2], crt_p[4], crt_p[5], chroma_resize=bool(crt_p[3]))
     if method == 7:
         red, base_tol, max_extra = (cmc_p[1], cmc_p[2], cmc_p[3]) if len(cmc_p) > 1 else (True, 20, 24)
         return chroma_bound_adaptive_merge(a, b, red, base_tol, max_extra, weight)

@@ -31,13 +31,15 @@ def net_output_square(sd, rgb_sq: np.ndarray) -> np.ndarray:
 def havc_colorizer_frame(sd, frame: np.ndarray, render_factor: int = 24, kernel: str = "spline64",
                          return_stages: bool = False, skip: bool = False, sd_other=None, video_weight: float = 0.5,
                          zhang=None, method: int = 0, merge_weight: float = 0.4, hue_adjust: str = "none", cmc_p=None,
-                         lmm_p=None, alm_p=None, crt_p=None, invert: bool = False, ddtweak=None, frame_size=None):
+                         lmm_p=None, alm_p=None, crt_p=None, invert: bool = False, ddtweak=None, frame_size=None, memo=None):
     """frame: uint8 [H,W,3].  Returns uint8 [H,W,3] (and the intermediate stages on request).
     skip: the scene-change gate returned the squeezed frame unchanged (vsslib/vsmodels.py:221-224).
     sd_other: 'stable'/'artistic' generator blended with the video one at S x S (visualize.py:118-137).
     zhang = (name, state_dict): second colour model (vs_sc_ddcolor models 2/3, vsmodels.py:339-344) with its hue
     adjustment (vsmodels.py:361-362), merged by vs_sc_combine_models(method, merge_weight, ...) (mcomb.py:125-192);
-    method 1 = second model only."""
+    method 1 = second model only.
+    memo: optional dict that keeps the expensive stages of THIS frame (squeeze, generator results, second model) so that
+    several merge methods can be checked against one set of network evaluations."""
     from . import filters_oracle as fo
     from . import zhang_oracle
     H, W = frame.shape[:2]
@@ -46,12 +48,19 @@ def havc_colorizer_frame(sd, frame: np.ndarray, render_factor: int = 24, kernel:
     S = min(render_factor * 16, W) if frame_size is None else frame_size
     N = render_factor * 16
 
+    memo = memo if memo is not None else {}
+
+    def cached(key, fn):
+        if key not in memo:
+            memo[key] = fn()
+        return memo[key]
+
     def deoldify(sd_):
         if N == S:
-            return px.chroma_post_process(model_process_square(sd_, small), small)   # _scale_to_square is the identity
-        return colorizer_filter(sd_, small, render_factor)
+            return cached(("deoldify", id(sd_)), lambda: px.chroma_post_process(model_process_square(sd_, small), small))
+        return cached(("deoldify", id(sd_)), lambda: colorizer_filter(sd_, small, render_factor))
 
-    small = px.resize_plane_u8(frame, S, S, kernel)                   # clip.resize.Spline64(S, S)
+    small = cached("small", lambda: px.resize_plane_u8(frame, S, S, kernel))   # clip.resize.Spline64(S, S)
     if skip:
         colored = small
     else:
@@ -67,7 +76,7 @@ def havc_colorizer_frame(sd, frame: np.ndarray, render_factor: int = 24, kernel:
                     src_b = fo.image_tweak(src_b, cont=ddtweak["cont"], bright=ddtweak["bright"])
                 src_b = fo.luma_adjusted_levels(src_b, ddtweak["luma_min"], ddtweak["gamma"], ddtweak["gamma_luma_min"],
                                                 ddtweak["gamma_alpha"], ddtweak["gamma_min"])
-            clipb = zhang_oracle.colorize_frame(zhang[1], zhang[0], src_b)
+            clipb = cached(("zhang", zhang[0], ddtweak is not None), lambda: zhang_oracle.colorize_frame(zhang[1], zhang[0], src_b))
             clipb = fo.adjust_hue_range(clipb, hue_adjust)
             if ddtweak is not None:            # vs_recover_clip_luma(clip, clipb_rgb) (vsmodels.py:367-368)
                 clipb = px.chroma_post_process(clipb, small)

@@ -107,6 +107,44 @@ def golden_render_narrow():
     np.savez_compressed(os.path.join(HERE, "model_image_render_narrow.npz"), **out)
 
 
+def golden_cfg1():
+    """BASELINE.json configs[0]: the reference's ModelImageRender('video', render_factor=24) on the 23 test_images/*.jpg stills
+    (1090 x 767), torch CPU, synthetic weights seed 1234.  The fixture holds the original JPEG bytes (the GPU box has no
+    /root/reference) and the reference's output sampled at every third pixel in both directions (1/9 of the values: the full
+    outputs would be 57 MB): tests/golden/cfg1_stills.npz."""
+    refshim.install()
+    import glob
+    import io
+    import vsdeoldify.deoldify.generators as gen
+    from vsdeoldify.fastai.vision.learner import create_body as _cb
+    gen.create_body = lambda arch, pretrained=True, cut=None: _cb(arch, False, cut)   # no network
+    from vsdeoldify.deoldify import device
+    from vsdeoldify.deoldify.device_id import DeviceId
+    device.set(device=DeviceId.CPU)
+    from PIL import Image
+    from vsdeoldify.deoldify.visualize import ModelImageRender
+    files = sorted(glob.glob("/root/reference/test_images/Image_*_test.jpg"))
+    assert len(files) == 23
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        os.makedirs(os.path.join(tmp, "models"))
+        torch.save(synth_weights.make_unet_state_dict("wide", 1234), os.path.join(tmp, "models", "ColorizeVideo_gen.pth"))
+        cwd = os.getcwd()
+        os.chdir(tmp)
+        try:
+            r = ModelImageRender(package_dir=tmp, modelname="video", render_factor=24, video_weight=0.5)
+            for k, f in enumerate(files):
+                raw = open(f, "rb").read()
+                img = Image.open(io.BytesIO(raw)).convert("RGB")
+                res = np.asarray(r.get_transformed_image(img))
+                out[f"jpeg_{k:02d}"] = np.frombuffer(raw, np.uint8)
+                out[f"ref_{k:02d}"] = np.ascontiguousarray(res[::3, ::3])
+                print(os.path.basename(f), res.shape, "done")
+        finally:
+            os.chdir(cwd)
+    np.savez_compressed(os.path.join(HERE, "cfg1_stills.npz"), **out)
+
+
 def golden_pixels():
     """Reference vsslib helpers that import without VapourSynth (imfilters/nputils)."""
     refshim.install()

@@ -204,3 +204,27 @@ def test_stabilizer_chain_vs_oracle(sbank):
         for li, r in enumerate(hwc(out)):
             same(r, fo.stabilizer_stages(imgs[li], **kw), f"{kw} frame {li}")
     assert not sbank.stabilizer_stages(t, out)            # nothing enabled: identity, `out` untouched
+
+
+def test_chroma_retention_merge_with_chroma_resize():
+    """ChromaRetentionMerge(chroma_resize=True) (mcomb.py:481-512): Spline64 squeeze of both clips to 256 x 256 (0.4 * 320 / 16
+    -> rf 16), gradient colour restore there, Spline64 back + luma of clip_a, std.Merge.  The float resize passes are not
+    bit-pinned (zimg absent), so the comparison with the oracle allows isolated rounding ties of the resize."""
+    from oracle import metrics, synth_weights
+    from vsdeoldify_b200.filters import FilterBank
+    H, W, B = 300, 320, 2
+    color = lambda seed: np.stack([synth_weights.make_test_frame(seed + c, H, W).numpy() for c in range(3)], -1)
+    a = [color(400 + 10 * i) for i in range(B)]
+    b = [color(500 + 10 * i) for i in range(B)]
+    a[1] = (a[1] // 6).astype(np.uint8)                                    # a dark frame: the luma gate (vsfilters.py:403-409) fires
+    bank = FilterBank(B, H, W, "cuda:0")
+    ta, tb = planar(a), planar(b)
+    out = torch.empty_like(ta)
+    for w, crt in ((0.7, [0.8, 30, 2.0, True, 0.0, 0]), (1.0, [0.6, 40, 3.0, True, -0.3, 1])):
+        bank.combine(ta, tb, out, 6, w, crt_p=crt)
+        torch.cuda.synchronize()
+        for li, r in enumerate(hwc(out)):
+            want = fo.combine_models(a[li], b[li], 6, w, crt_p=crt)
+            m = metrics.frame_parity(r, want)
+            assert m["mean_de00"] < 0.02 and m["n_err_gt2"] <= 2e-4 * m["n_values"], (w, crt, li, m)
+            assert np.abs(r.astype(int) - a[li].astype(int)).max() > 4, "the merge must change clip_a"

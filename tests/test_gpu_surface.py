@@ -245,3 +245,67 @@ def test_colorizer_ddtweak_inverted_merge(zmodel, zname, gate):
         img = np.stack([np.asarray(f[p]) for p in range(3)], -1)
         m = metrics.frame_parity(img, ref)
         assert m["mean_de00"] <= gate, (zname, i, m)
+
+
+def test_multi_gpu_sharded_clip_matches_single_gpu():
+    """HAVC_colorizer(device_index=[0, 1]) (vsdeoldify_b200/sharded.py): one engine + worker per GPU, the clip's frames
+    partitioned over them, delivered in order with their props; bytes equal the single-GPU clip for every frame, for the block
+    and the interleaved partition and for out-of-order requests.  Needs two visible GPUs."""
+    import os
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    havc = _register()
+    H, W, rf, n = 96, 128, 4, 23
+    old_batch = havc._BATCH
+    havc._BATCH = 4
+    try:
+        clip, fr, props = _clip(n, H, W, seed=310)
+        single = havc.HAVC_colorizer(clip, method=0, deoldify_p=[0, rf, 1.0, 0.0])
+        want = [np.stack([np.asarray(single.get_frame(i)[p]) for p in range(3)]) for i in range(n)]
+        for part in ("interleaved", "block"):
+            os.environ["HAVC_B200_PARTITION"] = part
+            multi = havc.HAVC_colorizer(clip, method=0, deoldify_p=[0, rf, 1.0, 0.0], device_index=[0, 1])
+            for i in list(range(n)) + [5, 22, 0, 13]:
+                f = multi.get_frame(i)
+                assert f.props == props[i], (part, i)
+                assert np.array_equal(np.stack([np.asarray(f[p]) for p in range(3)]), want[i]), (part, i)
+    finally:
+        havc._BATCH = old_batch
+        os.environ.pop("HAVC_B200_PARTITION", None)
+
+
+def test_havc_merge_with_clip_luma():
+    """HAVC_merge(clipa, clipb, clip_luma) (vsdeoldify/__init__.py:2633-2675): methods 3..7 squeeze both clips to
+    frame_size x frame_size (from 0.4 * clip_luma.width), merge there and go through _clip_chroma_resize(clip_luma, .);
+    methods 0 / 1 are _clip_chroma_resize of one clip.  Output frames are clip_luma's frames (props included) with the
+    scene-detection props of the merged clip (CopySCDetect)."""
+    from oracle import filters_oracle as fo, metrics, pixel_oracle as px, synth_weights
+    from vsdeoldify_b200 import havc, vs_shim
+    n, (Ha, Wa), (H, W) = 3, (120, 176), (288, 704)
+    color = lambda seed, h, w: np.stack([synth_weights.make_test_frame(seed + c, h, w).numpy() for c in range(3)])
+    fa = np.stack([color(600 + 5 * i, Ha, Wa) for i in range(n)])
+    fb = np.stack([color(700 + 5 * i, Ha, Wa) for i in range(n)])
+    fl = np.stack([color(800 + 5 * i, H, W) for i in range(n)])
+    pa = [{"_SceneChangePrev": int(i == 1), "who": "a"} for i in range(n)]
+    pl = [{"who": "luma", "idx": i} for i in range(n)]
+    ca, cb, cl = vs_shim.array_clip(fa, props=pa), vs_shim.array_clip(fb), vs_shim.array_clip(fl, props=pl)
+    hwc = lambda x: np.ascontiguousarray(np.transpose(x, (1, 2, 0)))
+    fs = min(min(max(int(0.4 * W / 16), 16), 32) * 16, W)
+    assert fs == 272
+    for method, weight in ((3, 0.5), (5, 0.4), (0, 0.5), (1, 0.5)):
+        out = havc.HAVC_merge(ca, cb, clip_luma=cl, weight=weight, method=method)
+        assert (out.width, out.height) == (W, H)
+        for i in range(n):
+            f = out.get_frame(i)
+            assert f.props["who"] == "luma" and f.props["idx"] == i
+            if method != 1:                                       # CopySCDetect from the merged clip (= clipa's props)
+                assert f.props.get("_SceneChangePrev") == pa[i]["_SceneChangePrev"]
+            if method in (0, 1):
+                low = hwc((fa if method == 0 else fb)[i])
+            else:
+                low = fo.combine_models(px.resize_plane_u8(hwc(fa[i]), fs, fs), px.resize_plane_u8(hwc(fb[i]), fs, fs), method, weight)
+            want = px.chroma_post_process(px.resize_plane_u8(low, W, H), hwc(fl[i]))
+            got = np.stack([np.asarray(f[p]) for p in range(3)], -1)
+            m = metrics.frame_parity(got, want)
+            assert m["mean_de00"] < 0.02 and m["n_err_gt2"] <= 2e-4 * m["n_values"], (method, i, m)

@@ -197,3 +197,32 @@ def test_clip_adapter_recycles_only_unreferenced_result_arrays():
     del v
     assert id(c._result_buf()) == first       # free again -> recycled, no new allocation
     assert len(c._bufs) == 2
+
+
+def test_legacy_spectral_norm_state_dict_folds_like_torch():
+    """Spectral-norm state-dicts written before torch 1.0 (version < 1) hold `weight`, `weight_orig`, `weight_u` and no
+    `weight_v`; torch's load hook (spectral_norm.py `_load_from_state_dict` -> `_solve_v_and_rescale`) derives v so that the
+    eval weight is weight_orig / mean(weight_orig / weight).  folded_weight must agree with what torch itself loads."""
+    import torch
+    from torch import nn
+    from vsdeoldify_b200.unet import folded_weight
+    torch.manual_seed(5)
+    conv = nn.utils.spectral_norm(nn.Conv2d(12, 20, 3, bias=False))
+    conv.train()
+    for _ in range(6):
+        conv(torch.randn(2, 12, 8, 8))                       # power iterations: u, v converge, weight = weight_orig / sigma
+    conv.eval()
+    w_eff = conv(torch.zeros(1, 12, 8, 8)) is not None and conv.weight.detach().clone()
+    sd_new = {"c." + k: v.clone() for k, v in conv.state_dict().items()}
+    assert torch.allclose(folded_weight(sd_new, "c"), w_eff, atol=1e-6)
+    # legacy schema: drop weight_v, add the materialised weight
+    legacy = {k: v for k, v in sd_new.items() if not k.endswith("weight_v")}
+    legacy["c.weight"] = w_eff.clone()
+    got = folded_weight(legacy, "c")
+    # what torch loads from the same legacy dict (no version metadata -> the version < 1 branch)
+    conv2 = nn.utils.spectral_norm(nn.Conv2d(12, 20, 3, bias=False))
+    conv2.load_state_dict({k[2:]: v for k, v in legacy.items()})
+    conv2.eval()
+    conv2(torch.zeros(1, 12, 8, 8))
+    assert torch.allclose(got, conv2.weight.detach(), atol=1e-5, rtol=1e-4)
+    assert torch.allclose(got, w_eff, atol=1e-5, rtol=1e-4)

@@ -121,15 +121,31 @@ class DeoldifyEngine:
         self._warm()
 
     # ---- launch list ------------------------------------------------------------------------------
-    def _launch(self, slot: int, stream: int):
-        lib, B, S, W, H = self.lib, self.B, self.S, self.W, self.H
-        skip = self.skip_slots[slot]
-        chk = _lib.check
-        td, tv, uh, uv = self.t_down_h, self.t_down_v, self.t_up_h, self.t_up_v
+    def _launch_pre(self, slot: int, stream: int):
+        """clip.resize.Spline64(S, S) (vsdeoldify/__init__.py:2504) fused with the gray transform + normalisation of the filter."""
+        lib, B, S, W, H, chk = self.lib, self.B, self.S, self.W, self.H, _lib.check
+        td, tv = self.t_down_h, self.t_down_v
         chk(lib.havc_resample_h(self.d_in[slot].data_ptr(), self.tmp_down.data_ptr(), B * 3 * H, W, S,
                                 td.start.data_ptr(), td.wt.data_ptr(), td.taps, stream), "pre.h")
         chk(lib.havc_pre_vertical(self.tmp_down.data_ptr(), self.rgb_small.data_ptr(), self.x_in.data_ptr(), B, H, S,
                                   tv.start.data_ptr(), tv.w.data_ptr(), tv.taps, self.hd, stream), "pre.v")
+
+    def _launch_post(self, slot: int, stream: int, result=None):
+        """_clip_chroma_resize (vsdeoldify/__init__.py:3545-3554): Spline64 back to W x H + full-resolution luma transplant;
+        the vertical pass runs on the S-wide image first, then the wide horizontal pass from shared memory."""
+        lib, B, S, W, H, chk = self.lib, self.B, self.S, self.W, self.H, _lib.check
+        uh, uv = self.t_up_h, self.t_up_v
+        result = result if result is not None else self.colored
+        chk(lib.havc_resample_v(result.data_ptr(), self.tmp_up.data_ptr(), B * 3, S, H, S,
+                                uv.start.data_ptr(), uv.w.data_ptr(), uv.taps, stream), "post.v")
+        chk(lib.havc_post_horizontal(self.tmp_up.data_ptr(), self.d_in[slot].data_ptr(), self.d_out[slot].data_ptr(), B, S,
+                                     H, W, uh.start.data_ptr(), uh.wt.data_ptr(), uh.taps, 1, stream), "post.h")
+
+    def _launch(self, slot: int, stream: int):
+        lib, B, S, W, H = self.lib, self.B, self.S, self.W, self.H
+        skip = self.skip_slots[slot]
+        chk = _lib.check
+        self._launch_pre(slot, stream)
         result = self.colored
         if self.run_deoldify and not self.rescale:
             self.prog.run(stream)
@@ -181,11 +197,7 @@ class DeoldifyEngine:
                                   stream=stream)
                 self.bank.select_frames(self.merged, a, skip, stream)           # merge selectors return f[0].copy()
                 result = self.merged
-        # back to W x H: vertical pass on the S-wide image first, then the wide horizontal pass from shared memory
-        chk(lib.havc_resample_v(result.data_ptr(), self.tmp_up.data_ptr(), B * 3, S, H, S,
-                                uv.start.data_ptr(), uv.w.data_ptr(), uv.taps, stream), "post.v")
-        chk(lib.havc_post_horizontal(self.tmp_up.data_ptr(), self.d_in[slot].data_ptr(), self.d_out[slot].data_ptr(), B, S,
-                                     H, W, uh.start.data_ptr(), uh.wt.data_ptr(), uh.taps, 1, stream), "post.h")
+        self._launch_post(slot, stream, result)
 
     # ---- frame_size != render_factor*16: the filter's own Pillow BILINEAR stretch around the generator ---------------
     def _pil(self, src, tmp, dst, Hin, Win, out_size, tabs, stream):

@@ -110,6 +110,44 @@ def gradient_mask_lut(tht: int, alpha: float, algo: int) -> np.ndarray:
     return np.clip(norm * 255, 0, 255).astype(np.uint8)
 
 
+class SquareSqueeze:
+    """clip.resize.Spline64(width=S, height=S) of planar u8 batches [B,3,H,W] and the way back with the luma transplant
+    (_clip_chroma_resize, vsdeoldify/__init__.py:3545-3554 = Spline64 to W x H + vs_recover_clip_luma): the table-driven
+    separable passes of the frame pre / post pipeline, reused by ChromaRetentionMerge(chroma_resize=True) (mcomb.py:481-512)
+    and HAVC_merge(clip_luma=...) (vsdeoldify/__init__.py:2660-2673)."""
+
+    def __init__(self, B: int, H: int, W: int, S: int, device, kernel: str = "spline64", out_hw: Optional[Tuple[int, int]] = None):
+        from .engine import _Tables
+        self.lib, self.B, self.H, self.W, self.S = _lib.lib(), B, H, W, S
+        self.dev = torch.device(device)
+        self.OH, self.OW = out_hw if out_hw is not None else (H, W)          # size of the way back (the luma clip's)
+        self.t_down_h, self.t_down_v = _Tables(W, S, kernel, self.dev), _Tables(H, S, kernel, self.dev)
+        self.t_up_h, self.t_up_v = _Tables(S, self.OW, kernel, self.dev), _Tables(S, self.OH, kernel, self.dev)
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        self.tmp_down = torch.empty(B, 3, H, S, **f32)
+        self.tmp_up = torch.empty(B, 3, self.OH, S, **f32)
+        self.x_scratch = torch.empty(B, S, S, 8, dtype=torch.float16, device=self.dev)     # pre_vertical's network-input by-product
+
+    def down(self, src, dst, stream: int = 0):
+        """src u8 [B,3,H,W] -> dst u8 [B,3,S,S]."""
+        lib, B, H, W, S, chk = self.lib, self.B, self.H, self.W, self.S, _lib.check
+        td, tv = self.t_down_h, self.t_down_v
+        chk(lib.havc_resample_h(src.data_ptr(), self.tmp_down.data_ptr(), B * 3 * H, W, S, td.start.data_ptr(), td.wt.data_ptr(),
+                                td.taps, stream), "squeeze.h")
+        chk(lib.havc_pre_vertical(self.tmp_down.data_ptr(), dst.data_ptr(), self.x_scratch.data_ptr(), B, H, S, tv.start.data_ptr(),
+                                  tv.w.data_ptr(), tv.taps, 0, stream), "squeeze.v")
+
+    def up(self, src, luma, dst, stream: int = 0, transplant: bool = True):
+        """src u8 [B,3,S,S] -> dst u8 [B,3,OH,OW], keeping the luma of `luma` (same size as dst) when transplant."""
+        lib, B, S, chk = self.lib, self.B, self.S, _lib.check
+        uh, uv = self.t_up_h, self.t_up_v
+        chk(lib.havc_resample_v(src.data_ptr(), self.tmp_up.data_ptr(), B * 3, S, self.OH, S, uv.start.data_ptr(), uv.w.data_ptr(),
+                                uv.taps, stream), "unsqueeze.v")
+        chk(lib.havc_post_horizontal(self.tmp_up.data_ptr(), luma.data_ptr() if luma is not None else None, dst.data_ptr(), B, S,
+                                     self.OH, self.OW, uh.start.data_ptr(), uh.wt.data_ptr(), uh.taps, int(transplant), stream),
+            "unsqueeze.h")
+
+
 class FilterBank:
     """Scratch buffers + launch sequencing for one (B, H, W) on one device."""
 
@@ -192,9 +230,12 @@ class FilterBank:
             return
         if method == 6:                                            # ChromaRetentionMerge
             sat, tht, alpha, resize, mask_weight, algo = crt_p[0], crt_p[1], crt_p[2], crt_p[3], crt_p[4], crt_p[5]
-            if resize:
-                raise FilterError("ChromaRetentionMerge with chroma_resize=True (Spline64 down/up) is not built")
             alpha = max(min(alpha, DEF_MAX_COLOR_ALPHA), DEF_MIN_COLOR_ALPHA)
+            if resize:                                             # mcomb.py:481-493: work on a Spline64-squeezed copy
+                import math
+                fs = min(min(max(math.trunc(0.4 * W / 16), 16), 48) * 16, W)
+                if fs < W:                                         # "sanity check, avoid upscale"
+                    return self._crt_resized(a, b, out, fs, sat, tht, alpha, mask_weight, algo, weight, stream)
             self.frame_stats(a, self.stats[0], stream)
             lut, lut_g = self._lut(tht, alpha, algo), self._lut(tht, max(alpha, 4.0), algo)
             if weight == 0:                                        # vs_simple_merge (vsfilters.py:730-739) returns clipa
@@ -206,6 +247,33 @@ class FilterBank:
                        "restore_color_gradient")
             return
         raise FilterError("HAVC: only dd_method in (0,6) is supported")          # mcomb.py:192
+
+    def _crt_resized(self, a, b, out, fs, sat, tht, alpha, mask_weight, algo, weight, stream):
+        """ChromaRetentionMerge(chroma_resize=True) (mcomb.py:481-512): both clips squeezed to fs x fs with Spline64, gradient
+        colour restore there (frame-luma gate included, on the squeezed frame), Spline64 back, luma of clip_a recovered
+        (vs_sc_recover_clip_luma), then std.Merge(clip_a, restored, weight)."""
+        if weight == 0:
+            return self.blend(a, a, out, 0.0, stream)
+        key = ("crt", fs)
+        if key not in self._luts:
+            sq = SquareSqueeze(self.B, self.H, self.W, fs, self.dev)
+            u8 = dict(dtype=torch.uint8, device=self.dev)
+            small = [torch.empty(self.B, 3, fs, fs, **u8) for _ in range(3)]
+            self._luts[key] = (sq, small, torch.zeros(self.B, 2, dtype=torch.int64, device=self.dev))
+        sq, (sa, sb, sr), stats = self._luts[key]
+        lib, B = self.lib, self.B
+        sq.down(a, sa, stream)
+        sq.down(b, sb, stream)
+        _lib.check(lib.havc_frame_stats(sa.data_ptr(), B, fs, fs, 1.0, stats.data_ptr(), stream), "frame_stats")
+        lut, lut_g = self._lut(tht, alpha, algo), self._lut(tht, max(alpha, 4.0), algo)
+        _lib.check(lib.havc_restore_color_gradient(sb.data_ptr(), sa.data_ptr(), sr.data_ptr(), B, fs, fs, float(sat), lut.data_ptr(),
+                                                   lut_g.data_ptr(), float(mask_weight), float(min(mask_weight, -0.5)),
+                                                   stats.data_ptr(), -1.0, self.simd, stream), "restore_color_gradient")
+        restored = out if weight == 1 else self.tmp[0]
+        sq.up(sr, a, restored, stream, transplant=True)
+        if weight != 1:
+            _lib.check(lib.havc_vs_merge_u8(a.data_ptr(), restored.data_ptr(), out.data_ptr(), out.numel(), float(weight), stream),
+                       "vs_merge")
 
     # ---- chroma-adjust filters ------------------------------------------------------------------------------
     def adjust_hue_range(self, img, out, hue_adjust: str, stream: int = 0) -> bool:
@@ -347,6 +415,62 @@ class MergeEngine:
             self.h_out.copy_(self.d_out, non_blocking=True)
         self.stream.synchronize()
         return self.h_out[:n].numpy().copy()
+
+
+class LumaMergeEngine:
+    """HAVC_merge(clipa, clipb, clip_luma=...) (vsdeoldify/__init__.py:2633-2675) on host batches:
+      methods 3..7: clipa / clipb are squeezed to frame_size x frame_size with Spline64 (frame_size from 0.4 * clip_luma.width,
+                    :2661-2664), merged there by vs_combine_models, and the result goes through _clip_chroma_resize(clip_luma, .)
+                    (:2670-2673): Spline64 to clip_luma's size + the luma of clip_luma;
+      methods 0 / 1 (or weight 0 / 1): _clip_chroma_resize(clip_luma, clipa | clipb) alone."""
+
+    def __init__(self, ab_size: Tuple[int, int], luma_size: Tuple[int, int], squeeze: bool, batch: int = 8, device: str = "cuda:0"):
+        import math
+        self.dev = torch.device(device)
+        torch.cuda.set_device(self.dev)
+        (self.Wab, self.Hab), (self.W, self.H), self.B = ab_size, luma_size, batch
+        self.lib = _lib.lib()
+        u8 = dict(dtype=torch.uint8, device=self.dev)
+        B = batch
+        self.d_a, self.d_b = (torch.empty(B, 3, self.Hab, self.Wab, **u8) for _ in range(2))
+        self.d_luma, self.d_out = (torch.empty(B, 3, self.H, self.W, **u8) for _ in range(2))
+        self.squeeze = squeeze
+        if squeeze:
+            rf = min(max(math.trunc(0.4 * self.W / 16), 16), 32)
+            self.S = min(rf * 16, self.W)
+            self.sq = SquareSqueeze(B, self.Hab, self.Wab, self.S, self.dev, out_hw=(self.H, self.W))
+            self.bank = FilterBank(B, self.S, self.S, self.dev)
+            self.small = [torch.empty(B, 3, self.S, self.S, **u8) for _ in range(3)]
+        else:       # plain Spline64 resize of one clip to clip_luma's size: vertical pass, then horizontal pass + transplant
+            from .engine import _Tables
+            self.t_v, self.t_h = _Tables(self.Hab, self.H, "spline64", self.dev), _Tables(self.Wab, self.W, "spline64", self.dev)
+            self.tmp = torch.empty(B, 3, self.H, self.Wab, dtype=torch.float32, device=self.dev)
+        self.stream = torch.cuda.Stream(device=self.dev)
+
+    def merge_batch(self, a, b, luma, method: int, weight: float, cmc_p=DEF_CMC_p, lmm_p=DEF_LMM_p, alm_p=DEF_ALM_p, crt_p=DEF_CRT_p):
+        """a / b: uint8 [n, 3, Hab, Wab] (one of them may be None when not squeezing), luma: uint8 [n, 3, H, W]."""
+        n = luma.shape[0]
+        lib, B, chk = self.lib, self.B, _lib.check
+        up = lambda t, x: t[:n].copy_(torch.from_numpy(np.ascontiguousarray(x)), non_blocking=True)
+        with torch.cuda.stream(self.stream):
+            st = self.stream.cuda_stream
+            up(self.d_luma, luma)
+            if self.squeeze:
+                up(self.d_a, a), up(self.d_b, b)
+                self.sq.down(self.d_a, self.small[0], st)
+                self.sq.down(self.d_b, self.small[1], st)
+                self.bank.combine(self.small[0], self.small[1], self.small[2], method, weight, cmc_p, lmm_p, alm_p, crt_p, stream=st)
+                self.sq.up(self.small[2], self.d_luma, self.d_out, st, transplant=True)
+            else:
+                src = self.d_a
+                up(src, a if a is not None else b)
+                chk(lib.havc_resample_v(src.data_ptr(), self.tmp.data_ptr(), B * 3, self.Hab, self.H, self.Wab, self.t_v.start.data_ptr(),
+                                        self.t_v.w.data_ptr(), self.t_v.taps, st), "resize.v")
+                chk(lib.havc_post_horizontal(self.tmp.data_ptr(), self.d_luma.data_ptr(), self.d_out.data_ptr(), B, self.Wab, self.H, self.W,
+                                             self.t_h.start.data_ptr(), self.t_h.wt.data_ptr(), self.t_h.taps, 1, st), "resize.h")
+            out = self.d_out[:n].cpu()
+        self.stream.synchronize()
+        return out.numpy()
 
 
 class StabilizerEngine:

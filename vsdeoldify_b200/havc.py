@@ -82,6 +82,20 @@ def load_state_dict(weights_name: str, models_dir: str = model_dir) -> Dict[str,
     return state["model"] if isinstance(state, dict) and "model" in state else state
 
 
+def _engine_or_smaller_batch(cls, *args, batch: int, **kw):
+    """Build an engine; when the device runs out of memory (activations scale with batch x render_factor^2) halve the batch
+    down to 1, then give up (None): the caller applies the reference's out-of-memory convention."""
+    b = batch
+    while True:
+        try:
+            return cls(*args, batch=b, **kw)
+        except torch.cuda.OutOfMemoryError:
+            torch.cuda.empty_cache()
+            if b == 1:
+                return None
+            b = max(1, b // 2)
+
+
 class _ColorizedClip:
     """frame_fn of the output clip: batches source frames through the engine, caches results by frame number.
 
@@ -160,6 +174,20 @@ class _ColorizedClip:
         self._store(n, srcs, self.engine.collect(ticket, out=self._result_buf(), pool=_COPY_POOL))
 
     def __call__(self, n: int):
+        try:
+            return self._render(n)
+        except RuntimeError as e:
+            # deoldify/filters.py:55-63: an out-of-memory RuntimeError inside a frame is a warning and the frame comes back
+            # uncoloured; anything else propagates
+            if "memory" not in str(e).lower():
+                raise
+            vs.core.log_message(vs.MESSAGE_TYPE_WARNING, "Warning: render_factor was set too high, and out of memory error resulted. "
+                                                         "Returning original image.")
+            torch.cuda.empty_cache()
+            self.pending = None
+            return self.clip.get_frame(n).copy()
+
+    def _render(self, n: int):
         with self.lock:
             if n in self.cache:
                 return self.cache[n]
@@ -266,17 +294,23 @@ def HAVC_colorizer(
                      crt_p=list(crt_p), invert=bool(cmb_sw))
     from .filters import FilterError
     try:
-        engines = [DeoldifyEngine(sd_video, clip.width, clip.height, render_factor=deoldify_rf, frame_size=frame_size,
+        engines = [_engine_or_smaller_batch(DeoldifyEngine, sd_video, clip.width, clip.height, render_factor=deoldify_rf, frame_size=frame_size,
                                   batch=_BATCH, dtype=_DTYPE, device=f"cuda:{d}", sd_other=sd_other, video_weight=weight,
                                   zhang=zhang, merge=merge, hue_adjust=hue_adjust, run_deoldify=run_deoldify, ddtweak=tweak)
                    for d in devices]
     except (ValueError, FilterError) as e:
         _raise("HAVC_colorizer: " + str(e))
+    if any(e is None for e in engines):
+        # the reference's out-of-memory convention (deoldify/filters.py:55-63): warn and hand back uncoloured frames
+        vs.core.log_message(vs.MESSAGE_TYPE_WARNING, "Warning: render_factor was set too high, and out of memory error resulted. "
+                                                     "Returning original image.")
+        return clip
+    batch = min(e.B for e in engines)
     if len(engines) == 1:
-        fn = _ColorizedClip(clip, engines[0], scenechange, _BATCH)
+        fn = _ColorizedClip(clip, engines[0], scenechange, batch)
     else:
         from .sharded import ShardedRenderer
-        renderer = ShardedRenderer(clip, engines, _BATCH, scenechange, partition=os.environ.get("HAVC_B200_PARTITION", "interleaved"),
+        renderer = ShardedRenderer(clip, engines, batch, scenechange, partition=os.environ.get("HAVC_B200_PARTITION", "interleaved"),
                                    copy_pool=_COPY_POOL)
 
         def fn(n, renderer=renderer):
@@ -288,11 +322,18 @@ def HAVC_colorizer(
         if vs is vs_shim else _wrap_real_vs(clip, fn)
 
 
-class _MergedClip:
-    """frame_fn of HAVC_merge's output clip: pulls B consecutive frames of both clips, merges them on the GPU."""
+_SC_PROPS = ('_SceneChangePrev', '_SceneChangeNext', 'sc_threshold', 'sc_frequency', 'sc_luma', 'sc_ratio')    # CopySCDetect, vsscdect.py:118-120
 
-    def __init__(self, clipa, clipb, engine, batch, method, weight, cmc_p, lmm_p, alm_p, crt_p):
-        self.clipa, self.clipb, self.engine, self.B = clipa, clipb, engine, batch
+
+class _MergedClip:
+    """frame_fn of HAVC_merge's output clip: pulls B consecutive frames of the clips, merges them on the GPU.
+    Without clip_luma the output frames are copies of clipa's frames (the mcomb.py selectors return f[0].copy()); with clip_luma
+    they are copies of clip_luma's frames (_clip_chroma_resize -> vs_recover_clip_luma) that take the scene-detection props of
+    the merged / selected clip (CopySCDetect)."""
+
+    def __init__(self, clipa, clipb, engine, batch, method, weight, cmc_p, lmm_p, alm_p, crt_p, clip_luma=None, sc_src=None):
+        self.clipa, self.clipb, self.clip_luma, self.engine, self.B = clipa, clipb, clip_luma, engine, batch
+        self.sc_src = sc_src
         self.args = (method, weight, cmc_p, lmm_p, alm_p, crt_p)
         self.cache: "OrderedDict[int, object]" = OrderedDict()
         self.lock = threading.Lock()
@@ -301,15 +342,26 @@ class _MergedClip:
         with self.lock:
             if n in self.cache:
                 return self.cache[n]
-            n1 = min(n + self.B, self.clipa.num_frames)
-            fa = [self.clipa.get_frame(i) for i in range(n, n1)]
-            fb = [self.clipb.get_frame(i) for i in range(n, n1)]
+            base = self.clip_luma if self.clip_luma is not None else self.clipa
+            n1 = min(n + self.B, base.num_frames)
             stack = lambda fs: np.stack([np.stack([np.asarray(f[p]) for p in range(3)]) for f in fs])
-            out = self.engine.merge_batch(stack(fa), stack(fb), *self.args)
-            for i, f in zip(range(n, n1), fa):
-                g = f.copy()                              # props of clipa's frame survive (mcomb.py selectors return f[0].copy())
+            get = lambda c: [c.get_frame(i) for i in range(n, n1)] if c is not None else None
+            fa, fb = get(self.clipa), get(self.clipb)
+            if self.clip_luma is None:
+                out = self.engine.merge_batch(stack(fa), stack(fb), *self.args)
+                fbase, fsc = fa, None
+            else:
+                fl = get(self.clip_luma)
+                out = self.engine.merge_batch(stack(fa) if fa else None, stack(fb) if fb else None, stack(fl), *self.args)
+                fbase, fsc = fl, get(self.sc_src)
+            for k, (i, f) in enumerate(zip(range(n, n1), fbase)):
+                g = f.copy()                              # every prop of the base frame survives
                 for p in range(3):
                     np.copyto(np.asarray(g[p]), out[i - n, p])
+                if fsc is not None:
+                    for key in _SC_PROPS:
+                        if key in fsc[k].props:
+                            g.props[key] = fsc[k].props[key]
                 self.cache[i] = g
             while len(self.cache) > 4 * self.B:
                 self.cache.popitem(last=False)
@@ -319,38 +371,51 @@ class _MergedClip:
 def HAVC_merge(clipa=None, clipb=None, clip_luma=None, weight: float = 0.5, method: int = 2, cmc_p: Sequence = DEF_CMC_p,
                lmm_p: Sequence = DEF_LMM_p, alm_p: Sequence = DEF_ALM_p, crt_p: Sequence = DEF_CRT_p, device_index: int = 0):
     """Drop-in for vsdeoldify.HAVC_merge (vsdeoldify/__init__.py:2536-2675) on RGB24 clips: method 2 = std.Merge,
-    methods 3-7 = the vsslib merges of vs_combine_models.  `clip_luma` (the Spline64 squeeze + chroma-resize detour of
-    :2653-2673) and non-RGB24 formats (convert_format_RGB24 / restore_format) are not built and raise."""
+    methods 3-7 = the vsslib merges of vs_combine_models, `clip_luma` = the Spline64 squeeze + _clip_chroma_resize detour of
+    :2633-2673.  Non-RGB24 formats (convert_format_RGB24 / restore_format) raise."""
     for name, c in (("clipa", clipa), ("clipb", clipb), ("clip_luma", clip_luma)):
         if c is not None and not hasattr(c, "get_frame"):
             _raise("HAVC_merge: this is not a clip: " + name)                            # :2624-2631
-    if clip_luma is not None:
-        _raise("HAVC_merge: clip_luma is not handled by the B200 build yet")
-    if method == 0 or weight == 0:                                                        # :2633-2638
-        return clipa
-    if method == 1 or weight == 1:                                                        # :2640-2645
-        return clipb
     rgb24 = getattr(vs.RGB24, "id", vs.RGB24)
-    for c in (clipa, clipb):
-        if getattr(c.format, "id", c.format) != rgb24:
+    for c in (clipa, clipb, clip_luma):
+        if c is not None and getattr(c.format, "id", c.format) != rgb24:
             _raise("HAVC_merge: only RGB24 clips are handled by the B200 build (convert_format_RGB24 is a 'next' row)")
+    from .filters import FilterError, LumaMergeEngine, MergeEngine
+    args = (list(cmc_p), list(lmm_p), list(alm_p), list(crt_p))
+    mk = lambda fn, base: (vs_shim.VideoNode(base.num_frames, base.width, base.height, base.format, fn, base.fps_num, base.fps_den)
+                           if vs is vs_shim else _wrap_real_vs(base, fn))
+
+    def guarded(fn):
+        def call(n):
+            try:
+                return fn(n)
+            except FilterError as e:
+                _raise("HAVC_merge: " + str(e))
+        return call
+    if method == 0 or weight == 0 or method == 1 or weight == 1:                         # :2633-2645
+        sel = clipa if (method == 0 or weight == 0) else clipb
+        if clip_luma is None:
+            return sel
+        if not torch.cuda.is_available():
+            _raise("HAVC_merge: CUDA is not available")
+        eng = LumaMergeEngine((sel.width, sel.height), (clip_luma.width, clip_luma.height), False, batch=_BATCH,
+                              device=f"cuda:{device_index}")
+        fn = _MergedClip(sel, None, eng, _BATCH, 0, 0.0, *args, clip_luma=clip_luma, sc_src=sel)
+        return mk(guarded(fn), clip_luma)
     if (clipa.width, clipa.height) != (clipb.width, clipb.height):
         _raise("HAVC_merge: clipa and clipb must have the same size")
     if not torch.cuda.is_available():
         _raise("HAVC_merge: CUDA is not available")
     if method not in (2, 3, 4, 5, 6, 7):
         _raise("HAVC: only dd_method in (0,6) is supported")                              # mcomb.py:192
-    from .filters import FilterError, MergeEngine
-    engine = MergeEngine(clipa.width, clipa.height, batch=_BATCH, device=f"cuda:{device_index}")
-    fn = _MergedClip(clipa, clipb, engine, _BATCH, method, weight, list(cmc_p), list(lmm_p), list(alm_p), list(crt_p))
-
-    def guarded(n):
-        try:
-            return fn(n)
-        except FilterError as e:
-            _raise("HAVC_merge: " + str(e))
-    return vs_shim.VideoNode(clipa.num_frames, clipa.width, clipa.height, clipa.format, guarded, clipa.fps_num, clipa.fps_den) \
-        if vs is vs_shim else _wrap_real_vs(clipa, guarded)
+    if method == 2 or clip_luma is None:                                                  # :2648-2650: method 2 ignores clip_luma
+        engine = MergeEngine(clipa.width, clipa.height, batch=_BATCH, device=f"cuda:{device_index}")
+        fn = _MergedClip(clipa, clipb, engine, _BATCH, method, weight, *args)
+        return mk(guarded(fn), clipa)
+    eng = LumaMergeEngine((clipa.width, clipa.height), (clip_luma.width, clip_luma.height), True, batch=_BATCH,
+                          device=f"cuda:{device_index}")
+    fn = _MergedClip(clipa, clipb, eng, _BATCH, method, weight, *args, clip_luma=clip_luma, sc_src=clipa)
+    return mk(guarded(fn), clip_luma)
 
 
 _COLORMAP_NAMES = ['none', 'blue->brown', 'blue->red', 'blue->green', 'green->brown', 'green->red', 'green->blue', 'redrose->brown',
@@ -560,15 +625,21 @@ def _get_color_tune(ColorTune: str, ColorFix: str, dd_model: int):
 def HAVC_main(clip, Preset: str = 'Medium', FrameInterp: int = 0, ColorModel: str = 'Video+Artistic', CombMethod: str = 'Simple',
               VideoTune: str = 'Stable', ColorFix: str = 'Magenta/Violet', ColorTune: str = 'Light', ColorMap: str = 'None',
               ColorTemp: str = 'None', BlackWhiteTune: str = 'None', BlackWhiteMode: int = 0, BlackWhiteBlend: bool = True,
-              EnableDeepEx: bool = False, enable_fp16: bool = True, debug_level: int = 0, device_index: int = 0, **kw):
-    """Drop-in for vsdeoldify.HAVC_main (vsdeoldify/__init__.py:101-330 -> HAVC_main_presets :469-912) restricted to the
-    per-frame image-model branch: the string presets are turned into HAVC_colorizer's numeric arguments exactly as the
-    reference does (colour-model split, CombMethod, VideoTune weight, ColorTune / ColorFix -> ddtweak + hue range, ColorMap ->
-    "chroma adjustment"), followed by the HAVC_stabilizer step the presets append (:896-910): colormap only for the fast
-    presets, dark + smooth + colormap for slower / slow / medium.  Where the reference would also switch on the TEMPORAL
-    chroma stabiliser (two-model presets with ColorTune != 'none'; scope row N3) the per-frame stages still run and a warning
-    says the temporal one is skipped.  Exemplar models, DDColor, tiling presets (placebo / veryslow), ColorTemp /
-    BlackWhiteTune raise."""
+              EnableDeepEx: bool = False, DeepExMethod: int = 0, DeepExPreset: str = 'Medium', DeepExRefMerge: int = 0,
+              DeepExOnlyRefFrames: bool = False, ScFrameDir: Optional[str] = None, ScThreshold: float = 0.10, ScThtOffset: int = 1,
+              ScMinFreq: int = 0, ScMinInt: int = 1, ScThtSSIM: float = 0.0, ScNormalize: bool = False, DeepExModel: int = 0,
+              DeepExVivid: bool = True, DeepExEncMode: int = 0, DeepExMaxMemFrames=0, RefRange: Sequence[int] = (0, 0),
+              enable_fp16: bool = True, debug_level: int = 0, device_index=0):
+    """Drop-in for vsdeoldify.HAVC_main (vsdeoldify/__init__.py:101-330 -> HAVC_main_presets :469-912): the reference's full
+    positional signature in the reference's order (`device_index`, keyword only in spirit, is this build's one addition at the
+    end), restricted to the per-frame image-model branch.  The string presets are turned into HAVC_colorizer's numeric
+    arguments exactly as the reference does (colour-model split, CombMethod, VideoTune weight, ColorTune / ColorFix ->
+    ddtweak + hue range, ColorMap -> "chroma adjustment"), followed by the HAVC_stabilizer step the presets append (:896-910):
+    colormap only for the fast presets, dark + smooth + colormap for slower / slow / medium.  The DeepEx* / Sc* / RefRange
+    parameters only feed the exemplar branch in the reference (they are not passed to HAVC_colorizer, :849-853) and are
+    accepted and ignored here exactly when EnableDeepEx is False; EnableDeepEx / FrameInterp / the tiled presets / ColorTemp /
+    BlackWhiteTune / DDColor models raise vs.Error.  Where the reference would also switch on the TEMPORAL chroma stabiliser
+    (two-model presets with ColorTune != 'none') the per-frame stages run and a warning says the temporal one is skipped."""
     rf = _get_render_factor(Preset)
     speed_id = _PRESETS.index(Preset.lower())
     if EnableDeepEx or FrameInterp != 0:

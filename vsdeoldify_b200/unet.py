@@ -57,17 +57,22 @@ def bn_affine(sd: SD, p: str) -> Tuple[torch.Tensor, torch.Tensor]:
 
 
 def folded_weight(sd: SD, p: str) -> torch.Tensor:
-    """Effective conv weight in eval mode: spectral norm (W/sigma, sigma=u^T W v, with the legacy
-    'no weight_v' case solved like torch's load hook is NOT needed for >=1.0 checkpoints), weight norm
-    (g*v/||v||) or plain."""
+    """Effective conv weight in eval mode:
+      spectral norm   W = weight_orig / sigma, sigma = u^T W_mat v with the STORED u, v (no power iteration in eval);
+      legacy spectral-norm state-dicts (version < 1: keys `weight`, `weight_orig`, `weight_u`, no `weight_v`): torch's load
+          hook (torch/nn/utils/spectral_norm.py `_load_from_state_dict` + `_solve_v_and_rescale`) sets
+          sigma = mean(weight_orig / weight) and solves v so that u^T W_mat v == sigma exactly, hence W = weight_orig / sigma;
+      weight norm     W = g * v / ||v|| (norm over all dims but 0);
+      plain           W = weight."""
     if p + ".weight_orig" in sd:
         w = sd[p + ".weight_orig"].double()
-        u = sd[p + ".weight_u"].double()
         if p + ".weight_v" in sd:
-            v = sd[p + ".weight_v"].double()
-        else:  # spectral-norm state-dict version < 1: derive v from u (one half power-iteration step)
-            v = torch.nn.functional.normalize(torch.mv(w.flatten(1).t(), u), dim=0)
-        sigma = torch.dot(u, torch.mv(w.flatten(1), v))
+            u, v = sd[p + ".weight_u"].double(), sd[p + ".weight_v"].double()
+            sigma = torch.dot(u, torch.mv(w.flatten(1), v))
+        elif p + ".weight" in sd:
+            sigma = (w / sd[p + ".weight"].double()).mean()
+        else:
+            raise KeyError(f"{p}: spectral-norm entry without weight_v (current schema) or weight (legacy schema)")
         return (w / sigma).float()
     if p + ".weight_g" in sd:
         v, g = sd[p + ".weight_v"].double(), sd[p + ".weight_g"].double()
