@@ -112,6 +112,12 @@ typedef struct {
      * (tools/precision_emulator.py) shows 16-bit storage dominates the logit error: the ResNet encoders.             */
     const void *src0_lo, *src1_lo, *weight_lo, *residual_lo;
     void *out_lo;
+    /* blur = 1 (with shuffle = 1): the ICNR blur that follows the PixelShuffle in (Custom)PixelShuffle_ICNR
+     * (vsdeoldify/deoldify/unet.py:47-52: ReplicationPad2d((1,0,1,0)) + AvgPool2d(2, stride=1)) is applied in the epilogue, so the
+     * shuffled tensor never goes to HBM un-blurred.  Column layout of the packed weight / bias: N tile t holds channels
+     * [t*BN/4, (t+1)*BN/4) as four consecutive sub-pixel groups g = 2*dy + dx, column = t*BN + g*BN/4 + (c - t*BN/4); the M tiles
+     * overlap by one halo row / column (recomputed), box_b must be 1; epilogue = bias + ReLU only.                          */
+    int32_t blur;
 } havc_conv_desc;
 
 const char *havc_last_error(void);
@@ -148,9 +154,9 @@ int havc_affine_act(const void *in, const void *in_lo, void *out, void *out_lo, 
 /* ReplicationPad2d((1,0,1,0)) + AvgPool2d(2,1) of (Custom)PixelShuffle_ICNR
  * (vsdeoldify/deoldify/unet.py:47-52, vsdeoldify/fastai/layers.py:214-220). */
 int havc_blur2x2(const void *in, void *out, int B, int H, int W, int C, int out_pix_stride, int dtype, void *stream);
-/* Row soft-max of fp32 attention logits -> 16-bit probabilities (F.softmax(.., dim=1) of
+/* Row soft-max of fp32 (in_dtype = HAVC_F32) or fp16 (HAVC_F16) attention logits -> 16-bit probabilities (F.softmax(.., dim=1) of
  * vsdeoldify/fastai/layers.py:94, stored transposed so the reduction runs along contiguous rows). */
-int havc_softmax_rows(const float *in, void *out, long long rows, int cols, int in_stride, int out_stride,
+int havc_softmax_rows(const void *in, int in_dtype, void *out, long long rows, int cols, int in_stride, int out_stride,
                       int out_dtype, void *stream);
 
 /* ---- frame pre / post pixel passes (planar u8 RGB frames [B][3][H][W]) ----------------------- */

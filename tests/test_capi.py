@@ -40,7 +40,7 @@ def test_argument_validation_without_device():
     assert lib.havc_conv_gemm(ctypes.byref(d), None) == -1           # HAVC_ERR_ARG, no kernel launched
     assert b"havc_conv_gemm" in lib.havc_last_error()
     assert lib.havc_blur2x2(None, None, 1, 8, 8, 8, 8, 0, None) == -1
-    assert lib.havc_softmax_rows(None, None, 4, 6, 6, 6, 0, None) == -1
+    assert lib.havc_softmax_rows(None, 2, None, 4, 6, 6, 6, 0, None) == -1
     assert lib.havc_version() >= 100
 
 

@@ -380,3 +380,43 @@ def test_x3_partial_planes():
 
 def test_x3_bf16():
     _run_conv_x3(2, 16, 16, [64], 64, 3, torch.bfloat16)
+
+
+# ---- fused PixelShuffle + ICNR blur epilogue ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,H,W,Cin,Cout,dtype", [(2, 48, 48, 64, 4 * 64, torch.float16), (1, 50, 37, 128, 4 * 100, torch.float16),
+                                                  (3, 96, 96, 64, 4 * 256, torch.bfloat16)])
+def test_shuffle_blur_fused_equals_unfused_and_torch(B, H, W, Cin, Cout, dtype):
+    """conv1x1 + bias + ReLU -> PixelShuffle(2) -> ReplicationPad2d((1,0,1,0)) + AvgPool2d(2, 1) (CustomPixelShuffle_ICNR,
+    unet.py:24-52) as ONE launch (havc_conv_desc.blur: halo recompute, blur in the epilogue) against the two-launch path
+    (PixelShuffle store + havc_blur2x2: bit-identical, same roundings in the same order) and against torch."""
+    from vsdeoldify_b200 import _lib, ops
+    _setup()
+    dev = "cuda"
+    x = torch.randn(B, Cin, H, W, device=dev)
+    w = torch.randn(Cout, Cin, 1, 1, device=dev) / Cin ** 0.5
+    bias = torch.randn(Cout, device=dev)
+    x16, w16 = x.to(dtype), w.to(dtype)
+    y = F.pixel_shuffle(F.relu(F.conv2d(x16.float(), w16.float()) + bias[None, :, None, None]), 2)
+    ref = F.avg_pool2d(F.pad(y.to(dtype).float(), (1, 0, 1, 0), mode="replicate"), 2, stride=1)
+    cg = Cout // 4
+    src = _nhwc(x16)
+    hd = ops.havc_dtype(dtype)
+    # two launches
+    wp, meta = ops.pack_conv_weight(w16.float().cpu(), None, dtype=dtype, shuffle=True)
+    t = torch.zeros(B, 2 * H, 2 * W, ops.chan_storage(cg), device=dev, dtype=dtype)
+    ops.make_conv(src, wp.to(dev), t, ops.taps_for(1), n_total=meta["rows"], bias=ops.pack_cols(bias, meta["rows"], 0.0, meta).to(dev),
+                  relu1=True, shuffle=True, group_n=meta["group_n"], c_store=ops.pad_to(cg, 8)).launch()
+    unfused = torch.zeros_like(t)
+    _lib.check(_lib.lib().havc_blur2x2(t.data_ptr(), unfused.data_ptr(), B, 2 * H, 2 * W, t.shape[-1], unfused.stride(2), hd, None))
+    # one launch
+    wpb, mb = ops.pack_conv_weight(w16.float().cpu(), None, dtype=dtype, shuffle="blur")
+    fused = torch.zeros_like(t)
+    for pair in (-1, 1):
+        fused.zero_()
+        ops.make_conv(src, wpb.to(dev), fused, ops.taps_for(1), n_total=mb["rows"], bn=4 * ops.BLUR_CW, box=(16, 8, 1),
+                      bias=ops.pack_cols(bias, mb["rows"], 0.0, mb).to(dev), relu1=True, shuffle=True, blur=True,
+                      c_store=ops.pad_to(cg, 8), pair=pair).launch()
+        torch.cuda.synchronize()
+        assert torch.equal(fused, unfused), f"pair={pair}: {(fused != unfused).sum().item()} of {fused.numel()} values differ"
+    _check(fused[..., :cg].permute(0, 3, 1, 2), ref, dtype, "shuffle+blur")
+    assert (fused[..., cg:] == 0).all()

@@ -10,10 +10,10 @@ pytestmark = pytest.mark.gpu
 def _register():
     from oracle import synth_weights
     from vsdeoldify_b200 import havc
-    if "ColorizeVideo_gen" not in havc._REGISTERED:
-        havc.register_state_dict("ColorizeVideo_gen", synth_weights.make_unet_state_dict("wide", 1234))
-        havc.register_state_dict("ColorizeStable_gen", synth_weights.make_unet_state_dict("wide", 4321))
-        havc.register_state_dict("ColorizeArtistic_gen", synth_weights.make_unet_state_dict("deep", 1234))
+    for name, (arch, seed) in {"ColorizeVideo_gen": ("wide", 1234), "ColorizeStable_gen": ("wide", 4321),
+                               "ColorizeArtistic_gen": ("deep", 1234)}.items():
+        if name not in havc._REGISTERED:        # another test module may have registered only some of them
+            havc.register_state_dict(name, synth_weights.make_unet_state_dict(arch, seed))
     return havc
 
 

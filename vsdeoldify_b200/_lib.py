@@ -69,6 +69,7 @@ class ConvDesc(C.Structure):
         ("pair", C.c_int32),
         ("src0_lo", C.c_void_p), ("src1_lo", C.c_void_p), ("weight_lo", C.c_void_p), ("residual_lo", C.c_void_p),
         ("out_lo", C.c_void_p),
+        ("blur", C.c_int32),
     ]
 
 
@@ -89,7 +90,7 @@ _SIGNATURES = {
     "havc_affine_act": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                   C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "havc_blur2x2": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p]),
-    "havc_softmax_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int,
+    "havc_softmax_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.c_void_p]),
     "havc_resample_h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                   C.c_int, C.c_void_p]),

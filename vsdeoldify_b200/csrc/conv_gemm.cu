@@ -104,6 +104,11 @@ struct ConvParams {
     int a0_lo, a1_lo, w_lo, nsub0, nsub1;
     int x3_out, res_lo;
     uint32_t lo_stage_off;        // byte offset of the lo plane's staging blocks inside the output staging area
+    // fused PixelShuffle(2) + ICNR blur epilogue (blur = 1): M tiles overlap by one halo row / column (halo = 1), the N tile holds
+    // the four sub-pixel groups of BN/4 channels, the tile is staged in shared memory and every output pixel averages its
+    // 2 x 2 neighbourhood of the shuffled image there (ReplicationPad2d((1,0,1,0)) + AvgPool2d(2, 1), unet.py:47-52)
+    int blur, halo;
+    uint32_t blur_row_bytes;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -467,7 +472,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             int nt, wt, ht, bt;
             decode_tile(tile, nt, wt, ht, bt);
             const int n0 = nt * p.BN;
-            const int w0 = wt * p.bw, h0 = ht * p.bh, b0 = bt * p.bb;
+            const int w0 = wt * (p.bw - p.halo) - p.halo, h0 = ht * (p.bh - p.halo) - p.halo, b0 = bt * p.bb;
             const int ab = p.a_batched ? b0 : 0, wb = p.b_batched ? b0 : 0;
             int tap = 0, kc_in_tap = 0;
             for (int ks = 0; ks < ksteps; ++ks) {
@@ -836,6 +841,130 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 tc_fence_before();
                 acc_signal(tempty_sig[as]);
                 if (++as == p.acc_stages) { as = 0; aphase ^= 1u; }
+                continue;
+            }
+            if (p.blur) {
+                // ---------------- fused PixelShuffle + blur epilogue (generic kernel, 8 epilogue warps) ----------------
+                // N tile = [4 sub-pixel groups][CW = BN/4 channels].  Phase 1: +bias, ReLU, 16-bit, whole tile -> shared memory
+                // (row = low-resolution pixel incl. the halo row / column; padded row pitch: conflict-free 16-byte accesses).
+                // Phase 2: every (output pixel, 8-channel chunk) averages its four contributors; 8 consecutive lanes write one
+                // full 128-byte line of the NHWC output.
+                const uint32_t pitch = p.blur_row_bytes;
+                if (last_nt == -1) {     // once per CTA: the bias of EVERY N tile (N_total <= kEpiSmemFloats) - the N tile changes with every tile
+                    for (int i = etid; i < p.N_total; i += 256) sparams[i] = p.bias ? __ldg(p.bias + i) : 0.f;
+                    last_nt = 0;
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");      // phase 2 of the previous tile has finished with the staging tile (+ bias visible)
+                mbar_wait_long(tfull_bar(as), aphase, p.wait_hint_ns);
+                tc_fence_after();
+                const uint32_t tb = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * p.acc_stride;
+                const uint32_t myrow = stage_out + (uint32_t)r * pitch;
+                uint32_t va[32], vb[32];
+                // this warp's chunks: half, half + 2, ... (four of the eight); the TMEM load of the next one is in flight while one is converted
+                auto emit = [&](int ci, uint32_t(&v)[32]) {
+                    const float4 *bs4 = reinterpret_cast<const float4 *>(sparams + n0 + ci * 32);
+#pragma unroll
+                    for (int g4 = 0; g4 < 4; ++g4) {
+                        const float4 b0 = bs4[2 * g4], b1 = bs4[2 * g4 + 1];
+                        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                        uint32_t o[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float y0 = fmaxf(__uint_as_float(v[8 * g4 + 2 * j]) + bb[2 * j], 0.f);
+                            const float y1 = fmaxf(__uint_as_float(v[8 * g4 + 2 * j + 1]) + bb[2 * j + 1], 0.f);
+                            o[j] = pack2(y0, y1, kDT);
+                        }
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(myrow + (uint32_t)(ci * 64 + g4 * 16)), "r"(o[0]),
+                                     "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+                    }
+                };
+                __syncwarp();
+                tmem_ld32(tb + half * 32, va);
+#pragma unroll
+                for (int kk = 0; kk < 4; kk += 2) {
+                    tmem_ld_wait();
+                    __syncwarp();
+                    tmem_ld32(tb + (half + 2 * (kk + 1)) * 32, vb);
+                    emit(half + 2 * kk, va);
+                    tmem_ld_wait();
+                    if (kk + 2 < 4) {
+                        __syncwarp();
+                        tmem_ld32(tb + (half + 2 * (kk + 2)) * 32, va);
+                    }
+                    emit(half + 2 * (kk + 1), vb);
+                }
+                tc_fence_before();
+                acc_signal(tempty_sig[as]);                          // the accumulator is out of TMEM: the next tile may start
+                if (++as == p.acc_stages) { as = 0; aphase ^= 1u; }
+                asm volatile("bar.sync 2, 256;" ::: "memory");      // the whole tile is staged
+                // phase 2 (BN = 256, box 16 x 8: compile-time geometry): thread = 16-byte channel chunk k = etid & 7 of the low-resolution
+                // pixels row = etid >> 3, + 32, ...  It loads the 3 x 3 high-resolution neighbourhood S[-1..1][-1..1] of the pixel's 2 x 2
+                // outputs (own four sub-pixels, two of the left neighbour, two of the upper one, one of the upper-left one; redirected
+                // onto the pixel's own values on the top / left image edge = replication padding), forms the horizontal pair sums once
+                // and writes the four outputs: ((S[y-1][x-1] + S[y-1][x]) + (S[y][x-1] + S[y][x])) / 4, havc_blur2x2's association.
+                {
+                    constexpr int kBW = 16, kCW = 64;
+                    const int k = etid & 7;
+                    const int w_base = wt * (kBW - 1) - 1, h_base = ht * (p.bh - 1) - 1;
+                    const int Wl = p.out_W, Hl = p.out_H;
+                    const int chan = nt * kCW + k * 8;
+                    const bool chan_ok = chan < p.c_store;
+                    uint16_t *obase = reinterpret_cast<uint16_t *>(p.out) + bt * p.osb + chan;
+                    auto grp = [&](int g) -> uint32_t { return (uint32_t)((g * kCW + k * 8) * 2); };   // byte offset of sub-pixel group g in a row
+                    auto lds8 = [&](uint32_t addr, float(&f)[8]) {
+                        uint4 o;
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w) : "r"(addr) : "memory");
+                        const uint32_t w[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) { const float2 t = unpack2(w[j], kDT); f[2 * j] = t.x; f[2 * j + 1] = t.y; }
+                    };
+                    for (int row = (etid >> 3); row < kTileM; row += 32) {
+                        const int trw = row & (kBW - 1), trh = row >> 4;
+                        const int pw = w_base + trw, ph = h_base + trh;
+                        if (trw == 0 || trh == 0 || pw >= Wl || ph >= Hl || !chan_ok) continue;   // halo rows / columns only contribute
+                        const uint32_t own = stage_out + (uint32_t)row * pitch;
+                        const uint32_t left = pw > 0 ? own - pitch : own;                 // X - 1 clamps onto X at the left image edge
+                        const uint32_t up = ph > 0 ? own - kBW * pitch : own;             // Y - 1 clamps onto Y at the top image edge
+                        const uint32_t upleft = ph > 0 ? left - kBW * pitch : left;
+                        // sub-pixel groups g = 2 a + b.  Column X-1 is sub-column b = 1 of the left neighbour (b = 0 of the pixel itself
+                        // when clamped); row Y-1 is sub-row a = 1 of the upper neighbour (a = 0 of the pixel itself when clamped)
+                        const int gl = pw > 0 ? 1 : 0, gu = ph > 0 ? 2 : 0;
+                        float s[8], t[8], hm[2][8], h0[2][8], h1[2][8];
+                        // row Y-1: S[-1][-1], S[-1][0], S[-1][1]
+                        lds8(upleft + grp(gu + gl), s); lds8(up + grp(gu), t);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) hm[0][j] = s[j] + t[j];
+                        lds8(up + grp(gu + 1), s);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) hm[1][j] = t[j] + s[j];
+                        // row Y (a = 0): S[0][-1], S[0][0], S[0][1]
+                        lds8(left + grp(gl), s); lds8(own + grp(0), t);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) h0[0][j] = s[j] + t[j];
+                        lds8(own + grp(1), s);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) h0[1][j] = t[j] + s[j];
+                        // row Y+1 (a = 1): S[1][-1], S[1][0], S[1][1]
+                        lds8(left + grp(2 + gl), s); lds8(own + grp(2), t);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) h1[0][j] = s[j] + t[j];
+                        lds8(own + grp(3), s);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) h1[1][j] = t[j] + s[j];
+                        uint16_t *dst = obase + (long long)(2 * ph) * p.osh + (long long)(2 * pw) * p.osw;
+#pragma unroll
+                        for (int bq = 0; bq < 2; ++bq) {
+                            uint32_t o0[4], o1[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                o0[j] = pack2((hm[bq][2 * j] + h0[bq][2 * j]) * 0.25f, (hm[bq][2 * j + 1] + h0[bq][2 * j + 1]) * 0.25f, kDT);
+                                o1[j] = pack2((h0[bq][2 * j] + h1[bq][2 * j]) * 0.25f, (h0[bq][2 * j + 1] + h1[bq][2 * j + 1]) * 0.25f, kDT);
+                            }
+                            *reinterpret_cast<uint4 *>(dst + bq * p.osw) = make_uint4(o0[0], o0[1], o0[2], o0[3]);
+                            *reinterpret_cast<uint4 *>(dst + p.osh + bq * p.osw) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+                        }
+                    }
+                }
                 continue;
             }
             const int ow = wt * p.bw + rw, oh = ht * p.bh + rh, ob = bt * p.bb + rb;
@@ -1228,8 +1357,8 @@ extern "C" int havc_conv_gemm(const havc_conv_desc *d, void *stream) {
                        (reinterpret_cast<uintptr_t>(d->out) & 15) == 0,
                    "havc_conv_gemm: output strides must be multiples of 8 elements");
     HAVC_CHECK_ARG(d->up >= 1, "havc_conv_gemm: up must be >= 1");
-    if (d->shuffle) HAVC_CHECK_ARG(d->group_n > 0 && d->group_n % 16 == 0 && d->N_total == 4 * d->group_n,
-                                   "havc_conv_gemm: shuffle needs N_total == 4*group_n, group_n %% 16 == 0");
+    if (d->shuffle && !d->blur) HAVC_CHECK_ARG(d->group_n > 0 && d->group_n % 16 == 0 && d->N_total == 4 * d->group_n,
+                                               "havc_conv_gemm: shuffle needs N_total == 4*group_n, group_n %% 16 == 0");
     if (d->residual) HAVC_CHECK_ARG(d->res_stride_w % 8 == 0 && d->res_stride_h % 8 == 0 && d->res_stride_b % 8 == 0 &&
                                         (reinterpret_cast<uintptr_t>(d->residual) & 15) == 0 && !d->shuffle,
                                     "havc_conv_gemm: residual strides invalid");
@@ -1239,8 +1368,14 @@ extern "C" int havc_conv_gemm(const havc_conv_desc *d, void *stream) {
     memset(&p, 0, sizeof(p));
     p.out_B = d->out_B; p.out_H = d->out_H; p.out_W = d->out_W;
     p.bw = d->box_w; p.bh = d->box_h; p.bb = d->box_b;
-    p.tiles_w = ceil_div(d->out_W, d->box_w);
-    p.tiles_h = ceil_div(d->out_H, d->box_h);
+    p.blur = d->blur ? 1 : 0;
+    p.halo = p.blur;
+    if (p.blur) HAVC_CHECK_ARG(d->shuffle && d->box_b == 1 && d->box_w == 16 && d->box_h == 8 && d->BN == 256 && d->N_total <= kEpiSmemFloats &&
+                                   d->N_total % d->BN == 0 && d->out_dtype == d->dtype && d->residual == nullptr && d->scale == nullptr &&
+                                   d->relu1 && d->leaky1 == 0.f && d->split_n == 0 && d->head_w == nullptr && d->out_lo == nullptr && d->BN <= 256,
+                               "havc_conv_gemm: blur needs a PixelShuffle launch (bias + ReLU only) with box_b = 1 and BN = 4 * channels per tile");
+    p.tiles_w = ceil_div(d->out_W, d->box_w - p.halo);
+    p.tiles_h = ceil_div(d->out_H, d->box_h - p.halo);
     p.tiles_b = ceil_div(d->out_B, d->box_b);
     p.BN = d->BN;
     p.tiles_n = ceil_div(d->N_total, d->BN);
@@ -1292,7 +1427,7 @@ extern "C" int havc_conv_gemm(const havc_conv_desc *d, void *stream) {
     p.acc_stride = p.staggered ? (int)kTmemCols - d->BN : d->BN;
     p.stage_bytes = kABytes + (pair ? d->BN / 2 : d->BN) * 128;     // per CTA
     const bool out16 = d->out_dtype == HAVC_F16 || d->out_dtype == HAVC_BF16;
-    p.tma_store = (d->tma_store && out16 && d->out != nullptr && d->BN % 64 == 0 && d->N_total % 64 == 0 && d->split_n == 0 &&
+    p.tma_store = (d->tma_store && !d->blur && out16 && d->out != nullptr && d->BN % 64 == 0 && d->N_total % 64 == 0 && d->split_n == 0 &&
                    d->head_w == nullptr && d->up == 1 && d->oy == 0 && d->ox == 0 && (!d->shuffle || d->group_n % 64 == 0))
                       ? 1 : 0;
     // split precision (hi + lo planes)
@@ -1305,6 +1440,10 @@ extern "C" int havc_conv_gemm(const havc_conv_desc *d, void *stream) {
         HAVC_CHECK_ARG((reinterpret_cast<uintptr_t>(lp) & 15) == 0, "havc_conv_gemm: lo planes must be 16-byte aligned");
     p.lo_stage_off = (uint32_t)(kTileM * d->BN * 2);
     p.stage_out_bytes = p.tma_store ? (uint32_t)(kTileM * d->BN * 2) * (p.x3_out ? 2u : 1u) : 0u;
+    if (p.blur) {       // staging tile of the fused blur: 128 rows, padded pitch (BN*2 + 16 bytes) for conflict-free 16-byte accesses
+        p.blur_row_bytes = (uint32_t)d->BN * 2u + 16u;
+        p.stage_out_bytes = ((uint32_t)kTileM * p.blur_row_bytes + 1023u) & ~1023u;
+    }
     static const char *hint_env = getenv("HAVC_B200_WAIT_HINT");            // ns; A/B switch for profiling
     p.wait_hint_ns = hint_env ? (uint32_t)atoi(hint_env) : 0u;
 

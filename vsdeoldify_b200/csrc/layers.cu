@@ -297,30 +297,41 @@ __global__ void blur2x2_kernel(const uint4 *__restrict__ in, uint4 *__restrict__
 // Row soft-max of the attention logits: P[j, :] = softmax_i S[j, i] (SelfAttention, fastai/layers.py:94:
 // softmax over dim=1 of beta[b,i,j] == over the contiguous row of the transposed logits we store).
 // One warp per row; the row lives in registers across the three passes when cols <= 32*kMaxPerLane.
-__global__ void softmax_rows_kernel(const float *__restrict__ in, void *__restrict__ out, long long rows, int cols,
+// kIn16: the logits were stored as fp16 (attention logits of the fp16 path: |S| stays far below the fp16 range and the 2^-11
+// rounding disappears in the soft-max, tools/precision_emulator.py) instead of fp32 - half the bytes of the N x N round trip.
+template <bool kIn16>
+__global__ void softmax_rows_kernel(const void *__restrict__ in, void *__restrict__ out, long long rows, int cols,
                                     int in_stride, int out_stride, int out_dtype) {
     const int lane = threadIdx.x & 31;
     const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    auto load4 = [&](long long row, int c) -> float4 {
+        if constexpr (kIn16) {
+            const uint2 u = *reinterpret_cast<const uint2 *>(reinterpret_cast<const uint16_t *>(in) + row * in_stride + c);
+            const float2 a = unpack2(u.x, HAVC_F16), b = unpack2(u.y, HAVC_F16);
+            return make_float4(a.x, a.y, b.x, b.y);
+        } else {
+            return *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(in) + row * in_stride + c);
+        }
+    };
     for (long long row = warp0; row < rows; row += nwarps) {
-        const float *r = in + row * in_stride;
         float m = -INFINITY;
         for (int c = lane * 4; c < cols; c += 128) {
-            const float4 v = *reinterpret_cast<const float4 *>(r + c);
+            const float4 v = load4(row, c);
             m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
         float s = 0.f;
         for (int c = lane * 4; c < cols; c += 128) {
-            const float4 v = *reinterpret_cast<const float4 *>(r + c);
+            const float4 v = load4(row, c);
             s += __expf(v.x - m) + __expf(v.y - m) + __expf(v.z - m) + __expf(v.w - m);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         const float inv = 1.f / s;
         for (int c = lane * 4; c < cols; c += 128) {
-            const float4 v = *reinterpret_cast<const float4 *>(r + c);
+            const float4 v = load4(row, c);
             const float e0 = __expf(v.x - m) * inv, e1 = __expf(v.y - m) * inv, e2 = __expf(v.z - m) * inv,
                         e3 = __expf(v.w - m) * inv;
             uint2 pk = make_uint2(pack2(e0, e1, out_dtype), pack2(e2, e3, out_dtype));
@@ -417,14 +428,16 @@ extern "C" int havc_blur2x2(const void *in, void *out, int B, int H, int W, int 
     return HAVC_OK;
 }
 
-extern "C" int havc_softmax_rows(const float *in, void *out, long long rows, int cols, int in_stride, int out_stride,
+extern "C" int havc_softmax_rows(const void *in, int in_dtype, void *out, long long rows, int cols, int in_stride, int out_stride,
                                  int out_dtype, void *stream) {
-    HAVC_CHECK_ARG(in && out && dt16(out_dtype) && cols % 4 == 0 && in_stride % 4 == 0 && out_stride % 4 == 0 &&
-                       in_stride >= cols && out_stride >= cols,
-                   "havc_softmax_rows: cols and strides must be multiples of 4");
+    HAVC_CHECK_ARG(in && out && dt16(out_dtype) && (in_dtype == HAVC_F32 || in_dtype == HAVC_F16) && cols % 4 == 0 &&
+                       in_stride % 4 == 0 && out_stride % 4 == 0 && in_stride >= cols && out_stride >= cols,
+                   "havc_softmax_rows: cols and strides must be multiples of 4, input fp32 or fp16");
     const long long nthreads = rows * 32;
-    softmax_rows_kernel<<<grid_for(nthreads, 256), 256, 0, (cudaStream_t)stream>>>(in, out, rows, cols, in_stride,
-                                                                                  out_stride, out_dtype);
+    if (in_dtype == HAVC_F16)
+        softmax_rows_kernel<true><<<grid_for(nthreads, 256), 256, 0, (cudaStream_t)stream>>>(in, out, rows, cols, in_stride, out_stride, out_dtype);
+    else
+        softmax_rows_kernel<false><<<grid_for(nthreads, 256), 256, 0, (cudaStream_t)stream>>>(in, out, rows, cols, in_stride, out_stride, out_dtype);
     HAVC_LAUNCHED();
     return HAVC_OK;
 }

@@ -140,6 +140,9 @@ def split_hi_lo(w: torch.Tensor, dtype) -> Tuple[torch.Tensor, torch.Tensor]:
     return hi, lo
 
 
+BLUR_CW = 64      # channels per N tile of a fused PixelShuffle + blur launch (BN = 4 * BLUR_CW = 256)
+
+
 def pack_conv_weight(w: torch.Tensor, cin_splits: Optional[Sequence[int]] = None, dtype=torch.float16,
                      shuffle: bool = False, row_pad: int = 16,
                      cin_storage: Optional[Sequence[int]] = None) -> Tuple[torch.Tensor, dict]:
@@ -171,7 +174,18 @@ def pack_conv_weight(w: torch.Tensor, cin_splits: Optional[Sequence[int]] = None
     cin_storage = wcat.shape[1]
     wk = wcat.permute(0, 2, 3, 1).reshape(Cout, kh * kw, cin_storage)
     meta = {"c1_off": c1_off, "taps": kh * kw, "cin": cin_storage, "cout": Cout}
-    if shuffle:
+    if shuffle == "blur":        # fused PixelShuffle + blur launch: N tile t = [4 sub-pixel groups][BLUR_CW channels]
+        assert Cout % 4 == 0
+        cg, cw = Cout // 4, BLUR_CW
+        nt = -(-cg // cw)
+        rows = wk.new_zeros(nt * 4 * cw, kh * kw, cin_storage)
+        for t in range(nt):
+            c0, c1 = t * cw, min((t + 1) * cw, cg)
+            for g in range(4):
+                rows[t * 4 * cw + g * cw: t * 4 * cw + g * cw + (c1 - c0)] = wk[c0 * 4 + g: c1 * 4: 4]
+        meta.update(blur_cw=cw, cg=cg, rows=nt * 4 * cw)
+        wk = rows
+    elif shuffle:
         assert Cout % 4 == 0
         cg = Cout // 4
         gn = pad_to(cg, row_pad)
@@ -196,7 +210,13 @@ def pack_cols(v: Optional[torch.Tensor], n_alloc: int, fill: float, shuffle_meta
         return None
     v = v.detach().float().cpu()
     out = torch.full((n_alloc,), fill, dtype=torch.float32)
-    if shuffle_meta and "group_n" in shuffle_meta:
+    if shuffle_meta and "blur_cw" in shuffle_meta:
+        cw, cg = shuffle_meta["blur_cw"], shuffle_meta["cg"]
+        for t in range(-(-cg // cw)):
+            c0, c1 = t * cw, min((t + 1) * cw, cg)
+            for g in range(4):
+                out[t * 4 * cw + g * cw: t * 4 * cw + g * cw + (c1 - c0)] = v[c0 * 4 + g: c1 * 4: 4]
+    elif shuffle_meta and "group_n" in shuffle_meta:
         gn, cg = shuffle_meta["group_n"], shuffle_meta["cg"]
         for g in range(4):
             out[g * gn:g * gn + cg] = v[g::4]
@@ -249,7 +269,7 @@ def make_conv(src0: torch.Tensor, weight: torch.Tensor, out: torch.Tensor, taps,
               head_out: Optional[torch.Tensor] = None, tma_store: Optional[bool] = None, leaky1: float = 0.0,
               pair: int = 0, name: str = "", src0_lo: Optional[torch.Tensor] = None, src1_lo: Optional[torch.Tensor] = None,
               weight_lo: Optional[torch.Tensor] = None, out_lo: Optional[torch.Tensor] = None,
-              residual_lo: Optional[torch.Tensor] = None) -> ConvOp:
+              residual_lo: Optional[torch.Tensor] = None, blur: bool = False) -> ConvOp:
     """src0/src1: NHWC (or [P,B,H,W,C]) 16-bit device tensors; weight: packed [rows,taps,cin] or
     [batches,rows,taps,cin]; out: NHWC tensor written at pixel (h*up+oy, w*up+ox)."""
     d = ConvDesc()
@@ -305,7 +325,8 @@ def make_conv(src0: torch.Tensor, weight: torch.Tensor, out: torch.Tensor, taps,
         assert head_w is not None, "a launch without an output tensor needs the fused head"
         d.out_dtype = d.dtype
     d.up, d.oy, d.ox = up, oy, ox
-    d.shuffle, d.group_n = int(shuffle), group_n
+    d.shuffle, d.group_n = int(bool(shuffle)), group_n
+    d.blur = int(blur)
     d.c_store = c_store if c_store is not None else out.shape[-1]
     d.src1_single_tap, d.src1_wi, d.split_n = int(src1_single_tap), src1_wi, split_n
     if out2 is not None:

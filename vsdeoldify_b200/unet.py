@@ -41,6 +41,7 @@ from .ops import Pair, chan_storage, hi_of, lo_of, pad_to
 #              parity suite: the artistic (ResNet-34) generator and eccv16; the video / stable generator passes it 2x over as is
 PRECISION = os.environ.get("HAVC_B200_PRECISION", "auto")
 PRECISIONS = ("fast", "balanced", "auto")
+FUSE_BLUR = os.environ.get("HAVC_B200_FUSE_BLUR", "1") != "0"          # A/B switch for profiling
 
 SD = Dict[str, torch.Tensor]
 BN_EPS = 1e-5
@@ -130,13 +131,14 @@ class LaunchProgram:
     def conv(self, name: str, src0, w: torch.Tensor, *, ks=1, src1=None, cin_splits=None, stride=1, bias=None,
              relu1=False, scale=None, shift=None, residual=None, relu2=False, shuffle=False, out=None,
              out_c: Optional[int] = None, dilation: int = 1, leaky1: float = 0.0, out_dtype=None, taps=None,
-             phase=None, flops: Optional[float] = None, head_w=None, head_out=None, x3: bool = False):
+             phase=None, flops: Optional[float] = None, head_w=None, head_out=None, x3: bool = False, blur: bool = False):
         """w: folded fp32 [Cout, Cin, ks, ks].  Returns the NHWC output tensor.
         taps: explicit (dh, dw, phase, weight tap) list (transposed convolutions); phase = (up, oy, ox): the output
         pixel of (h, w) is (h*up+oy, w*up+ox) of `out`.
         x3: split-precision launch - the weight is packed as hi + lo planes, sources / residual that are `Pair`s contribute
         their lo planes, and the result is a `Pair`.  The weight is pre-scaled by a power of two (undone by the epilogue's
-        scale) so that its lo plane stays in fp16's normal range.  A launch without x3 reads only the hi plane of a Pair."""
+        scale) so that its lo plane stays in fp16's normal range.  A launch without x3 reads only the hi plane of a Pair.
+        blur (with shuffle): the ICNR blur runs in the epilogue of the PixelShuffle launch (havc_conv_desc.blur)."""
         Cout, Cin = w.shape[0], w.shape[1]
         h0, h1 = hi_of(src0), hi_of(src1) if src1 is not None else None
         storage = [h0.shape[-1]] + ([h1.shape[-1]] if h1 is not None else [])
@@ -153,7 +155,8 @@ class LaunchProgram:
             scale = (torch.ones(Cout) if scale is None else scale.float().cpu()) / g
             shift = torch.zeros(Cout) if shift is None else shift
         else:
-            wp, meta = ops.pack_conv_weight(w, cin_splits, dtype=self.dtype, shuffle=shuffle, cin_storage=storage)
+            wp, meta = ops.pack_conv_weight(w, cin_splits, dtype=self.dtype, shuffle=("blur" if (shuffle and blur) else shuffle),
+                                            cin_storage=storage)
         wp = wp.to(self.dev)
         self.keep.append(wp)
         n_total = meta["rows"]
@@ -178,7 +181,8 @@ class LaunchProgram:
                            bias=pc(bias, 0.0), scale=pc(scale, 1.0), shift=pc(shift, 0.0), relu1=relu1, relu2=relu2,
                            residual=hi_of(residual), out_space=(B, H, W), shuffle=shuffle, group_n=meta.get("group_n", 0),
                            c_store=pad_to(c_real, 8), up=up, oy=oy, ox=ox, leaky1=leaky1, head_w=head_w, head_out=head_out,
-                           bn=n_total if head_w is not None else None, name=name, src0_lo=lo(src0), src1_lo=lo(src1),
+                           bn=(4 * ops.BLUR_CW) if blur else (n_total if head_w is not None else None), name=name,
+                           box=(16, 8, 1) if blur else None, blur=blur, src0_lo=lo(src0), src1_lo=lo(src1),
                            weight_lo=wl, out_lo=lo(out), residual_lo=lo(residual))
         if flops is None:
             flops = 2.0 * B * H * W * Cout * Cin * len(taps)
@@ -332,8 +336,11 @@ class UnetProgram(LaunchProgram):
 
         # ---- layers[8] PixelShuffle_ICNR; layers[9] MergeLayer(dense); layers[10] res_block; layers[11] head -------
         w8 = folded_weight(sd, "layers.8.conv.0")
-        t8 = self.conv("shuf8.conv", y, w8, bias=sd["layers.8.conv.0.bias"].float(), relu1=True, shuffle=True)
-        u = self.blur("shuf8.blur", t8)                         # [B,S,S,cu_s]: the 'x' half of cat([x, x.orig])
+        if self._fuse_blur(y):                                  # [B,S,S,cu_s]: the 'x' half of cat([x, x.orig])
+            u = self.conv("shuf8.conv+blur", y, w8, bias=sd["layers.8.conv.0.bias"].float(), relu1=True, shuffle=True, blur=True)
+        else:
+            t8 = self.conv("shuf8.conv", y, w8, bias=sd["layers.8.conv.0.bias"].float(), relu1=True, shuffle=True)
+            u = self.blur("shuf8.blur", t8)
         self.tap("shuf8", u)
         cu = w8.shape[0] // 4                                   # real channels of u (256 wide / 300 deep)
         cu_s = u.shape[-1]                                      # storage width (multiple of 64)
@@ -400,6 +407,12 @@ class UnetProgram(LaunchProgram):
         self.tap("logits", self.logits)
         self.head_flops = 0.0
 
+    def _fuse_blur(self, src) -> bool:
+        """Fuse the ICNR blur into the PixelShuffle launch (halo recompute: 15 x 7 useful pixels per 16 x 8 tile) where the
+        tensor is big enough for the saved HBM round trip (write + read + write of the shuffled tensor) to outweigh the 22 % of
+        recomputed 1x1-conv rows: the 48 x 48 inputs and up (96 % of the blur bytes of the wide net)."""
+        return FUSE_BLUR and min(src.shape[1], src.shape[2]) >= 48
+
     def _fold_bn(self, p_conv, p_bn):
         w = self.sd[p_conv + ".weight"].float()
         sc, sh = bn_affine(self.sd, p_bn)
@@ -452,8 +465,11 @@ class UnetProgram(LaunchProgram):
         # shuf: conv1x1 (no bias) -> BN -> ReLU -> PixelShuffle -> blur; BN folds into the conv (exact: 1x1, no pad)
         ws = folded_weight(sd, p + ".shuf.conv.0")
         sc, sh = bn_affine(sd, p + ".shuf.conv.1")
-        t = self.conv(p + ".shuf.conv", up_in, ws * sc.view(-1, 1, 1, 1), bias=sh, relu1=True, shuffle=True)
-        u = self.blur(p + ".shuf.blur", t)
+        if self._fuse_blur(up_in):
+            u = self.conv(p + ".shuf.conv+blur", up_in, ws * sc.view(-1, 1, 1, 1), bias=sh, relu1=True, shuffle=True, blur=True)
+        else:
+            t = self.conv(p + ".shuf.conv", up_in, ws * sc.view(-1, 1, 1, 1), bias=sh, relu1=True, shuffle=True)
+            u = self.blur(p + ".shuf.blur", t)
         if tuple(u.shape[1:3]) != tuple(skip.shape[1:3]):
             raise ValueError("up-path / skip size mismatch (odd render_factor) is not supported")
         sc, sh = bn_affine(sd, p + ".bn")
@@ -496,17 +512,21 @@ class UnetProgram(LaunchProgram):
         self.ops.append(Op(p + ".value_t", op.launch, flops=2.0 * B * N * Cc * Cc, kind="gemm"))
         self.keep.append(op)
         # S[b, j, i] = sum_c g[b,j,c] f[b,i,c]
-        Sx = self.buf(B, 1, N, N, dtype=torch.float32)
+        # fp16 path: the N x N logits make their HBM round trip as fp16 through the TMA-store epilogue (|S| ~ 40 at most; the 2^-11
+        # rounding disappears in the soft-max: tools/precision_emulator.py); bf16's 8 mantissa bits would not do, it keeps fp32
+        s16 = self.dtype == torch.float16 and N % 64 == 0
+        Sx = self.buf(B, 1, N, Ns, zero=True) if s16 else self.buf(B, 1, N, N, dtype=torch.float32)
         op = ops.make_conv(k, q.view(B, N, 1, dp), Sx, [(0, 0, 0, 0)], n_total=pad_to(N, 16), b_batched=True,
                            out_space=(B, 1, N), c_store=pad_to(N, 8), name=p + ".logits")
         self.ops.append(Op(p + ".logits", op.launch, flops=2.0 * B * N * N * d, kind="gemm"))
         self.keep.append(op)
         P = self.buf(B, 1, N, Ns, zero=True)
         sp, pp, hd, lib = Sx.data_ptr(), P.data_ptr(), self.hd, self.lib
+        s_dt, s_stride = (_lib.HAVC_F16, Ns) if s16 else (_lib.HAVC_F32, N)
 
         def softmax(stream):
-            _lib.check(lib.havc_softmax_rows(sp, pp, B * N, N, N, Ns, hd, stream), p + ".softmax")
-        self.aux(p + ".softmax", softmax, nbytes=6.0 * B * N * N)
+            _lib.check(lib.havc_softmax_rows(sp, s_dt, pp, B * N, N, s_stride, Ns, hd, stream), p + ".softmax")
+        self.aux(p + ".softmax", softmax, nbytes=(4.0 if s16 else 6.0) * B * N * N)
         # out[b, j, c] = x[b,j,c] + gamma * sum_i P[b,j,i] Ht[b,c,i]
         out = self.buf(B, H, W, Cc, zero=True)
         gs = self.dev_f32(torch.full((pad_to(Cc, 16),), gamma))
