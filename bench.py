@@ -103,8 +103,8 @@ def load_peaks():
 
 def load_traffic(batch: int):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant conv_gemm launch (res.conv0) from the
-    committed `ncu --set full` capture (profiles/r01_roofline_traffic.json), scaled linearly to this batch."""
-    p = os.path.join(ROOT, "profiles", "r01_roofline_traffic.json")
+    committed `ncu --set full` capture (profiles/r02_roofline_traffic.json), scaled linearly to this batch."""
+    p = os.path.join(ROOT, "profiles", "r02_roofline_traffic.json")
     if not os.path.exists(p):
         return None
     d = json.load(open(p))

@@ -161,3 +161,24 @@ def test_colorizer_frame_size_differs_from_render_size(H, W, rf, frame_size):
     assert_mean_gate(m)
     ref_skip = pipeline_oracle.havc_colorizer_frame(sd, np.transpose(frames[1], (1, 2, 0)), rf, frame_size=frame_size, skip=True)
     assert np.array_equal(np.transpose(out[1], (1, 2, 0)), ref_skip), "a scene-change-skipped frame is the uncoloured squeeze path"
+
+
+@pytest.mark.parametrize("arch,rf", [("wide", 5), ("deep", 5), ("wide", 7)])
+def test_odd_render_factor(arch, rf):
+    """Odd render factors (legal in the reference: 10..64, every preset value of HAVC_main is even but ddcolor_rf = 0 / custom
+    values are not): S = 16 * odd, the encoder's last stage is ceil(odd / 2) wide, the first U-Net block's up path comes out one
+    pixel larger than its skip and the reference resizes it with F.interpolate(mode='nearest') (unet.py:201-203) - a crop for a
+    one-pixel mismatch.  The attention runs on (S / 8)^2 = 4 * odd^2 tokens (not a multiple of 8)."""
+    from oracle import metrics, pipeline_oracle
+    from vsdeoldify_b200.engine import DeoldifyEngine
+    sd = _sd(arch)
+    H, W, B = 130, 176, 2
+    eng = DeoldifyEngine(sd, W, H, render_factor=rf, batch=B, dtype=torch.float16)
+    assert eng.N == rf * 16 and eng.N % 32 == 16
+    frames = _frames(B, H, W, seed=71)
+    out = eng.colorize_batch(frames)
+    for i in range(B):
+        ref = pipeline_oracle.havc_colorizer_frame(sd, np.transpose(frames[i], (1, 2, 0)), rf)
+        m = metrics.frame_parity(np.transpose(out[i], (1, 2, 0)), ref)
+        print(arch, rf, i, m)
+        assert_mean_gate(m, (arch, rf, i))

@@ -315,22 +315,48 @@ class DeoldifyEngine:
             self.compute.wait_event(ev["out"])               # d_out of this slot has been downloaded
         self.run_slot(s)
         ev["done"].record(self.compute)
+        ob = self._acquire_out()                             # a pinned result buffer no delivered frame references any more
         with torch.cuda.stream(self.copy_out):
             self.copy_out.wait_event(ev["done"])
-            self.h_out[s].copy_(self.d_out[s], non_blocking=True)
+            ob[0].copy_(self.d_out[s], non_blocking=True)
             ev["out"].record(self.copy_out)
-        ev["busy"], ev["used"] = True, True
-        return (s, n)
+        ev["busy"], ev["used"], ev["ob"] = True, True, ob
+        return (s, n, ob)
+
+    def _acquire_out(self):
+        """(pinned tensor, its numpy view) from the result-buffer pool: the first one whose numpy view is referenced by nobody
+        else (frames handed out by collect_view() are views of it and keep it busy through `.base`), else a new one."""
+        import sys
+        if not hasattr(self, "_out_pool"):
+            self._out_pool = []                             # separate from h_out (the synchronous / streaming APIs own those)
+        for ob in self._out_pool:
+            if sys.getrefcount(ob[1]) <= 2 and not any(ob is e.get("ob") for e in getattr(self, "_ev", [])):
+                return ob
+        t = torch.empty(self.B, 3, self.H, self.W, dtype=torch.uint8).pin_memory()
+        ob = (t, t.numpy())
+        self._out_pool.append(ob)
+        return ob
+
+    def collect_view(self, ticket) -> np.ndarray:
+        """Wait for a submitted batch and return its uint8 [n, 3, H, W] result as a VIEW of the pinned buffer it was downloaded
+        into: no host copy.  The buffer returns to the pool when the last view of it is dropped."""
+        s, n, ob = ticket
+        ev = self._ev[s]
+        ev["out"].synchronize()
+        ev["busy"] = False
+        ev["ob"] = None
+        return ob[1][:n]
 
     def collect(self, ticket, out: Optional[np.ndarray] = None, pool=None) -> np.ndarray:
         """Wait for a submitted batch and return its uint8 [n, 3, H, W] result: a fresh copy, or `out[:n]` when the caller
         supplies a (recycled) array - a fresh 200 MB allocation costs ten times the copy itself in page faults.  `pool`
         (a concurrent.futures executor) spreads the per-frame copies over host threads (numpy releases the GIL)."""
-        s, n = ticket
+        s, n, ob = ticket
         ev = self._ev[s]
         ev["out"].synchronize()
         ev["busy"] = False
-        src = self.h_out[s][:n].numpy()
+        ev["ob"] = None
+        src = ob[1][:n]
         if out is None:
             return src.copy()
         dst = out[:n]

@@ -166,7 +166,10 @@ class ShardedRenderer:
                     if len(inflight) < depth:
                         continue                      # try to queue a second batch behind it before waiting
                 jd, srcs, ticket = inflight.popleft()
-                out = eng.collect(ticket, out=self._result_buf(r), pool=self.copy_pool)
+                if hasattr(eng, "collect_view"):      # frames adopt views of the pinned download buffer: no host copy
+                    out = eng.collect_view(ticket)
+                else:
+                    out = eng.collect(ticket, out=self._result_buf(r), pool=self.copy_pool)
                 frames = [self.make_frame(f, out[k]) for k, f in enumerate(srcs)]
                 with self.cv:
                     self.results[jd] = frames

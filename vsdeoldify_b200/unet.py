@@ -254,9 +254,8 @@ class UnetProgram(LaunchProgram):
 
     def __init__(self, sd: SD, batch: int, size: int, dtype: torch.dtype = torch.float16, device="cuda",
                  keep_taps: bool = False, x: Optional[torch.Tensor] = None, precision: Optional[str] = None):
-        if size % 32 != 0:
-            raise ValueError(f"render size {size} must be a multiple of 32 (even render_factor); the nearest-"
-                             "neighbour up-path resize of unet.py:201-203 is not implemented")
+        if size % 16 != 0 or size < 32:
+            raise ValueError(f"render size {size} must be render_factor * 16 (a multiple of 16, at least 32)")
         super().__init__(sd, batch, size, dtype, device, keep_taps, precision)
         self.bottleneck = "layers.0.4.0.conv3.weight" in sd
         if self.precision == "auto":
@@ -471,7 +470,13 @@ class UnetProgram(LaunchProgram):
             t = self.conv(p + ".shuf.conv", up_in, ws * sc.view(-1, 1, 1, 1), bias=sh, relu1=True, shuffle=True)
             u = self.blur(p + ".shuf.blur", t)
         if tuple(u.shape[1:3]) != tuple(skip.shape[1:3]):
-            raise ValueError("up-path / skip size mismatch (odd render_factor) is not supported")
+            # odd render factors: the encoder halves 16*odd/16 = odd with a ceil, so the up path is one pixel larger than the skip
+            # and the reference resizes it with F.interpolate(mode='nearest') (unet.py:201-203 / 87-89).  For in = out + 1 the
+            # nearest source index floor(d * (out + 1) / out) is d itself: the resize is a crop of the last row / column.
+            Hs, Ws = int(skip.shape[1]), int(skip.shape[2])
+            if (int(u.shape[1]), int(u.shape[2])) != (Hs + 1, Ws + 1):
+                raise ValueError(f"up-path {tuple(u.shape[1:3])} vs skip {(Hs, Ws)}: only the one-pixel mismatch of odd render factors is handled")
+            u = u[:, :Hs, :Ws, :]
         sc, sh = bn_affine(sd, p + ".bn")
         sb = self.affine(p + ".skip_bn_relu", skip, sc, sh, True)
         cu = ws.shape[0] // 4
@@ -515,14 +520,15 @@ class UnetProgram(LaunchProgram):
         # fp16 path: the N x N logits make their HBM round trip as fp16 through the TMA-store epilogue (|S| ~ 40 at most; the 2^-11
         # rounding disappears in the soft-max: tools/precision_emulator.py); bf16's 8 mantissa bits would not do, it keeps fp32
         s16 = self.dtype == torch.float16 and N % 64 == 0
-        Sx = self.buf(B, 1, N, Ns, zero=True) if s16 else self.buf(B, 1, N, N, dtype=torch.float32)
+        # rows padded to Ns either way: with N % 8 != 0 (odd render factors) the epilogue stores up to 7 pad columns per row
+        Sx = self.buf(B, 1, N, Ns, zero=True) if s16 else self.buf(B, 1, N, Ns, dtype=torch.float32, zero=True)
         op = ops.make_conv(k, q.view(B, N, 1, dp), Sx, [(0, 0, 0, 0)], n_total=pad_to(N, 16), b_batched=True,
                            out_space=(B, 1, N), c_store=pad_to(N, 8), name=p + ".logits")
         self.ops.append(Op(p + ".logits", op.launch, flops=2.0 * B * N * N * d, kind="gemm"))
         self.keep.append(op)
         P = self.buf(B, 1, N, Ns, zero=True)
         sp, pp, hd, lib = Sx.data_ptr(), P.data_ptr(), self.hd, self.lib
-        s_dt, s_stride = (_lib.HAVC_F16, Ns) if s16 else (_lib.HAVC_F32, N)
+        s_dt, s_stride = (_lib.HAVC_F16 if s16 else _lib.HAVC_F32), Ns
 
         def softmax(stream):
             _lib.check(lib.havc_softmax_rows(sp, s_dt, pp, B * N, N, s_stride, Ns, hd, stream), p + ".softmax")
