@@ -48,7 +48,7 @@ def main():
     for ndev in sorted({1, a.gpus}):
         out = havc.HAVC_colorizer(src_clip(), method=0, deoldify_p=[0, bench.RF, 1.0, 0.0], ddcolor_p=[1, bench.RF, 1.0, 0.0, True],
                                   device_index=list(range(ndev)) if ndev > 1 else 0)
-        for i in range(min(n, 2 * a.batch * ndev)):        # warm: every engine has rendered
+        for i in range(min(n, 8 * a.batch * ndev)):        # warm: every engine has rendered and pinned its result-buffer pool
             out.get_frame(i)
         t0 = time.perf_counter()
         acc, ok_order = 0, True
@@ -65,6 +65,11 @@ def main():
                     res["bytes_equal_single_gpu"] = bool(res["bytes_equal_single_gpu"] and np.array_equal(planes, ref_frames[i]))
         dt = time.perf_counter() - t0
         res[f"fps_{ndev}gpu"] = n / dt
+        fn = getattr(out, "_frame_fn", None)
+        rend = getattr(fn, "__defaults__", [None])[0] if fn is not None and getattr(fn, "__defaults__", None) else None
+        if rend is not None and hasattr(rend, "stats"):
+            res[f"worker_seconds_{ndev}gpu"] = [{k: round(v, 3) for k, v in st.items()} for st in rend.stats]
+            res[f"out_pool_{ndev}gpu"] = [len(getattr(e, "_out_pool", [])) for e in rend.engines]
         res[f"order_ok_{ndev}gpu"] = bool(ok_order)
         del out
         torch.cuda.empty_cache()

@@ -328,7 +328,13 @@ class DeoldifyEngine:
         else (frames handed out by collect_view() are views of it and keep it busy through `.base`), else a new one."""
         import sys
         if not hasattr(self, "_out_pool"):
-            self._out_pool = []                             # separate from h_out (the synchronous / streaming APIs own those)
+            # separate from h_out (the synchronous / streaming APIs own those).  Eight buffers cover two batches in flight plus
+            # the batches a clip adapter keeps cached around its cursor; they are pinned ONCE here (pinning 200 MB takes ~0.14 s
+            # and stalls the device queue: measured, so growing the pool inside the steady state is what must not happen)
+            self._out_pool = []
+            for _ in range(8):
+                t = torch.empty(self.B, 3, self.H, self.W, dtype=torch.uint8).pin_memory()
+                self._out_pool.append((t, t.numpy()))
         for ob in self._out_pool:
             if sys.getrefcount(ob[1]) <= 2 and not any(ob is e.get("ob") for e in getattr(self, "_ev", [])):
                 return ob

@@ -50,6 +50,7 @@ _DTYPE = {"fp16": torch.float16, "bf16": torch.bfloat16}[os.environ.get("HAVC_B2
 # host threads for the big plane copies of the clip adapters (numpy releases the GIL while it copies)
 # (one process per GPU: share the host's cores between the local ranks)
 _LOCAL_RANKS = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")) or 1))
+_ZERO_COPY = os.environ.get("HAVC_B200_ZERO_COPY", "1") != "0"          # A/B switch
 _COPY_POOL = ThreadPoolExecutor(max_workers=max(1, min(16, (os.cpu_count() or 2) // (2 * _LOCAL_RANKS))))
 
 
@@ -171,7 +172,7 @@ class _ColorizedClip:
 
     def _finish(self, job):
         n, srcs, ticket = job
-        if hasattr(self.engine, "collect_view"):      # frames adopt views of the pinned download buffer: no host copy of the result
+        if _ZERO_COPY and hasattr(self.engine, "collect_view"):   # frames adopt views of the pinned download buffer: no host copy
             self._store(n, srcs, self.engine.collect_view(ticket))
         else:
             self._store(n, srcs, self.engine.collect(ticket, out=self._result_buf(), pool=_COPY_POOL))

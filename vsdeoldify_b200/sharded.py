@@ -20,12 +20,17 @@ from __future__ import annotations
 import bisect
 import sys
 import threading
+import time
 from collections import OrderedDict, deque
 from typing import Callable, List, Optional, Sequence, Tuple
 
 import numpy as np
 
+import os
+
 from . import partition as part
+
+ZERO_COPY = os.environ.get("HAVC_B200_ZERO_COPY", "1") != "0"          # A/B switch
 
 
 def plan_jobs(n_frames: int, world: int, batch: int, mode: str = "block") -> List[Tuple[int, int, int]]:
@@ -58,11 +63,13 @@ class ShardedRenderer:
         self.results: "OrderedDict[int, list]" = OrderedDict()
         self.error: Optional[BaseException] = None
         # jobs that may be rendered ahead of the most recently requested one; None = unbounded (whole-clip rendering: every
-        # result stays in host memory until close()).  Streaming default: two jobs per GPU.
+        # result stays in host memory until close()).  Streaming default: four jobs per GPU - with two, a worker that has just
+        # submitted a batch finds no second job inside the window, blocks in collect() for the whole GPU time of the first
+        # and never overlaps the next upload with it (measured: 35-45 ms per 23 ms batch).
         if window is None and partition == "interleaved":
-            window = 2 * self.world
+            window = 4 * self.world
         self.window = window
-        self.keep_behind = 2 * self.world                                          # finished jobs kept behind the cursor
+        self.keep_behind = self.world                                              # finished jobs kept behind the cursor
         self.cursor = 0                                                            # job of the most recent request
         self.cv = threading.Condition()
         self.stop = False
@@ -70,6 +77,8 @@ class ShardedRenderer:
         self.make_frame = make_frame or _adopt_planes
         self.require_scene_props = require_scene_props
         self._bufs: List[List[np.ndarray]] = [[] for _ in range(self.world)]
+        # per-worker wall-clock accounting (seconds): where a GPU's host thread spends its time
+        self.stats = [dict(fetch=0.0, copy_in=0.0, submit=0.0, collect=0.0, frames=0.0, wait=0.0, jobs=0) for _ in range(self.world)]
         self.threads = [threading.Thread(target=self._worker, args=(r,), daemon=True, name=f"havc-gpu{r}") for r in range(self.world)]
         for t in self.threads:
             t.start()
@@ -119,6 +128,8 @@ class ShardedRenderer:
         return scene_skip_flags(i0, srcs, self.require_scene_props)
 
     def _result_buf(self, r: int) -> np.ndarray:
+        if self.window is None:                              # whole-clip rendering: every result stays alive, nothing to recycle
+            return np.empty((self.B, 3, self.clip.height, self.clip.width), np.uint8)
         for b in self._bufs[r]:
             if sys.getrefcount(b) <= 3:
                 return b
@@ -137,6 +148,7 @@ class ShardedRenderer:
             inflight: deque = deque()
             depth = getattr(eng, "n_slots", 1)
             while True:
+                tw = time.perf_counter()
                 with self.cv:
                     j = None
                     while not self.stop:
@@ -148,9 +160,12 @@ class ShardedRenderer:
                         return
                     if j is not None:
                         self.state[j] = self.RUNNING
+                self.stats[r]["wait"] += time.perf_counter() - tw
                 if j is not None:
                     i0, i1, _ = self.jobs[j]
+                    t0 = time.perf_counter()
                     srcs = [self.clip.get_frame(i) for i in range(i0, i1)]
+                    t1 = time.perf_counter()
                     buf = eng.next_input()
 
                     def put(k, buf=buf, srcs=srcs):
@@ -161,16 +176,26 @@ class ShardedRenderer:
                     else:
                         for k in range(len(srcs)):
                             put(k)
+                    t2 = time.perf_counter()
                     ticket = eng.submit(None, skip=self._skip_flags(i0, srcs), n=len(srcs))
+                    t3 = time.perf_counter()
+                    st = self.stats[r]
+                    st["fetch"] += t1 - t0; st["copy_in"] += t2 - t1; st["submit"] += t3 - t2; st["jobs"] += 1
                     inflight.append((j, srcs, ticket))
                     if len(inflight) < depth:
                         continue                      # try to queue a second batch behind it before waiting
                 jd, srcs, ticket = inflight.popleft()
-                if hasattr(eng, "collect_view"):      # frames adopt views of the pinned download buffer: no host copy
+                t4 = time.perf_counter()
+                # bounded window: frames adopt views of the pinned download buffer (no host copy of the result); whole-clip rendering
+                # (window None) would pin the entire clip, so it copies into pageable arrays instead
+                if ZERO_COPY and self.window is not None and hasattr(eng, "collect_view"):
                     out = eng.collect_view(ticket)
                 else:
                     out = eng.collect(ticket, out=self._result_buf(r), pool=self.copy_pool)
+                t5 = time.perf_counter()
                 frames = [self.make_frame(f, out[k]) for k, f in enumerate(srcs)]
+                self.stats[r]["collect"] += t5 - t4
+                self.stats[r]["frames"] += time.perf_counter() - t5
                 with self.cv:
                     self.results[jd] = frames
                     self.state[jd] = self.DONE
