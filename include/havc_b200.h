@@ -298,6 +298,27 @@ int havc_select_frames(uint8_t *dst, const uint8_t *src, const uint8_t *skip, in
  * Restated from the VapourSynth sources; the library is absent here, so this edge is parity-unpinned. */
 int havc_vs_merge_u8(const uint8_t *a, const uint8_t *b, uint8_t *out, long long n, double weight, void *stream);
 
+/* ---- zimg-backed steps of vs_tweak (vsdeoldify/vsslib/vsfilters.py:753-850; also vs_clip_color_stabilizer :38-61 and the
+ * luma_mask_sat branch of LumaMaskedMerge, mcomb.py:243), restated from the published zimg algorithm (zimg / VapourSynth are not
+ * available here: parity unpinned against the real library, bit-exact against oracle/zimg_oracle.py).  Planar u8 batches. -------- */
+
+/* clip.resize.Bicubic(format=YUV420P8, matrix_s="709", range_s="full") (vsfilters.py:790): rgb u8 [B][3][H][W] -> y u8 [B][H][W],
+ * uv u8 [B][2][H/2][W/2].  scratch444: float [B][2][H][W]; scratch_v: float [B][2][H/2][W].  Tables (host built,
+ * resample.chroma420_tables): vertical H -> H/2 and horizontal W -> W/2 Bicubic with 'left' chroma siting, weights [out][T]. */
+int havc_zimg_rgb_to_yuv420p8(const uint8_t *rgb, uint8_t *y, uint8_t *uv, float *scratch444, float *scratch_v, int B, int H, int W,
+                              const int *start_v, const float *w_v, int Tv, const int *start_h, const float *w_h, int Th, void *stream);
+/* The std.Expr hue / saturation rotation of (U, V) (vsfilters.py:797-826; c1 = cos(hue) * sat, c2 = sin(hue) * sat; do_uv = 0
+ * skips it) and the std.Lut brightness / contrast table on Y (:828-845; lut = 256 device bytes or NULL), in place. */
+int havc_zimg_tweak_yuv(uint8_t *y, uint8_t *uv, int B, int H, int W, float c1, float c2, int do_uv, const uint8_t *lut, void *stream);
+/* clip.resize.Bicubic(format=RGB24, matrix_in_s="709", range_s="full", dither_type="error_diffusion") (vsfilters.py:848): the way
+ * back; dither = 1 runs zimg's Floyd-Steinberg error diffusion per plane (a warp-level wavefront), 0 rounds.
+ * scratch_h: float [B][2][H/2][W]; scratch_rgb: float [B][3][H][W] (dither only). */
+int havc_zimg_yuv420p8_to_rgb(const uint8_t *y, const uint8_t *uv, uint8_t *rgb, float *scratch_h, float *scratch_rgb, int B, int H, int W,
+                              const int *start_h, const float *w_h, int Th, const int *start_v, const float *w_v, int Tv, int dither,
+                              void *stream);
+/* The BT.709 RGB -> YCbCr matrix (inverse = 0) or its inverse (1) as 9 floats, row major (host memory). */
+int havc_zimg_inverse_matrix(float *out9, int inverse);
+
 #ifdef __cplusplus
 }
 #endif

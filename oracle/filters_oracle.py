@@ -471,9 +471,11 @@ def combine_models(a, b, method: int, weight: float, cmc_p=(0.15, True, 20, 24),
         m = image_weighted_merge(a, b, min(weight, 0.6))
         return image_weighted_merge(ccm, m, 0.3)
     if method == 4:
-        if lmm_p[2] < 1:
-            raise NotImplementedError("luma_mask_sat < 1 needs vs_tweak (zimg YUV420 round trip)")
-        return luma_masked_merge(a, b, a, lmm_p[0], lmm_p[1], weight)
+        c = a
+        if lmm_p[2] < 1:                      # mcomb.py:239-242: clipc = vs_tweak(clipa, sat=luma_mask_sat) (zimg round trip, restated)
+            from . import zimg_oracle
+            c = zimg_oracle.vs_tweak(a, sat=lmm_p[2])
+        return luma_masked_merge(a, b, c, lmm_p[0], lmm_p[1], weight)
     if method == 5:
         return adaptive_luma_merge(a, b, alm_p[0], alm_p[1], weight, alm_p[2])
     if method == 6:

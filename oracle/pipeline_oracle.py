@@ -31,7 +31,8 @@ def net_output_square(sd, rgb_sq: np.ndarray) -> np.ndarray:
 def havc_colorizer_frame(sd, frame: np.ndarray, render_factor: int = 24, kernel: str = "spline64",
                          return_stages: bool = False, skip: bool = False, sd_other=None, video_weight: float = 0.5,
                          zhang=None, method: int = 0, merge_weight: float = 0.4, hue_adjust: str = "none", cmc_p=None,
-                         lmm_p=None, alm_p=None, crt_p=None, invert: bool = False, ddtweak=None, frame_size=None, memo=None):
+                         lmm_p=None, alm_p=None, crt_p=None, invert: bool = False, ddtweak=None, frame_size=None, memo=None,
+                         sat=(1.0, 1.0), hue=(0.0, 0.0)):
     """frame: uint8 [H,W,3].  Returns uint8 [H,W,3] (and the intermediate stages on request).
     skip: the scene-change gate returned the squeezed frame unchanged (vsslib/vsmodels.py:221-224).
     sd_other: 'stable'/'artistic' generator blended with the video one at S x S (visualize.py:118-137).
@@ -42,6 +43,7 @@ def havc_colorizer_frame(sd, frame: np.ndarray, render_factor: int = 24, kernel:
     several merge methods can be checked against one set of network evaluations."""
     from . import filters_oracle as fo
     from . import zhang_oracle
+    from . import zimg_oracle as zo
     H, W = frame.shape[:2]
     # frame_size (vsdeoldify/__init__.py:2502) = min(max(ddcolor_rf, deoldify_rf)*16, W); the DeOldify filter itself renders at
     # render_factor*16 and stretches with Pillow BILINEAR when the two differ (deoldify/filters.py:37-41,70-73,82-84)
@@ -61,8 +63,9 @@ def havc_colorizer_frame(sd, frame: np.ndarray, render_factor: int = 24, kernel:
         return cached(("deoldify", id(sd_)), lambda: colorizer_filter(sd_, small, render_factor))
 
     small = cached("small", lambda: px.resize_plane_u8(frame, S, S, kernel))   # clip.resize.Spline64(S, S)
-    if skip:
-        colored = small
+    if skip:        # the selectors returned the frame unchanged; the clip-level vs_tweak of vs_sc_combine_models still runs on it
+        k = 1 if method == 1 else 0
+        colored = zo.vs_tweak(small, hue=hue[k], sat=sat[k])
     else:
         colored = None
         if method != 1:
@@ -81,11 +84,14 @@ def havc_colorizer_frame(sd, frame: np.ndarray, render_factor: int = 24, kernel:
             if ddtweak is not None:            # vs_recover_clip_luma(clip, clipb_rgb) (vsmodels.py:367-368)
                 clipb = px.chroma_post_process(clipb, small)
             if method == 1:
-                colored = clipb
+                colored = zo.vs_tweak(clipb, hue=hue[1], sat=sat[1])           # mcomb.py:166-169
             else:
                 a, b = (clipb, colored) if invert else (colored, clipb)
+                a, b = zo.vs_tweak(a, hue=hue[0], sat=sat[0]), zo.vs_tweak(b, hue=hue[1], sat=sat[1])   # mcomb.py:154-169
                 kw = {k: v for k, v in dict(cmc_p=cmc_p, lmm_p=lmm_p, alm_p=alm_p, crt_p=crt_p).items() if v is not None}
                 colored = fo.combine_models(a, b, method, merge_weight, **kw)
+        if method == 0 or zhang is None:
+            colored = zo.vs_tweak(colored, hue=hue[0], sat=sat[0])             # mcomb.py:161-164 (clipb is None)
     up = px.resize_plane_u8(colored, W, H, kernel)                    # clip_lowres.resize.Spline64(W, H)
     out = px.chroma_post_process(up, frame)                           # vs_recover_clip_luma
     if return_stages:

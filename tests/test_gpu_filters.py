@@ -228,3 +228,42 @@ def test_chroma_retention_merge_with_chroma_resize():
             m = metrics.frame_parity(r, want)
             assert m["mean_de00"] < 0.02 and m["n_err_gt2"] <= 2e-4 * m["n_values"], (w, crt, li, m)
             assert np.abs(r.astype(int) - a[li].astype(int)).max() > 4, "the merge must change clip_a"
+
+
+@pytest.mark.parametrize("H,W", [(64, 96), (130, 70)])
+def test_vs_tweak_zimg_round_trip_bit_exact_vs_restatement(H, W):
+    """vs_tweak (vsfilters.py:753-850): RGB24 -> YUV420P8 (Bicubic, BT.709 full range, 'left' chroma siting) -> std.Expr hue / sat
+    -> std.Lut bright / cont -> RGB24 with Floyd-Steinberg error diffusion, against oracle/zimg_oracle.py (the restatement of the
+    published zimg algorithm; VapourSynth is not installable here, so the restatement itself is unpinned): bit-exact, including
+    the wavefront-parallel error diffusion."""
+    from oracle import synth_weights, zimg_oracle as zo
+    from vsdeoldify_b200.filters import FilterBank
+    B = 3
+    imgs = [np.stack([synth_weights.make_test_frame(900 + 7 * i + c, H, W).numpy() for c in range(3)], -1) for i in range(B)]
+    imgs[2] = np.repeat(imgs[2][..., :1], 3, -1)                          # a gray frame: the round trip is the identity
+    bank = FilterBank(B, H, W, "cuda:0")
+    t = planar(imgs)
+    out = torch.empty_like(t)
+    assert not bank.vs_tweak(t, out)                                        # identity parameters: untouched
+    for kw in (dict(sat=0.8), dict(hue=12.0, sat=1.15), dict(sat=0.0), dict(bright=10.0, cont=1.1), dict(hue=-30.0, bright=-0.05)):
+        assert bank.vs_tweak(t, out, **kw)
+        torch.cuda.synchronize()
+        for i, r in enumerate(hwc(out)):
+            same(r, zo.vs_tweak(imgs[i], **kw), f"vs_tweak {kw} frame {i}")
+    assert bank.vs_tweak(t, out, sat=0.999999)                              # nothing but the 4:2:0 round trip + dither
+    torch.cuda.synchronize()
+    assert np.array_equal(hwc(out)[2], imgs[2])
+
+
+def test_luma_masked_merge_with_mask_saturation(bank, ab):
+    """LumaMaskedMerge(luma_mask_sat < 1) (mcomb.py:239-245): clip c = vs_tweak(clipa, sat)."""
+    a, b = ab
+    ta, tb = planar(a), planar(b)
+    out = torch.empty_like(ta)
+    H, W = a[0].shape[:2]
+    if H % 2 or W % 2:
+        pytest.skip("golden frames have an odd size")
+    bank.combine(ta, tb, out, 4, 0.5, lmm_p=[0.2, 0.7, 0.6])
+    torch.cuda.synchronize()
+    for li, r in enumerate(hwc(out)):
+        same(r, fo.combine_models(a[li], b[li], 4, 0.5, lmm_p=[0.2, 0.7, 0.6]), f"luma-masked merge with sat frame {li}")

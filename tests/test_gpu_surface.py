@@ -309,3 +309,26 @@ def test_havc_merge_with_clip_luma():
             got = np.stack([np.asarray(f[p]) for p in range(3)], -1)
             m = metrics.frame_parity(got, want)
             assert m["mean_de00"] < 0.02 and m["n_err_gt2"] <= 2e-4 * m["n_values"], (method, i, m)
+
+
+@pytest.mark.parametrize("method", [0, 2])
+def test_colorizer_sat_hue_tweak(method):
+    """deoldify_p / ddcolor_p saturation and hue (vs_tweak inside vs_sc_combine_models, mcomb.py:154-169) against the oracle of the
+    whole path with the restated zimg round trip."""
+    from oracle import metrics, pipeline_oracle
+    havc = _register()
+    _register_zhang(havc)
+    H, W, rf, n = 96, 176, 10, 2
+    clip, fr, props = _clip(n, H, W, seed=190)
+    out = havc.HAVC_colorizer(clip, method=method, mweight=0.4, deoldify_p=[0, rf, 0.85, 8.0], ddcolor_p=[2, rf, 1.2, -5.0, True])
+    sd = havc._REGISTERED["ColorizeVideo_gen"]
+    sdz = havc._REGISTERED[havc._ZHANG_FILES["siggraph17"]]
+    for i in range(n):
+        f = out.get_frame(i)
+        assert f.props == props[i]
+        ref = pipeline_oracle.havc_colorizer_frame(sd, np.transpose(fr[i], (1, 2, 0)), rf, zhang=("siggraph17", sdz) if method else None,
+                                                   method=method, merge_weight=0.4, hue_adjust="300:360|0.8,0.1", sat=(0.85, 1.2),
+                                                   hue=(8.0, -5.0))
+        img = np.stack([np.asarray(f[p]) for p in range(3)], -1)
+        m = metrics.frame_parity(img, ref)
+        assert m["mean_de00"] <= 0.5, (method, i, m)

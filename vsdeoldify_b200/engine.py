@@ -39,8 +39,10 @@ class DeoldifyEngine:
                  frame_size: Optional[int] = None, sd_other: Optional[Dict[str, torch.Tensor]] = None,
                  video_weight: float = 0.5, zhang: Optional[tuple] = None, merge: Optional[dict] = None,
                  hue_adjust: str = "none", run_deoldify: bool = True, ddtweak: Optional[dict] = None,
-                 precision: Optional[str] = None):
-        """zhang = (name, state_dict): the second colour model of HAVC_colorizer (vs_sc_ddcolor models 2 / 3,
+                 precision: Optional[str] = None, sat=(1.0, 1.0), hue=(0.0, 0.0)):
+        """sat / hue = (first clip, second clip): the vs_tweak of vs_sc_combine_models (mcomb.py:161-169; deoldify_p[2:4] and
+        ddcolor_p[2:4] of HAVC_colorizer), applied AFTER the optional clip swap, to every frame.
+        zhang = (name, state_dict): the second colour model of HAVC_colorizer (vs_sc_ddcolor models 2 / 3,
         vsslib/vsmodels.py:339-344), colourising the same S x S frame; hue_adjust: its vs_sc_adjust_clip_hue string
         (vsmodels.py:361-362); merge = dict(method, weight, cmc_p, lmm_p, alm_p, crt_p, invert) for
         vs_sc_combine_models (mcomb.py:125-192).  run_deoldify=False is method 1 (second model only).  ddtweak =
@@ -68,11 +70,15 @@ class DeoldifyEngine:
             if (sd_other is not None and run_deoldify) else None
         self.zhang = None
         self.merge, self.hue_adjust, self.ddtweak = merge, hue_adjust, ddtweak
-        if zhang is not None:
+        self.tweak = [(float(sat[i]), float(hue[i])) for i in (0, 1)]
+        self.has_tweak = any(t != (1.0, 0.0) for t in self.tweak)
+        if zhang is not None or self.has_tweak:
             from .filters import FilterBank
+            self.bank = FilterBank(B, S, S, self.dev)
+            self.tweaked = [torch.empty(B, 3, S, S, dtype=torch.uint8, device=self.dev) for _ in range(2)]
+        if zhang is not None:
             from .zhang import ZhangColorizer
             self.zhang = ZhangColorizer(zhang[1], zhang[0], B, S, dtype, device=self.dev, precision=precision)
-            self.bank = FilterBank(B, S, S, self.dev)
             self.colored_b = torch.empty(B, 3, S, S, dtype=torch.uint8, device=self.dev)
             self.colored_b2 = torch.empty(B, 3, S, S, dtype=torch.uint8, device=self.dev)
             self.merged = torch.empty(B, 3, S, S, dtype=torch.uint8, device=self.dev)
@@ -188,15 +194,25 @@ class DeoldifyEngine:
                     "recover_luma")
                 clipb = other
             self.bank.select_frames(clipb, self.rgb_small, skip, stream)        # scene-change gate of the 2nd model
-            if not self.run_deoldify:
+            if not self.run_deoldify:                                           # mcomb.py:166-169: only clipb, its own tweak
                 result = clipb
+                if self.bank.vs_tweak(clipb, self.tweaked[1], hue=self.tweak[1][1], sat=self.tweak[1][0], stream=stream):
+                    result = self.tweaked[1]
             else:
                 m = self.merge
                 a, b = (clipb, self.colored) if m.get("invert") else (self.colored, clipb)
+                # vs_tweak of both clips after the swap (mcomb.py:154-169): sat[0] / hue[0] go to whatever is clip a now
+                if self.bank.vs_tweak(a, self.tweaked[0], hue=self.tweak[0][1], sat=self.tweak[0][0], stream=stream):
+                    a = self.tweaked[0]
+                if self.bank.vs_tweak(b, self.tweaked[1], hue=self.tweak[1][1], sat=self.tweak[1][0], stream=stream):
+                    b = self.tweaked[1]
                 self.bank.combine(a, b, self.merged, m["method"], m["weight"], m["cmc_p"], m["lmm_p"], m["alm_p"], m["crt_p"],
                                   stream=stream)
                 self.bank.select_frames(self.merged, a, skip, stream)           # merge selectors return f[0].copy()
                 result = self.merged
+        elif self.has_tweak:                                                    # method 0: mcomb.py:161-164, clipa alone
+            if self.bank.vs_tweak(self.colored, self.tweaked[0], hue=self.tweak[0][1], sat=self.tweak[0][0], stream=stream):
+                result = self.tweaked[0]
         self._launch_post(slot, stream, result)
 
     # ---- frame_size != render_factor*16: the filter's own Pillow BILINEAR stretch around the generator ---------------

@@ -217,9 +217,11 @@ class FilterBank:
                 self.blend(res, t2, out, 0.3, stream)
             return
         if method == 4:                                            # LumaMaskedMerge
-            if lmm_p[2] < 1:
-                raise FilterError("LumaMaskedMerge with luma_mask_sat < 1 needs vs_tweak (zimg YUV420 round trip), not built")
-            _lib.check(lib.havc_luma_masked_merge(a.data_ptr(), b.data_ptr(), a.data_ptr(), out.data_ptr(), B, H, W, float(lmm_p[0]),
+            c = a
+            if lmm_p[2] < 1:                                       # mcomb.py:242-245: clipc = vs_tweak(clipa, sat=luma_mask_sat)
+                self.vs_tweak(a, t0, sat=float(lmm_p[2]), stream=stream)
+                c = t0
+            _lib.check(lib.havc_luma_masked_merge(a.data_ptr(), b.data_ptr(), c.data_ptr(), out.data_ptr(), B, H, W, float(lmm_p[0]),
                                                   float(lmm_p[1]), float(weight), stream), "luma_masked_merge")
             return
         if method == 5:                                            # AdaptiveLumaMerge
@@ -274,6 +276,58 @@ class FilterBank:
         if weight != 1:
             _lib.check(lib.havc_vs_merge_u8(a.data_ptr(), restored.data_ptr(), out.data_ptr(), out.numel(), float(weight), stream),
                        "vs_merge")
+
+    # ---- vs_tweak: the zimg YUV420P8 round trip (vsfilters.py:753-850) ---------------------------------------------
+    def _zimg_state(self):
+        if "zimg" not in self._luts:
+            import math
+            from . import resample
+            B, H, W, dev = self.B, self.H, self.W, self.dev
+            if H % 2 or W % 2:
+                raise FilterError("vs_tweak: the YUV420P8 round trip needs an even frame size")
+            up = lambda t: (torch.from_numpy(t[0]).to(dev), torch.from_numpy(np.ascontiguousarray(t[1])).to(dev), int(t[1].shape[1]))
+            dh, dv, uh, uv = (up(t) for t in resample.chroma420_tables(W, H))
+            f32 = dict(dtype=torch.float32, device=dev)
+            u8 = dict(dtype=torch.uint8, device=dev)
+            self._luts["zimg"] = dict(dh=dh, dv=dv, uh=uh, uv=uv, y=torch.empty(B, H, W, **u8), c=torch.empty(B, 2, H // 2, W // 2, **u8),
+                                      s444=torch.empty(B, 2, H, W, **f32), s_half=torch.empty(B, 2, H // 2, W, **f32),
+                                      s_rgb=torch.empty(B, 3, H, W, **f32), luts={})
+        return self._luts["zimg"]
+
+    def vs_tweak(self, img, out, hue: float = 0.0, sat: float = 1.0, bright: float = 0.0, cont: float = 1.0, gamma: float = 1.0,
+                 stream: int = 0) -> bool:
+        """vs_tweak (vsfilters.py:753-850) without gamma (std.Levels) / coring: RGB24 -> YUV420P8 (zimg Bicubic, BT.709 full
+        range) -> hue / saturation rotation of (U, V) -> brightness / contrast table on Y -> RGB24 with error-diffusion dither.
+        Returns False when it is the identity (`out` untouched).  The zimg steps are restated (library absent: parity unpinned)."""
+        import math
+        if hue == 0 and sat == 1 and bright == 0 and cont == 1 and gamma == 1:
+            return False
+        if gamma != 1:
+            raise FilterError("vs_tweak: gamma != 1 (std.Levels) is not built")
+        self._chk(img), self._chk(out)
+        z, lib, (B, H, W) = self._zimg_state(), self.lib, self._dims()
+        dh, dv, uh, uv = z["dh"], z["dv"], z["uh"], z["uv"]
+        _lib.check(lib.havc_zimg_rgb_to_yuv420p8(img.data_ptr(), z["y"].data_ptr(), z["c"].data_ptr(), z["s444"].data_ptr(),
+                                                 z["s_half"].data_ptr(), B, H, W, dv[0].data_ptr(), dv[1].data_ptr(), dv[2],
+                                                 dh[0].data_ptr(), dh[1].data_ptr(), dh[2], stream), "zimg.rgb_to_yuv420p8")
+        if -1.0 < bright < 1.0:
+            bright = bright * 255.0                                # vsfilters.py:792-793
+        lut = None
+        if bright != 0 or cont != 1:                               # vsfilters.py:828-841 (integer formats, no coring)
+            key = (float(bright), float(cont))
+            if key not in z["luts"]:
+                tab = np.array([min(max(int(i * cont + bright + 0.5), 0), 255) for i in range(256)], np.uint8)
+                z["luts"][key] = torch.from_numpy(tab).to(self.dev)
+            lut = z["luts"][key]
+        do_uv = hue != 0 or sat != 1
+        h = hue * math.pi / 180.0
+        c1, c2 = float(np.float32(math.cos(h) * sat)), float(np.float32(math.sin(h) * sat))
+        _lib.check(lib.havc_zimg_tweak_yuv(z["y"].data_ptr(), z["c"].data_ptr(), B, H, W, c1, c2, int(do_uv),
+                                           lut.data_ptr() if lut is not None else None, stream), "zimg.tweak_yuv")
+        _lib.check(lib.havc_zimg_yuv420p8_to_rgb(z["y"].data_ptr(), z["c"].data_ptr(), out.data_ptr(), z["s_half"].data_ptr(),
+                                                 z["s_rgb"].data_ptr(), B, H, W, uh[0].data_ptr(), uh[1].data_ptr(), uh[2],
+                                                 uv[0].data_ptr(), uv[1].data_ptr(), uv[2], 1, stream), "zimg.yuv420p8_to_rgb")
+        return True
 
     # ---- chroma-adjust filters ------------------------------------------------------------------------------
     def adjust_hue_range(self, img, out, hue_adjust: str, stream: int = 0) -> bool:

@@ -258,8 +258,6 @@ def HAVC_colorizer(
     if method != 0 and ddcolor_model not in (2, 3):
         _raise("HAVC_colorizer: DDColor (ddcolor_p model 0/1, the external vsddcolor package) is out of scope of the B200 "
                "build; use model 2 (Zhang siggraph17) or 3 (Zhang eccv16) as the second colour model")
-    if deoldify_sat != 1.0 or deoldify_hue != 0.0 or (method != 0 and (ddcolor_sat != 1.0 or ddcolor_hue != 0.0)):
-        _raise("HAVC_colorizer: vs_tweak (sat/hue != identity; a zimg YUV420 round trip) is not built yet")
     ddtweak = list(ddtweak) if isinstance(ddtweak, (list, tuple)) else [bool(ddtweak), False, False]
     ddtweak = (ddtweak + [False, False, False])[:3]
     scenechange = not (sc_threshold == 0 and sc_min_freq == 0)                            # :2494
@@ -300,7 +298,8 @@ def HAVC_colorizer(
     try:
         engines = [_engine_or_smaller_batch(DeoldifyEngine, sd_video, clip.width, clip.height, render_factor=deoldify_rf, frame_size=frame_size,
                                   batch=_BATCH, dtype=_DTYPE, device=f"cuda:{d}", sd_other=sd_other, video_weight=weight,
-                                  zhang=zhang, merge=merge, hue_adjust=hue_adjust, run_deoldify=run_deoldify, ddtweak=tweak)
+                                  zhang=zhang, merge=merge, hue_adjust=hue_adjust, run_deoldify=run_deoldify, ddtweak=tweak,
+                                  sat=(deoldify_sat, ddcolor_sat), hue=(deoldify_hue, ddcolor_hue))
                    for d in devices]
     except (ValueError, FilterError) as e:
         _raise("HAVC_colorizer: " + str(e))

@@ -42,11 +42,22 @@ def spline36(x: float) -> float:
     return 0.0
 
 
-KERNELS = {"spline64": (spline64, 4), "spline36": (spline36, 3)}
+def bicubic(x: float, b: float = 1.0 / 3.0, c: float = 1.0 / 3.0) -> float:
+    """zimg's Bicubic (Mitchell-Netravali family; VapourSynth resize.Bicubic defaults b = c = 1/3), support 2."""
+    x = abs(x)
+    if x < 1.0:
+        return (6.0 - 2.0 * b) / 6.0 + x * x * ((-18.0 + 12.0 * b + 6.0 * c) / 6.0 + x * (12.0 - 9.0 * b - 6.0 * c) / 6.0)
+    if x < 2.0:
+        return (8.0 * b + 24.0 * c) / 6.0 + x * ((-12.0 * b - 48.0 * c) / 6.0 + x * ((6.0 * b + 30.0 * c) / 6.0 + x * (-b - 6.0 * c) / 6.0))
+    return 0.0
 
 
-def filter_matrix(src: int, dst: int, kernel: str = "spline64") -> np.ndarray:
-    """Dense [dst, src] float64 resampling matrix (zimg compute_filter semantics)."""
+KERNELS = {"spline64": (spline64, 4), "spline36": (spline36, 3), "bicubic": (bicubic, 2)}
+
+
+def filter_matrix(src: int, dst: int, kernel: str = "spline64", shift: float = 0.0) -> np.ndarray:
+    """Dense [dst, src] float64 resampling matrix (zimg compute_filter semantics); `shift` moves the sampling positions by that
+    many SOURCE samples (chroma siting of the 4:2:0 conversions)."""
     f, support = KERNELS[kernel]
     scale = dst / src
     step = min(scale, 1.0)
@@ -54,7 +65,7 @@ def filter_matrix(src: int, dst: int, kernel: str = "spline64") -> np.ndarray:
     fsize = max(int(math.ceil(fsupport)) * 2, 1)
     m = np.zeros((dst, src), dtype=np.float64)
     for i in range(dst):
-        pos = (i + 0.5) / scale
+        pos = (i + 0.5) / scale + shift
         begin = math.floor(pos - fsize / 2.0 + 0.5) + 0.5
         ws = [f((begin + j - pos) * step) for j in range(fsize)]
         total = sum(ws)
@@ -71,9 +82,9 @@ def filter_matrix(src: int, dst: int, kernel: str = "spline64") -> np.ndarray:
     return m
 
 
-def build_tables(src: int, dst: int, kernel: str = "spline64") -> Tuple[np.ndarray, np.ndarray]:
+def build_tables(src: int, dst: int, kernel: str = "spline64", shift: float = 0.0) -> Tuple[np.ndarray, np.ndarray]:
     """(start int32 [dst], weights float32 [dst, T]) with out[o] = sum_t weights[o,t] * in[start[o]+t]."""
-    m = filter_matrix(src, dst, kernel)
+    m = filter_matrix(src, dst, kernel, shift)
     nz = m != 0.0
     first = np.where(nz.any(1), nz.argmax(1), 0)
     last = np.where(nz.any(1), src - 1 - nz[:, ::-1].argmax(1), 0)
@@ -134,3 +145,11 @@ def pil_tables(in_size: int, out_size: int, filt: str = "bilinear") -> Tuple[np.
         coeffs[o, :n] = np.where(fixed < 0, np.trunc(fixed - 0.5), np.trunc(fixed + 0.5)).astype(np.int32)
         bounds[o] = (lo, n)
     return bounds, coeffs
+
+
+def chroma420_tables(width: int, height: int):
+    """Bicubic tables of zimg's 4:4:4 <-> 4:2:0 chroma resampling with chroma location 'left' (MPEG-2: co-sited horizontally with
+    the even luma column, centred vertically): (down_h, down_v, up_h, up_v), each (start, weights).  Down: the chroma sample i sits
+    at luma column 2i, i.e. half a source sample left of the centred position; up: the inverse siting, +0.25 chroma samples."""
+    return (build_tables(width, width // 2, "bicubic", -0.5), build_tables(height, height // 2, "bicubic", 0.0),
+            build_tables(width // 2, width, "bicubic", 0.25), build_tables(height // 2, height, "bicubic", 0.0))
