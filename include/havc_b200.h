@@ -302,20 +302,27 @@ int havc_vs_merge_u8(const uint8_t *a, const uint8_t *b, uint8_t *out, long long
  * luma_mask_sat branch of LumaMaskedMerge, mcomb.py:243), restated from the published zimg algorithm (zimg / VapourSynth are not
  * available here: parity unpinned against the real library, bit-exact against oracle/zimg_oracle.py).  Planar u8 batches. -------- */
 
-/* clip.resize.Bicubic(format=YUV420P8, matrix_s="709", range_s="full") (vsfilters.py:790): rgb u8 [B][3][H][W] -> y u8 [B][H][W],
- * uv u8 [B][2][H/2][W/2].  scratch444: float [B][2][H][W]; scratch_v: float [B][2][H/2][W].  Tables (host built,
- * resample.chroma420_tables): vertical H -> H/2 and horizontal W -> W/2 Bicubic with 'left' chroma siting, weights [out][T]. */
-int havc_zimg_rgb_to_yuv420p8(const uint8_t *rgb, uint8_t *y, uint8_t *uv, float *scratch444, float *scratch_v, int B, int H, int W,
-                              const int *start_v, const float *w_v, int Tv, const int *start_h, const float *w_h, int Th, void *stream);
+/* clip.resize.Bicubic(format=YUV420P8, matrix_s=..., range_s=..., [dither_type="error_diffusion"]): vs_tweak (vsfilters.py:790:
+ * matrix 709, full range, no dither) and restore_format (havc_utils.py:199-222: the clip's matrix / range, dither on Y, U and V).
+ * rgb u8 [B][3][H][W] -> y u8 [B][H][W], uv u8 [B][2][H/2][W/2].  scratch444: float [B][2][H][W]; scratch_v: float [B][2][H/2][W];
+ * scratch_q (dither only): float [B][H][W] + [B][2][H/2][W/2].  Tables (host built, resample.chroma420_tables): vertical H -> H/2 and
+ * horizontal W -> W/2 Bicubic with 'left' chroma siting, weights [out][T].  matrix: 0 = BT.709, 1 = BT.601 (470bg / 170m);
+ * limited: 1 = 16-235 / 16-240, 0 = full range. */
+int havc_zimg_rgb_to_yuv420p8(const uint8_t *rgb, uint8_t *y, uint8_t *uv, float *scratch444, float *scratch_v, float *scratch_q, int B,
+                              int H, int W, const int *start_v, const float *w_v, int Tv, const int *start_h, const float *w_h, int Th,
+                              int matrix, int limited, int dither, void *stream);
 /* The std.Expr hue / saturation rotation of (U, V) (vsfilters.py:797-826; c1 = cos(hue) * sat, c2 = sin(hue) * sat; do_uv = 0
  * skips it) and the std.Lut brightness / contrast table on Y (:828-845; lut = 256 device bytes or NULL), in place. */
 int havc_zimg_tweak_yuv(uint8_t *y, uint8_t *uv, int B, int H, int W, float c1, float c2, int do_uv, const uint8_t *lut, void *stream);
-/* clip.resize.Bicubic(format=RGB24, matrix_in_s="709", range_s="full", dither_type="error_diffusion") (vsfilters.py:848): the way
- * back; dither = 1 runs zimg's Floyd-Steinberg error diffusion per plane (a warp-level wavefront), 0 rounds.
- * scratch_h: float [B][2][H/2][W]; scratch_rgb: float [B][3][H][W] (dither only). */
+/* clip.resize.Bicubic(format=RGB24, matrix_in=..., range_in_s=..., range_s="full", dither_type="error_diffusion"): the way back of
+ * vs_tweak (vsfilters.py:848) and convert_format_RGB24 for YUV clips (havc_utils.py:133-143); dither = 1 runs zimg's Floyd-Steinberg
+ * error diffusion per plane (a warp-level wavefront), 0 rounds.  scratch_h: float [B][2][H/2][W]; scratch_rgb: float [B][3][H][W]
+ * (dither only). */
 int havc_zimg_yuv420p8_to_rgb(const uint8_t *y, const uint8_t *uv, uint8_t *rgb, float *scratch_h, float *scratch_rgb, int B, int H, int W,
-                              const int *start_h, const float *w_h, int Th, const int *start_v, const float *w_v, int Tv, int dither,
-                              void *stream);
+                              const int *start_h, const float *w_h, int Th, const int *start_v, const float *w_v, int Tv, int matrix,
+                              int limited, int dither, void *stream);
+/* convert_format_RGB24 for GRAY8 clips (havc_utils.py:145-151): R = G = B = the luma expanded to full range, no dither. */
+int havc_zimg_gray8_to_rgb(const uint8_t *y, uint8_t *rgb, int B, int H, int W, int limited, void *stream);
 /* The BT.709 RGB -> YCbCr matrix (inverse = 0) or its inverse (1) as 9 floats, row major (host memory). */
 int havc_zimg_inverse_matrix(float *out9, int inverse);
 

@@ -132,3 +132,19 @@ def model_image_render(sd_video, sd_other, img: np.ndarray, render_factor: int, 
         return v
     o = colorizer_filter(sd_other, img, render_factor)
     return px.pil_blend(o, v, video_weight)
+
+
+def havc_colorizer_yuv_frame(sd, planes, render_factor: int = 24, matrix: str = "709", out_limited: bool = True, **kw):
+    """HAVC_colorizer on one 8-bit YUV 4:2:0 frame ([Y, U, V] planes) or GRAY frame ([Y]): convert_format_RGB24 (havc_utils.py:57-164:
+    limited-range input, the clip's matrix, error-diffusion dither for YUV; plain range expansion for GRAY), the RGB24 path above,
+    restore_format (:167-237: back to YUV420P8 with the clip's matrix / range - BT.709 for a GRAY source - and error-diffusion
+    dither).  Returns [Y, U, V].  The zimg steps are the restatement of oracle/zimg_oracle.py (parity unpinned)."""
+    from . import zimg_oracle as zo
+    if len(planes) == 1:
+        rgb = zo.gray8_to_rgb24(planes[0], limited=True)
+        out_matrix = "709"
+    else:
+        rgb = zo.yuv420p8_to_rgb24(planes[0], planes[1], planes[2], dither=True, matrix=matrix, limited=True)
+        out_matrix = matrix
+    res = havc_colorizer_frame(sd, rgb, render_factor, **kw)
+    return list(zo.rgb24_to_yuv420p8(res, matrix=out_matrix, limited=out_limited, dither=True))

@@ -26,6 +26,12 @@ import numpy as np
 F = np.float32
 KR, KB = 0.2126, 0.0722
 KG = 1.0 - KR - KB
+MATRICES = {"709": (0.2126, 0.0722), "601": (0.299, 0.114)}      # Kr, Kb (BT.709; BT.601 = VapourSynth's 470bg / 170m)
+
+
+def quant(limited: bool):
+    """float -> 8-bit integer scaling of zimg's depth conversion: (y_scale, y_off, c_scale, c_off)."""
+    return (F(219.0), F(16.0), F(224.0), F(128.0)) if limited else (F(255.0), F(0.0), F(255.0), F(128.0))
 
 
 def _bicubic(x: float, b: float = 1.0 / 3.0, c: float = 1.0 / 3.0) -> float:
@@ -101,32 +107,36 @@ def _rint_u8(x: np.ndarray) -> np.ndarray:
     return np.clip(np.rint(x), 0, 255).astype(np.uint8)
 
 
-def forward_matrix():
-    """RGB -> YCbCr (BT.709) in float32, rows Y, Cb, Cr (zimg ncl_rgb_to_yuv_matrix)."""
-    m = np.array([[KR, KG, KB],
-                  [-KR / (2 * (1 - KB)), -KG / (2 * (1 - KB)), 0.5],
-                  [0.5, -KG / (2 * (1 - KR)), -KB / (2 * (1 - KR))]], np.float64)
+def forward_matrix(matrix: str = "709"):
+    """RGB -> YCbCr in float32, rows Y, Cb, Cr (zimg ncl_rgb_to_yuv_matrix), and its inverse."""
+    kr, kb = MATRICES[matrix]
+    kg = 1.0 - kr - kb
+    m = np.array([[kr, kg, kb],
+                  [-kr / (2 * (1 - kb)), -kg / (2 * (1 - kb)), 0.5],
+                  [0.5, -kg / (2 * (1 - kr)), -kb / (2 * (1 - kr))]], np.float64)
     # inverse in closed form (what the numerical 3x3 inverse zimg takes in double rounds to in float32)
-    inv = np.array([[1.0, 0.0, 2 * (1 - KR)],
-                    [1.0, -2 * KB * (1 - KB) / KG, -2 * KR * (1 - KR) / KG],
-                    [1.0, 2 * (1 - KB), 0.0]], np.float64)
+    inv = np.array([[1.0, 0.0, 2 * (1 - kr)],
+                    [1.0, -2 * kb * (1 - kb) / kg, -2 * kr * (1 - kr) / kg],
+                    [1.0, 2 * (1 - kb), 0.0]], np.float64)
     return m.astype(F), inv.astype(F)
 
 
-def rgb24_to_yuv420p8(rgb: np.ndarray):
-    """uint8 [H,W,3] -> (Y u8 [H,W], U u8 [H/2,W/2], V u8 [H/2,W/2]), full range, BT.709."""
+def rgb24_to_yuv420p8(rgb: np.ndarray, matrix: str = "709", limited: bool = False, dither: bool = False):
+    """uint8 [H,W,3] -> (Y u8 [H,W], U u8 [H/2,W/2], V u8 [H/2,W/2]).  vs_tweak: BT.709, full range, no dither; restore_format
+    (havc_utils.py:199-222): the clip's matrix / range with error-diffusion dither on all three planes."""
     H, W = rgb.shape[:2]
     assert H % 2 == 0 and W % 2 == 0
-    fwd, _ = forward_matrix()
+    fwd, _ = forward_matrix(matrix)
+    ys, yo, cs, co = quant(limited)
     c = rgb.astype(F) * F(1.0 / 255.0)
     r, g, b = c[..., 0], c[..., 1], c[..., 2]
     planes = [((fwd[k, 0] * r).astype(F) + (fwd[k, 1] * g).astype(F)).astype(F) + (fwd[k, 2] * b).astype(F) for k in range(3)]
-    y = _rint_u8(planes[0] * F(255.0))
+    q = (lambda x: error_diffusion_u8(x)) if dither else _rint_u8
+    out = [q(((planes[0] * ys).astype(F) + yo).astype(F))]
     th, tv = chroma_down_tables(W, H)
-    out = [y]
     for k in (1, 2):
         ch = _resample(_resample(planes[k].astype(F), 0, tv), 1, th)           # vertical pass first (zimg orders by cost)
-        out.append(_rint_u8((ch * F(255.0)).astype(F) + F(128.0)))
+        out.append(q(((ch * cs).astype(F) + co).astype(F)))
     return tuple(out)
 
 
@@ -154,15 +164,17 @@ def error_diffusion_u8(x: np.ndarray) -> np.ndarray:
     return out
 
 
-def yuv420p8_to_rgb24(y: np.ndarray, u: np.ndarray, v: np.ndarray, dither: bool = True) -> np.ndarray:
-    """(Y [H,W], U, V [H/2,W/2]) u8 -> uint8 [H,W,3]: Bicubic chroma up-sampling, inverse BT.709 matrix, error diffusion."""
+def yuv420p8_to_rgb24(y: np.ndarray, u: np.ndarray, v: np.ndarray, dither: bool = True, matrix: str = "709",
+                      limited: bool = False) -> np.ndarray:
+    """(Y [H,W], U, V [H/2,W/2]) u8 -> uint8 [H,W,3]: Bicubic chroma up-sampling, inverse matrix, error diffusion."""
     H, W = y.shape
-    _, inv = forward_matrix()
+    _, inv = forward_matrix(matrix)
+    ys, yo, cs, co = quant(limited)
     th, tv = chroma_up_tables(W, H)
-    yf = y.astype(F) * F(1.0 / 255.0)
+    yf = ((y.astype(F) - yo).astype(F) * F(F(1.0) / ys)).astype(F)
     ch = []
     for p in (u, v):
-        c = (p.astype(F) - F(128.0)) * F(1.0 / 255.0)
+        c = ((p.astype(F) - co).astype(F) * F(F(1.0) / cs)).astype(F)
         ch.append(_resample(_resample(c.astype(F), 1, th), 0, tv))               # horizontal pass first when up-sampling
     planes = [((inv[k, 0] * yf).astype(F) + (inv[k, 1] * ch[0]).astype(F)).astype(F) + (inv[k, 2] * ch[1]).astype(F) for k in range(3)]
     outs = []
@@ -170,6 +182,13 @@ def yuv420p8_to_rgb24(y: np.ndarray, u: np.ndarray, v: np.ndarray, dither: bool 
         s = (planes[k].astype(F) * F(255.0)).astype(F)
         outs.append(error_diffusion_u8(s) if dither else _rint_u8(s))
     return np.stack(outs, -1)
+
+
+def gray8_to_rgb24(y: np.ndarray, limited: bool = True) -> np.ndarray:
+    """resize.Bicubic(format=RGB24, range_in_s="limited", range_s="full") of a GRAY8 clip (havc_utils.py:145-151): no dither."""
+    ys, yo, _, _ = quant(limited)
+    v = (((y.astype(F) - yo).astype(F) * F(F(1.0) / ys)).astype(F) * F(255.0)).astype(F)
+    return np.repeat(_rint_u8(v)[..., None], 3, -1)
 
 
 def vs_tweak(rgb: np.ndarray, hue: float = 0.0, sat: float = 1.0, bright: float = 0.0, cont: float = 1.0) -> np.ndarray:

@@ -332,3 +332,87 @@ def test_colorizer_sat_hue_tweak(method):
         img = np.stack([np.asarray(f[p]) for p in range(3)], -1)
         m = metrics.frame_parity(img, ref)
         assert m["mean_de00"] <= 0.5, (method, i, m)
+
+
+def _yuv_clip(n, H, W, seed, fmt, props_extra=None):
+    """A YUV420P8 (limited range) or GRAY8 clip of the stand-in VapourSynth with its plane arrays."""
+    from oracle import synth_weights
+    from vsdeoldify_b200 import vs_shim
+    frames = []
+    for i in range(n):
+        y = (16 + synth_weights.make_test_frame(seed + 3 * i, H, W).numpy().astype(np.float32) * (219.0 / 255.0)).astype(np.uint8)
+        if fmt == "gray8":
+            frames.append([y])
+        else:
+            u = (128 + (synth_weights.make_test_frame(seed + 3 * i + 1, H // 2, W // 2).numpy().astype(np.int32) - 128) // 4).astype(np.uint8)
+            v = (128 + (synth_weights.make_test_frame(seed + 3 * i + 2, H // 2, W // 2).numpy().astype(np.int32) - 128) // 5).astype(np.uint8)
+            frames.append([y, u, v])
+    vfmt = vs_shim.GRAY8 if fmt == "gray8" else vs_shim.YUV420P8
+    props = [dict({"_SceneChangePrev": int(i == 0), "idx": i}, **(props_extra or {})) for i in range(n)]
+    fn = lambda i: vs_shim.VideoFrame(frames[i], vfmt, props[i])
+    return vs_shim.VideoNode(n, W, H, vfmt, fn), frames, props
+
+
+@pytest.mark.parametrize("fmt,extra,matrix,out_limited", [("yuv420p8", {"_Matrix": 1}, "709", True), ("yuv420p8", {"_Matrix": 6, "_ColorRange": 0}, "601", False),
+                                                          ("gray8", {}, "709", True)])
+def test_colorizer_on_yuv420p8_and_gray8_clips(fmt, extra, matrix, out_limited):
+    """convert_format_RGB24 / restore_format (havc_utils.py:57-237) on the device: an 8-bit YUV 4:2:0 or GRAY clip goes in, a
+    YUV420P8 clip comes out (same format / props for YUV; a GRAY clip comes back as BT.709 YUV420P8), planes compared with the
+    oracle of the whole path (restated zimg conversions around the RGB24 pipeline)."""
+    from oracle import metrics, pipeline_oracle, zimg_oracle as zo
+    from vsdeoldify_b200 import vs_shim
+    havc = _register()
+    H, W, rf, n = 96, 160, 10, 3
+    clip, frames, props = _yuv_clip(n, H, W, 1200, fmt, extra)
+    out = havc.HAVC_colorizer(clip, method=0, deoldify_p=[0, rf, 1.0, 0.0], ddcolor_p=[1, rf, 1.0, 0.0, True])
+    assert out.format == vs_shim.YUV420P8 and (out.width, out.height) == (W, H)
+    sd = havc._REGISTERED["ColorizeVideo_gen"]
+    out_matrix = matrix if fmt == "yuv420p8" else "709"
+    for i in (2, 0, 1):
+        f = out.get_frame(i)
+        assert f.props == props[i] and f.format == vs_shim.YUV420P8
+        want = pipeline_oracle.havc_colorizer_yuv_frame(sd, frames[i], rf, matrix=matrix, out_limited=out_limited)
+        got = [np.asarray(f[p]) for p in range(3)]
+        assert all(g.shape == w.shape for g, w in zip(got, want))
+        assert np.abs(got[0].astype(int) - want[0].astype(int)).max() <= 2                 # luma: transplanted, dither ties only
+        rgb_g = zo.yuv420p8_to_rgb24(*got, dither=False, matrix=out_matrix, limited=out_limited)
+        rgb_w = zo.yuv420p8_to_rgb24(*want, dither=False, matrix=out_matrix, limited=out_limited)
+        m = metrics.frame_parity(rgb_g, rgb_w)
+        assert m["mean_de00"] <= 0.5, (fmt, i, m)
+
+
+def test_zimg_conversions_bit_exact_vs_restatement():
+    """RGB24 <-> YUV420P8 through the C ABI for both matrices / ranges with error-diffusion dither in both directions, and GRAY8 ->
+    RGB24, against oracle/zimg_oracle.py: bit-exact."""
+    import torch
+    from oracle import synth_weights, zimg_oracle as zo
+    from vsdeoldify_b200.engine import _FormatIO
+    B, H, W = 2, 48, 80
+    imgs = [np.stack([synth_weights.make_test_frame(1300 + 5 * i + c, H, W).numpy() for c in range(3)], -1) for i in range(B)]
+    rgb = torch.from_numpy(np.ascontiguousarray(np.stack([np.transpose(x, (2, 0, 1)) for x in imgs]))).cuda()
+    for matrix in ("709", "601"):
+        for limited in (True, False):
+            io = _FormatIO("yuv420p8", B, H, W, torch.device("cuda:0"), matrix, limited)
+            raw = torch.empty(io.out_bytes, dtype=torch.uint8, device="cuda")
+            io.from_rgb(rgb, raw, 0)
+            torch.cuda.synchronize()
+            arr = raw.cpu().numpy()
+            for j in range(B):
+                want = zo.rgb24_to_yuv420p8(imgs[j], matrix=matrix, limited=limited, dither=True)
+                for g, w in zip(io.planes(arr, j, out=True), want):
+                    assert np.array_equal(g, w), (matrix, limited, j, int((g != w).sum()))
+            if limited:                                    # the way in always reads limited-range YUV (havc_utils.py:139)
+                back = torch.empty_like(rgb)
+                io.to_rgb(raw, back, 0)
+                torch.cuda.synchronize()
+                for j in range(B):
+                    y, u, v = io.planes(arr, j, out=True)
+                    want = zo.yuv420p8_to_rgb24(y, u, v, dither=True, matrix=matrix, limited=True)
+                    assert np.array_equal(np.transpose(back[j].cpu().numpy(), (1, 2, 0)), want), (matrix, j)
+    io = _FormatIO("gray8", B, H, W, torch.device("cuda:0"))
+    g = torch.from_numpy(np.stack([x[..., 0] for x in imgs]).reshape(-1)).cuda()
+    back = torch.empty_like(rgb)
+    io.to_rgb(g, back, 0)
+    torch.cuda.synchronize()
+    for j in range(B):
+        assert np.array_equal(np.transpose(back[j].cpu().numpy(), (1, 2, 0)), zo.gray8_to_rgb24(imgs[j][..., 0]))

@@ -226,3 +226,60 @@ def test_legacy_spectral_norm_state_dict_folds_like_torch():
     conv2(torch.zeros(1, 12, 8, 8))
     assert torch.allclose(got, conv2.weight.detach(), atol=1e-5, rtol=1e-4)
     assert torch.allclose(got, w_eff, atol=1e-5, rtol=1e-4)
+
+
+def test_sharded_renderer_orders_frames_and_props_with_cpu_stand_in_engines():
+    """sharded.ShardedRenderer (the in-process multi-GPU clip renderer) with CPU stand-ins for the engines: block and interleaved
+    partitions, bounded and unbounded windows, in-order and out-of-order requests - every frame comes back under its own number
+    with its own props and the bytes its engine produced."""
+    import time
+    import numpy as np
+    from vsdeoldify_b200 import sharded, vs_shim
+
+    class FakeEngine:
+        n_slots = 2
+
+        def __init__(self, B, H, W):
+            self.bufs = [np.zeros((B, 3, H, W), np.uint8) for _ in range(2)]
+            self.nxt, self.busy = 0, [False, False]
+
+        def next_input(self):
+            assert not self.busy[self.nxt]
+            return self.bufs[self.nxt]
+
+        def submit(self, frames, skip=None, n=None):
+            s = self.nxt
+            self.busy[s] = True
+            self.nxt = (s + 1) % 2
+            return (s, n, None if skip is None else np.asarray(skip).copy())
+
+        def collect(self, t, out=None, pool=None):
+            s, n, skip = t
+            time.sleep(0.001)
+            self.busy[s] = False
+            out[:n] = 255 - self.bufs[s][:n]
+            if skip is not None:
+                out[:n][skip[:n]] = self.bufs[s][:n][skip[:n]]
+            return out[:n]
+
+    n, H, W, B = 53, 8, 12, 4
+    frames = np.random.default_rng(0).integers(0, 256, (n, 3, H, W), dtype=np.uint8)
+    clip = vs_shim.array_clip(frames, props=[{"_SceneChangePrev": int(i % 5 == 0), "id": i} for i in range(n)])
+    assert sharded.plan_jobs(10, 2, 4, "block") == [(0, 4, 0), (4, 5, 0), (5, 9, 1), (9, 10, 1)]
+    assert sharded.plan_jobs(10, 2, 4, "interleaved") == [(0, 4, 0), (4, 8, 1), (8, 10, 0)]
+    for mode, win, sc in (("block", None, False), ("interleaved", None, False), ("interleaved", 3, False), ("interleaved", None, True)):
+        r = sharded.ShardedRenderer(clip, [FakeEngine(B, H, W) for _ in range(3)], B, scenechange=sc, partition=mode, window=win)
+        order = list(range(n)) if win is None else [0, 1, 2, 40, 41, 7, 8, 52, 3]
+        for i in order:
+            f = r(i)
+            want = 255 - frames[i]
+            if sc and not (i == 0 or i % 5 == 0):
+                want = frames[i]                              # not a scene change: the gate leaves the frame uncoloured
+            assert f.props["id"] == i and np.array_equal(np.stack([f[p] for p in range(3)]), want), (mode, win, sc, i)
+        r.close()
+    # a frame without the scene-detection prop is an error, not a silently uncoloured frame
+    bare = vs_shim.array_clip(frames[:8], props=[{"id": i} for i in range(8)])
+    r = sharded.ShardedRenderer(bare, [FakeEngine(B, H, W)], B, scenechange=True)
+    with pytest.raises(KeyError):
+        r(1)
+    r.close()

@@ -134,12 +134,13 @@ _SIGNATURES = {
     "havc_vs_merge_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_double, C.c_void_p]),
     "havc_luma_adjusted_levels": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_double, C.c_double,
                                             C.c_double, C.c_double, C.c_double, C.c_void_p]),
-    "havc_zimg_rgb_to_yuv420p8": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 3 + [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
-                                            C.c_int, C.c_void_p]),
+    "havc_zimg_rgb_to_yuv420p8": (C.c_int, [C.c_void_p] * 6 + [C.c_int] * 3 + [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                            C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "havc_zimg_tweak_yuv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p,
                                       C.c_void_p]),
     "havc_zimg_yuv420p8_to_rgb": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 3 + [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
-                                            C.c_int, C.c_int, C.c_void_p]),
+                                            C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "havc_zimg_gray8_to_rgb": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "havc_zimg_inverse_matrix": (C.c_int, [C.c_void_p, C.c_int]),
 }
 

@@ -12,8 +12,10 @@ namespace havc {
 struct Mat3 { float m[3][3]; };
 
 // RGB u8 planes -> Y u8 (rint(y * 255)) + float Cb / Cr planes at full resolution.
-__global__ void zimg_rgb_to_yuv444_kernel(const uint8_t *__restrict__ rgb, uint8_t *__restrict__ y, float *__restrict__ cbcr,
-                                          int B, long long n, Mat3 fwd) {
+struct Quant { float y_scale, y_off, c_scale, c_off; };     // float -> integer: v * scale + off (full range: 255 / 0 / 255 / 128)
+
+__global__ void zimg_rgb_to_yuv444_kernel(const uint8_t *__restrict__ rgb, uint8_t *__restrict__ y, float *__restrict__ yf,
+                                          float *__restrict__ cbcr, int B, long long n, Mat3 fwd, Quant qn) {
     const long long total = (long long)B * n;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long b = i / n, px = i - b * n;
@@ -24,18 +26,20 @@ __global__ void zimg_rgb_to_yuv444_kernel(const uint8_t *__restrict__ rgb, uint8
 #pragma unroll
         for (int k = 0; k < 3; ++k)
             p[k] = __fadd_rn(__fadd_rn(__fmul_rn(fwd.m[k][0], r), __fmul_rn(fwd.m[k][1], g)), __fmul_rn(fwd.m[k][2], bl));
-        y[i] = (uint8_t)sat8(__float2int_rn(__fmul_rn(p[0], 255.0f)));
+        const float ys = __fadd_rn(__fmul_rn(p[0], qn.y_scale), qn.y_off);
+        if (yf) yf[i] = ys;                                   // quantised by the error-diffusion pass
+        else y[i] = (uint8_t)sat8(__float2int_rn(ys));
         cbcr[(b * 2 + 0) * n + px] = p[1];
         cbcr[(b * 2 + 1) * n + px] = p[2];
     }
 }
 
 // Generic separable pass on float planes: vertical (axis 0) or horizontal (axis 1); out = sum_t w[o][t] * in[start[o] + t].
-//   mode 0: float out;  mode 1: u8 out = rint(clamp(acc * 255 + 128))  (chroma quantisation, full range)
+//   mode 0: float out;  mode 1: u8 out = rint(clamp(acc * c_scale + c_off)) (chroma quantisation);  mode 2: the same, kept as float
 template <bool kVertical>
 __global__ void zimg_resample_kernel(const float *__restrict__ in, void *__restrict__ out, long long planes, int Hin, int Win,
                                      int Hout, int Wout, const int *__restrict__ start, const float *__restrict__ wts, int T,
-                                     int mode) {
+                                     int mode, float c_scale, float c_off) {
     const long long total = planes * Hout * Wout;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int ox = (int)(i % Wout);
@@ -54,15 +58,18 @@ __global__ void zimg_resample_kernel(const float *__restrict__ in, void *__restr
         }
         if (mode == 0) {
             reinterpret_cast<float *>(out)[i] = acc;
-        } else {
-            reinterpret_cast<uint8_t *>(out)[i] = (uint8_t)sat8(__float2int_rn(__fadd_rn(__fmul_rn(acc, 255.0f), 128.0f)));
+        } else if (mode == 1) {
+            reinterpret_cast<uint8_t *>(out)[i] = (uint8_t)sat8(__float2int_rn(__fadd_rn(__fmul_rn(acc, c_scale), c_off)));
+        } else {                                              // scaled float for the error-diffusion pass
+            reinterpret_cast<float *>(out)[i] = __fadd_rn(__fmul_rn(acc, c_scale), c_off);
         }
     }
 }
 
 // u8 chroma -> float ((p - 128) / 255), then the horizontal up-sampling pass.
 __global__ void zimg_chroma_up_h_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, long long planes, int Hc, int Wc,
-                                        int Wout, const int *__restrict__ start, const float *__restrict__ wts, int T) {
+                                        int Wout, const int *__restrict__ start, const float *__restrict__ wts, int T, float c_off,
+                                        float c_inv) {
     const long long total = planes * Hc * Wout;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int ox = (int)(i % Wout);
@@ -74,7 +81,7 @@ __global__ void zimg_chroma_up_h_kernel(const uint8_t *__restrict__ in, float *_
         float acc = 0.f;
         for (int t = 0; t < T; ++t) {
             const int idx = min(s0 + t, Wc - 1);
-            const float v = __fmul_rn(__fsub_rn((float)__ldg(src + idx), 128.0f), 1.0f / 255.0f);
+            const float v = __fmul_rn(__fsub_rn((float)__ldg(src + idx), c_off), c_inv);
             acc = __fadd_rn(acc, __fmul_rn(v, __ldg(w + t)));
         }
         out[i] = acc;
@@ -84,7 +91,8 @@ __global__ void zimg_chroma_up_h_kernel(const uint8_t *__restrict__ in, float *_
 // Vertical chroma up-sampling + inverse matrix + * 255: float RGB planes (for the dither) or rounded u8.
 __global__ void zimg_chroma_up_v_matrix_kernel(const uint8_t *__restrict__ y, const float *__restrict__ ch /*[B][2][Hc][W]*/,
                                                float *__restrict__ rgbf, uint8_t *__restrict__ rgb8, int B, int H, int W, int Hc,
-                                               const int *__restrict__ start, const float *__restrict__ wts, int T, Mat3 inv) {
+                                               const int *__restrict__ start, const float *__restrict__ wts, int T, Mat3 inv, float y_off,
+                                               float y_inv) {
     const long long n = (long long)H * W, total = (long long)B * n;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long b = i / n, px = i - b * n;
@@ -99,7 +107,7 @@ __global__ void zimg_chroma_up_v_matrix_kernel(const uint8_t *__restrict__ y, co
             for (int t = 0; t < T; ++t) acc = __fadd_rn(acc, __fmul_rn(__ldg(src + (long long)min(s0 + t, Hc - 1) * W), __ldg(w + t)));
             c[k] = acc;
         }
-        const float yf = __fmul_rn((float)__ldg(y + i), 1.0f / 255.0f);
+        const float yf = __fmul_rn(__fsub_rn((float)__ldg(y + i), y_off), y_inv);
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             const float p = __fadd_rn(__fadd_rn(__fmul_rn(inv.m[k][0], yf), __fmul_rn(inv.m[k][1], c[0])), __fmul_rn(inv.m[k][2], c[1]));
@@ -191,12 +199,25 @@ __global__ void zimg_error_diffusion_kernel(const float *__restrict__ in, uint8_
     }
 }
 
+// GRAY8 -> RGB24 planes: R = G = B = rint((y - y_off) * y_inv * 255) (resize.Bicubic(format=RGB24, range_in_s="limited", range_s="full"),
+// havc_utils.py:145-151: no dither).
+__global__ void zimg_gray_to_rgb_kernel(const uint8_t *__restrict__ y, uint8_t *__restrict__ rgb, int B, long long n, float y_off, float y_inv) {
+    const long long total = (long long)B * n;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / n, px = i - b * n;
+        const float v = __fmul_rn(__fmul_rn(__fsub_rn((float)__ldg(y + i), y_off), y_inv), 255.0f);
+        const uint8_t q = (uint8_t)sat8(__float2int_rn(v));
+        rgb[(b * 3) * n + px] = q; rgb[(b * 3 + 1) * n + px] = q; rgb[(b * 3 + 2) * n + px] = q;
+    }
+}
+
 }  // namespace havc
 
 using namespace havc;
 
-static Mat3 bt709(bool inverse) {
-    const double kr = 0.2126, kb = 0.0722, kg = 1.0 - kr - kb;
+// matrix: 0 = BT.709, 1 = BT.601 (470bg / 170m)
+static Mat3 ycbcr_matrix(bool inverse, int matrix) {
+    const double kr = matrix == 1 ? 0.299 : 0.2126, kb = matrix == 1 ? 0.114 : 0.0722, kg = 1.0 - kr - kb;
     double m[3][3] = {{kr, kg, kb}, {-kr / (2 * (1 - kb)), -kg / (2 * (1 - kb)), 0.5}, {0.5, -kg / (2 * (1 - kr)), -kb / (2 * (1 - kr))}};
     Mat3 o;
     if (!inverse) {
@@ -209,30 +230,47 @@ static Mat3 bt709(bool inverse) {
     return o;
 }
 
+static Quant quant_of(int limited) {
+    Quant q;
+    q.y_scale = limited ? 219.f : 255.f; q.y_off = limited ? 16.f : 0.f; q.c_scale = limited ? 224.f : 255.f; q.c_off = 128.f;
+    return q;
+}
+
 extern "C" int havc_zimg_inverse_matrix(float *out9, int inverse) {
     HAVC_CHECK_ARG(out9 != nullptr, "havc_zimg_inverse_matrix: null output");
-    const Mat3 m = bt709(inverse != 0);
+    const Mat3 m = ycbcr_matrix(inverse != 0, 0);
     for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) out9[3 * i + j] = m.m[i][j];
     return HAVC_OK;
 }
 
-extern "C" int havc_zimg_rgb_to_yuv420p8(const uint8_t *rgb, uint8_t *y, uint8_t *uv, float *scratch444, float *scratch_v, int B, int H,
-                                         int W, const int *start_v, const float *w_v, int Tv, const int *start_h, const float *w_h,
-                                         int Th, void *stream) {
-    HAVC_CHECK_ARG(rgb && y && uv && scratch444 && scratch_v && B > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && start_v && w_v &&
-                       start_h && w_h && Tv > 0 && Th > 0,
-                   "havc_zimg_rgb_to_yuv420p8: bad arguments (4:2:0 needs even width and height)");
+extern "C" int havc_zimg_rgb_to_yuv420p8(const uint8_t *rgb, uint8_t *y, uint8_t *uv, float *scratch444, float *scratch_v, float *scratch_q,
+                                         int B, int H, int W, const int *start_v, const float *w_v, int Tv, const int *start_h,
+                                         const float *w_h, int Th, int matrix, int limited, int dither, void *stream) {
+    HAVC_CHECK_ARG(rgb && y && uv && scratch444 && scratch_v && (scratch_q || !dither) && B > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 &&
+                       start_v && w_v && start_h && w_h && Tv > 0 && Th > 0 && (matrix == 0 || matrix == 1) &&
+                       (W + 2) * 2 * sizeof(float) <= 48 * 1024,
+                   "havc_zimg_rgb_to_yuv420p8: bad arguments (4:2:0 needs even width and height; matrix 0 = 709, 1 = 601)");
     cudaStream_t st = (cudaStream_t)stream;
-    const long long n = (long long)H * W;
-    zimg_rgb_to_yuv444_kernel<<<grid1d((long long)B * n, 256), 256, 0, st>>>(rgb, y, scratch444, B, n, bt709(false));
+    const long long n = (long long)H * W, nc = (long long)(H / 2) * (W / 2);
+    const Quant qn = quant_of(limited);
+    float *yf = dither ? scratch_q : nullptr;                     // [B][H][W], then [B][2][H/2][W/2]
+    float *cf = dither ? scratch_q + (long long)B * n : nullptr;
+    zimg_rgb_to_yuv444_kernel<<<grid1d((long long)B * n, 256), 256, 0, st>>>(rgb, y, yf, scratch444, B, n, ycbcr_matrix(false, matrix), qn);
     HAVC_LAUNCHED();
     // vertical pass first (zimg orders the passes by cost; for a 2:1 reduction in both directions that is the vertical one)
     zimg_resample_kernel<true><<<grid1d((long long)B * 2 * (H / 2) * W, 256), 256, 0, st>>>(scratch444, scratch_v, (long long)B * 2, H, W, H / 2, W,
-                                                                                          start_v, w_v, Tv, 0);
+                                                                                          start_v, w_v, Tv, 0, 0.f, 0.f);
     HAVC_LAUNCHED();
-    zimg_resample_kernel<false><<<grid1d((long long)B * 2 * (H / 2) * (W / 2), 256), 256, 0, st>>>(scratch_v, uv, (long long)B * 2, H / 2, W, H / 2,
-                                                                                               W / 2, start_h, w_h, Th, 1);
+    zimg_resample_kernel<false><<<grid1d((long long)B * 2 * nc, 256), 256, 0, st>>>(scratch_v, dither ? (void *)cf : (void *)uv, (long long)B * 2, H / 2,
+                                                                                  W, H / 2, W / 2, start_h, w_h, Th, dither ? 2 : 1, qn.c_scale,
+                                                                                  qn.c_off);
     HAVC_LAUNCHED();
+    if (dither) {
+        zimg_error_diffusion_kernel<<<B, 32, (size_t)(W + 2) * 2 * sizeof(float), st>>>(yf, y, H, W);
+        HAVC_LAUNCHED();
+        zimg_error_diffusion_kernel<<<B * 2, 32, (size_t)(W / 2 + 2) * 2 * sizeof(float), st>>>(cf, uv, H / 2, W / 2);
+        HAVC_LAUNCHED();
+    }
     return HAVC_OK;
 }
 
@@ -254,20 +292,32 @@ extern "C" int havc_zimg_tweak_yuv(uint8_t *y, uint8_t *uv, int B, int H, int W,
 
 extern "C" int havc_zimg_yuv420p8_to_rgb(const uint8_t *y, const uint8_t *uv, uint8_t *rgb, float *scratch_h, float *scratch_rgb, int B,
                                          int H, int W, const int *start_h, const float *w_h, int Th, const int *start_v, const float *w_v,
-                                         int Tv, int dither, void *stream) {
+                                         int Tv, int matrix, int limited, int dither, void *stream) {
     HAVC_CHECK_ARG(y && uv && rgb && scratch_h && (scratch_rgb || !dither) && B > 0 && H % 2 == 0 && W % 2 == 0 && H > 0 && W > 0 &&
-                       (W + 2) * 2 * sizeof(float) <= 48 * 1024,
-                   "havc_zimg_yuv420p8_to_rgb: bad arguments (even sizes, width <= 6142)");
+                       (matrix == 0 || matrix == 1) && (W + 2) * 2 * sizeof(float) <= 48 * 1024,
+                   "havc_zimg_yuv420p8_to_rgb: bad arguments (even sizes, width <= 6142; matrix 0 = 709, 1 = 601)");
     cudaStream_t st = (cudaStream_t)stream;
+    const Quant qn = quant_of(limited);
     zimg_chroma_up_h_kernel<<<grid1d((long long)B * 2 * (H / 2) * W, 256), 256, 0, st>>>(uv, scratch_h, (long long)B * 2, H / 2, W / 2, W, start_h,
-                                                                                       w_h, Th);
+                                                                                       w_h, Th, qn.c_off, 1.0f / qn.c_scale);
     HAVC_LAUNCHED();
     zimg_chroma_up_v_matrix_kernel<<<grid1d((long long)B * H * W, 256), 256, 0, st>>>(y, scratch_h, dither ? scratch_rgb : nullptr, rgb, B, H, W,
-                                                                                    H / 2, start_v, w_v, Tv, bt709(true));
+                                                                                    H / 2, start_v, w_v, Tv, ycbcr_matrix(true, matrix),
+                                                                                    qn.y_off, 1.0f / qn.y_scale);
     HAVC_LAUNCHED();
     if (dither) {
         zimg_error_diffusion_kernel<<<B * 3, 32, (size_t)(W + 2) * 2 * sizeof(float), st>>>(scratch_rgb, rgb, H, W);
         HAVC_LAUNCHED();
     }
+    return HAVC_OK;
+}
+
+/* GRAY8 (limited or full range) -> RGB24 planes, no dither (havc_utils.py:145-151). */
+extern "C" int havc_zimg_gray8_to_rgb(const uint8_t *y, uint8_t *rgb, int B, int H, int W, int limited, void *stream) {
+    HAVC_CHECK_ARG(y && rgb && B > 0 && H > 0 && W > 0, "havc_zimg_gray8_to_rgb: bad arguments");
+    const Quant qn = quant_of(limited);
+    zimg_gray_to_rgb_kernel<<<grid1d((long long)B * H * W, 256), 256, 0, (cudaStream_t)stream>>>(y, rgb, B, (long long)H * W, qn.y_off,
+                                                                                               1.0f / qn.y_scale);
+    HAVC_LAUNCHED();
     return HAVC_OK;
 }

@@ -26,6 +26,68 @@ class _Tables:
         self.wt = torch.from_numpy(np.ascontiguousarray(w.T)).to(dev)           # [taps][out]  (horizontal passes)
 
 
+class _FormatIO:
+    """convert_format_RGB24 / restore_format (vsdeoldify/havc_utils.py:57-237) for 8-bit YUV420 and GRAY clips, on the device and
+    inside the engine's CUDA graph, so that such clips cross PCIe at 1.5 (1) bytes per pixel instead of 3:
+      in : YUV420P8 -> RGB24  resize.Bicubic(format=RGB24, matrix_in=<_Matrix or 709>, range_in_s="limited", range_s="full",
+                              dither_type="error_diffusion") (:133-143);  GRAY8 -> RGB24 (limited -> full, no dither, :145-151)
+      out: RGB24 -> the clip's YUV format with its matrix / range and error-diffusion dither (:199-207); a GRAY clip comes back as
+           YUV420P8 BT.709 (:208-222).
+    zimg is restated (csrc/zimg.cu, oracle/zimg_oracle.py: parity unpinned).  Host / device layout of one batch: all Y planes
+    [B][H][W], then all chroma planes [B][2][H/2][W/2], one flat byte buffer."""
+
+    def __init__(self, fmt: str, B: int, H: int, W: int, dev, matrix: str = "709", out_limited: bool = True):
+        if fmt not in ("yuv420p8", "gray8"):
+            raise ValueError(f"unsupported clip format {fmt!r} (rgb24, yuv420p8, gray8)")
+        if H % 2 or W % 2:
+            raise ValueError("4:2:0 clips need an even width and height")
+        if matrix not in ("709", "601"):
+            raise ValueError(f"unsupported matrix {matrix!r} (BT.709, BT.601 / 470bg / 170m)")
+        self.fmt, self.B, self.H, self.W, self.dev = fmt, B, H, W, dev
+        self.lib = _lib.lib()
+        self.matrix_in = {"709": 0, "601": 1}[matrix]
+        self.matrix_out = self.matrix_in if fmt == "yuv420p8" else 0            # GRAY input comes back as BT.709 YUV (:216-219)
+        self.out_limited = int(bool(out_limited))
+        n = H * W
+        self.in_bytes = B * n * 3 // 2 if fmt == "yuv420p8" else B * n
+        self.out_bytes = B * n * 3 // 2
+        up = lambda t: (torch.from_numpy(t[0]).to(dev), torch.from_numpy(np.ascontiguousarray(t[1])).to(dev), int(t[1].shape[1]))
+        self.dh, self.dv, self.uh, self.uv = (up(t) for t in resample.chroma420_tables(W, H))
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.s444 = torch.empty(B, 2, H, W, **f32)
+        self.s_half = torch.empty(B, 2, H // 2, W, **f32)
+        self.s_rgb = torch.empty(B, 3, H, W, **f32)
+        self.s_q = torch.empty(B * n * 3 // 2, **f32)
+
+    def planes(self, buf: np.ndarray, j: int, out: bool = False):
+        """The plane arrays of frame j inside a flat batch buffer (views)."""
+        B, H, W = self.B, self.H, self.W
+        n = H * W
+        y = buf[j * n:(j + 1) * n].reshape(H, W)
+        if self.fmt == "gray8" and not out:
+            return [y]
+        c0 = B * n + 2 * j * (n // 4)
+        return [y, buf[c0:c0 + n // 4].reshape(H // 2, W // 2), buf[c0 + n // 4:c0 + n // 2].reshape(H // 2, W // 2)]
+
+    def to_rgb(self, raw: torch.Tensor, rgb: torch.Tensor, stream: int):
+        B, H, W, chk, lib = self.B, self.H, self.W, _lib.check, self.lib
+        if self.fmt == "gray8":
+            chk(lib.havc_zimg_gray8_to_rgb(raw.data_ptr(), rgb.data_ptr(), B, H, W, 1, stream), "gray8_to_rgb")
+            return
+        uh, uv = self.uh, self.uv
+        chk(lib.havc_zimg_yuv420p8_to_rgb(raw.data_ptr(), raw.data_ptr() + B * H * W, rgb.data_ptr(), self.s_half.data_ptr(),
+                                          self.s_rgb.data_ptr(), B, H, W, uh[0].data_ptr(), uh[1].data_ptr(), uh[2], uv[0].data_ptr(),
+                                          uv[1].data_ptr(), uv[2], self.matrix_in, 1, 1, stream), "yuv420p8_to_rgb")
+
+    def from_rgb(self, rgb: torch.Tensor, raw: torch.Tensor, stream: int):
+        B, H, W, chk, lib = self.B, self.H, self.W, _lib.check, self.lib
+        dh, dv = self.dh, self.dv
+        chk(lib.havc_zimg_rgb_to_yuv420p8(rgb.data_ptr(), raw.data_ptr(), raw.data_ptr() + B * H * W, self.s444.data_ptr(),
+                                          self.s_half.data_ptr(), self.s_q.data_ptr(), B, H, W, dv[0].data_ptr(), dv[1].data_ptr(), dv[2],
+                                          dh[0].data_ptr(), dh[1].data_ptr(), dh[2], self.matrix_out, self.out_limited, 1, stream),
+            "rgb_to_yuv420p8")
+
+
 class DeoldifyEngine:
     """DeOldify at render size S = render_factor*16 on frames of width x height, batch B.
 
@@ -39,9 +101,13 @@ class DeoldifyEngine:
                  frame_size: Optional[int] = None, sd_other: Optional[Dict[str, torch.Tensor]] = None,
                  video_weight: float = 0.5, zhang: Optional[tuple] = None, merge: Optional[dict] = None,
                  hue_adjust: str = "none", run_deoldify: bool = True, ddtweak: Optional[dict] = None,
-                 precision: Optional[str] = None, sat=(1.0, 1.0), hue=(0.0, 0.0)):
+                 precision: Optional[str] = None, sat=(1.0, 1.0), hue=(0.0, 0.0), fmt: str = "rgb24", matrix: str = "709",
+                 out_limited: bool = True):
         """sat / hue = (first clip, second clip): the vs_tweak of vs_sc_combine_models (mcomb.py:161-169; deoldify_p[2:4] and
         ddcolor_p[2:4] of HAVC_colorizer), applied AFTER the optional clip swap, to every frame.
+        fmt: the clip format the host hands over / gets back - 'rgb24' (planar [B,3,H,W]), 'yuv420p8' or 'gray8' (flat batch
+        buffers, see _FormatIO; converted on the device like convert_format_RGB24 / restore_format); matrix ('709' | '601') and
+        out_limited (the clip's colour range) as the reference reads them from the frame props.
         zhang = (name, state_dict): the second colour model of HAVC_colorizer (vs_sc_ddcolor models 2 / 3,
         vsslib/vsmodels.py:339-344), colourising the same S x S frame; hue_adjust: its vs_sc_adjust_clip_hue string
         (vsmodels.py:361-362); merge = dict(method, weight, cmc_p, lmm_p, alm_p, crt_p, invert) for
@@ -96,6 +162,14 @@ class DeoldifyEngine:
         self.d_out = [torch.empty(B, 3, H, W, **u8) for _ in range(self.n_slots)]
         self.h_in = [torch.empty(B, 3, H, W, dtype=torch.uint8).pin_memory() for _ in range(self.n_slots)]
         self.h_out = [torch.empty(B, 3, H, W, dtype=torch.uint8).pin_memory() for _ in range(self.n_slots)]
+        self.fmt = fmt
+        self.io = None
+        if fmt != "rgb24":      # what crosses PCIe is the clip's own format; the RGB24 buffers above stay device-side only
+            self.io = _FormatIO(fmt, B, H, W, self.dev, matrix, out_limited)
+            self.d_raw_in = [torch.empty(self.io.in_bytes, **u8) for _ in range(self.n_slots)]
+            self.d_raw_out = [torch.empty(self.io.out_bytes, **u8) for _ in range(self.n_slots)]
+            self.h_raw_in = [torch.empty(self.io.in_bytes, dtype=torch.uint8).pin_memory() for _ in range(self.n_slots)]
+        self.out_shape = (B, 3, H, W) if self.io is None else (self.io.out_bytes,)
         self.tmp_down = torch.empty(B, 3, H, S, **f32)
         self.rgb_small = torch.empty(B, 3, S, S, **u8)
         self.colored = torch.empty(B, 3, S, S, **u8)
@@ -151,6 +225,8 @@ class DeoldifyEngine:
         lib, B, S, W, H = self.lib, self.B, self.S, self.W, self.H
         skip = self.skip_slots[slot]
         chk = _lib.check
+        if self.io is not None:
+            self.io.to_rgb(self.d_raw_in[slot], self.d_in[slot], stream)
         self._launch_pre(slot, stream)
         result = self.colored
         if self.run_deoldify and not self.rescale:
@@ -214,6 +290,8 @@ class DeoldifyEngine:
             if self.bank.vs_tweak(self.colored, self.tweaked[0], hue=self.tweak[0][1], sat=self.tweak[0][0], stream=stream):
                 result = self.tweaked[0]
         self._launch_post(slot, stream, result)
+        if self.io is not None:
+            self.io.from_rgb(self.d_out[slot], self.d_raw_out[slot], stream)
 
     # ---- frame_size != render_factor*16: the filter's own Pillow BILINEAR stretch around the generator ---------------
     def _pil(self, src, tmp, dst, Hin, Win, out_size, tabs, stream):
@@ -247,6 +325,8 @@ class DeoldifyEngine:
         with torch.cuda.stream(self.compute):
             for s in range(self.n_slots):
                 self.d_in[s].zero_()
+                if self.io is not None:
+                    self.d_raw_in[s].fill_(128)
             n0 = self.lib.havc_launch_count()
             self._launch(0, self.compute.cuda_stream)
             self.launches_per_batch = int(self.lib.havc_launch_count() - n0)
@@ -273,6 +353,8 @@ class DeoldifyEngine:
         skip[i] = True leaves frame i uncoloured (scene-change gating, vsslib/vsmodels.py:221-224): it still goes
         through the squeeze / un-squeeze / luma transplant exactly like a frame the reference's selector returned
         unchanged."""
+        if self.io is not None:
+            return self._colorize_batch_raw(frames, skip)
         n = frames.shape[0]
         assert n <= self.B and frames.shape[1:] == (3, self.H, self.W) and frames.dtype == np.uint8
         self.h_in[0][:n].copy_(torch.from_numpy(np.ascontiguousarray(frames)))
@@ -288,6 +370,35 @@ class DeoldifyEngine:
         self.compute.synchronize()
         return self.h_out[0][:n].numpy().copy()
 
+    def _colorize_batch_raw(self, planes_per_frame, skip=None):
+        """Synchronous path for YUV420P8 / GRAY8 clips: planes_per_frame = list of per-frame plane lists ([Y, U, V] or [Y]);
+        returns a list of [Y, U, V] uint8 arrays per frame (the restored YUV420P8 frames)."""
+        n = len(planes_per_frame)
+        assert n <= self.B
+        buf = self.h_raw_in[0].numpy()
+        for j, pl in enumerate(planes_per_frame):
+            for dst, src in zip(self.io.planes(buf, j), pl):
+                np.copyto(dst, src)
+        self.h_skip.zero_()
+        if skip is not None:
+            self.h_skip[:n].copy_(torch.from_numpy(np.asarray(skip, dtype=np.uint8)))
+        with torch.cuda.stream(self.compute):
+            self.skip.copy_(self.h_skip, non_blocking=True)
+            self.d_raw_in[0].copy_(self.h_raw_in[0], non_blocking=True)
+        self.run_slot(0)
+        with torch.cuda.stream(self.compute):
+            out = self.d_raw_out[0].cpu()
+        self.compute.synchronize()
+        arr = out.numpy()
+        return [[p.copy() for p in self.io.planes(arr, j, out=True)] for j in range(n)]
+
+    # ---- plane views of host batch buffers (clip adapters) -------------------------------------------------
+    def in_planes(self, buf: np.ndarray, j: int):
+        return [buf[j, p] for p in range(3)] if self.io is None else self.io.planes(buf, j)
+
+    def out_planes(self, arr: np.ndarray, j: int):
+        return [arr[j, p] for p in range(3)] if self.io is None else self.io.planes(arr, j, out=True)
+
     # ---- asynchronous batch API (clip rendering with read-ahead) ----------------------------------------
     def _async_state(self):
         if not hasattr(self, "_ev"):
@@ -301,7 +412,7 @@ class DeoldifyEngine:
         plane by plane can write straight into it and call submit(None, n=...) - one host copy per frame instead of three."""
         if self._async_state()["busy"]:
             raise RuntimeError("DeoldifyEngine.next_input: every input slot is in flight; collect() a ticket first")
-        return self.h_in[self._next].numpy()
+        return (self.h_in if self.io is None else self.h_raw_in)[self._next].numpy()
 
     def submit(self, frames: Optional[np.ndarray], skip: Optional[np.ndarray] = None, n: Optional[int] = None):
         """Enqueue one batch (uint8 [n<=B, 3, H, W] host frames, or None when the caller filled next_input()[:n]) on the next
@@ -323,7 +434,10 @@ class DeoldifyEngine:
         with torch.cuda.stream(self.copy_in):
             if ev["used"]:
                 self.copy_in.wait_event(ev["done"])          # the previous graph on this slot has consumed d_in / skip
-            self.d_in[s].copy_(self.h_in[s], non_blocking=True)
+            if self.io is None:
+                self.d_in[s].copy_(self.h_in[s], non_blocking=True)
+            else:
+                self.d_raw_in[s].copy_(self.h_raw_in[s], non_blocking=True)
             self.skip_slots[s].copy_(self.h_skip_slots[s], non_blocking=True)
             ev["inp"].record(self.copy_in)
         self.compute.wait_event(ev["inp"])
@@ -334,7 +448,7 @@ class DeoldifyEngine:
         ob = self._acquire_out()                             # a pinned result buffer no delivered frame references any more
         with torch.cuda.stream(self.copy_out):
             self.copy_out.wait_event(ev["done"])
-            ob[0].copy_(self.d_out[s], non_blocking=True)
+            ob[0].copy_(self.d_out[s] if self.io is None else self.d_raw_out[s], non_blocking=True)
             ev["out"].record(self.copy_out)
         ev["busy"], ev["used"], ev["ob"] = True, True, ob
         return (s, n, ob)
@@ -349,12 +463,12 @@ class DeoldifyEngine:
             # and stalls the device queue: measured, so growing the pool inside the steady state is what must not happen)
             self._out_pool = []
             for _ in range(8):
-                t = torch.empty(self.B, 3, self.H, self.W, dtype=torch.uint8).pin_memory()
+                t = torch.empty(*self.out_shape, dtype=torch.uint8).pin_memory()
                 self._out_pool.append((t, t.numpy()))
         for ob in self._out_pool:
             if sys.getrefcount(ob[1]) <= 2 and not any(ob is e.get("ob") for e in getattr(self, "_ev", [])):
                 return ob
-        t = torch.empty(self.B, 3, self.H, self.W, dtype=torch.uint8).pin_memory()
+        t = torch.empty(*self.out_shape, dtype=torch.uint8).pin_memory()
         ob = (t, t.numpy())
         self._out_pool.append(ob)
         return ob
@@ -367,7 +481,7 @@ class DeoldifyEngine:
         ev["out"].synchronize()
         ev["busy"] = False
         ev["ob"] = None
-        return ob[1][:n]
+        return ob[1][:n] if self.io is None else ob[1]
 
     def collect(self, ticket, out: Optional[np.ndarray] = None, pool=None) -> np.ndarray:
         """Wait for a submitted batch and return its uint8 [n, 3, H, W] result: a fresh copy, or `out[:n]` when the caller

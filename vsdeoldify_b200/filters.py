@@ -308,8 +308,8 @@ class FilterBank:
         z, lib, (B, H, W) = self._zimg_state(), self.lib, self._dims()
         dh, dv, uh, uv = z["dh"], z["dv"], z["uh"], z["uv"]
         _lib.check(lib.havc_zimg_rgb_to_yuv420p8(img.data_ptr(), z["y"].data_ptr(), z["c"].data_ptr(), z["s444"].data_ptr(),
-                                                 z["s_half"].data_ptr(), B, H, W, dv[0].data_ptr(), dv[1].data_ptr(), dv[2],
-                                                 dh[0].data_ptr(), dh[1].data_ptr(), dh[2], stream), "zimg.rgb_to_yuv420p8")
+                                                 z["s_half"].data_ptr(), None, B, H, W, dv[0].data_ptr(), dv[1].data_ptr(), dv[2],
+                                                 dh[0].data_ptr(), dh[1].data_ptr(), dh[2], 0, 0, 0, stream), "zimg.rgb_to_yuv420p8")
         if -1.0 < bright < 1.0:
             bright = bright * 255.0                                # vsfilters.py:792-793
         lut = None
@@ -326,7 +326,7 @@ class FilterBank:
                                            lut.data_ptr() if lut is not None else None, stream), "zimg.tweak_yuv")
         _lib.check(lib.havc_zimg_yuv420p8_to_rgb(z["y"].data_ptr(), z["c"].data_ptr(), out.data_ptr(), z["s_half"].data_ptr(),
                                                  z["s_rgb"].data_ptr(), B, H, W, uh[0].data_ptr(), uh[1].data_ptr(), uh[2],
-                                                 uv[0].data_ptr(), uv[1].data_ptr(), uv[2], 1, stream), "zimg.yuv420p8_to_rgb")
+                                                 uv[0].data_ptr(), uv[1].data_ptr(), uv[2], 0, 0, 1, stream), "zimg.yuv420p8_to_rgb")
         return True
 
     # ---- chroma-adjust filters ------------------------------------------------------------------------------

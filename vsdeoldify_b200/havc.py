@@ -83,6 +83,43 @@ def load_state_dict(weights_name: str, models_dir: str = model_dir) -> Dict[str,
     return state["model"] if isinstance(state, dict) and "model" in state else state
 
 
+def _output_frame(src_frame, planes, out_format=None):
+    """Output frame = copy of the source frame (every prop survives, vsslib/vsutils.py:92-95) carrying the result planes; a GRAY
+    source comes back as a YUV420P8 frame with the source's props (restore_format, havc_utils.py:208-222)."""
+    if out_format is not None and getattr(src_frame.format, "id", None) != getattr(out_format, "id", out_format):
+        return vs_shim.VideoFrame([np.ascontiguousarray(p) for p in planes], out_format, dict(src_frame.props))
+    if hasattr(src_frame, "with_planes"):             # the stand-in adopts the result planes (views of a buffer that is ours)
+        return src_frame.with_planes(list(planes))
+    g = src_frame.copy()
+    for p, pl in enumerate(planes):
+        np.copyto(np.asarray(g[p]), pl)
+    return g
+
+
+def _clip_format(clip, who: str):
+    """(engine fmt, matrix, out_limited, output format) of a clip, the way convert_format_RGB24 reads them (havc_utils.py:57-164):
+    RGB24 as is; 8-bit YUV 4:2:0 and GRAY are converted on the device (matrix from frame 0's _Matrix, default BT.709; input
+    treated as limited range; the output range is the clip's _ColorRange, default limited); anything else raises."""
+    fid = getattr(clip.format, "id", clip.format)
+    ids = {getattr(getattr(vs, n, None), "id", getattr(vs, n, None)): n for n in ("RGB24", "YUV420P8", "GRAY8") if hasattr(vs, n)}
+    name = ids.get(fid)
+    if name == "RGB24":
+        return "rgb24", "709", True, None
+    if name not in ("YUV420P8", "GRAY8"):
+        _raise(f"{who}: only RGB24, YUV420P8 and GRAY8 clips are handled by the B200 build (convert_format_RGB24 for other formats "
+               "needs zimg's generic depth / subsampling conversions)")
+    props = clip.get_frame(0).props
+    m = int(props.get("_Matrix", 1))
+    if m in (1, 2):                                   # BT.709 / unspecified -> BT.709 (_matrixIsInvalid, havc_utils.py:76-77)
+        matrix = "709"
+    elif m in (5, 6):                                 # 470bg / 170m
+        matrix = "601"
+    else:
+        _raise(f"{who}: _Matrix = {m} is not handled by the B200 build (BT.709, BT.601)")
+    out_limited = int(props.get("_ColorRange", 1)) != 0                                   # 0 = full, 1 = limited (default)
+    return ("yuv420p8" if name == "YUV420P8" else "gray8"), matrix, out_limited, vs.YUV420P8
+
+
 def _engine_or_smaller_batch(cls, *args, batch: int, **kw):
     """Build an engine; when the device runs out of memory (activations scale with batch x render_factor^2) halve the batch
     down to 1, then give up (None): the caller applies the reference's out-of-memory convention."""
@@ -104,8 +141,9 @@ class _ColorizedClip:
     source frames of the NEXT batch are already fetched, uploaded and queued, so a sequential reader (the normal VapourSynth
     access pattern) keeps the device busy; any other access pattern still gets the same frames, batch by batch."""
 
-    def __init__(self, clip, engine, scenechange: bool, batch: int, run=None):
+    def __init__(self, clip, engine, scenechange: bool, batch: int, run=None, out_format=None):
         self.clip, self.engine = clip, engine
+        self.out_format = out_format                      # None: the source clip's format (frames are copies of the source frames)
         self.run = run if run is not None else engine.colorize_batch
         self.async_ok = run is None and hasattr(engine, "submit")
         self.scenechange, self.B = scenechange, batch
@@ -136,14 +174,10 @@ class _ColorizedClip:
         return srcs, batch, self._skip(n, srcs)
 
     def _store(self, n: int, srcs, out):
+        planes_of = getattr(self.engine, "out_planes", None)
         for i, f in zip(range(n, n + len(srcs)), srcs):
-            if hasattr(f, "with_planes"):             # the stand-in adopts the result planes (views of `out`, which is ours)
-                g = f.with_planes([out[i - n, p] for p in range(3)])
-            else:
-                g = f.copy()                          # all props of the source frame survive (vsutils.py:92-95)
-                for p in range(3):
-                    np.copyto(np.asarray(g[p]), out[i - n, p])
-            self.cache[i] = g
+            planes = planes_of(out, i - n) if planes_of is not None else [out[i - n, p] for p in range(3)]
+            self.cache[i] = _output_frame(f, planes, self.out_format)
         while len(self.cache) > 4 * self.B:
             self.cache.popitem(last=False)
 
@@ -152,10 +186,12 @@ class _ColorizedClip:
         n1 = min(n + self.B, self.clip.num_frames)
         srcs = [self.clip.get_frame(i) for i in range(n, n1)]
         buf = self.engine.next_input()
+        planes_of = getattr(self.engine, "in_planes", None)
 
         def put(j):
-            for p in range(3):
-                np.copyto(buf[j, p], np.asarray(srcs[j][p]))
+            dst = planes_of(buf, j) if planes_of is not None else [buf[j, p] for p in range(3)]
+            for p, d in enumerate(dst):
+                np.copyto(d, np.asarray(srcs[j][p]))
         list(_COPY_POOL.map(put, range(len(srcs))))
         return (n, srcs, self.engine.submit(None, skip=self._skip(n, srcs), n=len(srcs)))
 
@@ -226,8 +262,7 @@ def HAVC_colorizer(
         _raise("HAVC_colorizer: CPU mode (device_index=99) is not available in the B200 build (no CPU fallback)")
     if not torch.cuda.is_available():
         _raise("HAVC_colorizer: CUDA is not available")                                   # :2441
-    if getattr(clip.format, "id", clip.format) != getattr(vs.RGB24, "id", vs.RGB24):
-        _raise("HAVC_colorizer: only RGB24 input is handled by the B200 build (convert_format_RGB24 is a 'next' row)")
+    fmt, matrix, out_limited, out_format = _clip_format(clip, "HAVC_colorizer")
     if sc_threshold < 0:
         _raise("HAVC_colorizer: sc_threshold must be >= 0")                              # :2447
     if sc_min_freq < 0:
@@ -299,7 +334,8 @@ def HAVC_colorizer(
         engines = [_engine_or_smaller_batch(DeoldifyEngine, sd_video, clip.width, clip.height, render_factor=deoldify_rf, frame_size=frame_size,
                                   batch=_BATCH, dtype=_DTYPE, device=f"cuda:{d}", sd_other=sd_other, video_weight=weight,
                                   zhang=zhang, merge=merge, hue_adjust=hue_adjust, run_deoldify=run_deoldify, ddtweak=tweak,
-                                  sat=(deoldify_sat, ddcolor_sat), hue=(deoldify_hue, ddcolor_hue))
+                                  sat=(deoldify_sat, ddcolor_sat), hue=(deoldify_hue, ddcolor_hue), fmt=fmt, matrix=matrix,
+                                  out_limited=out_limited)
                    for d in devices]
     except (ValueError, FilterError) as e:
         _raise("HAVC_colorizer: " + str(e))
@@ -310,19 +346,19 @@ def HAVC_colorizer(
         return clip
     batch = min(e.B for e in engines)
     if len(engines) == 1:
-        fn = _ColorizedClip(clip, engines[0], scenechange, batch)
+        fn = _ColorizedClip(clip, engines[0], scenechange, batch, out_format=out_format)
     else:
         from .sharded import ShardedRenderer
         renderer = ShardedRenderer(clip, engines, batch, scenechange, partition=os.environ.get("HAVC_B200_PARTITION", "interleaved"),
-                                   copy_pool=_COPY_POOL)
+                                   copy_pool=_COPY_POOL, make_frame=lambda f, planes: _output_frame(f, planes, out_format))
 
         def fn(n, renderer=renderer):
             try:
                 return renderer(n)
             except KeyError as e:                    # a frame without the scene-detection prop
                 _raise("HAVC_colorizer: " + str(e.args[0]))
-    return vs_shim.VideoNode(clip.num_frames, clip.width, clip.height, clip.format, fn, clip.fps_num, clip.fps_den) \
-        if vs is vs_shim else _wrap_real_vs(clip, fn)
+    return vs_shim.VideoNode(clip.num_frames, clip.width, clip.height, out_format or clip.format, fn, clip.fps_num, clip.fps_den) \
+        if vs is vs_shim else _wrap_real_vs(clip, fn, out_format)
 
 
 _SC_PROPS = ('_SceneChangePrev', '_SceneChangeNext', 'sc_threshold', 'sc_frequency', 'sc_luma', 'sc_ratio')    # CopySCDetect, vsscdect.py:118-120
@@ -507,9 +543,13 @@ class ModelImageRender:
         return Image.fromarray(np.ascontiguousarray(np.transpose(out[0], (1, 2, 0))), "RGB")
 
 
-def _wrap_real_vs(clip, fn):
-    """Real VapourSynth: serve frames through std.ModifyFrame; the selector ignores `f` and returns our frame."""
-    return clip.std.ModifyFrame(clips=[clip], selector=lambda n, f: fn(n))
+def _wrap_real_vs(clip, fn, out_format=None):
+    """Real VapourSynth: serve frames through std.ModifyFrame; the selector ignores `f` and returns our frame.  When the output
+    format differs from the clip's (a GRAY clip comes back as YUV420P8) the node is built on a blank clip of that format."""
+    base = clip
+    if out_format is not None and clip.format.id != out_format:
+        base = vs.core.std.BlankClip(clip, format=out_format)
+    return base.std.ModifyFrame(clips=[base], selector=lambda n, f: fn(n))
 
 
 def HAVC_deoldify(clip, model: int = 0, render_factor: int = 24, sat: float = 1.0, hue: float = 0.0, **kw):

@@ -167,10 +167,12 @@ class ShardedRenderer:
                     srcs = [self.clip.get_frame(i) for i in range(i0, i1)]
                     t1 = time.perf_counter()
                     buf = eng.next_input()
+                    planes_in = getattr(eng, "in_planes", None)
 
-                    def put(k, buf=buf, srcs=srcs):
-                        for p in range(3):
-                            np.copyto(buf[k, p], np.asarray(srcs[k][p]))
+                    def put(k, buf=buf, srcs=srcs, planes_in=planes_in):
+                        dst = planes_in(buf, k) if planes_in is not None else [buf[k, p] for p in range(3)]
+                        for p, d in enumerate(dst):
+                            np.copyto(d, np.asarray(srcs[k][p]))
                     if self.copy_pool is not None:
                         list(self.copy_pool.map(put, range(len(srcs))))
                     else:
@@ -193,7 +195,9 @@ class ShardedRenderer:
                 else:
                     out = eng.collect(ticket, out=self._result_buf(r), pool=self.copy_pool)
                 t5 = time.perf_counter()
-                frames = [self.make_frame(f, out[k]) for k, f in enumerate(srcs)]
+                planes_out = getattr(eng, "out_planes", None)
+                frames = [self.make_frame(f, planes_out(out, k) if planes_out is not None else [out[k, p] for p in range(3)])
+                          for k, f in enumerate(srcs)]
                 self.stats[r]["collect"] += t5 - t4
                 self.stats[r]["frames"] += time.perf_counter() - t5
                 with self.cv:
@@ -226,11 +230,11 @@ def scene_skip_flags(i0: int, srcs, require_props: bool = True) -> np.ndarray:
     return flags
 
 
-def _adopt_planes(src_frame, planes: np.ndarray):
+def _adopt_planes(src_frame, planes):
     """Output frame = copy of the source frame (all props survive, vsslib/vsutils.py:92-95) with the result planes."""
     if hasattr(src_frame, "with_planes"):
-        return src_frame.with_planes([planes[p] for p in range(3)])
+        return src_frame.with_planes(list(planes))
     g = src_frame.copy()
-    for p in range(3):
-        np.copyto(np.asarray(g[p]), planes[p])
+    for p, pl in enumerate(planes):
+        np.copyto(np.asarray(g[p]), pl)
     return g
