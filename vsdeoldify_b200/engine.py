@@ -453,18 +453,23 @@ class DeoldifyEngine:
         ev["busy"], ev["used"], ev["ob"] = True, True, ob
         return (s, n, ob)
 
+    def prepare_async(self, buffers: int = 8):
+        """Pin the result-buffer pool of the submit() / collect_view() API now (clip adapters call this when they are built): eight
+        buffers cover two batches in flight plus the batches an adapter keeps cached around its cursor.  Pinning 200 MB takes
+        ~0.14 s and stalls the device queues of every GPU of the process (measured), so it must not happen inside the steady
+        state - nor lazily inside the first frames of a multi-GPU clip."""
+        if not hasattr(self, "_out_pool"):
+            self._out_pool = []                              # separate from h_out (the synchronous / streaming APIs own those)
+        while len(self._out_pool) < buffers:
+            t = torch.empty(*self.out_shape, dtype=torch.uint8).pin_memory()
+            self._out_pool.append((t, t.numpy()))
+
     def _acquire_out(self):
         """(pinned tensor, its numpy view) from the result-buffer pool: the first one whose numpy view is referenced by nobody
         else (frames handed out by collect_view() are views of it and keep it busy through `.base`), else a new one."""
         import sys
         if not hasattr(self, "_out_pool"):
-            # separate from h_out (the synchronous / streaming APIs own those).  Eight buffers cover two batches in flight plus
-            # the batches a clip adapter keeps cached around its cursor; they are pinned ONCE here (pinning 200 MB takes ~0.14 s
-            # and stalls the device queue: measured, so growing the pool inside the steady state is what must not happen)
-            self._out_pool = []
-            for _ in range(8):
-                t = torch.empty(*self.out_shape, dtype=torch.uint8).pin_memory()
-                self._out_pool.append((t, t.numpy()))
+            self.prepare_async()
         for ob in self._out_pool:
             if sys.getrefcount(ob[1]) <= 2 and not any(ob is e.get("ob") for e in getattr(self, "_ev", [])):
                 return ob

@@ -345,6 +345,8 @@ def HAVC_colorizer(
                                                      "Returning original image.")
         return clip
     batch = min(e.B for e in engines)
+    for e in engines:
+        e.prepare_async()                 # pin the result-buffer pools before the first frame is requested
     if len(engines) == 1:
         fn = _ColorizedClip(clip, engines[0], scenechange, batch, out_format=out_format)
     else:
