@@ -420,3 +420,23 @@ def test_shuffle_blur_fused_equals_unfused_and_torch(B, H, W, Cin, Cout, dtype):
         assert torch.equal(fused, unfused), f"pair={pair}: {(fused != unfused).sum().item()} of {fused.numel()} values differ"
     _check(fused[..., :cg].permute(0, 3, 1, 2), ref, dtype, "shuffle+blur")
     assert (fused[..., cg:] == 0).all()
+
+
+def test_fp16_outputs_saturate_instead_of_overflowing():
+    """fp16 tops out at 65504: an epilogue value beyond it is stored as +-65504 (F2FP.SATFINITE), not as inf - an inf would become
+    NaN for the whole receptive field in the next layer (0 * inf, inf - inf).  Values inside the range are untouched."""
+    from vsdeoldify_b200 import ops
+    _setup()
+    dev = "cuda"
+    B, H, W, C = 1, 16, 16, 64
+    x = torch.full((B, H, W, C), 30.0, device=dev, dtype=torch.float16)
+    w = torch.zeros(64, C, 1, 1)
+    w[0, :, 0, 0] = 40.0            # 64 * 30 * 40 = 76800 > 65504
+    w[1, :, 0, 0] = -40.0
+    w[2, :, 0, 0] = 1.0             # 1920: representable
+    wp, meta = ops.pack_conv_weight(w, None, dtype=torch.float16)
+    out = torch.zeros(B, H, W, 64, device=dev, dtype=torch.float16)
+    ops.make_conv(x, wp.to(dev), out, ops.taps_for(1), n_total=meta["rows"]).launch()
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
+    assert (out[..., 0] == 65504).all() and (out[..., 1] == -65504).all() and (out[..., 2] == 1920).all() and (out[..., 3:] == 0).all()

@@ -57,8 +57,11 @@ static inline void device_done(std::atomic<unsigned long long> &mask, unsigned l
 #ifdef __CUDACC__
 __device__ __forceinline__ uint32_t pack2(float a, float b, int dtype) {
     if (dtype == HAVC_F16) {
-        __half2 h = __floats2half2_rn(a, b);
-        return *reinterpret_cast<uint32_t *>(&h);
+        // saturating conversion (F2FP.SATFINITE, one instruction): a value beyond fp16's 65504 is stored as +-65504 instead of
+        // inf, which the next layer would turn into NaN (inf - inf, 0 * inf) for the whole receptive field
+        uint32_t r;
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+        return r;
     } else {
         __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
         return *reinterpret_cast<uint32_t *>(&h);
@@ -77,7 +80,7 @@ __device__ __forceinline__ float load16(const void *p, int64_t idx, int dtype) {
 }
 __device__ __forceinline__ void store16(void *p, int64_t idx, float v, int dtype) {
     if (dtype == HAVC_F16)
-        reinterpret_cast<__half *>(p)[idx] = __float2half_rn(v);
+        reinterpret_cast<__half *>(p)[idx] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
     else
         reinterpret_cast<__nv_bfloat16 *>(p)[idx] = __float2bfloat16_rn(v);
 }
