@@ -238,6 +238,22 @@ int havc_adaptive_luma_merge(const uint8_t *a, const uint8_t *b, uint8_t *out, i
 int havc_restore_color_gradient(const uint8_t *color, const uint8_t *gray, uint8_t *out, int B, int H, int W, double sat,
                                 const uint8_t *lut, const uint8_t *lut_gated, double weight, double weight_gated,
                                 const unsigned long long *stats_gray, double merge_weight, int simd_width, void *stream);
+/* The temporal chroma stabiliser (scope row N3: vs_chroma_stabilizer_ex, vsslib/vsfilters.py:84-287).
+ * havc_gray_mask_stats: stats[b] = { sum of OpenCV Y (get_image_luma, imfilters.py:597-601), number of pixels whose OpenCV
+ *   HSV saturation is < tht (the gray mask of restore_color, restcolor.py:51-55) }.
+ * havc_restore_color: restore_color (restcolor.py:38-83) as vs_sc_recover_clip_color calls it (vsfilters.py:327-351): gray pixels
+ *   of `gray` take the (desaturated) colours of `color`; weight > 0 merges with `gray`, < 0 with the colours; frames with a luma
+ *   outside [0.22, 0.78] use min(weight, -0.8); a frame whose gray share exceeds tht_scen, or with active[b] == 0 (frame number
+ *   < 15), comes back untouched.  lut: device table [256], lut[s] = s < tht ? 255 : 0.
+ * havc_average_frames_u8: std.AverageFrames on 8-bit planes (vsfilters.py:58,242,272; VapourSynth's filter restated, unpinned):
+ *   out[b] = clamp((sum_k w[k] * src[k * clip_stride + b * frame_elems + ..] + scale / 2) / scale); clip_stride = frame_elems
+ *   gives the temporal form on a sequence that carries its halo frames; weights are [n_clips] or per frame [B][n_clips]. */
+int havc_gray_mask_stats(const uint8_t *img, int B, int H, int W, int tht, unsigned long long *stats, void *stream);
+int havc_restore_color(const uint8_t *color, const uint8_t *gray, uint8_t *out, int B, int H, int W, double sat, int tht,
+                       double weight, double tht_scen, const unsigned long long *stats_gray, const uint8_t *active,
+                       const uint8_t *lut, int simd_width, void *stream);
+int havc_average_frames_u8(const uint8_t *src, long long clip_stride, int n_clips, const int *weights, int weights_per_frame,
+                           int scale, uint8_t *out, int B, long long frame_elems, void *stream);
 /* adjust_chroma (restcolor.py:239-286) behind adjust_hue_range / vs_sc_adjust_clip_hue (vsfilters.py:435-455). */
 int havc_adjust_chroma(const uint8_t *img, uint8_t *out, int B, int H, int W, const havc_hue_ranges *ranges, double sat, int hue,
                        double weight, int simd_width, void *stream);

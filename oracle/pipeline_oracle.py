@@ -112,6 +112,23 @@ def havc_stabilizer_frame(frame: np.ndarray, dark=False, dark_p=(0.2, 0.8), smoo
     return px.chroma_post_process(up, frame)
 
 
+def havc_stabilizer_clip(frames: np.ndarray, only, dark=False, dark_p=(0.2, 0.8), smooth=False, smooth_p=(0.3, 0.7, 0.9, 0.0, "none"),
+                         colormap_adjust: str = "none", stab_p=(5, 'A', 1, 15, 0.2, 0.8), render_factor: int = 24,
+                         kernel: str = "spline64", props=None) -> dict:
+    """HAVC_stabilizer with stab=True up to (not including) vs_reduce_flicker, the external ReduceFlicker plugin
+    (vsdeoldify/__init__.py:2792-2871): squeeze, per-frame stages, vs_chroma_stabilizer_ex on the squeezed clip (scope row N3,
+    oracle/temporal_oracle.py), _clip_chroma_resize.  frames uint8 [T,H,W,3]; returns {n: uint8 [H,W,3]} for n in `only`."""
+    from . import filters_oracle as fo, temporal_oracle as to
+    T, H, W = frames.shape[:3]
+    S = min(render_factor * 16, W)
+    small = np.stack([fo.stabilizer_stages(px.resize_plane_u8(frames[n], S, S, kernel), dark, dark_p, smooth, smooth_p, colormap_adjust)
+                      for n in range(T)])
+    hue = stab_p[6] if len(stab_p) > 6 else "none"
+    st = to.chroma_stabilizer_ex(small, nframes=stab_p[0], mode=stab_p[1], sat=stab_p[2], tht=stab_p[3], weight=stab_p[4],
+                                 tht_scen=stab_p[5], hue_adjust=hue.lower(), props=props, only=list(only))
+    return {n: px.chroma_post_process(px.resize_plane_u8(st[n], W, H, kernel), frames[n]) for n in only}
+
+
 def colorizer_filter(sd, img: np.ndarray, render_factor: int) -> np.ndarray:
     """MasterFilter([ColorizerFilter]).filter(img, img, rf) (deoldify/filters.py:81-124) on a uint8 [H,W,3] image:
     Pillow-BILINEAR squeeze to S x S, network, Pillow-BILINEAR back, luma transplant.  This is the path

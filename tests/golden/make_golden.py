@@ -278,6 +278,126 @@ def golden_stabilizer():
     print("stabilizer golden:", len(out), "arrays")
 
 
+def temporal_test_clip(seed, T, h, w):
+    """A short colourful clip with motion (a pattern drifting over a fixed background), gray areas and a luma ramp over time so
+    that both branches of the frame-luma gate and the gray mask of restore_color are exercised."""
+    rng = np.random.default_rng(seed)
+    a, b = filter_test_pair(seed, h, w + T, 0.45)
+    frames = []
+    for t in range(T):
+        img = a[:, t:t + w].astype(np.float32) * 0.7 + b[:, T - t:T - t + w].astype(np.float32) * 0.3
+        img[h // 3: h // 2, w // 4: w // 2] = img[h // 3: h // 2, w // 4: w // 2].mean(-1, keepdims=True)   # a gray box
+        gain = 0.35 + 1.1 * t / max(T - 1, 1)                     # frame luma from ~0.15 to ~0.65
+        img = img * gain + rng.normal(0, 1.5, img.shape)
+        frames.append(np.clip(img, 0, 255).astype(np.uint8))
+    return np.stack(frames)
+
+
+def _install_vs_primitives(vs_shim):
+    """Give the VapourSynth stand-in the two primitives the reference's temporal stabiliser calls — `clip.resize.Bicubic` between
+    RGB24 and YUV420P8 and `std.AverageFrames` — backed by the restatements in oracle/ (zimg_oracle, temporal_oracle).  Golden
+    generation only: this pins the reference's GRAPH (which frame / plane goes where), not the primitives (unpinned)."""
+    from oracle import temporal_oracle as to, zimg_oracle as zo
+
+    class _Resize:
+        def __init__(self, clip):
+            self.clip = clip
+
+        def Bicubic(self, format=None, matrix_s=None, matrix_in_s=None, range_s=None, dither_type="none", **kw):
+            src = self.clip
+            fmt = format if isinstance(format, vs_shim.VideoFormat) else {1: vs_shim.RGB24, 3: vs_shim.YUV420P8}[int(format)]
+            dither = dither_type == "error_diffusion"
+            assert range_s == "full"
+
+            def fn(n):
+                f = src.get_frame(n)
+                if src.format == vs_shim.RGB24 and fmt == vs_shim.YUV420P8:
+                    assert matrix_s == "709"
+                    planes = zo.rgb24_to_yuv420p8(np.dstack([np.asarray(f[p]) for p in range(3)]), "709", False, dither)
+                elif src.format == vs_shim.YUV420P8 and fmt == vs_shim.RGB24:
+                    assert matrix_in_s == "709"
+                    rgb = zo.yuv420p8_to_rgb24(np.asarray(f[0]), np.asarray(f[1]), np.asarray(f[2]), dither, "709", False)
+                    planes = [np.ascontiguousarray(rgb[..., p]) for p in range(3)]
+                else:
+                    raise AssertionError("conversion not needed by the temporal stabiliser")
+                return vs_shim.VideoFrame(list(planes), fmt, dict(f.props))
+            return vs_shim.VideoNode(src.num_frames, src.width, src.height, fmt, fn, src.fps_num, src.fps_den)
+
+    vs_shim.VideoNode.resize = property(lambda self: _Resize(self))
+
+    def AverageFrames(self, clips=None, weights=None, scale=None, scenechange=None, planes=None):
+        clips = self._clip if clips is None else clips
+        single = isinstance(clips, vs_shim.VideoNode) or len(clips) == 1
+        lst = [clips] if isinstance(clips, vs_shim.VideoNode) else list(clips)
+        base = lst[0]
+        planes_ = [0, 1, 2] if planes is None else list(planes)
+        sc = sum(weights) if scale is None else scale
+
+        def fn(n):
+            if single:
+                r = len(weights) // 2
+                fr = [base.get_frame(min(max(n + d, 0), base.num_frames - 1)) for d in range(-r, r + 1)]
+                w = list(weights)
+                if scenechange:
+                    w = to.scene_folded_weights(w, [f.props.get("_SceneChangePrev", 0) for f in fr], [f.props.get("_SceneChangeNext", 0) for f in fr])
+                center = fr[r]
+            else:
+                fr, w, center = [c.get_frame(n) for c in lst], list(weights), lst[0].get_frame(n)
+            out = [to.average_planes([np.asarray(f[p]) for f in fr], w, sc) if p in planes_ else np.asarray(center[p]).copy()
+                   for p in range(base.format.num_planes)]
+            return vs_shim.VideoFrame(out, base.format, dict(center.props))
+        return vs_shim.VideoNode(base.num_frames, base.width, base.height, base.format, fn, base.fps_num, base.fps_den)
+
+    vs_shim._Std.AverageFrames = lambda self, clips=None, weights=None, scale=None, scenechange=None, planes=None: \
+        AverageFrames(self, clips, weights, scale, scenechange, planes)
+
+
+def golden_temporal():
+    """Scope row N3: the REAL vs_chroma_stabilizer_ex / vs_clip_color_stabilizer / vs_sc_recover_clip_color / restore_color /
+    weight-table code of the reference on the stand-in (see _install_vs_primitives for what that does and does not pin)."""
+    refshim.install()
+    from vsdeoldify_b200 import vs_shim
+    sys.modules["vapoursynth"] = vs_shim
+    _install_vs_primitives(vs_shim)
+    from PIL import Image
+    from vsdeoldify.vsslib import restcolor, vsfilters
+    out = {}
+    T, H, W = 20, 24, 32
+    clip_np = temporal_test_clip(91, T, H, W)
+    out["clip"] = clip_np
+    for n in range(3, 16):
+        out[f"avg_arith_{n}"] = np.array(vsfilters._build_avg_arithmetic(n))
+        out[f"avg_weighted_{n}"] = np.array(vsfilters._build_avg_weighted(n))
+    # restore_color, image level
+    for k, (i, j, kw) in enumerate([(16, 17, dict(sat=1.0, tht=15, weight=0.2, tht_scen=0.8)),
+                                    (5, 18, dict(sat=0.8, tht=40, weight=-0.5, tht_scen=0.8)),
+                                    (19, 2, dict(sat=1.0, tht=30, weight=0.0, tht_scen=0.9, hue_adjust="0:60|0.8,0.1")),
+                                    (10, 11, dict(sat=1.0, tht=250, weight=0.2, tht_scen=0.5))]):     # last: the tht_scen bypass
+        out[f"restore_{k}"] = np.asarray(restcolor.restore_color(Image.fromarray(clip_np[i]), Image.fromarray(clip_np[j]), **kw))
+    props = [{"_SceneChangePrev": int(n in (0, 9)), "_SceneChangeNext": int(n in (8, T - 1))} for n in range(T)]
+    clip = vs_shim.array_clip(np.ascontiguousarray(np.transpose(clip_np, (0, 3, 1, 2))), props=props)
+    get = lambda c, n: np.dstack([np.asarray(c.get_frame(n)[p]) for p in range(3)])
+    # the selector of vs_sc_recover_clip_color (n < 15 passes through; the luma gate flips the weight on dark frames)
+    other = vs_shim.array_clip(np.ascontiguousarray(np.transpose(clip_np[::-1], (0, 3, 1, 2))))
+    rec = vsfilters.vs_recover_clip_color(clip=other, clip_color=clip, sat=0.9, tht=25, weight=0.3, tht_scen=0.8)
+    for n in (3, 15, 19):
+        out[f"recover_{n}"] = get(rec, n)
+    frames = (0, 1, 8, 9, 14, 15, 16, 18, 19)
+    out["frames"] = np.array(frames)
+    st = vsfilters.vs_chroma_stabilizer_ex(clip, nframes=5, mode="A", sat=1.0, tht=15, weight=0.2, tht_scen=0.8, hue_adjust="none", algo=0)
+    for n in frames:
+        out[f"stab_default_{n}"] = get(st, n)
+    st = vsfilters.vs_chroma_stabilizer_ex(clip, nframes=3, mode="W", sat=0.8, tht=30, weight=-0.4, tht_scen=0.8,
+                                           hue_adjust="0:60|0.8,0.1", algo=0)
+    for n in frames:
+        out[f"stab_w3_{n}"] = get(st, n)
+    st = vsfilters.vs_chroma_stabilizer_ex(clip, nframes=7, mode="A", tht=0)              # vs_clip_color_stabilizer, scenechange=True
+    for n in frames:
+        out[f"stab_tht0_{n}"] = get(st, n)
+    np.savez_compressed(os.path.join(HERE, "vsslib_temporal.npz"), **out)
+    print("temporal golden:", len(out), "arrays")
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1:        # regenerate selected fixtures only: python make_golden.py golden_render_narrow ...
         for name in sys.argv[1:]:
@@ -289,5 +409,6 @@ if __name__ == "__main__":
     golden_filters()
     golden_zhang()
     golden_stabilizer()
+    golden_temporal()
     golden_render()
     print("golden fixtures written to", HERE)

@@ -1,6 +1,8 @@
 """GPU tests through the plugin surface (HAVC_colorizer / HAVC_main on clips): frame order under out-of-order
 requests, bit-exact property pass-through, scene-change gating, and the stable/artistic S x S blend against the
 CPU oracle."""
+import os
+
 import numpy as np
 import pytest
 
@@ -416,3 +418,68 @@ def test_zimg_conversions_bit_exact_vs_restatement():
     torch.cuda.synchronize()
     for j in range(B):
         assert np.array_equal(np.transpose(back[j].cpu().numpy(), (1, 2, 0)), zo.gray8_to_rgb24(imgs[j][..., 0]))
+
+
+GT = np.load(os.path.join(os.path.dirname(__file__), "golden", "vsslib_temporal.npz"))
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("stab_default", dict(nframes=5, mode="A", sat=1.0, tht=15, weight=0.2, tht_scen=0.8)),
+    ("stab_w3", dict(nframes=3, mode="W", sat=0.8, tht=30, weight=-0.4, tht_scen=0.8, hue_adjust="0:60|0.8,0.1")),
+    ("stab_tht0", dict(nframes=7, mode="A", tht=0))])
+def test_temporal_stabilizer_bit_exact_vs_reference_graph(name, kw):
+    """Scope row N3: vs_chroma_stabilizer_ex on the device against the golden of the REAL reference graph
+    (tests/golden/make_golden.py::golden_temporal; zimg / std.AverageFrames underneath restated: unpinned).  Every byte equal:
+    halo frames at the clip's ends and across batch boundaries, the n < 15 pass-through, the luma gate, the scene-change
+    folding of the weights, props untouched, any request order."""
+    from vsdeoldify_b200 import havc, vs_shim
+    clip_np = GT["clip"]
+    T = clip_np.shape[0]
+    props = [{"_SceneChangePrev": int(n in (0, 9)), "_SceneChangeNext": int(n in (8, T - 1)), "idx": n} for n in range(T)]
+    clip = vs_shim.array_clip(np.ascontiguousarray(np.transpose(clip_np, (0, 3, 1, 2))), props=props)
+    out = havc.vs_chroma_stabilizer_ex(clip, **kw)
+    frames = [int(n) for n in GT["frames"]]
+    for n in frames[::-1]:
+        f = out.get_frame(n)
+        assert f.props == props[n]
+        got = np.dstack([np.asarray(f[p]) for p in range(3)])
+        want = GT[f"{name}_{n}"]
+        assert np.array_equal(got, want), (name, n, int((got != want).sum()), int(np.abs(got.astype(int) - want).max()))
+
+
+def test_havc_stabilizer_temporal_chain_with_host_plugin():
+    """HAVC_stabilizer(stab=True): squeeze -> per-frame stages -> temporal stabiliser -> (host-provided ReduceFlicker) ->
+    _clip_chroma_resize, against the CPU restatement of the chain.  The plugin is external (vsplugins.py:263-272): the test
+    registers a pass-through `core.rdfl` on the stand-in and checks that it is what the chain ends in."""
+    from oracle import pipeline_oracle
+    from vsdeoldify_b200 import havc, vs_shim
+    import types
+    fr = np.ascontiguousarray(np.kron(GT["clip"], np.ones((1, 2, 2, 1), np.uint8)))       # the golden clip, 2x: 20 x 48 x 64 x 3
+    T, H, W = fr.shape[:3]
+    props = [{"_SceneChangePrev": int(n == 0), "idx": n} for n in range(T)]
+    clip = vs_shim.array_clip(np.ascontiguousarray(np.transpose(fr, (0, 3, 1, 2))), props=props)
+    with pytest.raises(vs_shim.Error, match="ReduceFlicker"):
+        havc.HAVC_stabilizer(clip, stab=True, render_factor=16)
+    calls = []
+
+    def reduce_flicker(clip=None, strength=None, aggressive=None):
+        calls.append((strength, aggressive))
+        return clip
+    vs_shim.core.rdfl = types.SimpleNamespace(ReduceFlicker=reduce_flicker)
+    try:
+        kw = dict(dark=True, dark_p=[0.2, 0.8], smooth=True, smooth_p=[0.3, 0.7, 0.9, 0.0, "none"])
+        out = havc.HAVC_stabilizer(clip, stab=True, stab_p=[5, 'A', 1, 15, 0.2, 0.8], render_factor=16, **kw)
+        assert calls == [(2, 0)]                                                      # vs_reduce_flicker's defaults
+        only = (16, 3, 19)
+        ref = pipeline_oracle.havc_stabilizer_clip(fr, only, render_factor=16, **kw)
+        for n in only:
+            f = out.get_frame(n)
+            assert f.props == props[n]
+            img = np.stack([np.asarray(f[p]) for p in range(3)], -1)
+            d = np.abs(img.astype(int) - ref[n].astype(int))
+            # the Spline64 squeeze may differ in the last bit before rounding; error diffusion then places its +-1 decisions
+            # elsewhere: a tolerance on the distribution, the temporal stage itself is bit-exact (test above)
+            assert d.mean() < 0.35 and np.percentile(d, 99) <= 2, (n, float(d.mean()), int(d.max()))
+            assert not np.array_equal(img, fr[n])
+    finally:
+        del vs_shim.core.rdfl

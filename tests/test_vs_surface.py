@@ -134,8 +134,11 @@ def test_stabilizer_surface_and_errors():
     clip = _clip()
     with pytest.raises(vs_shim.Error, match="render_factor must be between: 16-64"):       # :2796
         havc.HAVC_stabilizer(clip, dark=True, render_factor=12)
-    with pytest.raises(vs_shim.Error, match="temporal"):
+    # stab=True ends in the external ReduceFlicker plugin (vsplugins.py:263-272): without it, the reference's own error
+    with pytest.raises(vs_shim.Error, match="ReduceFlicker.dll' not properly loaded/installed"):
         havc.HAVC_stabilizer(clip, stab=True)
+    with pytest.raises(vs_shim.Error, match="algo=1"):
+        havc.vs_chroma_stabilizer_ex(clip, tht=15, algo=1)
 
 
 def test_deprecated_aliases_forward_like_the_reference(monkeypatch):

@@ -88,6 +88,38 @@ __global__ void frame_stats_kernel(Img img, unsigned long long *stats, float bri
     block_add(sl, stats + 2 * b + 1);
 }
 
+// stats[b][0] = sum of OpenCV Y (get_image_luma, imfilters.py:597-601), stats[b][1] = number of pixels whose OpenCV HSV
+// saturation is below `tht` (the gray mask of restore_color, restcolor.py:51-55)
+__global__ void gray_mask_stats_kernel(Img img, unsigned long long *stats, int tht) {
+    const int b = blockIdx.y;
+    unsigned long long sy = 0, cnt = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < img.plane; i += (long long)gridDim.x * blockDim.x) {
+        int r, g, bl, y, u, v, h, s, vv;
+        img.load(b, i, r, g, bl);
+        rgb2yuv(r, g, bl, y, u, v);
+        rgb2hsv(r, g, bl, h, s, vv);
+        sy += (unsigned)y;
+        cnt += s < tht ? 1u : 0u;
+    }
+    block_add(sy, stats + 2 * b);
+    block_add(cnt, stats + 2 * b + 1);
+}
+
+// std.AverageFrames on 8-bit planes (VapourSynth averageframes restated; unpinned): out = clamp((sum_k w_k * src_k + scale/2) / scale).
+// Source k of frame b is src + k * clip_stride + b * frame_elems: clip_stride = a whole clip for the multi-clip form,
+// = frame_elems for the temporal form on a sequence that carries its halo frames.  Weights are per frame (scene-change folding).
+__global__ void average_frames_u8_kernel(const uint8_t *__restrict__ src, long long clip_stride, int n_clips, const int *__restrict__ weights,
+                                         int weights_per_frame, int scale, uint8_t *__restrict__ out, long long frame_elems) {
+    const int b = blockIdx.y;
+    const int *w = weights + (weights_per_frame ? (long long)b * n_clips : 0);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < frame_elems; i += (long long)gridDim.x * blockDim.x) {
+        int acc = 0;
+        for (int k = 0; k < n_clips; ++k) acc += w[k] * (int)src[k * clip_stride + (long long)b * frame_elems + i];
+        acc = (acc + scale / 2) / scale;
+        out[(long long)b * frame_elems + i] = (uint8_t)(acc < 0 ? 0 : (acc > 255 ? 255 : acc));
+    }
+}
+
 // ---- chroma_stabilizer / chroma_stabilizer_adaptive (imfilters.py:160-269) -------------------------------------
 struct StabParams {
     int adaptive;
@@ -243,9 +275,25 @@ struct RestoreParams {
     int gate; double dark, bright;       // DEF_STANDARD_DARK / BRIGHT gating on the frame luma of `gray`
     int merge_w15;                       // std.Merge(gray, restored, w): 15-bit weight, < 0 = no merge
     int W, simd_width;
+    // restore_color (restcolor.py:38-83, the temporal stabiliser's binary restore): frame-level bypasses -> out = gray
+    const uint8_t *active;               // per frame; 0 = the selector returns the frame untouched (n < 15, vsfilters.py:337)
+    double tht_scen;                     // > 0: a frame whose share of gray pixels (stats[2b+1] / plane) exceeds it is returned as is
 };
 __global__ void restore_color_gradient_kernel(Img color, Img gray, uint8_t *out, RestoreParams p, const unsigned long long *stats) {
     const int fb = blockIdx.y;
+    bool bypass = p.active != nullptr && p.active[fb] == 0;
+    if (!bypass && p.tht_scen > 0.0 && p.tht_scen < 1.0) {                 // np.mean(mask) / 255 > tht_scen (restcolor.py:55-61)
+        const double share = __ddiv_rn(__ddiv_rn((double)(255ull * stats[2 * fb + 1]), (double)gray.plane), 255.0);
+        bypass = share > p.tht_scen;
+    }
+    if (bypass) {
+        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < gray.plane; i += (long long)gridDim.x * blockDim.x) {
+            int rg, gg, bg;
+            gray.load(fb, i, rg, gg, bg);
+            store_px(out, gray.plane, fb, i, rg, gg, bg);
+        }
+        return;
+    }
     bool gated = false;
     if (p.gate) {
         const double luma = frame_luma(stats[2 * fb], gray.plane);
@@ -587,6 +635,54 @@ extern "C" int havc_restore_color_gradient(const uint8_t *color, const uint8_t *
     p.W = W; p.simd_width = simd_width;
     Img ic{color, (long long)H * W}, ig{gray, (long long)H * W};
     restore_color_gradient_kernel<<<frame_grid(ic.plane, B), 256, 0, (cudaStream_t)stream>>>(ic, ig, out, p, stats_gray);
+    HAVC_LAUNCHED();
+    return HAVC_OK;
+}
+
+/* restore_color (restcolor.py:38-83) as vs_sc_recover_clip_color calls it (vsfilters.py:327-351): binary gray mask (OpenCV S of
+   `gray` < tht) takes the (desaturated) colours of `color`; weight > 0 merges the result with `gray`, < 0 with the colours;
+   frames whose luma is outside [0.22, 0.78] use min(weight, -0.8); a frame whose gray share exceeds tht_scen, or whose
+   active[b] == 0, is returned untouched.  stats = havc_gray_mask_stats(gray). */
+extern "C" int havc_restore_color(const uint8_t *color, const uint8_t *gray, uint8_t *out, int B, int H, int W, double sat, int tht,
+                                  double weight, double tht_scen, const unsigned long long *stats_gray, const uint8_t *active,
+                                  const uint8_t *lut, int simd_width, void *stream) {
+    HAVC_CHECK_ARG(color && gray && out && lut && stats_gray && HAVC_IMG_ARGS_OK(B, H, W) && tht >= 0 && tht <= 256,
+                   "havc_restore_color: bad arguments");
+    RestoreParams p;
+    memset(&p, 0, sizeof(p));
+    p.scale_sat = sat != 1.0;
+    p.sat = sat < 0 ? 0 : (sat > 10 ? 10 : sat);
+    p.lut = lut; p.lut_gated = lut;                                       // lut[s] = s < tht ? 255 : 0 (host-built)
+    const double wg = weight < -0.8 ? weight : -0.8;                      // vsfilters.py:347-348
+    // the kernel's sign convention is restore_color_gradient's (> 0: merge with the colours), restore_color's is the opposite
+    p.w = fabs(weight); p.omw = 1.0 - p.w; p.wsign = weight > 0 ? -1 : (weight < 0 ? 1 : 0);
+    p.wg = fabs(wg); p.omwg = 1.0 - p.wg; p.wgsign = 1;
+    p.gate = 1; p.dark = 0.22; p.bright = 0.78;
+    p.merge_w15 = -1;
+    p.W = W; p.simd_width = simd_width;
+    p.active = active; p.tht_scen = tht_scen;
+    Img ic{color, (long long)H * W}, ig{gray, (long long)H * W};
+    restore_color_gradient_kernel<<<frame_grid(ic.plane, B), 256, 0, (cudaStream_t)stream>>>(ic, ig, out, p, stats_gray);
+    HAVC_LAUNCHED();
+    return HAVC_OK;
+}
+
+extern "C" int havc_gray_mask_stats(const uint8_t *img, int B, int H, int W, int tht, unsigned long long *stats, void *stream) {
+    HAVC_CHECK_ARG(img && stats && HAVC_IMG_ARGS_OK(B, H, W), "havc_gray_mask_stats: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    HAVC_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(unsigned long long) * 2 * B, st));
+    Img im{img, (long long)H * W};
+    gray_mask_stats_kernel<<<frame_grid(im.plane, B), 256, 0, st>>>(im, stats, tht);
+    HAVC_LAUNCHED();
+    return HAVC_OK;
+}
+
+extern "C" int havc_average_frames_u8(const uint8_t *src, long long clip_stride, int n_clips, const int *weights, int weights_per_frame,
+                                      int scale, uint8_t *out, int B, long long frame_elems, void *stream) {
+    HAVC_CHECK_ARG(src && weights && out && B > 0 && frame_elems > 0 && n_clips > 0 && n_clips <= 31 && scale > 0 && clip_stride > 0,
+                   "havc_average_frames_u8: bad arguments");
+    average_frames_u8_kernel<<<frame_grid(frame_elems, B), 256, 0, (cudaStream_t)stream>>>(src, clip_stride, n_clips, weights,
+                                                                                           weights_per_frame, scale, out, frame_elems);
     HAVC_LAUNCHED();
     return HAVC_OK;
 }

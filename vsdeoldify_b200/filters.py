@@ -11,6 +11,8 @@ from __future__ import annotations
 import ctypes as C
 from typing import List, Optional, Sequence, Tuple
 
+import math
+
 import numpy as np
 import torch
 
@@ -436,6 +438,167 @@ class FilterBank:
         return True
 
 
+def stab_weight_list(nframes: int, mode: str) -> list:
+    """The temporal weights of vs_chroma_stabilizer_ex / vs_clip_color_stabilizer (vsfilters.py:40-51, 118-160), scale 100."""
+    if nframes % 2 == 0:
+        nframes += 1
+    n = max(3, min(nframes, 15))
+    nh = round((n - 1) / 2)
+    if mode in ("A", "arithmetic", "center"):
+        wi = math.trunc(100.0 / n)
+        return [wi] * nh + [100 - (n - 1) * wi] + [wi] * nh
+    if mode in ("W", "weighted", "left", "right"):
+        base = n * (n + 1) * 0.5
+        side = [math.trunc(100 * (i + 1) / base) for i in range(nh)]
+        return side + [100 - 2 * sum(side)] + side
+    raise FilterError("HybridAVC: unknown average method: " + str(mode))
+
+
+def scene_folded_weights(weights, prev_flags, next_flags) -> list:
+    """std.AverageFrames(scenechange=True) (vsfilters.py:58; VapourSynth's filter restated, unpinned): the weights of the frames
+    beyond a _SceneChangePrev (left) / _SceneChangeNext (right) boundary are added to the boundary frame's."""
+    w = list(weights)
+    n, c = len(w), len(w) // 2
+    lo, hi = 0, n - 1
+    for i in range(c, 0, -1):
+        if prev_flags[i]:
+            lo = i
+            break
+    for i in range(c, n - 1):
+        if next_flags[i]:
+            hi = i
+            break
+    for i in range(lo):
+        w[lo] += w[i]
+        w[i] = 0
+    for i in range(n - 1, hi, -1):
+        w[hi] += w[i]
+        w[i] = 0
+    return w
+
+
+class TemporalStabilizer:
+    """The temporal chroma stabiliser, scope row N3: vs_chroma_stabilizer_ex (vsslib/vsfilters.py:84-287; algo = 0, the value
+    HAVC_stabilizer passes) on a batch of B frames that carries its `nh` halo frames on either side: `seq` u8
+    [B + 2 nh, 3, H, W] (frame b of the batch is seq[nh + b]; the caller clamps the halo to the clip's ends like
+    std.AverageFrames does), result u8 [B, 3, H, W].
+
+      tht > 0 (_average_clips_ex, :214-249): for every offset d != 0 the frame with the chroma of frame n + d
+        (vs_get_clip_frame, :259-287: YUV420P8 round trip, error diffusion on the way back) is repaired against frame n
+        (vs_recover_clip_color -> restore_color: gray pixels take frame n's colours; frames n < 15 pass), converted to YUV420P8
+        with error diffusion, and the chroma planes of the 2 nh + 1 clips are averaged with the weight table; luma = first clip's.
+      tht = 0 (vs_clip_color_stabilizer, :38-63): std.AverageFrames of the neighbours' chroma, scene-change aware
+        (per-frame weights, folded on the host from the frame props).
+    Every zimg / std.AverageFrames step is a restatement (csrc/zimg.cu, oracle/zimg_oracle.py: parity unpinned).  The serial part
+    (Floyd-Steinberg) runs as one wavefront warp per plane and frame: B * 3 planes in flight per launch."""
+
+    def __init__(self, B: int, H: int, W: int, device, nframes: int = 5, mode: str = "A", sat: float = 1.0, tht: int = 0,
+                 weight: float = 0.5, tht_scen: float = 0.8, hue_adjust: str = "none", simd_width: int = CV_SIMD_WIDTH):
+        from . import resample
+        if H % 2 or W % 2:
+            raise FilterError("HAVC_stabilizer: the temporal stabiliser's YUV420P8 round trips need an even frame size")
+        self.lib, self.dev = _lib.lib(), torch.device(device)
+        self.B, self.H, self.W = B, H, W
+        self.wl = stab_weight_list(nframes, mode)
+        self.nh = len(self.wl) // 2
+        self.sat, self.tht, self.weight, self.tht_scen = float(sat), int(tht), float(weight), float(tht_scen)
+        self.hue_adjust = (hue_adjust or "none").lower()
+        self.simd = simd_width
+        dev, n, nc, T, K = self.dev, H * W, (H // 2) * (W // 2), B + 2 * self.nh, 2 * self.nh + 1
+        up = lambda t: (torch.from_numpy(t[0]).to(dev), torch.from_numpy(np.ascontiguousarray(t[1])).to(dev), int(t[1].shape[1]))
+        self.dh, self.dv, self.uh, self.uv = (up(t) for t in resample.chroma420_tables(W, H))
+        u8, f32 = dict(dtype=torch.uint8, device=dev), dict(dtype=torch.float32, device=dev)
+        self.y_nd, self.c_nd = torch.empty(T, H, W, **u8), torch.empty(T, 2, H // 2, W // 2, **u8)      # no-dither YUV of the sequence
+        self.ys, self.cs = torch.empty(K, B, H, W, **u8), torch.empty(K, B, 2, H // 2, W // 2, **u8)    # the clips std.AverageFrames sees
+        self.c_avg = torch.empty(B, 2, H // 2, W // 2, **u8)
+        self.rgb_a, self.rgb_b = torch.empty(B, 3, H, W, **u8), torch.empty(B, 3, H, W, **u8)
+        self.s444, self.s_half = torch.empty(T, 2, H, W, **f32), torch.empty(T, 2, H // 2, W, **f32)
+        self.s_rgb, self.s_q = torch.empty(B, 3, H, W, **f32), torch.empty(B * n * 3 // 2, **f32)
+        self.stats = torch.zeros(B, 2, dtype=torch.int64, device=dev)
+        self.lut = torch.from_numpy(np.where(np.arange(256) < self.tht, 255, 0).astype(np.uint8)).to(dev)
+        self.w_shared = torch.tensor(self.wl, dtype=torch.int32, device=dev)
+        self.bank = FilterBank(B, H, W, dev, simd_width) if self.hue_adjust not in ("none", "") else None
+
+    def _to_yuv(self, rgb, y, c, count, dither, st):
+        dh, dv = self.dh, self.dv
+        _lib.check(self.lib.havc_zimg_rgb_to_yuv420p8(rgb.data_ptr(), y.data_ptr(), c.data_ptr(), self.s444.data_ptr(), self.s_half.data_ptr(),
+                                                      self.s_q.data_ptr() if dither else None, count, self.H, self.W, dv[0].data_ptr(),
+                                                      dv[1].data_ptr(), dv[2], dh[0].data_ptr(), dh[1].data_ptr(), dh[2], 0, 0, int(dither), st),
+                   "temporal.rgb_to_yuv420p8")
+
+    def _to_rgb(self, y, c, rgb, st):
+        uh, uv = self.uh, self.uv
+        _lib.check(self.lib.havc_zimg_yuv420p8_to_rgb(y.data_ptr(), c.data_ptr(), rgb.data_ptr(), self.s_half.data_ptr(), self.s_rgb.data_ptr(),
+                                                      self.B, self.H, self.W, uh[0].data_ptr(), uh[1].data_ptr(), uh[2], uv[0].data_ptr(),
+                                                      uv[1].data_ptr(), uv[2], 0, 0, 1, st), "temporal.yuv420p8_to_rgb")
+
+    def run(self, seq, out, active=None, weights=None, stream: int = 0):
+        """seq [B + 2 nh, 3, H, W] -> out [B, 3, H, W].  active: device u8 [B], 0 where the frame number is < 15 (tht > 0 only);
+        weights: device int32 [B, 2 nh + 1] (tht == 0 with scene changes; None = the plain table for every frame)."""
+        lib, B, H, W, nh, st = self.lib, self.B, self.H, self.W, self.nh, stream
+        T, K, n, nc = B + 2 * nh, 2 * nh + 1, H * W, 2 * (H // 2) * (W // 2)
+        assert tuple(seq.shape) == (T, 3, H, W) and tuple(out.shape) == (B, 3, H, W) and seq.is_contiguous() and out.is_contiguous()
+        self._to_yuv(seq, self.y_nd, self.c_nd, T, False, st)                              # vsfilters.py:56 / :275
+        cur = seq[nh:nh + B]
+        if self.tht == 0:
+            w = self.w_shared if weights is None else weights
+            _lib.check(lib.havc_average_frames_u8(self.c_nd.data_ptr(), nc, K, w.data_ptr(), int(weights is not None), 100,
+                                                  self.c_avg.data_ptr(), B, nc, st), "temporal.average_frames")
+            self._to_rgb(self.y_nd[nh:nh + B], self.c_avg, out, st)                        # vsfilters.py:60
+            return
+        assert active is not None
+        for k, d in enumerate(range(-nh, nh + 1)):
+            if d == 0:
+                self._to_yuv(cur, self.ys[k], self.cs[k], B, True, st)                     # vsfilters.py:222
+                continue
+            self._to_rgb(self.y_nd[nh:nh + B], self.c_nd[nh + d:nh + d + B], self.rgb_a, st)          # vs_get_clip_frame
+            _lib.check(lib.havc_gray_mask_stats(self.rgb_a.data_ptr(), B, H, W, self.tht, self.stats.data_ptr(), st), "temporal.stats")
+            _lib.check(lib.havc_restore_color(cur.data_ptr(), self.rgb_a.data_ptr(), self.rgb_b.data_ptr(), B, H, W, self.sat, self.tht,
+                                              self.weight, self.tht_scen, self.stats.data_ptr(), active.data_ptr(), self.lut.data_ptr(),
+                                              self.simd, st), "temporal.restore_color")
+            self._to_yuv(self.rgb_b, self.ys[k], self.cs[k], B, True, st)                  # vsfilters.py:230,239
+        _lib.check(lib.havc_average_frames_u8(self.cs.data_ptr(), B * nc, K, self.w_shared.data_ptr(), 0, 100, self.c_avg.data_ptr(), B, nc,
+                                              st), "temporal.average_frames")
+        dst = out if self.bank is None else self.rgb_a
+        self._to_rgb(self.ys[0], self.c_avg, dst, st)                                      # vsfilters.py:242-247: luma of the first clip
+        if self.bank is not None and not self.bank.adjust_hue_range(dst, out, self.hue_adjust, st):       # vsfilters.py:113
+            self.bank.blend(dst, dst, out, 0.0, st)
+
+
+class TemporalEngine:
+    """vs_chroma_stabilizer_ex on batches of planar RGB24 host frames at the clip's own size (the function is also used on its own,
+    outside HAVC_stabilizer): H2D of the batch with its halo -> TemporalStabilizer -> D2H, one CUDA graph."""
+
+    def __init__(self, width: int, height: int, batch: int = 8, device: str = "cuda:0", **stab):
+        self.dev = torch.device(device)
+        torch.cuda.set_device(self.dev)
+        self.temporal = TemporalStabilizer(batch, height, width, self.dev, **stab)
+        self.nh, self.out_B, self.B, self.H, self.W = self.temporal.nh, batch, batch + 2 * self.temporal.nh, height, width
+        u8 = dict(dtype=torch.uint8, device=self.dev)
+        self.d_in, self.d_out = torch.empty(self.B, 3, height, width, **u8), torch.empty(batch, 3, height, width, **u8)
+        self.active = torch.ones(batch, **u8)
+        self.tw = torch.zeros(batch, 2 * self.nh + 1, dtype=torch.int32, device=self.dev)
+        self.h_in = torch.empty(self.B, 3, height, width, dtype=torch.uint8).pin_memory()
+        self.h_out = torch.empty(batch, 3, height, width, dtype=torch.uint8).pin_memory()
+        self.h_active = torch.ones(batch, dtype=torch.uint8).pin_memory()
+        self.h_tw = torch.zeros(batch, 2 * self.nh + 1, dtype=torch.int32).pin_memory()
+        self.stream = torch.cuda.Stream(device=self.dev)
+        with torch.cuda.stream(self.stream):
+            self.d_in.zero_()
+            self._launch(self.stream.cuda_stream)
+        self.stream.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, stream=self.stream):
+            self._launch(torch.cuda.current_stream().cuda_stream)
+        self.stream.synchronize()
+
+    def _launch(self, st: int):
+        self.temporal.run(self.d_in, self.d_out, active=self.active, weights=self.tw if self.temporal.tht == 0 else None, stream=st)
+
+    def process_sequence(self, frames, n0, weights=None):
+        return StabilizerEngine.process_sequence(self, frames, n0, weights)
+
+
 class MergeEngine:
     """HAVC_merge on batches of planar RGB24 host frames: H2D -> FilterBank.combine / std.Merge -> D2H."""
 
@@ -533,11 +696,18 @@ class StabilizerEngine:
     Spline64 back to W x H + full-resolution luma transplant), one CUDA graph per batch."""
 
     def __init__(self, width: int, height: int, frame_size: int, stages: dict, batch: int = 8, device: str = "cuda:0",
-                 resize_kernel: str = "spline64"):
+                 resize_kernel: str = "spline64", stab: Optional[dict] = None):
         from .engine import _Tables
         self.lib = _lib.lib()
         self.dev = torch.device(device)
         torch.cuda.set_device(self.dev)
+        # `stab` (the temporal stage, N3): the device batch carries nh halo frames on either side, every per-frame stage runs on
+        # all of them (the temporal filter reads its neighbours AFTER dark / smooth / colormap, __init__.py:2843-2861), the way
+        # back only on the `out_B` frames in the middle
+        self.temporal = TemporalStabilizer(batch, frame_size, frame_size, self.dev, **stab) if stab else None
+        self.nh = self.temporal.nh if self.temporal else 0
+        self.out_B = batch
+        batch = batch + 2 * self.nh
         self.B, self.H, self.W, self.S = batch, height, width, frame_size
         B, H, W, S = batch, height, width, frame_size
         self.stages = stages
@@ -550,6 +720,11 @@ class StabilizerEngine:
         self.h_out = torch.empty(B, 3, H, W, dtype=torch.uint8).pin_memory()
         self.tmp_f = torch.empty(B, 3, H, S, **f32)
         self.small, self.small_out = torch.empty(B, 3, S, S, **u8), torch.empty(B, 3, S, S, **u8)
+        self.small_t = torch.empty(self.out_B, 3, S, S, **u8) if self.temporal else None
+        self.active = torch.ones(self.out_B, **u8)                                        # frame number >= 15 (vsfilters.py:337)
+        self.tw = torch.zeros(self.out_B, 2 * self.nh + 1, dtype=torch.int32, device=self.dev)   # per-frame weights (tht == 0)
+        self.h_active = torch.ones(self.out_B, dtype=torch.uint8).pin_memory()
+        self.h_tw = torch.zeros(self.out_B, 2 * self.nh + 1, dtype=torch.int32).pin_memory()
         self.x_scratch = torch.empty(B, S, S, 8, dtype=torch.float16, device=self.dev)    # pre_vertical's network-input by-product
         self.stream = torch.cuda.Stream(device=self.dev)
         with torch.cuda.stream(self.stream):
@@ -569,9 +744,13 @@ class StabilizerEngine:
         chk(lib.havc_pre_vertical(self.tmp_f.data_ptr(), self.small.data_ptr(), self.x_scratch.data_ptr(), B, H, S, tv.start.data_ptr(),
                                   tv.w.data_ptr(), tv.taps, 0, st), "squeeze.v")
         res = self.small_out if self.bank.stabilizer_stages(self.small, self.small_out, stream=st, **self.stages) else self.small
-        chk(lib.havc_resample_v(res.data_ptr(), self.tmp_f.data_ptr(), B * 3, S, H, S, uv.start.data_ptr(), uv.w.data_ptr(), uv.taps, st),
+        src, nb = self.d_in, B
+        if self.temporal is not None:
+            self.temporal.run(res, self.small_t, active=self.active, weights=self.tw if self.temporal.tht == 0 else None, stream=st)
+            res, nb, src = self.small_t, self.out_B, self.d_in[self.nh:self.nh + self.out_B]
+        chk(lib.havc_resample_v(res.data_ptr(), self.tmp_f.data_ptr(), nb * 3, S, H, S, uv.start.data_ptr(), uv.w.data_ptr(), uv.taps, st),
             "unsqueeze.v")
-        chk(lib.havc_post_horizontal(self.tmp_f.data_ptr(), self.d_in.data_ptr(), self.d_out.data_ptr(), B, S, H, W, uh.start.data_ptr(),
+        chk(lib.havc_post_horizontal(self.tmp_f.data_ptr(), src.data_ptr(), self.d_out.data_ptr(), nb, S, H, W, uh.start.data_ptr(),
                                      uh.wt.data_ptr(), uh.taps, 1, st), "unsqueeze.h")
 
     def process_batch(self, frames: np.ndarray, skip=None) -> np.ndarray:
@@ -585,3 +764,21 @@ class StabilizerEngine:
             self.h_out.copy_(self.d_out, non_blocking=True)
         self.stream.synchronize()
         return self.h_out[:n].numpy().copy()
+
+    def process_sequence(self, frames: np.ndarray, n0: int, weights: Optional[np.ndarray] = None) -> np.ndarray:
+        """The temporal form: frames uint8 [out_B + 2 nh, 3, H, W] = the batch that starts at clip frame n0 with its halo (clamped
+        to the clip's ends by the caller) -> uint8 [out_B, 3, H, W].  weights: int32 [out_B, 2 nh + 1] (scene-change folded
+        std.AverageFrames weights, tht == 0 only)."""
+        assert self.temporal is not None and frames.shape == (self.B, 3, self.H, self.W) and frames.dtype == np.uint8
+        self.h_in.copy_(torch.from_numpy(np.ascontiguousarray(frames)))
+        self.h_active.copy_(torch.from_numpy((np.arange(n0, n0 + self.out_B) >= 15).astype(np.uint8)))
+        self.h_tw.copy_(torch.from_numpy(np.ascontiguousarray(weights, dtype=np.int32)) if weights is not None
+                        else torch.tensor(self.temporal.wl, dtype=torch.int32).expand(self.out_B, -1))
+        with torch.cuda.stream(self.stream):
+            self.d_in.copy_(self.h_in, non_blocking=True)
+            self.active.copy_(self.h_active, non_blocking=True)
+            self.tw.copy_(self.h_tw, non_blocking=True)
+            self.graph.replay()
+            self.h_out.copy_(self.d_out, non_blocking=True)
+        self.stream.synchronize()
+        return self.h_out[:self.out_B].numpy().copy()

@@ -480,20 +480,107 @@ def _get_colormap(ColorMap: str = "red->brown", ColorTune: str = "light") -> str
     return cm
 
 
+class _TemporalClip:
+    """frame_fn of a temporally filtered clip (scope row N3): batches of B consecutive frames go to the engine together with
+    their `nh` halo frames on either side, clamped to the clip's ends the way std.AverageFrames clamps its requests
+    (min(max(n + d, 0), last)); source frames are cached so that the halo shared by neighbouring batches is fetched once."""
+
+    def __init__(self, clip, engine, scene_weights: bool):
+        self.clip, self.engine, self.B, self.nh = clip, engine, engine.out_B, engine.nh
+        self.scene_weights = scene_weights
+        self.src: "OrderedDict[int, object]" = OrderedDict()
+        self.cache: "OrderedDict[int, object]" = OrderedDict()
+        self.lock = threading.Lock()
+
+    def _src(self, i: int):
+        f = self.src.get(i)
+        if f is None:
+            f = self.src[i] = self.clip.get_frame(i)
+            while len(self.src) > 2 * (self.B + 2 * self.nh):
+                self.src.popitem(last=False)
+        return f
+
+    def __call__(self, n: int):
+        with self.lock:
+            if n in self.cache:
+                return self.cache[n]
+            last = self.clip.num_frames - 1
+            n0 = (n // self.B) * self.B
+            idx = [min(max(i, 0), last) for i in range(n0 - self.nh, n0 + self.B + self.nh)]
+            frames = [self._src(i) for i in idx]
+            seq = np.stack([np.stack([np.asarray(f[p]) for p in range(3)]) for f in frames])
+            weights = None
+            if self.scene_weights:                    # vs_clip_color_stabilizer: std.AverageFrames(scenechange=True), vsfilters.py:58
+                from .filters import scene_folded_weights
+                wl, K = self.engine.temporal.wl, 2 * self.nh + 1
+                weights = np.array([scene_folded_weights(wl, [int(frames[b + k].props.get("_SceneChangePrev", 0)) for k in range(K)],
+                                                         [int(frames[b + k].props.get("_SceneChangeNext", 0)) for k in range(K)])
+                                    for b in range(self.B)], np.int32)
+            out = self.engine.process_sequence(seq, n0, weights)
+            for b in range(min(self.B, last + 1 - n0)):
+                self.cache[n0 + b] = _output_frame(frames[self.nh + b], [out[b, p] for p in range(3)])
+            while len(self.cache) > 4 * self.B:
+                self.cache.popitem(last=False)
+            return self.cache[n]
+
+
+def _node_like(clip, fn):
+    return vs_shim.VideoNode(clip.num_frames, clip.width, clip.height, clip.format, fn, clip.fps_num, clip.fps_den) \
+        if vs is vs_shim else _wrap_real_vs(clip, fn)
+
+
+def _stab_params(nframes, mode, sat, tht, weight, tht_scen, hue_adjust) -> dict:
+    return dict(nframes=int(nframes), mode=mode, sat=float(sat), tht=int(tht), weight=float(weight), tht_scen=float(tht_scen),
+                hue_adjust=(hue_adjust or "none").lower())
+
+
+def vs_chroma_stabilizer_ex(clip, nframes: int = 5, mode: str = "A", sat: float = 1.0, tht: int = 0, weight: float = 0.5,
+                            tht_scen: float = 0.8, hue_adjust: str = 'none', algo: int = 0, device_index: int = 0):
+    """Drop-in for vsslib.vsfilters.vs_chroma_stabilizer_ex (vsslib/vsfilters.py:84-115) on RGB24 clips, algo = 0 (the value
+    HAVC_stabilizer passes; algo = 1, the ModifyFrame variant, raises): the temporal chroma stabiliser, scope row N3."""
+    if getattr(clip.format, "id", clip.format) != getattr(vs.RGB24, "id", vs.RGB24):
+        _raise("vs_chroma_stabilizer_ex: only RGB24 clips are handled")
+    if algo != 0:
+        _raise("vs_chroma_stabilizer_ex: algo=1 (_average_frames_ex) is not built; HAVC_stabilizer uses algo=0")
+    if not torch.cuda.is_available():
+        _raise("vs_chroma_stabilizer_ex: CUDA is not available")
+    from .filters import FilterError, TemporalEngine
+    try:
+        engine = TemporalEngine(clip.width, clip.height, batch=min(_BATCH, 8), device=f"cuda:{device_index}",
+                                **_stab_params(nframes, mode, sat, tht, weight, tht_scen, hue_adjust))
+    except (ValueError, FilterError) as e:
+        _raise(str(e))
+    return _node_like(clip, _TemporalClip(clip, engine, scene_weights=int(tht) == 0))
+
+
+def _reduce_flicker(clip, strength: int = 2, aggressive: int = 0):
+    """vs_reduce_flicker (vsslib/vsplugins.py:263-272): the external ReduceFlicker VapourSynth plugin (`core.rdfl`) that ends
+    HAVC_stabilizer's temporal stage.  It is not part of the reference tree (a binary the reference loads from its plugin
+    directory), so it is called when the host provides it and raises the reference's error otherwise."""
+    rdfl = getattr(vs.core, "rdfl", None)
+    try:
+        if rdfl is None:
+            raise RuntimeError("no plugin with the namespace 'rdfl' is loaded")
+        return rdfl.ReduceFlicker(clip=clip, strength=strength, aggressive=aggressive)
+    except Exception as error:
+        _raise("vs_retinex: plugin 'ReduceFlicker.dll' not properly loaded/installed -> " + str(error))     # vsplugins.py:270
+
+
 def HAVC_stabilizer(clip, dark: bool = False, dark_p: Sequence = (0.2, 0.8), smooth: bool = False,
                     smooth_p: Sequence = (0.3, 0.7, 0.9, 0.0, "none"), stab: bool = False,
                     stab_p: Sequence = (5, 'A', 1, 15, 0.2, 0.8), colormap: str = "none", render_factor: int = 24,
                     device_index: int = 0):
     """Drop-in for vsdeoldify.HAVC_stabilizer (vsdeoldify/__init__.py:2748-2873) for its per-frame stages: Spline64 squeeze
     to render_factor*16, vs_dark_tweak (`dark`), vs_chroma_bright_tweak (`smooth`), vs_colormap (`colormap`), then
-    _clip_chroma_resize back to the clip's size with the original luma.  The temporal chroma stabiliser (`stab=True`:
-    vs_chroma_stabilizer_ex + vs_reduce_flicker average neighbouring frames - row N3 of the scope table) raises."""
+    _clip_chroma_resize back to the clip's size with the original luma.  `stab=True` adds the temporal chroma stabiliser
+    (vs_chroma_stabilizer_ex, row N3 of the scope table) on the squeezed clip, followed - as in the reference - by the external
+    ReduceFlicker plugin (`core.rdfl`), which must be provided by the host (the reference's error is raised without it)."""
     if getattr(clip.format, "id", clip.format) != getattr(vs.RGB24, "id", vs.RGB24):
         _raise("HAVC_stabilizer: only RGB24 input is handled by the B200 build (convert_format_RGB24 is a 'next' row)")
     if render_factor != 0 and render_factor not in range(16, 65):
         _raise("HAVC_stabilizer: render_factor must be between: 16-64")                   # :2796
-    if stab:
-        _raise("HAVC_stabilizer: the temporal chroma stabilizer (stab=True) is not built (cross-frame filter, scope row N3)")
+    if stab and getattr(vs.core, "rdfl", None) is None:
+        _reduce_flicker(clip)                         # raises at graph-build time, like the reference without the plugin (:2861)
     if not torch.cuda.is_available():
         _raise("HAVC_stabilizer: CUDA is not available")
     if render_factor == 0:
@@ -503,13 +590,17 @@ def HAVC_stabilizer(clip, dark: bool = False, dark_p: Sequence = (0.2, 0.8), smo
     colormap_adjust = _get_colormap(cm) if cm not in ("none", "") else "none"             # :2827-2832
     stages = dict(dark=bool(dark), dark_p=list(dark_p), smooth=bool(smooth), smooth_p=list(smooth_p), colormap_adjust=colormap_adjust)
     from .filters import FilterError, StabilizerEngine
+    stab_kw = None
+    if stab:                                                                              # :2835-2845 (stab_algo = 0)
+        stab_kw = _stab_params(stab_p[0], stab_p[1], stab_p[2], stab_p[3], stab_p[4], stab_p[5], stab_p[6] if len(stab_p) > 6 else "none")
     try:
-        engine = StabilizerEngine(clip.width, clip.height, frame_size, stages, batch=_BATCH, device=f"cuda:{device_index}")
+        engine = StabilizerEngine(clip.width, clip.height, frame_size, stages, batch=min(_BATCH, 16) if stab else _BATCH,
+                                  device=f"cuda:{device_index}", stab=stab_kw)
     except (ValueError, FilterError) as e:
         _raise("HAVC_stabilizer: " + str(e))
-    fn = _ColorizedClip(clip, engine, False, _BATCH, run=engine.process_batch)
-    return vs_shim.VideoNode(clip.num_frames, clip.width, clip.height, clip.format, fn, clip.fps_num, clip.fps_den) \
-        if vs is vs_shim else _wrap_real_vs(clip, fn)
+    if stab:
+        return _reduce_flicker(_node_like(clip, _TemporalClip(clip, engine, scene_weights=stab_kw["tht"] == 0)))
+    return _node_like(clip, _ColorizedClip(clip, engine, False, _BATCH, run=engine.process_batch))
 
 
 class ModelImageRender:
@@ -684,7 +775,8 @@ def HAVC_main(clip, Preset: str = 'Medium', FrameInterp: int = 0, ColorModel: st
     parameters only feed the exemplar branch in the reference (they are not passed to HAVC_colorizer, :849-853) and are
     accepted and ignored here exactly when EnableDeepEx is False; EnableDeepEx / FrameInterp / the tiled presets / ColorTemp /
     BlackWhiteTune / DDColor models raise vs.Error.  Where the reference would also switch on the TEMPORAL chroma stabiliser
-    (two-model presets with ColorTune != 'none') the per-frame stages run and a warning says the temporal one is skipped."""
+    (two-model presets with ColorTune != 'none') it runs when the host provides the ReduceFlicker plugin its chain ends in
+    (`core.rdfl`); without the plugin the per-frame stages run and a warning says the temporal one is skipped."""
     rf = _get_render_factor(Preset)
     speed_id = _PRESETS.index(Preset.lower())
     if EnableDeepEx or FrameInterp != 0:
@@ -713,8 +805,14 @@ def HAVC_main(clip, Preset: str = 'Medium', FrameInterp: int = 0, ColorModel: st
                                   device_index=device_index, debug_level=debug_level)
     if speed_id > 4:                     # 'fast', 'faster', 'veryfast': only the colormap (:896-897)
         return HAVC_stabilizer(clip_colored, colormap=chroma_adjust, device_index=device_index)
-    if dd_method != 0 and tune != "none":    # :903-906 stab=stab_enabled
-        vs.core.log_message(vs.MESSAGE_TYPE_WARNING, "HAVC_main (B200 build): the temporal chroma stabilizer of this preset "
-                                                     "(HAVC_stabilizer stab=True) is not applied; its per-frame stages are")
+    stab_enabled = dd_method != 0 and tune != "none"       # :903-906 stab=stab_enabled
+    if stab_enabled and getattr(vs.core, "rdfl", None) is None:
+        # the preset's temporal stage ends in the external ReduceFlicker plugin (vsplugins.py:263-272); without it the reference
+        # raises - here the per-frame stages still run and the log says what was left out
+        vs.core.log_message(vs.MESSAGE_TYPE_WARNING, "HAVC_main (B200 build): plugin 'ReduceFlicker' (core.rdfl) is not loaded; the "
+                                                     "temporal chroma stabilizer of this preset (HAVC_stabilizer stab=True) is not "
+                                                     "applied, its per-frame stages are")
+        stab_enabled = False
     return HAVC_stabilizer(clip_colored, dark=True, dark_p=[0.2, 0.8], colormap=chroma_adjust, smooth=True,
-                           smooth_p=[0.3, 0.7, 0.9, 0.0, "none"], stab=False, device_index=device_index)
+                           smooth_p=[0.3, 0.7, 0.9, 0.0, "none"], stab=stab_enabled, stab_p=[5, 'A', 1, 15, 0.2, 0.8],
+                           device_index=device_index)
