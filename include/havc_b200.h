@@ -161,6 +161,25 @@ int havc_softmax_rows(const void *in, int in_dtype, void *out, long long rows, i
 
 /* ---- frame pre / post pixel passes (planar u8 RGB frames [B][3][H][W]) ----------------------- */
 
+/* Phase-periodic form of the two horizontal passes (integer ratios: 1920 <-> 384 / 480, 3840 <-> 640): every interior column of a
+ * phase has the same weights and a window that moves by a fixed step, so the kernels keep the weights in their parameter bank
+ * and a run of input pixels in registers (no table look-ups, no shared-memory load per FMA).  The host proves the periodicity
+ * of the table bit for bit (vsdeoldify_b200/resample.py:periodic_plan) and passes the interior range; border columns, whose
+ * windows are folded at the image edge, take the table path inside the same kernel.  Results are bit-identical to
+ * havc_resample_h / havc_post_horizontal (same fmaf chain per output). */
+typedef struct havc_periodic_plan {
+    int ratio;   /* Win / Wout (squeeze) or W / S (way back): 4, 5 or 6 */
+    int taps;    /* padded taps per output: squeeze = (window start mod 4) leading zeros + table taps; back = table taps + spread of the phase starts */
+    int offset;  /* squeeze: aligned window start of column block 0 (input pixels, multiple of 4, may be negative); back: -min phase start */
+    int lo, hi;  /* interior range: squeeze in blocks of 8 output columns, back in units of 4 input positions */
+    float w[72]; /* squeeze: w[t]; back: w[phase * taps + t] */
+} havc_periodic_plan;
+int havc_resample_h_periodic(const uint8_t *in, float *out, long long rows, int Win, int Wout, const int *start,
+                             const float *weights, int taps, const havc_periodic_plan *plan, void *stream);
+int havc_post_horizontal_periodic(const float *in, const uint8_t *orig, uint8_t *out, int B, int S, int H, int W,
+                                  const int *start, const float *weights, int taps, int transplant,
+                                  const havc_periodic_plan *plan, void *stream);
+
 /* Table-driven separable resampling, horizontal pass: out[row][o] = sum_t weights_t[t][o]*in[row][start[o]+t]
  * (horizontal passes take the weight table TRANSPOSED, [taps][Wout], so a warp reads it coalesced; vertical
  * passes take it as [Hout][taps]).  With Spline64 tables this is zimg's resize.Spline64 of

@@ -283,3 +283,40 @@ def test_sharded_renderer_orders_frames_and_props_with_cpu_stand_in_engines():
     with pytest.raises(KeyError):
         r(1)
     r.close()
+
+
+def test_periodic_resampling_plans_are_bit_identical_to_the_tables():
+    """resample.periodic_plan_down / _up (the phase-periodic horizontal kernels' host side): on the interior range the plan's
+    weights and offsets reproduce the table formula out[o] = sum_t w[o, t] * in[start[o] + t] term by term (zero taps are
+    exact no-ops of the fmaf chain), for the integer ratios of the BASELINE configs; other ratios have no plan."""
+    import numpy as np
+    from vsdeoldify_b200 import resample
+    rng = np.random.default_rng(0)
+
+    def fma_chain(ws, xs):
+        acc = np.float32(0)
+        for wv, xv in zip(ws, xs):
+            acc = np.float32(np.float64(wv) * np.float64(xv) + np.float64(acc))      # an fp32 product is exact in fp64: this is fmaf
+        return acc
+    for src, dst in [(1920, 384), (1920, 480), (3840, 640)]:
+        st, w = resample.build_tables(src, dst, "spline64")
+        p = resample.periodic_plan_down(st, w, src, dst)
+        assert p is not None and p["hi"] - p["lo"] >= dst // 8 - 4
+        x = rng.uniform(0, 255, src).astype(np.float32)
+        R, kTP = p["ratio"], resample.PERIODIC_DOWN_TAPS[p["ratio"]]
+        for o in list(range(8 * p["lo"], 8 * p["lo"] + 16)) + list(range(8 * p["hi"] - 16, 8 * p["hi"])):
+            a0 = p["offset"] + R * 8 * (o // 8) + R * (o % 8)
+            xs = [x[a0 + t] if 0 <= a0 + t < src else np.float32(0) for t in range(kTP)]
+            assert fma_chain(p["w"][:kTP], xs).view(np.int32) == fma_chain(w[o], x[st[o]:st[o] + w.shape[1]]).view(np.int32), (src, dst, o)
+        st, w = resample.build_tables(dst, src, "spline64")
+        p = resample.periodic_plan_up(st, w, dst, src)
+        assert p is not None and p["taps"] in resample.PERIODIC_UP_TAPS and p["hi"] - p["lo"] >= dst // 4 - 4
+        x = rng.uniform(-5, 260, dst).astype(np.float32)
+        for o in list(range(4 * R * p["lo"], 4 * R * p["lo"] + 3 * R)) + list(range(4 * R * p["hi"] - 3 * R, 4 * R * p["hi"])):
+            i, ph = divmod(o, R)
+            xs = [x[i - p["offset"] + t] if 0 <= i - p["offset"] + t < dst else np.float32(0) for t in range(p["taps"])]
+            got = fma_chain(p["w"][ph * p["taps"]:(ph + 1) * p["taps"]], xs)
+            assert got.view(np.int32) == fma_chain(w[o], x[st[o]:st[o] + w.shape[1]]).view(np.int32), (dst, src, o)
+    for src, dst in [(1920, 256), (1280, 384), (1000, 384)]:
+        assert resample.periodic_plan_down(*resample.build_tables(src, dst, "spline64"), src, dst) is None
+        assert resample.periodic_plan_up(*resample.build_tables(dst, src, "spline64"), dst, src) is None

@@ -66,8 +66,10 @@ def timed(label, fn):
 st = eng.compute.cuda_stream
 B, S, W, H = eng.B, eng.S, eng.W, eng.H
 td, tv, uh, uv = eng.t_down_h, eng.t_down_v, eng.t_up_h, eng.t_up_v
-timed("pre.h", lambda: lib.havc_resample_h(eng.d_in[0].data_ptr(), eng.tmp_down.data_ptr(), B * 3 * H, W, S, td.start.data_ptr(), td.wt.data_ptr(), td.taps, st))
+timed("pre.h", lambda: td.resample_h(lib, eng.d_in[0].data_ptr(), eng.tmp_down.data_ptr(), B * 3 * H, st))
+timed("pre.h (table kernel)", lambda: lib.havc_resample_h(eng.d_in[0].data_ptr(), eng.tmp_down.data_ptr(), B * 3 * H, W, S, td.start.data_ptr(), td.wt.data_ptr(), td.taps, st))
 timed("pre.v", lambda: lib.havc_pre_vertical(eng.tmp_down.data_ptr(), eng.rgb_small.data_ptr(), eng.prog.x.data_ptr(), B, H, S, tv.start.data_ptr(), tv.w.data_ptr(), tv.taps, eng.hd, st))
 timed("head", lambda: lib.havc_head(eng.prog.logits.data_ptr(), 0, None, eng.prog.b11.data_ptr(), eng.rgb_small.data_ptr(), eng.colored.data_ptr(), None, eng.skip_slots[0].data_ptr(), B, S, eng.hd, 1, st))
 timed("post.v", lambda: lib.havc_resample_v(eng.colored.data_ptr(), eng.tmp_up.data_ptr(), B * 3, S, H, S, uv.start.data_ptr(), uv.w.data_ptr(), uv.taps, st))
-timed("post.h", lambda: lib.havc_post_horizontal(eng.tmp_up.data_ptr(), eng.d_in[0].data_ptr(), eng.d_out[0].data_ptr(), B, S, H, W, uh.start.data_ptr(), uh.wt.data_ptr(), uh.taps, 1, st))
+timed("post.h", lambda: uh.post_horizontal(lib, eng.tmp_up.data_ptr(), eng.d_in[0].data_ptr(), eng.d_out[0].data_ptr(), B, H, 1, st))
+timed("post.h (table kernel)", lambda: lib.havc_post_horizontal(eng.tmp_up.data_ptr(), eng.d_in[0].data_ptr(), eng.d_out[0].data_ptr(), B, S, H, W, uh.start.data_ptr(), uh.wt.data_ptr(), uh.taps, 1, st))

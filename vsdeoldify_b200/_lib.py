@@ -77,6 +77,11 @@ class HueRanges(C.Structure):
     _fields_ = [("n", C.c_int32), ("lo_deg", C.c_double * 8), ("hi_deg", C.c_double * 8)]
 
 
+class PeriodicPlan(C.Structure):
+    """havc_periodic_plan (include/havc_b200.h)."""
+    _fields_ = [("ratio", C.c_int32), ("taps", C.c_int32), ("offset", C.c_int32), ("lo", C.c_int32), ("hi", C.c_int32), ("w", C.c_float * 72)]
+
+
 # every symbol include/havc_b200.h declares: name -> (restype, argtypes)
 _SIGNATURES = {
     "havc_last_error": (C.c_char_p, []),
@@ -92,6 +97,10 @@ _SIGNATURES = {
     "havc_blur2x2": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p]),
     "havc_softmax_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.c_void_p]),
+    "havc_resample_h_periodic": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                           C.POINTER(PeriodicPlan), C.c_void_p]),
+    "havc_post_horizontal_periodic": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                                C.c_void_p, C.c_int, C.c_int, C.POINTER(PeriodicPlan), C.c_void_p]),
     "havc_resample_h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                   C.c_int, C.c_void_p]),
     "havc_pre_vertical": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,

@@ -510,6 +510,225 @@ __global__ void blend_u8_kernel(const uint4 *a, const uint4 *b, uint4 *out, long
     }
 }
 
+// ---- phase-periodic horizontal passes ------------------------------------------------------------------------------------
+// When the resampling ratio is an integer (1920 <-> 384, 1920 <-> 480, 3840 <-> 640) every interior output column of a phase has
+// the SAME weights and its window moves by a fixed step: the table lookups disappear (the weights sit in the kernel's parameter
+// bank and feed the FMAs as constant operands) and one thread keeps a run of input pixels in registers for several outputs, so
+// the one-shared-memory-load-per-FMA bound of the table kernels (profiles/r01_ncu_post_horizontal_b32.txt) turns into an
+// FMA / ALU bound.  The host checks the periodicity of the table bit for bit (resample.periodic_plan) and passes the interior
+// range; the few border columns, whose windows are folded at the image edge, go through the table path inside the same
+// kernel.  Every output is the same fmaf chain over the taps in the same order as the table kernels: bit-identical results.
+struct PeriodicW { float w[72]; };
+
+// Down-scaling (the squeeze): u8 rows -> float rows, ratio kRt = Win / Wout.  A thread owns 8 adjacent output columns of one
+// row: its inputs are kN aligned 16-byte shared-memory loads, its 8 x kTP FMAs take their weights from the parameter bank
+// (pw.w = the kT taps preceded by `sh` zeros, sh = window start mod 4, so that the run starts on a 16-byte boundary).
+// Small blocks (2 rows each), many per SM: the phases of one block (stage, compute, border) overlap with the other blocks'.
+template <int kTP, int kRt>
+__global__ void __launch_bounds__(160)
+resample_h_periodic_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, long long rows, int Win, int Wout,
+                           const int *__restrict__ start, const float *__restrict__ wts, int T,
+                           const __grid_constant__ PeriodicW pw, int a_off, int lo8, int hi8) {
+    extern __shared__ float srow[];          // [kRows][Win + 64] (the 64 floats behind each row stay zero), then the border table
+    constexpr int kRows = 2;
+    constexpr int kSpan = kRt * 7 + kTP;     // input floats behind one thread's 8 outputs
+    constexpr int kN = (kSpan + 3) / 4;
+    const int rowlen = Win + 64;
+    const int w4 = Win / 4;
+    const int words = kRows * w4;
+    const int nblk = hi8 - lo8;                               // interior column blocks (8 columns each)
+    const int nborder = 8 * lo8 + (Wout - 8 * hi8);           // border columns per row
+    float *bw = srow + kRows * rowlen;                        // [nborder][T] weights of the border columns
+    int *bs = reinterpret_cast<int *>(bw + nborder * T);      // [nborder] window starts
+    for (int i = threadIdx.x; i < kRows * 64; i += blockDim.x) srow[(i / 64) * rowlen + Win + (i % 64)] = 0.f;
+    for (int i = threadIdx.x; i < nborder * T; i += blockDim.x) {
+        const int k = i / T, t = i - k * T;
+        const int ox = k < 8 * lo8 ? k : 8 * hi8 + (k - 8 * lo8);
+        bw[i] = __ldg(wts + (long long)t * Wout + ox);
+        if (t == 0) bs[k] = __ldg(start + ox);
+    }
+    const int ur = threadIdx.x / nblk, ucb = lo8 + threadIdx.x % nblk;
+    const bool unit = threadIdx.x < kRows * nblk;
+    const int bit = (int)blockDim.x - 1 - (int)threadIdx.x;   // border item of this thread (the last warp's lanes take them)
+    const long long groups = (rows + kRows - 1) / kRows;
+    for (long long g = blockIdx.x; g < groups; g += gridDim.x) {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(in + g * kRows * (long long)Win);
+        const long long lim = (rows - g * kRows) * w4;      // words that exist (the last group may be short)
+        __syncthreads();                                     // the previous group's readers are done
+        for (int i = threadIdx.x; i < words; i += blockDim.x) {
+            const uint32_t v = i < lim ? __ldg(src + i) : 0u;
+            const int r = i / w4, c = i - r * w4;
+            *reinterpret_cast<float4 *>(srow + r * rowlen + 4 * c) =
+                make_float4((float)(v & 0xff), (float)((v >> 8) & 0xff), (float)((v >> 16) & 0xff), (float)(v >> 24));
+        }
+        __syncthreads();
+        if (unit) {
+            const float4 *sp = reinterpret_cast<const float4 *>(srow + ur * rowlen + a_off + kRt * 8 * ucb);
+            float x[4 * kN];
+#pragma unroll
+            for (int k = 0; k < kN; ++k) {
+                const float4 v = sp[k];
+                x[4 * k] = v.x; x[4 * k + 1] = v.y; x[4 * k + 2] = v.z; x[4 * k + 3] = v.w;
+            }
+            float acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+            for (int t = 0; t < kTP; ++t)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = fmaf(pw.w[t], x[kRt * j + t], acc[j]);
+            const long long row = g * kRows + ur;
+            if (row < rows) {
+                float4 *op = reinterpret_cast<float4 *>(out + row * Wout + 8 * ucb);
+                op[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                op[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            }
+        }
+        for (int it = bit; it < kRows * nborder; it += blockDim.x) {      // border columns: the table path (table in shared memory)
+            const int r = it / nborder, k = it - r * nborder;
+            const int ox = k < 8 * lo8 ? k : 8 * hi8 + (k - 8 * lo8);
+            const long long row = g * kRows + r;
+            if (row < rows) {
+                const float *sp = srow + r * rowlen + bs[k];
+                const float *wk = bw + k * T;
+                float acc = 0.f;
+                for (int t = 0; t < T; ++t) acc = fmaf(wk[t], sp[t], acc);
+                out[row * Wout + ox] = acc;
+            }
+        }
+    }
+}
+
+// Up-scaling (the way back) fused with the full-resolution luma transplant, ratio kRt = W / S.  A thread owns 4 input
+// positions = 4 kRt output pixels of one row: 3 + kTP input floats per channel in registers (kTP = taps + the spread of the
+// per-phase window starts; pw.w[p * kTP + t] = the weights of phase p, zero-padded to the common window), the original pixels
+// read as 32-bit words, the result staged per warp in shared memory and written back as full 128-byte lines.  One row per block
+// and iteration, several blocks per SM.
+template <int kRt, int kTP>
+__global__ void __launch_bounds__(160)
+post_horizontal_periodic_kernel(const float *__restrict__ in, const uint8_t *__restrict__ orig, uint8_t *__restrict__ out, int B, int S,
+                                int H, int W, const int *__restrict__ start, const float *__restrict__ wts, int T, int transplant,
+                                const __grid_constant__ PeriodicW pw, int base_off, int ulo, int uhi) {
+    extern __shared__ float sm_f[];
+    constexpr int kX = 3 + kTP;                 // inputs behind one thread's 4 positions
+    constexpr int kN = (kX + 3) / 4;
+    constexpr int kWords = kRt;                 // 4 kRt output bytes per plane = kRt words per thread
+    const int spitch = S + 16;                  // row pitch in floats (data at +base_off, zeros around it)
+    const int upr = S / 4;                      // units per row
+    const int nbu = ulo + (upr - uhi);          // border units per row
+    const int nbpx = nbu * 4 * kRt;             // border pixels per row
+    float *srows = sm_f;                                                        // [3][spitch]
+    uint32_t *stage = reinterpret_cast<uint32_t *>(sm_f + 3 * spitch);          // [warps][3][32 kRt]
+    float *bw = reinterpret_cast<float *>(stage + (blockDim.x >> 5) * 3 * 32 * kWords);   // [nbpx][T]
+    int *bs = reinterpret_cast<int *>(bw + nbpx * T);                           // [nbpx] window starts
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int u = threadIdx.x;
+    const long long ps = (long long)H * W;
+    const long long nrows = (long long)B * H;
+    uint32_t *stg = stage + warp * (3 * 32 * kWords);
+    for (int i = threadIdx.x; i < 3 * spitch; i += blockDim.x) srows[i] = 0.f;
+    for (int i = threadIdx.x; i < nbpx * T; i += blockDim.x) {
+        const int k = i / T, t = i - k * T;
+        const int bu = k / (4 * kRt), uu = bu < ulo ? bu : uhi + (bu - ulo);
+        const int ox = uu * 4 * kRt + (k - bu * 4 * kRt);
+        bw[i] = __ldg(wts + (long long)t * W + ox);
+        if (t == 0) bs[k] = __ldg(start + ox);
+    }
+    const int bit = (int)blockDim.x - 1 - (int)threadIdx.x;
+    for (long long r = blockIdx.x; r < nrows; r += gridDim.x) {
+        const int oy = (int)(r % H), b = (int)(r / H);
+        __syncthreads();
+        if ((base_off & 3) == 0) {
+            for (int i = threadIdx.x; i < 3 * upr; i += blockDim.x) {
+                const int c = i / upr, x4 = i - c * upr;
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(in + (((long long)b * 3 + c) * H + oy) * S) + x4);
+                *reinterpret_cast<float4 *>(srows + c * spitch + base_off + 4 * x4) = v;
+            }
+        } else {
+            for (int i = threadIdx.x; i < 3 * S; i += blockDim.x) {
+                const int c = i / S, x = i - c * S;
+                srows[c * spitch + base_off + x] = __ldg(in + (((long long)b * 3 + c) * H + oy) * S + x);
+            }
+        }
+        __syncthreads();
+        const long long base = ((long long)b * 3 * H + oy) * W;
+        if (u >= ulo && u < uhi) {
+            uint32_t ow[3][kWords];
+#pragma unroll
+            for (int pl = 0; pl < 3; ++pl)
+#pragma unroll
+                for (int k = 0; k < kWords; ++k)
+                    ow[pl][k] = transplant ? __ldg(reinterpret_cast<const uint32_t *>(orig + base + pl * ps) + u * kWords + k) : 0u;
+            float x[3][4 * kN];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float4 *sp = reinterpret_cast<const float4 *>(srows + c * spitch + 4 * u);
+#pragma unroll
+                for (int k = 0; k < kN; ++k) {
+                    const float4 v = sp[k];
+                    x[c][4 * k] = v.x; x[c][4 * k + 1] = v.y; x[c][4 * k + 2] = v.z; x[c][4 * k + 3] = v.w;
+                }
+            }
+            uint32_t res[3][kWords];
+#pragma unroll
+            for (int pl = 0; pl < 3; ++pl)
+#pragma unroll
+                for (int k = 0; k < kWords; ++k) res[pl][k] = 0u;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int p = 0; p < kRt; ++p) {
+                    const int j = q * kRt + p;                    // pixel within the unit
+                    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+                    for (int t = 0; t < kTP; ++t) {
+                        const float wt = pw.w[p * kTP + t];
+                        a0 = fmaf(wt, x[0][q + t], a0);
+                        a1 = fmaf(wt, x[1][q + t], a1);
+                        a2 = fmaf(wt, x[2][q + t], a2);
+                    }
+                    const int q0 = round_u8(a0), q1 = round_u8(a1), q2 = round_u8(a2);
+                    int rr = q0, gg = q1, bb = q2;
+                    const int sh = 8 * (j & 3), wd = j >> 2;
+                    if (transplant)
+                        luma_transplant((ow[0][wd] >> sh) & 0xff, (ow[1][wd] >> sh) & 0xff, (ow[2][wd] >> sh) & 0xff, q0, q1, q2, rr, gg, bb);
+                    res[0][wd] |= (uint32_t)rr << sh; res[1][wd] |= (uint32_t)gg << sh; res[2][wd] |= (uint32_t)bb << sh;
+                }
+#pragma unroll
+            for (int pl = 0; pl < 3; ++pl)
+#pragma unroll
+                for (int k = 0; k < kWords; ++k) stg[pl * 32 * kWords + lane * kWords + k] = res[pl][k];
+        }
+        __syncwarp();
+        {   // write-back of the warp's interior units as whole words, consecutive lanes -> consecutive words
+            const int ufirst = max(ulo, warp * 32), ulast = min(uhi, min(upr, warp * 32 + 32));
+            const int w0 = (ufirst - warp * 32) * kWords, w1 = (ulast - warp * 32) * kWords;
+            for (int pl = 0; pl < 3; ++pl)
+                for (int k = w0 + lane; k < w1; k += 32)
+                    reinterpret_cast<uint32_t *>(out + base + pl * ps)[warp * 32 * kWords + k] = stg[pl * 32 * kWords + k];
+        }
+        // border pixels (windows folded at the image edge): the table path with the table in shared memory, one pixel per thread
+        for (int it = bit; it < nbpx; it += blockDim.x) {
+            const int bu = it / (4 * kRt), uu = bu < ulo ? bu : uhi + (bu - ulo);
+            const int ox = uu * 4 * kRt + (it - bu * 4 * kRt);
+            const float *sp = srows + base_off + bs[it];
+            const float *wk = bw + it * T;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+            for (int t = 0; t < T; ++t) {
+                a0 = fmaf(wk[t], sp[t], a0);
+                a1 = fmaf(wk[t], sp[spitch + t], a1);
+                a2 = fmaf(wk[t], sp[2 * spitch + t], a2);
+            }
+            const int q0 = round_u8(a0), q1 = round_u8(a1), q2 = round_u8(a2);
+            int cr = q0, cg = q1, cb = q2;
+            if (transplant) luma_transplant(__ldg(orig + base + ox), __ldg(orig + base + ps + ox), __ldg(orig + base + 2 * ps + ox), q0, q1, q2, cr, cg, cb);
+            out[base + ox] = (uint8_t)cr;
+            out[base + ps + ox] = (uint8_t)cg;
+            out[base + 2 * ps + ox] = (uint8_t)cb;
+        }
+    }
+}
+
 }  // namespace havc
 
 using namespace havc;
@@ -621,6 +840,90 @@ extern "C" int havc_gray_normalize(const uint8_t *rgb, void *x, int B, long long
     HAVC_CHECK_ARG(rgb && x && B > 0 && n_pixels > 0 && (dtype == HAVC_F16 || dtype == HAVC_BF16), "havc_gray_normalize: bad arguments");
     gray_normalize_kernel<<<grid1d((long long)B * n_pixels, 256), 256, 0, (cudaStream_t)stream>>>(rgb, x, B, n_pixels, dtype);
     HAVC_LAUNCHED();
+    return HAVC_OK;
+}
+
+template <int kTP, int kRt>
+static int launch_h_periodic(const uint8_t *in, float *out, long long rows, int Win, int Wout, const int *start, const float *weights,
+                             int taps, const havc_periodic_plan *pl, cudaStream_t st) {
+    const int nblk = pl->hi - pl->lo, nborder = 8 * pl->lo + (Wout - 8 * pl->hi);
+    const int block = ((2 * nblk + 31) / 32) * 32;
+    const size_t sm = (size_t)2 * (Win + 64) * sizeof(float) + (size_t)nborder * (taps + 1) * sizeof(float);
+    HAVC_CHECK_ARG(block <= 160 && sm <= 96 * 1024, "havc_resample_h_periodic: row too wide for the periodic kernel");
+    static std::atomic<unsigned long long> attr{0ull};
+    unsigned long long bit;
+    if (device_pending(attr, &bit)) {
+        HAVC_CHECK_CUDA(cudaFuncSetAttribute(resample_h_periodic_kernel<kTP, kRt>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        device_done(attr, bit);
+    }
+    PeriodicW pw;
+    memcpy(pw.w, pl->w, sizeof(pw.w));
+    const long long groups = (rows + 1) / 2;
+    const long long cap = (long long)num_sms() * 8;
+    const int grid = (int)(groups < cap ? groups : cap);
+    resample_h_periodic_kernel<kTP, kRt><<<grid, block, sm, st>>>(in, out, rows, Win, Wout, start, weights, taps, pw, pl->offset, pl->lo, pl->hi);
+    HAVC_LAUNCHED();
+    return HAVC_OK;
+}
+
+/* havc_resample_h for an integer ratio Win / Wout whose interior columns share one weight vector (resample.periodic_plan). */
+extern "C" int havc_resample_h_periodic(const uint8_t *in, float *out, long long rows, int Win, int Wout, const int *start,
+                                        const float *weights, int taps, const havc_periodic_plan *plan, void *stream) {
+    HAVC_CHECK_ARG(in && out && start && weights && plan && taps > 0 && rows > 0, "havc_resample_h_periodic: bad arguments");
+    HAVC_CHECK_ARG(Win == plan->ratio * Wout && (Win & 3) == 0 && (Wout & 7) == 0 && (reinterpret_cast<uintptr_t>(in) & 3) == 0 &&
+                       (reinterpret_cast<uintptr_t>(out) & 15) == 0 && plan->lo >= 0 && plan->lo < plan->hi && 8 * plan->hi <= Wout &&
+                       (plan->offset & 3) == 0 && plan->offset + plan->ratio * 8 * plan->lo >= 0 && taps <= 48,
+                   "havc_resample_h_periodic: plan does not fit the call");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int r = plan->ratio, tp = plan->taps;
+    if (r == 5 && tp <= 43) return launch_h_periodic<43, 5>(in, out, rows, Win, Wout, start, weights, taps, plan, st);
+    if (r == 4 && tp <= 35) return launch_h_periodic<35, 4>(in, out, rows, Win, Wout, start, weights, taps, plan, st);
+    if (r == 6 && tp <= 51) return launch_h_periodic<51, 6>(in, out, rows, Win, Wout, start, weights, taps, plan, st);
+    HAVC_CHECK_ARG(false, "havc_resample_h_periodic: ratio / taps not instantiated (4: <= 35, 5: <= 43, 6: <= 51)");
+    return HAVC_OK;
+}
+
+template <int kRt, int kTP>
+static int launch_post_periodic(const float *in, const uint8_t *orig, uint8_t *out, int B, int S, int H, int W, const int *start,
+                                const float *weights, int taps, int transplant, const havc_periodic_plan *pl, cudaStream_t st) {
+    const int upr = S / 4, warps = (upr + 31) / 32;
+    const int nbpx = (pl->lo + (upr - pl->hi)) * 4 * kRt;
+    const size_t sm = (size_t)3 * (S + 16) * sizeof(float) + (size_t)warps * 3 * 32 * kRt * sizeof(uint32_t) + (size_t)nbpx * (taps + 1) * sizeof(float);
+    HAVC_CHECK_ARG(warps <= 5 && sm <= 96 * 1024, "havc_post_horizontal_periodic: row too wide for the periodic kernel");
+    static std::atomic<unsigned long long> attr{0ull};
+    unsigned long long bit;
+    if (device_pending(attr, &bit)) {
+        HAVC_CHECK_CUDA(cudaFuncSetAttribute(post_horizontal_periodic_kernel<kRt, kTP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        device_done(attr, bit);
+    }
+    PeriodicW pw;
+    memcpy(pw.w, pl->w, sizeof(pw.w));
+    const long long nrows = (long long)B * H;
+    const long long cap = (long long)num_sms() * 12;
+    const int grid = (int)(nrows < cap ? nrows : cap);
+    post_horizontal_periodic_kernel<kRt, kTP><<<grid, warps * 32, sm, st>>>(in, orig, out, B, S, H, W, start, weights, taps, transplant, pw,
+                                                                           pl->offset, pl->lo, pl->hi);
+    HAVC_LAUNCHED();
+    return HAVC_OK;
+}
+
+/* havc_post_horizontal for an integer ratio W / S whose interior columns are phase-periodic (resample.periodic_plan). */
+extern "C" int havc_post_horizontal_periodic(const float *in, const uint8_t *orig, uint8_t *out, int B, int S, int H, int W,
+                                             const int *start, const float *weights, int taps, int transplant,
+                                             const havc_periodic_plan *plan, void *stream) {
+    HAVC_CHECK_ARG(in && out && start && weights && plan && taps > 0 && (!transplant || orig), "havc_post_horizontal_periodic: bad arguments");
+    HAVC_CHECK_ARG(W == plan->ratio * S && (S & 3) == 0 && ((reinterpret_cast<uintptr_t>(orig) | reinterpret_cast<uintptr_t>(out)) & 3) == 0 &&
+                       (reinterpret_cast<uintptr_t>(in) & 15) == 0 && plan->lo >= 0 && plan->lo < plan->hi && plan->hi <= S / 4 &&
+                       plan->offset >= 0 && plan->offset <= 8 && plan->ratio * plan->taps <= 72,
+                   "havc_post_horizontal_periodic: plan does not fit the call");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int r = plan->ratio, tp = plan->taps;
+#define HAVC_POST_P(R, TP) \
+    if (r == R && tp == TP) return launch_post_periodic<R, TP>(in, orig, out, B, S, H, W, start, weights, taps, transplant, plan, st);
+    HAVC_POST_P(5, 8) HAVC_POST_P(5, 9) HAVC_POST_P(5, 10) HAVC_POST_P(4, 8) HAVC_POST_P(4, 9) HAVC_POST_P(4, 10)
+    HAVC_POST_P(6, 8) HAVC_POST_P(6, 9) HAVC_POST_P(6, 10)
+#undef HAVC_POST_P
+    HAVC_CHECK_ARG(false, "havc_post_horizontal_periodic: ratio / taps not instantiated (ratio 4-6, taps 8-10)");
     return HAVC_OK;
 }
 

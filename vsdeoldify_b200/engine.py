@@ -10,11 +10,16 @@ from __future__ import annotations
 
 from typing import Dict, List, Optional
 
+import os
+
 import numpy as np
 import torch
 
 from . import _lib, ops, resample
 from .unet import UnetProgram
+
+
+_NO_PERIODIC = bool(os.environ.get("HAVC_B200_NO_PERIODIC"))      # A/B switch for profiling: table-driven horizontal passes
 
 
 class _Tables:
@@ -24,6 +29,36 @@ class _Tables:
         self.start = torch.from_numpy(start).to(dev)
         self.w = torch.from_numpy(w).contiguous().to(dev)                       # [out][taps]  (vertical passes)
         self.wt = torch.from_numpy(np.ascontiguousarray(w.T)).to(dev)           # [taps][out]  (horizontal passes)
+        # integer ratios: the phase-periodic horizontal kernels (csrc/pixel.cu); None = the table kernels
+        self.src, self.dst = src, dst
+        plan = None if _NO_PERIODIC else (resample.periodic_plan_down(start, w, src, dst) if src > dst else
+                                          resample.periodic_plan_up(start, w, src, dst))
+        self.plan = None
+        if plan is not None:
+            self.plan = _lib.PeriodicPlan(plan["ratio"], plan["taps"], plan["offset"], plan["lo"], plan["hi"])
+            for i, v in enumerate(plan["w"]):
+                self.plan.w[i] = float(v)
+
+    def resample_h(self, lib, src_ptr: int, dst_ptr: int, rows: int, stream: int, what: str = "resample.h"):
+        """Horizontal squeeze pass u8 [rows][src] -> float [rows][dst]."""
+        import ctypes as C
+        if self.plan is not None and self.src > self.dst and rows >= 8 and src_ptr % 4 == 0 and dst_ptr % 16 == 0:
+            _lib.check(lib.havc_resample_h_periodic(src_ptr, dst_ptr, rows, self.src, self.dst, self.start.data_ptr(), self.wt.data_ptr(),
+                                                    self.taps, C.byref(self.plan), stream), what)
+        else:
+            _lib.check(lib.havc_resample_h(src_ptr, dst_ptr, rows, self.src, self.dst, self.start.data_ptr(), self.wt.data_ptr(), self.taps,
+                                           stream), what)
+
+    def post_horizontal(self, lib, in_ptr: int, orig_ptr, out_ptr: int, B: int, H: int, transplant: int, stream: int,
+                        what: str = "post.h"):
+        """Final horizontal pass float [B][3][H][src] -> u8 [B][3][H][dst] (+ luma transplant from `orig`)."""
+        import ctypes as C
+        if self.plan is not None and self.dst > self.src and out_ptr % 4 == 0 and (orig_ptr or 0) % 4 == 0:
+            _lib.check(lib.havc_post_horizontal_periodic(in_ptr, orig_ptr, out_ptr, B, self.src, H, self.dst, self.start.data_ptr(),
+                                                         self.wt.data_ptr(), self.taps, transplant, C.byref(self.plan), stream), what)
+        else:
+            _lib.check(lib.havc_post_horizontal(in_ptr, orig_ptr, out_ptr, B, self.src, H, self.dst, self.start.data_ptr(), self.wt.data_ptr(),
+                                                self.taps, transplant, stream), what)
 
 
 class _FormatIO:
@@ -205,8 +240,7 @@ class DeoldifyEngine:
         """clip.resize.Spline64(S, S) (vsdeoldify/__init__.py:2504) fused with the gray transform + normalisation of the filter."""
         lib, B, S, W, H, chk = self.lib, self.B, self.S, self.W, self.H, _lib.check
         td, tv = self.t_down_h, self.t_down_v
-        chk(lib.havc_resample_h(self.d_in[slot].data_ptr(), self.tmp_down.data_ptr(), B * 3 * H, W, S,
-                                td.start.data_ptr(), td.wt.data_ptr(), td.taps, stream), "pre.h")
+        td.resample_h(lib, self.d_in[slot].data_ptr(), self.tmp_down.data_ptr(), B * 3 * H, stream, "pre.h")
         chk(lib.havc_pre_vertical(self.tmp_down.data_ptr(), self.rgb_small.data_ptr(), self.x_in.data_ptr(), B, H, S,
                                   tv.start.data_ptr(), tv.w.data_ptr(), tv.taps, self.hd, stream), "pre.v")
 
@@ -218,8 +252,7 @@ class DeoldifyEngine:
         result = result if result is not None else self.colored
         chk(lib.havc_resample_v(result.data_ptr(), self.tmp_up.data_ptr(), B * 3, S, H, S,
                                 uv.start.data_ptr(), uv.w.data_ptr(), uv.taps, stream), "post.v")
-        chk(lib.havc_post_horizontal(self.tmp_up.data_ptr(), self.d_in[slot].data_ptr(), self.d_out[slot].data_ptr(), B, S,
-                                     H, W, uh.start.data_ptr(), uh.wt.data_ptr(), uh.taps, 1, stream), "post.h")
+        uh.post_horizontal(lib, self.tmp_up.data_ptr(), self.d_in[slot].data_ptr(), self.d_out[slot].data_ptr(), B, H, 1, stream, "post.h")
 
     def _launch(self, slot: int, stream: int):
         lib, B, S, W, H = self.lib, self.B, self.S, self.W, self.H

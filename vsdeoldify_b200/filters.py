@@ -134,8 +134,7 @@ class SquareSqueeze:
         """src u8 [B,3,H,W] -> dst u8 [B,3,S,S]."""
         lib, B, H, W, S, chk = self.lib, self.B, self.H, self.W, self.S, _lib.check
         td, tv = self.t_down_h, self.t_down_v
-        chk(lib.havc_resample_h(src.data_ptr(), self.tmp_down.data_ptr(), B * 3 * H, W, S, td.start.data_ptr(), td.wt.data_ptr(),
-                                td.taps, stream), "squeeze.h")
+        td.resample_h(lib, src.data_ptr(), self.tmp_down.data_ptr(), B * 3 * H, stream, "squeeze.h")
         chk(lib.havc_pre_vertical(self.tmp_down.data_ptr(), dst.data_ptr(), self.x_scratch.data_ptr(), B, H, S, tv.start.data_ptr(),
                                   tv.w.data_ptr(), tv.taps, 0, stream), "squeeze.v")
 
@@ -145,9 +144,8 @@ class SquareSqueeze:
         uh, uv = self.t_up_h, self.t_up_v
         chk(lib.havc_resample_v(src.data_ptr(), self.tmp_up.data_ptr(), B * 3, S, self.OH, S, uv.start.data_ptr(), uv.w.data_ptr(),
                                 uv.taps, stream), "unsqueeze.v")
-        chk(lib.havc_post_horizontal(self.tmp_up.data_ptr(), luma.data_ptr() if luma is not None else None, dst.data_ptr(), B, S,
-                                     self.OH, self.OW, uh.start.data_ptr(), uh.wt.data_ptr(), uh.taps, int(transplant), stream),
-            "unsqueeze.h")
+        uh.post_horizontal(lib, self.tmp_up.data_ptr(), luma.data_ptr() if luma is not None else None, dst.data_ptr(), B, self.OH,
+                           int(transplant), stream, "unsqueeze.h")
 
 
 class FilterBank:
@@ -739,8 +737,7 @@ class StabilizerEngine:
     def _launch(self, st: int):
         lib, B, S, W, H, chk = self.lib, self.B, self.S, self.W, self.H, _lib.check
         td, tv, uh, uv = self.t_down_h, self.t_down_v, self.t_up_h, self.t_up_v
-        chk(lib.havc_resample_h(self.d_in.data_ptr(), self.tmp_f.data_ptr(), B * 3 * H, W, S, td.start.data_ptr(), td.wt.data_ptr(),
-                                td.taps, st), "squeeze.h")
+        td.resample_h(lib, self.d_in.data_ptr(), self.tmp_f.data_ptr(), B * 3 * H, st, "squeeze.h")
         chk(lib.havc_pre_vertical(self.tmp_f.data_ptr(), self.small.data_ptr(), self.x_scratch.data_ptr(), B, H, S, tv.start.data_ptr(),
                                   tv.w.data_ptr(), tv.taps, 0, st), "squeeze.v")
         res = self.small_out if self.bank.stabilizer_stages(self.small, self.small_out, stream=st, **self.stages) else self.small
@@ -750,8 +747,7 @@ class StabilizerEngine:
             res, nb, src = self.small_t, self.out_B, self.d_in[self.nh:self.nh + self.out_B]
         chk(lib.havc_resample_v(res.data_ptr(), self.tmp_f.data_ptr(), nb * 3, S, H, S, uv.start.data_ptr(), uv.w.data_ptr(), uv.taps, st),
             "unsqueeze.v")
-        chk(lib.havc_post_horizontal(self.tmp_f.data_ptr(), src.data_ptr(), self.d_out.data_ptr(), nb, S, H, W, uh.start.data_ptr(),
-                                     uh.wt.data_ptr(), uh.taps, 1, st), "unsqueeze.h")
+        uh.post_horizontal(lib, self.tmp_f.data_ptr(), src.data_ptr(), self.d_out.data_ptr(), nb, H, 1, st, "unsqueeze.h")
 
     def process_batch(self, frames: np.ndarray, skip=None) -> np.ndarray:
         """frames: uint8 [n<=B, 3, H, W] -> uint8 [n, 3, H, W] (the stabilizer's selectors run with scenechange=False: no gate)."""

@@ -98,6 +98,95 @@ def build_tables(src: int, dst: int, kernel: str = "spline64", shift: float = 0.
     return start, w
 
 
+# ---- phase-periodic plans for the horizontal passes (csrc/pixel.cu: resample_h_periodic_kernel, post_horizontal_periodic_kernel) ----
+PERIODIC_DOWN_TAPS = {4: 35, 5: 43, 6: 51}          # padded taps the squeeze kernel is instantiated for, per ratio
+PERIODIC_UP_TAPS = (8, 9, 10)
+
+
+def _same_bits(a: np.ndarray, b: np.ndarray) -> bool:
+    return np.array_equal(a.view(np.int32), b.view(np.int32))
+
+
+def _interior(ok: np.ndarray, mid: int):
+    """The maximal run of True around `mid`: [lo, hi)."""
+    if not ok[mid]:
+        return mid, mid
+    lo = mid
+    while lo > 0 and ok[lo - 1]:
+        lo -= 1
+    hi = mid + 1
+    while hi < len(ok) and ok[hi]:
+        hi += 1
+    return lo, hi
+
+
+def periodic_plan_down(start: np.ndarray, w: np.ndarray, src: int, dst: int):
+    """Plan of the phase-periodic squeeze (src = ratio * dst): dict(ratio, taps, offset, lo, hi, w) or None.  Interior output
+    columns must satisfy start[o] == ratio * o + c and carry bit-identical weights; the kernel handles blocks of 8 columns."""
+    if dst <= 0 or src % dst or dst % 8 or src % 4:
+        return None
+    R, T = src // dst, int(w.shape[1])
+    if R not in PERIODIC_DOWN_TAPS:
+        return None
+    w = np.ascontiguousarray(w, np.float32)
+    mid = dst // 2
+    c, wref = int(start[mid]) - R * mid, w[mid]
+    ok = np.array([int(start[o]) == R * o + c and _same_bits(w[o], wref) for o in range(dst)])
+    lo, hi = _interior(ok, mid)
+    sh = c % 4
+    offset, taps = c - sh, sh + T
+    lo8, hi8 = -(-lo // 8), hi // 8
+    while lo8 < hi8 and offset + R * 8 * lo8 < 0:
+        lo8 += 1
+    span = 4 * ((R * 7 + PERIODIC_DOWN_TAPS[R] + 3) // 4)
+    while hi8 > lo8 and offset + R * 8 * (hi8 - 1) + span > src + 64:
+        hi8 -= 1
+    if taps > PERIODIC_DOWN_TAPS[R] or hi8 - lo8 < max(1, dst // 16):
+        return None
+    pw = np.zeros(72, np.float32)
+    pw[sh:sh + T] = wref
+    return dict(ratio=R, taps=taps, offset=offset, lo=lo8, hi=hi8, w=pw)
+
+
+def periodic_plan_up(start: np.ndarray, w: np.ndarray, src: int, dst: int):
+    """Plan of the phase-periodic way back (dst = ratio * src): output ratio * i + p has the window start i + c_p and the weights
+    of phase p for every interior input position i; the kernel handles units of 4 positions."""
+    if src <= 0 or dst % src or src % 4:
+        return None
+    R, T = dst // src, int(w.shape[1])
+    if R not in (4, 5, 6):
+        return None
+    w = np.ascontiguousarray(w, np.float32)
+    mid = src // 2
+    cp = [int(start[R * mid + p]) - mid for p in range(R)]
+    ok = np.array([all(int(start[R * i + p]) == i + cp[p] and _same_bits(w[R * i + p], w[R * mid + p]) for p in range(R)) for i in range(src)])
+    lo, hi = _interior(ok, mid)
+    # common window of the phases = the range of their NON-ZERO taps (a phase that samples exactly on a source pixel has the
+    # single weight 1 at its centre; zero taps are exact no-ops of the fmaf chain, so re-basing a window does not change a bit)
+    lo_nz, hi_nz = [], []
+    for p in range(R):
+        nz = np.nonzero(w[R * mid + p])[0]
+        if len(nz) == 0:
+            return None
+        lo_nz.append(cp[p] + int(nz[0])), hi_nz.append(cp[p] + int(nz[-1]))
+    cmin = min(lo_nz)
+    taps = max(max(hi_nz) - cmin + 1, PERIODIC_UP_TAPS[0])
+    ulo, uhi = -(-lo // 4), hi // 4
+    while ulo < uhi and 4 * ulo + cmin < 0:
+        ulo += 1
+    while uhi > ulo and 4 * (uhi - 1) + 3 + cmin + taps > src:
+        uhi -= 1
+    if taps not in PERIODIC_UP_TAPS or not 0 <= -cmin <= 8 or uhi - ulo < max(1, src // 8) or R * taps > 72:
+        return None
+    pw = np.zeros(72, np.float32)
+    for p in range(R):
+        for t in range(T):
+            k = cp[p] + t - cmin
+            if w[R * mid + p, t] != 0.0:
+                pw[p * taps + k] = w[R * mid + p, t]
+    return dict(ratio=R, taps=taps, offset=-cmin, lo=ulo, hi=uhi, w=pw)
+
+
 # ---- Pillow Image.resize tables (ImagingResample, libImaging/Resample.c: precompute_coeffs + normalize_coeffs_8bpc) ----
 # BILINEAR: BaseFilter._scale_to_square / _unsquare (vsdeoldify/deoldify/filters.py:37-41,70-73); BICUBIC (a = -0.5):
 # colorizers/util.py:21-22.  The support is widened by the shrink ratio, weights are normalised in float64 and then
