@@ -859,7 +859,8 @@ static int launch_h_periodic(const uint8_t *in, float *out, long long rows, int 
     PeriodicW pw;
     memcpy(pw.w, pl->w, sizeof(pw.w));
     const long long groups = (rows + 1) / 2;
-    const long long cap = (long long)num_sms() * 8;
+    static const int per_sm = getenv("HAVC_B200_PX_BLOCKS") ? atoi(getenv("HAVC_B200_PX_BLOCKS")) : 8;   // tuning knob
+    const long long cap = (long long)num_sms() * per_sm;
     const int grid = (int)(groups < cap ? groups : cap);
     resample_h_periodic_kernel<kTP, kRt><<<grid, block, sm, st>>>(in, out, rows, Win, Wout, start, weights, taps, pw, pl->offset, pl->lo, pl->hi);
     HAVC_LAUNCHED();
@@ -899,7 +900,8 @@ static int launch_post_periodic(const float *in, const uint8_t *orig, uint8_t *o
     PeriodicW pw;
     memcpy(pw.w, pl->w, sizeof(pw.w));
     const long long nrows = (long long)B * H;
-    const long long cap = (long long)num_sms() * 12;
+    static const int per_sm = getenv("HAVC_B200_PX_BLOCKS") ? atoi(getenv("HAVC_B200_PX_BLOCKS")) : 12;  // tuning knob
+    const long long cap = (long long)num_sms() * per_sm;
     const int grid = (int)(nrows < cap ? nrows : cap);
     post_horizontal_periodic_kernel<kRt, kTP><<<grid, warps * 32, sm, st>>>(in, orig, out, B, S, H, W, start, weights, taps, transplant, pw,
                                                                            pl->offset, pl->lo, pl->hi);
