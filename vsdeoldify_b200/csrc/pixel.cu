@@ -201,7 +201,13 @@ __global__ void resample_v4_kernel(const uint8_t *__restrict__ in, float4 *__res
     }
 }
 
-__device__ __forceinline__ int round_u8(float v) { return sat8(__float2int_rn(v)); }
+// round half to even and clamp to [0, 255] in one conversion (float -> integer conversions saturate; NaN -> 0): the value
+// sat8(__float2int_rn(v)) of the two-step form
+__device__ __forceinline__ int round_u8(float v) {
+    uint32_t r;
+    asm("cvt.rni.u8.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return (int)r;
+}
 
 // Vertical pass of the pre-resize fused with gray conversion + ImageNet normalisation.
 // in: float [B][3][Hin][S]; out: rgb_small u8 [B][3][S][S]; x: 16-bit [B][S][S][8] (channels 3..7 = 0).
@@ -557,7 +563,7 @@ resample_h_periodic_kernel(const uint8_t *__restrict__ in, float *__restrict__ o
         __syncthreads();                                     // the previous group's readers are done
         for (int i = threadIdx.x; i < words; i += blockDim.x) {
             const uint32_t v = i < lim ? __ldg(src + i) : 0u;
-            const int r = i / w4, c = i - r * w4;
+            const int r = i >= w4 ? 1 : 0, c = i - r * w4;      // kRows == 2
             *reinterpret_cast<float4 *>(srow + r * rowlen + 4 * c) =
                 make_float4((float)(v & 0xff), (float)((v >> 8) & 0xff), (float)((v >> 16) & 0xff), (float)(v >> 24));
         }
@@ -859,7 +865,7 @@ static int launch_h_periodic(const uint8_t *in, float *out, long long rows, int 
     PeriodicW pw;
     memcpy(pw.w, pl->w, sizeof(pw.w));
     const long long groups = (rows + 1) / 2;
-    static const int per_sm = getenv("HAVC_B200_PX_BLOCKS") ? atoi(getenv("HAVC_B200_PX_BLOCKS")) : 8;   // tuning knob
+    static const int per_sm = getenv("HAVC_B200_PX_BLOCKS") ? atoi(getenv("HAVC_B200_PX_BLOCKS")) : 12;  // tuning knob
     const long long cap = (long long)num_sms() * per_sm;
     const int grid = (int)(groups < cap ? groups : cap);
     resample_h_periodic_kernel<kTP, kRt><<<grid, block, sm, st>>>(in, out, rows, Win, Wout, start, weights, taps, pw, pl->offset, pl->lo, pl->hi);

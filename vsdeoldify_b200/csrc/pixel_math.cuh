@@ -16,7 +16,8 @@ static inline int grid1d(long long n, int block) {
     return (int)g;
 }
 
-__device__ __forceinline__ int sat8(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
+// clamp to [0, 255]: one VIMNMX with the relu modifier (max(min(v, 255), 0))
+__device__ __forceinline__ int sat8(int v) { return __vimin_s32_relu(v, 255); }
 
 // OpenCV 8-bit COLOR_RGB2YUV / COLOR_YUV2RGB, Q14 fixed point (pinned against
 // cv2 4.13 by tests/test_pixel_oracle.py).
