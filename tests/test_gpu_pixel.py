@@ -54,3 +54,24 @@ def test_periodic_way_back_equals_table_kernel(S, W, B, H, transplant):
 
 def test_non_integer_ratio_has_no_plan_and_uses_the_table_kernels():
     assert _tables(1280, 384).plan is None and _tables(384, 1280).plan is None and _tables(1920, 256).plan is None
+
+
+@pytest.mark.parametrize("B,S,c0", [(2, 384, 4), (1, 96, 4), (3, 64, 0), (1, 130, 4)])
+def test_stem_im2col_rows_are_the_gathered_input_words(B, S, c0):
+    """havc_im2col_small for the stem (7 x 7, stride 2, pad 3, two channels, Kp = 128 -> im2col_stem_kernel): pure data movement,
+    every byte compared with a torch gather (zero padding outside the image, zero tail of every K row)."""
+    from vsdeoldify_b200 import _lib
+    lib = _lib.lib()
+    g = torch.Generator().manual_seed(S + c0)
+    x = torch.randn(B, S, S, 8, generator=g).half().cuda()
+    OH = (S + 6 - 7) // 2 + 1
+    out = torch.full((B, OH, OH, 128), 7.0, dtype=torch.float16, device="cuda")
+    _lib.check(lib.havc_im2col_small(x.data_ptr(), out.data_ptr(), B, S, S, 8, c0, 2, 7, 2, 3, 128, 0, 0))
+    torch.cuda.synchronize()
+    xp = torch.nn.functional.pad(x[..., c0:c0 + 2].permute(0, 3, 1, 2), (3, 3, 3, 3))          # [B, 2, S + 6, S + 6]
+    want = torch.zeros(B, OH, OH, 128, dtype=torch.float16, device="cuda")
+    for kh in range(7):
+        for kw in range(7):
+            patch = xp[:, :, kh:kh + 2 * OH:2, kw:kw + 2 * OH:2]                                # [B, 2, OH, OH]
+            want[..., kh * 16 + kw * 2:kh * 16 + kw * 2 + 2] = patch.permute(0, 2, 3, 1)
+    assert torch.equal(out.view(torch.int16), want.view(torch.int16)), int((out.view(torch.int16) != want.view(torch.int16)).sum())

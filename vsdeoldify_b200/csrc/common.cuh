@@ -74,6 +74,19 @@ __device__ __forceinline__ float2 unpack2(uint32_t v, int dtype) {
         return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162 *>(&v));
     }
 }
+// packed 16-bit arithmetic on two lanes (round to nearest even in the storage type): the ICNR blur's sums
+__device__ __forceinline__ uint32_t add2(uint32_t a, uint32_t b, int dtype) {
+    uint32_t r;
+    if (dtype == HAVC_F16) asm("add.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    else asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+__device__ __forceinline__ uint32_t quarter2(uint32_t a, int dtype) {      // a * 0.25 (exact unless the result is subnormal)
+    uint32_t r;
+    if (dtype == HAVC_F16) asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(0x34003400u));
+    else asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(0x3E803E80u));
+    return r;
+}
 __device__ __forceinline__ float load16(const void *p, int64_t idx, int dtype) {
     if (dtype == HAVC_F16) return __half2float(reinterpret_cast<const __half *>(p)[idx]);
     return __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(p)[idx]);

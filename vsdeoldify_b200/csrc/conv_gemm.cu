@@ -901,7 +901,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 // pixels row = etid >> 3, + 32, ...  It loads the 3 x 3 high-resolution neighbourhood S[-1..1][-1..1] of the pixel's 2 x 2
                 // outputs (own four sub-pixels, two of the left neighbour, two of the upper one, one of the upper-left one; redirected
                 // onto the pixel's own values on the top / left image edge = replication padding), forms the horizontal pair sums once
-                // and writes the four outputs: ((S[y-1][x-1] + S[y-1][x]) + (S[y][x-1] + S[y][x])) / 4, havc_blur2x2's association.
+                // and writes the four outputs: ((S[y-1][x-1] + S[y-1][x]) + (S[y][x-1] + S[y][x])) / 4, havc_blur2x2's association and
+                // arithmetic (packed 16-bit adds).
                 {
                     constexpr int kBW = 16, kCW = 64;
                     const int k = etid & 7;
@@ -911,12 +912,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                     const bool chan_ok = chan < p.c_store;
                     uint16_t *obase = reinterpret_cast<uint16_t *>(p.out) + bt * p.osb + chan;
                     auto grp = [&](int g) -> uint32_t { return (uint32_t)((g * kCW + k * 8) * 2); };   // byte offset of sub-pixel group g in a row
-                    auto lds8 = [&](uint32_t addr, float(&f)[8]) {
-                        uint4 o;
-                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w) : "r"(addr) : "memory");
-                        const uint32_t w[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) { const float2 t = unpack2(w[j], kDT); f[2 * j] = t.x; f[2 * j + 1] = t.y; }
+                    auto lds4 = [&](uint32_t addr, uint32_t(&w)[4]) {
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(addr) : "memory");
                     };
                     for (int row = (etid >> 3); row < kTileM; row += 32) {
                         const int trw = row & (kBW - 1), trh = row >> 4;
@@ -929,36 +926,37 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         // sub-pixel groups g = 2 a + b.  Column X-1 is sub-column b = 1 of the left neighbour (b = 0 of the pixel itself
                         // when clamped); row Y-1 is sub-row a = 1 of the upper neighbour (a = 0 of the pixel itself when clamped)
                         const int gl = pw > 0 ? 1 : 0, gu = ph > 0 ? 2 : 0;
-                        float s[8], t[8], hm[2][8], h0[2][8], h1[2][8];
+                        // packed 16-bit sums (add2: two channels per instruction, no conversions), havc_blur2x2's operations and order
+                        uint32_t s[4], t[4], hm[2][4], h0[2][4], h1[2][4];
                         // row Y-1: S[-1][-1], S[-1][0], S[-1][1]
-                        lds8(upleft + grp(gu + gl), s); lds8(up + grp(gu), t);
+                        lds4(upleft + grp(gu + gl), s); lds4(up + grp(gu), t);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) hm[0][j] = s[j] + t[j];
-                        lds8(up + grp(gu + 1), s);
+                        for (int j = 0; j < 4; ++j) hm[0][j] = add2(s[j], t[j], kDT);
+                        lds4(up + grp(gu + 1), s);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) hm[1][j] = t[j] + s[j];
+                        for (int j = 0; j < 4; ++j) hm[1][j] = add2(t[j], s[j], kDT);
                         // row Y (a = 0): S[0][-1], S[0][0], S[0][1]
-                        lds8(left + grp(gl), s); lds8(own + grp(0), t);
+                        lds4(left + grp(gl), s); lds4(own + grp(0), t);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) h0[0][j] = s[j] + t[j];
-                        lds8(own + grp(1), s);
+                        for (int j = 0; j < 4; ++j) h0[0][j] = add2(s[j], t[j], kDT);
+                        lds4(own + grp(1), s);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) h0[1][j] = t[j] + s[j];
+                        for (int j = 0; j < 4; ++j) h0[1][j] = add2(t[j], s[j], kDT);
                         // row Y+1 (a = 1): S[1][-1], S[1][0], S[1][1]
-                        lds8(left + grp(2 + gl), s); lds8(own + grp(2), t);
+                        lds4(left + grp(2 + gl), s); lds4(own + grp(2), t);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) h1[0][j] = s[j] + t[j];
-                        lds8(own + grp(3), s);
+                        for (int j = 0; j < 4; ++j) h1[0][j] = add2(s[j], t[j], kDT);
+                        lds4(own + grp(3), s);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) h1[1][j] = t[j] + s[j];
+                        for (int j = 0; j < 4; ++j) h1[1][j] = add2(t[j], s[j], kDT);
                         uint16_t *dst = obase + (long long)(2 * ph) * p.osh + (long long)(2 * pw) * p.osw;
 #pragma unroll
                         for (int bq = 0; bq < 2; ++bq) {
                             uint32_t o0[4], o1[4];
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                o0[j] = pack2((hm[bq][2 * j] + h0[bq][2 * j]) * 0.25f, (hm[bq][2 * j + 1] + h0[bq][2 * j + 1]) * 0.25f, kDT);
-                                o1[j] = pack2((h0[bq][2 * j] + h1[bq][2 * j]) * 0.25f, (h0[bq][2 * j + 1] + h1[bq][2 * j + 1]) * 0.25f, kDT);
+                                o0[j] = quarter2(add2(hm[bq][j], h0[bq][j], kDT), kDT);
+                                o1[j] = quarter2(add2(h0[bq][j], h1[bq][j], kDT), kDT);
                             }
                             *reinterpret_cast<uint4 *>(dst + bq * p.osw) = make_uint4(o0[0], o0[1], o0[2], o0[3]);
                             *reinterpret_cast<uint4 *>(dst + p.osh + bq * p.osw) = make_uint4(o1[0], o1[1], o1[2], o1[3]);

@@ -132,6 +132,49 @@ __global__ void im2col_tile_kernel(const uint4 *__restrict__ in, uint4 *__restri
     }
 }
 
+// The stem's im2col (7 x 7, stride 2, pad 3, two channels = one 32-bit word per input pixel, Kp = 128): one block per output
+// row.  The seven input rows are staged once in shared memory as words (the generic kernel issues 49 16-byte loads per output
+// pixel to use 4 bytes of each); a thread assembles its pixel's 14 chunks from 7 consecutive words per filter row and the tile
+// leaves as whole lines, exactly like im2col_tile_kernel (same layout, same bytes).
+__global__ void im2col_stem_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, int H, int W, int OH, int OW,
+                                   long long rows_total, int c0) {
+    extern __shared__ uint4 tile[];                       // [OW][16] swizzled, then the 7 staged input rows
+    constexpr int KS = 7, CH = 16;
+    const int wp = W + 8;                                 // staged row pitch in words: 4 zero words on either side
+    uint32_t *srow = reinterpret_cast<uint32_t *>(tile + OW * CH);
+    const int t = threadIdx.x;
+    const uint32_t *in32 = reinterpret_cast<const uint32_t *>(in) + (c0 ? 2 : 0);
+    for (long long r = blockIdx.x; r < rows_total; r += gridDim.x) {
+        const int oy = (int)(r % OH);
+        const long long b = r / OH;
+        for (int i = t; i < KS * wp; i += blockDim.x) {
+            const int kh = i / wp, ix = i - kh * wp - 4;
+            const int iy = oy * 2 - 3 + kh;
+            srow[i] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(in32 + ((b * H + iy) * W + ix) * 4) : 0u;
+        }
+        __syncthreads();
+        if (t < OW) {
+            uint4 *row = tile + t * CH;
+#pragma unroll
+            for (int kh = 0; kh < KS; ++kh) {
+                const uint32_t *sp = srow + kh * wp + 2 * t + 1;          // input column 2 t - 3 sits at word 2 t - 3 + 4
+                const int c0k = kh * 2, c1k = kh * 2 + 1;
+                row[(c0k & ~7) | ((c0k ^ t) & 7)] = make_uint4(sp[0], sp[1], sp[2], sp[3]);
+                row[(c1k & ~7) | ((c1k ^ t) & 7)] = make_uint4(sp[4], sp[5], sp[6], 0u);
+            }
+#pragma unroll
+            for (int chunk = 2 * KS; chunk < CH; ++chunk) row[(chunk & ~7) | ((chunk ^ t) & 7)] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        __syncthreads();
+        uint4 *dst = out + r * OW * CH;
+        for (int f = t; f < OW * CH; f += blockDim.x) {
+            const int pl = f / CH, slot = f - pl * CH;
+            dst[pl * CH + ((slot & ~7) | ((slot ^ pl) & 7))] = tile[f];
+        }
+        __syncthreads();
+    }
+}
+
 // 3x3 stride-2 pad-1 max-pool (torchvision resnet maxpool).  Split-precision tensors (in_lo / out_lo != NULL) are compared as
 // hi + lo in fp32 (exact: 11 + 11 significant bits) and stored as hi / lo planes again.
 __global__ void maxpool_kernel(const uint4 *__restrict__ in, const uint4 *__restrict__ in_lo, uint4 *__restrict__ out,
@@ -247,14 +290,13 @@ __global__ void affine_act_kernel(const uint4 *__restrict__ in, const uint4 *__r
 // taps in registers, so every output costs two 16-byte loads instead of four.
 static constexpr int kBlurRows = 8;
 static constexpr int kBlurCols = 4;   // adjacent output columns per thread: kBlurCols + 1 loads per row for kBlurCols outputs
+// ((a + b) + (c + d)) * 0.25 in packed 16-bit arithmetic (three roundings in the storage type; the inputs are non-negative
+// ReLU outputs, so there is no cancellation): the same operations, in the same order, as the fused epilogue of conv_gemm.cu
 __device__ __forceinline__ uint4 blur_avg4(const uint4 &a, const uint4 &b, const uint4 &c, const uint4 &d, int dtype) {
     const uint32_t pa[4] = {a.x, a.y, a.z, a.w}, pb[4] = {b.x, b.y, b.z, b.w}, pc[4] = {c.x, c.y, c.z, c.w}, pd[4] = {d.x, d.y, d.z, d.w};
     uint32_t o[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const float2 fa = unpack2(pa[j], dtype), fb = unpack2(pb[j], dtype), fc = unpack2(pc[j], dtype), fd = unpack2(pd[j], dtype);
-        o[j] = pack2(((fa.x + fb.x) + (fc.x + fd.x)) * 0.25f, ((fa.y + fb.y) + (fc.y + fd.y)) * 0.25f, dtype);
-    }
+    for (int j = 0; j < 4; ++j) o[j] = quarter2(add2(add2(pa[j], pb[j], dtype), add2(pc[j], pd[j], dtype), dtype), dtype);
     return make_uint4(o[0], o[1], o[2], o[3]);
 }
 __global__ void blur2x2_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, int B, int H, int W, int C8,
@@ -369,6 +411,21 @@ extern "C" int havc_im2col_small(const void *in, void *out, int B, int H, int W,
         else                                                                                                                     \
             im2col_rows_kernel<KS_, CIN_><<<grid, 256, 0, st>>>((const uint4 *)in, (uint16_t *)out, B, H, W, cin, stride, pad, OH, OW, Kp, c0); \
     } while (0)
+    if (tiled && ks == 7 && cin == 2 && stride == 2 && pad == 3 && Kp == 128 && OW <= 256 && (size_t)OW * 256 + 7 * (W + 8) * 4 <= 96 * 1024) {
+        // the stem of the exact-input path: one block per output row
+        const size_t sm2 = (size_t)OW * 256 + (size_t)7 * (W + 8) * 4;
+        static std::atomic<unsigned long long> attr{0ull};
+        unsigned long long bit;
+        if (device_pending(attr, &bit)) {
+            HAVC_CHECK_CUDA(cudaFuncSetAttribute(im2col_stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            device_done(attr, bit);
+        }
+        const long long rows_total = (long long)B * OH;
+        const int g3 = (int)(rows_total < (long long)num_sms() * 4 ? rows_total : (long long)num_sms() * 4);
+        im2col_stem_kernel<<<g3, 256, sm2, st>>>((const uint4 *)in, (uint4 *)out, H, W, OH, OW, rows_total, c0);
+        HAVC_LAUNCHED();
+        return HAVC_OK;
+    }
     if (ks == 7 && cin == 3) HAVC_IM2COL(7, 3);
     else if (ks == 7 && cin == 2) HAVC_IM2COL(7, 2);
     else if (ks == 3 && cin == 3) HAVC_IM2COL(3, 3);
