@@ -483,3 +483,37 @@ def test_havc_stabilizer_temporal_chain_with_host_plugin():
             assert not np.array_equal(img, fr[n])
     finally:
         del vs_shim.core.rdfl
+
+
+def test_merge_and_temporal_stabilizer_on_yuv_clips():
+    """The format glue of the other entry points under the stand-in (convert_format_RGB24 / restore_format on the device,
+    engine.FormatEngine): HAVC_merge converts clipa / clipb and restores clipa's format (vsdeoldify/__init__.py:2651-2675);
+    vs_chroma_stabilizer_ex / HAVC_stabilizer accept a YUV420P8 clip.  Bit-exact against the restated conversions around the
+    RGB24 oracles (the conversions and the merges are integer / fixed-order float32 arithmetic on both sides)."""
+    from oracle import filters_oracle as fo, temporal_oracle as to, zimg_oracle as zo
+    from vsdeoldify_b200 import havc, vs_shim
+    H, W, n = 48, 64, 18
+    ca, fa, pa = _yuv_clip(n, H, W, 2100, "yuv420p8", {"_Matrix": 6, "_ColorRange": 0})
+    cb, fb, _ = _yuv_clip(n, H, W, 2200, "yuv420p8", {"_Matrix": 1})
+    rgb_a = [zo.yuv420p8_to_rgb24(*f, dither=True, matrix="601", limited=True) for f in fa]     # the input range is read as limited (:133-143)
+    rgb_b = [zo.yuv420p8_to_rgb24(*f, dither=True, matrix="709", limited=True) for f in fb]
+    out = havc.HAVC_merge(ca, cb, weight=0.4, method=3)
+    assert out.format == vs_shim.YUV420P8
+    for i in (5, 0):
+        f = out.get_frame(i)
+        assert f.props == pa[i]
+        want = zo.rgb24_to_yuv420p8(fo.combine_models(rgb_a[i], rgb_b[i], 3, 0.4), "601", False, True)    # clipa's matrix / range
+        for p in range(3):
+            assert np.array_equal(np.asarray(f[p]), want[p]), (i, p, int((np.asarray(f[p]) != want[p]).sum()))
+    st = havc.vs_chroma_stabilizer_ex(ca, nframes=3, mode="A", sat=1.0, tht=20, weight=0.2, tht_scen=0.8)
+    assert st.format == vs_shim.YUV420P8
+    ref = to.chroma_stabilizer_ex(np.stack(rgb_a), nframes=3, mode="A", sat=1.0, tht=20, weight=0.2, tht_scen=0.8, only=[16, 3])
+    for i in (16, 3):
+        f = st.get_frame(i)
+        assert f.props == pa[i]
+        want = zo.rgb24_to_yuv420p8(ref[i], "601", False, True)
+        for p in range(3):
+            assert np.array_equal(np.asarray(f[p]), want[p]), (i, p, int((np.asarray(f[p]) != want[p]).sum()))
+    g, fg, pg = _yuv_clip(3, H, 80, 2300, "gray8")
+    sg = havc.HAVC_stabilizer(g, dark=True, render_factor=16)                                      # GRAY8 in -> YUV420P8 out (:208-222)
+    assert sg.format == vs_shim.YUV420P8 and sg.get_frame(1).props == pg[1] and np.asarray(sg.get_frame(1)[1]).shape == (H // 2, 40)

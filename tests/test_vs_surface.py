@@ -165,3 +165,61 @@ def test_deprecated_aliases_forward_like_the_reference(monkeypatch):
     assert kw["sc_threshold"] == 0 and kw["sc_min_freq"] == 0
     havc.ddeoldify_stabilizer(clip, True, (0.3, 0.7), colormap="blue->brown", render_factor=20)
     assert calls["stab"][1] is True and calls["stab"][7] == "blue->brown" and calls["stab"][8] == 20
+
+
+def test_convert_and_restore_format_call_vapoursynth_like_the_reference(monkeypatch):
+    """Under real VapourSynth convert_format_RGB24 / restore_format (havc_utils.py:57-237) are VapourSynth's own resize.Bicubic
+    with the reference's arguments (zimg itself does the work: any format).  VapourSynth is not installable here, so a recording
+    stand-in of the few calls is swapped in for `havc.vs` and the argument lists are compared with the reference's source."""
+    import types
+    from vsdeoldify_b200 import havc
+    calls = []
+
+    class Fmt:
+        def __init__(self, id, family, bits):
+            self.id, self.color_family, self.bits_per_sample = id, family, bits
+
+        def replace(self, bits_per_sample):
+            return Fmt(self.id + 1000, self.color_family, bits_per_sample)
+
+    class Clip:
+        def __init__(self, fmt, props=None):
+            self.format, self.width, self.height, self.num_frames = fmt, 64, 48, 5
+            self._props = props or {}
+            self.std = types.SimpleNamespace(SetFrameProps=lambda **kw: (calls.append(("SetFrameProps", kw)), Clip(self.format, {**self._props, **kw}))[1])
+
+        def get_frame(self, n):
+            return types.SimpleNamespace(props=self._props)
+
+    def bicubic(clip, **kw):
+        calls.append(("Bicubic", kw))
+        f = kw["format"]
+        return Clip(f if isinstance(f, Fmt) else Fmt(f, "RGB" if f == 1 else "YUV", 8), clip._props)
+    fake = types.SimpleNamespace(RGB24=1, YUV420P8=3, YUV="YUV", GRAY="GRAY", RGB="RGB", MATRIX_BT709=1, Error=havc.vs.Error,
+                                 core=types.SimpleNamespace(core_version=types.SimpleNamespace(release_major=70),
+                                                            resize=types.SimpleNamespace(Bicubic=bicubic)))
+    monkeypatch.setattr(havc, "vs", fake)
+    # a 10-bit BT.601 limited-range YUV clip
+    src = Clip(Fmt(77, "YUV", 10), {"_Matrix": 6, "_ColorRange": 1})
+    rgb, restore = havc.convert_format_RGB24(src)
+    assert [c[0] for c in calls] == ["Bicubic", "Bicubic", "SetFrameProps"]
+    assert calls[0][1]["format"].bits_per_sample == 8                                                     # :126-127
+    assert {k: v for k, v in calls[1][1].items()} == dict(format=1, matrix_in=6, range_in_s="limited", range_s="full",
+                                                          dither_type="error_diffusion")                  # :133-143
+    assert calls[2][1] == {"_ColorRange": 0}                                                               # :160-163
+    calls.clear()
+    restore(rgb)
+    assert calls == [("Bicubic", dict(format=77, matrix_in=1, matrix=6, range_in_s="full", range_s="limited",
+                                      dither_type="error_diffusion"))]                                    # :199-207
+    # GRAY8 full range: no dither on the way in, YUV420P8 BT.709 full range on the way out (:145-151, :208-222)
+    calls.clear()
+    rgb, restore = havc.convert_format_RGB24(Clip(Fmt(9, "GRAY", 8), {"_ColorRange": 0}))
+    assert calls[0] == ("Bicubic", dict(format=1, range_in_s="limited", range_s="full"))
+    calls.clear()
+    restore(rgb)
+    assert calls == [("Bicubic", dict(format=3, matrix=1, range_in_s="full", range_s="full", dither_type="error_diffusion"))]
+    # RGB24 passes through untouched
+    calls.clear()
+    c = Clip(Fmt(1, "RGB", 8))
+    rgb, restore = havc.convert_format_RGB24(c)
+    assert rgb is c and restore(c) is c and calls == []

@@ -123,6 +123,51 @@ class _FormatIO:
             "rgb_to_yuv420p8")
 
 
+class FormatEngine:
+    """convert_format_RGB24 / restore_format (vsdeoldify/havc_utils.py:57-237) for YUV420P8 / GRAY8 clips on batches of host
+    frames, outside a colorizer engine: the format glue of HAVC_stabilizer / HAVC_merge / vs_chroma_stabilizer_ex under the
+    VapourSynth stand-in (under real VapourSynth those entry points call VapourSynth's own resize, like the reference)."""
+
+    def __init__(self, fmt: str, width: int, height: int, batch: int = 8, device: str = "cuda:0", matrix: str = "709",
+                 out_limited: bool = True):
+        self.dev = torch.device(device)
+        torch.cuda.set_device(self.dev)
+        self.B, self.H, self.W = batch, height, width
+        self.io = _FormatIO(fmt, batch, height, width, self.dev, matrix, out_limited)
+        u8 = dict(dtype=torch.uint8, device=self.dev)
+        self.d_raw_in, self.d_raw_out = torch.zeros(self.io.in_bytes, **u8), torch.zeros(self.io.out_bytes, **u8)
+        self.d_rgb = torch.zeros(batch, 3, height, width, **u8)
+        self.h_raw_in, self.h_raw_out = torch.zeros(self.io.in_bytes, dtype=torch.uint8).pin_memory(), torch.zeros(self.io.out_bytes, dtype=torch.uint8).pin_memory()
+        self.h_rgb = torch.zeros(batch, 3, height, width, dtype=torch.uint8).pin_memory()
+        self.stream = torch.cuda.Stream(device=self.dev)
+
+    def to_rgb(self, frames) -> np.ndarray:
+        """frames: up to B source frames (indexable by plane) -> uint8 [n, 3, H, W]."""
+        n = len(frames)
+        buf = self.h_raw_in.numpy()
+        for j, f in enumerate(frames):
+            for d, p in zip(self.io.planes(buf, j), range(3)):
+                np.copyto(d, np.asarray(f[p]))
+        with torch.cuda.stream(self.stream):
+            self.d_raw_in.copy_(self.h_raw_in, non_blocking=True)
+            self.io.to_rgb(self.d_raw_in, self.d_rgb, self.stream.cuda_stream)
+            self.h_rgb.copy_(self.d_rgb, non_blocking=True)
+        self.stream.synchronize()
+        return self.h_rgb[:n].numpy().copy()
+
+    def from_rgb(self, rgb: np.ndarray):
+        """uint8 [n <= B, 3, H, W] -> per frame [Y, U, V] plane arrays (copies)."""
+        n = rgb.shape[0]
+        self.h_rgb[:n].copy_(torch.from_numpy(np.ascontiguousarray(rgb)))
+        with torch.cuda.stream(self.stream):
+            self.d_rgb.copy_(self.h_rgb, non_blocking=True)
+            self.io.from_rgb(self.d_rgb, self.d_raw_out, self.stream.cuda_stream)
+            self.h_raw_out.copy_(self.d_raw_out, non_blocking=True)
+        self.stream.synchronize()
+        buf = self.h_raw_out.numpy()
+        return [[pl.copy() for pl in self.io.planes(buf, j, out=True)] for j in range(n)]
+
+
 class DeoldifyEngine:
     """DeOldify at render size S = render_factor*16 on frames of width x height, batch B.
 

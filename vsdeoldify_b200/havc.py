@@ -96,6 +96,17 @@ def _output_frame(src_frame, planes, out_format=None):
     return g
 
 
+def _native_format(clip) -> bool:
+    """RGB24, YUV420P8 (BT.709 / BT.601) or GRAY8: the formats the engines convert on the device."""
+    fid = getattr(clip.format, "id", clip.format)
+    ids = [getattr(getattr(vs, n, None), "id", getattr(vs, n, None)) for n in ("RGB24", "YUV420P8", "GRAY8") if hasattr(vs, n)]
+    if fid not in ids:
+        return False
+    if fid == ids[0]:
+        return True
+    return int(clip.get_frame(0).props.get("_Matrix", 1)) in (1, 2, 5, 6)
+
+
 def _clip_format(clip, who: str):
     """(engine fmt, matrix, out_limited, output format) of a clip, the way convert_format_RGB24 reads them (havc_utils.py:57-164):
     RGB24 as is; 8-bit YUV 4:2:0 and GRAY are converted on the device (matrix from frame 0's _Matrix, default BT.709; input
@@ -262,6 +273,13 @@ def HAVC_colorizer(
         _raise("HAVC_colorizer: CPU mode (device_index=99) is not available in the B200 build (no CPU fallback)")
     if not torch.cuda.is_available():
         _raise("HAVC_colorizer: CUDA is not available")                                   # :2441
+    if vs is not vs_shim and not _native_format(clip):
+        # real VapourSynth, a format the device conversion does not cover (10-bit, 4:2:2, 4:4:4, RGB48, ...): VapourSynth's own
+        # convert_format_RGB24 / restore_format around the RGB24 path, exactly what the reference does (:2493, :2523)
+        rgb, restore = convert_format_RGB24(clip, "HAVC_colorizer")
+        return restore(HAVC_colorizer(rgb, method, mweight, deoldify_p, ddcolor_p, ddtweak, ddtweak_p, cmc_p, lmm_p, alm_p, crt_p, cmb_sw,
+                                      sc_threshold, sc_tht_offset, sc_min_freq, sc_tht_ssim, sc_normalize, sc_min_int, sc_tht_white,
+                                      sc_tht_black, device_index, torch_dir, debug_level))
     fmt, matrix, out_limited, out_format = _clip_format(clip, "HAVC_colorizer")
     if sc_threshold < 0:
         _raise("HAVC_colorizer: sc_threshold must be >= 0")                              # :2447
@@ -413,14 +431,22 @@ def HAVC_merge(clipa=None, clipb=None, clip_luma=None, weight: float = 0.5, meth
                lmm_p: Sequence = DEF_LMM_p, alm_p: Sequence = DEF_ALM_p, crt_p: Sequence = DEF_CRT_p, device_index: int = 0):
     """Drop-in for vsdeoldify.HAVC_merge (vsdeoldify/__init__.py:2536-2675) on RGB24 clips: method 2 = std.Merge,
     methods 3-7 = the vsslib merges of vs_combine_models, `clip_luma` = the Spline64 squeeze + _clip_chroma_resize detour of
-    :2633-2673.  Non-RGB24 formats (convert_format_RGB24 / restore_format) raise."""
+    :2633-2673.  clipa / clipb in other formats go through convert_format_RGB24 and the result is restored to clipa's format
+    (:2651-2652, :2675), like the reference."""
     for name, c in (("clipa", clipa), ("clipb", clipb), ("clip_luma", clip_luma)):
         if c is not None and not hasattr(c, "get_frame"):
             _raise("HAVC_merge: this is not a clip: " + name)                            # :2624-2631
     rgb24 = getattr(vs.RGB24, "id", vs.RGB24)
-    for c in (clipa, clipb, clip_luma):
-        if c is not None and getattr(c.format, "id", c.format) != rgb24:
-            _raise("HAVC_merge: only RGB24 clips are handled by the B200 build (convert_format_RGB24 is a 'next' row)")
+    shortcut = method == 0 or weight == 0 or method == 1 or weight == 1
+    # :2651-2652: the merge proper converts clipa / clipb with convert_format_RGB24 and restores clipa's format at the end; the
+    # shortcuts (:2633-2649) and clip_luma (_clip_chroma_resize) use the clips as they are: RGB24
+    for name, c in (("clipa", clipa), ("clipb", clipb), ("clip_luma", clip_luma)):
+        if c is not None and (shortcut or name == "clip_luma") and getattr(c.format, "id", c.format) != rgb24:
+            _raise("HAVC_merge: " + name + " must be RGB24 here (only the merge proper converts clipa / clipb, vsdeoldify/__init__.py:2651)")
+    restore = lambda c: c
+    if not shortcut:
+        clipa, restore = convert_format_RGB24(clipa, "HAVC_merge", device_index)
+        clipb, _ = convert_format_RGB24(clipb, "HAVC_merge", device_index)
     from .filters import FilterError, LumaMergeEngine, MergeEngine
     args = (list(cmc_p), list(lmm_p), list(alm_p), list(crt_p))
     mk = lambda fn, base: (vs_shim.VideoNode(base.num_frames, base.width, base.height, base.format, fn, base.fps_num, base.fps_den)
@@ -452,11 +478,11 @@ def HAVC_merge(clipa=None, clipb=None, clip_luma=None, weight: float = 0.5, meth
     if method == 2 or clip_luma is None:                                                  # :2648-2650: method 2 ignores clip_luma
         engine = MergeEngine(clipa.width, clipa.height, batch=_BATCH, device=f"cuda:{device_index}")
         fn = _MergedClip(clipa, clipb, engine, _BATCH, method, weight, *args)
-        return mk(guarded(fn), clipa)
+        return restore(mk(guarded(fn), clipa))
     eng = LumaMergeEngine((clipa.width, clipa.height), (clip_luma.width, clip_luma.height), True, batch=_BATCH,
                           device=f"cuda:{device_index}")
     fn = _MergedClip(clipa, clipb, eng, _BATCH, method, weight, *args, clip_luma=clip_luma, sc_src=clipa)
-    return mk(guarded(fn), clip_luma)
+    return restore(mk(guarded(fn), clip_luma))
 
 
 _COLORMAP_NAMES = ['none', 'blue->brown', 'blue->red', 'blue->green', 'green->brown', 'green->red', 'green->blue', 'redrose->brown',
@@ -478,6 +504,91 @@ def _get_colormap(ColorMap: str = "red->brown", ColorTune: str = "light") -> str
     if parse_hue_adjust(cm) is None:
         _raise("HAVC_main: ColorMap choice is invalid for '" + cm + "'")
     return cm
+
+
+class _ConvertedClip:
+    """frame_fn of a format-converted clip under the VapourSynth stand-in: batches of frames through engine.FormatEngine
+    (to_rgb = convert_format_RGB24, from_rgb = restore_format); props are carried over from the source frames."""
+
+    def __init__(self, clip, engine, to_rgb: bool, props_from=None):
+        self.clip, self.engine, self.to_rgb, self.B = clip, engine, to_rgb, engine.B
+        self.props_from = props_from if props_from is not None else clip
+        self.cache: "OrderedDict[int, object]" = OrderedDict()
+        self.lock = threading.Lock()
+
+    def __call__(self, n: int):
+        with self.lock:
+            if n in self.cache:
+                return self.cache[n]
+            n0 = (n // self.B) * self.B
+            idx = range(n0, min(n0 + self.B, self.clip.num_frames))
+            frames = [self.clip.get_frame(i) for i in idx]
+            if self.to_rgb:
+                rgb = self.engine.to_rgb(frames)
+                outs = [vs_shim.VideoFrame([rgb[j, p] for p in range(3)], vs_shim.RGB24, dict(f.props)) for j, f in enumerate(frames)]
+            else:
+                planes = self.engine.from_rgb(np.stack([np.stack([np.asarray(f[p]) for p in range(3)]) for f in frames]))
+                outs = [vs_shim.VideoFrame(planes[j], vs_shim.YUV420P8, dict(self.props_from.get_frame(i).props)) for j, i in enumerate(idx)]
+            for i, f in zip(idx, outs):
+                self.cache[i] = f
+            while len(self.cache) > 4 * self.B:
+                self.cache.popitem(last=False)
+            return self.cache[n]
+
+
+def convert_format_RGB24(clip, who: str = "convert_format_RGB24", device_index: int = 0):
+    """Drop-in for havc_utils.convert_format_RGB24 (vsdeoldify/havc_utils.py:57-164, chroma_resize=False): (RGB24 clip, restore),
+    `restore(rgb_clip)` being restore_format (:167-237) for this clip.  Real VapourSynth: VapourSynth's own resize.Bicubic with
+    the reference's arguments (every format the reference handles).  Stand-in: YUV420P8 / GRAY8 on the device (zimg restated)."""
+    fid = getattr(clip.format, "id", clip.format)
+    if fid == getattr(vs.RGB24, "id", vs.RGB24):
+        return clip, (lambda c: c)
+    if vs is not vs_shim:
+        fmt = clip.format
+        props = clip.get_frame(0).props
+        v74 = vs.core.core_version.release_major >= 74
+        rkey = "_Range" if v74 else "_ColorRange"
+        matrix = props.get("_Matrix", int(vs.MATRIX_BT709))
+        if int(matrix) == 2:                                                               # unspecified (_matrixIsInvalid, :76-77)
+            matrix = int(vs.MATRIX_BT709)
+            clip = clip.std.SetFrameProps(_Matrix=matrix)
+        full = int(props.get(rkey, 1)) == 0
+        c = clip
+        if fmt.bits_per_sample != 8:
+            c = vs.core.resize.Bicubic(c, format=fmt.replace(bits_per_sample=8))           # :126-127
+        if fmt.color_family == vs.YUV:
+            c = vs.core.resize.Bicubic(c, format=vs.RGB24, matrix_in=matrix, range_in_s="limited", range_s="full",
+                                       dither_type="error_diffusion")                      # :133-143
+        elif fmt.color_family == vs.GRAY:
+            c = vs.core.resize.Bicubic(c, format=vs.RGB24, range_in_s="limited", range_s="full")   # :145-151
+        else:
+            c = vs.core.resize.Bicubic(c, format=vs.RGB24, range_s="full")                 # :152-157
+        c = c.std.SetFrameProps(**{rkey: 0})                                               # :160-163 (RANGE_FULL)
+
+        def restore(rgb):                                                                  # restore_format, :167-237
+            rs = "full" if full else "limited"
+            if fmt.color_family == vs.YUV:
+                return vs.core.resize.Bicubic(rgb, format=fmt.id, matrix_in=int(vs.MATRIX_BT709), matrix=matrix, range_in_s="full",
+                                              range_s=rs, dither_type="error_diffusion")
+            if fmt.color_family == vs.GRAY:
+                return vs.core.resize.Bicubic(rgb, format=vs.YUV420P8, matrix=int(vs.MATRIX_BT709), range_in_s="full", range_s=rs,
+                                              dither_type="error_diffusion")
+            return vs.core.resize.Bicubic(rgb, format=fmt.id, range_in_s="full", range_s=rs)
+        return c, restore
+    from .engine import FormatEngine
+    fmt, matrix, out_limited, out_format = _clip_format(clip, who)
+    if not torch.cuda.is_available():
+        _raise(f"{who}: CUDA is not available")
+    try:
+        eng = FormatEngine(fmt, clip.width, clip.height, batch=min(_BATCH, 8), device=f"cuda:{device_index}", matrix=matrix,
+                           out_limited=out_limited)
+    except ValueError as e:
+        _raise(f"{who}: " + str(e))
+    rgb = vs_shim.VideoNode(clip.num_frames, clip.width, clip.height, vs_shim.RGB24, _ConvertedClip(clip, eng, True), clip.fps_num, clip.fps_den)
+
+    def restore(c):
+        return vs_shim.VideoNode(c.num_frames, c.width, c.height, out_format, _ConvertedClip(c, eng, False), c.fps_num, c.fps_den)
+    return rgb, restore
 
 
 class _TemporalClip:
@@ -538,19 +649,18 @@ def vs_chroma_stabilizer_ex(clip, nframes: int = 5, mode: str = "A", sat: float 
                             tht_scen: float = 0.8, hue_adjust: str = 'none', algo: int = 0, device_index: int = 0):
     """Drop-in for vsslib.vsfilters.vs_chroma_stabilizer_ex (vsslib/vsfilters.py:84-115) on RGB24 clips, algo = 0 (the value
     HAVC_stabilizer passes; algo = 1, the ModifyFrame variant, raises): the temporal chroma stabiliser, scope row N3."""
-    if getattr(clip.format, "id", clip.format) != getattr(vs.RGB24, "id", vs.RGB24):
-        _raise("vs_chroma_stabilizer_ex: only RGB24 clips are handled")
     if algo != 0:
         _raise("vs_chroma_stabilizer_ex: algo=1 (_average_frames_ex) is not built; HAVC_stabilizer uses algo=0")
     if not torch.cuda.is_available():
         _raise("vs_chroma_stabilizer_ex: CUDA is not available")
+    clip, restore = convert_format_RGB24(clip, "vs_chroma_stabilizer_ex", device_index)       # the reference's function is RGB24 only
     from .filters import FilterError, TemporalEngine
     try:
         engine = TemporalEngine(clip.width, clip.height, batch=min(_BATCH, 8), device=f"cuda:{device_index}",
                                 **_stab_params(nframes, mode, sat, tht, weight, tht_scen, hue_adjust))
     except (ValueError, FilterError) as e:
         _raise(str(e))
-    return _node_like(clip, _TemporalClip(clip, engine, scene_weights=int(tht) == 0))
+    return restore(_node_like(clip, _TemporalClip(clip, engine, scene_weights=int(tht) == 0)))
 
 
 def _reduce_flicker(clip, strength: int = 2, aggressive: int = 0):
@@ -575,14 +685,13 @@ def HAVC_stabilizer(clip, dark: bool = False, dark_p: Sequence = (0.2, 0.8), smo
     _clip_chroma_resize back to the clip's size with the original luma.  `stab=True` adds the temporal chroma stabiliser
     (vs_chroma_stabilizer_ex, row N3 of the scope table) on the squeezed clip, followed - as in the reference - by the external
     ReduceFlicker plugin (`core.rdfl`), which must be provided by the host (the reference's error is raised without it)."""
-    if getattr(clip.format, "id", clip.format) != getattr(vs.RGB24, "id", vs.RGB24):
-        _raise("HAVC_stabilizer: only RGB24 input is handled by the B200 build (convert_format_RGB24 is a 'next' row)")
     if render_factor != 0 and render_factor not in range(16, 65):
         _raise("HAVC_stabilizer: render_factor must be between: 16-64")                   # :2796
     if stab and getattr(vs.core, "rdfl", None) is None:
         _reduce_flicker(clip)                         # raises at graph-build time, like the reference without the plugin (:2861)
     if not torch.cuda.is_available():
         _raise("HAVC_stabilizer: CUDA is not available")
+    clip, restore = convert_format_RGB24(clip, "HAVC_stabilizer", device_index)           # :2787 (restore_format at :2871)
     if render_factor == 0:
         render_factor = min(max(math.trunc(0.4 * clip.width / 16), 16), 32)               # :2799
     frame_size = min(render_factor * 16, clip.width)                                      # :2803
@@ -599,8 +708,8 @@ def HAVC_stabilizer(clip, dark: bool = False, dark_p: Sequence = (0.2, 0.8), smo
     except (ValueError, FilterError) as e:
         _raise("HAVC_stabilizer: " + str(e))
     if stab:
-        return _reduce_flicker(_node_like(clip, _TemporalClip(clip, engine, scene_weights=stab_kw["tht"] == 0)))
-    return _node_like(clip, _ColorizedClip(clip, engine, False, _BATCH, run=engine.process_batch))
+        return restore(_reduce_flicker(_node_like(clip, _TemporalClip(clip, engine, scene_weights=stab_kw["tht"] == 0))))
+    return restore(_node_like(clip, _ColorizedClip(clip, engine, False, _BATCH, run=engine.process_batch)))
 
 
 class ModelImageRender:
