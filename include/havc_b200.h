@@ -213,6 +213,11 @@ int havc_blend_u8(const uint8_t *a, const uint8_t *b, uint8_t *out, long long n,
  * out[plane][oy][x] = sum_t weights[oy][t] * in[plane][start[oy]+t][x].  in: u8 [planes][Hin][W]; out: float. */
 int havc_resample_v(const uint8_t *in, float *out, long long planes, int Hin, int Hout, int W, const int *start,
                     const float *weights, int taps, void *stream);
+/* Vertical pass float -> u8 (round half to even, clamp): the second pass of a horizontal-first resize to a rectangular size
+ * (vsslib/vsresize.py:30-75 resize_min_HW -> resize.Spline36).  in float [planes][Hin][W]; out u8 [planes][Hout][W];
+ * weights [Hout][taps]. */
+int havc_resample_v_f32_u8(const float *in, uint8_t *out, long long planes, int Hin, int Hout, int W, const int *start,
+                           const float *weights, int taps, void *stream);
 /* Final horizontal pass of the resize back to W x H fused with vs_recover_clip_luma / chroma_post_process
  * (vsdeoldify/vsslib/vsfilters.py:863-899, imfilters.py:312-321): keep the luma of `orig`, the chroma of the
  * upscaled colour image (OpenCV Q14 8-bit YUV).  in: float [B][3][H][S]; orig/out: u8 [B][3][H][W];

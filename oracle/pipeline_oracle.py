@@ -129,6 +129,37 @@ def havc_stabilizer_clip(frames: np.ndarray, only, dark=False, dark_p=(0.2, 0.8)
     return {n: px.chroma_post_process(px.resize_plane_u8(st[n], W, H, kernel), frames[n]) for n in only}
 
 
+def min_hw_size(width: int, height: int, min_size=(512, 480)):
+    """vsslib/vsresize.py:30-99: the size resize_min_HW resizes to, or None."""
+    if height < width:
+        if height <= min_size[1]:
+            return None
+        w = round(width * min_size[1] / height)
+        return (w - 1 if w % 2 else w), min_size[1]
+    if width <= min_size[0]:
+        return None
+    h = round(height * min_size[0] / width)
+    return min_size[0], (h + 1 if h % 2 else h)
+
+
+def resize_min_hw(frame: np.ndarray) -> np.ndarray:
+    """resize_min_HW (vsslib/vsresize.py:30-50) on a uint8 [H,W,3] frame: zimg Spline36 (restated, unpinned)."""
+    size = min_hw_size(frame.shape[1], frame.shape[0])
+    return frame if size is None else px.resize_plane_u8(frame, size[0], size[1], "spline36")
+
+
+def resize_to_chroma(high: np.ndarray, low: np.ndarray) -> np.ndarray:
+    """resize_to_chroma (vsslib/vsresize.py:101-127): Spline36 of `low` to the size of `high`, both to YUV420P8 (BT.709 full range,
+    no dither), luma of `high` + chroma of `low`, RGB24 with error diffusion (zimg restated, unpinned)."""
+    from . import zimg_oracle as zo
+    H, W = high.shape[:2]
+    if low.shape[:2] != (H, W):
+        low = px.resize_plane_u8(low, W, H, "spline36")
+    y = zo.rgb24_to_yuv420p8(high, "709", False, False)[0]
+    _, u, v = zo.rgb24_to_yuv420p8(low, "709", False, False)
+    return zo.yuv420p8_to_rgb24(y, u, v, True, "709", False)
+
+
 def colorizer_filter(sd, img: np.ndarray, render_factor: int) -> np.ndarray:
     """MasterFilter([ColorizerFilter]).filter(img, img, rf) (deoldify/filters.py:81-124) on a uint8 [H,W,3] image:
     Pillow-BILINEAR squeeze to S x S, network, Pillow-BILINEAR back, luma transplant.  This is the path

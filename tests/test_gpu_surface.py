@@ -79,6 +79,9 @@ def test_havc_main_preset_path():
     a = havc.HAVC_main(clip, Preset="VeryFast", ColorModel="DeOldify(Video)", ColorMap="red->brown")
     b = havc.HAVC_stabilizer(havc.HAVC_deoldify(clip, model=0, render_factor=16, ddcolor_p=[1, 16, 1.0, 0.0, True]),
                              colormap="320:360|+50,0.90")
+    # every preset built here runs with chroma_resize (vsdeoldify/__init__.py:492-494): resize_min_HW is the identity on a clip this
+    # small, resize_to_chroma (restore_format, havc_utils.py:183-184) still takes the result's chroma through YUV420P8
+    b = havc.resize_to_chroma(clip, b)
     for i in range(2):
         fa, fb = a.get_frame(i), b.get_frame(i)
         assert all(np.array_equal(np.asarray(fa[p]), np.asarray(fb[p])) for p in range(3))
@@ -517,3 +520,35 @@ def test_merge_and_temporal_stabilizer_on_yuv_clips():
     g, fg, pg = _yuv_clip(3, H, 80, 2300, "gray8")
     sg = havc.HAVC_stabilizer(g, dark=True, render_factor=16)                                      # GRAY8 in -> YUV420P8 out (:208-222)
     assert sg.format == vs_shim.YUV420P8 and sg.get_frame(1).props == pg[1] and np.asarray(sg.get_frame(1)[1]).shape == (H // 2, 40)
+
+
+def test_resize_min_hw_and_resize_to_chroma_vs_oracle():
+    """HAVC_main's chroma_resize detour (vsslib/vsresize.py:30-127): Spline36 reduction to height 480 and the way back with the luma
+    of the full-size clip, against the CPU restatement; and HAVC_main == the same steps chained by hand (one frame, 644 x 484)."""
+    from oracle import pipeline_oracle
+    havc = _register()
+    H, W = 484, 644
+    clip, fr, props = _clip(2, H, W, seed=910)
+    small = havc.resize_min_HW(clip)
+    assert (small.width, small.height) == pipeline_oracle.min_hw_size(W, H) == (638, 480)
+    src = np.ascontiguousarray(np.transpose(fr[1], (1, 2, 0)))
+    got = np.stack([np.asarray(small.get_frame(1)[p]) for p in range(3)], -1)
+    want = pipeline_oracle.resize_min_hw(src)
+    d = np.abs(got.astype(int) - want.astype(int))
+    assert d.max() <= 1 and (d > 0).mean() < 0.01, (int(d.max()), float((d > 0).mean()))   # float passes: last-bit ties only
+    assert small.get_frame(1).props == props[1]
+    # the way back: the low-resolution frame of the oracle goes in on both sides, so only the float resize can differ
+    from vsdeoldify_b200 import vs_shim
+    low_clip = vs_shim.array_clip(np.ascontiguousarray(np.transpose(want, (2, 0, 1)))[None].repeat(2, 0),
+                                  props=[{"_SceneChangePrev": 1, "sc_threshold": 0.25}, {"_SceneChangePrev": 0, "sc_threshold": 0.25}])
+    back = havc.resize_to_chroma(clip, low_clip)
+    f = back.get_frame(1)
+    assert f.props == dict(props[1], _SceneChangePrev=0, sc_threshold=0.25)               # CopyFrameProps of the SC props (:124-125)
+    got = np.stack([np.asarray(f[p]) for p in range(3)], -1)
+    want_back = pipeline_oracle.resize_to_chroma(src, want)
+    d = np.abs(got.astype(int) - want_back.astype(int))
+    assert d.mean() < 0.05 and np.percentile(d, 99.9) <= 2, (float(d.mean()), int(d.max()))   # error diffusion moves +-1 decisions
+    a = havc.HAVC_main(clip, Preset="VeryFast", ColorModel="DeOldify(Video)")
+    b = havc.resize_to_chroma(clip, havc.HAVC_stabilizer(havc.HAVC_deoldify(small, model=0, render_factor=16, ddcolor_p=[1, 16, 1.0, 0.0, True])))
+    fa, fb = a.get_frame(0), b.get_frame(0)
+    assert (a.width, a.height) == (W, H) and all(np.array_equal(np.asarray(fa[p]), np.asarray(fb[p])) for p in range(3))

@@ -283,6 +283,23 @@ __global__ void pre_vertical4_kernel(const float *__restrict__ in, uint8_t *__re
     }
 }
 
+// Vertical pass float rows -> u8 (second pass of a horizontal-first resize to a rectangular size, e.g. resize_min_HW's Spline36):
+// in float [planes][Hin][W] -> out u8 [planes][Hout][W], round half to even + clamp.
+__global__ void resample_v_f32_u8_kernel(const float *__restrict__ in, uint8_t *__restrict__ out, long long planes, int Hin, int Hout,
+                                         int W, const int *__restrict__ start, const float *__restrict__ wts, int T) {
+    const long long total = planes * Hout * W;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ox = (int)(i % W);
+        const int oy = (int)((i / W) % Hout);
+        const long long pl = i / ((long long)W * Hout);
+        const float *src = in + (pl * Hin + __ldg(start + oy)) * W + ox;
+        const float *w = wts + (long long)oy * T;
+        float acc = 0.f;
+        for (int t = 0; t < T; ++t) acc = fmaf(__ldg(w + t), __ldg(src + (long long)t * W), acc);
+        out[i] = (uint8_t)round_u8(acc);
+    }
+}
+
 // ColorizerFilter._transform (convert('LA').convert('RGB'), filters.py:92-93) + ImageNet normalisation (filters.py:50-53)
 // of an already square u8 image: rgb u8 [B][3][n] -> x 16-bit [B][n][8].
 __global__ void gray_normalize_kernel(const uint8_t *__restrict__ rgb, void *__restrict__ x, int B, long long n, int dtype) {
@@ -838,6 +855,14 @@ extern "C" int havc_pre_vertical(const float *in, uint8_t *rgb_small, void *x, i
     else
         pre_vertical_kernel<<<grid1d((long long)B * S * S, 256), 256, 0, (cudaStream_t)stream>>>(
             in, rgb_small, x, B, Hin, S, start, weights, taps, dtype);
+    HAVC_LAUNCHED();
+    return HAVC_OK;
+}
+
+extern "C" int havc_resample_v_f32_u8(const float *in, uint8_t *out, long long planes, int Hin, int Hout, int W, const int *start,
+                                      const float *weights, int taps, void *stream) {
+    HAVC_CHECK_ARG(in && out && start && weights && taps > 0 && planes > 0 && Hin > 0 && Hout > 0 && W > 0, "havc_resample_v_f32_u8: bad arguments");
+    resample_v_f32_u8_kernel<<<grid1d(planes * Hout * W, 256), 256, 0, (cudaStream_t)stream>>>(in, out, planes, Hin, Hout, W, start, weights, taps);
     HAVC_LAUNCHED();
     return HAVC_OK;
 }

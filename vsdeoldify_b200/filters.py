@@ -148,6 +148,33 @@ class SquareSqueeze:
                            int(transplant), stream, "unsqueeze.h")
 
 
+class RectResize:
+    """clip.resize.Spline36 / Spline64(width, height) of planar u8 batches [B,3,H,W] -> [B,3,OH,OW] (zimg restated: two separable
+    float32 passes, the cheaper one first, one rounding at the end - oracle/pixel_oracle.py:resize_plane_u8): the resize of
+    resize_min_HW / resize_to_chroma (vsslib/vsresize.py:30-127)."""
+
+    def __init__(self, B: int, H: int, W: int, OH: int, OW: int, device, kernel: str = "spline36"):
+        from .engine import _Tables
+        self.lib, self.B, self.H, self.W, self.OH, self.OW = _lib.lib(), B, H, W, OH, OW
+        self.dev = torch.device(device)
+        self.h_first = OW * H <= OH * W                     # size of the intermediate image = cost of the second pass
+        self.t_h, self.t_v = _Tables(W, OW, kernel, self.dev), _Tables(H, OH, kernel, self.dev)
+        shape = (B, 3, H, OW) if self.h_first else (B, 3, OH, W)
+        self.tmp = torch.empty(*shape, dtype=torch.float32, device=self.dev)
+
+    def run(self, src, dst, stream: int = 0):
+        lib, B, H, W, OH, OW, chk = self.lib, self.B, self.H, self.W, self.OH, self.OW, _lib.check
+        th, tv = self.t_h, self.t_v
+        if self.h_first:
+            th.resample_h(lib, src.data_ptr(), self.tmp.data_ptr(), B * 3 * H, stream, "resize.h")
+            chk(lib.havc_resample_v_f32_u8(self.tmp.data_ptr(), dst.data_ptr(), B * 3, H, OH, OW, tv.start.data_ptr(), tv.w.data_ptr(),
+                                           tv.taps, stream), "resize.v")
+        else:
+            chk(lib.havc_resample_v(src.data_ptr(), self.tmp.data_ptr(), B * 3, H, OH, W, tv.start.data_ptr(), tv.w.data_ptr(), tv.taps,
+                                    stream), "resize.v")
+            th.post_horizontal(lib, self.tmp.data_ptr(), None, dst.data_ptr(), B, OH, 0, stream, "resize.h")
+
+
 class FilterBank:
     """Scratch buffers + launch sequencing for one (B, H, W) on one device."""
 
@@ -595,6 +622,75 @@ class TemporalEngine:
 
     def process_sequence(self, frames, n0, weights=None):
         return StabilizerEngine.process_sequence(self, frames, n0, weights)
+
+
+class ResizeEngine:
+    """resize_min_HW and resize_to_chroma (vsslib/vsresize.py:30-127) on batches of planar RGB24 host frames - the
+    `chroma_resize=True` detour HAVC_main takes for every preset but the two slowest (vsdeoldify/__init__.py:492-494, restore_format
+    havc_utils.py:183-184):
+      down(high) : Spline36 to (low_w, low_h)
+      chroma(high, low): Spline36 of `low` back to the size of `high`, both to YUV420P8 (BT.709, full range, no dither), the Y plane
+                  of `high` with the chroma of `low`, RGB24 with error-diffusion dither.
+    zimg is restated (parity unpinned)."""
+
+    def __init__(self, width: int, height: int, low_w: int, low_h: int, batch: int = 8, device: str = "cuda:0"):
+        from . import resample
+        self.dev = torch.device(device)
+        torch.cuda.set_device(self.dev)
+        if height % 2 or width % 2:
+            raise FilterError("resize_to_chroma: the YUV420P8 round trip needs an even frame size")
+        self.B, self.H, self.W, self.h, self.w = batch, height, width, low_h, low_w
+        B, H, W, dev = batch, height, width, self.dev
+        self.same = (low_w, low_h) == (width, height)
+        self.r_down = None if self.same else RectResize(B, H, W, low_h, low_w, dev, "spline36")
+        self.r_up = None if self.same else RectResize(B, low_h, low_w, H, W, dev, "spline36")
+        u8, f32 = dict(dtype=torch.uint8, device=dev), dict(dtype=torch.float32, device=dev)
+        self.d_high, self.d_up, self.d_out = (torch.empty(B, 3, H, W, **u8) for _ in range(3))
+        self.d_low = torch.empty(B, 3, low_h, low_w, **u8)
+        self.h_high, self.h_out = (torch.empty(B, 3, H, W, dtype=torch.uint8).pin_memory() for _ in range(2))
+        self.h_low = torch.empty(B, 3, low_h, low_w, dtype=torch.uint8).pin_memory()
+        up = lambda t: (torch.from_numpy(t[0]).to(dev), torch.from_numpy(np.ascontiguousarray(t[1])).to(dev), int(t[1].shape[1]))
+        self.dh, self.dv, self.uh, self.uv = (up(t) for t in resample.chroma420_tables(W, H))
+        self.y_hi, self.c_hi = torch.empty(B, H, W, **u8), torch.empty(B, 2, H // 2, W // 2, **u8)
+        self.y_lo, self.c_lo = torch.empty(B, H, W, **u8), torch.empty(B, 2, H // 2, W // 2, **u8)
+        self.s444, self.s_half, self.s_rgb = torch.empty(B, 2, H, W, **f32), torch.empty(B, 2, H // 2, W, **f32), torch.empty(B, 3, H, W, **f32)
+        self.stream = torch.cuda.Stream(device=dev)
+
+    def down(self, frames: np.ndarray) -> np.ndarray:
+        n = frames.shape[0]
+        if self.same:
+            return frames
+        self.h_high[:n].copy_(torch.from_numpy(np.ascontiguousarray(frames)))
+        with torch.cuda.stream(self.stream):
+            self.d_high.copy_(self.h_high, non_blocking=True)
+            self.r_down.run(self.d_high, self.d_low, self.stream.cuda_stream)
+            self.h_low.copy_(self.d_low, non_blocking=True)
+        self.stream.synchronize()
+        return self.h_low[:n].numpy().copy()
+
+    def chroma(self, high: np.ndarray, low: np.ndarray) -> np.ndarray:
+        n = high.shape[0]
+        self.h_high[:n].copy_(torch.from_numpy(np.ascontiguousarray(high)))
+        self.h_low[:n].copy_(torch.from_numpy(np.ascontiguousarray(low)))
+        lib, B, H, W, dh, dv, uh, uv, st = _lib.lib(), self.B, self.H, self.W, self.dh, self.dv, self.uh, self.uv, self.stream.cuda_stream
+        with torch.cuda.stream(self.stream):
+            self.d_high.copy_(self.h_high, non_blocking=True)
+            self.d_low.copy_(self.h_low, non_blocking=True)
+            if self.same:
+                colour = self.d_low
+            else:
+                self.r_up.run(self.d_low, self.d_up, st)
+                colour = self.d_up
+            for rgb, y, c in ((self.d_high, self.y_hi, self.c_hi), (colour, self.y_lo, self.c_lo)):
+                _lib.check(lib.havc_zimg_rgb_to_yuv420p8(rgb.data_ptr(), y.data_ptr(), c.data_ptr(), self.s444.data_ptr(), self.s_half.data_ptr(),
+                                                         None, B, H, W, dv[0].data_ptr(), dv[1].data_ptr(), dv[2], dh[0].data_ptr(),
+                                                         dh[1].data_ptr(), dh[2], 0, 0, 0, st), "resize_to_chroma.to_yuv")
+            _lib.check(lib.havc_zimg_yuv420p8_to_rgb(self.y_hi.data_ptr(), self.c_lo.data_ptr(), self.d_out.data_ptr(), self.s_half.data_ptr(),
+                                                     self.s_rgb.data_ptr(), B, H, W, uh[0].data_ptr(), uh[1].data_ptr(), uh[2], uv[0].data_ptr(),
+                                                     uv[1].data_ptr(), uv[2], 0, 0, 1, st), "resize_to_chroma.to_rgb")
+            self.h_out.copy_(self.d_out, non_blocking=True)
+        self.stream.synchronize()
+        return self.h_out[:n].numpy().copy()
 
 
 class MergeEngine:

@@ -591,6 +591,97 @@ def convert_format_RGB24(clip, who: str = "convert_format_RGB24", device_index: 
     return rgb, restore
 
 
+class _BatchedClip:
+    """frame_fn that renders frames in aligned batches of B through `render(first, count) -> list of frames` and caches them."""
+
+    def __init__(self, num_frames: int, B: int, render):
+        self.num_frames, self.B, self.render = num_frames, B, render
+        self.cache: "OrderedDict[int, object]" = OrderedDict()
+        self.lock = threading.Lock()
+
+    def __call__(self, n: int):
+        with self.lock:
+            if n not in self.cache:
+                n0 = (n // self.B) * self.B
+                for i, f in enumerate(self.render(n0, min(self.B, self.num_frames - n0))):
+                    self.cache[n0 + i] = f
+                while len(self.cache) > 4 * self.B:
+                    self.cache.popitem(last=False)
+            return self.cache[n]
+
+
+_SC_COPY_PROPS = ['_SceneChangePrev', '_SceneChangeNext', 'sc_threshold', 'sc_frequency', 'sc_luma', 'sc_ratio']     # vsresize.py:124-125
+
+
+def _min_hw_size(width: int, height: int, min_size=(512, 480)):
+    """Target size of resize_min_HW (vsslib/vsresize.py:30-101), or None when the clip is not resized."""
+    if height < width:
+        if height <= min_size[1]:
+            return None
+        w = round(width * min_size[1] / height)
+        return (w - 1 if w % 2 else w), min_size[1]                                          # resize_to_height, :52-75
+    if width <= min_size[0]:
+        return None
+    h = round(height * min_size[0] / width)
+    return min_size[0], (h + 1 if h % 2 else h)                                              # resize_to_width, :77-99
+
+
+def _stack_planes(frames):
+    return np.stack([np.stack([np.asarray(f[p]) for p in range(3)]) for f in frames])
+
+
+def resize_min_HW(clip, device_index: int = 0):
+    """Drop-in for vsresize.resize_min_HW (vsslib/vsresize.py:30-50) on RGB24 clips: Spline36 to height 480 (landscape) / width
+    512 (portrait) with the aspect ratio kept and even sizes; smaller clips pass through."""
+    size = _min_hw_size(clip.width, clip.height)
+    if size is None:
+        return clip
+    if vs is not vs_shim:
+        return clip.resize.Spline36(width=size[0], height=size[1])
+    from .filters import ResizeEngine
+    eng = ResizeEngine(clip.width, clip.height, size[0], size[1], batch=min(_BATCH, 8), device=f"cuda:{device_index}")
+
+    def render(n0, cnt):
+        src = [clip.get_frame(i) for i in range(n0, n0 + cnt)]
+        out = eng.down(_stack_planes(src))
+        return [vs_shim.VideoFrame([out[j, p] for p in range(3)], vs_shim.RGB24, dict(f.props)) for j, f in enumerate(src)]
+    return vs_shim.VideoNode(clip.num_frames, size[0], size[1], clip.format, _BatchedClip(clip.num_frames, eng.B, render), clip.fps_num, clip.fps_den)
+
+
+def resize_to_chroma(clip_highres, clip_lowres, device_index: int = 0):
+    """Drop-in for vsresize.resize_to_chroma (vsslib/vsresize.py:101-127) on RGB24 clips: `clip_lowres` resized to the size of
+    `clip_highres` with Spline36, both to YUV420P8 (BT.709, full range), the Y plane of `clip_highres` with the chroma of the
+    resized clip, back to RGB24 with error-diffusion dither; the scene-change props come from `clip_lowres`."""
+    if vs is not vs_shim:
+        c = clip_lowres
+        if (clip_highres.width, clip_highres.height) != (c.width, c.height):
+            c = c.resize.Spline36(width=clip_highres.width, height=clip_highres.height)
+        bw = clip_highres.resize.Bicubic(format=vs.YUV420P8, matrix_s="709", range_s="full")
+        col = c.resize.Bicubic(format=vs.YUV420P8, matrix_s="709", range_s="full")
+        yuv = vs.core.std.ShufflePlanes(clips=[bw, col, col], planes=[0, 1, 2], colorfamily=vs.YUV)
+        yuv = yuv.std.CopyFrameProps(prop_src=col, props=_SC_COPY_PROPS)
+        return yuv.resize.Bicubic(format=vs.RGB24, matrix_in_s="709", range_s="full", dither_type="error_diffusion")
+    from .filters import FilterError, ResizeEngine
+    try:
+        eng = ResizeEngine(clip_highres.width, clip_highres.height, clip_lowres.width, clip_lowres.height, batch=min(_BATCH, 8),
+                           device=f"cuda:{device_index}")
+    except FilterError as e:
+        _raise(str(e))
+
+    def render(n0, cnt):
+        hi = [clip_highres.get_frame(i) for i in range(n0, n0 + cnt)]
+        lo = [clip_lowres.get_frame(i) for i in range(n0, n0 + cnt)]
+        out = eng.chroma(_stack_planes(hi), _stack_planes(lo))
+        frames = []
+        for j, (fh, fl) in enumerate(zip(hi, lo)):
+            props = dict(fh.props)
+            props.update({k: fl.props[k] for k in _SC_COPY_PROPS if k in fl.props})
+            frames.append(vs_shim.VideoFrame([out[j, p] for p in range(3)], vs_shim.RGB24, props))
+        return frames
+    return vs_shim.VideoNode(clip_highres.num_frames, clip_highres.width, clip_highres.height, vs_shim.RGB24,
+                             _BatchedClip(clip_highres.num_frames, eng.B, render), clip_highres.fps_num, clip_highres.fps_den)
+
+
 class _TemporalClip:
     """frame_fn of a temporally filtered clip (scope row N3): batches of B consecutive frames go to the engine together with
     their `nh` halo frames on either side, clamped to the clip's ends the way std.AverageFrames clamps its requests
@@ -909,11 +1000,23 @@ def HAVC_main(clip, Preset: str = 'Medium', FrameInterp: int = 0, ColorModel: st
             _raise(f"HAVC_main: {label} post filters are not built (temporal / B&W tuning filters are outside the per-frame path)")
     tune = (ColorTune or "none").lower()
     chroma_adjust = "none" if str(ColorMap).lower() in ("none", "") else _get_colormap(str(ColorMap), tune)   # havc_utils.py:519-548
-    clip_colored = HAVC_colorizer(clip, method=dd_method, mweight=weight, deoldify_p=[do_model, rf, 1.0, 0.0],
+    # :492-494 chroma_resize = speed_id > 1 (every preset built here): the clip is reduced with resize_min_HW (Spline36 to height
+    # 480 / width 512) before the colour models run and the result goes back through resize_to_chroma (luma of the full-size clip,
+    # chroma of the result) inside restore_format (havc_utils.py:183-184).  Real VapourSynth: the reference's order (the reduction
+    # happens in the clip's own format); stand-in: the clip is converted to RGB24 first (the reduction is built for RGB24 only)
+    dev0 = device_index[0] if isinstance(device_index, (list, tuple)) else device_index
+    if vs is vs_shim:
+        high, restore = convert_format_RGB24(clip, "HAVC_main", dev0)
+        low = resize_min_HW(high, dev0)
+    else:
+        high = clip
+        low, restore = convert_format_RGB24(resize_min_HW(clip), "HAVC_main")
+    finish = lambda c: restore(resize_to_chroma(high, c, dev0))
+    clip_colored = HAVC_colorizer(low, method=dd_method, mweight=weight, deoldify_p=[do_model, rf, 1.0, 0.0],
                                   ddcolor_p=[dd_model, rf, 1.0, 0.0, enable_fp16], ddtweak=dd_tweak, ddtweak_p=[DEF_TWEAK_p, hue_range],
                                   device_index=device_index, debug_level=debug_level)
     if speed_id > 4:                     # 'fast', 'faster', 'veryfast': only the colormap (:896-897)
-        return HAVC_stabilizer(clip_colored, colormap=chroma_adjust, device_index=device_index)
+        return finish(HAVC_stabilizer(clip_colored, colormap=chroma_adjust, device_index=dev0))
     stab_enabled = dd_method != 0 and tune != "none"       # :903-906 stab=stab_enabled
     if stab_enabled and getattr(vs.core, "rdfl", None) is None:
         # the preset's temporal stage ends in the external ReduceFlicker plugin (vsplugins.py:263-272); without it the reference
@@ -922,6 +1025,6 @@ def HAVC_main(clip, Preset: str = 'Medium', FrameInterp: int = 0, ColorModel: st
                                                      "temporal chroma stabilizer of this preset (HAVC_stabilizer stab=True) is not "
                                                      "applied, its per-frame stages are")
         stab_enabled = False
-    return HAVC_stabilizer(clip_colored, dark=True, dark_p=[0.2, 0.8], colormap=chroma_adjust, smooth=True,
-                           smooth_p=[0.3, 0.7, 0.9, 0.0, "none"], stab=stab_enabled, stab_p=[5, 'A', 1, 15, 0.2, 0.8],
-                           device_index=device_index)
+    return finish(HAVC_stabilizer(clip_colored, dark=True, dark_p=[0.2, 0.8], colormap=chroma_adjust, smooth=True,
+                                  smooth_p=[0.3, 0.7, 0.9, 0.0, "none"], stab=stab_enabled, stab_p=[5, 'A', 1, 15, 0.2, 0.8],
+                                  device_index=dev0))
