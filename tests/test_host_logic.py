@@ -320,3 +320,57 @@ def test_periodic_resampling_plans_are_bit_identical_to_the_tables():
     for src, dst in [(1920, 256), (1280, 384), (1000, 384)]:
         assert resample.periodic_plan_down(*resample.build_tables(src, dst, "spline64"), src, dst) is None
         assert resample.periodic_plan_up(*resample.build_tables(dst, src, "spline64"), dst, src) is None
+
+
+def test_temporal_clip_adapter_feeds_halo_batches_and_scene_weights():
+    """havc._TemporalClip (scope row N3, host side) with a recording stand-in engine: every request renders the aligned batch
+    that holds the frame, the batch carries nh halo frames on either side clamped to the clip's ends (std.AverageFrames'
+    min(max(n + d, 0), last)), the scene-change props of the window fold the weights per frame, frames come back under their
+    own number with their own props and are cached."""
+    import numpy as np
+    from vsdeoldify_b200 import havc, vs_shim
+    from vsdeoldify_b200.filters import scene_folded_weights, stab_weight_list
+    n, H, W, B, nh = 11, 4, 6, 4, 2
+    frames = np.arange(n * 3 * H * W, dtype=np.uint8).reshape(n, 3, H, W)
+    props = [{"_SceneChangePrev": int(i in (0, 6)), "_SceneChangeNext": int(i == 5), "id": i} for i in range(n)]
+    clip = vs_shim.array_clip(frames, props=props)
+    calls = []
+
+    class Engine:
+        out_B = B
+
+        def __init__(self):
+            self.nh = nh
+            self.temporal = type("T", (), {"wl": stab_weight_list(5, "A")})()
+
+        def process_sequence(self, seq, n0, weights):
+            calls.append((n0, seq[:, 0, 0, 0].copy(), None if weights is None else weights.copy()))
+            return 255 - seq[nh:nh + B]
+    fn = havc._TemporalClip(clip, Engine(), scene_weights=True)
+    f = fn(9)                                                   # last, partial batch [8, 11): halo 6..7 before, clamped to 10 after
+    assert f.props == props[9] and np.array_equal(np.stack([f[p] for p in range(3)]), 255 - frames[9])
+    n0, first_px, w = calls[-1]
+    assert n0 == 8 and list(first_px) == [frames[min(max(i, 0), n - 1), 0, 0, 0] for i in range(6, 14)]
+    wl = stab_weight_list(5, "A")
+    for b in range(B):
+        idx = [min(max(8 + b + d, 0), n - 1) for d in range(-nh, nh + 1)]
+        assert list(w[b]) == scene_folded_weights(wl, [props[i]["_SceneChangePrev"] for i in idx], [props[i]["_SceneChangeNext"] for i in idx])
+    assert fn(10).props == props[10] and len(calls) == 1       # same batch: cached
+    f = fn(1)                                                   # first batch: halo clamped to frame 0
+    assert calls[-1][0] == 0 and list(calls[-1][1][:3]) == [frames[0, 0, 0, 0]] * 3
+    # frame 5 ends a scene (_SceneChangeNext) and frame 6 starts one (_SceneChangePrev): the window of frame 5 keeps nothing beyond it
+    fn(5)
+    w5 = calls[-1][2][1]                                        # batch [4, 8): frame 5 is slot 1
+    assert list(w5[3:]) == [0, 0] and sum(w5) == 100 and w5[2] == wl[2] + wl[3] + wl[4]
+    assert scene_folded_weights([20] * 5, [0, 0, 0, 0, 0], [0, 0, 0, 0, 0]) == [20] * 5
+
+
+def test_resize_min_hw_sizes_follow_the_reference_rules():
+    """havc._min_hw_size (vsslib/vsresize.py:30-99): landscape clips above 480 lines go to height 480 with an even width (odd widths
+    round down), portrait clips above 512 columns go to width 512 with an even height (odd heights round up), others stay."""
+    from vsdeoldify_b200 import havc
+    from oracle import pipeline_oracle
+    cases = {(1920, 1080): (852, 480), (1280, 720): (852, 480), (720, 576): (600, 480), (640, 480): None, (644, 484): (638, 480),
+             (1080, 1920): (512, 910), (600, 800): (512, 684), (500, 900): None, (3840, 2160): (852, 480)}
+    for (w, h), want in cases.items():
+        assert havc._min_hw_size(w, h) == want == pipeline_oracle.min_hw_size(w, h), (w, h)
